@@ -1,0 +1,166 @@
+/*
+ * tnpy_cuda.h -- C ABI of the B200-native finite-DMRG local-update hot path.
+ *
+ * This is the boundary a maintainer of tanlin2013/tnpy would bind (ctypes stub in INTEGRATION.md).
+ * The reference has no FFI of its own -- the path is pure Python on top of quimb / primme /
+ * numpy -- so every entry point names the reference *Python* callable it replaces (file:line under
+ * /root/reference/tnpy).
+ *
+ * Conventions
+ *   - All tensor pointers are DEVICE pointers to C-order (row-major) float64 unless the name ends
+ *     in `_host`.  Nothing here owns memory: the caller (PyTorch on the Python side) allocates
+ *     inputs, outputs and workspaces; the library only borrows them for the duration of the call.
+ *   - Every call takes the CUDA stream to enqueue on (as a `void*` == cudaStream_t) and is
+ *     asynchronous with respect to the host unless documented otherwise.
+ *   - Return value: 0 on success, a negative TNPY_E* code otherwise.  Never throws.
+ *     `tnpy_last_error()` returns a thread-local human-readable message for the last failure.
+ *   - Layouts (reference: matrix_product_state.py:40-45, :411-440):
+ *       site tensor x / A : (l, d, r)          "lpr"
+ *       MPO tensor W      : (wl, wr, d, d)     "lrud"  (u = ket index, d = bra index)
+ *       left env  L       : (l, wl, l)         (ket bond, MPO bond, bra bond)
+ *       right env R       : (r, wr, r)         (ket bond, MPO bond, bra bond)
+ *     Edge sites are expressed with unit bonds: pass l == 1, wl == 1 and L == NULL for site 0
+ *     (r == 1, wr == 1, R == NULL for the last site); NULL stands for the 1x1x1 tensor [1.0].
+ */
+#ifndef TNPY_CUDA_H_
+#define TNPY_CUDA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TNPY_OK 0
+#define TNPY_EINVAL (-1)    /* bad argument (null pointer, non-positive dimension, ...) */
+#define TNPY_EWORKSPACE (-2) /* caller-supplied workspace too small */
+#define TNPY_ECUDA (-3)     /* a CUDA runtime / driver call failed */
+#define TNPY_ENOCONV (-4)   /* iterative routine hit its iteration limit (result still written) */
+
+/* GEMM kernel selection for tnpy_gemm_tn / the contraction chain. */
+#define TNPY_GEMM_AUTO 0    /* TMA+DMMA kernel when shapes/alignments allow, else the generic one */
+#define TNPY_GEMM_GENERIC 1 /* generic shared-memory tiled DFMA kernel (any shape / stride)       */
+#define TNPY_GEMM_DMMA 2    /* force the TMA + mbarrier + FP64 tensor-core (DMMA) kernel           */
+
+/* ---- library ---------------------------------------------------------------------------- */
+int tnpy_version(void);
+const char* tnpy_last_error(void);
+/* Number of kernels this library has launched from the calling process so far (for bench.py's
+ * `gpu_launches`). */
+int64_t tnpy_launch_count(void);
+/* Override the GEMM selection used inside the fused chains (default TNPY_GEMM_AUTO). */
+int tnpy_set_gemm_algo(int algo);
+
+/* Force the DMMA tile configuration (benchmarking): -1 auto, 0 = 128x128, 1 = 128x64, 2 = 64x64. */
+int tnpy_set_gemm_tile(int cfg);
+/* Register-resident FP64 throughput probe (fixes the FP64 roofline denominator on the box):
+ * kind 0 = DMMA m8n8k4 tensor pipe, kind 1 = DFMA.  Synchronous; writes achieved TFLOP/s. */
+int tnpy_probe_fp64(int kind, int threads_per_block, int blocks_per_sm, int ilp, int iters,
+                    double* tflops_host, void* scratch_dev);
+
+/* ---- dense building block ----------------------------------------------------------------
+ * C[m, n] (+)= sum_k A[k, m] * B[k, n]   (C = A^T B, all three row-major, contraction index slow)
+ * A: K x M with row stride lda, B: K x N with row stride ldb, C: M x N with row stride ldc.
+ * This is the shape every big contraction of the path takes once the contracted bond is the
+ * slowest index of both operands; replaces the numpy.tensordot -> dgemm lowering that
+ * quimb/opt_einsum produce for matrix_product_state.py:315, :336, :438.
+ * accumulate != 0 adds into C. */
+int tnpy_gemm_tn(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
+                 int M, int N, int K, int accumulate, int algo, void* stream);
+
+/* ---- a1: Environment.one_site_matvec(site).matvec(x)  (matrix_product_state.py:411-440) ----
+ * y[m,q,s] = sum_{l,a,p,b,r} L[l,a,m] W[a,b,p,q] R[r,b,s] x[l,p,r]
+ * x, y: (l, d, r).  Workspace: tnpy_heff_workspace_bytes(). */
+size_t tnpy_heff_workspace_bytes(int l, int r, int wl, int wr, int d);
+int tnpy_heff_apply(const double* L, const double* W, const double* R, const double* x, double* y,
+                    int l, int r, int wl, int wr, int d, void* workspace, size_t workspace_bytes,
+                    void* stream);
+
+/* ---- a7: Environment.update_left / update_right  (matrix_product_state.py:296-336) ---------
+ * left : Lout[r,b,s] = sum L[l,a,m] A[l,p,r] W[a,b,p,q] A[m,q,s]      Lout: (r, wr, r)
+ * right: Rout[l,a,m] = sum R[r,b,s] A[l,p,r] W[a,b,p,q] A[m,q,s]      Rout: (l, wl, l)
+ * A: (l, d, r).  Workspace: tnpy_env_workspace_bytes(). */
+size_t tnpy_env_workspace_bytes(int l, int r, int wl, int wr, int d);
+int tnpy_env_update_left(const double* L, const double* A, const double* W, double* Lout,
+                         int l, int r, int wl, int wr, int d, void* workspace, size_t workspace_bytes,
+                         void* stream);
+int tnpy_env_update_right(const double* R, const double* A, const double* W, double* Rout,
+                          int l, int r, int wl, int wr, int d, void* workspace, size_t workspace_bytes,
+                          void* stream);
+
+/* ---- a6: Environment.one_site_full_matrix  (matrix_product_state.py:372-409) ---------------
+ * H[(l,p,r),(m,q,s)] dense, N = l*d*r; H is N x N row-major.  Built by applying the matvec
+ * chain to the N unit vectors in one batched pass (rows of a symmetric matrix).
+ * Workspace: tnpy_heff_dense_workspace_bytes(). */
+size_t tnpy_heff_dense_workspace_bytes(int l, int r, int wl, int wr, int d);
+int tnpy_heff_dense(const double* L, const double* W, const double* R, double* H,
+                    int l, int r, int wl, int wr, int d, void* workspace, size_t workspace_bytes,
+                    void* stream);
+
+/* ---- vector kernels used by the on-device eigensolver (replace primme's host BLAS-1/2) -----
+ * Results of reductions are written to DEVICE memory (result pointers are device pointers). */
+int tnpy_dot(const double* x, const double* y, int64_t n, double* result, void* stream);
+int tnpy_nrm2(const double* x, int64_t n, double* result, void* stream);
+/* y += alpha * x   (alpha passed by value) */
+int tnpy_axpy(double alpha, const double* x, double* y, int64_t n, void* stream);
+/* y += (*alpha_dev * alpha_scale) * x   (alpha read from device memory: no host round trip) */
+int tnpy_axpy_dev(const double* alpha_dev, double alpha_scale, const double* x, double* y, int64_t n,
+                  void* stream);
+int tnpy_scal(double alpha, double* x, int64_t n, void* stream);
+/* h[j] = sum_i V[j, i] * w[i], j < m; V is m x n row-major with row stride ldv. */
+int tnpy_multi_dot(const double* V, int64_t ldv, int m, const double* w, int64_t n, double* h,
+                   void* stream);
+/* w[i] -= sum_j h[j] * V[j, i] */
+int tnpy_multi_axpy(const double* V, int64_t ldv, int m, const double* h, double* w, int64_t n,
+                    void* stream);
+
+/* ---- a2: linalg.eigshmv -> primme.eigsh(A, v0, k=1, which="SA", tol)  (linalg.py:64-87) ------
+ * Lowest eigenpair of H_eff(L, W, R) by thick-restart Lanczos with full reorthogonalisation, run
+ * entirely on the device (matvec chain + vector kernels + on-device Ritz solve + convergence flag).
+ * psi: in = start vector v0, out = normalised eigenvector, N = l*d*r doubles.
+ * Stops when ||H x - theta x|| <= tol * max|Ritz| (primme's rule); tol <= 0 means 1e4 * eps.
+ * stats_host (>= 8 doubles, host memory): [0] = theta, [1] = residual norm, [2] = matvec count,
+ * [3] = restart count, [4] = converged (1/0), [5] = max |Ritz value| (the ||A|| estimate).  The call synchronises the stream before returning (one host read-back
+ * per convergence check, never per matvec).
+ * Workspace: tnpy_eig_workspace_bytes(). */
+size_t tnpy_eig_workspace_bytes(int l, int r, int wl, int wr, int d, int ncv);
+int tnpy_eig_lowest(const double* L, const double* W, const double* R, double* psi,
+                    int l, int r, int wl, int wr, int d, double tol, int max_matvec, int ncv,
+                    double* stats_host, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a5: linalg.eigh(matrix)  (linalg.py:42-61), k = 1 --------------------------------------
+ * Lowest eigenpair of a dense symmetric N x N matrix (row-major, destroyed) by cyclic Jacobi
+ * on the device.  evec: N doubles, eval_dev: 1 double (device). */
+size_t tnpy_eigh_workspace_bytes(int n);
+int tnpy_eigh_lowest(double* H, int n, double* eval_dev, double* evec, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
+/* ---- a8: linalg.svd(matrix, cutoff)  (linalg.py:9-23) ---------------------------------------
+ * Thin SVD of a row-major rows x cols matrix A (destroyed): A = U diag(s) Vt with singular values
+ * sorted descending (ties broken by original column index => deterministic).  k = min(rows, cols).
+ * U: rows x k (ldu = k), s: k, Vt: k x cols (ldvt = cols).  One-sided Jacobi (Hestenes) on the
+ * short side after a Householder-free orthogonal reduction; see DESIGN.md.
+ * Workspace: tnpy_svd_workspace_bytes(). */
+size_t tnpy_svd_workspace_bytes(int rows, int cols);
+int tnpy_svd(double* A, int rows, int cols, double* U, double* s, double* Vt, void* workspace,
+             size_t workspace_bytes, void* stream);
+
+/* ---- a9: MatrixProductState.split_tensor neighbour absorb  (matrix_product_state.py:207-223) --
+ * right: out[k, j] = sum_i s[k] * Vt[k, i] * Nb[i, j]      Nb: (k, cols_nb)   (diag(s) Vt . A[site+1])
+ * left : out[i, k] = sum_j Nb[i, j] * U[j, k] * s[k]       Nb: (rows_nb, k)   (A[site-1] . U diag(s)) */
+int tnpy_absorb_right(const double* s, const double* Vt, int k, int n, const double* Nb, int cols_nb,
+                      double* out, void* workspace, size_t workspace_bytes, void* stream);
+int tnpy_absorb_left(const double* U, const double* s, int n, int k, const double* Nb, int rows_nb,
+                     double* out, void* workspace, size_t workspace_bytes, void* stream);
+/* nb = cols_nb (right) or rows_nb (left) */
+size_t tnpy_absorb_workspace_bytes(int k, int n, int nb);
+
+/* ---- layout helper: out[r, p, l] = in[l, p, r]  (mirror of a site tensor, used by the right
+ * environment update so that the contracted bond is the slowest index) */
+int tnpy_mirror_lpr(const double* in, double* out, int l, int d, int r, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TNPY_CUDA_H_ */

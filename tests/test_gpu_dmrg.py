@@ -1,0 +1,120 @@
+"""End-to-end parity of the GPU FiniteDMRG against the CPU oracle and the reference's own anchors."""
+import numpy as np
+import pytest
+
+from oracle import tnpy_oracle as oracle
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def normalised_overlap(a, b):
+    return abs(oracle.mps_overlap(a, b)) / np.sqrt(oracle.mps_overlap(a, a) * oracle.mps_overlap(b, b))
+
+
+def test_reference_anchor_xxz_n10():
+    """tests/test_finite_dmrg.py:22-23 -- fDMRG energy == dense ED, atol 1e-8 (random start)."""
+    from tnpy_b200.finite_dmrg import FiniteDMRG
+    from tnpy_b200.model import XXZ
+
+    model = XXZ(n=10, delta=0.5)
+    e_ed = oracle.exact_ground_energy(model.mpo.arrays)
+    energies = FiniteDMRG(model.mpo, bond_dim=2**5).run(tol=1e-8)
+    np.testing.assert_allclose(energies[-1], e_ed, atol=1e-8)
+
+
+def test_readme_spelling():
+    """README.md:97-101 -- FiniteDMRG(mpo=..., chi=...).update(tol=...)."""
+    from tnpy_b200.finite_dmrg import FiniteDMRG
+    from tnpy_b200.model import XXZ
+
+    model = XXZ(n=8, delta=0.5)
+    fdmrg = FiniteDMRG(mpo=model.mpo, chi=16, seed=0)
+    with pytest.raises(RuntimeError):
+        fdmrg.measurements
+    energies = fdmrg.update(tol=1e-8)
+    np.testing.assert_allclose(energies[-1], oracle.exact_ground_energy(model.mpo.arrays), atol=1e-8)
+    assert abs(fdmrg.measurements.expectation_value(model.mpo) / fdmrg.measurements.expectation_value() - energies[-1]) < 1e-8
+
+
+@pytest.mark.parametrize(
+    "name,n,chi",
+    [("xxz", 10, 32), ("xxz", 16, 24), ("thirring", 12, 20), ("random_heisenberg", 12, 16)],
+)
+def test_parity_with_oracle(name, n, chi):
+    """Same model, chi and initial MPS on both sides (north_star): energy 1e-10 relative,
+    per-bond singular values 1e-9, |<psi_ref|psi_gpu>| > 1 - 1e-8 on normalised states."""
+    from tnpy_b200.finite_dmrg import FiniteDMRG
+    from tnpy_b200.matrix_product_state import MatrixProductState
+    from tnpy_b200 import model as models
+
+    mdl = {
+        "xxz": lambda: models.XXZ(n=n, delta=0.5),
+        "thirring": lambda: models.Thirring(n=n, delta=0.5, ma=1.0, penalty=100.0, s_target=0),
+        "random_heisenberg": lambda: models.RandomHeisenberg(n=n, h=1.0, seed=2022),
+    }[name]()
+    init = oracle.random_mps(n, chi, 2, seed=11)
+    tol = 1e-10
+    ref = oracle.FiniteDMRG(mdl.mpo.arrays, chi, mps=[a.copy() for a in init], exact_local_solver=True)
+    e_ref = ref.run(tol=tol, max_sweep=30)
+    gpu = FiniteDMRG(mdl.mpo, bond_dim=chi, mps=MatrixProductState([a.copy() for a in init]))
+    e_gpu = gpu.run(tol=tol, max_sweep=30)
+    assert abs(e_gpu[-1] - e_ref[-1]) <= 1e-10 * abs(e_ref[-1])
+    assert normalised_overlap(ref.mps, gpu.mps.arrays) > 1 - 1e-8
+    # the un-normalised state carries the reference's (1 + alpha E) factors
+    assert abs(oracle.mps_overlap(gpu.mps.arrays, gpu.mps.arrays) / oracle.mps_overlap(ref.mps, ref.mps) - 1) < 1e-8
+    sv_gpu = gpu.bond_singular_values
+    for bond, s_ref in ref.bond_singular_values.items():
+        assert np.abs(sv_gpu[bond] - s_ref).max() < 1e-9, bond
+    # variance bookkeeping of run() (finite_dmrg.py:248)
+    assert abs(gpu._variances[-1] - ref.variances[-1]) < 1e-8 * max(1.0, abs(e_ref[-1])) ** 2
+
+
+def test_environment_invariants():
+    """Kernel-level pins the reference lacks: canonical identity channels, symmetry of
+    H_eff, <psi|H_eff|psi> == <H>."""
+    from tnpy_b200.matrix_product_state import Environment, MatrixProductState
+    from tnpy_b200.model import XXZ
+
+    n, chi = 12, 16
+    model = XXZ(n=n, delta=0.5)
+    mps = MatrixProductState.random(n, chi, 2, seed=5)
+    env = Environment(model.mpo, mps)
+    for site in (1, 5, n - 2):
+        R = env.right[site].data
+        assert np.abs(R[:, -1, :] - np.eye(R.shape[0])).max() < 1e-12  # right-canonical => identity channel
+    site = 0
+    h = env.one_site_full_matrix(site)
+    assert np.abs(h - h.T).max() < 1e-12
+    x = mps[site].data.reshape(-1)
+    full = oracle.mps_expectation(mps.arrays, model.mpo.arrays)
+    assert abs(x @ h @ x - full) < 1e-12
+    op = env.one_site_matvec(site)
+    y = op.matvec(x)
+    assert np.abs(y - h.T @ x).max() < 1e-12
+    assert abs(env.expectation() - full) < 1e-12
+    assert abs(env.variance() - (oracle.mps_expectation(mps.arrays, oracle.mpo_square(model.mpo.arrays)) - full**2)) < 1e-10
+
+
+def test_split_tensor_invariance():
+    """tests/test_matrix_product_state.py:83-89 -- A[site].A[site+1] is preserved, atol 1e-12."""
+    from tnpy_b200.matrix_product_state import Direction, MatrixProductState
+
+    mps = MatrixProductState.random(n=8, bond_dim=10, phys_dim=2, seed=3)
+    for site in (2, 3, 4, 6):
+        before = np.tensordot(mps.three_leg(site), mps.three_leg(site + 1), axes=(2, 0))
+        mps.split_tensor(site, direction=Direction.RIGHTWARD)
+        after = np.tensordot(mps.three_leg(site), mps.three_leg(site + 1), axes=(2, 0))
+        np.testing.assert_allclose(before, after, atol=1e-12)
+        assert mps[site].tags == {f"I{site}"}
+    with pytest.raises(KeyError):
+        mps.split_tensor(2, direction="sideways")
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from tnpy_b200 import _cuda
+
+    monkeypatch.setattr(_cuda, "_lib", None)
+    monkeypatch.setattr(_cuda, "LIB_PATH", tmp_path / "nope.so")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _cuda.load()

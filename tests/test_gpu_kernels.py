@@ -1,0 +1,280 @@
+"""Parity of every CUDA kernel of the path against the CPU oracle, through the C ABI (-m gpu).
+
+Tolerances: all arithmetic is float64; contraction results are compared at 1e-12 relative to the
+largest entry (summation-order differences only), eigenvalues at 1e-10 relative (north_star),
+singular values at 1e-9 (north_star).
+"""
+import numpy as np
+import pytest
+
+from oracle import tnpy_oracle as oracle
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def dev(x):
+    return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).cuda()
+
+
+def rel_err(got, want):
+    scale = max(np.abs(want).max(), 1e-300)
+    return np.abs(got - want).max() / scale
+
+
+@pytest.fixture(scope="module")
+def cu():
+    from tnpy_b200 import _cuda
+
+    _cuda.load()
+    return _cuda
+
+
+# ------------------------------------------------------------------------------------------ GEMM
+GEMM_SHAPES = [
+    (1, 1, 1), (3, 5, 7), (64, 64, 16), (120, 300, 60), (128, 128, 128), (130, 254, 100),
+    (256, 640, 128), (512, 384, 200), (1024, 1280, 256), (96, 2048, 48),
+]
+
+
+@pytest.mark.parametrize("m,n,k", GEMM_SHAPES)
+@pytest.mark.parametrize("algo", ["generic", "dmma", "auto"])
+def test_gemm_tn(cu, m, n, k, algo):
+    rng = np.random.default_rng(m * 1000003 + n * 1009 + k)
+    a, b = rng.standard_normal((k, m)), rng.standard_normal((k, n))
+    code = {"generic": cu.GEMM_GENERIC, "dmma": cu.GEMM_DMMA, "auto": cu.GEMM_AUTO}[algo]
+    if algo == "dmma" and (m % 2 or n % 2):
+        with pytest.raises(RuntimeError):
+            cu.gemm_tn(dev(a), dev(b), algo=code)
+        return
+    got = cu.gemm_tn(dev(a), dev(b), algo=code).cpu().numpy()
+    want = a.T @ b
+    assert rel_err(got, want) < 1e-13 * max(k, 16)
+
+
+@pytest.mark.parametrize("tile", [0, 1, 2])
+def test_gemm_tn_every_tile_config(cu, tile):
+    rng = np.random.default_rng(tile)
+    m, n, k = 384, 448, 272
+    a, b = rng.standard_normal((k, m)), rng.standard_normal((k, n))
+    cu.load().tnpy_set_gemm_tile(tile)
+    try:
+        got = cu.gemm_tn(dev(a), dev(b), algo=cu.GEMM_DMMA).cpu().numpy()
+        c0 = rng.standard_normal((m, n))
+        acc = cu.gemm_tn(dev(a), dev(b), out=dev(c0), accumulate=True, algo=cu.GEMM_DMMA).cpu().numpy()
+    finally:
+        cu.load().tnpy_set_gemm_tile(-1)
+    assert rel_err(got, a.T @ b) < 1e-12
+    assert rel_err(acc, c0 + a.T @ b) < 1e-12
+
+
+def test_gemm_linearity_large(cu):
+    """Size-independent property at a bench-like shape: (A1 + A2)^T B == A1^T B + A2^T B."""
+    g = torch.Generator(device="cuda").manual_seed(0)
+    k, m, n = 1024, 2048, 2560
+    a1 = torch.randn((k, m), generator=g, dtype=torch.float64, device="cuda")
+    a2 = torch.randn((k, m), generator=g, dtype=torch.float64, device="cuda")
+    b = torch.randn((k, n), generator=g, dtype=torch.float64, device="cuda")
+    lhs = cu.gemm_tn(a1 + a2, b)
+    rhs = cu.gemm_tn(a1, b) + cu.gemm_tn(a2, b)
+    assert float((lhs - rhs).abs().max() / lhs.abs().max()) < 1e-12
+
+
+# ------------------------------------------------------------------------- contraction chains
+def random_operands(rng, l, r, wl, wr, d, sparse_w=True):
+    L = rng.standard_normal((l, wl, l))
+    R = rng.standard_normal((r, wr, r))
+    W = rng.standard_normal((wl, wr, d, d))
+    if sparse_w:
+        W *= rng.random((wl, wr, d, d)) < 0.35
+    x = rng.standard_normal((l, d, r))
+    return L, W, R, x
+
+
+CHAIN_DIMS = [
+    (4, 8, 5, 5, 2), (16, 16, 5, 5, 2), (60, 60, 5, 5, 2), (32, 64, 6, 6, 2), (64, 32, 5, 6, 2),
+    (128, 128, 5, 5, 2), (256, 256, 6, 6, 2), (7, 9, 3, 4, 3), (33, 17, 5, 5, 2), (96, 96, 25, 25, 2),
+]
+
+
+@pytest.mark.parametrize("l,r,wl,wr,d", CHAIN_DIMS)
+def test_heff_apply_bulk(cu, l, r, wl, wr, d):
+    rng = np.random.default_rng(l * 7919 + r)
+    L, W, R, x = random_operands(rng, l, r, wl, wr, d)
+    want = oracle.heff_apply(L, W, R, x)
+    got = cu.heff_apply(dev(L), dev(W), dev(R), dev(x)).cpu().numpy()
+    assert rel_err(got, want) < 1e-12
+
+
+@pytest.mark.parametrize("chi,w,d", [(2, 5, 2), (16, 5, 2), (64, 6, 2), (5, 3, 3)])
+def test_heff_apply_edges(cu, chi, w, d):
+    rng = np.random.default_rng(chi)
+    # site 0: no L, W (w_r, d, d), x (d, r)
+    R = rng.standard_normal((chi, w, chi))
+    W0 = rng.standard_normal((w, d, d))
+    x0 = rng.standard_normal((d, chi))
+    want = oracle.heff_apply(None, W0, R, x0)
+    got = cu.heff_apply(None, dev(W0[None]), dev(R), dev(x0[None])).cpu().numpy()[0]
+    assert rel_err(got, want) < 1e-12
+    # last site: no R, W (w_l, d, d), x (l, d)
+    L = rng.standard_normal((chi, w, chi))
+    x1 = rng.standard_normal((chi, d))
+    want = oracle.heff_apply(L, W0, None, x1)
+    got = cu.heff_apply(dev(L), dev(W0[:, None]), None, dev(x1[:, :, None])).cpu().numpy()[:, :, 0]
+    assert rel_err(got, want) < 1e-12
+
+
+@pytest.mark.parametrize("l,r,wl,wr,d", CHAIN_DIMS)
+def test_env_updates(cu, l, r, wl, wr, d):
+    rng = np.random.default_rng(l * 31 + r * 17 + wl)
+    L, W, R, A = random_operands(rng, l, r, wl, wr, d)
+    got = cu.env_update_left(dev(L), dev(A), dev(W)).cpu().numpy()
+    assert rel_err(got, oracle.env_update_left(L, A, W)) < 1e-12
+    got = cu.env_update_right(dev(R), dev(A), dev(W)).cpu().numpy()
+    assert rel_err(got, oracle.env_update_right(R, A, W)) < 1e-12
+
+
+def test_env_updates_edges(cu):
+    rng = np.random.default_rng(5)
+    d, chi, w = 2, 8, 5
+    A0, W0 = rng.standard_normal((d, chi)), rng.standard_normal((w, d, d))
+    got = cu.env_update_left(None, dev(A0[None]), dev(W0[None])).cpu().numpy()
+    assert rel_err(got, oracle.env_update_left(None, A0, W0)) < 1e-12
+    An = rng.standard_normal((chi, d))
+    got = cu.env_update_right(None, dev(An[:, :, None]), dev(W0[:, None])).cpu().numpy()
+    assert rel_err(got, oracle.env_update_right(None, An, W0)) < 1e-12
+
+
+@pytest.mark.parametrize("l,r,wl,wr,d", [(2, 4, 5, 5, 2), (4, 8, 5, 6, 2), (1, 2, 1, 5, 2), (3, 3, 4, 4, 3)])
+def test_heff_dense(cu, l, r, wl, wr, d):
+    rng = np.random.default_rng(l + 10 * r)
+    L, W, R, _ = random_operands(rng, l, r, wl, wr, d)
+    want = np.einsum("lam,abpq,rbs->lprmqs", L, W, R, optimize=True).reshape(l * d * r, l * d * r)
+    got = cu.heff_dense(dev(L), dev(W), dev(R), l, r).cpu().numpy()
+    assert rel_err(got, want) < 1e-13
+
+
+def test_mirror(cu):
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((37, 3, 50))
+    assert np.array_equal(cu.mirror_lpr(dev(a)).cpu().numpy(), np.transpose(a, (2, 1, 0)))
+
+
+# -------------------------------------------------------------------------------- vector kernels
+@pytest.mark.parametrize("n", [1, 2, 7, 1000, 7200, 131072, 1 << 20, (1 << 20) + 3])
+def test_blas1(cu, n):
+    rng = np.random.default_rng(n)
+    x, y = rng.standard_normal(n), rng.standard_normal(n)
+    assert abs(cu.dot(dev(x), dev(y)).item() - x @ y) <= 1e-13 * (np.abs(x) @ np.abs(y))
+    assert abs(cu.nrm2(dev(x)).item() - np.linalg.norm(x)) <= 1e-13 * np.linalg.norm(x)
+    assert np.allclose(cu.axpy(0.37, dev(x), dev(y)).cpu().numpy(), y + 0.37 * x, rtol=1e-15, atol=1e-15)
+    assert np.allclose(cu.scal(-1.5, dev(x)).cpu().numpy(), -1.5 * x, rtol=1e-15)
+
+
+@pytest.mark.parametrize("n,m", [(7200, 1), (7200, 3), (131072, 9), (100001, 20), (1 << 20, 5)])
+def test_multi_dot_axpy(cu, n, m):
+    rng = np.random.default_rng(n + m)
+    ld = n + (n & 1)
+    V = np.zeros((m, ld))
+    V[:, :n] = rng.standard_normal((m, n))
+    w = rng.standard_normal(n)
+    Vd, wd = dev(V), dev(w)
+    h = cu.multi_dot(Vd, wd).cpu().numpy()
+    want = V[:, :n] @ w
+    assert np.abs(h - want).max() <= 1e-13 * (np.abs(V[:, :n]) @ np.abs(w)).max()
+    out = cu.multi_axpy(Vd, dev(want), wd).cpu().numpy()
+    assert np.allclose(out, w - want @ V[:, :n], rtol=1e-12, atol=1e-12)
+
+
+def test_reductions_are_deterministic(cu):
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(1 << 22, generator=g, dtype=torch.float64, device="cuda")
+    vals = {cu.nrm2(x).item() for _ in range(5)}
+    assert len(vals) == 1
+
+
+# ------------------------------------------------------------------------------------ eigensolver
+def canonical_problem(n_sites, chi, site, seed=0, model="xxz"):
+    mpo = oracle.xxz_mpo(n_sites, 0.5) if model == "xxz" else oracle.thirring_mpo(n_sites, 0.5, 1.0, 100.0, 0)
+    mps = oracle.random_mps(n_sites, chi, 2, seed=seed)
+    env = oracle.Environment(mpo, mps)
+    return env, mpo, mps
+
+
+@pytest.mark.parametrize("n_sites,chi,site,model", [(10, 16, 4, "xxz"), (12, 24, 6, "thirring"), (10, 32, 5, "xxz")])
+def test_eig_lowest_matches_dense(cu, n_sites, chi, site, model):
+    env, mpo, mps = canonical_problem(n_sites, chi, site, model=model)
+    H = env.one_site_full_matrix(site)
+    evals = np.linalg.eigvalsh(0.5 * (H + H.T))
+    psi = dev(mps[site])
+    W = dev(mpo[site])
+    stats = cu.eig_lowest(dev(env.left[site]), W, dev(env.right[site]), psi, tol=1e-10)
+    assert stats["converged"]
+    assert abs(stats["theta"] - evals[0]) <= 1e-10 * max(abs(evals).max(), 1.0)
+    x = psi.cpu().numpy().reshape(-1)
+    assert abs(np.linalg.norm(x) - 1.0) < 1e-12
+    resid = np.linalg.norm(H.T @ x - stats["theta"] * x)
+    assert resid <= 1e-9 * abs(evals).max()
+
+
+def test_eig_lowest_restarts(cu):
+    """A tiny basis forces thick restarts; the answer must not change."""
+    env, mpo, mps = canonical_problem(12, 32, 6, seed=3)
+    site = 6
+    H = env.one_site_full_matrix(site)
+    e0 = np.linalg.eigvalsh(0.5 * (H + H.T))[0]
+    psi = dev(np.random.default_rng(0).standard_normal(mps[site].shape))
+    stats = cu.eig_lowest(dev(env.left[site]), dev(mpo[site]), dev(env.right[site]), psi, tol=1e-10, ncv=6,
+                          max_matvec=2000)
+    assert stats["converged"] and stats["n_restart"] > 0
+    assert abs(stats["theta"] - e0) <= 1e-9 * abs(e0)
+
+
+@pytest.mark.parametrize("n", [4, 16, 64, 100, 199])
+def test_eigh_lowest(cu, n):
+    rng = np.random.default_rng(n)
+    a = rng.standard_normal((n, n))
+    a = a + a.T
+    ev, vec = cu.eigh_lowest(dev(a))
+    w, v = np.linalg.eigh(a)
+    assert abs(ev.item() - w[0]) <= 1e-12 * np.abs(w).max()
+    x = vec.cpu().numpy()
+    assert np.linalg.norm(a @ x - ev.item() * x) <= 1e-10 * np.abs(w).max()
+
+
+# -------------------------------------------------------------------------------------------- SVD
+@pytest.mark.parametrize("rows,cols", [(2, 2), (4, 2), (2, 4), (16, 8), (8, 16), (64, 32), (120, 60), (60, 120),
+                                        (512, 256), (256, 512), (300, 300)])
+def test_svd(cu, rows, cols):
+    rng = np.random.default_rng(rows * 1000 + cols)
+    a = rng.standard_normal((rows, cols)) * np.logspace(0, -6, cols)[None, :]
+    u, s, vt = (t.cpu().numpy() for t in cu.svd(dev(a)))
+    k = min(rows, cols)
+    s_ref = np.linalg.svd(a, compute_uv=False)
+    assert np.all(np.diff(s) <= 0)
+    assert np.abs(s - s_ref).max() <= 1e-12 * s_ref[0]
+    assert np.abs(u @ np.diag(s) @ vt - a).max() <= 1e-12 * s_ref[0]
+    assert np.abs(u.T @ u - np.eye(k)).max() <= 1e-11
+    assert np.abs(vt @ vt.T - np.eye(k)).max() <= 1e-11
+
+
+def test_svd_graded_spectrum(cu):
+    """DMRG wave functions have singular values over 16 decades; small ones must keep absolute 1e-9."""
+    rng = np.random.default_rng(7)
+    q1, _ = np.linalg.qr(rng.standard_normal((128, 64)))
+    q2, _ = np.linalg.qr(rng.standard_normal((64, 64)))
+    s_true = np.logspace(0, -15, 64)
+    a = (q1 * s_true) @ q2.T
+    _, s, _ = cu.svd(dev(a))
+    assert np.abs(s.cpu().numpy() - s_true).max() < 1e-14
+
+
+def test_absorb(cu):
+    rng = np.random.default_rng(3)
+    k, n, cols, rows = 24, 24, 80, 70
+    s, vt, nb = rng.random(k), rng.standard_normal((k, n)), rng.standard_normal((n, cols))
+    got = cu.absorb_right(dev(s), dev(vt), dev(nb)).cpu().numpy()
+    assert rel_err(got, np.diag(s) @ vt @ nb) < 1e-13
+    u, nb2 = rng.standard_normal((n, k)), rng.standard_normal((rows, n))
+    got = cu.absorb_left(dev(u), dev(s), dev(nb2)).cpu().numpy()
+    assert rel_err(got, nb2 @ u @ np.diag(s)) < 1e-13

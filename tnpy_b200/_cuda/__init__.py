@@ -1,0 +1,362 @@
+"""ctypes binding of ``libtnpy_cuda.so`` -- the C ABI declared in ``include/tnpy_cuda.h``.
+
+PyTorch is used for device memory and streams only; every numerical operation of the hot path goes
+through this library.  There is no CPU fallback: if the library is missing or a call fails, a
+``RuntimeError`` is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_char_p, c_double, c_int, c_int64, c_size_t, c_void_p
+from pathlib import Path
+from typing import Optional
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libtnpy_cuda.so"
+
+GEMM_AUTO, GEMM_GENERIC, GEMM_DMMA = 0, 1, 2
+ENOCONV = -4
+
+_PD = c_void_p  # device double*
+
+# name -> (restype, argtypes); mirrors include/tnpy_cuda.h one to one
+SIGNATURES = {
+    "tnpy_version": (c_int, []),
+    "tnpy_last_error": (c_char_p, []),
+    "tnpy_launch_count": (c_int64, []),
+    "tnpy_set_gemm_algo": (c_int, [c_int]),
+    "tnpy_set_gemm_tile": (c_int, [c_int]),
+    "tnpy_probe_fp64": (c_int, [c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_double), c_void_p]),
+    "tnpy_gemm_tn": (c_int, [_PD, c_int64, _PD, c_int64, _PD, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "tnpy_heff_workspace_bytes": (c_size_t, [c_int] * 5),
+    "tnpy_heff_apply": (c_int, [_PD, _PD, _PD, _PD, _PD] + [c_int] * 5 + [c_void_p, c_size_t, c_void_p]),
+    "tnpy_env_workspace_bytes": (c_size_t, [c_int] * 5),
+    "tnpy_env_update_left": (c_int, [_PD, _PD, _PD, _PD] + [c_int] * 5 + [c_void_p, c_size_t, c_void_p]),
+    "tnpy_env_update_right": (c_int, [_PD, _PD, _PD, _PD] + [c_int] * 5 + [c_void_p, c_size_t, c_void_p]),
+    "tnpy_heff_dense_workspace_bytes": (c_size_t, [c_int] * 5),
+    "tnpy_heff_dense": (c_int, [_PD, _PD, _PD, _PD] + [c_int] * 5 + [c_void_p, c_size_t, c_void_p]),
+    "tnpy_dot": (c_int, [_PD, _PD, c_int64, _PD, c_void_p]),
+    "tnpy_nrm2": (c_int, [_PD, c_int64, _PD, c_void_p]),
+    "tnpy_axpy": (c_int, [c_double, _PD, _PD, c_int64, c_void_p]),
+    "tnpy_axpy_dev": (c_int, [_PD, c_double, _PD, _PD, c_int64, c_void_p]),
+    "tnpy_scal": (c_int, [c_double, _PD, c_int64, c_void_p]),
+    "tnpy_multi_dot": (c_int, [_PD, c_int64, c_int, _PD, c_int64, _PD, c_void_p]),
+    "tnpy_multi_axpy": (c_int, [_PD, c_int64, c_int, _PD, _PD, c_int64, c_void_p]),
+    "tnpy_eig_workspace_bytes": (c_size_t, [c_int] * 6),
+    "tnpy_eig_lowest": (
+        c_int,
+        [_PD, _PD, _PD, _PD] + [c_int] * 5 + [c_double, c_int, c_int, ctypes.POINTER(c_double), c_void_p, c_size_t, c_void_p],
+    ),
+    "tnpy_eigh_workspace_bytes": (c_size_t, [c_int]),
+    "tnpy_eigh_lowest": (c_int, [_PD, c_int, _PD, _PD, c_void_p, c_size_t, c_void_p]),
+    "tnpy_svd_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "tnpy_svd": (c_int, [_PD, c_int, c_int, _PD, _PD, _PD, c_void_p, c_size_t, c_void_p]),
+    "tnpy_absorb_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "tnpy_absorb_right": (c_int, [_PD, _PD, c_int, c_int, _PD, c_int, _PD, c_void_p, c_size_t, c_void_p]),
+    "tnpy_absorb_left": (c_int, [_PD, _PD, c_int, c_int, _PD, c_int, _PD, c_void_p, c_size_t, c_void_p]),
+    "tnpy_mirror_lpr": (c_int, [_PD, _PD, c_int, c_int, c_int, c_void_p]),
+}
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+def load() -> ctypes.CDLL:
+    """Load the shared library (once) and attach the prototypes.  Fails loudly if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RuntimeError(
+            f"{LIB_PATH} not found: the CUDA library has not been built. "
+            "Run `python -m tnpy_b200._cuda.build` (needs nvcc); there is no CPU fallback."
+        )
+    lib = ctypes.CDLL(str(LIB_PATH))
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError => header and library out of sync
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().tnpy_last_error().decode()
+
+
+def check(rc: int, what: str, allow_noconv: bool = False) -> int:
+    if rc == 0 or (allow_noconv and rc == ENOCONV):
+        return rc
+    raise RuntimeError(f"{what} failed (code {rc}): {last_error()}")
+
+
+def launch_count() -> int:
+    return int(load().tnpy_launch_count())
+
+
+def set_gemm_algo(algo: int) -> None:
+    check(load().tnpy_set_gemm_algo(algo), "tnpy_set_gemm_algo")
+
+
+# ------------------------------------------------------------------------------------------------
+# torch-facing helpers (device memory + stream plumbing only)
+# ------------------------------------------------------------------------------------------------
+def _ptr(t) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*tensors) -> None:
+    import torch
+
+    for t in tensors:
+        if t is None:
+            continue
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()):
+            raise RuntimeError(
+                "tnpy_b200 kernels need contiguous float64 CUDA tensors "
+                f"(got {type(t).__name__} {getattr(t, 'dtype', None)} on {getattr(t, 'device', None)}); no CPU fallback exists"
+            )
+
+
+class Scratch:
+    """Grow-only device workspace owned by the Python side and lent to the library per call."""
+
+    def __init__(self):
+        self._buf = None
+
+    def get(self, nbytes: int):
+        import torch
+
+        if self._buf is None or self._buf.numel() < nbytes:
+            self._buf = None
+            self._buf = torch.empty(int(nbytes), dtype=torch.uint8, device="cuda")
+        return self._buf
+
+
+_scratch = Scratch()
+
+
+def gemm_tn(a, b, out=None, accumulate: bool = False, algo: int = GEMM_AUTO):
+    """out[m, n] (+)= sum_k a[k, m] * b[k, n]; a: (K, M), b: (K, N)."""
+    import torch
+
+    _need_cuda(a, b, out)
+    k, m = a.shape
+    k2, n = b.shape
+    assert k == k2
+    if out is None:
+        out = torch.empty((m, n), dtype=torch.float64, device=a.device)
+    rc = load().tnpy_gemm_tn(_ptr(a), a.stride(0), _ptr(b), b.stride(0), _ptr(out), out.stride(0), m, n, k,
+                             int(accumulate), algo, _stream())
+    check(rc, "tnpy_gemm_tn")
+    return out
+
+
+def _dims(x_shape, w_shape):
+    l, d, r = x_shape
+    wl, wr = w_shape[0], w_shape[1]
+    return l, r, wl, wr, d
+
+
+def heff_apply(L, W, R, x, out=None):
+    """y = H_eff x with x (l, d, r), W (wl, wr, d, d), L (l, wl, l) or None, R (r, wr, r) or None."""
+    import torch
+
+    _need_cuda(L, W, R, x, out)
+    l, r, wl, wr, d = _dims(x.shape, W.shape)
+    if out is None:
+        out = torch.empty_like(x)
+    lib = load()
+    nbytes = lib.tnpy_heff_workspace_bytes(l, r, wl, wr, d)
+    ws = _scratch.get(nbytes)
+    rc = lib.tnpy_heff_apply(_ptr(L), _ptr(W), _ptr(R), _ptr(x), _ptr(out), l, r, wl, wr, d, _ptr(ws), nbytes, _stream())
+    check(rc, "tnpy_heff_apply")
+    return out
+
+
+def env_update_left(L, A, W, out=None):
+    import torch
+
+    _need_cuda(L, A, W, out)
+    l, r, wl, wr, d = _dims(A.shape, W.shape)
+    if out is None:
+        out = torch.empty((r, wr, r), dtype=torch.float64, device=A.device)
+    lib = load()
+    nbytes = lib.tnpy_env_workspace_bytes(l, r, wl, wr, d)
+    ws = _scratch.get(nbytes)
+    rc = lib.tnpy_env_update_left(_ptr(L), _ptr(A), _ptr(W), _ptr(out), l, r, wl, wr, d, _ptr(ws), nbytes, _stream())
+    check(rc, "tnpy_env_update_left")
+    return out
+
+
+def env_update_right(R, A, W, out=None):
+    import torch
+
+    _need_cuda(R, A, W, out)
+    l, r, wl, wr, d = _dims(A.shape, W.shape)
+    if out is None:
+        out = torch.empty((l, wl, l), dtype=torch.float64, device=A.device)
+    lib = load()
+    nbytes = lib.tnpy_env_workspace_bytes(l, r, wl, wr, d)
+    ws = _scratch.get(nbytes)
+    rc = lib.tnpy_env_update_right(_ptr(R), _ptr(A), _ptr(W), _ptr(out), l, r, wl, wr, d, _ptr(ws), nbytes, _stream())
+    check(rc, "tnpy_env_update_right")
+    return out
+
+
+def heff_dense(L, W, R, l, r):
+    import torch
+
+    _need_cuda(L, W, R)
+    wl, wr, d = W.shape[0], W.shape[1], W.shape[2]
+    n = l * d * r
+    out = torch.empty((n, n), dtype=torch.float64, device=W.device)
+    rc = load().tnpy_heff_dense(_ptr(L), _ptr(W), _ptr(R), _ptr(out), l, r, wl, wr, d, None, 0, _stream())
+    check(rc, "tnpy_heff_dense")
+    return out
+
+
+def eig_lowest(L, W, R, psi, tol: float = 1e-8, max_matvec: int = 1000, ncv: int = 0):
+    """In-place: psi (l, d, r) holds v0 on entry and the eigenvector on return.
+    Returns dict(theta, resid, n_matvec, n_restart, converged, anorm)."""
+    _need_cuda(L, W, R, psi)
+    l, r, wl, wr, d = _dims(psi.shape, W.shape)
+    lib = load()
+    nbytes = lib.tnpy_eig_workspace_bytes(l, r, wl, wr, d, ncv)
+    ws = _scratch.get(nbytes)
+    stats = (c_double * 8)()
+    rc = lib.tnpy_eig_lowest(_ptr(L), _ptr(W), _ptr(R), _ptr(psi), l, r, wl, wr, d, float(tol), int(max_matvec),
+                             int(ncv), stats, _ptr(ws), nbytes, _stream())
+    check(rc, "tnpy_eig_lowest", allow_noconv=True)
+    return {
+        "theta": stats[0], "resid": stats[1], "n_matvec": int(stats[2]), "n_restart": int(stats[3]),
+        "converged": bool(stats[4]), "anorm": stats[5],
+    }
+
+
+def eigh_lowest(H):
+    """Lowest eigenpair of a dense symmetric matrix (destroyed).  Returns (eval 0-d tensor, evec)."""
+    import torch
+
+    _need_cuda(H)
+    n = H.shape[0]
+    lib = load()
+    nbytes = lib.tnpy_eigh_workspace_bytes(n)
+    ws = _scratch.get(nbytes)
+    ev = torch.empty((), dtype=torch.float64, device=H.device)
+    vec = torch.empty(n, dtype=torch.float64, device=H.device)
+    rc = lib.tnpy_eigh_lowest(_ptr(H), n, _ptr(ev), _ptr(vec), _ptr(ws), nbytes, _stream())
+    check(rc, "tnpy_eigh_lowest")
+    return ev, vec
+
+
+def svd(A):
+    """Thin SVD of a 2-D tensor (destroyed).  Returns (U, s, Vt), s descending."""
+    import torch
+
+    _need_cuda(A)
+    rows, cols = A.shape
+    k = min(rows, cols)
+    U = torch.empty((rows, k), dtype=torch.float64, device=A.device)
+    s = torch.empty(k, dtype=torch.float64, device=A.device)
+    Vt = torch.empty((k, cols), dtype=torch.float64, device=A.device)
+    lib = load()
+    nbytes = lib.tnpy_svd_workspace_bytes(rows, cols)
+    ws = _scratch.get(nbytes)
+    rc = lib.tnpy_svd(_ptr(A), rows, cols, _ptr(U), _ptr(s), _ptr(Vt), _ptr(ws), nbytes, _stream())
+    check(rc, "tnpy_svd")
+    return U, s, Vt
+
+
+def absorb_right(s, Vt, nb):
+    """diag(s) Vt @ nb  with nb (n, cols)."""
+    import torch
+
+    _need_cuda(s, Vt, nb)
+    k, n = Vt.shape
+    cols = nb.shape[1]
+    out = torch.empty((k, cols), dtype=torch.float64, device=nb.device)
+    lib = load()
+    nbytes = lib.tnpy_absorb_workspace_bytes(k, n, cols)
+    ws = _scratch.get(nbytes)
+    rc = lib.tnpy_absorb_right(_ptr(s), _ptr(Vt), k, n, _ptr(nb), cols, _ptr(out), _ptr(ws), nbytes, _stream())
+    check(rc, "tnpy_absorb_right")
+    return out
+
+
+def absorb_left(U, s, nb):
+    """nb @ U diag(s)  with nb (rows, n)."""
+    import torch
+
+    _need_cuda(U, s, nb)
+    n, k = U.shape
+    rows = nb.shape[0]
+    out = torch.empty((rows, k), dtype=torch.float64, device=nb.device)
+    lib = load()
+    nbytes = lib.tnpy_absorb_workspace_bytes(k, n, rows)
+    ws = _scratch.get(nbytes)
+    rc = lib.tnpy_absorb_left(_ptr(U), _ptr(s), n, k, _ptr(nb), rows, _ptr(out), _ptr(ws), nbytes, _stream())
+    check(rc, "tnpy_absorb_left")
+    return out
+
+
+def mirror_lpr(a):
+    import torch
+
+    _need_cuda(a)
+    l, d, r = a.shape
+    out = torch.empty((r, d, l), dtype=torch.float64, device=a.device)
+    check(load().tnpy_mirror_lpr(_ptr(a), _ptr(out), l, d, r, _stream()), "tnpy_mirror_lpr")
+    return out
+
+
+def dot(x, y):
+    import torch
+
+    _need_cuda(x, y)
+    out = torch.empty((), dtype=torch.float64, device=x.device)
+    check(load().tnpy_dot(_ptr(x), _ptr(y), x.numel(), _ptr(out), _stream()), "tnpy_dot")
+    return out
+
+
+def nrm2(x):
+    import torch
+
+    _need_cuda(x)
+    out = torch.empty((), dtype=torch.float64, device=x.device)
+    check(load().tnpy_nrm2(_ptr(x), x.numel(), _ptr(out), _stream()), "tnpy_nrm2")
+    return out
+
+
+def axpy(alpha: float, x, y):
+    _need_cuda(x, y)
+    check(load().tnpy_axpy(float(alpha), _ptr(x), _ptr(y), x.numel(), _stream()), "tnpy_axpy")
+    return y
+
+
+def scal(alpha: float, x):
+    _need_cuda(x)
+    check(load().tnpy_scal(float(alpha), _ptr(x), x.numel(), _stream()), "tnpy_scal")
+    return x
+
+
+def multi_dot(V, w, m: Optional[int] = None):
+    import torch
+
+    _need_cuda(V, w)
+    m = V.shape[0] if m is None else m
+    out = torch.empty(m, dtype=torch.float64, device=w.device)
+    check(load().tnpy_multi_dot(_ptr(V), V.stride(0), m, _ptr(w), w.numel(), _ptr(out), _stream()), "tnpy_multi_dot")
+    return out
+
+
+def multi_axpy(V, h, w, m: Optional[int] = None):
+    _need_cuda(V, h, w)
+    m = V.shape[0] if m is None else m
+    check(load().tnpy_multi_axpy(_ptr(V), V.stride(0), m, _ptr(h), _ptr(w), w.numel(), _stream()), "tnpy_multi_axpy")
+    return w

@@ -1,0 +1,78 @@
+"""Build the sm_100a CUDA library in-tree with nvcc (no JIT cache: the .so must travel with the repo).
+
+    python -m tnpy_b200._cuda.build [--force]
+
+Output: tnpy_b200/_cuda/libtnpy_cuda.so
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+CSRC = HERE.parent / "csrc"
+INCLUDE = HERE.parent.parent / "include"
+LIB = HERE / "libtnpy_cuda.so"
+OBJ_DIR = HERE / "build"
+SOURCES = ["lib.cu", "gemm_tn.cu", "contract.cu", "blas1.cu", "lanczos.cu", "svd.cu", "probe.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC",
+    "-Xptxas", "-v",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and Path(cand).exists():
+            return cand
+    raise RuntimeError("nvcc not found; cannot build tnpy_b200's CUDA library")
+
+
+def _digest() -> str:
+    h = hashlib.sha256()
+    for path in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(INCLUDE.glob("*.h"))):
+        h.update(path.name.encode())
+        h.update(path.read_bytes())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    stamp = OBJ_DIR / "stamp.txt"
+    digest = _digest()
+    if not force and LIB.exists() and stamp.exists() and stamp.read_text() == digest:
+        return LIB
+    nvcc = _nvcc()
+    OBJ_DIR.mkdir(exist_ok=True)
+
+    def compile_one(src: str) -> str:
+        obj = OBJ_DIR / (src + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, "-I", str(INCLUDE), "-c", str(CSRC / src), "-o", str(obj)]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        (OBJ_DIR / (src + ".log")).write_text(res.stdout + res.stderr)
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{res.stdout}\n{res.stderr}")
+        if verbose:
+            print(res.stderr)
+        return str(obj)
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+        objs = list(pool.map(compile_one, SOURCES))
+    link = [nvcc, "-shared", "-o", str(LIB), *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+    res = subprocess.run(link, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
+    stamp.write_text(digest)
+    return LIB
+
+
+if __name__ == "__main__":
+    out = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print(out)

@@ -1,0 +1,307 @@
+// On-device lowest-eigenpair solver for H_eff (replaces primme.eigsh behind linalg.eigshmv,
+// reference linalg.py:64-87, called from finite_dmrg.py:111).
+//
+// Thick-restart Lanczos with full (twice-applied classical Gram-Schmidt) reorthogonalisation and an
+// explicitly projected matrix T = V^T H V.  Everything -- the matvec chain, the vector kernels,
+// the Rayleigh-Ritz solve (parallel cyclic Jacobi on T in one CTA) and the convergence test -- runs
+// on the device; the host only reads one 5-double status record per Lanczos step to decide whether to
+// stop or restart.  Basis vectors never leave HBM.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace tnpy {
+
+int heff_apply(const double* L, const double* W, const double* R, const double* x, double* y, int l, int r, int wl,
+               int wr, int d, Workspace& ws, cudaStream_t stream);
+int multi_dot(const double* V, int64_t ldv, int m, const double* w, int64_t n, double* h, int mode,
+              cudaStream_t stream);
+int multi_axpy(const double* V, int64_t ldv, int m, const double* h, double* w, int64_t n, double* nrm_out,
+               cudaStream_t stream);
+int scale_copy(const double* x, double* out, int64_t n, double alpha, const double* s_dev, int inv,
+               cudaStream_t stream);
+int combine(const double* V, int64_t ldv, int m, const double* c, int64_t ldc_, int nout, double* out, int64_t ldo,
+            int64_t n, cudaStream_t stream);
+
+constexpr int kMaxNcv = 48;
+
+// status record (device and pinned host mirror)
+enum { ST_THETA = 0, ST_RESID = 1, ST_ANORM = 2, ST_DONE = 3, ST_BETA = 4, ST_SIZE = 8 };
+
+// Symmetric eigen-decomposition of the m x m matrix held in shared memory `a` (leading dim kMaxNcv)
+// by parallel cyclic Jacobi (round-robin pair ordering).  Eigenvectors accumulate in `z` (columns).
+__device__ void jacobi_eig_smem(double (*a)[kMaxNcv], double (*z)[kMaxNcv], int m, double* cs, double* sn, int* pp,
+                                int* qq, double* red) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int idx = tid; idx < m * m; idx += nt) z[idx / m][idx % m] = (idx / m == idx % m) ? 1.0 : 0.0;
+  __syncthreads();
+  if (m == 1) return;
+  const int me = (m + 1) & ~1;  // even player count (last one may be a bye)
+  const int half = me / 2;
+  for (int sweep = 0; sweep < 40; ++sweep) {
+    // convergence: off-diagonal mass vs diagonal mass
+    double off = 0.0, dia = 0.0;
+    for (int idx = tid; idx < m * m; idx += nt) {
+      const int i = idx / m, j = idx % m;
+      const double v = a[i][j];
+      if (i == j) dia += v * v; else off += v * v;
+    }
+    off = warp_sum(off);
+    dia = warp_sum(dia);
+    if ((tid & 31) == 0) { red[tid >> 5] = off; red[32 + (tid >> 5)] = dia; }
+    __syncthreads();
+    if (tid == 0) {
+      double o = 0.0, d2 = 0.0;
+      for (int w = 0; w < (nt >> 5); ++w) { o += red[w]; d2 += red[32 + w]; }
+      red[64] = (o <= 1e-31 * d2 || o == 0.0) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    const bool converged = red[64] != 0.0;
+    __syncthreads();
+    if (converged) break;
+    for (int round = 0; round < me - 1; ++round) {
+      // round-robin tournament: player me-1 fixed, the others rotate
+      if (tid < half) {
+        int p = (tid == 0) ? me - 1 : (round + tid) % (me - 1);
+        int q = (round + me - 1 - tid) % (me - 1);
+        if (p > q) { const int t = p; p = q; q = t; }
+        double c = 1.0, s = 0.0;
+        if (q < m) {
+          const double apq = a[p][q];
+          if (apq != 0.0) {
+            const double app = a[p][p], aqq = a[q][q];
+            if (fabs(apq) > 1e-300 && fabs(apq) >= 2.3e-16 * 1e-3 * sqrt(fabs(app * aqq)) ) {
+              const double tau = (aqq - app) / (2.0 * apq);
+              const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+              c = 1.0 / sqrt(1.0 + t * t);
+              s = t * c;
+            }
+          }
+        }
+        cs[tid] = c; sn[tid] = s; pp[tid] = p; qq[tid] = q;
+      }
+      __syncthreads();
+      // column rotations: A <- A J, Z <- Z J
+      for (int idx = tid; idx < half * m; idx += nt) {
+        const int i = idx / m, k = idx % m;
+        const int p = pp[i], q = qq[i];
+        if (q >= m || sn[i] == 0.0) continue;
+        const double c = cs[i], s = sn[i];
+        const double akp = a[k][p], akq = a[k][q];
+        a[k][p] = c * akp - s * akq;
+        a[k][q] = s * akp + c * akq;
+        const double zkp = z[k][p], zkq = z[k][q];
+        z[k][p] = c * zkp - s * zkq;
+        z[k][q] = s * zkp + c * zkq;
+      }
+      __syncthreads();
+      // row rotations: A <- J^T A
+      for (int idx = tid; idx < half * m; idx += nt) {
+        const int i = idx / m, k = idx % m;
+        const int p = pp[i], q = qq[i];
+        if (q >= m || sn[i] == 0.0) continue;
+        const double c = cs[i], s = sn[i];
+        const double apk = a[p][k], aqk = a[q][k];
+        a[p][k] = c * apk - s * aqk;
+        a[q][k] = s * apk + c * aqk;
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// After Lanczos step j: fold h (+ h2) into column j of T, solve the (j+1) x (j+1) Ritz problem, write
+// status, the sorted Ritz values `thetas` and the sorted Ritz coefficient matrix S (column i = i-th lowest).
+__global__ void __launch_bounds__(256) ritz_kernel(double* __restrict__ T, const double* __restrict__ h,
+                                                   const double* __restrict__ h2, const double* __restrict__ beta_dev,
+                                                   int j, double tol, double* __restrict__ S,
+                                                   double* __restrict__ thetas, double* __restrict__ status) {
+  __shared__ double a[kMaxNcv][kMaxNcv];
+  __shared__ double z[kMaxNcv][kMaxNcv];
+  __shared__ double cs[kMaxNcv], sn[kMaxNcv], red[72];
+  __shared__ int pp[kMaxNcv], qq[kMaxNcv], order[kMaxNcv];
+  const int m = j + 1;
+  const int tid = threadIdx.x;
+  if (tid < m) {
+    const double v = h[tid] + (h2 ? h2[tid] : 0.0);
+    T[tid * kMaxNcv + j] = v;
+    T[j * kMaxNcv + tid] = v;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < m * m; idx += blockDim.x) a[idx / m][idx % m] = T[(idx / m) * kMaxNcv + idx % m];
+  __syncthreads();
+  jacobi_eig_smem(a, z, m, cs, sn, pp, qq, red);
+  if (tid == 0) {
+    // sort eigenvalues ascending (stable selection; m <= 48)
+    for (int i = 0; i < m; ++i) order[i] = i;
+    for (int i = 0; i < m; ++i) {
+      int best = i;
+      for (int k = i + 1; k < m; ++k)
+        if (a[order[k]][order[k]] < a[order[best]][order[best]]) best = k;
+      const int t = order[i]; order[i] = order[best]; order[best] = t;
+    }
+    double anorm = 0.0;
+    for (int i = 0; i < m; ++i) anorm = fmax(anorm, fabs(a[i][i]));
+    const int lo = order[0];
+    const double beta = *beta_dev;
+    const double resid = fabs(beta * z[m - 1][lo]);
+    status[ST_THETA] = a[lo][lo];
+    status[ST_RESID] = resid;
+    status[ST_ANORM] = anorm;
+    status[ST_BETA] = beta;
+    status[ST_DONE] = (resid <= tol * anorm) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < m * m; idx += blockDim.x) {
+    const int k = idx / m, i = idx % m;
+    const int col = order[i];
+    // fix the sign of every Ritz vector so that its first basis component is non-negative
+    const double sgn = z[0][col] < 0.0 ? -1.0 : 1.0;
+    S[k * kMaxNcv + i] = sgn * z[k][col];
+  }
+  if (tid < m) thetas[tid] = a[order[tid]][order[tid]];
+}
+
+__global__ void restart_T_kernel(double* __restrict__ T, const double* __restrict__ thetas, int keep) {
+  for (int idx = threadIdx.x; idx < kMaxNcv * kMaxNcv; idx += blockDim.x) {
+    const int i = idx / kMaxNcv, k = idx % kMaxNcv;
+    T[idx] = (i == k && i < keep) ? thetas[i] : 0.0;
+  }
+}
+
+struct PinnedStatus {
+  double* host = nullptr;
+  PinnedStatus() { cudaMallocHost(&host, sizeof(double) * ST_SIZE); }
+};
+static double* pinned_status() {
+  static PinnedStatus p;
+  return p.host;
+}
+
+static size_t eig_ws_layout(int64_t n, int ncv, int keep, size_t chain) {
+  const int64_t ldv = n + (n & 1);
+  size_t total = 0;
+  total += Workspace::need((size_t)(ncv + 1) * ldv);  // V
+  total += Workspace::need((size_t)keep * ldv);       // Y
+  total += Workspace::need(kMaxNcv * kMaxNcv) * 2;    // T, S
+  total += Workspace::need(64) * 4;                   // thetas, h, h2, status
+  total += chain + 512;
+  return total;
+}
+
+static void pick_sizes(int64_t n, int ncv_in, int& ncv, int& keep) {
+  ncv = ncv_in <= 0 ? 20 : ncv_in;
+  if (ncv > kMaxNcv) ncv = kMaxNcv;
+  if (ncv < 3) ncv = 3;
+  if (ncv > n) ncv = (int)n;
+  keep = ncv / 3;
+  if (keep < 1) keep = 1;
+  if (keep > 8) keep = 8;
+}
+
+}  // namespace tnpy
+
+using namespace tnpy;
+
+extern "C" size_t tnpy_eig_workspace_bytes(int l, int r, int wl, int wr, int d, int ncv_in) {
+  int ncv, keep;
+  const int64_t n = (int64_t)l * d * r;
+  pick_sizes(n, ncv_in, ncv, keep);
+  return eig_ws_layout(n, ncv, keep, tnpy_heff_workspace_bytes(l, r, wl, wr, d));
+}
+
+extern "C" int tnpy_eig_lowest(const double* L, const double* W, const double* R, double* psi, int l, int r, int wl,
+                               int wr, int d, double tol, int max_matvec, int ncv_in, double* stats_host,
+                               void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TNPY_CHECK_ARG(psi && W, "null pointer");
+  TNPY_CHECK_ARG(l > 0 && r > 0 && wl > 0 && wr > 0 && d > 0, "non-positive dimension");
+  const int64_t n = (int64_t)l * d * r;
+  const int64_t ldv = n + (n & 1);
+  int ncv, keep;
+  pick_sizes(n, ncv_in, ncv, keep);
+  if (tol <= 0.0) tol = 2.220446049250313e-16 * 1e4;
+  if (max_matvec <= 0) max_matvec = 1000;
+
+  Workspace ws(workspace, workspace_bytes);
+  double* V = ws.take<double>((size_t)(ncv + 1) * ldv);
+  double* Y = ws.take<double>((size_t)keep * ldv);
+  double* T = ws.take<double>(kMaxNcv * kMaxNcv);
+  double* S = ws.take<double>(kMaxNcv * kMaxNcv);
+  double* thetas = ws.take<double>(64);
+  double* h = ws.take<double>(64);
+  double* h2 = ws.take<double>(64);
+  double* status = ws.take<double>(64);
+  if (!V || !Y || !T || !S || !thetas || !h || !h2 || !status) {
+    set_error("tnpy_eig_lowest: workspace too small (%zu bytes given)", workspace_bytes);
+    return TNPY_EWORKSPACE;
+  }
+  const size_t chain_off = ws.used;
+  double* hst = pinned_status();
+  if (!hst) {
+    set_error("tnpy_eig_lowest: pinned status allocation failed");
+    return TNPY_ECUDA;
+  }
+
+  // V[0] = v0 / ||v0||
+  TNPY_TRY(multi_dot(psi, ldv, 1, psi, n, status + ST_BETA, 1, stream));
+  TNPY_TRY(scale_copy(psi, V, n, 1.0, status + ST_BETA, 1, stream));
+  TNPY_CUDA_OK(cudaMemsetAsync(T, 0, sizeof(double) * kMaxNcv * kMaxNcv, stream));
+
+  int j = 0, n_matvec = 0, n_restart = 0;
+  bool done = false;
+  while (true) {
+    double* vj = V + (int64_t)j * ldv;
+    double* w = V + (int64_t)(j + 1) * ldv;
+    Workspace chain(static_cast<char*>(workspace) + chain_off, workspace_bytes - chain_off);
+    TNPY_TRY(heff_apply(L, W, R, vj, w, l, r, wl, wr, d, chain, stream));
+    ++n_matvec;
+    // classical Gram-Schmidt against the whole basis, applied twice; the first-pass coefficients are
+    // column j of T = V^T H V, the second pass adds the rounding-level correction.
+    TNPY_TRY(multi_dot(V, ldv, j + 1, w, n, h, 0, stream));
+    TNPY_TRY(multi_axpy(V, ldv, j + 1, h, w, n, nullptr, stream));
+    TNPY_TRY(multi_dot(V, ldv, j + 1, w, n, h2, 0, stream));
+    TNPY_TRY(multi_axpy(V, ldv, j + 1, h2, w, n, status + ST_BETA, stream));
+    ritz_kernel<<<1, 256, 0, stream>>>(T, h, h2, status + ST_BETA, j, tol, S, thetas, status);
+    TNPY_LAUNCH_OK();
+    TNPY_TRY(scale_copy(w, w, n, 1.0, status + ST_BETA, 1, stream));
+    TNPY_CUDA_OK(cudaMemcpyAsync(hst, status, sizeof(double) * ST_SIZE, cudaMemcpyDeviceToHost, stream));
+    TNPY_CUDA_OK(cudaStreamSynchronize(stream));
+    const int m = j + 1;
+    done = hst[ST_DONE] != 0.0 || !(hst[ST_BETA] > 0.0) || m >= n;
+    if (done || n_matvec >= max_matvec) {
+      // psi = V[0..m-1] . S[:, 0]
+      TNPY_TRY(combine(V, ldv, m, S, kMaxNcv, 1, psi, ldv, n, stream));
+      break;
+    }
+    if (m == ncv) {
+      // thick restart: keep the `keep` lowest Ritz vectors plus the residual direction V[m]
+      const int k = keep < m ? keep : m;
+      TNPY_TRY(combine(V, ldv, m, S, kMaxNcv, k, Y, ldv, n, stream));
+      TNPY_CUDA_OK(cudaMemcpyAsync(V + (int64_t)k * ldv, V + (int64_t)m * ldv, sizeof(double) * n,
+                                   cudaMemcpyDeviceToDevice, stream));
+      TNPY_CUDA_OK(cudaMemcpyAsync(V, Y, sizeof(double) * (size_t)k * ldv, cudaMemcpyDeviceToDevice, stream));
+      restart_T_kernel<<<1, 256, 0, stream>>>(T, thetas, k);
+      TNPY_LAUNCH_OK();
+      j = k;
+      ++n_restart;
+    } else {
+      ++j;
+    }
+  }
+  TNPY_CUDA_OK(cudaStreamSynchronize(stream));
+  if (stats_host) {
+    stats_host[0] = hst[ST_THETA];
+    stats_host[1] = hst[ST_RESID];
+    stats_host[2] = (double)n_matvec;
+    stats_host[3] = (double)n_restart;
+    stats_host[4] = done ? 1.0 : 0.0;
+    stats_host[5] = hst[ST_ANORM];
+  }
+  if (!done) {
+    set_error("tnpy_eig_lowest: not converged after %d matvecs (resid %.3e, tol*|A| %.3e)", n_matvec, hst[ST_RESID],
+              tol * hst[ST_ANORM]);
+    return TNPY_ENOCONV;
+  }
+  return TNPY_OK;
+}

@@ -1,0 +1,463 @@
+"""MPS container (host) and the device-resident environment cache of the fDMRG local update.
+
+Mirrors tnpy/matrix_product_state.py: ``Direction`` (:19-25), ``MatrixProductState`` (:28-228, arrays in
+'lpr' order), ``Environment`` (:231-440) and ``MatrixProductStateMeasurements`` (:443-453).
+
+What lives where
+  * ``MatrixProductState`` holds host float64 arrays and is what ``FiniteDMRG.mps`` hands back
+    (``to_quimb()`` converts when quimb is importable; quimb is not a dependency of this package).
+  * ``Environment`` keeps the site tensors, the MPO tensors and the L / R stacks as float64 CUDA
+    tensors for its whole life and does every contraction through the C ABI (``tnpy_b200._cuda``):
+    ``update_left/right`` -> ``tnpy_env_update_*``, ``one_site_matvec`` -> ``tnpy_heff_apply``,
+    ``split_tensor`` -> ``tnpy_svd`` + ``tnpy_absorb_*``.  Real data: the bra copy the reference
+    keeps (``_conj_mps``, :243) is the ket itself.
+"""
+from __future__ import annotations
+
+from enum import Enum
+from pathlib import Path
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+from scipy.sparse.linalg import LinearOperator
+
+from tnpy_b200 import _cuda, logger
+from tnpy_b200.operators import MatrixProductOperator
+
+
+class Direction(Enum):
+    RIGHTWARD = 1
+    LEFTWARD = -1
+
+
+def compressed_bond_dims(n: int, bond_dim: int, phys_dim: int) -> List[int]:
+    """Bond dimensions after quimb's ``compress()``: min(d^i, chi, d^(n-i)) (pinned by the
+    reference's tests/test_matrix_product_state.py:13-37)."""
+    return [int(min(phys_dim ** (i + 1), bond_dim, phys_dim ** (n - 1 - i))) for i in range(n - 1)]
+
+
+class SiteTensor:
+    """The slice of quimb's Tensor API the reference touches on a site: data/shape/size/inds/tags/modify."""
+
+    def __init__(self, data: np.ndarray, inds: Sequence[str], tags: Sequence[str]):
+        self.data = data
+        self.inds = tuple(inds)
+        self.tags = set(tags)
+
+    shape = property(lambda self: self.data.shape)
+    size = property(lambda self: self.data.size)
+
+    def modify(self, data: np.ndarray):
+        self.data = np.asarray(data, dtype=float)
+
+
+class MatrixProductState:
+    """Open-boundary MPS, per-site arrays in 'lpr' order: (d, r) / (l, d, r) / (l, d)."""
+
+    def __init__(self, arrays: Sequence[np.ndarray], shape: str = "lpr"):
+        arrays = [np.array(a, dtype=float) for a in arrays]
+        n = len(arrays)
+        if n < 2:
+            raise ValueError("An MPS needs at least two sites.")
+        if shape != "lpr":  # accept quimb's default 'lrp' too
+            arrays = [self._to_lpr(a, shape, i, n) for i, a in enumerate(arrays)]
+        self._tensors: List[SiteTensor] = []
+        for i, a in enumerate(arrays):
+            inds = ([f"_bond{i - 1}"] if i > 0 else []) + [f"k{i}"] + ([f"_bond{i}"] if i < n - 1 else [])
+            self._tensors.append(SiteTensor(a, inds, [f"I{i}"]))
+
+    @staticmethod
+    def _to_lpr(a: np.ndarray, shape: str, site: int, n: int) -> np.ndarray:
+        have = [s for s in shape if not ((s == "l" and site == 0) or (s == "r" and site == n - 1))]
+        want = [s for s in "lpr" if s in have]
+        return np.transpose(a, [have.index(s) for s in want])
+
+    # -- bookkeeping ------------------------------------------------------------------------------
+    @property
+    def n_sites(self) -> int:
+        return len(self._tensors)
+
+    nsites = n_sites
+    L = n_sites
+
+    @property
+    def phys_dim(self) -> int:
+        return self._tensors[0].shape[0]
+
+    @property
+    def bond_dim(self) -> int:
+        return self.max_bond()
+
+    def max_bond(self) -> int:
+        return max(t.shape[-1] for t in self._tensors[:-1])
+
+    def bond_dims(self) -> List[int]:
+        return [t.shape[-1] for t in self._tensors[:-1]]
+
+    def site_tag(self, site: int) -> str:
+        return f"I{site}"
+
+    def site_ind(self, site: int) -> str:
+        return f"k{site}"
+
+    def __len__(self) -> int:
+        return self.n_sites
+
+    def __getitem__(self, site: int) -> SiteTensor:
+        return self._tensors[site]
+
+    def __iter__(self):
+        return iter(self._tensors)
+
+    @property
+    def arrays(self) -> List[np.ndarray]:
+        return [t.data for t in self._tensors]
+
+    def three_leg(self, site: int) -> np.ndarray:
+        a = self._tensors[site].data
+        if a.ndim == 3:
+            return a
+        return a[None] if site == 0 else a[:, :, None]
+
+    def copy(self) -> "MatrixProductState":
+        return MatrixProductState([a.copy() for a in self.arrays])
+
+    def conj(self, mangle_inner: bool = False, mangle_outer: bool = False) -> "MatrixProductState":
+        """Real tensors: a copy (the reference renames indices only, :93-116)."""
+        out = self.copy()
+        if mangle_outer:
+            for i, t in enumerate(out._tensors):
+                t.inds = tuple(f"b{i}" if ind == f"k{i}" else ind for ind in t.inds)
+        return out
+
+    # -- constructors -------------------------------------------------------------------------------
+    @classmethod
+    def random(cls, n: int, bond_dim: int, phys_dim: int, seed: Optional[int] = None, **kwargs) -> "MatrixProductState":
+        """Random normalised right-canonical MPS at the compressed bond dimensions (:170-185).
+
+        The reference draws from quimb's RNG and calls ``compress()``; here ``default_rng(seed)``
+        standard normals are right-canonicalised by QR from the last site down, site 0 normalised
+        (the same state class; SURVEY 8d fixes this generator for both sides of every parity test).
+        """
+        rng = np.random.default_rng(seed)
+        dims = [1] + compressed_bond_dims(n, bond_dim, phys_dim) + [1]
+        arrays = [rng.standard_normal((dims[i], phys_dim, dims[i + 1])) for i in range(n)]
+        for site in range(n - 1, 0, -1):
+            l, d, r = arrays[site].shape
+            q, rr = np.linalg.qr(arrays[site].reshape(l, d * r).T)
+            arrays[site] = q.T.reshape(l, d, r)
+            arrays[site - 1] = np.einsum("lpr,sr->lps", arrays[site - 1], rr)
+        arrays[0] /= np.linalg.norm(arrays[0])
+        arrays[0] = arrays[0].reshape(phys_dim, dims[1])
+        arrays[-1] = arrays[-1].reshape(dims[n - 1], phys_dim)
+        return cls(arrays, **kwargs)
+
+    def save(self, filename: str):
+        """'lpr' arrays keyed by site tag, ``.npz`` or ``.hdf5`` (:118-143)."""
+        datasets = {self.site_tag(i): t.data for i, t in enumerate(self._tensors)}
+        suffix = Path(filename).suffix
+        if suffix == ".npz":
+            np.savez(str(filename), **datasets)
+        elif suffix == ".hdf5":
+            import h5py  # optional, as in the reference
+
+            with h5py.File(str(filename), "w") as f:
+                for tag, array in datasets.items():
+                    f.create_dataset(tag, data=array)
+        else:
+            raise ValueError(f"File extension {suffix} is not supported.")
+
+    @classmethod
+    def load(cls, filename: str) -> "MatrixProductState":
+        """Inverse of :meth:`save`; sites are ordered by the integer in their tag (fixes the
+        alphabetical-order defect the reference flags at :130/:158)."""
+        suffix = Path(filename).suffix
+        if suffix == ".npz":
+            with np.load(str(filename)) as f:
+                items = {k: f[k] for k in f.files}
+        elif suffix == ".hdf5":
+            import h5py
+
+            with h5py.File(str(filename), "r") as f:
+                items = {k: v[()] for k, v in f.items()}
+        else:
+            raise ValueError(f"File extension {suffix} is not supported.")
+        return cls([items[k] for k in sorted(items, key=lambda tag: int(tag[1:]))])
+
+    # -- host-side measurements ---------------------------------------------------------------------
+    def overlap(self, other: "MatrixProductState") -> float:
+        e = np.ones((1, 1))
+        for site in range(self.n_sites):
+            e = np.einsum("lm,lpr,mps->rs", e, self.three_leg(site), other.three_leg(site), optimize=True)
+        return float(e[0, 0])
+
+    def norm(self) -> float:
+        return float(np.sqrt(self.overlap(self)))
+
+    def __matmul__(self, other: "MatrixProductState") -> float:
+        return self.overlap(other)
+
+    def to_dense(self) -> np.ndarray:
+        acc = self.three_leg(0)[0]
+        for site in range(1, self.n_sites):
+            acc = np.tensordot(acc, self.three_leg(site), axes=(acc.ndim - 1, 0)).reshape(-1, self.three_leg(site).shape[2])
+        return acc.reshape(-1)
+
+    def to_quimb(self):
+        import quimb.tensor as qtn  # only if the user has it
+
+        return qtn.MatrixProductState(self.arrays, shape="lpr")
+
+    # -- a9: split_tensor ---------------------------------------------------------------------------
+    def split_tensor(self, site: int, direction: Direction):
+        """SVD-split ``site`` and push ``s Vt`` / ``U s`` into the neighbour (:187-225); runs on the
+        GPU through the same kernels as :meth:`Environment.split_tensor`."""
+        import torch
+
+        if direction not in (Direction.RIGHTWARD, Direction.LEFTWARD):
+            raise KeyError("MatrixProductState only supplies left or right direction.")
+        nb_site = site + 1 if direction == Direction.RIGHTWARD else site - 1
+        a = torch.from_numpy(np.ascontiguousarray(self.three_leg(site))).cuda()
+        nb = torch.from_numpy(np.ascontiguousarray(self.three_leg(nb_site))).cuda()
+        a, nb, _ = _split_on_device(a, nb, direction)
+        self[site].modify(data=a.cpu().numpy().reshape(self[site].shape))
+        self[nb_site].modify(data=nb.cpu().numpy().reshape(self[nb_site].shape))
+
+    def enlarge_bond_dim(self, new_bond_dim: int, method: str):
+        return NotImplemented
+
+
+def _split_on_device(a, nb, direction: Direction):
+    """Device tensors in, device tensors out: (new site tensor, new neighbour, singular values)."""
+    l, d, r = a.shape
+    if direction == Direction.RIGHTWARD:
+        if l * d < r:
+            raise ValueError(f"split_tensor: site tensor {tuple(a.shape)} cannot keep a right bond of {r}")
+        u, s, vt = _cuda.svd(a.reshape(l * d, r).clone())
+        r2 = nb.shape[2]
+        new_nb = _cuda.absorb_right(s, vt, nb.reshape(r, d * r2)).reshape(r, d, r2)
+        return u.reshape(l, d, r), new_nb, s
+    if d * r < l:
+        raise ValueError(f"split_tensor: site tensor {tuple(a.shape)} cannot keep a left bond of {l}")
+    u, s, vt = _cuda.svd(a.reshape(l, d * r).clone())
+    l0 = nb.shape[0]
+    new_nb = _cuda.absorb_left(u, s, nb.reshape(l0 * d, l)).reshape(l0, d, l)
+    return vt.reshape(l, d, r), new_nb, s
+
+
+class HeffOperator(LinearOperator):
+    """``Environment.one_site_matvec(site)``: a SciPy LinearOperator whose matvec runs on the GPU.
+
+    Host seam (the reference's contract, :411-440): ``matvec(x)`` takes a host vector of length N
+    (shape (N,) or (N,1)), copies it to the device, applies H_eff through ``tnpy_heff_apply`` and
+    copies the result back as (N,1) / (N,).  ``linalg.eigshmv`` recognises this class and keeps
+    the whole eigensolve on the device instead of calling back per matvec.
+    """
+
+    def __init__(self, env: "Environment", site: int):
+        self.env = env
+        self.site = site
+        self.site_shape = tuple(env.device_tensor(site).shape)
+        n = int(np.prod(self.site_shape))
+        super().__init__(dtype=np.dtype("float64"), shape=(n, n))
+
+    def apply_device(self, x, out=None):
+        L, W, R = self.env.operands(self.site)
+        return _cuda.heff_apply(L, W, R, x.reshape(self.site_shape), out)
+
+    def _matvec(self, x: np.ndarray) -> np.ndarray:
+        import torch
+
+        xd = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64).reshape(self.site_shape)).cuda()
+        return self.apply_device(xd).reshape(-1).cpu().numpy()
+
+    def _adjoint(self):
+        return self  # H_eff is real symmetric
+
+
+class _DeviceDictView:
+    """Read-only mapping over an environment stack: ``view[site].data`` is a host copy in the
+    reference's (ket, mpo, bra) order, ``view.device(site)`` the CUDA tensor itself."""
+
+    class _Item:
+        def __init__(self, t):
+            self._t = t
+            self.inds = ("ket", "mpo", "bra")
+
+        @property
+        def data(self) -> np.ndarray:
+            return self._t.cpu().numpy()
+
+        @property
+        def shape(self):
+            return tuple(self._t.shape)
+
+    def __init__(self, store: Dict[int, object]):
+        self._store = store
+
+    def __getitem__(self, site: int):
+        return self._Item(self._store[site])
+
+    def __contains__(self, site: int) -> bool:
+        return site in self._store
+
+    def __len__(self) -> int:
+        return len(self._store)
+
+    def keys(self):
+        return self._store.keys()
+
+    def device(self, site: int):
+        return self._store[site]
+
+
+class Environment:
+    def __init__(self, mpo: MatrixProductOperator, mps: MatrixProductState, build_left: bool = True):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("tnpy_b200.Environment needs a CUDA device; there is no CPU fallback.")
+        _cuda.load()
+        self._mpo = mpo
+        self._n_sites = mpo.nsites
+        if mps.n_sites != self._n_sites:
+            raise ValueError("MPO and MPS have different lengths.")
+        self._shapes = [tuple(t.shape) for t in mps]
+        self._A = [torch.from_numpy(np.ascontiguousarray(mps.three_leg(i))).cuda() for i in range(self._n_sites)]
+        self._W = [torch.from_numpy(np.ascontiguousarray(mpo.as_four_leg(i))).cuda() for i in range(self._n_sites)]
+        self._W2 = None
+        self._left: Dict[int, object] = {}
+        self._right: Dict[int, object] = {}
+        self._host_mps = mps
+        self._dirty = set()
+        self.bond_singular_values: Dict[int, object] = {}
+        if build_left:  # the reference builds both stacks up front (:247-250)
+            for site in range(1, self.n_sites):
+                self.update_left(site)
+        for site in range(self.n_sites - 2, -1, -1):
+            self.update_right(site)
+
+    def close(self):
+        logger.info("Deleting left and right environments.")
+        self._left, self._right = {}, {}
+
+    # -- accessors ----------------------------------------------------------------------------------
+    @property
+    def mpo(self) -> MatrixProductOperator:
+        return self._mpo
+
+    @property
+    def n_sites(self) -> int:
+        return self._n_sites
+
+    @property
+    def mps(self) -> MatrixProductState:
+        """Host MPS, refreshed from the device for every site changed since the last access."""
+        for site in sorted(self._dirty):
+            self._host_mps[site].modify(data=self._A[site].cpu().numpy().reshape(self._shapes[site]))
+        self._dirty.clear()
+        return self._host_mps
+
+    @property
+    def left(self) -> _DeviceDictView:
+        return _DeviceDictView(self._left)
+
+    @property
+    def right(self) -> _DeviceDictView:
+        return _DeviceDictView(self._right)
+
+    def device_tensor(self, site: int):
+        return self._A[site]
+
+    def site_shape(self, site: int):
+        return self._shapes[site]
+
+    def operands(self, site: int):
+        """(L, W, R) device operands of H_eff at ``site`` (None = unit boundary)."""
+        return self._left.get(site) if site > 0 else None, self._W[site], (
+            self._right.get(site) if site < self.n_sites - 1 else None
+        )
+
+    # -- a7 -------------------------------------------------------------------------------------------
+    def update_left(self, site: int):
+        prev = None if site == 1 else self._left[site - 1]
+        self._left[site] = _cuda.env_update_left(prev, self._A[site - 1], self._W[site - 1], self._left.get(site))
+
+    def update_right(self, site: int):
+        prev = None if site == self.n_sites - 2 else self._right[site + 1]
+        self._right[site] = _cuda.env_update_right(prev, self._A[site + 1], self._W[site + 1], self._right.get(site))
+
+    def update(self, site: int, direction: Direction):
+        if direction == Direction.RIGHTWARD:
+            self.update_left(site + 1)
+        elif direction == Direction.LEFTWARD:
+            self.update_right(site - 1)
+
+    # -- a10 ------------------------------------------------------------------------------------------
+    def update_mps(self, site: int, data):
+        import torch
+
+        if isinstance(data, torch.Tensor):
+            src = data.to(device="cuda", dtype=torch.float64)
+        else:
+            src = torch.from_numpy(np.ascontiguousarray(data, dtype=np.float64)).cuda()
+        self._A[site].copy_(src.reshape(self._A[site].shape))
+        self._dirty.add(site)
+
+    # -- a9 -------------------------------------------------------------------------------------------
+    def split_tensor(self, site: int, direction: Direction):
+        if direction not in (Direction.RIGHTWARD, Direction.LEFTWARD):
+            raise KeyError("MatrixProductState only supplies left or right direction.")
+        nb_site = site + 1 if direction == Direction.RIGHTWARD else site - 1
+        a, nb, s = _split_on_device(self._A[site], self._A[nb_site], direction)
+        self._A[site], self._A[nb_site] = a.contiguous(), nb.contiguous()
+        self._dirty.update((site, nb_site))
+        self.bond_singular_values[min(site, nb_site)] = s
+        return s
+
+    # -- a13 ------------------------------------------------------------------------------------------
+    def _expectation(self, w_tensors) -> float:
+        e = None
+        for site in range(self.n_sites):
+            e = _cuda.env_update_left(e, self._A[site], w_tensors[site])
+        return float(e.reshape(-1)[0].item())
+
+    def variance(self) -> float:
+        """<H^2> - <H>^2 on the current (un-normalised) state (:367-370), as two transfer-matrix
+        passes of the environment-update chain (w^2 channels for the squared MPO)."""
+        import torch
+
+        if self._W2 is None:
+            sq = self._mpo.square()
+            self._W2 = [torch.from_numpy(np.ascontiguousarray(sq.as_four_leg(i))).cuda() for i in range(self.n_sites)]
+        return self._expectation(self._W2) - self._expectation(self._W) ** 2
+
+    def expectation(self) -> float:
+        return self._expectation(self._W)
+
+    # -- a6 / a1 --------------------------------------------------------------------------------------
+    def one_site_full_matrix_device(self, site: int):
+        L, W, R = self.operands(site)
+        l, _, r = self._A[site].shape
+        return _cuda.heff_dense(L, W, R, l, r)
+
+    def one_site_full_matrix(self, site: int) -> np.ndarray:
+        return self.one_site_full_matrix_device(site).cpu().numpy()
+
+    def one_site_matvec(self, site: int) -> HeffOperator:
+        return HeffOperator(self, site)
+
+
+class MatrixProductStateMeasurements:
+    def __init__(self, mps: MatrixProductState):
+        self._mps = mps
+
+    def expectation_value(self, mpo: Optional[MatrixProductOperator] = None) -> float:
+        """<psi|psi> or <psi|O|psi> (:447-453); host transfer matrices on the returned MPS."""
+        if mpo is None:
+            return self._mps.overlap(self._mps)
+        e = np.ones((1, 1, 1))
+        for site in range(self._mps.n_sites):
+            a, w = self._mps.three_leg(site), mpo.as_four_leg(site)
+            e = np.einsum("lam,lpr,abpq,mqs->rbs", e, a, w, a, optimize=True)
+        return float(e[0, 0, 0])
