@@ -77,6 +77,14 @@ int tnpy_heff_apply(const double* L, const double* W, const double* R, const dou
                     int l, int r, int wl, int wr, int d, void* workspace, size_t workspace_bytes,
                     void* stream);
 
+/* Row block of the same matvec for the chi-sharded multi-GPU layout: the caller holds
+ * L_rows = L[:, :, m0:m0+l_rows] stored contiguously as (l, wl, l_rows), the full x and R, and gets
+ * y_rows = y[m0:m0+l_rows] as (l_rows, d, r).  No reduction across ranks is needed; the ranks
+ * all-gather the next x.  Workspace: tnpy_heff_workspace_bytes() of the full problem is enough. */
+int tnpy_heff_apply_rows(const double* L_rows, const double* W, const double* R, const double* x,
+                         double* y_rows, int l, int l_rows, int r, int wl, int wr, int d,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- a7: Environment.update_left / update_right  (matrix_product_state.py:296-336) ---------
  * left : Lout[r,b,s] = sum L[l,a,m] A[l,p,r] W[a,b,p,q] A[m,q,s]      Lout: (r, wr, r)
  * right: Rout[l,a,m] = sum R[r,b,s] A[l,p,r] W[a,b,p,q] A[m,q,s]      Rout: (l, wl, l)

@@ -39,7 +39,7 @@ def test_readme_spelling():
 
 @pytest.mark.parametrize(
     "name,n,chi",
-    [("xxz", 10, 32), ("xxz", 16, 24), ("thirring", 12, 20), ("random_heisenberg", 12, 16)],
+    [("xxz", 10, 32), ("xxz", 16, 24), ("thirring", 12, 20), ("thirring_script", 8, 8), ("random_heisenberg", 12, 16)],
 )
 def test_parity_with_oracle(name, n, chi):
     """Same model, chi and initial MPS on both sides (north_star): energy 1e-10 relative,
@@ -50,7 +50,9 @@ def test_parity_with_oracle(name, n, chi):
 
     mdl = {
         "xxz": lambda: models.XXZ(n=n, delta=0.5),
-        "thirring": lambda: models.Thirring(n=n, delta=0.5, ma=1.0, penalty=100.0, s_target=0),
+        "thirring": lambda: models.Thirring(n=n, delta=0.5, ma=1.0, penalty=1.0, s_target=0),
+        # scripts/thirring_fdmrg.py:10 parameters; chi=8 keeps every site on the dense (N < 200) branch
+        "thirring_script": lambda: models.Thirring(n=n, delta=0.5, ma=1.0, penalty=100.0, s_target=0),
         "random_heisenberg": lambda: models.RandomHeisenberg(n=n, h=1.0, seed=2022),
     }[name]()
     init = oracle.random_mps(n, chi, 2, seed=11)

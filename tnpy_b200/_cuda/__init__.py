@@ -30,6 +30,7 @@ SIGNATURES = {
     "tnpy_gemm_tn": (c_int, [_PD, c_int64, _PD, c_int64, _PD, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "tnpy_heff_workspace_bytes": (c_size_t, [c_int] * 5),
     "tnpy_heff_apply": (c_int, [_PD, _PD, _PD, _PD, _PD] + [c_int] * 5 + [c_void_p, c_size_t, c_void_p]),
+    "tnpy_heff_apply_rows": (c_int, [_PD, _PD, _PD, _PD, _PD] + [c_int] * 6 + [c_void_p, c_size_t, c_void_p]),
     "tnpy_env_workspace_bytes": (c_size_t, [c_int] * 5),
     "tnpy_env_update_left": (c_int, [_PD, _PD, _PD, _PD] + [c_int] * 5 + [c_void_p, c_size_t, c_void_p]),
     "tnpy_env_update_right": (c_int, [_PD, _PD, _PD, _PD] + [c_int] * 5 + [c_void_p, c_size_t, c_void_p]),
@@ -176,6 +177,24 @@ def heff_apply(L, W, R, x, out=None):
     ws = _scratch.get(nbytes)
     rc = lib.tnpy_heff_apply(_ptr(L), _ptr(W), _ptr(R), _ptr(x), _ptr(out), l, r, wl, wr, d, _ptr(ws), nbytes, _stream())
     check(rc, "tnpy_heff_apply")
+    return out
+
+
+def heff_apply_rows(L_rows, W, R, x, out=None):
+    """Row block of H_eff x: L_rows (l, wl, l_rows) contiguous, x (l, d, r) full -> (l_rows, d, r)."""
+    import torch
+
+    _need_cuda(L_rows, W, R, x, out)
+    l, r, wl, wr, d = _dims(x.shape, W.shape)
+    lo = L_rows.shape[2]
+    if out is None:
+        out = torch.empty((lo, d, r), dtype=torch.float64, device=x.device)
+    lib = load()
+    nbytes = lib.tnpy_heff_workspace_bytes(l, r, wl, wr, d)
+    ws = _scratch.get(nbytes)
+    rc = lib.tnpy_heff_apply_rows(_ptr(L_rows), _ptr(W), _ptr(R), _ptr(x), _ptr(out), l, lo, r, wl, wr, d, _ptr(ws),
+                                  nbytes, _stream())
+    check(rc, "tnpy_heff_apply_rows")
     return out
 
 

@@ -135,30 +135,38 @@ static int check_dims(int l, int r, int wl, int wr, int d) {
   return TNPY_OK;
 }
 
-int heff_apply(const double* L, const double* W, const double* R, const double* x, double* y, int l, int r, int wl,
-               int wr, int d, Workspace& ws, cudaStream_t stream) {
+// lo = number of output (bra) rows of L held by the caller: L is (l, wl, lo), y is (lo, d, r).
+// lo == l is the ordinary matvec; lo < l is one rank's row block of the chi-sharded matvec.
+int heff_apply_rows(const double* L, const double* W, const double* R, const double* x, double* y, int l, int lo,
+                    int r, int wl, int wr, int d, Workspace& ws, cudaStream_t stream) {
   TNPY_TRY(check_dims(l, r, wl, wr, d));
+  TNPY_CHECK_ARG(lo > 0, "non-positive row count");
   TNPY_CHECK_ARG(W && x && y, "null pointer");
-  TNPY_CHECK_ARG(L || (l == 1 && wl == 1), "L may be NULL only for unit left bond");
+  TNPY_CHECK_ARG(L || (l == 1 && wl == 1 && lo == 1), "L may be NULL only for unit left bond");
   TNPY_CHECK_ARG(R || (r == 1 && wr == 1), "R may be NULL only for unit right bond");
   if (!L) L = device_one();
   if (!R) R = device_one();
-  double* t1 = ws.take<double>((size_t)d * r * wl * l);
-  double* t2 = ws.take<double>((size_t)r * wr * d * l);
+  double* t1 = ws.take<double>((size_t)d * r * wl * lo);
+  double* t2 = ws.take<double>((size_t)r * wr * d * lo);
   if (!t1 || !t2) {
     set_error("heff_apply: workspace too small");
     return TNPY_EWORKSPACE;
   }
   const int algo = TNPY_GEMM_AUTO;
   // T1[p, r, a, m] = sum_l x[l, (p r)] L[l, (a m)]
-  TNPY_TRY(gemm_tn(x, (int64_t)d * r, L, (int64_t)wl * l, plain_out(t1, (int64_t)wl * l, d * r), d * r, wl * l, l, 0,
-                   algo, stream));
+  TNPY_TRY(gemm_tn(x, (int64_t)d * r, L, (int64_t)wl * lo, plain_out(t1, (int64_t)wl * lo, d * r), d * r, wl * lo, l,
+                   0, algo, stream));
   // T2[r, b, q, m] = sum_{a p} W[a, b, p, q] T1[p, r, a, m]          (u=p, u'=q, v=a, v'=b)
-  TNPY_TRY(wmix(t1, t2, W, d, d, wl, wr, r, l, d, 1, wr * d * d, d * d, stream));
+  TNPY_TRY(wmix(t1, t2, W, d, d, wl, wr, r, lo, d, 1, wr * d * d, d * d, stream));
   // y[m, q, s] = sum_{r b} T2[(r b), (q m)] R[(r b), s]               rows (q m) -> (m q)
-  GemmOut out{y, (int64_t)d * r, (int64_t)r, l};
-  TNPY_TRY(gemm_tn(t2, (int64_t)d * l, R, (int64_t)r, out, d * l, r, r * wr, 0, algo, stream));
+  GemmOut out{y, (int64_t)d * r, (int64_t)r, lo};
+  TNPY_TRY(gemm_tn(t2, (int64_t)d * lo, R, (int64_t)r, out, d * lo, r, r * wr, 0, algo, stream));
   return TNPY_OK;
+}
+
+int heff_apply(const double* L, const double* W, const double* R, const double* x, double* y, int l, int r, int wl,
+               int wr, int d, Workspace& ws, cudaStream_t stream) {
+  return heff_apply_rows(L, W, R, x, y, l, l, r, wl, wr, d, ws, stream);
 }
 
 int env_update_left(const double* L, const double* A, const double* W, double* Lout, int l, int r, int wl, int wr,
@@ -253,6 +261,13 @@ extern "C" int tnpy_heff_apply(const double* L, const double* W, const double* R
                                int r, int wl, int wr, int d, void* workspace, size_t workspace_bytes, void* stream) {
   Workspace ws(workspace, workspace_bytes);
   return heff_apply(L, W, R, x, y, l, r, wl, wr, d, ws, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int tnpy_heff_apply_rows(const double* L_rows, const double* W, const double* R, const double* x,
+                                    double* y_rows, int l, int l_rows, int r, int wl, int wr, int d, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  Workspace ws(workspace, workspace_bytes);
+  return heff_apply_rows(L_rows, W, R, x, y_rows, l, l_rows, r, wl, wr, d, ws, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int tnpy_env_update_left(const double* L, const double* A, const double* W, double* Lout, int l, int r,

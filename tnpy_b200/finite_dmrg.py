@@ -41,7 +41,7 @@ class FiniteDMRG:
         mpo: MatrixProductOperator,
         bond_dim: Optional[int] = None,
         block_size: int = 1,
-        mps: Optional[MatrixProductState] = None,
+        mps=None,
         exact_solver_dim: int = 200,
         *,
         chi: Optional[int] = None,

@@ -265,11 +265,37 @@ class HeffOperator(LinearOperator):
         L, W, R = self.env.operands(self.site)
         return _cuda.heff_apply(L, W, R, x.reshape(self.site_shape), out)
 
-    def _matvec(self, x: np.ndarray) -> np.ndarray:
+    def _staging(self):
         import torch
 
-        xd = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64).reshape(self.site_shape)).cuda()
-        return self.apply_device(xd).reshape(-1).cpu().numpy()
+        if getattr(self, "_stage", None) is None:
+            n = self.shape[0]
+            self._stage = {
+                "xd": torch.empty(self.site_shape, dtype=torch.float64, device="cuda"),
+                "yd": torch.empty(self.site_shape, dtype=torch.float64, device="cuda"),
+                "pin_in": torch.empty(n, dtype=torch.float64).pin_memory(),
+                "pin_out": [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(2)],
+                "flip": 0,
+            }
+        return self._stage
+
+    def _matvec(self, x: np.ndarray) -> np.ndarray:
+        """Host vector in, host vector out.  Copies go through pinned staging buffers; the returned
+        array is a view of one of two alternating pinned buffers (valid until the call after next)."""
+        import torch
+
+        st = self._staging()
+        src = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64).reshape(-1))
+        if not src.is_pinned():
+            st["pin_in"].copy_(src)
+            src = st["pin_in"]
+        st["xd"].reshape(-1).copy_(src, non_blocking=True)
+        self.apply_device(st["xd"], st["yd"])
+        st["flip"] ^= 1
+        out = st["pin_out"][st["flip"]]
+        out.copy_(st["yd"].reshape(-1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return out.numpy()
 
     def _adjoint(self):
         return self  # H_eff is real symmetric
@@ -312,7 +338,9 @@ class _DeviceDictView:
 
 
 class Environment:
-    def __init__(self, mpo: MatrixProductOperator, mps: MatrixProductState, build_left: bool = True):
+    def __init__(self, mpo: MatrixProductOperator, mps, build_left: bool = True):
+        """``mps`` is a :class:`MatrixProductState` (host, as in the reference) or a list of
+        three-leg (l, d, r) float64 CUDA tensors (device-born synthetic states for benchmarks)."""
         import torch
 
         if not torch.cuda.is_available():
@@ -320,16 +348,26 @@ class Environment:
         _cuda.load()
         self._mpo = mpo
         self._n_sites = mpo.nsites
-        if mps.n_sites != self._n_sites:
+        if len(mps) != self._n_sites:
             raise ValueError("MPO and MPS have different lengths.")
-        self._shapes = [tuple(t.shape) for t in mps]
-        self._A = [torch.from_numpy(np.ascontiguousarray(mps.three_leg(i))).cuda() for i in range(self._n_sites)]
+        if isinstance(mps, MatrixProductState):
+            self._shapes = [tuple(t.shape) for t in mps]
+            self._A = [torch.from_numpy(np.ascontiguousarray(mps.three_leg(i))).cuda() for i in range(self._n_sites)]
+            self._host_mps = mps
+            self._dirty = set()
+        else:
+            self._A = [t.to(device="cuda", dtype=torch.float64).contiguous() for t in mps]
+            n = self._n_sites
+            self._shapes = [
+                tuple(t.shape[1:]) if i == 0 else (tuple(t.shape[:2]) if i == n - 1 else tuple(t.shape))
+                for i, t in enumerate(self._A)
+            ]
+            self._host_mps = None
+            self._dirty = set(range(n))
         self._W = [torch.from_numpy(np.ascontiguousarray(mpo.as_four_leg(i))).cuda() for i in range(self._n_sites)]
         self._W2 = None
         self._left: Dict[int, object] = {}
         self._right: Dict[int, object] = {}
-        self._host_mps = mps
-        self._dirty = set()
         self.bond_singular_values: Dict[int, object] = {}
         if build_left:  # the reference builds both stacks up front (:247-250)
             for site in range(1, self.n_sites):
@@ -353,6 +391,11 @@ class Environment:
     @property
     def mps(self) -> MatrixProductState:
         """Host MPS, refreshed from the device for every site changed since the last access."""
+        if self._host_mps is None:
+            self._host_mps = MatrixProductState(
+                [a.cpu().numpy().reshape(shape) for a, shape in zip(self._A, self._shapes)]
+            )
+            self._dirty.clear()
         for site in sorted(self._dirty):
             self._host_mps[site].modify(data=self._A[site].cpu().numpy().reshape(self._shapes[site]))
         self._dirty.clear()

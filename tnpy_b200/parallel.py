@@ -1,0 +1,70 @@
+"""chi-row sharding of the H_eff matvec across the GPUs of one box.
+
+Rank g of G owns the row block ``rows_g`` of the bra bond: ``L[:, :, rows_g]`` (stored contiguously),
+the matching rows of x / y and of every Lanczos vector, plus a full copy of R.  One matvec is
+
+    all-gather(x rows) -> x           (torch.distributed, NCCL over NVLink; the only exchange step)
+    y[rows_g] = tnpy_heff_apply_rows(L[:, :, rows_g], W, R, x)        (no reduction needed)
+
+Scalars of the eigensolver (dots, norms) are all-reduced.  The host-side index logic lives here so it
+can be tested on CPU with the gloo backend.
+"""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+
+def row_block(chi: int, world: int, rank: int) -> Tuple[int, int]:
+    """Half-open row range [lo, hi) of ``rank``: blocks differ by at most one row, 2-row aligned
+    when chi allows it (keeps every shard's leading dimension even for the TMA path)."""
+    if not 0 <= rank < world:
+        raise ValueError(f"rank {rank} outside world of {world}")
+    unit = 2 if chi % 2 == 0 and chi >= 2 * world else 1
+    n_units = chi // unit
+    base, extra = divmod(n_units, world)
+    lo_u = rank * base + min(rank, extra)
+    hi_u = lo_u + base + (1 if rank < extra else 0)
+    return lo_u * unit, hi_u * unit
+
+
+def all_row_blocks(chi: int, world: int) -> List[Tuple[int, int]]:
+    return [row_block(chi, world, g) for g in range(world)]
+
+
+def shard_left_env(L, world: int, rank: int):
+    """Contiguous copy of this rank's bra-row block of a left environment (l, w, l)."""
+    lo, hi = row_block(L.shape[2], world, rank)
+    return L[:, :, lo:hi].contiguous()
+
+
+def gather_rows(x_rows, chi: int, group=None):
+    """All-gather the row blocks of a site tensor into the full (chi, d, r) tensor on every rank."""
+    import torch
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    blocks = all_row_blocks(chi, world)
+    full = torch.empty((chi,) + tuple(x_rows.shape[1:]), dtype=x_rows.dtype, device=x_rows.device)
+    assert blocks[rank][1] - blocks[rank][0] == x_rows.shape[0]
+    if all(hi - lo == blocks[0][1] - blocks[0][0] for lo, hi in blocks):
+        dist.all_gather_into_tensor(full, x_rows.contiguous(), group=group)
+        return full
+    # ragged blocks: pad every block to the largest one, gather, then drop the padding
+    most = max(hi - lo for lo, hi in blocks)
+    padded = torch.zeros((most,) + tuple(x_rows.shape[1:]), dtype=x_rows.dtype, device=x_rows.device)
+    padded[: x_rows.shape[0]] = x_rows
+    stacked = torch.empty((world * most,) + tuple(x_rows.shape[1:]), dtype=x_rows.dtype, device=x_rows.device)
+    dist.all_gather_into_tensor(stacked, padded, group=group)
+    for g, (lo, hi) in enumerate(blocks):
+        full[lo:hi] = stacked[g * most : g * most + hi - lo]
+    return full
+
+
+def sharded_dot(a_rows, b_rows, group=None):
+    """Global <a|b> from row blocks: local partial + all-reduce of one scalar."""
+    import torch
+    import torch.distributed as dist
+
+    part = (a_rows * b_rows).sum().reshape(1)
+    dist.all_reduce(part, op=dist.ReduceOp.SUM, group=group)
+    return part[0]
