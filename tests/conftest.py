@@ -28,3 +28,15 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(autouse=True)
+def _quiet_tnpy_logger():
+    """The reference logs one INFO line per site; keep test output readable."""
+    import logging
+
+    logger = logging.getLogger("tnpy")
+    old = logger.level
+    logger.setLevel(logging.WARNING)
+    yield
+    logger.setLevel(old)

@@ -260,6 +260,26 @@ def test_svd(cu, rows, cols):
     assert np.abs(vt @ vt.T - np.eye(k)).max() <= 1e-11
 
 
+@pytest.mark.parametrize("rows,cols", [(2048, 1024), (1024, 2048), (1000, 700)])
+def test_svd_block_path_large(cu, rows, cols):
+    """Block-Jacobi path at a size where a host SVD would take seconds: checked through
+    size-independent properties (orthogonality, reconstruction, sortedness) and against the
+    singular values of cuSOLVER (yardstick only)."""
+    g = torch.Generator(device="cuda").manual_seed(rows + cols)
+    a = torch.randn((rows, cols), generator=g, dtype=torch.float64, device="cuda")
+    a = a * torch.logspace(0, -8, cols, dtype=torch.float64, device="cuda")[None, :]
+    u, s, vt = cu.svd(a.clone())
+    k = min(rows, cols)
+    eye = torch.eye(k, dtype=torch.float64, device="cuda")
+    assert float((u.t() @ u - eye).abs().max()) < 1e-11
+    assert float((vt @ vt.t() - eye).abs().max()) < 1e-11
+    assert float(((u * s) @ vt - a).abs().max()) < 1e-12 * float(s[0])
+    assert bool((s[1:] <= s[:-1]).all())
+    s_ref = torch.linalg.svdvals(a)
+    assert float((s - s_ref).abs().max()) < 1e-12 * float(s_ref[0])
+    assert cu.load().tnpy_last_svd_sweeps() < 40
+
+
 def test_svd_graded_spectrum(cu):
     """DMRG wave functions have singular values over 16 decades; small ones must keep absolute 1e-9."""
     rng = np.random.default_rng(7)

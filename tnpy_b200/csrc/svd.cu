@@ -107,63 +107,215 @@ __global__ void __launch_bounds__(512) hestenes_small_kernel(double* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------
-// large path: one launch per round, one CTA per pair
+// large path: block one-sided Jacobi.  Rows are grouped in blocks of kJB; a round pairs the blocks
+// round-robin and, for every pair (a 64-row panel), runs three kernels:
+//   jb_gram    partial Gram matrices of the panel over column chunks of G      (DMMA, all SMs)
+//   jb_rotate  fixed-order reduction of the partials, one cyclic Jacobi sweep on the 64x64 Gram
+//              in shared memory -> the accumulated 64x64 rotation J^T          (one CTA per pair)
+//   jb_apply   panel <- J^T panel over column chunks of [G | P], in place      (DMMA, all SMs)
+// The matrix is touched 3x per round instead of once per row pair: (n/kJB - 1) rounds per sweep
+// instead of (n - 1), and both heavy kernels run on the FP64 tensor pipe.  Rotations are computed
+// from freshly formed Gram entries at every visit, so the iteration is self-correcting and the
+// singular values keep Hestenes' relative accuracy (the final norms come from the rows themselves).
 // ---------------------------------------------------------------------------------------------
-__global__ void identity_kernel(double* __restrict__ P, int n) {
-  const int64_t total = (int64_t)n * n;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x)
-    P[e] = (e / n == e % n) ? 1.0 : 0.0;
+constexpr int kJB = 32;             // rows per block
+constexpr int kJP = 2 * kJB;        // rows per panel (block pair)
+constexpr int kJCH = 128;           // columns per shared-memory chunk
+constexpr int kJST = kJCH + 4;      // panel row stride in shared memory (conflict-free DMMA fragments)
+constexpr int kJTS = kJP + 4;       // rotation-matrix row stride in shared memory
+constexpr int kJGramCols = 512;     // columns of G per jb_gram CTA
+
+__device__ __forceinline__ void dmma884_(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
 }
 
-template <bool STAGE>
-__global__ void __launch_bounds__(256) hestenes_round_kernel(double* __restrict__ G, int n, int m, int64_t ldg,
-                                                             double* __restrict__ P, int round, int me, double tol,
-                                                             unsigned int* __restrict__ rot_count) {
-  extern __shared__ double rows[];  // STAGE: 2 x m doubles
-  __shared__ double sh[32];
-  __shared__ double rot_cs[2];
-  __shared__ int do_rot;
-  int p, q;
-  rr_pair(round, blockIdx.x, me, p, q);
-  if (q >= n) return;
-  double* gp = G + (int64_t)p * ldg;
-  double* gq = G + (int64_t)q * ldg;
-  double a = 0.0, b = 0.0, c = 0.0;
-  for (int k = threadIdx.x; k < m; k += blockDim.x) {
-    const double x = gp[k], y = gq[k];
-    if (STAGE) {
-      rows[k] = x;
-      rows[m + k] = y;
+// GP = [G | P] (n_pad x ld): G from A (transposed when `tall`), P = identity, padding rows zero.
+__global__ void __launch_bounds__(256) jb_init_kernel(const double* __restrict__ A, int rows, int cols, int tall,
+                                                      double* __restrict__ GP, int n, int m, int n_pad, int64_t ld) {
+  const int64_t total = (int64_t)n_pad * ld;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(e / ld), c = (int)(e % ld);
+    double v = 0.0;
+    if (c < m) {
+      if (k < n) v = tall ? A[(int64_t)c * cols + k] : A[(int64_t)k * cols + c];
+    } else if (c - m == k) {
+      v = 1.0;
     }
-    a = fma(x, x, a);
-    b = fma(y, y, b);
-    c = fma(x, y, c);
+    GP[e] = v;
   }
-  a = block_sum(a, sh);
-  b = block_sum(b, sh);
-  c = block_sum(c, sh);
-  if (threadIdx.x == 0) {
-    double cs = 1.0, sn = 0.0;
-    do_rot = hestenes_cs(a, b, c, tol, cs, sn) ? 1 : 0;
-    rot_cs[0] = cs;
-    rot_cs[1] = sn;
-    if (do_rot) atomicAdd(rot_count, 1u);
+}
+
+__device__ __forceinline__ int panel_row(int I, int J, int r) { return r < kJB ? I * kJB + r : J * kJB + (r - kJB); }
+
+// Load a kJP x kJCH chunk of the panel (columns [c0, c0 + kJCH) clipped to c_end) into shared memory.
+__device__ __forceinline__ void load_panel(const double* __restrict__ GP, int64_t ld, int I, int J, int c0, int c_end,
+                                           double* __restrict__ panel) {
+  for (int idx = threadIdx.x; idx < kJP * (kJCH / 2); idx += blockDim.x) {
+    const int r = idx / (kJCH / 2), c = (idx % (kJCH / 2)) * 2;
+    const double* src = GP + (int64_t)panel_row(I, J, r) * ld + c0 + c;
+    double2 v = make_double2(0.0, 0.0);
+    if (c0 + c + 1 < c_end) v = *reinterpret_cast<const double2*>(src);
+    else if (c0 + c < c_end) v.x = src[0];
+    panel[r * kJST + c] = v.x;
+    panel[r * kJST + c + 1] = v.y;
+  }
+}
+
+__global__ void __launch_bounds__(256) jb_gram_kernel(const double* __restrict__ GP, int64_t ld, int m, int nb,
+                                                      int round, int gchunks, double* __restrict__ partial) {
+  extern __shared__ double sm[];
+  double* panel = sm;
+  int I, J;
+  rr_pair(round, blockIdx.x, nb, I, J);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int c_begin = blockIdx.y * kJGramCols, c_end = min(m, c_begin + kJGramCols);
+  double acc[8][2];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = 0.0;
+  for (int c0 = c_begin; c0 < c_end; c0 += kJCH) {
+    load_panel(GP, ld, I, J, c0, c_end, panel);
+    __syncthreads();
+#pragma unroll 4
+    for (int k0 = 0; k0 < kJCH; k0 += 4) {
+      const double a = panel[(8 * warp + g) * kJST + k0 + t];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dmma884_(acc[j][0], acc[j][1], a, panel[(8 * j + g) * kJST + k0 + t]);
+    }
+    __syncthreads();
+  }
+  double* out = partial + ((int64_t)blockIdx.x * gchunks + blockIdx.y) * (kJP * kJP);
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<double2*>(out + (8 * warp + g) * kJP + 8 * j + 2 * t) = make_double2(acc[j][0], acc[j][1]);
+}
+
+__global__ void __launch_bounds__(256) jb_rotate_kernel(const double* __restrict__ partial, int gchunks, double tol,
+                                                        int inner_sweeps, double* __restrict__ Jt,
+                                                        unsigned int* __restrict__ rot_count) {
+  extern __shared__ double sm[];
+  double(*a)[kJP + 1] = reinterpret_cast<double(*)[kJP + 1]>(sm);
+  double(*z)[kJP + 1] = reinterpret_cast<double(*)[kJP + 1]>(sm + kJP * (kJP + 1));
+  __shared__ double cs[kJB], sn[kJB];
+  __shared__ int pp[kJB], qq[kJB];
+  __shared__ int significant;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const double* src = partial + (int64_t)blockIdx.x * gchunks * (kJP * kJP);
+  if (tid == 0) significant = 0;
+  for (int idx = tid; idx < kJP * kJP; idx += nt) {
+    double v = 0.0;
+    for (int c = 0; c < gchunks; ++c) v += src[(int64_t)c * (kJP * kJP) + idx];  // fixed order: deterministic
+    a[idx / kJP][idx % kJP] = v;
+    z[idx / kJP][idx % kJP] = (idx / kJP == idx % kJP) ? 1.0 : 0.0;
   }
   __syncthreads();
-  if (!do_rot) return;
-  const double cs = rot_cs[0], sn = rot_cs[1];
-  for (int k = threadIdx.x; k < m; k += blockDim.x) {
-    const double x = STAGE ? rows[k] : gp[k];
-    const double y = STAGE ? rows[m + k] : gq[k];
-    gp[k] = cs * x - sn * y;
-    gq[k] = sn * x + cs * y;
+  // convergence bookkeeping on the freshly formed Gram matrix
+  int mine = 0;
+  for (int idx = tid; idx < kJP * kJP; idx += nt) {
+    const int p = idx / kJP, q = idx % kJP;
+    if (p < q && fabs(a[p][q]) > tol * sqrt(a[p][p] * a[q][q])) ++mine;
   }
-  double* pp = P + (int64_t)p * n;
-  double* pq = P + (int64_t)q * n;
-  for (int k = threadIdx.x; k < n; k += blockDim.x) {
-    const double x = pp[k], y = pq[k];
-    pp[k] = cs * x - sn * y;
-    pq[k] = sn * x + cs * y;
+  if (mine) atomicAdd(&significant, mine);
+  __syncthreads();
+  const int nsig = significant;
+  if (nsig == 0) {
+    // already orthogonal: identity rotation
+    for (int idx = tid; idx < kJP * kJP; idx += nt)
+      Jt[(int64_t)blockIdx.x * kJP * kJP + idx] = (idx / kJP == idx % kJP) ? 1.0 : 0.0;
+    return;
+  }
+  if (tid == 0) atomicAdd(rot_count, (unsigned int)nsig);
+  constexpr int half = kJP / 2;
+  for (int sweep = 0; sweep < inner_sweeps; ++sweep) {
+    for (int round = 0; round < kJP - 1; ++round) {
+      if (tid < half) {
+        int p, q;
+        rr_pair(round, tid, kJP, p, q);
+        double c = 1.0, s = 0.0;
+        const double apq = a[p][q], app = a[p][p], aqq = a[q][q];
+        if (fabs(apq) > tol * sqrt(app * aqq) && apq != 0.0) {
+          const double tau = (aqq - app) / (2.0 * apq);
+          const double tt = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+          c = 1.0 / sqrt(1.0 + tt * tt);
+          s = tt * c;
+        }
+        cs[tid] = c;
+        sn[tid] = s;
+        pp[tid] = p;
+        qq[tid] = q;
+      }
+      __syncthreads();
+      for (int idx = tid; idx < half * kJP; idx += nt) {
+        const int i = idx / kJP, k = idx % kJP;
+        const double s = sn[i];
+        if (s == 0.0) continue;
+        const double c = cs[i];
+        const int p = pp[i], q = qq[i];
+        const double akp = a[k][p], akq = a[k][q];
+        a[k][p] = c * akp - s * akq;
+        a[k][q] = s * akp + c * akq;
+        const double zkp = z[k][p], zkq = z[k][q];
+        z[k][p] = c * zkp - s * zkq;
+        z[k][q] = s * zkp + c * zkq;
+      }
+      __syncthreads();
+      for (int idx = tid; idx < half * kJP; idx += nt) {
+        const int i = idx / kJP, k = idx % kJP;
+        const double s = sn[i];
+        if (s == 0.0) continue;
+        const double c = cs[i];
+        const int p = pp[i], q = qq[i];
+        const double apk = a[p][k], aqk = a[q][k];
+        a[p][k] = c * apk - s * aqk;
+        a[q][k] = s * apk + c * aqk;
+      }
+      __syncthreads();
+    }
+  }
+  // new_row[i] = sum_k Z[k][i] * old_row[k]  =>  Jt[i][k] = Z[k][i]
+  for (int idx = tid; idx < kJP * kJP; idx += nt) Jt[(int64_t)blockIdx.x * kJP * kJP + idx] = z[idx % kJP][idx / kJP];
+}
+
+__global__ void __launch_bounds__(256) jb_apply_kernel(double* __restrict__ GP, int64_t ld, int width, int nb, int round,
+                                                       const double* __restrict__ Jt) {
+  extern __shared__ double sm[];
+  double* jt = sm;                  // kJP x kJTS
+  double* panel = sm + kJP * kJTS;  // kJP x kJST
+  int I, J;
+  rr_pair(round, blockIdx.x, nb, I, J);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int c0 = blockIdx.y * kJCH, c_end = min(width, c0 + kJCH);
+  const double* jsrc = Jt + (int64_t)blockIdx.x * kJP * kJP;
+  for (int idx = threadIdx.x; idx < kJP * kJP; idx += blockDim.x) jt[(idx / kJP) * kJTS + idx % kJP] = jsrc[idx];
+  load_panel(GP, ld, I, J, c0, c_end, panel);
+  __syncthreads();
+  double acc[8][2][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll 2
+  for (int k0 = 0; k0 < kJP; k0 += 4) {
+    double b[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) b[j] = panel[(k0 + t) * kJST + 16 * warp + 8 * j + g];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const double a = jt[(8 * i + g) * kJTS + k0 + t];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) dmma884_(acc[i][j][0], acc[i][j][1], a, b[j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    double* dst = GP + (int64_t)panel_row(I, J, 8 * i + g) * ld + c0;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int c = 16 * warp + 8 * j + 2 * t;
+      if (c0 + c + 1 < c_end) *reinterpret_cast<double2*>(dst + c) = make_double2(acc[i][j][0], acc[i][j][1]);
+      else if (c0 + c < c_end) dst[c] = acc[i][j][0];
+    }
   }
 }
 
@@ -198,7 +350,8 @@ __global__ void rank_kernel(const double* __restrict__ norms, int n, int* __rest
 
 // w_out[rank[k]*wa + i*wb] = G[k][i] / s_k  (i < m);   p_out[rank[k]*pa + j*pb] = P[k][j]  (j < n)
 __global__ void __launch_bounds__(256) scatter_kernel(const double* __restrict__ G, int n, int m, int64_t ldg,
-                                                      const double* __restrict__ P, const double* __restrict__ norms,
+                                                      const double* __restrict__ P, int64_t ldp,
+                                                      const double* __restrict__ norms,
                                                       const int* __restrict__ rank, double* __restrict__ w_out,
                                                       int64_t wa, int64_t wb, double* __restrict__ p_out, int64_t pa,
                                                       int64_t pb) {
@@ -207,7 +360,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(const double* __restrict__
   const double nk = norms[k];
   const double inv = nk > 0.0 ? 1.0 / nk : 0.0;
   for (int i = threadIdx.x; i < m; i += blockDim.x) w_out[r * wa + i * wb] = G[(int64_t)k * ldg + i] * inv;
-  for (int j = threadIdx.x; j < n; j += blockDim.x) p_out[r * pa + j * pb] = P[(int64_t)k * n + j];
+  for (int j = threadIdx.x; j < n; j += blockDim.x) p_out[r * pa + j * pb] = P[(int64_t)k * ldp + j];
 }
 
 __global__ void __launch_bounds__(256) transpose2d_kernel(const double* __restrict__ in, int rows, int cols,
@@ -247,50 +400,75 @@ struct PinnedWord {
   PinnedWord() { cudaMallocHost(&host, 64); }
 };
 
-// Orthogonalise the rows of G (n x m, n <= m) in place; P (n x n) receives the accumulated rotations.
-static int hestenes(double* G, int n, int m, int64_t ldg, double* P, unsigned int* counter_dev, cudaStream_t stream,
-                    int* sweeps_out) {
-  const double tol = fmax(1e-15, 2.220446049250313e-16 * sqrt((double)m));
-  const int max_sweeps = 60;
-  const size_t small_bytes = sizeof(double) * ((size_t)n * m + (size_t)n * n);
-  if (small_bytes <= 200 * 1024) {
-    static bool configured = false;
-    if (!configured) {
-      TNPY_CUDA_OK(cudaFuncSetAttribute(hestenes_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      configured = true;
-    }
-    const int threads = n >= 32 ? 512 : (n >= 8 ? 256 : 64);
-    hestenes_small_kernel<<<1, threads, small_bytes, stream>>>(G, n, m, ldg, P, tol, max_sweeps, nullptr);
-    TNPY_LAUNCH_OK();
-    if (sweeps_out) *sweeps_out = -1;
-    return TNPY_OK;
+static double jacobi_tol(int m) { return fmax(1e-15, 2.220446049250313e-16 * sqrt((double)m)); }
+
+static bool fits_small(int n, int m) { return sizeof(double) * ((size_t)n * m + (size_t)n * n) <= 200 * 1024; }
+
+// small path: G (n x m, ld m) in place, P (n x n) out
+static int hestenes_small(double* G, int n, int m, double* P, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    TNPY_CUDA_OK(cudaFuncSetAttribute(hestenes_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = true;
   }
+  const size_t bytes = sizeof(double) * ((size_t)n * m + (size_t)n * n);
+  const int threads = n >= 32 ? 512 : (n >= 8 ? 256 : 64);
+  hestenes_small_kernel<<<1, threads, bytes, stream>>>(G, n, m, m, P, jacobi_tol(m), 60, nullptr);
+  TNPY_LAUNCH_OK();
+  return TNPY_OK;
+}
+
+struct BlockPlan {
+  int n_pad, nb, pairs, gchunks, achunks;
+  int64_t ld;
+  size_t gp_elems, partial_elems, jt_elems;
+};
+
+static BlockPlan block_plan(int n, int m) {
+  BlockPlan p;
+  p.n_pad = (n + kJP - 1) / kJP * kJP;  // whole panels => an even number of blocks, no byes
+  p.nb = p.n_pad / kJB;
+  p.pairs = p.nb / 2;
+  p.ld = ((int64_t)m + p.n_pad + 3) / 4 * 4;
+  p.gchunks = (m + kJGramCols - 1) / kJGramCols;
+  p.achunks = (int)((m + p.n_pad + kJCH - 1) / kJCH);
+  p.gp_elems = (size_t)p.n_pad * p.ld;
+  p.partial_elems = (size_t)p.pairs * p.gchunks * kJP * kJP;
+  p.jt_elems = (size_t)p.pairs * kJP * kJP;
+  return p;
+}
+
+// large path: GP = [G | P] (n_pad x ld) in place
+static int hestenes_block(double* GP, const BlockPlan& p, int m, double* partial, double* Jt, unsigned int* counter_dev,
+                          cudaStream_t stream, int* sweeps_out) {
   static PinnedWord pinned;
   if (!pinned.host) {
     set_error("hestenes: pinned allocation failed");
     return TNPY_ECUDA;
   }
-  identity_kernel<<<sm_count() * 4, 256, 0, stream>>>(P, n);
-  TNPY_LAUNCH_OK();
-  const int me = (n + 1) & ~1, half = me / 2;
-  const size_t stage_bytes = sizeof(double) * 2 * (size_t)m;
-  const bool stage = stage_bytes <= 96 * 1024;
-  static bool configured2 = false;
-  if (stage && !configured2) {
-    TNPY_CUDA_OK(cudaFuncSetAttribute(hestenes_round_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    configured2 = true;
+  const size_t gram_smem = sizeof(double) * kJP * kJST;
+  const size_t rot_smem = sizeof(double) * 2 * kJP * (kJP + 1);
+  const size_t apply_smem = sizeof(double) * (kJP * kJTS + kJP * kJST);
+  static bool configured = false;
+  if (!configured) {
+    TNPY_CUDA_OK(cudaFuncSetAttribute(jb_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gram_smem));
+    TNPY_CUDA_OK(cudaFuncSetAttribute(jb_rotate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rot_smem));
+    TNPY_CUDA_OK(cudaFuncSetAttribute(jb_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)apply_smem));
+    configured = true;
   }
+  const double tol = jacobi_tol(m);
+  const int width = m + p.n_pad;
+  const int max_sweeps = 60;
   int sweep = 0;
   for (; sweep < max_sweeps; ++sweep) {
     TNPY_CUDA_OK(cudaMemsetAsync(counter_dev, 0, sizeof(unsigned int), stream));
-    for (int round = 0; round < me - 1; ++round) {
-      if (stage)
-        hestenes_round_kernel<true><<<half, 256, stage_bytes, stream>>>(G, n, m, ldg, P, round, me, tol, counter_dev);
-      else
-        hestenes_round_kernel<false><<<half, 256, 0, stream>>>(G, n, m, ldg, P, round, me, tol, counter_dev);
+    for (int round = 0; round < p.nb - 1; ++round) {
+      jb_gram_kernel<<<dim3(p.pairs, p.gchunks), 256, gram_smem, stream>>>(GP, p.ld, m, p.nb, round, p.gchunks, partial);
+      jb_rotate_kernel<<<p.pairs, 256, rot_smem, stream>>>(partial, p.gchunks, tol, 1, Jt, counter_dev);
+      jb_apply_kernel<<<dim3(p.pairs, p.achunks), 256, apply_smem, stream>>>(GP, p.ld, width, p.nb, round, Jt);
     }
     TNPY_LAUNCH_OK();
-    count_launch(me - 2);
+    count_launch(3 * (p.nb - 1) - 1);
     TNPY_CUDA_OK(cudaMemcpyAsync(pinned.host, counter_dev, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
     TNPY_CUDA_OK(cudaStreamSynchronize(stream));
     if (*pinned.host == 0u) break;
@@ -317,9 +495,15 @@ __global__ void add_diag_kernel(double* __restrict__ H, int n, const double* __r
 using namespace tnpy;
 
 extern "C" size_t tnpy_svd_workspace_bytes(int rows, int cols) {
-  const size_t n = rows < cols ? rows : cols, m = rows < cols ? cols : rows;
-  return Workspace::need(n * m) + Workspace::need(n * n) + Workspace::need(n) + Workspace::need(n, sizeof(int)) + 1024;
+  const int n = rows < cols ? rows : cols, m = rows < cols ? cols : rows;
+  size_t total = Workspace::need(n) + Workspace::need(n, sizeof(int)) + 1024;
+  if (fits_small(n, m)) return total + Workspace::need((size_t)n * m) + Workspace::need((size_t)n * n);
+  const BlockPlan p = block_plan(n, m);
+  return total + Workspace::need(p.gp_elems) + Workspace::need(p.partial_elems) + Workspace::need(p.jt_elems);
 }
+
+static int g_last_svd_sweeps = 0;
+extern "C" int tnpy_last_svd_sweeps(void) { return g_last_svd_sweeps; }
 
 extern "C" int tnpy_svd(double* A, int rows, int cols, double* U, double* s, double* Vt, void* workspace,
                         size_t workspace_bytes, void* stream_) {
@@ -328,29 +512,53 @@ extern "C" int tnpy_svd(double* A, int rows, int cols, double* U, double* s, dou
   const bool tall = rows >= cols;
   const int n = tall ? cols : rows, m = tall ? rows : cols;
   Workspace ws(workspace, workspace_bytes);
-  double* Gt = ws.take<double>((size_t)n * m);
-  double* P = ws.take<double>((size_t)n * n);
   double* norms = ws.take<double>(n);
   int* rank = ws.take<int>(n);
   unsigned int* counter = ws.take<unsigned int>(64);
-  if (!Gt || !P || !norms || !rank || !counter) {
-    set_error("tnpy_svd: workspace too small");
-    return TNPY_EWORKSPACE;
+  const double* G = nullptr;
+  const double* P = nullptr;
+  int64_t ldg = m, ldp = n;
+  if (fits_small(n, m)) {
+    double* Gt = ws.take<double>((size_t)n * m);
+    double* Pm = ws.take<double>((size_t)n * n);
+    if (!norms || !rank || !counter || !Gt || !Pm) {
+      set_error("tnpy_svd: workspace too small");
+      return TNPY_EWORKSPACE;
+    }
+    double* Gm = A;
+    if (tall) {
+      TNPY_TRY(transpose2d(A, rows, cols, Gt, nullptr, stream));
+      Gm = Gt;
+    }
+    TNPY_TRY(hestenes_small(Gm, n, m, Pm, stream));
+    G = Gm;
+    P = Pm;
+    g_last_svd_sweeps = -1;
+  } else {
+    const BlockPlan p = block_plan(n, m);
+    double* GP = ws.take<double>(p.gp_elems);
+    double* partial = ws.take<double>(p.partial_elems);
+    double* Jt = ws.take<double>(p.jt_elems);
+    if (!norms || !rank || !counter || !GP || !partial || !Jt) {
+      set_error("tnpy_svd: workspace too small");
+      return TNPY_EWORKSPACE;
+    }
+    jb_init_kernel<<<sm_count() * 8, 256, 0, stream>>>(A, rows, cols, tall ? 1 : 0, GP, n, m, p.n_pad, p.ld);
+    TNPY_LAUNCH_OK();
+    TNPY_TRY(hestenes_block(GP, p, m, partial, Jt, counter, stream, &g_last_svd_sweeps));
+    G = GP;
+    P = GP + m;
+    ldg = p.ld;
+    ldp = p.ld;
   }
-  double* G = A;
-  if (tall) {
-    TNPY_TRY(transpose2d(A, rows, cols, Gt, nullptr, stream));
-    G = Gt;
-  }
-  TNPY_TRY(hestenes(G, n, m, m, P, counter, stream, nullptr));
-  row_norm_kernel<<<n, 256, 0, stream>>>(G, n, m, m, norms);
+  row_norm_kernel<<<n, 256, 0, stream>>>(G, n, m, ldg, norms);
   TNPY_LAUNCH_OK();
   rank_kernel<<<ceil_div(n, 128), 128, 0, stream>>>(norms, n, rank, s);
   TNPY_LAUNCH_OK();
   if (tall)  // U = W^T (rows x n): U[i][r] ; Vt = P (n x cols): Vt[r][j]
-    scatter_kernel<<<n, 256, 0, stream>>>(G, n, m, m, P, norms, rank, U, 1, n, Vt, cols, 1);
-  else       // Vt = W (n x cols): Vt[r][i] ; U = P^T (rows x n): U[j][r]
-    scatter_kernel<<<n, 256, 0, stream>>>(G, n, m, m, P, norms, rank, Vt, cols, 1, U, 1, n);
+    scatter_kernel<<<n, 256, 0, stream>>>(G, n, m, ldg, P, ldp, norms, rank, U, 1, n, Vt, cols, 1);
+  else  // Vt = W (n x cols): Vt[r][i] ; U = P^T (rows x n): U[j][r]
+    scatter_kernel<<<n, 256, 0, stream>>>(G, n, m, ldg, P, ldp, norms, rank, Vt, cols, 1, U, 1, n);
   TNPY_LAUNCH_OK();
   return TNPY_OK;
 }
