@@ -16,7 +16,7 @@ for rows, cols, kind in ((120, 60, "rand"), (512, 256, "rand"), (2048, 1024, "ra
     if kind == "near":  # nearly orthogonal columns, as in late DMRG sweeps
         q, _ = torch.linalg.qr(a)
         a = q * torch.logspace(0, -10, cols, dtype=torch.float64, device="cuda")[None, :]
-        a = a + 1e-6 * torch.randn((rows, cols), generator=g, dtype=torch.float64, device="cuda") * a.abs().mean()
+        a = (a + 1e-6 * torch.randn((rows, cols), generator=g, dtype=torch.float64, device="cuda") * a.abs().mean()).contiguous()
     _cuda.svd(a.clone())
     torch.cuda.synchronize()
     t0 = time.perf_counter()

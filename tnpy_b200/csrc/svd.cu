@@ -147,6 +147,16 @@ __global__ void __launch_bounds__(256) jb_init_kernel(const double* __restrict__
   }
 }
 
+// block pair of CTA `i` in `round` (round -1: adjacent blocks)
+__device__ __forceinline__ void block_pair(int round, int i, int nb, int& I, int& J) {
+  if (round < 0) {
+    I = 2 * i;
+    J = 2 * i + 1;
+  } else {
+    rr_pair(round, i, nb, I, J);
+  }
+}
+
 __device__ __forceinline__ int panel_row(int I, int J, int r) { return r < kJB ? I * kJB + r : J * kJB + (r - kJB); }
 
 // Load a kJP x kJCH chunk of the panel (columns [c0, c0 + kJCH) clipped to c_end) into shared memory.
@@ -168,7 +178,7 @@ __global__ void __launch_bounds__(256) jb_gram_kernel(const double* __restrict__
   extern __shared__ double sm[];
   double* panel = sm;
   int I, J;
-  rr_pair(round, blockIdx.x, nb, I, J);
+  block_pair(round, blockIdx.x, nb, I, J);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int c_begin = blockIdx.y * kJGramCols, c_end = min(m, c_begin + kJGramCols);
   double acc[8][2];
@@ -191,18 +201,22 @@ __global__ void __launch_bounds__(256) jb_gram_kernel(const double* __restrict__
     *reinterpret_cast<double2*>(out + (8 * warp + g) * kJP + 8 * j + 2 * t) = make_double2(acc[j][0], acc[j][1]);
 }
 
-__global__ void __launch_bounds__(256) jb_rotate_kernel(const double* __restrict__ partial, int gchunks, double tol,
-                                                        int inner_sweeps, double* __restrict__ Jt,
-                                                        unsigned int* __restrict__ rot_count) {
+// cross_only: rotate only (row of block I, row of block J) pairs -- 32 inner rounds instead of 63; the
+// first round of every sweep pairs blocks (0,1),(2,3),... with the full 64x64 sweep so every block is
+// also orthogonalised internally once per sweep.
+__global__ void __launch_bounds__(512) jb_rotate_kernel(const double* __restrict__ partial, int gchunks, double tol,
+                                                        int cross_only, double* __restrict__ Jt,
+                                                        unsigned int* __restrict__ rot_count,
+                                                        int* __restrict__ skip) {
   extern __shared__ double sm[];
   double(*a)[kJP + 1] = reinterpret_cast<double(*)[kJP + 1]>(sm);
   double(*z)[kJP + 1] = reinterpret_cast<double(*)[kJP + 1]>(sm + kJP * (kJP + 1));
   __shared__ double cs[kJB], sn[kJB];
   __shared__ int pp[kJB], qq[kJB];
-  __shared__ int significant;
+  __shared__ int significant, significant_all;
   const int tid = threadIdx.x, nt = blockDim.x;
   const double* src = partial + (int64_t)blockIdx.x * gchunks * (kJP * kJP);
-  if (tid == 0) significant = 0;
+  if (tid == 0) significant = significant_all = 0;
   for (int idx = tid; idx < kJP * kJP; idx += nt) {
     double v = 0.0;
     for (int c = 0; c < gchunks; ++c) v += src[(int64_t)c * (kJP * kJP) + idx];  // fixed order: deterministic
@@ -211,27 +225,35 @@ __global__ void __launch_bounds__(256) jb_rotate_kernel(const double* __restrict
   }
   __syncthreads();
   // convergence bookkeeping on the freshly formed Gram matrix
-  int mine = 0;
+  int mine = 0, mine_all = 0;
   for (int idx = tid; idx < kJP * kJP; idx += nt) {
     const int p = idx / kJP, q = idx % kJP;
-    if (p < q && fabs(a[p][q]) > tol * sqrt(a[p][p] * a[q][q])) ++mine;
+    if (p < q && fabs(a[p][q]) > tol * sqrt(a[p][p] * a[q][q])) {
+      ++mine_all;
+      if (!cross_only || (p < kJB && q >= kJB)) ++mine;  // pairs this round is going to rotate (p < kJB <= q)
+    }
   }
   if (mine) atomicAdd(&significant, mine);
+  if (mine_all) atomicAdd(&significant_all, mine_all);
   __syncthreads();
   const int nsig = significant;
-  if (nsig == 0) {
-    // already orthogonal: identity rotation
-    for (int idx = tid; idx < kJP * kJP; idx += nt)
-      Jt[(int64_t)blockIdx.x * kJP * kJP + idx] = (idx / kJP == idx % kJP) ? 1.0 : 0.0;
-    return;
+  if (tid == 0) {
+    skip[blockIdx.x] = (nsig == 0);
+    if (significant_all) atomicAdd(rot_count, (unsigned int)significant_all);  // drives the sweep loop
   }
-  if (tid == 0) atomicAdd(rot_count, (unsigned int)nsig);
+  if (nsig == 0) return;  // nothing to rotate here: jb_apply skips this panel
   constexpr int half = kJP / 2;
-  for (int sweep = 0; sweep < inner_sweeps; ++sweep) {
-    for (int round = 0; round < kJP - 1; ++round) {
+  {
+    const int inner_rounds = cross_only ? kJB : kJP - 1;
+    for (int round = 0; round < inner_rounds; ++round) {
       if (tid < half) {
         int p, q;
-        rr_pair(round, tid, kJP, p, q);
+        if (cross_only) {
+          p = tid;
+          q = kJB + ((tid + round) & (kJB - 1));
+        } else {
+          rr_pair(round, tid, kJP, p, q);
+        }
         double c = 1.0, s = 0.0;
         const double apq = a[p][q], app = a[p][p], aqq = a[q][q];
         if (fabs(apq) > tol * sqrt(app * aqq) && apq != 0.0) {
@@ -278,12 +300,13 @@ __global__ void __launch_bounds__(256) jb_rotate_kernel(const double* __restrict
 }
 
 __global__ void __launch_bounds__(256) jb_apply_kernel(double* __restrict__ GP, int64_t ld, int width, int nb, int round,
-                                                       const double* __restrict__ Jt) {
+                                                       const double* __restrict__ Jt, const int* __restrict__ skip) {
   extern __shared__ double sm[];
+  if (skip[blockIdx.x]) return;
   double* jt = sm;                  // kJP x kJTS
   double* panel = sm + kJP * kJTS;  // kJP x kJST
   int I, J;
-  rr_pair(round, blockIdx.x, nb, I, J);
+  block_pair(round, blockIdx.x, nb, I, J);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int c0 = blockIdx.y * kJCH, c_end = min(width, c0 + kJCH);
   const double* jsrc = Jt + (int64_t)blockIdx.x * kJP * kJP;
@@ -439,8 +462,8 @@ static BlockPlan block_plan(int n, int m) {
 }
 
 // large path: GP = [G | P] (n_pad x ld) in place
-static int hestenes_block(double* GP, const BlockPlan& p, int m, double* partial, double* Jt, unsigned int* counter_dev,
-                          cudaStream_t stream, int* sweeps_out) {
+static int hestenes_block(double* GP, const BlockPlan& p, int m, double* partial, double* Jt, int* skip,
+                          unsigned int* counter_dev, cudaStream_t stream, int* sweeps_out) {
   static PinnedWord pinned;
   if (!pinned.host) {
     set_error("hestenes: pinned allocation failed");
@@ -462,13 +485,15 @@ static int hestenes_block(double* GP, const BlockPlan& p, int m, double* partial
   int sweep = 0;
   for (; sweep < max_sweeps; ++sweep) {
     TNPY_CUDA_OK(cudaMemsetAsync(counter_dev, 0, sizeof(unsigned int), stream));
-    for (int round = 0; round < p.nb - 1; ++round) {
+    for (int round = -1; round < p.nb - 1; ++round) {
+      // round -1: blocks (0,1),(2,3),... with the full 64x64 inner sweep (intra-block pairs included);
+      // rounds 0..nb-2: round-robin block pairs, cross pairs only.
       jb_gram_kernel<<<dim3(p.pairs, p.gchunks), 256, gram_smem, stream>>>(GP, p.ld, m, p.nb, round, p.gchunks, partial);
-      jb_rotate_kernel<<<p.pairs, 256, rot_smem, stream>>>(partial, p.gchunks, tol, 1, Jt, counter_dev);
-      jb_apply_kernel<<<dim3(p.pairs, p.achunks), 256, apply_smem, stream>>>(GP, p.ld, width, p.nb, round, Jt);
+      jb_rotate_kernel<<<p.pairs, 512, rot_smem, stream>>>(partial, p.gchunks, tol, round >= 0 ? 1 : 0, Jt, counter_dev, skip);
+      jb_apply_kernel<<<dim3(p.pairs, p.achunks), 256, apply_smem, stream>>>(GP, p.ld, width, p.nb, round, Jt, skip);
     }
     TNPY_LAUNCH_OK();
-    count_launch(3 * (p.nb - 1) - 1);
+    count_launch(3 * p.nb - 1);
     TNPY_CUDA_OK(cudaMemcpyAsync(pinned.host, counter_dev, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
     TNPY_CUDA_OK(cudaStreamSynchronize(stream));
     if (*pinned.host == 0u) break;
@@ -499,7 +524,8 @@ extern "C" size_t tnpy_svd_workspace_bytes(int rows, int cols) {
   size_t total = Workspace::need(n) + Workspace::need(n, sizeof(int)) + 1024;
   if (fits_small(n, m)) return total + Workspace::need((size_t)n * m) + Workspace::need((size_t)n * n);
   const BlockPlan p = block_plan(n, m);
-  return total + Workspace::need(p.gp_elems) + Workspace::need(p.partial_elems) + Workspace::need(p.jt_elems);
+  return total + Workspace::need(p.gp_elems) + Workspace::need(p.partial_elems) + Workspace::need(p.jt_elems) +
+         Workspace::need(p.pairs, sizeof(int));
 }
 
 static int g_last_svd_sweeps = 0;
@@ -545,7 +571,12 @@ extern "C" int tnpy_svd(double* A, int rows, int cols, double* U, double* s, dou
     }
     jb_init_kernel<<<sm_count() * 8, 256, 0, stream>>>(A, rows, cols, tall ? 1 : 0, GP, n, m, p.n_pad, p.ld);
     TNPY_LAUNCH_OK();
-    TNPY_TRY(hestenes_block(GP, p, m, partial, Jt, counter, stream, &g_last_svd_sweeps));
+    int* skip = ws.take<int>(p.pairs);
+    if (!skip) {
+      set_error("tnpy_svd: workspace too small");
+      return TNPY_EWORKSPACE;
+    }
+    TNPY_TRY(hestenes_block(GP, p, m, partial, Jt, skip, counter, stream, &g_last_svd_sweeps));
     G = GP;
     P = GP + m;
     ldg = p.ld;
