@@ -26,8 +26,12 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
+
+# torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm (--impl reference, rank 0 only) has to
+# use all host cores, and OpenBLAS sizes its pool when NumPy is first imported.
+if "reference" in sys.argv and os.environ.get("OMP_NUM_THREADS") == "1":
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
 
 import numpy as np
 
@@ -129,9 +133,29 @@ def random_right_canonical_device(n, chi, d, seed):
 
 
 # ---------------------------------------------------------------------------------------------------
+def all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm must use every host core it can."""
+    try:
+        from threadpoolctl import threadpool_limits
+
+        return threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        from contextlib import nullcontext
+
+        return nullcontext()
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU algorithm for this step (NumPy restatement in
     oracle/ -- quimb/primme are not installable here) on the box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    with all_host_threads():
+        return _run_reference(args)
+
+
+def _run_reference(args):
     from oracle import tnpy_oracle as oracle
 
     rank = int(os.environ.get("RANK", "0"))
@@ -175,6 +199,11 @@ def workload_name(n_gpus, chi):
 
 def cpu_baseline(chi, budget_s=20.0):
     """Oracle matvec on the host cores, bounded sample (same shapes when they fit the budget)."""
+    with all_host_threads():
+        return _cpu_baseline(chi, budget_s)
+
+
+def _cpu_baseline(chi, budget_s):
     from oracle import tnpy_oracle as oracle
 
     w, d = 5, 2

@@ -306,9 +306,11 @@ def heff_apply(L: Optional[np.ndarray], W: np.ndarray, R: Optional[np.ndarray], 
     if R is None:
         t = np.tensordot(L, x, axes=(0, 0))  # (a, m, p)
         return np.einsum("apq,amp->mq", W, t)
+    # three pairwise tensordots (transpose-copy + dgemm each), the lowering opt_einsum gives quimb
     t1 = np.tensordot(L, x, axes=(0, 0))  # (a, m, p, r)
-    t2 = np.einsum("abpq,ampr->bmqr", W, t1, optimize=True)
-    return np.einsum("bmqr,rbs->mqs", t2, R, optimize=True)
+    t2 = np.tensordot(W, t1, axes=((0, 2), (0, 2)))  # (b, q, m, r)
+    y = np.tensordot(t2, R, axes=((0, 3), (1, 0)))  # (q, m, s)
+    return np.ascontiguousarray(np.transpose(y, (1, 0, 2)))
 
 
 def env_update_left(L: Optional[np.ndarray], A: np.ndarray, W: np.ndarray) -> np.ndarray:
