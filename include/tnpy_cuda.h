@@ -153,6 +153,8 @@ int tnpy_eigh_lowest(double* H, int n, double* eval_dev, double* evec, void* wor
 size_t tnpy_svd_workspace_bytes(int rows, int cols);
 /* Jacobi sweeps the last tnpy_svd call on this process needed (-1: single-CTA shared-memory path). */
 int tnpy_last_svd_sweeps(void);
+/* Significant (not yet orthogonal) pair counts per Jacobi sweep of that call; returns how many were written. */
+int tnpy_last_svd_trace(unsigned int* counts, int max_counts);
 int tnpy_svd(double* A, int rows, int cols, double* U, double* s, double* Vt, void* workspace,
              size_t workspace_bytes, void* stream);
 

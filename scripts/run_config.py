@@ -40,16 +40,30 @@ def main():
     if args.config == 1:
         n, chi = args.n or 100, args.chi or 60
         mdl = models.XXZ(n=n, delta=0.5)
-    else:
+    elif args.config == 2:
         n, chi = args.n or 100, args.chi or 256
         mdl = models.Thirring(n=n, delta=0.5, ma=1.0, penalty=100.0, s_target=0)
-    init = oracle.random_mps(n, chi, 2, seed=args.seed)
+    else:  # 3: XXZ n=100 chi=2048 (the roofline configuration); device-born synthetic start
+        n, chi = args.n or 100, args.chi or 2048
+        mdl = models.XXZ(n=n, delta=0.5)
+    if args.config == 3:
+        from bench import random_right_canonical_device
+
+        init = None
+        device_init = random_right_canonical_device(n, chi, 2, seed=args.seed)
+    else:
+        init = oracle.random_mps(n, chi, 2, seed=args.seed)
     kw = dict(tol=args.tol)
     if args.sweeps:
         kw.update(tol=args.tol, max_sweep=args.sweeps)
     out = {"config": args.config, "n": n, "chi": chi, "tol": args.tol}
 
-    gpu = FiniteDMRG(mdl.mpo, bond_dim=chi, mps=MatrixProductState([a.copy() for a in init]))
+    if init is None:
+        gpu = FiniteDMRG(mdl.mpo, bond_dim=chi, mps=device_init, compute_variance=False)
+        del device_init
+    else:
+        gpu = FiniteDMRG(mdl.mpo, bond_dim=chi, mps=MatrixProductState([a.copy() for a in init]))
+    gpu.phase_seconds = {}
     torch.cuda.synchronize()
     l0 = _cuda.launch_count()
     t0 = time.perf_counter()
@@ -64,6 +78,8 @@ def main():
             e_gpu.append(gpu.sweep(direction, tol=args.tol))
             torch.cuda.synchronize()
             per_sweep.append(time.perf_counter() - t)
+            out.setdefault("gpu_matvecs_per_sweep", []).append(sum(s.get("n_matvec", 0) for s in gpu.solver_stats))
+            out.setdefault("gpu_phase_s_cumulative", []).append(dict(gpu.phase_seconds))
         out["gpu_sweep_s"] = per_sweep
         out["gpu_matvecs_last_sweep"] = sum(s.get("n_matvec", 0) for s in gpu.solver_stats)
     else:

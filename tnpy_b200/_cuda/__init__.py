@@ -52,6 +52,7 @@ SIGNATURES = {
     "tnpy_eigh_lowest": (c_int, [_PD, c_int, _PD, _PD, c_void_p, c_size_t, c_void_p]),
     "tnpy_svd_workspace_bytes": (c_size_t, [c_int, c_int]),
     "tnpy_last_svd_sweeps": (c_int, []),
+    "tnpy_last_svd_trace": (c_int, [ctypes.POINTER(ctypes.c_uint), c_int]),
     "tnpy_svd": (c_int, [_PD, c_int, c_int, _PD, _PD, _PD, c_void_p, c_size_t, c_void_p]),
     "tnpy_absorb_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "tnpy_absorb_right": (c_int, [_PD, _PD, c_int, c_int, _PD, c_int, _PD, c_void_p, c_size_t, c_void_p]),

@@ -418,6 +418,10 @@ __global__ void colscale_kernel(const double* __restrict__ in, const double* __r
     out[e] = in[e] * s[e % cols];
 }
 
+// significant-pair count seen in each Jacobi sweep of the last block-path SVD (diagnostics)
+static unsigned int g_trace[64];
+static int g_trace_len = 0;
+
 struct PinnedWord {
   unsigned int* host = nullptr;
   PinnedWord() { cudaMallocHost(&host, 64); }
@@ -496,6 +500,10 @@ static int hestenes_block(double* GP, const BlockPlan& p, int m, double* partial
     count_launch(3 * p.nb - 1);
     TNPY_CUDA_OK(cudaMemcpyAsync(pinned.host, counter_dev, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
     TNPY_CUDA_OK(cudaStreamSynchronize(stream));
+    if (sweep < 64) {
+      g_trace[sweep] = *pinned.host;
+      g_trace_len = sweep + 1;
+    }
     if (*pinned.host == 0u) break;
   }
   if (sweeps_out) *sweeps_out = sweep;
@@ -530,6 +538,11 @@ extern "C" size_t tnpy_svd_workspace_bytes(int rows, int cols) {
 
 static int g_last_svd_sweeps = 0;
 extern "C" int tnpy_last_svd_sweeps(void) { return g_last_svd_sweeps; }
+extern "C" int tnpy_last_svd_trace(unsigned int* counts, int max_counts) {
+  int n = 0;
+  for (; n < tnpy::g_trace_len && n < max_counts; ++n) counts[n] = tnpy::g_trace[n];
+  return n;
+}
 
 extern "C" int tnpy_svd(double* A, int rows, int cols, double* U, double* s, double* Vt, void* workspace,
                         size_t workspace_bytes, void* stream_) {

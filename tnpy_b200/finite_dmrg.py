@@ -64,6 +64,8 @@ class FiniteDMRG:
         self._energies: List[float] = [np.nan]
         self._variances: List[float] = [np.nan]
         self.solver_stats: List[Dict] = []  # one record per local solve of the last sweep
+        #: set to a dict to collect synchronised per-phase wall seconds of the sweeps (benchmarking aid)
+        self.phase_seconds: Optional[Dict[str, float]] = None
 
     # -- properties ---------------------------------------------------------------------------------
     bond_dim = property(lambda self: self._bond_dim)
@@ -132,13 +134,34 @@ class FiniteDMRG:
         sites = range(self.n_sites - 1) if direction == Direction.RIGHTWARD else range(self.n_sites - 1, 0, -1)
         energy = None
         self.solver_stats = []
+        tick = self._phase_timer()
         for site in sites:
             energy = self._solve_on_device(site, tol, **kwargs)
+            tick("eigensolve")
             logger.info(f"Sweeping to site [{site + 1}/{self.n_sites}], E0 = {energy}")
             self.perturb_wave_function(site)
+            tick("perturb")
             self._env.split_tensor(site, direction=direction)
+            tick("svd_split")
             self._env.update(site, direction=direction)
+            tick("env_update")
         return energy
+
+    def _phase_timer(self):
+        if self.phase_seconds is None:
+            return lambda name: None
+        import torch
+
+        torch.cuda.synchronize()
+        last = [time.perf_counter()]
+
+        def tick(name: str):
+            torch.cuda.synchronize()
+            now = time.perf_counter()
+            self.phase_seconds[name] = self.phase_seconds.get(name, 0.0) + now - last[0]
+            last[0] = now
+
+        return tick
 
     def _converged(self, n_sweep: int, tol: float, max_sweep: int, metric: Metric) -> bool:
         series = self._variances if metric == Metric.VARIANCE else self._energies
