@@ -1,0 +1,76 @@
+"""BASELINE configs[3]: random-disorder Heisenberg, a batch of disorder realisations over the GPUs of
+one box -- replicas only (one process per GPU, no collective on the data path).
+
+    torchrun --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 scripts/run_disorder_batch.py \
+        --n 64 --chi 1024 --realisations 64 --sweeps 2
+    python scripts/run_disorder_batch.py --n 16 --chi 32 --realisations 4        # single GPU
+"""
+import argparse
+import json
+import logging
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=64)
+    ap.add_argument("--chi", type=int, default=1024)
+    ap.add_argument("--h", type=float, default=1.0)
+    ap.add_argument("--realisations", type=int, default=64)
+    ap.add_argument("--sweeps", type=int, default=2)
+    ap.add_argument("--tol", type=float, default=1e-8)
+    args = ap.parse_args()
+
+    import torch
+    import torch.distributed as dist
+
+    from tnpy_b200.finite_dmrg import FiniteDMRG
+    from tnpy_b200.matrix_product_state import Direction
+    from tnpy_b200.model import RandomHeisenberg
+    from tnpy_b200.parallel import assign_realisations
+
+    logging.getLogger("tnpy").setLevel(logging.WARNING)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    mine = assign_realisations(args.realisations, world, rank)
+    results = {}
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for seed in mine:
+        model = RandomHeisenberg(n=args.n, h=args.h, seed=seed)
+        dmrg = FiniteDMRG(model.mpo, bond_dim=args.chi, seed=seed, compute_variance=False)
+        energy = None
+        for k in range(args.sweeps):
+            energy = dmrg.sweep(Direction.RIGHTWARD if k % 2 == 0 else Direction.LEFTWARD, tol=args.tol)
+        results[seed] = energy
+    torch.cuda.synchronize()
+    elapsed = time.perf_counter() - t0
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (results, elapsed))  # the only communication: final gather
+        dist.destroy_process_group()
+    else:
+        gathered = [(results, elapsed)]
+    if rank == 0:
+        energies = {}
+        for res, _ in gathered:
+            energies.update(res)
+        wall = max(t for _, t in gathered)
+        print(json.dumps({
+            "config": "RandomHeisenberg n=%d chi=%d h=%g, %d realisations on %d GPU(s), %d sweeps each" % (
+                args.n, args.chi, args.h, args.realisations, world, args.sweeps),
+            "wall_s": wall, "realisations_per_s": args.realisations / wall,
+            "energies": [energies[s] for s in sorted(energies)],
+        }), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -10,7 +10,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from oracle import tnpy_oracle as oracle
-from tnpy_b200.parallel import all_row_blocks, row_block
+from tnpy_b200.parallel import all_row_blocks, assign_realisations, row_block
 
 
 @pytest.mark.parametrize("chi,world", [(8, 2), (60, 8), (2048, 8), (8192, 4), (7, 2), (10, 3), (3, 4)])
@@ -77,3 +77,16 @@ def test_sharded_matvec_gloo(world, chi):
     for rank, err, dot, dot_ref in results:
         assert err < 1e-13
         assert abs(dot - dot_ref) < 1e-10 * abs(dot_ref)
+
+
+def test_realisations_partition():
+    """configs[3]: 64 disorder realisations over 8 GPUs -- every seed exactly once, 8 per rank."""
+    seen = []
+    for rank in range(8):
+        mine = assign_realisations(64, 8, rank)
+        assert len(mine) == 8
+        seen += mine
+    assert sorted(seen) == list(range(64))
+    assert assign_realisations(5, 2, 1) == [1, 3]
+    with pytest.raises(ValueError):
+        assign_realisations(4, 2, 2)

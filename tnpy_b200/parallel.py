@@ -68,3 +68,11 @@ def sharded_dot(a_rows, b_rows, group=None):
     part = (a_rows * b_rows).sum().reshape(1)
     dist.all_reduce(part, op=dist.ReduceOp.SUM, group=group)
     return part[0]
+
+
+def assign_realisations(n_realisations: int, world: int, rank: int) -> List[int]:
+    """Disorder batches (BASELINE configs[3]) are replicas only: realisation s runs on rank s % world,
+    no collective on the data path; results are gathered once at the end."""
+    if not 0 <= rank < world:
+        raise ValueError(f"rank {rank} outside world of {world}")
+    return list(range(rank, n_realisations, world))
