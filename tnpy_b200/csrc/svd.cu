@@ -124,6 +124,7 @@ constexpr int kJCH = 128;           // columns per shared-memory chunk
 constexpr int kJST = kJCH + 4;      // panel row stride in shared memory (conflict-free DMMA fragments)
 constexpr int kJTS = kJP + 4;       // rotation-matrix row stride in shared memory
 constexpr int kJGramCols = 512;     // columns of G per jb_gram CTA
+constexpr double kClusterTheta = 1e-6;  // vectors below theta * max norm form the phase-2 cluster
 
 __device__ __forceinline__ void dmma884_(double& c0, double& c1, double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -132,29 +133,83 @@ __device__ __forceinline__ void dmma884_(double& c0, double& c1, double a, doubl
 }
 
 // GP = [G | P] (n_pad x ld): G from A (transposed when `tall`), P = identity, padding rows zero.
+// Row k of GP holds source vector src[k] (vectors sorted by decreasing norm: src = inverse of rank),
+// and P starts as the matching permutation matrix so that G_in = P^T G_out still holds.
 __global__ void __launch_bounds__(256) jb_init_kernel(const double* __restrict__ A, int rows, int cols, int tall,
-                                                      double* __restrict__ GP, int n, int m, int n_pad, int64_t ld) {
+                                                      const int* __restrict__ src, double* __restrict__ GP, int n,
+                                                      int m, int n_pad, int64_t ld) {
   const int64_t total = (int64_t)n_pad * ld;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int k = (int)(e / ld), c = (int)(e % ld);
     double v = 0.0;
-    if (c < m) {
-      if (k < n) v = tall ? A[(int64_t)c * cols + k] : A[(int64_t)k * cols + c];
-    } else if (c - m == k) {
-      v = 1.0;
+    if (k < n) {
+      const int o = src[k];
+      if (c < m) v = tall ? A[(int64_t)c * cols + o] : A[(int64_t)o * cols + c];
+      else if (c - m == o) v = 1.0;
     }
     GP[e] = v;
   }
 }
 
-// block pair of CTA `i` in `round` (round -1: adjacent blocks)
-__device__ __forceinline__ void block_pair(int round, int i, int nb, int& I, int& J) {
+// norms of the vectors of A that the SVD orthogonalises: columns when `tall`, rows otherwise
+__global__ void __launch_bounds__(256) vec_norm_kernel(const double* __restrict__ A, int rows, int cols, int tall,
+                                                       double* __restrict__ norms) {
+  if (tall) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= cols) return;
+    double a = 0.0;
+    for (int i = 0; i < rows; ++i) {
+      const double x = A[(int64_t)i * cols + k];
+      a = fma(x, x, a);
+    }
+    norms[k] = sqrt(a);
+  } else {
+    __shared__ double sh[32];
+    for (int k = blockIdx.x; k < rows; k += gridDim.x) {
+      double a = 0.0;
+      for (int i = threadIdx.x; i < cols; i += blockDim.x) {
+        const double x = A[(int64_t)k * cols + i];
+        a = fma(x, x, a);
+      }
+      a = block_sum(a, sh);
+      if (threadIdx.x == 0) norms[k] = sqrt(a);
+    }
+  }
+}
+
+// src[rank[k]] = k;  n_big = number of vectors with norm >= theta * max norm (written to info[0])
+__global__ void invert_rank_kernel(const int* __restrict__ rank, const double* __restrict__ sorted, int n, double theta,
+                                   int* __restrict__ src, int* __restrict__ info) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) {
+    src[rank[k]] = k;
+    const double cut = theta * sorted[0];
+    if (sorted[k] >= cut && (k == n - 1 || sorted[k + 1] < cut)) info[0] = k + 1;
+    if (k == 0 && !(sorted[0] >= cut)) info[0] = 0;
+  }
+}
+
+// Which blocks take part and which pairs matter in the current phase of the two-phase schedule:
+//   phase 1: all nb blocks, but panels made of two "small" blocks (index >= nbig) are skipped and only
+//            pairs touching a big block count -- the well-separated part converges in a few sweeps;
+//   phase 2: only the blocks [b0, b0 + nb) (the cluster of tiny, noise-dominated vectors), every pair.
+struct JbPhase {
+  int b0;    // first block of the round-robin
+  int nb;    // number of blocks in the round-robin (even)
+  int nbig;  // blocks with absolute index >= nbig are "small"
+};
+
+// block pair of CTA `i` in `round` (round -1: adjacent blocks); false when the panel is skipped
+__device__ __forceinline__ bool block_pair(int round, int i, const JbPhase& ph, int& I, int& J) {
   if (round < 0) {
     I = 2 * i;
     J = 2 * i + 1;
   } else {
-    rr_pair(round, i, nb, I, J);
+    rr_pair(round, i, ph.nb, I, J);
   }
+  I += ph.b0;
+  J += ph.b0;
+  return !(I >= ph.nbig && J >= ph.nbig);
 }
 
 __device__ __forceinline__ int panel_row(int I, int J, int r) { return r < kJB ? I * kJB + r : J * kJB + (r - kJB); }
@@ -173,12 +228,12 @@ __device__ __forceinline__ void load_panel(const double* __restrict__ GP, int64_
   }
 }
 
-__global__ void __launch_bounds__(256) jb_gram_kernel(const double* __restrict__ GP, int64_t ld, int m, int nb,
+__global__ void __launch_bounds__(256) jb_gram_kernel(const double* __restrict__ GP, int64_t ld, int m, JbPhase ph,
                                                       int round, int gchunks, double* __restrict__ partial) {
   extern __shared__ double sm[];
   double* panel = sm;
   int I, J;
-  block_pair(round, blockIdx.x, nb, I, J);
+  if (!block_pair(round, blockIdx.x, ph, I, J)) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int c_begin = blockIdx.y * kJGramCols, c_end = min(m, c_begin + kJGramCols);
   double acc[8][2];
@@ -205,9 +260,16 @@ __global__ void __launch_bounds__(256) jb_gram_kernel(const double* __restrict__
 // first round of every sweep pairs blocks (0,1),(2,3),... with the full 64x64 sweep so every block is
 // also orthogonalised internally once per sweep.
 __global__ void __launch_bounds__(512) jb_rotate_kernel(const double* __restrict__ partial, int gchunks, double tol,
-                                                        int cross_only, double* __restrict__ Jt,
+                                                        int cross_only, JbPhase ph, int round,
+                                                        double* __restrict__ Jt,
                                                         unsigned int* __restrict__ rot_count,
                                                         int* __restrict__ skip) {
+  int I, J;
+  if (!block_pair(round, blockIdx.x, ph, I, J)) {
+    if (threadIdx.x == 0) skip[blockIdx.x] = 1;
+    return;
+  }
+  const bool i_big = I < ph.nbig, j_big = J < ph.nbig;
   extern __shared__ double sm[];
   double(*a)[kJP + 1] = reinterpret_cast<double(*)[kJP + 1]>(sm);
   double(*z)[kJP + 1] = reinterpret_cast<double(*)[kJP + 1]>(sm + kJP * (kJP + 1));
@@ -229,7 +291,8 @@ __global__ void __launch_bounds__(512) jb_rotate_kernel(const double* __restrict
   for (int idx = tid; idx < kJP * kJP; idx += nt) {
     const int p = idx / kJP, q = idx % kJP;
     if (p < q && fabs(a[p][q]) > tol * sqrt(a[p][p] * a[q][q])) {
-      ++mine_all;
+      const bool relevant = (p < kJB ? i_big : j_big) || (q < kJB ? i_big : j_big);
+      if (relevant) ++mine_all;  // drives the sweep loop of the current phase
       if (!cross_only || (p < kJB && q >= kJB)) ++mine;  // pairs this round is going to rotate (p < kJB <= q)
     }
   }
@@ -299,14 +362,15 @@ __global__ void __launch_bounds__(512) jb_rotate_kernel(const double* __restrict
   for (int idx = tid; idx < kJP * kJP; idx += nt) Jt[(int64_t)blockIdx.x * kJP * kJP + idx] = z[idx % kJP][idx / kJP];
 }
 
-__global__ void __launch_bounds__(256) jb_apply_kernel(double* __restrict__ GP, int64_t ld, int width, int nb, int round,
-                                                       const double* __restrict__ Jt, const int* __restrict__ skip) {
+__global__ void __launch_bounds__(256) jb_apply_kernel(double* __restrict__ GP, int64_t ld, int width, JbPhase ph,
+                                                       int round, const double* __restrict__ Jt,
+                                                       const int* __restrict__ skip) {
   extern __shared__ double sm[];
   if (skip[blockIdx.x]) return;
   double* jt = sm;                  // kJP x kJTS
   double* panel = sm + kJP * kJTS;  // kJP x kJST
   int I, J;
-  block_pair(round, blockIdx.x, nb, I, J);
+  block_pair(round, blockIdx.x, ph, I, J);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int c0 = blockIdx.y * kJCH, c_end = min(width, c0 + kJCH);
   const double* jsrc = Jt + (int64_t)blockIdx.x * kJP * kJP;
@@ -465,8 +529,9 @@ static BlockPlan block_plan(int n, int m) {
   return p;
 }
 
-// large path: GP = [G | P] (n_pad x ld) in place
-static int hestenes_block(double* GP, const BlockPlan& p, int m, double* partial, double* Jt, int* skip,
+// large path: GP = [G | P] (n_pad x ld) in place.  n_big = number of leading (largest-norm) vectors
+// outside the cluster of tiny vectors; see JbPhase.
+static int hestenes_block(double* GP, const BlockPlan& p, int m, int n_big, double* partial, double* Jt, int* skip,
                           unsigned int* counter_dev, cudaStream_t stream, int* sweeps_out) {
   static PinnedWord pinned;
   if (!pinned.host) {
@@ -486,25 +551,44 @@ static int hestenes_block(double* GP, const BlockPlan& p, int m, double* partial
   const double tol = jacobi_tol(m);
   const int width = m + p.n_pad;
   const int max_sweeps = 60;
+  // phase plan
+  int nb_big = (n_big + kJB - 1) / kJB;
+  if (nb_big < 1) nb_big = 1;
+  if (nb_big > p.nb) nb_big = p.nb;
+  const int nb_small = p.nb - nb_big;
+  JbPhase phases[2];
+  int n_phases = 1;
+  phases[0] = JbPhase{0, p.nb, nb_small >= 2 ? nb_big : (1 << 30)};
+  if (nb_small >= 2) {
+    int b0 = nb_big - (nb_small & 1);  // even number of blocks in the cluster round-robin
+    phases[1] = JbPhase{b0, p.nb - b0, 1 << 30};
+    n_phases = 2;
+  }
   int sweep = 0;
-  for (; sweep < max_sweeps; ++sweep) {
-    TNPY_CUDA_OK(cudaMemsetAsync(counter_dev, 0, sizeof(unsigned int), stream));
-    for (int round = -1; round < p.nb - 1; ++round) {
-      // round -1: blocks (0,1),(2,3),... with the full 64x64 inner sweep (intra-block pairs included);
-      // rounds 0..nb-2: round-robin block pairs, cross pairs only.
-      jb_gram_kernel<<<dim3(p.pairs, p.gchunks), 256, gram_smem, stream>>>(GP, p.ld, m, p.nb, round, p.gchunks, partial);
-      jb_rotate_kernel<<<p.pairs, 512, rot_smem, stream>>>(partial, p.gchunks, tol, round >= 0 ? 1 : 0, Jt, counter_dev, skip);
-      jb_apply_kernel<<<dim3(p.pairs, p.achunks), 256, apply_smem, stream>>>(GP, p.ld, width, p.nb, round, Jt, skip);
+  g_trace_len = 0;
+  for (int phase = 0; phase < n_phases; ++phase) {
+    const JbPhase ph = phases[phase];
+    const int pairs = ph.nb / 2;
+    for (; sweep < max_sweeps; ++sweep) {
+      TNPY_CUDA_OK(cudaMemsetAsync(counter_dev, 0, sizeof(unsigned int), stream));
+      for (int round = -1; round < ph.nb - 1; ++round) {
+        // round -1: adjacent blocks with the full 64x64 inner sweep (intra-block pairs included);
+        // rounds 0..nb-2: round-robin block pairs, cross pairs only.
+        jb_gram_kernel<<<dim3(pairs, p.gchunks), 256, gram_smem, stream>>>(GP, p.ld, m, ph, round, p.gchunks, partial);
+        jb_rotate_kernel<<<pairs, 512, rot_smem, stream>>>(partial, p.gchunks, tol, round >= 0 ? 1 : 0, ph, round, Jt,
+                                                          counter_dev, skip);
+        jb_apply_kernel<<<dim3(pairs, p.achunks), 256, apply_smem, stream>>>(GP, p.ld, width, ph, round, Jt, skip);
+      }
+      TNPY_LAUNCH_OK();
+      count_launch(3 * ph.nb - 1);
+      TNPY_CUDA_OK(cudaMemcpyAsync(pinned.host, counter_dev, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
+      TNPY_CUDA_OK(cudaStreamSynchronize(stream));
+      if (g_trace_len < 64) g_trace[g_trace_len++] = *pinned.host | (phase ? 0x80000000u : 0u);
+      if (*pinned.host == 0u) {
+        ++sweep;
+        break;
+      }
     }
-    TNPY_LAUNCH_OK();
-    count_launch(3 * p.nb - 1);
-    TNPY_CUDA_OK(cudaMemcpyAsync(pinned.host, counter_dev, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
-    TNPY_CUDA_OK(cudaStreamSynchronize(stream));
-    if (sweep < 64) {
-      g_trace[sweep] = *pinned.host;
-      g_trace_len = sweep + 1;
-    }
-    if (*pinned.host == 0u) break;
   }
   if (sweeps_out) *sweeps_out = sweep;
   return TNPY_OK;
@@ -533,7 +617,7 @@ extern "C" size_t tnpy_svd_workspace_bytes(int rows, int cols) {
   if (fits_small(n, m)) return total + Workspace::need((size_t)n * m) + Workspace::need((size_t)n * n);
   const BlockPlan p = block_plan(n, m);
   return total + Workspace::need(p.gp_elems) + Workspace::need(p.partial_elems) + Workspace::need(p.jt_elems) +
-         Workspace::need(p.pairs, sizeof(int));
+         Workspace::need(p.pairs, sizeof(int)) + Workspace::need(n, sizeof(int)) + 512;
 }
 
 static int g_last_svd_sweeps = 0;
@@ -582,14 +666,27 @@ extern "C" int tnpy_svd(double* A, int rows, int cols, double* U, double* s, dou
       set_error("tnpy_svd: workspace too small");
       return TNPY_EWORKSPACE;
     }
-    jb_init_kernel<<<sm_count() * 8, 256, 0, stream>>>(A, rows, cols, tall ? 1 : 0, GP, n, m, p.n_pad, p.ld);
-    TNPY_LAUNCH_OK();
     int* skip = ws.take<int>(p.pairs);
-    if (!skip) {
+    int* src = ws.take<int>(n);
+    int* info = ws.take<int>(64);
+    if (!skip || !src || !info) {
       set_error("tnpy_svd: workspace too small");
       return TNPY_EWORKSPACE;
     }
-    TNPY_TRY(hestenes_block(GP, p, m, partial, Jt, skip, counter, stream, &g_last_svd_sweeps));
+    // sort the vectors by decreasing norm (de Rijk-style ordering) and find the cluster of tiny ones
+    vec_norm_kernel<<<tall ? ceil_div(cols, 256) : min(rows, sm_count() * 8), 256, 0, stream>>>(A, rows, cols,
+                                                                                             tall ? 1 : 0, norms);
+    TNPY_LAUNCH_OK();
+    rank_kernel<<<ceil_div(n, 128), 128, 0, stream>>>(norms, n, rank, s);
+    TNPY_LAUNCH_OK();
+    invert_rank_kernel<<<ceil_div(n, 128), 128, 0, stream>>>(rank, s, n, kClusterTheta, src, info);
+    TNPY_LAUNCH_OK();
+    int n_big = n;
+    TNPY_CUDA_OK(cudaMemcpyAsync(&n_big, info, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    TNPY_CUDA_OK(cudaStreamSynchronize(stream));
+    jb_init_kernel<<<sm_count() * 8, 256, 0, stream>>>(A, rows, cols, tall ? 1 : 0, src, GP, n, m, p.n_pad, p.ld);
+    TNPY_LAUNCH_OK();
+    TNPY_TRY(hestenes_block(GP, p, m, n_big, partial, Jt, skip, counter, stream, &g_last_svd_sweeps));
     G = GP;
     P = GP + m;
     ldg = p.ld;
