@@ -32,7 +32,7 @@ def traced(site, direction):
     dt = time.perf_counter() - t
     buf = (ctypes.c_uint * 64)()
     k = lib.tnpy_last_svd_trace(buf, 64)
-    records.append({"site": site, "ms": dt * 1e3, "sweeps": lib.tnpy_last_svd_sweeps(), "trace": [("p2:" if v & 0x80000000 else "") + str(v & 0x7FFFFFFF) for v in buf[:k]],
+    records.append({"site": site, "ms": dt * 1e3, "sweeps": lib.tnpy_last_svd_sweeps(), "trace": [("c:" if v & 0x80000000 else "") + str(v & 0x7FFFFFFF) for v in buf[:k]],
                     "s_min": float(s.min()), "s_max": float(s.max())})
     return s
 

@@ -124,7 +124,11 @@ constexpr int kJCH = 128;           // columns per shared-memory chunk
 constexpr int kJST = kJCH + 4;      // panel row stride in shared memory (conflict-free DMMA fragments)
 constexpr int kJTS = kJP + 4;       // rotation-matrix row stride in shared memory
 constexpr int kJGramCols = 512;     // columns of G per jb_gram CTA
-constexpr double kClusterTheta = 1e-6;  // vectors below theta * max norm form the phase-2 cluster
+// Vectors below theta * max norm would be orthogonalised among themselves first (cluster phase).
+// Measured on DMRG wave functions (scripts/svd_trace.py): the cluster phase converges, but the full
+// phase that follows still needs as many sweeps as without it, so the schedule is disabled (theta = 0
+// => single phase).  The norm-sorted placement of the vectors is kept.
+constexpr double kClusterTheta = 0.0;
 
 __device__ __forceinline__ void dmma884_(double& c0, double& c1, double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -556,14 +560,19 @@ static int hestenes_block(double* GP, const BlockPlan& p, int m, int n_big, doub
   if (nb_big < 1) nb_big = 1;
   if (nb_big > p.nb) nb_big = p.nb;
   const int nb_small = p.nb - nb_big;
+  // Two-phase schedule.  The tiny, noise-dominated vectors (norm < kClusterTheta * max) are far from
+  // mutually orthogonal and need the bulk of the Jacobi sweeps; they are orthogonalised among
+  // themselves first, at (cluster/n)^2 of the cost of a full sweep.  The full round-robin that follows
+  // then starts from two internally orthogonal groups and converges in a few sweeps.  (Skipping the
+  // cluster-cluster pairs in the full phase instead does NOT work: the non-orthogonal cluster couples
+  // the big-small eliminations and the iteration stalls -- measured.)
   JbPhase phases[2];
-  int n_phases = 1;
-  phases[0] = JbPhase{0, p.nb, nb_small >= 2 ? nb_big : (1 << 30)};
+  int n_phases = 0;
   if (nb_small >= 2) {
-    int b0 = nb_big - (nb_small & 1);  // even number of blocks in the cluster round-robin
-    phases[1] = JbPhase{b0, p.nb - b0, 1 << 30};
-    n_phases = 2;
+    const int b0 = nb_big - (nb_small & 1);  // even number of blocks in the cluster round-robin
+    phases[n_phases++] = JbPhase{b0, p.nb - b0, 1 << 30};
   }
+  phases[n_phases++] = JbPhase{0, p.nb, 1 << 30};
   int sweep = 0;
   g_trace_len = 0;
   for (int phase = 0; phase < n_phases; ++phase) {
@@ -583,7 +592,7 @@ static int hestenes_block(double* GP, const BlockPlan& p, int m, int n_big, doub
       count_launch(3 * ph.nb - 1);
       TNPY_CUDA_OK(cudaMemcpyAsync(pinned.host, counter_dev, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
       TNPY_CUDA_OK(cudaStreamSynchronize(stream));
-      if (g_trace_len < 64) g_trace[g_trace_len++] = *pinned.host | (phase ? 0x80000000u : 0u);
+      if (g_trace_len < 64) g_trace[g_trace_len++] = *pinned.host | (ph.nb < p.nb ? 0x80000000u : 0u);
       if (*pinned.host == 0u) {
         ++sweep;
         break;
