@@ -281,6 +281,22 @@ def run_single(args):
     dt = cuda_time(step, args.steps, sync)
     launches = _cuda.launch_count() - launches0
 
+    # the same step in the gauge the sweep actually runs in: mixed-canonical MPS => L[:,0,:] = R[:,w-1,:] = I,
+    # the library replaces those two channel slices of the GEMMs by transposes (executed flops (w-1)/w)
+    Lc = L.clone()
+    Lc[:, 0, :] = torch.eye(l, dtype=torch.float64, device="cuda")
+    Rc = R.clone()
+    Rc[:, wr - 1, :] = torch.eye(r, dtype=torch.float64, device="cuda")
+    both = _cuda.LEFT_IDENTITY | _cuda.RIGHT_IDENTITY
+    step_c = lambda: _cuda.heff_apply(Lc, W, Rc, x, y, flags=both)  # noqa: E731
+    y_ref = _cuda.heff_apply(Lc, W, Rc, x).clone()
+    for _ in range(args.warmup):
+        step_c()
+    dt_c = cuda_time(step_c, args.steps, sync)
+    gauge_diff = float((y - y_ref).abs().max() / y_ref.abs().max())
+    _cuda.heff_apply(L, W, R, x, y)
+    del Lc, Rc, y_ref
+
     # dominant kernel alone: the two gemm_tn_dmma launches of the chain, timed with events per launch group
     ws = torch.empty(lib.tnpy_heff_workspace_bytes(l, r, wl, wr, d), dtype=torch.uint8, device="cuda")
     t1 = torch.empty((d * r, wl * l), dtype=torch.float64, device="cuda")
@@ -343,6 +359,12 @@ def run_single(args):
         },
         "gpu_launches": int(launches),
         "clocks": clocks,
+        "canonical_gauge": {
+            "ms_per_step": dt_c / args.steps * 1e3, "tflops_algorithmic": flops * args.steps / dt_c / 1e12,
+            "executed_flop_fraction": (wl - 1) / wl if wl == wr else None, "rel_diff_vs_dense_path": gauge_diff,
+            "note": "same matvec with L[:,0,:] = R[:,w-1,:] = I flagged (the state of every site inside a sweep); "
+                    "`value` above is the general dense path",
+        },
     }
     if sweep is not None:
         line["sweep"] = sweep

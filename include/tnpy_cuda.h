@@ -43,6 +43,15 @@ extern "C" {
 #define TNPY_GEMM_GENERIC 1 /* generic shared-memory tiled DFMA kernel (any shape / stride)       */
 #define TNPY_GEMM_DMMA 2    /* force the TMA + mbarrier + FP64 tensor-core (DMMA) kernel           */
 
+/* Canonical-gauge shortcuts for the contraction chains (`flags` arguments).  With tnpy's
+ * upper-triangular MPOs (model/utils.py:25-28: row 0 / last column are the boundary vectors) and a
+ * mixed-canonical MPS, L[:, 0, :] and R[:, w_r - 1, :] are identity matrices.  The caller vouches for a
+ * flag (tnpy_identity_defect measures it); a set flag replaces that channel's GEMM slice by a
+ * transpose/copy.  Results change at the level of the measured defect; executed flops drop by up to
+ * 2/w while the algorithmic flop count F_mv quoted everywhere is unchanged. */
+#define TNPY_LEFT_IDENTITY 1
+#define TNPY_RIGHT_IDENTITY 2
+
 /* ---- library ---------------------------------------------------------------------------- */
 int tnpy_version(void);
 const char* tnpy_last_error(void);
@@ -74,8 +83,12 @@ int tnpy_gemm_tn(const double* A, int64_t lda, const double* B, int64_t ldb, dou
  * x, y: (l, d, r).  Workspace: tnpy_heff_workspace_bytes(). */
 size_t tnpy_heff_workspace_bytes(int l, int r, int wl, int wr, int d);
 int tnpy_heff_apply(const double* L, const double* W, const double* R, const double* x, double* y,
-                    int l, int r, int wl, int wr, int d, void* workspace, size_t workspace_bytes,
-                    void* stream);
+                    int l, int r, int wl, int wr, int d, int flags, void* workspace,
+                    size_t workspace_bytes, void* stream);
+/* max_ij |E[i, channel, j] - delta_ij| of an environment E (dim, w, dim), written to device memory.
+ * Workspace: 8 KB. */
+int tnpy_identity_defect(const double* E, int dim, int w, int channel, double* defect_dev,
+                         void* workspace, size_t workspace_bytes, void* stream);
 
 /* Row block of the same matvec for the chi-sharded multi-GPU layout: the caller holds
  * L_rows = L[:, :, m0:m0+l_rows] stored contiguously as (l, wl, l_rows), the full x and R, and gets
@@ -91,11 +104,11 @@ int tnpy_heff_apply_rows(const double* L_rows, const double* W, const double* R,
  * A: (l, d, r).  Workspace: tnpy_env_workspace_bytes(). */
 size_t tnpy_env_workspace_bytes(int l, int r, int wl, int wr, int d);
 int tnpy_env_update_left(const double* L, const double* A, const double* W, double* Lout,
-                         int l, int r, int wl, int wr, int d, void* workspace, size_t workspace_bytes,
-                         void* stream);
+                         int l, int r, int wl, int wr, int d, int flags, void* workspace,
+                         size_t workspace_bytes, void* stream);
 int tnpy_env_update_right(const double* R, const double* A, const double* W, double* Rout,
-                          int l, int r, int wl, int wr, int d, void* workspace, size_t workspace_bytes,
-                          void* stream);
+                          int l, int r, int wl, int wr, int d, int flags, void* workspace,
+                          size_t workspace_bytes, void* stream);
 
 /* ---- a6: Environment.one_site_full_matrix  (matrix_product_state.py:372-409) ---------------
  * H[(l,p,r),(m,q,s)] dense, N = l*d*r; H is N x N row-major.  Built by applying the matvec
@@ -134,7 +147,7 @@ int tnpy_multi_axpy(const double* V, int64_t ldv, int m, const double* h, double
  * Workspace: tnpy_eig_workspace_bytes(). */
 size_t tnpy_eig_workspace_bytes(int l, int r, int wl, int wr, int d, int ncv);
 int tnpy_eig_lowest(const double* L, const double* W, const double* R, double* psi,
-                    int l, int r, int wl, int wr, int d, double tol, int max_matvec, int ncv,
+                    int l, int r, int wl, int wr, int d, int flags, double tol, int max_matvec, int ncv,
                     double* stats_host, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- a5: linalg.eigh(matrix)  (linalg.py:42-61), k = 1 --------------------------------------

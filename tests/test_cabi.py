@@ -47,7 +47,7 @@ def test_host_only_entry_points(lib):
 def test_argument_validation_without_gpu(lib):
     rc = lib.tnpy_gemm_tn(None, 1, None, 1, None, 1, 1, 1, 1, 0, 0, None)
     assert rc == -1 and b"invalid argument" in lib.tnpy_last_error()
-    rc = lib.tnpy_heff_apply(None, None, None, None, None, 0, 1, 1, 1, 2, None, 0, None)
+    rc = lib.tnpy_heff_apply(None, None, None, None, None, 0, 1, 1, 1, 2, 0, None, 0, None)
     assert rc == -1
 
 

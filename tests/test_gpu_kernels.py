@@ -363,3 +363,45 @@ def test_svd_round_trip_at_bench_size(cu):
     assert bool((s[1:] <= s[:-1]).all())
     # checksum of checksums: sum of squared singular values == squared Frobenius norm
     assert abs(float((s * s).sum()) / float((a * a).sum()) - 1) < 1e-12
+
+
+# ------------------------------------------------------------- canonical-gauge identity channels
+@pytest.mark.parametrize("l,r,wl,wr,d", [(16, 16, 5, 5, 2), (64, 96, 5, 6, 2), (128, 128, 6, 6, 2), (33, 17, 5, 5, 2), (8, 8, 1, 5, 2)])
+@pytest.mark.parametrize("flags", [1, 2, 3])
+def test_identity_channel_shortcuts(cu, l, r, wl, wr, d, flags):
+    """With L[:, 0, :] = I and R[:, wr-1, :] = I the flagged chains must reproduce the dense ones."""
+    rng = np.random.default_rng(l + r + flags)
+    L, W, R, x = random_operands(rng, l, r, wl, wr, d)
+    L[:, 0, :] = np.eye(l)
+    R[:, wr - 1, :] = np.eye(r)
+    Ld, Wd, Rd, xd = dev(L), dev(W), dev(R), dev(x)
+    assert cu.identity_defect(Ld, 0) == 0.0 and cu.identity_defect(Rd, wr - 1) == 0.0
+    assert cu.identity_defect(Rd, 0) > 0.1
+    want = oracle.heff_apply(L, W, R, x)
+    got = cu.heff_apply(Ld, Wd, Rd, xd, flags=flags).cpu().numpy()
+    assert rel_err(got, want) < 1e-12
+    if flags & 1:
+        got = cu.env_update_left(Ld, xd, Wd, flags=1).cpu().numpy()
+        assert rel_err(got, oracle.env_update_left(L, x, W)) < 1e-12
+    if flags & 2:
+        got = cu.env_update_right(Rd, xd, Wd, flags=2).cpu().numpy()
+        assert rel_err(got, oracle.env_update_right(R, x, W)) < 1e-12
+
+
+def test_identity_flags_are_measured_not_assumed():
+    """Environment sets the flags only where the channel really is the identity: a right-canonical
+    random MPS has identity right channels and non-identity left channels."""
+    from tnpy_b200.matrix_product_state import Environment, MatrixProductState
+    from tnpy_b200.model import XXZ
+
+    env = Environment(XXZ(n=10, delta=0.5).mpo, MatrixProductState.random(10, 16, 2, seed=2))
+    assert env.gauge_flags(5) == cu_flags("right")
+    assert env.gauge_flags(0) == cu_flags("right")
+    off = Environment(XXZ(n=10, delta=0.5).mpo, MatrixProductState.random(10, 16, 2, seed=2), use_identity_channels=False)
+    assert off.gauge_flags(5) == 0
+
+
+def cu_flags(which):
+    from tnpy_b200 import _cuda
+
+    return {"left": _cuda.LEFT_IDENTITY, "right": _cuda.RIGHT_IDENTITY}[which]

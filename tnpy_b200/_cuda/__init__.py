@@ -15,6 +15,7 @@ _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "libtnpy_cuda.so"
 
 GEMM_AUTO, GEMM_GENERIC, GEMM_DMMA = 0, 1, 2
+LEFT_IDENTITY, RIGHT_IDENTITY = 1, 2
 ENOCONV = -4
 
 _PD = c_void_p  # device double*
@@ -29,11 +30,12 @@ SIGNATURES = {
     "tnpy_probe_fp64": (c_int, [c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_double), c_void_p]),
     "tnpy_gemm_tn": (c_int, [_PD, c_int64, _PD, c_int64, _PD, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "tnpy_heff_workspace_bytes": (c_size_t, [c_int] * 5),
-    "tnpy_heff_apply": (c_int, [_PD, _PD, _PD, _PD, _PD] + [c_int] * 5 + [c_void_p, c_size_t, c_void_p]),
+    "tnpy_heff_apply": (c_int, [_PD, _PD, _PD, _PD, _PD] + [c_int] * 6 + [c_void_p, c_size_t, c_void_p]),
+    "tnpy_identity_defect": (c_int, [_PD, c_int, c_int, c_int, _PD, c_void_p, c_size_t, c_void_p]),
     "tnpy_heff_apply_rows": (c_int, [_PD, _PD, _PD, _PD, _PD] + [c_int] * 6 + [c_void_p, c_size_t, c_void_p]),
     "tnpy_env_workspace_bytes": (c_size_t, [c_int] * 5),
-    "tnpy_env_update_left": (c_int, [_PD, _PD, _PD, _PD] + [c_int] * 5 + [c_void_p, c_size_t, c_void_p]),
-    "tnpy_env_update_right": (c_int, [_PD, _PD, _PD, _PD] + [c_int] * 5 + [c_void_p, c_size_t, c_void_p]),
+    "tnpy_env_update_left": (c_int, [_PD, _PD, _PD, _PD] + [c_int] * 6 + [c_void_p, c_size_t, c_void_p]),
+    "tnpy_env_update_right": (c_int, [_PD, _PD, _PD, _PD] + [c_int] * 6 + [c_void_p, c_size_t, c_void_p]),
     "tnpy_heff_dense_workspace_bytes": (c_size_t, [c_int] * 5),
     "tnpy_heff_dense": (c_int, [_PD, _PD, _PD, _PD] + [c_int] * 5 + [c_void_p, c_size_t, c_void_p]),
     "tnpy_dot": (c_int, [_PD, _PD, c_int64, _PD, c_void_p]),
@@ -46,7 +48,7 @@ SIGNATURES = {
     "tnpy_eig_workspace_bytes": (c_size_t, [c_int] * 6),
     "tnpy_eig_lowest": (
         c_int,
-        [_PD, _PD, _PD, _PD] + [c_int] * 5 + [c_double, c_int, c_int, ctypes.POINTER(c_double), c_void_p, c_size_t, c_void_p],
+        [_PD, _PD, _PD, _PD] + [c_int] * 6 + [c_double, c_int, c_int, ctypes.POINTER(c_double), c_void_p, c_size_t, c_void_p],
     ),
     "tnpy_eigh_workspace_bytes": (c_size_t, [c_int]),
     "tnpy_eigh_lowest": (c_int, [_PD, c_int, _PD, _PD, c_void_p, c_size_t, c_void_p]),
@@ -166,8 +168,9 @@ def _dims(x_shape, w_shape):
     return l, r, wl, wr, d
 
 
-def heff_apply(L, W, R, x, out=None):
-    """y = H_eff x with x (l, d, r), W (wl, wr, d, d), L (l, wl, l) or None, R (r, wr, r) or None."""
+def heff_apply(L, W, R, x, out=None, flags: int = 0):
+    """y = H_eff x with x (l, d, r), W (wl, wr, d, d), L (l, wl, l) or None, R (r, wr, r) or None.
+    ``flags``: LEFT_IDENTITY / RIGHT_IDENTITY canonical-gauge shortcuts (the caller vouches for them)."""
     import torch
 
     _need_cuda(L, W, R, x, out)
@@ -177,7 +180,8 @@ def heff_apply(L, W, R, x, out=None):
     lib = load()
     nbytes = lib.tnpy_heff_workspace_bytes(l, r, wl, wr, d)
     ws = _scratch.get(nbytes)
-    rc = lib.tnpy_heff_apply(_ptr(L), _ptr(W), _ptr(R), _ptr(x), _ptr(out), l, r, wl, wr, d, _ptr(ws), nbytes, _stream())
+    rc = lib.tnpy_heff_apply(_ptr(L), _ptr(W), _ptr(R), _ptr(x), _ptr(out), l, r, wl, wr, d, int(flags), _ptr(ws), nbytes,
+                             _stream())
     check(rc, "tnpy_heff_apply")
     return out
 
@@ -200,7 +204,20 @@ def heff_apply_rows(L_rows, W, R, x, out=None):
     return out
 
 
-def env_update_left(L, A, W, out=None):
+def identity_defect(E, channel: int) -> float:
+    """max |E[:, channel, :] - I| of an environment tensor (dim, w, dim); one scalar read-back."""
+    import torch
+
+    _need_cuda(E)
+    dim, w = E.shape[0], E.shape[1]
+    out = torch.empty((), dtype=torch.float64, device=E.device)
+    ws = _scratch.get(16384)
+    check(load().tnpy_identity_defect(_ptr(E), dim, w, int(channel), _ptr(out), _ptr(ws), 16384, _stream()),
+          "tnpy_identity_defect")
+    return float(out.item())
+
+
+def env_update_left(L, A, W, out=None, flags: int = 0):
     import torch
 
     _need_cuda(L, A, W, out)
@@ -210,12 +227,13 @@ def env_update_left(L, A, W, out=None):
     lib = load()
     nbytes = lib.tnpy_env_workspace_bytes(l, r, wl, wr, d)
     ws = _scratch.get(nbytes)
-    rc = lib.tnpy_env_update_left(_ptr(L), _ptr(A), _ptr(W), _ptr(out), l, r, wl, wr, d, _ptr(ws), nbytes, _stream())
+    rc = lib.tnpy_env_update_left(_ptr(L), _ptr(A), _ptr(W), _ptr(out), l, r, wl, wr, d, int(flags), _ptr(ws), nbytes,
+                                  _stream())
     check(rc, "tnpy_env_update_left")
     return out
 
 
-def env_update_right(R, A, W, out=None):
+def env_update_right(R, A, W, out=None, flags: int = 0):
     import torch
 
     _need_cuda(R, A, W, out)
@@ -225,7 +243,8 @@ def env_update_right(R, A, W, out=None):
     lib = load()
     nbytes = lib.tnpy_env_workspace_bytes(l, r, wl, wr, d)
     ws = _scratch.get(nbytes)
-    rc = lib.tnpy_env_update_right(_ptr(R), _ptr(A), _ptr(W), _ptr(out), l, r, wl, wr, d, _ptr(ws), nbytes, _stream())
+    rc = lib.tnpy_env_update_right(_ptr(R), _ptr(A), _ptr(W), _ptr(out), l, r, wl, wr, d, int(flags), _ptr(ws), nbytes,
+                                   _stream())
     check(rc, "tnpy_env_update_right")
     return out
 
@@ -242,7 +261,7 @@ def heff_dense(L, W, R, l, r):
     return out
 
 
-def eig_lowest(L, W, R, psi, tol: float = 1e-8, max_matvec: int = 1000, ncv: int = 0):
+def eig_lowest(L, W, R, psi, tol: float = 1e-8, max_matvec: int = 1000, ncv: int = 0, flags: int = 0):
     """In-place: psi (l, d, r) holds v0 on entry and the eigenvector on return.
     Returns dict(theta, resid, n_matvec, n_restart, converged, anorm)."""
     _need_cuda(L, W, R, psi)
@@ -251,7 +270,7 @@ def eig_lowest(L, W, R, psi, tol: float = 1e-8, max_matvec: int = 1000, ncv: int
     nbytes = lib.tnpy_eig_workspace_bytes(l, r, wl, wr, d, ncv)
     ws = _scratch.get(nbytes)
     stats = (c_double * 8)()
-    rc = lib.tnpy_eig_lowest(_ptr(L), _ptr(W), _ptr(R), _ptr(psi), l, r, wl, wr, d, float(tol), int(max_matvec),
+    rc = lib.tnpy_eig_lowest(_ptr(L), _ptr(W), _ptr(R), _ptr(psi), l, r, wl, wr, d, int(flags), float(tol), int(max_matvec),
                              int(ncv), stats, _ptr(ws), nbytes, _stream())
     check(rc, "tnpy_eig_lowest", allow_noconv=True)
     return {

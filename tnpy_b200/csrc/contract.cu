@@ -26,7 +26,7 @@ constexpr int kMixMaxTerms = 288;
 template <int VEC>
 __global__ void __launch_bounds__(256) wmix_kernel(const double* __restrict__ in, double* __restrict__ out,
                                                    const double* __restrict__ W, int nu, int nup, int nv, int nvp,
-                                                   int X, int Y, int su, int sup, int sv, int svp) {
+                                                   int X, int Y, int su, int sup, int sv, int svp, int channel_major) {
   __shared__ double coef[kMixMaxTerms];
   __shared__ int64_t inoff[kMixMaxTerms];
   __shared__ int nterms;
@@ -61,7 +61,9 @@ __global__ void __launch_bounds__(256) wmix_kernel(const double* __restrict__ in
     const int64_t x = e / yv;
     const int y = (int)(e - x * yv) * VEC;
     const int64_t ibase = x * (int64_t)nv * Y + y;
-    const int64_t obase = ((x * nvp + vp) * nup + up) * (int64_t)Y + y;
+    // default out[X][v'][u'][Y]; channel_major: out[v'][X][u'][Y] (MPO bond slowest, so a GEMM can drop
+    // whole channels from its K range)
+    const int64_t obase = (channel_major ? (((int64_t)vp * X + x) * nup + up) : ((x * nvp + vp) * nup + up)) * (int64_t)Y + y;
     if (VEC == 2) {
       double2 acc = make_double2(0.0, 0.0);
       for (int k = 0; k < nt; ++k) {
@@ -79,7 +81,7 @@ __global__ void __launch_bounds__(256) wmix_kernel(const double* __restrict__ in
 }
 
 static int wmix(const double* in, double* out, const double* W, int nu, int nup, int nv, int nvp, int X, int Y, int su,
-                int sup, int sv, int svp, cudaStream_t stream) {
+                int sup, int sv, int svp, cudaStream_t stream, int channel_major = 0) {
   if (nu * nv > kMixMaxTerms) {
     set_error("wmix: MPO bond x physical dimension %d exceeds the compiled limit %d", nu * nv, kMixMaxTerms);
     return TNPY_EINVAL;
@@ -93,9 +95,9 @@ static int wmix(const double* in, double* out, const double* W, int nu, int nup,
   if (bx < 1) bx = 1;
   dim3 grid((unsigned)bx, (unsigned)channels);
   if (vec)
-    wmix_kernel<2><<<grid, 256, 0, stream>>>(in, out, W, nu, nup, nv, nvp, X, Y, su, sup, sv, svp);
+    wmix_kernel<2><<<grid, 256, 0, stream>>>(in, out, W, nu, nup, nv, nvp, X, Y, su, sup, sv, svp, channel_major);
   else
-    wmix_kernel<1><<<grid, 256, 0, stream>>>(in, out, W, nu, nup, nv, nvp, X, Y, su, sup, sv, svp);
+    wmix_kernel<1><<<grid, 256, 0, stream>>>(in, out, W, nu, nup, nv, nvp, X, Y, su, sup, sv, svp, channel_major);
   TNPY_LAUNCH_OK();
   return TNPY_OK;
 }
@@ -127,6 +129,75 @@ static int mirror(const double* in, double* out, int l, int d, int r, cudaStream
   return TNPY_OK;
 }
 
+// out[z][c][r] = in[z][r][c]: batched strided transpose (32x32 shared-memory tiles).
+// in rows have stride ld_in, out rows stride ld_out; batch z advances by in_z / out_z elements.
+__global__ void __launch_bounds__(256) transpose_strided_kernel(const double* __restrict__ in, int64_t ld_in,
+                                                                int64_t in_z, int rows, int cols,
+                                                                double* __restrict__ out, int64_t ld_out,
+                                                                int64_t out_z) {
+  __shared__ double tile[32][33];
+  in += blockIdx.z * in_z;
+  out += blockIdx.z * out_z;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    if (r < rows && c < cols) tile[i][tx] = in[(int64_t)r * ld_in + c];
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + tx;
+    if (r < rows && c < cols) out[(int64_t)c * ld_out + r] = tile[tx][i];
+  }
+}
+
+static int transpose_strided(const double* in, int64_t ld_in, int64_t in_z, int rows, int cols, double* out,
+                             int64_t ld_out, int64_t out_z, int batch, cudaStream_t stream) {
+  dim3 grid(ceil_div(cols, 32), ceil_div(rows, 32), batch);
+  transpose_strided_kernel<<<grid, 256, 0, stream>>>(in, ld_in, in_z, rows, cols, out, ld_out, out_z);
+  TNPY_LAUNCH_OK();
+  return TNPY_OK;
+}
+
+// R2[b][r][s] = R[r][b][s] for b < w_keep  (MPO bond slowest, trailing channels dropped)
+__global__ void __launch_bounds__(256) channel_major_kernel(const double* __restrict__ R, double* __restrict__ R2,
+                                                            int r, int w, int w_keep, int s_dim) {
+  const int64_t total = (int64_t)r * w_keep * s_dim;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int s = (int)(e % s_dim);
+    const int64_t br = e / s_dim;
+    const int ri = (int)(br % r), b = (int)(br / r);
+    R2[e] = R[((int64_t)ri * w + b) * s_dim + s];
+  }
+}
+
+// max_ij |E[i][c][j] - delta_ij| for an environment E (dim, w, dim): is channel c the identity?
+__global__ void __launch_bounds__(256) identity_defect_kernel(const double* __restrict__ E, int dim, int w, int c,
+                                                              double* __restrict__ partial) {
+  __shared__ double sh[32];
+  double worst = 0.0;
+  const int64_t total = (int64_t)dim * dim;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e / dim), j = (int)(e % dim);
+    worst = fmax(worst, fabs(E[((int64_t)i * w + c) * dim + j] - (i == j ? 1.0 : 0.0)));
+  }
+  // max-reduce (values are >= 0, so a sum-free shuffle max)
+  for (int o = 16; o > 0; o >>= 1) worst = fmax(worst, __shfl_xor_sync(0xffffffffu, worst, o));
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = worst;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (threadIdx.x == 0) partial[blockIdx.x] = v;
+  }
+}
+__global__ void max_reduce_kernel(const double* __restrict__ partial, int n, double* __restrict__ out) {
+  double v = 0.0;
+  for (int i = threadIdx.x; i < n; i += 32) v = fmax(v, partial[i]);
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if (threadIdx.x == 0) *out = v;
+}
+
 // ---------------------------------------------------------------------------------------------
 // chains
 // ---------------------------------------------------------------------------------------------
@@ -137,8 +208,16 @@ static int check_dims(int l, int r, int wl, int wr, int d) {
 
 // lo = number of output (bra) rows of L held by the caller: L is (l, wl, lo), y is (lo, d, r).
 // lo == l is the ordinary matvec; lo < l is one rank's row block of the chi-sharded matvec.
+//
+// flags (canonical-gauge shortcuts, SURVEY 7 "identity channels"): with the upper-triangular MPOs of
+// tnpy.model and a mixed-canonical MPS, L[:, 0, :] and R[:, wr-1, :] are identity matrices.
+//   TNPY_LEFT_IDENTITY : T1[p,r,0,m] = x[m,p,r] is a transpose instead of 1/wl of the first GEMM;
+//   TNPY_RIGHT_IDENTITY: the b = wr-1 slice of the second GEMM is y[m,q,s] += T2[s,wr-1,q,m]; the
+//                        intermediate is laid out MPO-bond-slowest so the GEMM just drops that K range.
+// The caller vouches for the flags (tnpy_identity_defect measures them); executed flops drop by up to
+// 2/w while the algorithmic flop count F_mv is unchanged.
 int heff_apply_rows(const double* L, const double* W, const double* R, const double* x, double* y, int l, int lo,
-                    int r, int wl, int wr, int d, Workspace& ws, cudaStream_t stream) {
+                    int r, int wl, int wr, int d, int flags, Workspace& ws, cudaStream_t stream) {
   TNPY_TRY(check_dims(l, r, wl, wr, d));
   TNPY_CHECK_ARG(lo > 0, "non-positive row count");
   TNPY_CHECK_ARG(W && x && y, "null pointer");
@@ -146,31 +225,49 @@ int heff_apply_rows(const double* L, const double* W, const double* R, const dou
   TNPY_CHECK_ARG(R || (r == 1 && wr == 1), "R may be NULL only for unit right bond");
   if (!L) L = device_one();
   if (!R) R = device_one();
+  const bool left_id = (flags & TNPY_LEFT_IDENTITY) && wl > 1 && lo == l;
+  const bool right_id = (flags & TNPY_RIGHT_IDENTITY) && wr > 1;
   double* t1 = ws.take<double>((size_t)d * r * wl * lo);
   double* t2 = ws.take<double>((size_t)r * wr * d * lo);
-  if (!t1 || !t2) {
+  double* r2 = right_id ? ws.take<double>((size_t)r * (wr - 1) * r) : nullptr;
+  if (!t1 || !t2 || (right_id && !r2)) {
     set_error("heff_apply: workspace too small");
     return TNPY_EWORKSPACE;
   }
   const int algo = TNPY_GEMM_AUTO;
   // T1[p, r, a, m] = sum_l x[l, (p r)] L[l, (a m)]
-  TNPY_TRY(gemm_tn(x, (int64_t)d * r, L, (int64_t)wl * lo, plain_out(t1, (int64_t)wl * lo, d * r), d * r, wl * lo, l,
-                   0, algo, stream));
-  // T2[r, b, q, m] = sum_{a p} W[a, b, p, q] T1[p, r, a, m]          (u=p, u'=q, v=a, v'=b)
-  TNPY_TRY(wmix(t1, t2, W, d, d, wl, wr, r, lo, d, 1, wr * d * d, d * d, stream));
+  if (left_id) {
+    TNPY_TRY(transpose_strided(x, (int64_t)d * r, 0, l, d * r, t1, (int64_t)wl * lo, 0, 1, stream));  // a = 0
+    TNPY_TRY(gemm_tn(x, (int64_t)d * r, L + lo, (int64_t)wl * lo, plain_out(t1 + lo, (int64_t)wl * lo, d * r), d * r,
+                     (wl - 1) * lo, l, 0, algo, stream));
+  } else {
+    TNPY_TRY(gemm_tn(x, (int64_t)d * r, L, (int64_t)wl * lo, plain_out(t1, (int64_t)wl * lo, d * r), d * r, wl * lo, l,
+                     0, algo, stream));
+  }
+  // T2[r, b, q, m] (or [b, r, q, m]) = sum_{a p} W[a, b, p, q] T1[p, r, a, m]      (u=p, u'=q, v=a, v'=b)
+  TNPY_TRY(wmix(t1, t2, W, d, d, wl, wr, r, lo, d, 1, wr * d * d, d * d, stream, right_id ? 1 : 0));
   // y[m, q, s] = sum_{r b} T2[(r b), (q m)] R[(r b), s]               rows (q m) -> (m q)
   GemmOut out{y, (int64_t)d * r, (int64_t)r, lo};
-  TNPY_TRY(gemm_tn(t2, (int64_t)d * lo, R, (int64_t)r, out, d * lo, r, r * wr, 0, algo, stream));
+  if (right_id) {
+    // y[m, q, s] = T2[wr-1, s, q, m]  (+ the GEMM over the other channels)
+    const double* t2_last = t2 + (size_t)(wr - 1) * r * d * lo;
+    TNPY_TRY(transpose_strided(t2_last, (int64_t)d * lo, lo, r, lo, y, (int64_t)d * r, r, d, stream));
+    channel_major_kernel<<<sm_count() * 8, 256, 0, stream>>>(R, r2, r, wr, wr - 1, r);
+    TNPY_LAUNCH_OK();
+    TNPY_TRY(gemm_tn(t2, (int64_t)d * lo, r2, (int64_t)r, out, d * lo, r, r * (wr - 1), 1, algo, stream));
+  } else {
+    TNPY_TRY(gemm_tn(t2, (int64_t)d * lo, R, (int64_t)r, out, d * lo, r, r * wr, 0, algo, stream));
+  }
   return TNPY_OK;
 }
 
 int heff_apply(const double* L, const double* W, const double* R, const double* x, double* y, int l, int r, int wl,
-               int wr, int d, Workspace& ws, cudaStream_t stream) {
-  return heff_apply_rows(L, W, R, x, y, l, l, r, wl, wr, d, ws, stream);
+               int wr, int d, int flags, Workspace& ws, cudaStream_t stream) {
+  return heff_apply_rows(L, W, R, x, y, l, l, r, wl, wr, d, flags, ws, stream);
 }
 
 int env_update_left(const double* L, const double* A, const double* W, double* Lout, int l, int r, int wl, int wr,
-                    int d, Workspace& ws, cudaStream_t stream) {
+                    int d, int flags, Workspace& ws, cudaStream_t stream) {
   TNPY_TRY(check_dims(l, r, wl, wr, d));
   TNPY_CHECK_ARG(A && W && Lout, "null pointer");
   TNPY_CHECK_ARG(L || (l == 1 && wl == 1), "L may be NULL only for unit left bond");
@@ -182,9 +279,15 @@ int env_update_left(const double* L, const double* A, const double* W, double* L
     return TNPY_EWORKSPACE;
   }
   const int algo = TNPY_GEMM_AUTO;
-  // T1[a, m, p, r] = sum_l L[l, (a m)] A[l, (p r)]
-  TNPY_TRY(gemm_tn(L, (int64_t)wl * l, A, (int64_t)d * r, plain_out(t1, (int64_t)d * r, wl * l), wl * l, d * r, l, 0,
-                   algo, stream));
+  // T1[a, m, p, r] = sum_l L[l, (a m)] A[l, (p r)];  identity channel a = 0: T1[0] = A
+  if ((flags & TNPY_LEFT_IDENTITY) && wl > 1) {
+    TNPY_CUDA_OK(cudaMemcpyAsync(t1, A, sizeof(double) * (size_t)l * d * r, cudaMemcpyDeviceToDevice, stream));
+    TNPY_TRY(gemm_tn(L + l, (int64_t)wl * l, A, (int64_t)d * r, plain_out(t1 + (size_t)l * d * r, (int64_t)d * r, (wl - 1) * l),
+                     (wl - 1) * l, d * r, l, 0, algo, stream));
+  } else {
+    TNPY_TRY(gemm_tn(L, (int64_t)wl * l, A, (int64_t)d * r, plain_out(t1, (int64_t)d * r, wl * l), wl * l, d * r, l, 0,
+                     algo, stream));
+  }
   // T2[m, q, b, r] = sum_{a p} W[a, b, p, q] T1[a, m, p, r]          (u=a, u'=b, v=p, v'=q)
   TNPY_TRY(wmix(t1, t2, W, wl, wr, d, d, l, r, wr * d * d, d * d, d, 1, stream));
   // Lout[r, b, s] = sum_{m q} T2[(m q), (b r)] A[(m q), s]             rows (b r) -> (r b)
@@ -194,7 +297,7 @@ int env_update_left(const double* L, const double* A, const double* W, double* L
 }
 
 int env_update_right(const double* R, const double* A, const double* W, double* Rout, int l, int r, int wl, int wr,
-                     int d, Workspace& ws, cudaStream_t stream) {
+                     int d, int flags, Workspace& ws, cudaStream_t stream) {
   TNPY_TRY(check_dims(l, r, wl, wr, d));
   TNPY_CHECK_ARG(A && W && Rout, "null pointer");
   TNPY_CHECK_ARG(R || (r == 1 && wr == 1), "R may be NULL only for unit right bond");
@@ -210,9 +313,16 @@ int env_update_right(const double* R, const double* A, const double* W, double* 
   // At[r, p, l] = A[l, p, r]  -- mirror image of the site tensor; the right update is the left
   // update of the mirrored chain with the MPO bond roles swapped.
   TNPY_TRY(mirror(A, at, l, d, r, stream));
-  // T1[b, s, p, l] = sum_r R[r, (b s)] At[r, (p l)]
-  TNPY_TRY(gemm_tn(R, (int64_t)wr * r, at, (int64_t)d * l, plain_out(t1, (int64_t)d * l, wr * r), wr * r, d * l, r, 0,
-                   algo, stream));
+  // T1[b, s, p, l] = sum_r R[r, (b s)] At[r, (p l)];  identity channel b = wr-1: T1[wr-1] = At
+  if ((flags & TNPY_RIGHT_IDENTITY) && wr > 1) {
+    TNPY_CUDA_OK(cudaMemcpyAsync(t1 + (size_t)(wr - 1) * r * d * l, at, sizeof(double) * (size_t)r * d * l,
+                                 cudaMemcpyDeviceToDevice, stream));
+    TNPY_TRY(gemm_tn(R, (int64_t)wr * r, at, (int64_t)d * l, plain_out(t1, (int64_t)d * l, (wr - 1) * r), (wr - 1) * r,
+                     d * l, r, 0, algo, stream));
+  } else {
+    TNPY_TRY(gemm_tn(R, (int64_t)wr * r, at, (int64_t)d * l, plain_out(t1, (int64_t)d * l, wr * r), wr * r, d * l, r, 0,
+                     algo, stream));
+  }
   // T2[s, q, a, l] = sum_{b p} W[a, b, p, q] T1[b, s, p, l]          (u=b, u'=a, v=p, v'=q)
   TNPY_TRY(wmix(t1, t2, W, wr, wl, d, d, r, l, d * d, wr * d * d, d, 1, stream));
   // Rout[l, a, m] = sum_{s q} T2[(s q), (a l)] At[(s q), m]            rows (a l) -> (l a)
@@ -250,7 +360,7 @@ using namespace tnpy;
 
 static size_t chain_ws(int l, int r, int wl, int wr, int d) {
   const size_t wmax = (size_t)(wl > wr ? wl : wr);
-  return 3 * Workspace::need((size_t)l * r * d * wmax) + 1024;
+  return 3 * Workspace::need((size_t)l * r * d * wmax) + Workspace::need((size_t)r * wr * r) + 1024;
 }
 
 extern "C" size_t tnpy_heff_workspace_bytes(int l, int r, int wl, int wr, int d) { return chain_ws(l, r, wl, wr, d); }
@@ -258,28 +368,49 @@ extern "C" size_t tnpy_env_workspace_bytes(int l, int r, int wl, int wr, int d) 
 extern "C" size_t tnpy_heff_dense_workspace_bytes(int, int, int, int, int) { return 256; }
 
 extern "C" int tnpy_heff_apply(const double* L, const double* W, const double* R, const double* x, double* y, int l,
-                               int r, int wl, int wr, int d, void* workspace, size_t workspace_bytes, void* stream) {
+                               int r, int wl, int wr, int d, int flags, void* workspace, size_t workspace_bytes,
+                               void* stream) {
   Workspace ws(workspace, workspace_bytes);
-  return heff_apply(L, W, R, x, y, l, r, wl, wr, d, ws, static_cast<cudaStream_t>(stream));
+  return heff_apply(L, W, R, x, y, l, r, wl, wr, d, flags, ws, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int tnpy_identity_defect(const double* E, int dim, int w, int channel, double* defect_dev, void* workspace,
+                                    size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TNPY_CHECK_ARG(E && defect_dev && dim > 0 && w > 0 && channel >= 0 && channel < w, "bad argument");
+  Workspace ws(workspace, workspace_bytes);
+  const int blocks = sm_count() * 4;
+  double* partial = ws.take<double>(blocks);
+  if (!partial) {
+    set_error("tnpy_identity_defect: workspace too small (need %zu bytes)", Workspace::need(blocks) + 256);
+    return TNPY_EWORKSPACE;
+  }
+  identity_defect_kernel<<<blocks, 256, 0, stream>>>(E, dim, w, channel, partial);
+  TNPY_LAUNCH_OK();
+  max_reduce_kernel<<<1, 32, 0, stream>>>(partial, blocks, defect_dev);
+  TNPY_LAUNCH_OK();
+  return TNPY_OK;
 }
 
 extern "C" int tnpy_heff_apply_rows(const double* L_rows, const double* W, const double* R, const double* x,
                                     double* y_rows, int l, int l_rows, int r, int wl, int wr, int d, void* workspace,
                                     size_t workspace_bytes, void* stream) {
   Workspace ws(workspace, workspace_bytes);
-  return heff_apply_rows(L_rows, W, R, x, y_rows, l, l_rows, r, wl, wr, d, ws, static_cast<cudaStream_t>(stream));
+  return heff_apply_rows(L_rows, W, R, x, y_rows, l, l_rows, r, wl, wr, d, 0, ws, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int tnpy_env_update_left(const double* L, const double* A, const double* W, double* Lout, int l, int r,
-                                    int wl, int wr, int d, void* workspace, size_t workspace_bytes, void* stream) {
+                                    int wl, int wr, int d, int flags, void* workspace, size_t workspace_bytes,
+                                    void* stream) {
   Workspace ws(workspace, workspace_bytes);
-  return env_update_left(L, A, W, Lout, l, r, wl, wr, d, ws, static_cast<cudaStream_t>(stream));
+  return env_update_left(L, A, W, Lout, l, r, wl, wr, d, flags, ws, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int tnpy_env_update_right(const double* R, const double* A, const double* W, double* Rout, int l, int r,
-                                     int wl, int wr, int d, void* workspace, size_t workspace_bytes, void* stream) {
+                                     int wl, int wr, int d, int flags, void* workspace, size_t workspace_bytes,
+                                     void* stream) {
   Workspace ws(workspace, workspace_bytes);
-  return env_update_right(R, A, W, Rout, l, r, wl, wr, d, ws, static_cast<cudaStream_t>(stream));
+  return env_update_right(R, A, W, Rout, l, r, wl, wr, d, flags, ws, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int tnpy_heff_dense(const double* L, const double* W, const double* R, double* H, int l, int r, int wl,

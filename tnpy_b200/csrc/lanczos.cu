@@ -13,7 +13,7 @@
 namespace tnpy {
 
 int heff_apply(const double* L, const double* W, const double* R, const double* x, double* y, int l, int r, int wl,
-               int wr, int d, Workspace& ws, cudaStream_t stream);
+               int wr, int d, int flags, Workspace& ws, cudaStream_t stream);
 int multi_dot(const double* V, int64_t ldv, int m, const double* w, int64_t n, double* h, int mode,
               cudaStream_t stream);
 int multi_axpy(const double* V, int64_t ldv, int m, const double* h, double* w, int64_t n, double* nrm_out,
@@ -211,7 +211,7 @@ extern "C" size_t tnpy_eig_workspace_bytes(int l, int r, int wl, int wr, int d, 
 }
 
 extern "C" int tnpy_eig_lowest(const double* L, const double* W, const double* R, double* psi, int l, int r, int wl,
-                               int wr, int d, double tol, int max_matvec, int ncv_in, double* stats_host,
+                               int wr, int d, int flags, double tol, int max_matvec, int ncv_in, double* stats_host,
                                void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   TNPY_CHECK_ARG(psi && W, "null pointer");
@@ -254,7 +254,7 @@ extern "C" int tnpy_eig_lowest(const double* L, const double* W, const double* R
     double* vj = V + (int64_t)j * ldv;
     double* w = V + (int64_t)(j + 1) * ldv;
     Workspace chain(static_cast<char*>(workspace) + chain_off, workspace_bytes - chain_off);
-    TNPY_TRY(heff_apply(L, W, R, vj, w, l, r, wl, wr, d, chain, stream));
+    TNPY_TRY(heff_apply(L, W, R, vj, w, l, r, wl, wr, d, flags, chain, stream));
     ++n_matvec;
     // classical Gram-Schmidt against the whole basis, applied twice; the first-pass coefficients are
     // column j of T = V^T H V, the second pass adds the rounding-level correction.

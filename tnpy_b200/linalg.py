@@ -68,7 +68,8 @@ def eigshmv(linear_operator, v0, k: int = 1, which: str = "SA", tol: float = 0, 
     psi, was_tensor = _to_device(v0)
     psi = psi.reshape(linear_operator.site_shape).clone()
     L, W, R = linear_operator.env.operands(linear_operator.site)
-    stats = _cuda.eig_lowest(L, W, R, psi, tol=tol, **opts)
+    flags = linear_operator.env.gauge_flags(linear_operator.site)
+    stats = _cuda.eig_lowest(L, W, R, psi, tol=tol, flags=flags, **opts)
     if not stats["converged"]:
         logger.warning(f"eigshmv: not converged after {stats['n_matvec']} matvecs, residual {stats['resid']:.3e}")
     linear_operator.last_stats = stats

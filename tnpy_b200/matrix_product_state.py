@@ -263,7 +263,7 @@ class HeffOperator(LinearOperator):
 
     def apply_device(self, x, out=None):
         L, W, R = self.env.operands(self.site)
-        return _cuda.heff_apply(L, W, R, x.reshape(self.site_shape), out)
+        return _cuda.heff_apply(L, W, R, x.reshape(self.site_shape), out, flags=self.env.gauge_flags(self.site))
 
     def _staging(self):
         import torch
@@ -338,7 +338,10 @@ class _DeviceDictView:
 
 
 class Environment:
-    def __init__(self, mpo: MatrixProductOperator, mps, build_left: bool = True):
+    #: an environment channel counts as the identity when max|E[:, c, :] - I| is below this
+    IDENTITY_TOL = 1e-12
+
+    def __init__(self, mpo: MatrixProductOperator, mps, build_left: bool = True, use_identity_channels: bool = True):
         """``mps`` is a :class:`MatrixProductState` (host, as in the reference) or a list of
         three-leg (l, d, r) float64 CUDA tensors (device-born synthetic states for benchmarks)."""
         import torch
@@ -368,6 +371,11 @@ class Environment:
         self._W2 = None
         self._left: Dict[int, object] = {}
         self._right: Dict[int, object] = {}
+        # canonical-gauge shortcuts: is L[site][:, 0, :] / R[site][:, -1, :] the identity?  Measured on the
+        # device after every environment update (one scalar read-back), never assumed.
+        self._use_identity = use_identity_channels
+        self._left_identity: Dict[int, bool] = {}
+        self._right_identity: Dict[int, bool] = {}
         self.bond_singular_values: Dict[int, object] = {}
         if build_left:  # the reference builds both stacks up front (:247-250)
             for site in range(1, self.n_sites):
@@ -421,14 +429,32 @@ class Environment:
             self._right.get(site) if site < self.n_sites - 1 else None
         )
 
+    def gauge_flags(self, site: int) -> int:
+        """TNPY_LEFT_IDENTITY / TNPY_RIGHT_IDENTITY bits valid for H_eff at ``site``."""
+        flags = 0
+        if self._left_identity.get(site, False):
+            flags |= _cuda.LEFT_IDENTITY
+        if self._right_identity.get(site, False):
+            flags |= _cuda.RIGHT_IDENTITY
+        return flags
+
     # -- a7 -------------------------------------------------------------------------------------------
     def update_left(self, site: int):
         prev = None if site == 1 else self._left[site - 1]
-        self._left[site] = _cuda.env_update_left(prev, self._A[site - 1], self._W[site - 1], self._left.get(site))
+        flags = _cuda.LEFT_IDENTITY if self._left_identity.get(site - 1, False) else 0
+        self._left[site] = _cuda.env_update_left(prev, self._A[site - 1], self._W[site - 1], self._left.get(site), flags)
+        self._left_identity[site] = (
+            self._use_identity and _cuda.identity_defect(self._left[site], 0) <= self.IDENTITY_TOL
+        )
 
     def update_right(self, site: int):
         prev = None if site == self.n_sites - 2 else self._right[site + 1]
-        self._right[site] = _cuda.env_update_right(prev, self._A[site + 1], self._W[site + 1], self._right.get(site))
+        flags = _cuda.RIGHT_IDENTITY if self._right_identity.get(site + 1, False) else 0
+        self._right[site] = _cuda.env_update_right(prev, self._A[site + 1], self._W[site + 1], self._right.get(site), flags)
+        w = self._right[site].shape[1]
+        self._right_identity[site] = (
+            self._use_identity and _cuda.identity_defect(self._right[site], w - 1) <= self.IDENTITY_TOL
+        )
 
     def update(self, site: int, direction: Direction):
         if direction == Direction.RIGHTWARD:
