@@ -150,6 +150,18 @@ int tnpy_eig_lowest(const double* L, const double* W, const double* R, double* p
                     int l, int r, int wl, int wr, int d, int flags, double tol, int max_matvec, int ncv,
                     double* stats_host, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- f2: ShiftInvertDMRG.one_site_solver -> primme.eigsh(A, M=M, k=1, which="SA")  (finite_dmrg.py:341-355)
+ * Lowest eigenpair of the symmetric-definite pencil  A x = lambda M x,  A = H_eff(LA, WA, RA) (MPO of
+ * H - eps), M = H_eff(LM, WM, RM) (its square, w^2 channels), both at the same site (same l, r, d).
+ * Generalised Davidson on the device; psi: in = start vector, out = eigenvector normalised to
+ * x^T M x = 1 (the convention of primme.eigsh(A, M=M) and scipy.linalg.eigh(a, b)).  Stops when ||A x - theta M x|| <= tol (||A x|| + |theta| ||M x||).
+ * stats_host as for tnpy_eig_lowest ([2] counts iterations = one A and one M matvec each). */
+size_t tnpy_geig_workspace_bytes(int l, int r, int wl_a, int wr_a, int wl_m, int wr_m, int d, int ncv);
+int tnpy_geig_lowest(const double* LA, const double* WA, const double* RA, const double* LM,
+                     const double* WM, const double* RM, double* psi, int l, int r, int wl_a, int wr_a,
+                     int wl_m, int wr_m, int d, int flags_a, double tol, int max_iter, int ncv,
+                     double* stats_host, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- a5: linalg.eigh(matrix)  (linalg.py:42-61), k = 1 --------------------------------------
  * Lowest eigenpair of a dense symmetric N x N matrix (row-major, destroyed) by cyclic Jacobi
  * on the device.  evec: N doubles, eval_dev: 1 double (device). */

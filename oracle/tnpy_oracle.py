@@ -545,3 +545,58 @@ class FiniteDMRG:
 def exact_ground_energy(mpo: Sequence[np.ndarray]) -> float:
     """exact_diagonalization.py:57-58 -- dense eigh of the full Hamiltonian."""
     return float(np.linalg.eigvalsh(full_hamiltonian(mpo))[0])
+
+
+# --------------------------------------------------------------------------------------
+# finite_dmrg.py:266-407 -- ShiftInvertDMRG
+# --------------------------------------------------------------------------------------
+class ShiftInvertDMRG(FiniteDMRG):
+    """Restatement of the reference's shift-invert driver.  The generalised local problem
+    A x = lambda M x (A from the MPO of H - eps, M from its square) is solved densely with
+    scipy.linalg.eigh(a, b) at every site (the reference does that below ``exact_solver_dim`` and
+    hands larger sites to primme.eigsh(A, M=M); dense is the solver-independent answer)."""
+
+    def __init__(self, mpo, bond_dim, offset=0.0, mps=None, seed=0):
+        super().__init__(mpo, bond_dim, mps=mps, seed=seed)
+        self.env2 = Environment(mpo_square(mpo), self.env.mps)
+        self.env2.mps = self.env.mps  # one shared list of site tensors (finite_dmrg.py:379-385 keeps them in step)
+        self.offset = offset
+        self.restored_mps = None
+
+    def one_site_solver(self, site, tol=1e-8):
+        a = self.env.one_site_full_matrix(site)
+        b = self.env2.one_site_full_matrix(site)
+        a, b = 0.5 * (a + a.T), 0.5 * (b + b.T)
+        evals, evecs = spla.eigh(a, b, subset_by_index=[0, 0])
+        return float(evals[0]), evecs[:, 0]  # b-normalised: x^T b x = 1, as primme / scipy return it
+
+    def sweep(self, direction=RIGHTWARD, tol=1e-8):
+        sites = range(self.n_sites - 1) if direction == RIGHTWARD else range(self.n_sites - 1, 0, -1)
+        energy = None
+        for site in sites:
+            energy, psi = self.one_site_solver(site, tol)
+            self.env.update_mps(site, np.asarray(psi).reshape(self.mps[site].shape))
+            self.perturb_wave_function(site)
+            self.env.split_tensor(site, direction)
+            self.env.update(site, direction)
+            self.env2.update(site, direction)
+        return float(energy)
+
+    def restore_mps(self):
+        """finite_dmrg.py:313-339: |psi> = (H - eps)|phi>, fused bonds (MPS bond slow, MPO bond fast)."""
+        n = self.n_sites
+        arrays = []
+        for site in range(n):
+            a, w = _as3(self.mps[site], site, n), _w4(self.env.mpo[site], site, n)
+            t = np.einsum("lbr,xykb->lxkry", a, w)
+            l, wl, k, r, wr = t.shape
+            arrays.append(t.reshape(l * wl, k, r * wr))
+        arrays[0] = arrays[0][0]
+        arrays[-1] = arrays[-1][:, :, 0]
+        self.restored_mps = arrays
+        return arrays
+
+    def run(self, tol=1e-7, max_sweep=100):
+        energies = super().run(tol=tol, max_sweep=max_sweep, with_variance=False)
+        self.restore_mps()
+        return (np.reciprocal(energies) + self.offset).tolist()

@@ -1,0 +1,80 @@
+"""ShiftInvertDMRG (reference finite_dmrg.py:266-407, pinned by tests/test_finite_dmrg.py:26-72)."""
+import numpy as np
+import pytest
+import scipy.linalg as spla
+
+from oracle import tnpy_oracle as oracle
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def dev(x):
+    return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).cuda()
+
+
+@pytest.mark.parametrize("site", [0, 3, 7])
+def test_geig_lowest_matches_dense_pencil(site):
+    from tnpy_b200 import _cuda
+
+    n, chi, offset = 8, 16, 0.1
+    mpo = oracle.random_heisenberg_mpo(n, 10.5, seed=2022, offset=offset)
+    mps = oracle.random_mps(n, chi, 2, seed=5)
+    env, env2 = oracle.Environment(mpo, mps), oracle.Environment(oracle.mpo_square(mpo), mps)
+    a, b = env.one_site_full_matrix(site), env2.one_site_full_matrix(site)
+    want = spla.eigh(0.5 * (a + a.T), 0.5 * (b + b.T), eigvals_only=True, subset_by_index=[0, 0])[0]
+
+    def ops(e, s):
+        L = None if s == 0 else dev(e.left[s])
+        R = None if s == n - 1 else dev(e.right[s])
+        return L, dev(oracle._w4(e.mpo[s], s, n)), R
+
+    psi = dev(oracle._as3(mps[site], site, n)).clone()
+    stats = _cuda.geig_lowest(*ops(env, site), *ops(env2, site), psi, tol=1e-10)
+    assert stats["converged"]
+    assert abs(stats["theta"] - want) <= 1e-8 * abs(want)
+    x = psi.cpu().numpy().reshape(-1)
+    assert abs(x @ b.T @ x - 1.0) < 1e-8  # M-normalised
+    assert np.linalg.norm(a.T @ x - stats["theta"] * (b.T @ x)) <= 1e-7 * np.linalg.norm(a.T @ x)
+
+
+@pytest.mark.parametrize("offset", [-0.1, 0.1, 0.2])
+def test_shift_invert_reference_anchors(offset):
+    """tests/test_finite_dmrg.py:56-72 at n=8, chi=16: nearest eigenvalue below the offset (atol 1e-6),
+    the restored state equals the ED eigenvector up to a sign (atol 1e-6), and the returned energy
+    equals <H> on the restored state (atol 1e-6)."""
+    from tnpy_b200.finite_dmrg import ShiftInvertDMRG
+    from tnpy_b200.model import RandomHeisenberg
+
+    n, h, seed = 8, 10.5, 2022
+    model = RandomHeisenberg(n=n, h=h, seed=seed)
+    evals, evecs = np.linalg.eigh(oracle.full_hamiltonian(model.mpo.arrays))
+    idx = np.where(evals < offset)[0].max()
+    shifted = RandomHeisenberg(n=n, h=h, seed=seed, offset=offset)
+    sidmrg = ShiftInvertDMRG(shifted.mpo, bond_dim=2**4, offset=offset, seed=1)
+    with pytest.raises(RuntimeError):
+        sidmrg.measurements
+    energies = sidmrg.run(tol=1e-8)
+    np.testing.assert_allclose(energies[-1], evals[idx], atol=1e-6)
+    vec = sidmrg.restored_mps.to_dense()
+    if not np.allclose(vec, evecs[:, idx], atol=1e-6):
+        np.testing.assert_allclose(-vec, evecs[:, idx], atol=1e-6)
+    np.testing.assert_allclose(energies[-1], sidmrg.measurements.expectation_value(model.mpo), atol=1e-6)
+
+
+def test_shift_invert_parity_with_oracle():
+    from tnpy_b200.finite_dmrg import ShiftInvertDMRG
+    from tnpy_b200.matrix_product_state import MatrixProductState
+    from tnpy_b200.model import RandomHeisenberg
+
+    n, chi, offset = 8, 12, 0.1
+    shifted = RandomHeisenberg(n=n, h=10.5, seed=2022, offset=offset)
+    init = oracle.random_mps(n, chi, 2, seed=3)
+    ref = oracle.ShiftInvertDMRG(shifted.mpo.arrays, chi, offset=offset, mps=[a.copy() for a in init])
+    e_ref = ref.run(tol=1e-12, max_sweep=4)
+    gpu = ShiftInvertDMRG(shifted.mpo, bond_dim=chi, offset=offset, mps=MatrixProductState([a.copy() for a in init]))
+    e_gpu = gpu.run(tol=1e-12, max_sweep=4)
+    assert len(e_gpu) == len(e_ref)
+    np.testing.assert_allclose(e_gpu, e_ref, rtol=1e-8)
+    a, b = oracle.mps_to_dense(ref.restored_mps), gpu.restored_mps.to_dense()
+    assert abs(a @ b) / np.sqrt((a @ a) * (b @ b)) > 1 - 1e-8

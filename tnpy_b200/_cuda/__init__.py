@@ -50,6 +50,11 @@ SIGNATURES = {
         c_int,
         [_PD, _PD, _PD, _PD] + [c_int] * 6 + [c_double, c_int, c_int, ctypes.POINTER(c_double), c_void_p, c_size_t, c_void_p],
     ),
+    "tnpy_geig_workspace_bytes": (c_size_t, [c_int] * 8),
+    "tnpy_geig_lowest": (
+        c_int,
+        [_PD] * 7 + [c_int] * 8 + [c_double, c_int, c_int, ctypes.POINTER(c_double), c_void_p, c_size_t, c_void_p],
+    ),
     "tnpy_eigh_workspace_bytes": (c_size_t, [c_int]),
     "tnpy_eigh_lowest": (c_int, [_PD, c_int, _PD, _PD, c_void_p, c_size_t, c_void_p]),
     "tnpy_svd_workspace_bytes": (c_size_t, [c_int, c_int]),
@@ -277,6 +282,24 @@ def eig_lowest(L, W, R, psi, tol: float = 1e-8, max_matvec: int = 1000, ncv: int
         "theta": stats[0], "resid": stats[1], "n_matvec": int(stats[2]), "n_restart": int(stats[3]),
         "converged": bool(stats[4]), "anorm": stats[5],
     }
+
+
+def geig_lowest(LA, WA, RA, LM, WM, RM, psi, tol: float = 1e-8, max_iter: int = 2000, ncv: int = 0, flags_a: int = 0):
+    """Lowest eigenpair of A x = lambda M x (A, M = H_eff of two environments at the same site).
+    In-place on psi (l, d, r).  Returns dict(theta, resid, n_iter, n_restart, converged)."""
+    _need_cuda(LA, WA, RA, LM, WM, RM, psi)
+    l, d, r = psi.shape
+    wla, wra, wlm, wrm = WA.shape[0], WA.shape[1], WM.shape[0], WM.shape[1]
+    lib = load()
+    nbytes = lib.tnpy_geig_workspace_bytes(l, r, wla, wra, wlm, wrm, d, ncv)
+    ws = _scratch.get(nbytes)
+    stats = (c_double * 8)()
+    rc = lib.tnpy_geig_lowest(_ptr(LA), _ptr(WA), _ptr(RA), _ptr(LM), _ptr(WM), _ptr(RM), _ptr(psi), l, r, wla, wra,
+                              wlm, wrm, d, int(flags_a), float(tol), int(max_iter), int(ncv), stats, _ptr(ws), nbytes,
+                              _stream())
+    check(rc, "tnpy_geig_lowest", allow_noconv=True)
+    return {"theta": stats[0], "resid": stats[1], "n_iter": int(stats[2]), "n_restart": int(stats[3]),
+            "converged": bool(stats[4])}
 
 
 def eigh_lowest(H):

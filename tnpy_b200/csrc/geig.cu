@@ -1,0 +1,338 @@
+// On-device lowest eigenpair of the symmetric-definite pencil  A x = lambda M x  with A = H_eff of one
+// environment and M = H_eff of a second one (ShiftInvertDMRG: A from the MPO of H - eps, M from its
+// square; reference finite_dmrg.py:341-355 -> primme.eigsh(A, M=...)).
+//
+// Generalised Davidson without preconditioner: an orthonormal basis V with A V and M V kept alongside,
+// the projected pencil (V^T A V, V^T M V) solved in one CTA (Cholesky of the projected M, reduction to
+// a standard problem, parallel Jacobi), residual r = A x - theta M x as the expansion direction
+// (orthogonalised twice against V), restart with the current Ritz vector plus the residual direction.
+// One 64-byte status read-back per iteration, vectors never leave the device.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace tnpy {
+
+int heff_apply(const double* L, const double* W, const double* R, const double* x, double* y, int l, int r, int wl,
+               int wr, int d, int flags, Workspace& ws, cudaStream_t stream);
+int multi_dot(const double* V, int64_t ldv, int m, const double* w, int64_t n, double* h, int mode,
+              cudaStream_t stream);
+int multi_axpy(const double* V, int64_t ldv, int m, const double* h, double* w, int64_t n, double* nrm_out,
+               cudaStream_t stream);
+int scale_copy(const double* x, double* out, int64_t n, double alpha, const double* s_dev, int inv,
+               cudaStream_t stream);
+int axpy(double alpha, const double* a_dev, const double* x, double* y, int64_t n, cudaStream_t stream);
+int combine(const double* V, int64_t ldv, int m, const double* c, int64_t ldc_, int nout, double* out, int64_t ldo,
+            int64_t n, cudaStream_t stream);
+
+constexpr int kMaxG = 40;  // largest projected pencil (3 x 40 x 40 doubles of shared memory)
+
+// status record
+enum { GS_THETA = 0, GS_RESID = 1, GS_NA = 2, GS_NM = 3, GS_DONE = 4, GS_FAIL = 5, GS_TNORM = 6, GS_SIZE = 8 };
+
+// Fold the new columns ha / hm (length j+1) into GA / GM, then solve the (j+1)x(j+1) pencil.
+// y: coefficients of the lowest Ritz vector (y^T GM y = 1); theta -> status[GS_THETA].
+__global__ void __launch_bounds__(256) geig_small_kernel(double* __restrict__ GA, double* __restrict__ GM,
+                                                         const double* __restrict__ ha, const double* __restrict__ hm,
+                                                         int j, double* __restrict__ y, double* __restrict__ status) {
+  __shared__ double a[kMaxG][kMaxG];  // GA -> C^-1 GA C^-T -> its eigenvalues on the diagonal
+  __shared__ double b[kMaxG][kMaxG];  // GM -> Cholesky factor C (lower)
+  __shared__ double z[kMaxG][kMaxG];  // eigenvectors
+  __shared__ double cs[kMaxG], sn[kMaxG], red[72];
+  __shared__ int pp[kMaxG], qq[kMaxG];
+  __shared__ int fail, lo_idx;
+  const int m = j + 1, tid = threadIdx.x, nt = blockDim.x;
+  if (tid < m) {
+    GA[tid * kMaxG + j] = GA[j * kMaxG + tid] = ha[tid];
+    GM[tid * kMaxG + j] = GM[j * kMaxG + tid] = hm[tid];
+  }
+  if (tid == 0) fail = 0;
+  __syncthreads();
+  for (int idx = tid; idx < m * m; idx += nt) {
+    a[idx / m][idx % m] = GA[(idx / m) * kMaxG + idx % m];
+    b[idx / m][idx % m] = GM[(idx / m) * kMaxG + idx % m];
+  }
+  __syncthreads();
+  // Cholesky b = C C^T (right-looking, lower triangle)
+  for (int k = 0; k < m; ++k) {
+    if (tid == 0) {
+      const double dkk = b[k][k];
+      if (!(dkk > 0.0)) fail = 1;
+      b[k][k] = sqrt(dkk > 0.0 ? dkk : 1.0);
+    }
+    __syncthreads();
+    const double ckk = b[k][k];
+    for (int i = k + 1 + tid; i < m; i += nt) b[i][k] /= ckk;
+    __syncthreads();
+    const int rem = m - k - 1;
+    for (int idx = tid; idx < rem * rem; idx += nt) {
+      const int i = k + 1 + idx / rem, c = k + 1 + idx % rem;
+      if (c <= i) b[i][c] -= b[i][k] * b[c][k];
+    }
+    __syncthreads();
+  }
+  // a <- C^-1 a   (forward substitution, one thread per column)
+  for (int c = tid; c < m; c += nt)
+    for (int i = 0; i < m; ++i) {
+      double v = a[i][c];
+      for (int p = 0; p < i; ++p) v -= b[i][p] * a[p][c];
+      a[i][c] = v / b[i][i];
+    }
+  __syncthreads();
+  // a <- a C^-T   (same substitution on the rows)
+  for (int rrow = tid; rrow < m; rrow += nt)
+    for (int i = 0; i < m; ++i) {
+      double v = a[rrow][i];
+      for (int p = 0; p < i; ++p) v -= b[i][p] * a[rrow][p];
+      a[rrow][i] = v / b[i][i];
+    }
+  __syncthreads();
+  // symmetrise against rounding, then Jacobi
+  for (int idx = tid; idx < m * m; idx += nt) {
+    const int i = idx / m, c = idx % m;
+    if (i < c) {
+      const double v = 0.5 * (a[i][c] + a[c][i]);
+      a[i][c] = v;
+      a[c][i] = v;
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < m * m; idx += nt) z[idx / m][idx % m] = (idx / m == idx % m) ? 1.0 : 0.0;
+  __syncthreads();
+  if (m > 1) {
+    const int me = (m + 1) & ~1, half = me / 2;
+    for (int sweep = 0; sweep < 40; ++sweep) {
+      double off = 0.0, dia = 0.0;
+      for (int idx = tid; idx < m * m; idx += nt) {
+        const double v = a[idx / m][idx % m];
+        if (idx / m == idx % m) dia += v * v; else off += v * v;
+      }
+      off = warp_sum(off);
+      dia = warp_sum(dia);
+      if ((tid & 31) == 0) { red[tid >> 5] = off; red[32 + (tid >> 5)] = dia; }
+      __syncthreads();
+      if (tid == 0) {
+        double o = 0.0, d2 = 0.0;
+        for (int w = 0; w < (nt >> 5); ++w) { o += red[w]; d2 += red[32 + w]; }
+        red[64] = (o <= 1e-31 * d2 || o == 0.0) ? 1.0 : 0.0;
+      }
+      __syncthreads();
+      const bool converged = red[64] != 0.0;
+      __syncthreads();
+      if (converged) break;
+      for (int round = 0; round < me - 1; ++round) {
+        if (tid < half) {
+          int p = (tid == 0) ? me - 1 : (round + tid) % (me - 1);
+          int q = (round + me - 1 - tid) % (me - 1);
+          if (p > q) { const int t = p; p = q; q = t; }
+          double c = 1.0, s = 0.0;
+          if (q < m && a[p][q] != 0.0) {
+            const double tau = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
+            const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+            c = 1.0 / sqrt(1.0 + t * t);
+            s = t * c;
+          }
+          cs[tid] = c; sn[tid] = s; pp[tid] = p; qq[tid] = q;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < half * m; idx += nt) {
+          const int i = idx / m, k = idx % m, p = pp[i], q = qq[i];
+          if (q >= m || sn[i] == 0.0) continue;
+          const double c = cs[i], s = sn[i];
+          const double akp = a[k][p], akq = a[k][q];
+          a[k][p] = c * akp - s * akq;
+          a[k][q] = s * akp + c * akq;
+          const double zkp = z[k][p], zkq = z[k][q];
+          z[k][p] = c * zkp - s * zkq;
+          z[k][q] = s * zkp + c * zkq;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < half * m; idx += nt) {
+          const int i = idx / m, k = idx % m, p = pp[i], q = qq[i];
+          if (q >= m || sn[i] == 0.0) continue;
+          const double c = cs[i], s = sn[i];
+          const double apk = a[p][k], aqk = a[q][k];
+          a[p][k] = c * apk - s * aqk;
+          a[q][k] = s * apk + c * aqk;
+        }
+        __syncthreads();
+      }
+    }
+  }
+  if (tid == 0) {
+    int lo = 0;
+    for (int i = 1; i < m; ++i)
+      if (a[i][i] < a[lo][lo]) lo = i;
+    lo_idx = lo;
+    status[GS_THETA] = a[lo][lo];
+    status[GS_FAIL] = fail ? 1.0 : 0.0;
+    // y = C^-T z_lo  (back substitution), sign: first component non-negative
+    double yy[kMaxG];
+    for (int i = m - 1; i >= 0; --i) {
+      double v = z[i][lo];
+      for (int p = i + 1; p < m; ++p) v -= b[p][i] * yy[p];
+      yy[i] = v / b[i][i];
+    }
+    const double sgn = yy[0] < 0.0 ? -1.0 : 1.0;
+    for (int i = 0; i < m; ++i) y[i] = sgn * yy[i];
+  }
+}
+
+// status[DONE] = ||r|| <= tol * (||A x|| + |theta| ||M x||)
+__global__ void geig_status_kernel(double* __restrict__ status, double tol) {
+  const double scale = status[GS_NA] + fabs(status[GS_THETA]) * status[GS_NM];
+  status[GS_DONE] = (status[GS_RESID] <= tol * scale) ? 1.0 : 0.0;
+}
+
+__global__ void geig_reset_kernel(double* __restrict__ GA, double* __restrict__ GM) {
+  for (int idx = threadIdx.x; idx < kMaxG * kMaxG; idx += blockDim.x) GA[idx] = GM[idx] = 0.0;
+}
+
+struct PinnedG {
+  double* host = nullptr;
+  PinnedG() { cudaMallocHost(&host, sizeof(double) * GS_SIZE); }
+};
+
+static void geig_sizes(int64_t n, int ncv_in, int& ncv) {
+  ncv = ncv_in <= 0 ? 24 : ncv_in;
+  if (ncv > kMaxG) ncv = kMaxG;
+  if (ncv < 3) ncv = 3;
+  if (ncv > n) ncv = (int)n;
+}
+
+}  // namespace tnpy
+
+using namespace tnpy;
+
+extern "C" size_t tnpy_geig_workspace_bytes(int l, int r, int wl_a, int wr_a, int wl_m, int wr_m, int d, int ncv_in) {
+  const int64_t n = (int64_t)l * d * r, ldv = n + (n & 1);
+  int ncv;
+  geig_sizes(n, ncv_in, ncv);
+  const size_t chain_a = tnpy_heff_workspace_bytes(l, r, wl_a, wr_a, d), chain_m = tnpy_heff_workspace_bytes(l, r, wl_m, wr_m, d);
+  return 3 * Workspace::need((size_t)(ncv + 1) * ldv) + 3 * Workspace::need(ldv) + 2 * Workspace::need(kMaxG * kMaxG) +
+         4 * Workspace::need(64) + (chain_a > chain_m ? chain_a : chain_m) + 1024;
+}
+
+extern "C" int tnpy_geig_lowest(const double* LA, const double* WA, const double* RA, const double* LM,
+                                const double* WM, const double* RM, double* psi, int l, int r, int wl_a, int wr_a,
+                                int wl_m, int wr_m, int d, int flags_a, double tol, int max_iter, int ncv_in,
+                                double* stats_host, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TNPY_CHECK_ARG(psi && WA && WM, "null pointer");
+  TNPY_CHECK_ARG(l > 0 && r > 0 && d > 0 && wl_a > 0 && wr_a > 0 && wl_m > 0 && wr_m > 0, "non-positive dimension");
+  const int64_t n = (int64_t)l * d * r, ldv = n + (n & 1);
+  int ncv;
+  geig_sizes(n, ncv_in, ncv);
+  if (tol <= 0.0) tol = 2.220446049250313e-16 * 1e4;
+  if (max_iter <= 0) max_iter = 2000;
+  Workspace ws(workspace, workspace_bytes);
+  double* V = ws.take<double>((size_t)(ncv + 1) * ldv);
+  double* AV = ws.take<double>((size_t)(ncv + 1) * ldv);
+  double* MV = ws.take<double>((size_t)(ncv + 1) * ldv);
+  double* t = ws.take<double>(ldv);
+  double* tmp = ws.take<double>(ldv);
+  double* tmp2 = ws.take<double>(ldv);
+  double* GA = ws.take<double>(kMaxG * kMaxG);
+  double* GM = ws.take<double>(kMaxG * kMaxG);
+  double* ha = ws.take<double>(64);
+  double* hm = ws.take<double>(64);
+  double* y = ws.take<double>(64);
+  double* status = ws.take<double>(64);
+  if (!V || !AV || !MV || !t || !tmp || !tmp2 || !GA || !GM || !ha || !hm || !y || !status) {
+    set_error("tnpy_geig_lowest: workspace too small (%zu bytes given)", workspace_bytes);
+    return TNPY_EWORKSPACE;
+  }
+  const size_t chain_off = ws.used;
+  static PinnedG pinned;
+  double* hst = pinned.host;
+  if (!hst) {
+    set_error("tnpy_geig_lowest: pinned status allocation failed");
+    return TNPY_ECUDA;
+  }
+  auto apply = [&](const double* L, const double* W, const double* R, int wl, int wr, int flags, const double* x,
+                   double* out) {
+    Workspace chain(static_cast<char*>(workspace) + chain_off, workspace_bytes - chain_off);
+    return heff_apply(L, W, R, x, out, l, r, wl, wr, d, flags, chain, stream);
+  };
+
+  geig_reset_kernel<<<1, 256, 0, stream>>>(GA, GM);
+  TNPY_LAUNCH_OK();
+  TNPY_TRY(multi_dot(psi, ldv, 1, psi, n, status + GS_TNORM, 1, stream));
+  TNPY_TRY(scale_copy(psi, V, n, 1.0, status + GS_TNORM, 1, stream));
+  int j = 0, iters = 0, restarts = 0;
+  bool done = false;
+  while (true) {
+    double* vj = V + (int64_t)j * ldv;
+    double* avj = AV + (int64_t)j * ldv;
+    double* mvj = MV + (int64_t)j * ldv;
+    TNPY_TRY(apply(LA, WA, RA, wl_a, wr_a, flags_a, vj, avj));
+    TNPY_TRY(apply(LM, WM, RM, wl_m, wr_m, 0, vj, mvj));
+    ++iters;
+    TNPY_TRY(multi_dot(V, ldv, j + 1, avj, n, ha, 0, stream));
+    TNPY_TRY(multi_dot(V, ldv, j + 1, mvj, n, hm, 0, stream));
+    geig_small_kernel<<<1, 256, 0, stream>>>(GA, GM, ha, hm, j, y, status);
+    TNPY_LAUNCH_OK();
+    const int m = j + 1;
+    // residual r = A x - theta M x with x = V y
+    TNPY_TRY(combine(AV, ldv, m, y, 1, 1, t, ldv, n, stream));
+    TNPY_TRY(multi_dot(t, ldv, 1, t, n, status + GS_NA, 1, stream));
+    TNPY_TRY(combine(MV, ldv, m, y, 1, 1, tmp, ldv, n, stream));
+    TNPY_TRY(multi_dot(tmp, ldv, 1, tmp, n, status + GS_NM, 1, stream));
+    TNPY_TRY(axpy(-1.0, status + GS_THETA, tmp, t, n, stream));
+    TNPY_TRY(multi_dot(t, ldv, 1, t, n, status + GS_RESID, 1, stream));
+    geig_status_kernel<<<1, 1, 0, stream>>>(status, tol);
+    TNPY_LAUNCH_OK();
+    TNPY_CUDA_OK(cudaMemcpyAsync(hst, status, sizeof(double) * GS_SIZE, cudaMemcpyDeviceToHost, stream));
+    TNPY_CUDA_OK(cudaStreamSynchronize(stream));
+    if (hst[GS_FAIL] != 0.0) {
+      set_error("tnpy_geig_lowest: projected M is not positive definite (basis size %d)", m);
+      return TNPY_EINVAL;
+    }
+    done = hst[GS_DONE] != 0.0 || m >= n;
+    if (done || iters >= max_iter) {
+      // psi = V y, normalised like primme / scipy.linalg.eigh(a, b): x^T M x = 1 (y^T GM y = 1 by construction)
+      TNPY_TRY(combine(V, ldv, m, y, 1, 1, psi, ldv, n, stream));
+      break;
+    }
+    if (m == ncv) {
+      // restart: basis = {x, residual direction}; A x and M x come from the stored products
+      TNPY_TRY(combine(V, ldv, m, y, 1, 1, tmp, ldv, n, stream));
+      TNPY_TRY(multi_dot(tmp, ldv, 1, tmp, n, status + GS_TNORM, 1, stream));
+      TNPY_TRY(combine(AV, ldv, m, y, 1, 1, tmp2, ldv, n, stream));
+      TNPY_TRY(scale_copy(tmp2, AV, n, 1.0, status + GS_TNORM, 1, stream));
+      TNPY_TRY(combine(MV, ldv, m, y, 1, 1, tmp2, ldv, n, stream));
+      TNPY_TRY(scale_copy(tmp2, MV, n, 1.0, status + GS_TNORM, 1, stream));
+      TNPY_TRY(scale_copy(tmp, V, n, 1.0, status + GS_TNORM, 1, stream));
+      geig_reset_kernel<<<1, 256, 0, stream>>>(GA, GM);
+      TNPY_LAUNCH_OK();
+      TNPY_TRY(multi_dot(V, ldv, 1, AV, n, ha, 0, stream));
+      TNPY_TRY(multi_dot(V, ldv, 1, MV, n, hm, 0, stream));
+      geig_small_kernel<<<1, 256, 0, stream>>>(GA, GM, ha, hm, 0, y, status);
+      TNPY_LAUNCH_OK();
+      j = 0;
+      ++restarts;
+    }
+    // expand with the residual, orthogonalised twice against the basis
+    double* vnext = V + (int64_t)(j + 1) * ldv;
+    TNPY_TRY(multi_dot(V, ldv, j + 1, t, n, ha, 0, stream));
+    TNPY_TRY(multi_axpy(V, ldv, j + 1, ha, t, n, nullptr, stream));
+    TNPY_TRY(multi_dot(V, ldv, j + 1, t, n, ha, 0, stream));
+    TNPY_TRY(multi_axpy(V, ldv, j + 1, ha, t, n, status + GS_TNORM, stream));
+    TNPY_TRY(scale_copy(t, vnext, n, 1.0, status + GS_TNORM, 1, stream));
+    ++j;
+  }
+  TNPY_CUDA_OK(cudaStreamSynchronize(stream));
+  if (stats_host) {
+    stats_host[0] = hst[GS_THETA];
+    stats_host[1] = hst[GS_RESID];
+    stats_host[2] = (double)iters;
+    stats_host[3] = (double)restarts;
+    stats_host[4] = done ? 1.0 : 0.0;
+    stats_host[5] = hst[GS_NA];
+  }
+  if (!done) {
+    set_error("tnpy_geig_lowest: not converged after %d iterations (resid %.3e)", iters, hst[GS_RESID]);
+    return TNPY_ENOCONV;
+  }
+  return TNPY_OK;
+}

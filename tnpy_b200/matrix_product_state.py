@@ -341,9 +341,12 @@ class Environment:
     #: an environment channel counts as the identity when max|E[:, c, :] - I| is below this
     IDENTITY_TOL = 1e-12
 
-    def __init__(self, mpo: MatrixProductOperator, mps, build_left: bool = True, use_identity_channels: bool = True):
+    def __init__(self, mpo: MatrixProductOperator, mps, build_left: bool = True, use_identity_channels: bool = True,
+                 share_state_with: Optional["Environment"] = None):
         """``mps`` is a :class:`MatrixProductState` (host, as in the reference) or a list of
-        three-leg (l, d, r) float64 CUDA tensors (device-born synthetic states for benchmarks)."""
+        three-leg (l, d, r) float64 CUDA tensors (device-born synthetic states for benchmarks).
+        ``share_state_with``: a second environment over the *same* MPS (ShiftInvertDMRG's H^2
+        environment) borrows the first one's device site tensors instead of copying them."""
         import torch
 
         if not torch.cuda.is_available():
@@ -353,7 +356,11 @@ class Environment:
         self._n_sites = mpo.nsites
         if len(mps) != self._n_sites:
             raise ValueError("MPO and MPS have different lengths.")
-        if isinstance(mps, MatrixProductState):
+        if share_state_with is not None:
+            other = share_state_with
+            self._A, self._shapes = other._A, other._shapes  # same list objects: updates are seen by both
+            self._host_mps, self._dirty = other._host_mps, other._dirty
+        elif isinstance(mps, MatrixProductState):
             self._shapes = [tuple(t.shape) for t in mps]
             self._A = [torch.from_numpy(np.ascontiguousarray(mps.three_leg(i))).cuda() for i in range(self._n_sites)]
             self._host_mps = mps
