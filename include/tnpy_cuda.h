@@ -162,6 +162,12 @@ int tnpy_geig_lowest(const double* LA, const double* WA, const double* RA, const
                      int wl_m, int wr_m, int d, int flags_a, double tol, int max_iter, int ncv,
                      double* stats_host, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Dense route for the same pencil (reference: scipy.linalg.eigh(a, b), finite_dmrg.py:344-348): a, b are
+ * n x n row-major symmetric (b positive definite), both destroyed.  x is normalised to x^T b x = 1. */
+size_t tnpy_geig_dense_workspace_bytes(int n);
+int tnpy_geig_dense_lowest(double* a, double* b, int n, double* theta_dev, double* x, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
 /* ---- a5: linalg.eigh(matrix)  (linalg.py:42-61), k = 1 --------------------------------------
  * Lowest eigenpair of a dense symmetric N x N matrix (row-major, destroyed) by cyclic Jacobi
  * on the device.  evec: N doubles, eval_dev: 1 double (device). */

@@ -55,6 +55,8 @@ SIGNATURES = {
         c_int,
         [_PD] * 7 + [c_int] * 8 + [c_double, c_int, c_int, ctypes.POINTER(c_double), c_void_p, c_size_t, c_void_p],
     ),
+    "tnpy_geig_dense_workspace_bytes": (c_size_t, [c_int]),
+    "tnpy_geig_dense_lowest": (c_int, [_PD, _PD, c_int, _PD, _PD, c_void_p, c_size_t, c_void_p]),
     "tnpy_eigh_workspace_bytes": (c_size_t, [c_int]),
     "tnpy_eigh_lowest": (c_int, [_PD, c_int, _PD, _PD, c_void_p, c_size_t, c_void_p]),
     "tnpy_svd_workspace_bytes": (c_size_t, [c_int, c_int]),
@@ -300,6 +302,22 @@ def geig_lowest(LA, WA, RA, LM, WM, RM, psi, tol: float = 1e-8, max_iter: int = 
     check(rc, "tnpy_geig_lowest", allow_noconv=True)
     return {"theta": stats[0], "resid": stats[1], "n_iter": int(stats[2]), "n_restart": int(stats[3]),
             "converged": bool(stats[4])}
+
+
+def geig_dense_lowest(a, b):
+    """Lowest eigenpair of the dense pencil a x = lambda b x (both destroyed).  Returns (theta 0-d, x)."""
+    import torch
+
+    _need_cuda(a, b)
+    n = a.shape[0]
+    lib = load()
+    nbytes = lib.tnpy_geig_dense_workspace_bytes(n)
+    ws = _scratch.get(nbytes)
+    theta = torch.empty((), dtype=torch.float64, device=a.device)
+    x = torch.empty(n, dtype=torch.float64, device=a.device)
+    check(lib.tnpy_geig_dense_lowest(_ptr(a), _ptr(b), n, _ptr(theta), _ptr(x), _ptr(ws), nbytes, _stream()),
+          "tnpy_geig_dense_lowest")
+    return theta, x
 
 
 def eigh_lowest(H):

@@ -336,3 +336,62 @@ extern "C" int tnpy_geig_lowest(const double* LA, const double* WA, const double
   }
   return TNPY_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Dense route (reference: scipy.linalg.eigh(a, b), finite_dmrg.py:344-348).  The projected H^2 is so
+// ill-conditioned (kappa ~ 1e9 already at N = 256) that no inverse-free Krylov iteration converges
+// in a useful number of steps, so up to a few thousand unknowns the pencil is solved densely:
+//   b = Q diag(s) Q^T (Jacobi SVD of the SPD matrix),  X = Q diag(s)^-1/2,  S = X^T a X,
+//   lowest eigenpair (lambda, z) of S (Jacobi),  x = X z  (x^T b x = 1).
+// ---------------------------------------------------------------------------------------------
+namespace tnpy {
+// X[p][k] = U[p][k] / sqrt(s[k]);  Xt[k][p] = Vt[k][p] / sqrt(s[k])
+__global__ void geig_scale_kernel(const double* __restrict__ U, const double* __restrict__ Vt,
+                                  const double* __restrict__ s, int n, double* __restrict__ X,
+                                  double* __restrict__ Xt) {
+  const int64_t total = (int64_t)n * n;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e / n), k = (int)(e % n);
+    const double sk = s[k], si = s[i];
+    X[e] = sk > 0.0 ? U[e] / sqrt(sk) : 0.0;
+    Xt[e] = si > 0.0 ? Vt[e] / sqrt(si) : 0.0;
+  }
+}
+}  // namespace tnpy
+
+extern "C" size_t tnpy_geig_dense_workspace_bytes(int n) {
+  const size_t nn = (size_t)n * n;
+  return 6 * Workspace::need(nn) + 2 * Workspace::need(n) + tnpy_svd_workspace_bytes(n, n) + tnpy_eigh_workspace_bytes(n) + 2048;
+}
+
+extern "C" int tnpy_geig_dense_lowest(double* a, double* b, int n, double* theta_dev, double* x, void* workspace,
+                                      size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TNPY_CHECK_ARG(a && b && theta_dev && x && n > 0, "bad argument");
+  Workspace ws(workspace, workspace_bytes);
+  const size_t nn = (size_t)n * n;
+  double* U = ws.take<double>(nn);
+  double* Vt = ws.take<double>(nn);
+  double* X = ws.take<double>(nn);
+  double* Xt = ws.take<double>(nn);
+  double* Y = ws.take<double>(nn);
+  double* S = ws.take<double>(nn);
+  double* s = ws.take<double>(n);
+  double* z = ws.take<double>(n);
+  if (!U || !Vt || !X || !Xt || !Y || !S || !s || !z) {
+    set_error("tnpy_geig_dense_lowest: workspace too small");
+    return TNPY_EWORKSPACE;
+  }
+  char* rest = static_cast<char*>(workspace) + ws.used;
+  const size_t rest_bytes = workspace_bytes - ws.used;
+  TNPY_TRY(tnpy_svd(b, n, n, U, s, Vt, rest, rest_bytes, stream_));  // b is destroyed
+  geig_scale_kernel<<<sm_count() * 4, 256, 0, stream>>>(U, Vt, s, n, X, Xt);
+  TNPY_LAUNCH_OK();
+  // Y = a^T X (= a X, a symmetric);  S = X^T Y
+  TNPY_TRY(gemm_tn(a, n, X, n, plain_out(Y, n, n), n, n, n, 0, TNPY_GEMM_AUTO, stream));
+  TNPY_TRY(gemm_tn(X, n, Y, n, plain_out(S, n, n), n, n, n, 0, TNPY_GEMM_AUTO, stream));
+  TNPY_TRY(tnpy_eigh_lowest(S, n, theta_dev, z, rest, rest_bytes, stream_));
+  // x = X z = sum_k z[k] * Xt[k][:]
+  TNPY_TRY(combine(Xt, n, n, z, 1, 1, x, n, n, stream));
+  return TNPY_OK;
+}

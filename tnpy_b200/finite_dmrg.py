@@ -247,9 +247,21 @@ class ShiftInvertDMRG(FiniteDMRG):
         arrays[-1] = arrays[-1][:, :, 0]
         self._restored_mps = MatrixProductState(arrays)
 
+    #: up to this many unknowns the local pencil is solved densely on the device (the projected H^2 is too
+    #: ill-conditioned for inverse-free Krylov iterations, see csrc/geig.cu); larger sites iterate
+    dense_pencil_dim = 2048
+
     def _solve_on_device(self, site: int, tol: float, **kwargs) -> float:
         env, env2 = self._env, self._env2
         psi = env.device_tensor(site)
+        if psi.numel() <= self.dense_pencil_dim:
+            a = env.one_site_full_matrix_device(site)
+            b = env2.one_site_full_matrix_device(site)
+            theta, x = _cuda.geig_dense_lowest(a, b)
+            psi.copy_(x.reshape(psi.shape))
+            env._dirty.add(site)
+            self.solver_stats.append({"site": site, "dense": True, "n_matvec": 0})
+            return float(theta.item())
         la, wa, ra = env.operands(site)
         lm, wm, rm = env2.operands(site)
         opts = {}
