@@ -452,6 +452,16 @@ def run_sharded(args):
         dist.barrier()
         torch.cuda.synchronize()
 
+    # per-GPU FP64 roofline denominator: cuBLAS dgemm 8192^3 on this rank (yardstick only), max over ranks
+    a8 = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
+    b8 = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
+    torch.matmul(a8, b8)
+    best = min(cuda_time(lambda: torch.matmul(a8, b8), 1, torch.cuda.synchronize) for _ in range(3))
+    peak = torch.tensor([2.0 * 8192**3 / best / 1e12], dtype=torch.float64, device="cuda")
+    dist.all_reduce(peak, op=dist.ReduceOp.MAX)
+    fp64_peak = float(peak.item())
+    del a8, b8
+
     for _ in range(args.warmup):
         step()
     barrier()
@@ -512,8 +522,10 @@ def run_sharded(args):
                 "flops_per_step": flops, "l2_policy": "operands exceed L2; no flush needed",
             },
             "roofline": {
-                "bound": "tensor", "achieved": flops * args.steps / tc / 1e12 / world, "peak": None, "unit": "TFLOP/s",
-                "frac": None, "traffic": None, "kernel": "local chain per GPU (gemm_tn_dmma x2 + wmix), all-gather excluded",
+                "bound": "tensor", "achieved": flops * args.steps / tc / 1e12 / world, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": flops * args.steps / tc / 1e12 / world / fp64_peak, "traffic": None,
+                "kernel": "local chain per GPU (gemm_tn_dmma x2 + wmix), all-gather excluded",
+                "peak_source": "cuBLAS dgemm 8192^3 per GPU, best of 3, max over ranks",
                 "ms_compute_per_step": tc / args.steps * 1e3, "ms_allgather_per_step": (t - tc) / args.steps * 1e3,
             },
             "e2e": {
