@@ -125,3 +125,40 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_cuda, "LIB_PATH", tmp_path / "nope.so")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         _cuda.load()
+
+
+def test_user_mps_can_be_canonicalised_on_device():
+    """a non-canonical user MPS (plain Gaussian tensors) is right-canonicalised by device
+    SVD splits; the state itself is unchanged and the run reaches the ED energy."""
+    from tnpy_b200.finite_dmrg import FiniteDMRG
+    from tnpy_b200.matrix_product_state import Environment, MatrixProductState
+    from tnpy_b200.model import XXZ
+
+    n, chi = 8, 16
+    rng = np.random.default_rng(0)
+    dims = [1, 2, 4, 8, 16, 8, 4, 2, 1]
+    arrays = [rng.standard_normal((dims[i], 2, dims[i + 1])) for i in range(n)]
+    arrays[0], arrays[-1] = arrays[0][0], arrays[-1][:, :, 0]
+    mps = MatrixProductState(arrays)
+    before = mps.to_dense()
+    model = XXZ(n=n, delta=0.5)
+    env = Environment(model.mpo, mps.copy(), canonicalize=True)
+    after = env.mps
+    np.testing.assert_allclose(after.to_dense(), before, atol=1e-10 * np.abs(before).max())
+    for site in range(1, n):
+        a = after.three_leg(site)
+        m = a.reshape(a.shape[0], -1)
+        np.testing.assert_allclose(m @ m.T, np.eye(a.shape[0]), atol=1e-12)
+    energies = FiniteDMRG(model.mpo, bond_dim=chi, mps=mps, canonicalize=True).run(tol=1e-9)
+    np.testing.assert_allclose(energies[-1], oracle.exact_ground_energy(model.mpo.arrays), atol=1e-8)
+
+
+def test_odd_bond_dimension():
+    """chi = 15: odd leading dimensions take the generic GEMM / scalar vector paths end to end."""
+    from tnpy_b200.finite_dmrg import FiniteDMRG
+    from tnpy_b200.model import XXZ
+
+    model = XXZ(n=8, delta=0.5)
+    energies = FiniteDMRG(model.mpo, bond_dim=15, seed=4).run(tol=1e-9)
+    e_ed = oracle.exact_ground_energy(model.mpo.arrays)
+    assert energies[-1] >= e_ed - 1e-10 and energies[-1] - e_ed < 1e-5

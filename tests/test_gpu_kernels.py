@@ -405,3 +405,25 @@ def cu_flags(which):
     from tnpy_b200 import _cuda
 
     return {"left": _cuda.LEFT_IDENTITY, "right": _cuda.RIGHT_IDENTITY}[which]
+
+
+@pytest.mark.parametrize("rows,cols,rank", [(16, 8, 5), (8, 16, 3), (300, 200, 120), (200, 300, 0)])
+def test_svd_exact_null_space(cu, rows, cols, rank):
+    """Exactly rank-deficient input (product-state-like site tensors): zero singular values are reported
+    as 0 and U / Vt are still complete isometries (LAPACK's orthonormal completion)."""
+    rng = np.random.default_rng(rows + cols + rank)
+    a = rng.standard_normal((rows, rank)) @ rng.standard_normal((rank, cols)) if rank else np.zeros((rows, cols))
+    k = min(rows, cols)
+    if rank:  # make the null space exact: zero out whole columns / rows of a factor instead of relying on rounding
+        a = np.zeros((rows, cols))
+        a[:, :rank] = rng.standard_normal((rows, rank))
+        if rows < cols:
+            a = np.zeros((rows, cols))
+            a[:rank, :] = rng.standard_normal((rank, cols))
+    u, s, vt = (t.cpu().numpy() for t in cu.svd(dev(a)))
+    s_ref = np.linalg.svd(a, compute_uv=False)
+    assert np.abs(s - s_ref).max() <= 1e-12 * max(s_ref[0], 1e-300) + 1e-130
+    assert np.all(s[rank:] < 1e-100)
+    assert np.abs(u.T @ u - np.eye(k)).max() < 1e-11
+    assert np.abs(vt @ vt.T - np.eye(k)).max() < 1e-11
+    assert np.abs(u @ np.diag(s) @ vt - a).max() <= 1e-12 * max(s_ref[0], 1.0)

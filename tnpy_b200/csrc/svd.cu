@@ -411,6 +411,55 @@ __global__ void __launch_bounds__(256) jb_apply_kernel(double* __restrict__ GP, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// exact null vectors: LAPACK returns an orthonormal completion for zero singular values, and the DMRG
+// sweep needs it (A[site] must stay an isometry).  Rows whose norm is (numerically) zero are replaced
+// by pseudo-random rows of norm ~1e-140 * max before the Jacobi iteration: the rotations
+// orthogonalise them against everything else without moving the other rows (angles ~1e-140), their
+// direction becomes the completion, and their singular value is reported as exactly 0.
+// ---------------------------------------------------------------------------------------------
+constexpr double kNullFill = 1e-140;   // norm scale of injected rows (squares stay representable)
+constexpr double kNullCut = 1e-120;    // singular values below cut * s_max are reported as 0
+
+__global__ void max_kernel(const double* __restrict__ v, int n, double* __restrict__ out) {
+  __shared__ double sh[32];
+  double m = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmax(m, v[i]);
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, sh[w]);
+    *out = m;
+  }
+}
+
+// rows k < n of G with norms[k] <= 1e-150 * max (or max == 0) get deterministic pseudo-random entries
+__global__ void __launch_bounds__(256) fill_null_rows_kernel(double* __restrict__ G, int n, int m, int64_t ld,
+                                                             const double* __restrict__ norms,
+                                                             const double* __restrict__ max_norm) {
+  const int k = blockIdx.x;
+  const double mx = *max_norm;
+  if (norms[k] > 1e-150 * mx && mx > 0.0) return;
+  const double scale = kNullFill * (mx > 0.0 ? mx : 1.0);
+  for (int i = threadIdx.x; i < m; i += blockDim.x) {
+    // splitmix64 hash of (k, i) -> uniform in (-1, 1)
+    unsigned long long z = ((unsigned long long)k << 32) ^ (unsigned long long)i ^ 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    G[(int64_t)k * ld + i] = scale * ((double)(z >> 11) * (2.0 / 9007199254740992.0) - 1.0);
+  }
+}
+
+// s is sorted descending: report numerically-null singular values as exactly zero
+__global__ void zero_null_s_kernel(double* __restrict__ s, int n) {
+  const double top = s[0];
+  __syncthreads();
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
+    if (k > 0 && s[k] < kNullCut * top) s[k] = 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // finalize: norms, deterministic descending rank, scatter into U / s / Vt
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) row_norm_kernel(const double* __restrict__ G, int n, int m, int64_t ldg,
@@ -662,6 +711,12 @@ extern "C" int tnpy_svd(double* A, int rows, int cols, double* U, double* s, dou
       TNPY_TRY(transpose2d(A, rows, cols, Gt, nullptr, stream));
       Gm = Gt;
     }
+    row_norm_kernel<<<n, 256, 0, stream>>>(Gm, n, m, m, norms);
+    TNPY_LAUNCH_OK();
+    max_kernel<<<1, 256, 0, stream>>>(norms, n, reinterpret_cast<double*>(counter) + 1);
+    TNPY_LAUNCH_OK();
+    fill_null_rows_kernel<<<n, 256, 0, stream>>>(Gm, n, m, m, norms, reinterpret_cast<double*>(counter) + 1);
+    TNPY_LAUNCH_OK();
     TNPY_TRY(hestenes_small(Gm, n, m, Pm, stream));
     G = Gm;
     P = Pm;
@@ -695,6 +750,8 @@ extern "C" int tnpy_svd(double* A, int rows, int cols, double* U, double* s, dou
     TNPY_CUDA_OK(cudaStreamSynchronize(stream));
     jb_init_kernel<<<sm_count() * 8, 256, 0, stream>>>(A, rows, cols, tall ? 1 : 0, src, GP, n, m, p.n_pad, p.ld);
     TNPY_LAUNCH_OK();
+    fill_null_rows_kernel<<<n, 256, 0, stream>>>(GP, n, m, p.ld, s, s);  // sorted: norm of row k is s[k], max s[0]
+    TNPY_LAUNCH_OK();
     TNPY_TRY(hestenes_block(GP, p, m, n_big, partial, Jt, skip, counter, stream, &g_last_svd_sweeps));
     G = GP;
     P = GP + m;
@@ -704,6 +761,8 @@ extern "C" int tnpy_svd(double* A, int rows, int cols, double* U, double* s, dou
   row_norm_kernel<<<n, 256, 0, stream>>>(G, n, m, ldg, norms);
   TNPY_LAUNCH_OK();
   rank_kernel<<<ceil_div(n, 128), 128, 0, stream>>>(norms, n, rank, s);
+  TNPY_LAUNCH_OK();
+  zero_null_s_kernel<<<1, 256, 0, stream>>>(s, n);
   TNPY_LAUNCH_OK();
   if (tall)  // U = W^T (rows x n): U[i][r] ; Vt = P (n x cols): Vt[r][j]
     scatter_kernel<<<n, 256, 0, stream>>>(G, n, m, ldg, P, ldp, norms, rank, U, 1, n, Vt, cols, 1);

@@ -47,6 +47,7 @@ class FiniteDMRG:
         chi: Optional[int] = None,
         compute_variance: bool = True,
         seed: Optional[int] = None,
+        canonicalize: bool = False,
     ):
         if bond_dim is None:
             bond_dim = chi
@@ -60,7 +61,9 @@ class FiniteDMRG:
         self._compute_variance = compute_variance
         if mps is None:
             mps = MatrixProductState.random(n=self.n_sites, bond_dim=self.bond_dim, phys_dim=self.phys_dim, seed=seed)
-        self._env = Environment(mpo=mpo, mps=mps)
+        # canonicalize=True right-canonicalises a user-supplied MPS on the device first; the reference
+        # (and the default here) trusts the caller, as MatrixProductState.random is right-canonical
+        self._env = Environment(mpo=mpo, mps=mps, canonicalize=canonicalize)
         self._energies: List[float] = [np.nan]
         self._variances: List[float] = [np.nan]
         self.solver_stats: List[Dict] = []  # one record per local solve of the last sweep

@@ -342,7 +342,7 @@ class Environment:
     IDENTITY_TOL = 1e-12
 
     def __init__(self, mpo: MatrixProductOperator, mps, build_left: bool = True, use_identity_channels: bool = True,
-                 share_state_with: Optional["Environment"] = None):
+                 share_state_with: Optional["Environment"] = None, canonicalize: bool = False):
         """``mps`` is a :class:`MatrixProductState` (host, as in the reference) or a list of
         three-leg (l, d, r) float64 CUDA tensors (device-born synthetic states for benchmarks).
         ``share_state_with``: a second environment over the *same* MPS (ShiftInvertDMRG's H^2
@@ -384,11 +384,22 @@ class Environment:
         self._left_identity: Dict[int, bool] = {}
         self._right_identity: Dict[int, bool] = {}
         self.bond_singular_values: Dict[int, object] = {}
+        if canonicalize and share_state_with is None:
+            self.right_canonicalize()
         if build_left:  # the reference builds both stacks up front (:247-250)
             for site in range(1, self.n_sites):
                 self.update_left(site)
         for site in range(self.n_sites - 2, -1, -1):
             self.update_right(site)
+
+    def right_canonicalize(self):
+        """Bring a user-supplied MPS into the right-canonical form the solver assumes (the reference
+        relies on ``MatrixProductState.random`` being right-canonical and does not canonicalise a
+        user ``mps=``, finite_dmrg.py:67-74).  Device SVD splits from the last site down."""
+        for site in range(self.n_sites - 1, 0, -1):
+            a, nb, _ = _split_on_device(self._A[site], self._A[site - 1], Direction.LEFTWARD)
+            self._A[site], self._A[site - 1] = a.contiguous(), nb.contiguous()
+            self._dirty.update((site, site - 1))
 
     def close(self):
         logger.info("Deleting left and right environments.")
