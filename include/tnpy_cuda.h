@@ -111,9 +111,8 @@ int tnpy_env_update_right(const double* R, const double* A, const double* W, dou
                           size_t workspace_bytes, void* stream);
 
 /* ---- a6: Environment.one_site_full_matrix  (matrix_product_state.py:372-409) ---------------
- * H[(l,p,r),(m,q,s)] dense, N = l*d*r; H is N x N row-major.  Built by applying the matvec
- * chain to the N unit vectors in one batched pass (rows of a symmetric matrix).
- * Workspace: tnpy_heff_dense_workspace_bytes(). */
+ * H[(l,p,r),(m,q,s)] = sum_{a,b} L[l,a,m] W[a,b,p,q] R[r,b,s] dense, N = l*d*r <= 4096; H is N x N
+ * row-major (one thread per matrix element).  Workspace: none needed (query returns a token size). */
 size_t tnpy_heff_dense_workspace_bytes(int l, int r, int wl, int wr, int d);
 int tnpy_heff_dense(const double* L, const double* W, const double* R, double* H,
                     int l, int r, int wl, int wr, int d, void* workspace, size_t workspace_bytes,
@@ -178,8 +177,10 @@ int tnpy_eigh_lowest(double* H, int n, double* eval_dev, double* evec, void* wor
 /* ---- a8: linalg.svd(matrix, cutoff)  (linalg.py:9-23) ---------------------------------------
  * Thin SVD of a row-major rows x cols matrix A (destroyed): A = U diag(s) Vt with singular values
  * sorted descending (ties broken by original column index => deterministic).  k = min(rows, cols).
- * U: rows x k (ldu = k), s: k, Vt: k x cols (ldvt = cols).  One-sided Jacobi (Hestenes) on the
- * short side after a Householder-free orthogonal reduction; see DESIGN.md.
+ * U: rows x k (ldu = k), s: k, Vt: k x cols (ldvt = cols).  One-sided Jacobi (Hestenes) on the short
+ * side: a single-CTA shared-memory kernel for small problems, block Jacobi on the FP64 tensor pipe
+ * otherwise.  Exactly-zero singular values are reported as 0 with an orthonormal
+ * completion of U / Vt, as LAPACK does.  Synchronises the stream once per Jacobi sweep.
  * Workspace: tnpy_svd_workspace_bytes(). */
 size_t tnpy_svd_workspace_bytes(int rows, int cols);
 /* Jacobi sweeps the last tnpy_svd call on this process needed (-1: single-CTA shared-memory path). */

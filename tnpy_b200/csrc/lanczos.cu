@@ -4,7 +4,7 @@
 // Thick-restart Lanczos with full (twice-applied classical Gram-Schmidt) reorthogonalisation and an
 // explicitly projected matrix T = V^T H V.  Everything -- the matvec chain, the vector kernels,
 // the Rayleigh-Ritz solve (parallel cyclic Jacobi on T in one CTA) and the convergence test -- runs
-// on the device; the host only reads one 5-double status record per Lanczos step to decide whether to
+// on the device; the host only reads one 64-byte status record per Lanczos step to decide whether to
 // stop or restart.  Basis vectors never leave HBM.
 #include <math.h>
 

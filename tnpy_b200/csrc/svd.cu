@@ -10,8 +10,9 @@
 //   wide input  A (rows <  cols): G = A,    U = P^T, Vt = W.
 //   tall input  A (rows >= cols): G = A^T,  U = W^T, Vt = P.
 // Two execution paths: a single-CTA kernel with G and P resident in shared memory (edge bonds,
-// small chi: no launch or sync overhead), and a per-round multi-CTA kernel (one CTA per row pair,
-// rows staged in shared memory, L2-resident matrix) for large bonds.
+// small chi: no launch or sync overhead), and block Jacobi on the FP64 tensor pipe for large bonds
+// (32-row blocks paired round-robin; per round a Gram kernel, a 64x64 rotation kernel and an apply
+// kernel -- see the comment above jb_gram_kernel).
 #include <math.h>
 
 #include "common.cuh"
