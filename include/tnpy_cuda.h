@@ -78,6 +78,15 @@ int tnpy_probe_fp64(int kind, int threads_per_block, int blocks_per_sm, int ilp,
 int tnpy_gemm_tn(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
                  int M, int N, int K, int accumulate, int algo, void* stream);
 
+/* ---- EXPERIMENT: the same GEMM in FP64 accuracy on the tcgen05 int8 tensor cores (Ozaki scheme: `slices`
+ * error-free 7-bit slices per operand, exact int8 x int8 -> int32 slice products accumulated in TMEM,
+ * FP64 recombination in the epilogue).  Not used by the chains unless asked for; reported separately.
+ * phase: 0 = slice + multiply, 1 = slice only into the workspace, 2 = multiply from the workspace. */
+size_t tnpy_ozaki_workspace_bytes(int M, int N, int K, int slices);
+int tnpy_ozaki_gemm_tn(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
+                       int M, int N, int K, int slices, int accumulate, int phase, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
 /* ---- a1: Environment.one_site_matvec(site).matvec(x)  (matrix_product_state.py:411-440) ----
  * y[m,q,s] = sum_{l,a,p,b,r} L[l,a,m] W[a,b,p,q] R[r,b,s] x[l,p,r]
  * x, y: (l, d, r).  Workspace: tnpy_heff_workspace_bytes(). */

@@ -29,6 +29,11 @@ SIGNATURES = {
     "tnpy_set_gemm_tile": (c_int, [c_int]),
     "tnpy_probe_fp64": (c_int, [c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_double), c_void_p]),
     "tnpy_gemm_tn": (c_int, [_PD, c_int64, _PD, c_int64, _PD, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "tnpy_ozaki_workspace_bytes": (c_size_t, [c_int] * 4),
+    "tnpy_ozaki_gemm_tn": (
+        c_int,
+        [_PD, c_int64, _PD, c_int64, _PD, c_int64] + [c_int] * 6 + [c_void_p, c_size_t, c_void_p],
+    ),
     "tnpy_heff_workspace_bytes": (c_size_t, [c_int] * 5),
     "tnpy_heff_apply": (c_int, [_PD, _PD, _PD, _PD, _PD] + [c_int] * 6 + [c_void_p, c_size_t, c_void_p]),
     "tnpy_identity_defect": (c_int, [_PD, c_int, c_int, c_int, _PD, c_void_p, c_size_t, c_void_p]),
@@ -166,6 +171,24 @@ def gemm_tn(a, b, out=None, accumulate: bool = False, algo: int = GEMM_AUTO):
     rc = load().tnpy_gemm_tn(_ptr(a), a.stride(0), _ptr(b), b.stride(0), _ptr(out), out.stride(0), m, n, k,
                              int(accumulate), algo, _stream())
     check(rc, "tnpy_gemm_tn")
+    return out
+
+
+def ozaki_gemm_tn(a, b, out=None, slices: int = 8, accumulate: bool = False, phase: int = 0):
+    """EXPERIMENT: out[m, n] (+)= sum_k a[k, m] b[k, n] in FP64 accuracy on the int8 tensor cores."""
+    import torch
+
+    _need_cuda(a, b, out)
+    k, m = a.shape
+    n = b.shape[1]
+    if out is None:
+        out = torch.empty((m, n), dtype=torch.float64, device=a.device)
+    lib = load()
+    nbytes = lib.tnpy_ozaki_workspace_bytes(m, n, k, slices)
+    ws = _scratch.get(nbytes)
+    rc = lib.tnpy_ozaki_gemm_tn(_ptr(a), a.stride(0), _ptr(b), b.stride(0), _ptr(out), out.stride(0), m, n, k, int(slices),
+                                int(accumulate), int(phase), _ptr(ws), nbytes, _stream())
+    check(rc, "tnpy_ozaki_gemm_tn")
     return out
 
 

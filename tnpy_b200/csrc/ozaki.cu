@@ -1,0 +1,358 @@
+// EXPERIMENT (reported separately, never substituted silently): FP64-accurate GEMM on the 5th-gen
+// tensor cores.  tcgen05 has no f64 kind, so C = A^T B is evaluated with the Ozaki scheme: every
+// operand column is scaled by a power of two and split error-free into S signed 7-bit slices,
+//     A[k][m] = 2^ea[m] * sum_i a_i[k][m] * 2^(-7(i+1)),    |a_i| <= 64,
+// all slice products a_i^T b_j are exact int8 x int8 -> int32 GEMMs (tcgen05.mma.kind::i8, accumulators
+// in TMEM), slice pairs of equal weight i + j = d share one TMEM accumulator (exact: < 2^31 for
+// K <= 65536), pairs with i + j >= S are below the target precision and skipped, and the epilogue
+// recombines the S accumulators in FP64:  C[m][n] = 2^(ea[m]+eb[n]) * sum_d acc_d[m][n] * 2^(-7(d+2)).
+//
+// Kernel anatomy (one 128 x 64 output tile per CTA, 256 threads):
+//   warp 0   TMA producer: one 3-D box (k, rows, slices) per operand per stage, 64B-swizzled, K-major
+//   warp 1   MMA issuer (one lane): S(S+1)/2 slice pairs x 2 k-steps of tcgen05.mma per stage,
+//            tcgen05.commit to the stage's empty barrier, final commit to the epilogue barrier
+//   warp 2   TMEM allocator (512 columns = S accumulators of 64 int32 columns)
+//   warps 4-7 epilogue: tcgen05.ld 32x32b, FP64 recombination, scaled store through the GEMM row map
+#include <cudaTypedefs.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace tnpy {
+
+constexpr int kOzBM = 128;   // tile rows (TMEM lanes)
+constexpr int kOzBN = 64;    // tile columns per accumulator
+constexpr int kOzBK = 64;    // k elements (= bytes) per stage row: one 64B swizzle span
+constexpr int kOzStages = 2;
+constexpr int kOzMaxSlices = 8;  // 8 accumulators x 64 columns = all 512 TMEM columns
+
+// ---------------------------------------------------------------------------------------------
+// slicing
+// ---------------------------------------------------------------------------------------------
+// scale[c] = 2^e with |P[k][c]| / 2^e <= 0.5 for all k  (0 for an all-zero column)
+__global__ void __launch_bounds__(256) oz_colscale_kernel(const double* __restrict__ P, int64_t ld, int K, int MN,
+                                                          double* __restrict__ scale) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= MN) return;
+  double mx = 0.0;
+  for (int k = 0; k < K; ++k) mx = fmax(mx, fabs(P[(int64_t)k * ld + c]));
+  scale[c] = mx > 0.0 ? ldexp(1.0, ilogb(mx) + 2) : 0.0;
+}
+
+// slices[s][c][k] (k contiguous, Kp bytes per row) from P[k][c]; 32 x 32 shared-memory transpose
+template <int S>
+__global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict__ P, int64_t ld, int K, int MN,
+                                                       const double* __restrict__ scale, int8_t* __restrict__ slices,
+                                                       int64_t Kp, int64_t slice_stride) {
+  __shared__ int8_t tile[S][32][33];
+  const int c0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
+  for (int i = ty; i < 32; i += 8) {
+    const int k = k0 + i, c = c0 + tx;
+    double t = 0.0;
+    if (k < K && c < MN) {
+      const double sc = scale[c];
+      t = sc > 0.0 ? P[(int64_t)k * ld + c] / sc : 0.0;  // exact: power-of-two scaling, |t| <= 0.5
+    }
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      t *= 128.0;
+      const double dgt = rint(t);  // |dgt| <= 64
+      tile[s][i][tx] = (int8_t)(int)dgt;
+      t -= dgt;                    // exact remainder, |t| <= 0.5
+    }
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, k = k0 + tx;
+    if (c < MN && k < Kp) {
+#pragma unroll
+      for (int s = 0; s < S; ++s) slices[s * slice_stride + (int64_t)c * Kp + k] = (k < K) ? tile[s][tx][i] : (int8_t)0;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// tcgen05 kernel
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t oz_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void oz_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(oz_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void oz_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(oz_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void oz_mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = oz_smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void oz_tma_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(oz_smem_u32(dst)), "l"(map), "r"(oz_smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// K-major operand tile, rows of kOzBK bytes, 64B swizzle: SBO = 8 rows * 64 B, LBO unused, version 1
+__device__ __forceinline__ uint64_t oz_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);             // start address
+  d |= (uint64_t)0 << 16;                             // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)((8 * kOzBK) >> 4) << 32;            // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                             // descriptor version (sm_100)
+  d |= (uint64_t)4 << 61;                             // layout type: SWIZZLE_64B
+  return d;
+}
+__device__ __forceinline__ void oz_mma_i8(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  const uint32_t z = 0;
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n}\n"
+      ::"r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(z), "r"(z), "r"(z), "r"(z)
+      : "memory");
+}
+__device__ __forceinline__ void oz_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(oz_smem_u32(bar))
+               : "memory");
+}
+
+template <int S>
+__global__ void __launch_bounds__(256, 1)
+    oz_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const double* __restrict__ scaleA, const double* __restrict__ scaleB, GemmOut out, int M, int N,
+                  int KT, int accumulate) {
+  constexpr int kABytes = S * kOzBM * kOzBK, kBBytes = S * kOzBN * kOzBK;
+  constexpr int kStageBytes = kABytes + kBBytes;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kOzStages * kStageBytes);
+  uint64_t* empty_bar = full_bar + kOzStages;
+  uint64_t* tmem_full = empty_bar + kOzStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * kOzBM, n0 = blockIdx.x * kOzBN;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kOzStages; ++s) {
+      oz_mbar_init(&full_bar[s], 1);
+      oz_mbar_init(&empty_bar[s], 1);
+    }
+    oz_mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(oz_smem_u32(tmem_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int kt = 0; kt < KT; ++kt) {
+        oz_mbar_wait(&empty_bar[stage], phase ^ 1);
+        oz_mbar_expect_tx(&full_bar[stage], kStageBytes);
+        uint8_t* sa = smem + stage * kStageBytes;
+        oz_tma_3d(sa, &tmA, &full_bar[stage], kt * kOzBK, m0, 0);
+        oz_tma_3d(sa + kABytes, &tmB, &full_bar[stage], kt * kOzBK, n0, 0);
+        if (++stage == kOzStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // instruction descriptor: D = S32, A = B = signed int8, both K-major, N = 64, M = 128
+      constexpr uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kOzBN >> 3) << 17) | ((uint32_t)(kOzBM >> 4) << 24);
+      uint32_t stage = 0, phase = 0;
+      for (int kt = 0; kt < KT; ++kt) {
+        oz_mbar_wait(&full_bar[stage], phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = oz_smem_u32(smem + stage * kStageBytes);
+        const uint32_t sb = sa + kABytes;
+#pragma unroll
+        for (int kk = 0; kk < kOzBK / 32; ++kk) {
+#pragma unroll
+          for (int i = 0; i < S; ++i) {
+            const uint64_t da = oz_smem_desc(sa + i * (kOzBM * kOzBK) + kk * 32);
+#pragma unroll
+            for (int j = 0; j < S - i; ++j) {
+              const uint64_t db = oz_smem_desc(sb + j * (kOzBN * kOzBK) + kk * 32);
+              // accumulator d = i + j; its first contribution in program order is (kt, kk, i) = (0, 0, 0)
+              oz_mma_i8(tmem_base + (uint32_t)((i + j) * kOzBN), da, db, idesc, (kt | kk | i) != 0 ? 1u : 0u);
+            }
+          }
+        }
+        oz_commit(&empty_bar[stage]);  // frees the stage once these MMAs have read it
+        if (++stage == kOzStages) { stage = 0; phase ^= 1; }
+      }
+      oz_commit(tmem_full);
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;  // TMEM lane quadrant this warp may read
+    oz_mbar_wait(tmem_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int m = m0 + q * 32 + lane;
+    const double sa = (m < M) ? scaleA[m] : 0.0;
+    double* crow = nullptr;
+    if (m < M) crow = out.C + (int64_t)(m / out.m_inner) * out.c_outer + (int64_t)(m % out.m_inner) * out.c_inner;
+    for (int c0 = 0; c0 < kOzBN; c0 += 8) {
+      double acc[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[c] = 0.0;
+#pragma unroll
+      for (int d = S - 1; d >= 0; --d) {  // smallest weights first
+        uint32_t v[8];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(d * kOzBN + c0);
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                     : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const double wgt = ldexp(1.0, -7 * (d + 2));
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] = fma((double)(int)v[c], wgt, acc[c]);
+      }
+      if (m < M) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const int n = n0 + c0 + c;
+          if (n < N) {
+            const double val = acc[c] * sa * scaleB[n];
+            crow[n] = accumulate ? crow[n] + val : val;
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 oz_encoder() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  });
+  return fn;
+}
+
+// slices[s][row][k]: dims (Kp, rows, S), box (kOzBK, box_rows, S), 64B swizzle
+static int oz_make_map(CUtensorMap* map, const int8_t* base, int64_t Kp, int rows, int S, int box_rows) {
+  auto enc = oz_encoder();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return TNPY_ECUDA;
+  }
+  cuuint64_t dims[3] = {(cuuint64_t)Kp, (cuuint64_t)rows, (cuuint64_t)S};
+  cuuint64_t strides[2] = {(cuuint64_t)Kp, (cuuint64_t)Kp * rows};
+  cuuint32_t box[3] = {(cuuint32_t)kOzBK, (cuuint32_t)box_rows, (cuuint32_t)S};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<int8_t*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("ozaki: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return TNPY_ECUDA;
+  }
+  return TNPY_OK;
+}
+
+template <int S>
+static int oz_slice(const double* P, int64_t ld, int K, int MN, double* scale, int8_t* slices, int64_t Kp,
+                    cudaStream_t stream) {
+  oz_colscale_kernel<<<ceil_div(MN, 256), 256, 0, stream>>>(P, ld, K, MN, scale);
+  TNPY_LAUNCH_OK();
+  dim3 grid(ceil_div(MN, 32), (unsigned)((Kp + 31) / 32));
+  oz_slice_kernel<S><<<grid, 256, 0, stream>>>(P, ld, K, MN, scale, slices, Kp, (int64_t)MN * Kp);
+  TNPY_LAUNCH_OK();
+  return TNPY_OK;
+}
+
+template <int S>
+static int oz_gemm(const int8_t* As, const double* scaleA, const int8_t* Bs, const double* scaleB, GemmOut out, int M,
+                   int N, int64_t Kp, int accumulate, cudaStream_t stream) {
+  CUtensorMap tmA, tmB;
+  TNPY_TRY(oz_make_map(&tmA, As, Kp, M, S, kOzBM));
+  TNPY_TRY(oz_make_map(&tmB, Bs, Kp, N, S, kOzBN));
+  constexpr int smem = kOzStages * S * (kOzBM + kOzBN) * kOzBK + 1024 + 128;
+  static bool configured = false;
+  if (!configured) {
+    TNPY_CUDA_OK(cudaFuncSetAttribute(oz_mma_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  dim3 grid(ceil_div(N, kOzBN), ceil_div(M, kOzBM));
+  oz_mma_kernel<S><<<grid, 256, smem, stream>>>(tmA, tmB, scaleA, scaleB, out, M, N, (int)(Kp / kOzBK), accumulate);
+  TNPY_LAUNCH_OK();
+  return TNPY_OK;
+}
+
+}  // namespace tnpy
+
+using namespace tnpy;
+
+static int64_t oz_kp(int K) { return ((int64_t)K + kOzBK - 1) / kOzBK * kOzBK; }
+
+extern "C" size_t tnpy_ozaki_workspace_bytes(int M, int N, int K, int slices) {
+  const int64_t Kp = oz_kp(K);
+  return Workspace::need((size_t)slices * M * Kp, 1) + Workspace::need((size_t)slices * N * Kp, 1) + Workspace::need(M) +
+         Workspace::need(N) + 1024;
+}
+
+// C[m,n] (+)= sum_k A[k,m] B[k,n] in FP64 accuracy on the int8 tensor cores (slices in 6..8).
+// phase: 0 = slice both operands and multiply, 1 = slice only (fills the workspace), 2 = multiply only
+// (workspace already holds the slices of these operands) -- lets a caller time / reuse the parts.
+extern "C" int tnpy_ozaki_gemm_tn(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
+                                  int M, int N, int K, int slices, int accumulate, int phase, void* workspace,
+                                  size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TNPY_CHECK_ARG(A && B && C && M > 0 && N > 0 && K > 0, "bad argument");
+  TNPY_CHECK_ARG(slices >= 6 && slices <= kOzMaxSlices, "slices must be 6, 7 or 8");
+  TNPY_CHECK_ARG(K <= 65536, "K too large for exact int32 accumulation");
+  const int64_t Kp = oz_kp(K);
+  Workspace ws(workspace, workspace_bytes);
+  int8_t* As = ws.take<int8_t>((size_t)slices * M * Kp);
+  int8_t* Bs = ws.take<int8_t>((size_t)slices * N * Kp);
+  double* sa = ws.take<double>(M);
+  double* sb = ws.take<double>(N);
+  if (!As || !Bs || !sa || !sb) {
+    set_error("tnpy_ozaki_gemm_tn: workspace too small");
+    return TNPY_EWORKSPACE;
+  }
+  GemmOut out = plain_out(C, ldc, M);
+  if (phase != 2) {
+    switch (slices) {
+      case 6: TNPY_TRY(oz_slice<6>(A, lda, K, M, sa, As, Kp, stream)); TNPY_TRY(oz_slice<6>(B, ldb, K, N, sb, Bs, Kp, stream)); break;
+      case 7: TNPY_TRY(oz_slice<7>(A, lda, K, M, sa, As, Kp, stream)); TNPY_TRY(oz_slice<7>(B, ldb, K, N, sb, Bs, Kp, stream)); break;
+      default: TNPY_TRY(oz_slice<8>(A, lda, K, M, sa, As, Kp, stream)); TNPY_TRY(oz_slice<8>(B, ldb, K, N, sb, Bs, Kp, stream)); break;
+    }
+  }
+  if (phase != 1) {
+    switch (slices) {
+      case 6: return oz_gemm<6>(As, sa, Bs, sb, out, M, N, Kp, accumulate, stream);
+      case 7: return oz_gemm<7>(As, sa, Bs, sb, out, M, N, Kp, accumulate, stream);
+      default: return oz_gemm<8>(As, sa, Bs, sb, out, M, N, Kp, accumulate, stream);
+    }
+  }
+  return TNPY_OK;
+}
