@@ -297,6 +297,28 @@ def run_single(args):
     _cuda.heff_apply(L, W, R, x, y)
     del Lc, Rc, y_ref
 
+    # the tcgen05 path: same matvec with the GEMMs on the int8 tensor cores (Ozaki scheme, 8 slices)
+    _cuda.set_gemm_algo(_cuda.GEMM_OZAKI)
+    try:
+        y_oz = _cuda.heff_apply(L, W, R, x).clone()
+        step_o = lambda: _cuda.heff_apply(L, W, R, x, y)  # noqa: E731
+        for _ in range(args.warmup):
+            step_o()
+        dt_o = cuda_time(step_o, args.steps, sync)
+        Lc = L.clone()
+        Lc[:, 0, :] = torch.eye(l, dtype=torch.float64, device="cuda")
+        Rc = R.clone()
+        Rc[:, wr - 1, :] = torch.eye(r, dtype=torch.float64, device="cuda")
+        step_oc = lambda: _cuda.heff_apply(Lc, W, Rc, x, y, flags=both)  # noqa: E731
+        step_oc()
+        dt_oc = cuda_time(step_oc, args.steps, sync)
+        del Lc, Rc
+    finally:
+        _cuda.set_gemm_algo(_cuda.GEMM_AUTO)
+    _cuda.heff_apply(L, W, R, x, y)
+    ozaki_diff = float((y_oz - y).abs().max() / y.abs().max())
+    del y_oz
+
     # dominant kernel alone: the two gemm_tn_dmma launches of the chain, timed with events per launch group
     ws = torch.empty(lib.tnpy_heff_workspace_bytes(l, r, wl, wr, d), dtype=torch.uint8, device="cuda")
     t1 = torch.empty((d * r, wl * l), dtype=torch.float64, device="cuda")
@@ -359,6 +381,14 @@ def run_single(args):
         },
         "gpu_launches": int(launches),
         "clocks": clocks,
+        "tcgen05_ozaki": {
+            "ms_per_step": dt_o / args.steps * 1e3, "tflops_fp64_equivalent": flops * args.steps / dt_o / 1e12,
+            "ms_per_step_canonical_gauge": dt_oc / args.steps * 1e3,
+            "tflops_fp64_equivalent_canonical_gauge": flops * args.steps / dt_oc / 1e12,
+            "rel_diff_vs_dmma_path": ozaki_diff, "slices": 8,
+            "note": "same matvec with both GEMMs as 36 exact int8 slice GEMMs on tcgen05 (TMEM int32 accumulators), "
+                    "operands re-sliced every call; opt-in via TNPY_GEMM_ALGO=ozaki / tnpy_set_gemm_algo(3)",
+        },
         "canonical_gauge": {
             "ms_per_step": dt_c / args.steps * 1e3, "tflops_algorithmic": flops * args.steps / dt_c / 1e12,
             "executed_flop_fraction": (wl - 1) / wl if wl == wr else None, "rel_diff_vs_dense_path": gauge_diff,

@@ -42,6 +42,8 @@ extern "C" {
 #define TNPY_GEMM_AUTO 0    /* TMA+DMMA kernel when shapes/alignments allow, else the generic one */
 #define TNPY_GEMM_GENERIC 1 /* generic shared-memory tiled DFMA kernel (any shape / stride)       */
 #define TNPY_GEMM_DMMA 2    /* force the TMA + mbarrier + FP64 tensor-core (DMMA) kernel           */
+#define TNPY_GEMM_OZAKI 3   /* FP64-accurate GEMM on the tcgen05 int8 tensor cores (Ozaki scheme) for large
+                               problems, DMMA / generic below its size threshold                       */
 
 /* Canonical-gauge shortcuts for the contraction chains (`flags` arguments).  With tnpy's
  * upper-triangular MPOs (model/utils.py:25-28: row 0 / last column are the boundary vectors) and a
@@ -83,6 +85,9 @@ int tnpy_gemm_tn(const double* A, int64_t lda, const double* B, int64_t ldb, dou
  * FP64 recombination in the epilogue).  Not used by the chains unless asked for; reported separately.
  * phase: 0 = slice + multiply, 1 = slice only into the workspace, 2 = multiply from the workspace. */
 size_t tnpy_ozaki_workspace_bytes(int M, int N, int K, int slices);
+/* Number of 7-bit slices per operand used when TNPY_GEMM_OZAKI is selected for the chains: 8 (default,
+ * componentwise error ~4e-16, same as DMMA), 7 (~2e-14) or 6 (~3e-12). */
+int tnpy_set_ozaki_slices(int slices);
 int tnpy_ozaki_gemm_tn(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
                        int M, int N, int K, int slices, int accumulate, int phase, void* workspace,
                        size_t workspace_bytes, void* stream);

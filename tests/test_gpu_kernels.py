@@ -427,3 +427,55 @@ def test_svd_exact_null_space(cu, rows, cols, rank):
     assert np.abs(u.T @ u - np.eye(k)).max() < 1e-11
     assert np.abs(vt @ vt.T - np.eye(k)).max() < 1e-11
     assert np.abs(u @ np.diag(s) @ vt - a).max() <= 1e-12 * max(s_ref[0], 1.0)
+
+
+# --------------------------------------------------- tcgen05 int8 (Ozaki) FP64 GEMM
+@pytest.mark.parametrize("m,n,k", [(128, 64, 64), (130, 70, 100), (512, 384, 200), (1000, 999, 777), (2048, 1024, 4096)])
+def test_ozaki_gemm_matches_fp64(cu, m, n, k):
+    """8 slices: componentwise error relative to |A|^T |B| at the level of a plain FP64 GEMM, also for
+    operands whose columns span many orders of magnitude."""
+    g = torch.Generator(device="cuda").manual_seed(m + n + k)
+    a = torch.randn((k, m), generator=g, dtype=torch.float64, device="cuda")
+    b = torch.randn((k, n), generator=g, dtype=torch.float64, device="cuda")
+    a = a * torch.logspace(0, -9, m, dtype=torch.float64, device="cuda")[None, :]
+    b = b * torch.logspace(3, -3, n, dtype=torch.float64, device="cuda")[None, :]
+    ref = a.t() @ b
+    bound = a.abs().t() @ b.abs()
+    got = cu.ozaki_gemm_tn(a, b, slices=8)
+    assert float(((got - ref).abs() / bound).max()) < 4e-15
+    c0 = torch.randn((m, n), generator=g, dtype=torch.float64, device="cuda")
+    acc = cu.ozaki_gemm_tn(a, b, out=c0.clone(), slices=8, accumulate=True)
+    assert float(((acc - (c0 + ref)).abs() / (bound + c0.abs())).max()) < 4e-15
+    loose = cu.ozaki_gemm_tn(a, b, slices=6)
+    assert float(((loose - ref).abs() / bound).max()) < 1e-10
+
+
+def test_ozaki_handles_zero_columns_and_ragged_k(cu):
+    g = torch.Generator(device="cuda").manual_seed(1)
+    a = torch.randn((333, 256), generator=g, dtype=torch.float64, device="cuda")
+    b = torch.randn((333, 128), generator=g, dtype=torch.float64, device="cuda")
+    a[:, 5] = 0.0
+    b[:, 7] = 0.0
+    got = cu.ozaki_gemm_tn(a, b)
+    ref = a.t() @ b
+    assert float((got - ref).abs().max()) < 1e-12
+    assert float(got[5].abs().max()) == 0.0 and float(got[:, 7].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("chi,w", [(512, 5), (768, 6)])
+def test_chain_with_ozaki_gemm(cu, chi, w):
+    """The matvec / environment chains with the tcgen05 path selected agree with the DMMA path."""
+    d = 2
+    g = torch.Generator(device="cuda").manual_seed(chi)
+    rnd = lambda *s: torch.randn(s, generator=g, dtype=torch.float64, device="cuda")  # noqa: E731
+    L, R, W, x = rnd(chi, w, chi), rnd(chi, w, chi), rnd(w, w, d, d), rnd(chi, d, chi)
+    ref = cu.heff_apply(L, W, R, x)
+    ref_env = cu.env_update_left(L, x, W)
+    cu.set_gemm_algo(cu.GEMM_OZAKI)
+    try:
+        got = cu.heff_apply(L, W, R, x)
+        got_env = cu.env_update_left(L, x, W)
+    finally:
+        cu.set_gemm_algo(cu.GEMM_AUTO)
+    assert float((got - ref).abs().max() / ref.abs().max()) < 1e-13
+    assert float((got_env - ref_env).abs().max() / ref_env.abs().max()) < 1e-13

@@ -14,7 +14,7 @@ from typing import Optional
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "libtnpy_cuda.so"
 
-GEMM_AUTO, GEMM_GENERIC, GEMM_DMMA = 0, 1, 2
+GEMM_AUTO, GEMM_GENERIC, GEMM_DMMA, GEMM_OZAKI = 0, 1, 2, 3
 LEFT_IDENTITY, RIGHT_IDENTITY = 1, 2
 ENOCONV = -4
 
@@ -30,6 +30,7 @@ SIGNATURES = {
     "tnpy_probe_fp64": (c_int, [c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_double), c_void_p]),
     "tnpy_gemm_tn": (c_int, [_PD, c_int64, _PD, c_int64, _PD, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "tnpy_ozaki_workspace_bytes": (c_size_t, [c_int] * 4),
+    "tnpy_set_ozaki_slices": (c_int, [c_int]),
     "tnpy_ozaki_gemm_tn": (
         c_int,
         [_PD, c_int64, _PD, c_int64, _PD, c_int64] + [c_int] * 6 + [c_void_p, c_size_t, c_void_p],
@@ -93,6 +94,14 @@ def load() -> ctypes.CDLL:
         fn.restype = restype
         fn.argtypes = argtypes
     _lib = lib
+    import os
+
+    choice = os.environ.get("TNPY_GEMM_ALGO", "").lower()
+    if choice:
+        table = {"auto": GEMM_AUTO, "generic": GEMM_GENERIC, "dmma": GEMM_DMMA, "ozaki": GEMM_OZAKI}
+        if choice not in table:
+            raise RuntimeError(f"TNPY_GEMM_ALGO={choice!r}: expected one of {sorted(table)}")
+        lib.tnpy_set_gemm_algo(table[choice])
     return lib
 
 
@@ -111,7 +120,13 @@ def launch_count() -> int:
 
 
 def set_gemm_algo(algo: int) -> None:
+    """Select the GEMM used inside the chains: GEMM_AUTO (DMMA / generic), GEMM_OZAKI (tcgen05 int8,
+    FP64-accurate) ...  Also settable through the environment: TNPY_GEMM_ALGO=ozaki|dmma|generic|auto."""
     check(load().tnpy_set_gemm_algo(algo), "tnpy_set_gemm_algo")
+
+
+def set_ozaki_slices(slices: int) -> None:
+    check(load().tnpy_set_ozaki_slices(int(slices)), "tnpy_set_ozaki_slices")
 
 
 # ------------------------------------------------------------------------------------------------

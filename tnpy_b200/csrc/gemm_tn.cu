@@ -23,6 +23,9 @@
 namespace tnpy {
 
 int forced_gemm_tile();
+bool ozaki_applicable(int M, int N, int K);
+int ozaki_gemm(const double* A, int64_t lda, const double* B, int64_t ldb, GemmOut out, int M, int N, int K,
+               int accumulate, cudaStream_t stream);
 
 // =============================================================================================
 // generic kernel
@@ -357,6 +360,11 @@ int gemm_tn(const double* A, int64_t lda, const double* B, int64_t ldb, GemmOut 
   TNPY_CHECK_ARG(M > 0 && N > 0 && K > 0, "non-positive dimension");
   TNPY_CHECK_ARG(lda >= M && ldb >= N && out.m_inner > 0, "leading dimension too small");
   if (algo == TNPY_GEMM_AUTO) algo = current_gemm_algo();
+  if (algo == TNPY_GEMM_OZAKI) {
+    // FP64-accurate GEMM on the tcgen05 int8 tensor cores; small / very deep problems fall through to DMMA
+    if (ozaki_applicable(M, N, K)) return ozaki_gemm(A, lda, B, ldb, out, M, N, K, accumulate, stream);
+    algo = TNPY_GEMM_AUTO;
+  }
   const bool can_tma = tma_ok(A, lda) && tma_ok(B, ldb);
   if (algo == TNPY_GEMM_DMMA && !can_tma) {
     set_error("gemm_tn: TNPY_GEMM_DMMA requested but operands are not TMA-describable (16B base, even ld)");

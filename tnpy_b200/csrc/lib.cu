@@ -50,7 +50,7 @@ extern "C" int tnpy_version(void) { return 100; }
 extern "C" const char* tnpy_last_error(void) { return tnpy::g_error; }
 extern "C" int64_t tnpy_launch_count(void) { return tnpy::g_launch_count.load(); }
 extern "C" int tnpy_set_gemm_algo(int algo) {
-  if (algo < TNPY_GEMM_AUTO || algo > TNPY_GEMM_DMMA) {
+  if (algo < TNPY_GEMM_AUTO || algo > TNPY_GEMM_OZAKI) {
     tnpy::set_error("tnpy_set_gemm_algo: unknown algo %d", algo);
     return TNPY_EINVAL;
   }

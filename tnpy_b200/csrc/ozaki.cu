@@ -30,46 +30,56 @@ constexpr int kOzMaxSlices = 8;  // 8 accumulators x 64 columns = all 512 TMEM c
 // ---------------------------------------------------------------------------------------------
 // slicing
 // ---------------------------------------------------------------------------------------------
-// scale[c] = 2^e with |P[k][c]| / 2^e <= 0.5 for all k  (0 for an all-zero column)
-__global__ void __launch_bounds__(256) oz_colscale_kernel(const double* __restrict__ P, int64_t ld, int K, int MN,
-                                                          double* __restrict__ scale) {
+// colmax[c] = max_k |P[k][c]| as the bit pattern of a non-negative double (integer order == value
+// order), reduced over k-chunks with atomicMax; colmax must be zeroed first.
+__global__ void __launch_bounds__(256) oz_colmax_kernel(const double* __restrict__ P, int64_t ld, int K, int MN,
+                                                        int k_chunk, unsigned long long* __restrict__ colmax) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= MN) return;
+  const int k0 = blockIdx.y * k_chunk, k1 = min(K, k0 + k_chunk);
   double mx = 0.0;
-  for (int k = 0; k < K; ++k) mx = fmax(mx, fabs(P[(int64_t)k * ld + c]));
-  scale[c] = mx > 0.0 ? ldexp(1.0, ilogb(mx) + 2) : 0.0;
+  for (int k = k0; k < k1; ++k) mx = fmax(mx, fabs(P[(int64_t)k * ld + c]));
+  if (mx > 0.0) atomicMax(&colmax[c], (unsigned long long)__double_as_longlong(mx));
 }
 
-// slices[s][c][k] (k contiguous, Kp bytes per row) from P[k][c]; 32 x 32 shared-memory transpose
+// scale = 2^e with |P[k][c]| / 2^e <= 0.5 for all k  (0 for an all-zero column)
+__device__ __forceinline__ double oz_scale_of(unsigned long long bits) {
+  const double mx = __longlong_as_double((long long)bits);
+  return mx > 0.0 ? ldexp(1.0, ilogb(mx) + 2) : 0.0;
+}
+
+// slices[s][c][k] (k contiguous, Kp bytes per row) from P[k][c]: 32 columns x 128 k per block, digits staged
+// in shared memory so that every (slice, column) row leaves as one 128-byte line.
 template <int S>
 __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict__ P, int64_t ld, int K, int MN,
-                                                       const double* __restrict__ scale, int8_t* __restrict__ slices,
+                                                       const unsigned long long* __restrict__ colmax,
+                                                       double* __restrict__ scale, int8_t* __restrict__ slices,
                                                        int64_t Kp, int64_t slice_stride) {
-  __shared__ int8_t tile[S][32][33];
-  const int c0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+  __shared__ __align__(16) int8_t tile[S][32][132];
+  const int c0 = blockIdx.x * 32, k0 = blockIdx.y * 128;
   const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
-  for (int i = ty; i < 32; i += 8) {
-    const int k = k0 + i, c = c0 + tx;
-    double t = 0.0;
-    if (k < K && c < MN) {
-      const double sc = scale[c];
-      t = sc > 0.0 ? P[(int64_t)k * ld + c] / sc : 0.0;  // exact: power-of-two scaling, |t| <= 0.5
-    }
+  const int c = c0 + tx;
+  const double sc = c < MN ? oz_scale_of(colmax[c]) : 0.0;
+  const double inv = sc > 0.0 ? 1.0 / sc : 0.0;  // exact: power of two
+  if (blockIdx.y == 0 && ty == 0 && c < MN) scale[c] = sc;
+  for (int i = ty; i < 128; i += 8) {
+    const int k = k0 + i;
+    double t = (k < K && c < MN) ? P[(int64_t)k * ld + c] * inv : 0.0;  // |t| <= 0.5
 #pragma unroll
-    for (int s = 0; s < S; ++s) {
+    for (int sl = 0; sl < S; ++sl) {
       t *= 128.0;
       const double dgt = rint(t);  // |dgt| <= 64
-      tile[s][i][tx] = (int8_t)(int)dgt;
+      tile[sl][tx][i] = (int8_t)(int)dgt;
       t -= dgt;                    // exact remainder, |t| <= 0.5
     }
   }
   __syncthreads();
-  for (int i = ty; i < 32; i += 8) {
-    const int c = c0 + i, k = k0 + tx;
-    if (c < MN && k < Kp) {
-#pragma unroll
-      for (int s = 0; s < S; ++s) slices[s * slice_stride + (int64_t)c * Kp + k] = (k < K) ? tile[s][tx][i] : (int8_t)0;
-    }
+  for (int idx = threadIdx.x; idx < S * 32 * 32; idx += 256) {
+    const int w = idx % 32, cc = (idx / 32) % 32, sl = idx / 1024;
+    const int64_t k = k0 + 4 * w;
+    if (c0 + cc < MN && k < Kp)
+      *reinterpret_cast<int32_t*>(slices + sl * slice_stride + (int64_t)(c0 + cc) * Kp + k) =
+          *reinterpret_cast<const int32_t*>(&tile[sl][cc][4 * w]);
   }
 }
 
@@ -278,13 +288,17 @@ static int oz_make_map(CUtensorMap* map, const int8_t* base, int64_t Kp, int row
   return TNPY_OK;
 }
 
+// `scale` doubles as scratch for the column maxima: the first MN 8-byte words of `colmax_scratch`.
 template <int S>
-static int oz_slice(const double* P, int64_t ld, int K, int MN, double* scale, int8_t* slices, int64_t Kp,
-                    cudaStream_t stream) {
-  oz_colscale_kernel<<<ceil_div(MN, 256), 256, 0, stream>>>(P, ld, K, MN, scale);
+static int oz_slice(const double* P, int64_t ld, int K, int MN, double* scale, unsigned long long* colmax_scratch,
+                    int8_t* slices, int64_t Kp, cudaStream_t stream) {
+  TNPY_CUDA_OK(cudaMemsetAsync(colmax_scratch, 0, sizeof(unsigned long long) * (size_t)MN, stream));
+  const int k_chunk = K > 4096 ? 256 : 64;
+  dim3 g1(ceil_div(MN, 256), ceil_div(K, k_chunk));
+  oz_colmax_kernel<<<g1, 256, 0, stream>>>(P, ld, K, MN, k_chunk, colmax_scratch);
   TNPY_LAUNCH_OK();
-  dim3 grid(ceil_div(MN, 32), (unsigned)((Kp + 31) / 32));
-  oz_slice_kernel<S><<<grid, 256, 0, stream>>>(P, ld, K, MN, scale, slices, Kp, (int64_t)MN * Kp);
+  dim3 grid(ceil_div(MN, 32), (unsigned)((Kp + 127) / 128));
+  oz_slice_kernel<S><<<grid, 256, 0, stream>>>(P, ld, K, MN, colmax_scratch, scale, slices, Kp, (int64_t)MN * Kp);
   TNPY_LAUNCH_OK();
   return TNPY_OK;
 }
@@ -307,16 +321,93 @@ static int oz_gemm(const int8_t* As, const double* scaleA, const int8_t* Bs, con
   return TNPY_OK;
 }
 
+static int64_t oz_kp_(int K) { return ((int64_t)K + kOzBK - 1) / kOzBK * kOzBK; }
+
+// Library-internal grow-only scratch for the slices (the chains call gemm_tn without a workspace for
+// this purpose).  One buffer per process; calls are expected on one stream at a time.
+struct OzScratch {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+};
+static int oz_scratch(size_t need, void** out) {
+  static OzScratch sc;
+  if (sc.bytes < need) {
+    if (sc.ptr) {
+      TNPY_CUDA_OK(cudaDeviceSynchronize());
+      TNPY_CUDA_OK(cudaFree(sc.ptr));
+      sc.ptr = nullptr;
+      sc.bytes = 0;
+    }
+    const size_t want = need + need / 8;
+    TNPY_CUDA_OK(cudaMalloc(&sc.ptr, want));
+    sc.bytes = want;
+  }
+  *out = sc.ptr;
+  return TNPY_OK;
+}
+
+static std::atomic<int> g_oz_slices{8};
+int ozaki_slices() { return g_oz_slices.load(); }
+
+bool ozaki_applicable(int M, int N, int K) {
+  return K <= 65536 && K >= 64 && M >= 128 && N >= 64 && (double)M * N * K >= 1.0e9;
+}
+
+// C (+)= A^T B through the int8 tensor cores; operands are sliced into the internal scratch.
+int ozaki_gemm(const double* A, int64_t lda, const double* B, int64_t ldb, GemmOut out, int M, int N, int K,
+               int accumulate, cudaStream_t stream) {
+  const int S = ozaki_slices();
+  const int64_t Kp = oz_kp_(K);
+  const size_t need = Workspace::need((size_t)S * M * Kp, 1) + Workspace::need((size_t)S * N * Kp, 1) +
+                      2 * Workspace::need(M) + 2 * Workspace::need(N) + 1024;
+  void* base = nullptr;
+  TNPY_TRY(oz_scratch(need, &base));
+  Workspace ws(base, need);
+  int8_t* As = ws.take<int8_t>((size_t)S * M * Kp);
+  int8_t* Bs = ws.take<int8_t>((size_t)S * N * Kp);
+  double* sa = ws.take<double>(M);
+  double* sb = ws.take<double>(N);
+  unsigned long long* ma = ws.take<unsigned long long>(M);
+  unsigned long long* mb = ws.take<unsigned long long>(N);
+  if (!As || !Bs || !sa || !sb || !ma || !mb) {
+    set_error("ozaki_gemm: internal scratch layout failed");
+    return TNPY_EWORKSPACE;
+  }
+  switch (S) {
+    case 6:
+      TNPY_TRY(oz_slice<6>(A, lda, K, M, sa, ma, As, Kp, stream));
+      TNPY_TRY(oz_slice<6>(B, ldb, K, N, sb, mb, Bs, Kp, stream));
+      return oz_gemm<6>(As, sa, Bs, sb, out, M, N, Kp, accumulate, stream);
+    case 7:
+      TNPY_TRY(oz_slice<7>(A, lda, K, M, sa, ma, As, Kp, stream));
+      TNPY_TRY(oz_slice<7>(B, ldb, K, N, sb, mb, Bs, Kp, stream));
+      return oz_gemm<7>(As, sa, Bs, sb, out, M, N, Kp, accumulate, stream);
+    default:
+      TNPY_TRY(oz_slice<8>(A, lda, K, M, sa, ma, As, Kp, stream));
+      TNPY_TRY(oz_slice<8>(B, ldb, K, N, sb, mb, Bs, Kp, stream));
+      return oz_gemm<8>(As, sa, Bs, sb, out, M, N, Kp, accumulate, stream);
+  }
+}
+
 }  // namespace tnpy
 
 using namespace tnpy;
+
+extern "C" int tnpy_set_ozaki_slices(int slices) {
+  if (slices < 6 || slices > kOzMaxSlices) {
+    set_error("tnpy_set_ozaki_slices: slices must be 6, 7 or 8");
+    return TNPY_EINVAL;
+  }
+  g_oz_slices.store(slices);
+  return TNPY_OK;
+}
 
 static int64_t oz_kp(int K) { return ((int64_t)K + kOzBK - 1) / kOzBK * kOzBK; }
 
 extern "C" size_t tnpy_ozaki_workspace_bytes(int M, int N, int K, int slices) {
   const int64_t Kp = oz_kp(K);
-  return Workspace::need((size_t)slices * M * Kp, 1) + Workspace::need((size_t)slices * N * Kp, 1) + Workspace::need(M) +
-         Workspace::need(N) + 1024;
+  return Workspace::need((size_t)slices * M * Kp, 1) + Workspace::need((size_t)slices * N * Kp, 1) +
+         2 * Workspace::need(M) + 2 * Workspace::need(N) + 1024;
 }
 
 // C[m,n] (+)= sum_k A[k,m] B[k,n] in FP64 accuracy on the int8 tensor cores (slices in 6..8).
@@ -335,16 +426,18 @@ extern "C" int tnpy_ozaki_gemm_tn(const double* A, int64_t lda, const double* B,
   int8_t* Bs = ws.take<int8_t>((size_t)slices * N * Kp);
   double* sa = ws.take<double>(M);
   double* sb = ws.take<double>(N);
-  if (!As || !Bs || !sa || !sb) {
+  unsigned long long* ma = ws.take<unsigned long long>(M);
+  unsigned long long* mb = ws.take<unsigned long long>(N);
+  if (!As || !Bs || !sa || !sb || !ma || !mb) {
     set_error("tnpy_ozaki_gemm_tn: workspace too small");
     return TNPY_EWORKSPACE;
   }
   GemmOut out = plain_out(C, ldc, M);
   if (phase != 2) {
     switch (slices) {
-      case 6: TNPY_TRY(oz_slice<6>(A, lda, K, M, sa, As, Kp, stream)); TNPY_TRY(oz_slice<6>(B, ldb, K, N, sb, Bs, Kp, stream)); break;
-      case 7: TNPY_TRY(oz_slice<7>(A, lda, K, M, sa, As, Kp, stream)); TNPY_TRY(oz_slice<7>(B, ldb, K, N, sb, Bs, Kp, stream)); break;
-      default: TNPY_TRY(oz_slice<8>(A, lda, K, M, sa, As, Kp, stream)); TNPY_TRY(oz_slice<8>(B, ldb, K, N, sb, Bs, Kp, stream)); break;
+      case 6: TNPY_TRY(oz_slice<6>(A, lda, K, M, sa, ma, As, Kp, stream)); TNPY_TRY(oz_slice<6>(B, ldb, K, N, sb, mb, Bs, Kp, stream)); break;
+      case 7: TNPY_TRY(oz_slice<7>(A, lda, K, M, sa, ma, As, Kp, stream)); TNPY_TRY(oz_slice<7>(B, ldb, K, N, sb, mb, Bs, Kp, stream)); break;
+      default: TNPY_TRY(oz_slice<8>(A, lda, K, M, sa, ma, As, Kp, stream)); TNPY_TRY(oz_slice<8>(B, ldb, K, N, sb, mb, Bs, Kp, stream)); break;
     }
   }
   if (phase != 1) {
