@@ -131,6 +131,7 @@ static int mirror(const double* in, double* out, int l, int d, int r, cudaStream
 
 // out[z][c][r] = in[z][r][c]: batched strided transpose (32x32 shared-memory tiles).
 // in rows have stride ld_in, out rows stride ld_out; batch z advances by in_z / out_z elements.
+template <bool ADD>
 __global__ void __launch_bounds__(256) transpose_strided_kernel(const double* __restrict__ in, int64_t ld_in,
                                                                 int64_t in_z, int rows, int cols,
                                                                 double* __restrict__ out, int64_t ld_out,
@@ -147,14 +148,20 @@ __global__ void __launch_bounds__(256) transpose_strided_kernel(const double* __
   __syncthreads();
   for (int i = ty; i < 32; i += 8) {
     const int c = c0 + i, r = r0 + tx;
-    if (r < rows && c < cols) out[(int64_t)c * ld_out + r] = tile[tx][i];
+    if (r < rows && c < cols) {
+      double* dst = out + (int64_t)c * ld_out + r;
+      *dst = ADD ? *dst + tile[tx][i] : tile[tx][i];
+    }
   }
 }
 
 static int transpose_strided(const double* in, int64_t ld_in, int64_t in_z, int rows, int cols, double* out,
-                             int64_t ld_out, int64_t out_z, int batch, cudaStream_t stream) {
+                             int64_t ld_out, int64_t out_z, int batch, cudaStream_t stream, bool add = false) {
   dim3 grid(ceil_div(cols, 32), ceil_div(rows, 32), batch);
-  transpose_strided_kernel<<<grid, 256, 0, stream>>>(in, ld_in, in_z, rows, cols, out, ld_out, out_z);
+  if (add)
+    transpose_strided_kernel<true><<<grid, 256, 0, stream>>>(in, ld_in, in_z, rows, cols, out, ld_out, out_z);
+  else
+    transpose_strided_kernel<false><<<grid, 256, 0, stream>>>(in, ld_in, in_z, rows, cols, out, ld_out, out_z);
   TNPY_LAUNCH_OK();
   return TNPY_OK;
 }
@@ -249,12 +256,13 @@ int heff_apply_rows(const double* L, const double* W, const double* R, const dou
   // y[m, q, s] = sum_{r b} T2[(r b), (q m)] R[(r b), s]               rows (q m) -> (m q)
   GemmOut out{y, (int64_t)d * r, (int64_t)r, lo};
   if (right_id) {
-    // y[m, q, s] = T2[wr-1, s, q, m]  (+ the GEMM over the other channels)
-    const double* t2_last = t2 + (size_t)(wr - 1) * r * d * lo;
-    TNPY_TRY(transpose_strided(t2_last, (int64_t)d * lo, lo, r, lo, y, (int64_t)d * r, r, d, stream));
+    // y[m, q, s] = (GEMM over the channels b < wr-1) + T2[wr-1, s, q, m]; the identity-channel term is
+    // added by a transposing pass afterwards so that the GEMM epilogue stays store-only
     channel_major_kernel<<<sm_count() * 8, 256, 0, stream>>>(R, r2, r, wr, wr - 1, r);
     TNPY_LAUNCH_OK();
-    TNPY_TRY(gemm_tn(t2, (int64_t)d * lo, r2, (int64_t)r, out, d * lo, r, r * (wr - 1), 1, algo, stream));
+    TNPY_TRY(gemm_tn(t2, (int64_t)d * lo, r2, (int64_t)r, out, d * lo, r, r * (wr - 1), 0, algo, stream));
+    const double* t2_last = t2 + (size_t)(wr - 1) * r * d * lo;
+    TNPY_TRY(transpose_strided(t2_last, (int64_t)d * lo, lo, r, lo, y, (int64_t)d * r, r, d, stream, true));
   } else {
     TNPY_TRY(gemm_tn(t2, (int64_t)d * lo, R, (int64_t)r, out, d * lo, r, r * wr, 0, algo, stream));
   }
