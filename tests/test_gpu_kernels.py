@@ -462,7 +462,7 @@ def test_ozaki_handles_zero_columns_and_ragged_k(cu):
     assert float(got[5].abs().max()) == 0.0 and float(got[:, 7].abs().max()) == 0.0
 
 
-@pytest.mark.parametrize("chi,w", [(512, 5), (768, 6)])
+@pytest.mark.parametrize("chi,w", [(1024, 5), (1280, 6)])
 def test_chain_with_ozaki_gemm(cu, chi, w):
     """The matvec / environment chains with the tcgen05 path selected agree with the DMMA path."""
     d = 2

@@ -148,7 +148,18 @@ __global__ void __launch_bounds__(256, 1)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * kOzBM, n0 = blockIdx.x * kOzBN;
+  // grouped rasterisation (8 m-tiles per sweep over n) so that co-resident CTAs share operand panels in L2
+  int tm, tn;
+  {
+    const int tiles_m = (M + kOzBM - 1) / kOzBM, tiles_n = (N + kOzBN - 1) / kOzBN;
+    constexpr int GROUP = 8;
+    const int tile = blockIdx.x, per_group = GROUP * tiles_n;
+    const int gid = tile / per_group, first_m = gid * GROUP;
+    const int gsz = min(tiles_m - first_m, GROUP), rem = tile - gid * per_group;
+    tm = first_m + rem % gsz;
+    tn = rem / gsz;
+  }
+  const int m0 = tm * kOzBM, n0 = tn * kOzBN;
   if (threadIdx.x == 0) {
     for (int s = 0; s < kOzStages; ++s) {
       oz_mbar_init(&full_bar[s], 1);
@@ -315,7 +326,7 @@ static int oz_gemm(const int8_t* As, const double* scaleA, const int8_t* Bs, con
     TNPY_CUDA_OK(cudaFuncSetAttribute(oz_mma_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  dim3 grid(ceil_div(N, kOzBN), ceil_div(M, kOzBM));
+  const int grid = ceil_div(N, kOzBN) * ceil_div(M, kOzBM);
   oz_mma_kernel<S><<<grid, 256, smem, stream>>>(tmA, tmB, scaleA, scaleB, out, M, N, (int)(Kp / kOzBK), accumulate);
   TNPY_LAUNCH_OK();
   return TNPY_OK;
@@ -350,7 +361,8 @@ static std::atomic<int> g_oz_slices{8};
 int ozaki_slices() { return g_oz_slices.load(); }
 
 bool ozaki_applicable(int M, int N, int K) {
-  return K <= 65536 && K >= 64 && M >= 128 && N >= 64 && (double)M * N * K >= 1.0e9;
+  // below ~chi = 1024 the slicing passes and extra launches cost more than the faster MMA saves (measured at chi = 512)
+  return K <= 65536 && K >= 64 && M >= 128 && N >= 64 && (double)M * N * K >= 6.0e9;
 }
 
 // C (+)= A^T B through the int8 tensor cores; operands are sliced into the internal scratch.
