@@ -88,6 +88,10 @@ size_t tnpy_ozaki_workspace_bytes(int M, int N, int K, int slices);
 /* Number of 7-bit slices per operand used when TNPY_GEMM_OZAKI is selected for the chains: 8 (default,
  * componentwise error ~4e-16, same as DMMA), 7 (~2e-14) or 6 (~3e-12). */
 int tnpy_set_ozaki_slices(int slices);
+/* Kernel generation of the tcgen05 GEMM: 2 (default) = CTA pair (cta_group::2), 256 x 128 tile, the slice
+ * diagonals accumulated in two passes of four TMEM accumulators; 1 = one CTA per 128 x 64 tile, all eight
+ * accumulators at once (operand-pipe bound, kept for comparison).  Env TNPY_OZAKI_VARIANT=1 selects 1. */
+int tnpy_set_ozaki_variant(int variant);
 int tnpy_ozaki_gemm_tn(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
                        int M, int N, int K, int slices, int accumulate, int phase, void* workspace,
                        size_t workspace_bytes, void* stream);

@@ -31,6 +31,7 @@ SIGNATURES = {
     "tnpy_gemm_tn": (c_int, [_PD, c_int64, _PD, c_int64, _PD, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "tnpy_ozaki_workspace_bytes": (c_size_t, [c_int] * 4),
     "tnpy_set_ozaki_slices": (c_int, [c_int]),
+    "tnpy_set_ozaki_variant": (c_int, [c_int]),
     "tnpy_ozaki_gemm_tn": (
         c_int,
         [_PD, c_int64, _PD, c_int64, _PD, c_int64] + [c_int] * 6 + [c_void_p, c_size_t, c_void_p],
@@ -127,6 +128,11 @@ def set_gemm_algo(algo: int) -> None:
 
 def set_ozaki_slices(slices: int) -> None:
     check(load().tnpy_set_ozaki_slices(int(slices)), "tnpy_set_ozaki_slices")
+
+
+def set_ozaki_variant(variant: int) -> None:
+    """2 (default): CTA-pair 256x128 two-pass tcgen05 kernel; 1: single-CTA 128x64 kernel."""
+    check(load().tnpy_set_ozaki_variant(int(variant)), "tnpy_set_ozaki_variant")
 
 
 # ------------------------------------------------------------------------------------------------

@@ -15,6 +15,7 @@
 //   warps 4-7 epilogue: tcgen05.ld 32x32b, FP64 recombination, scaled store through the GEMM row map
 #include <cudaTypedefs.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -263,6 +264,280 @@ __global__ void __launch_bounds__(256, 1)
 }
 
 // ---------------------------------------------------------------------------------------------
+// tcgen05 kernel, second generation: CTA pair (cta_group::2), 256 x 128 tile, two accumulator passes
+// ---------------------------------------------------------------------------------------------
+// ncu on oz_mma_kernel (profiles/r01_oz_mma_kernel_ncu_full_raw.csv) shows the tensor cores' shared-memory
+// operand pipe at 74-89 % of peak with the MMA pipe only 50-60 % busy: an M=128, N=64, K=32 int8 MMA reads
+// 4 KB of A + 2 KB of B = 48 wavefronts of 128 B for 32 cycles of math.  N per instruction is capped by TMEM
+// (S accumulators x N columns <= 512), so this kernel (a) runs the S diagonals in two passes of <= 4
+// accumulators, which allows N = 128, and (b) pairs two CTAs (cta_group::2, M = 256): each CTA stages its own
+// 128 rows of A and only half (64 rows) of B, i.e. 4 + 2 KB per 64 cycles of math = 75 % of the operand pipe.
+//
+//   pass 0: diagonals d = 4 .. S-1 (small weights; needs all slices: two 48 KB slots per 64-byte K chunk)
+//   pass 1: diagonals d = 0 .. 3   (needs slices 0..3 of both operands: one slot per K chunk)
+//
+// Shared-memory ring: 4 slots of {A slices[4][128 rows][64 B], B slices[4][64 rows][64 B]} per CTA.  Both CTAs'
+// TMA loads complete on the leader's full barrier; the leader's elected thread issues every MMA and frees
+// slots / publishes accumulators in both CTAs with multicast commits; each CTA's epilogue warps drain their
+// own 128 TMEM lanes (pass 0 writes C, pass 1 adds to it) and release TMEM to the leader between the passes.
+constexpr int kOz2SlotA = 4 * kOzBM * kOzBK;  // 32 KB
+constexpr int kOz2SlotB = 4 * kOzBN * kOzBK;  // 16 KB
+constexpr int kOz2Slot = kOz2SlotA + kOz2SlotB;
+constexpr int kOz2Slots = 4;
+constexpr int kOz2TileN = 2 * kOzBN;  // 128 columns per accumulator
+constexpr int kOz2EpiWarps = 8;       // two per TMEM lane quadrant
+constexpr int kOz2Threads = 128 + 32 * kOz2EpiWarps;
+
+__device__ __forceinline__ uint32_t oz_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void oz_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local` (a shared::cta address) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t oz_mapa(uint32_t local, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void oz_tma_3d_pair(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1,
+                                               int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(oz_smem_u32(dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void oz_tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void oz_mma_i8_pair(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc,
+                                               uint32_t accumulate) {
+  const uint32_t z = 0;
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8, %9, %10, %11, %12}, p;\n}\n"
+      ::"r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(z), "r"(z), "r"(z), "r"(z), "r"(z), "r"(z),
+      "r"(z), "r"(z)
+      : "memory");
+}
+// arrive (once the preceding MMAs have completed) on the barrier at this offset in both CTAs of the pair
+__device__ __forceinline__ void oz_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "{\n.reg .b16 lo, hi;\nmov.b32 {lo, hi}, %1;\n"
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], lo;\n}\n"
+      ::"r"(oz_smem_u32(bar)), "r"(3u)
+      : "memory");
+}
+__device__ __forceinline__ void oz_mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
+// Issue the MMAs of one 64-byte K chunk for pass PASS (0: diagonals 4..S-1, 1: diagonals 0..3).  lo4 / hi4 are the
+// (address >> 4) fields of the slot(s) holding slice groups 0..3 / 4..7; everything else is a compile-time
+// constant so the single issuing thread spends two integer adds per MMA.
+template <int S, int PASS>
+__device__ __forceinline__ void oz2_issue_chunk(uint32_t lo4, uint32_t hi4, uint32_t tmem_base, bool first_chunk) {
+  constexpr int d_lo = PASS == 0 ? 4 : 0, d_hi = PASS == 0 ? S - 1 : 3;
+  // instruction descriptor: D = S32, A = B = signed int8, both K-major, N = 128, M = 256 (128 rows per CTA)
+  constexpr uint32_t idesc =
+      (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kOz2TileN >> 3) << 17) | ((uint32_t)((2 * kOzBM) >> 4) << 24);
+  // K-major, 64B swizzle: SBO = 8 rows * 64 B, descriptor version 1, layout type SWIZZLE_64B
+  constexpr uint64_t desc_hi = ((uint64_t)((8 * kOzBK) >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
+#pragma unroll
+  for (int kk = 0; kk < kOzBK / 32; ++kk) {
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+      const uint64_t da = desc_hi | (uint64_t)((i < 4 ? lo4 : hi4) + (uint32_t)(((i & 3) * (kOzBM * kOzBK) + kk * 32) >> 4));
+#pragma unroll
+      for (int j = 0; j < S; ++j) {
+        if (i + j < d_lo || i + j > d_hi) continue;
+        const uint64_t db = desc_hi | (uint64_t)((j < 4 ? lo4 : hi4) +
+                                                 (uint32_t)((kOz2SlotA + (j & 3) * (kOzBN * kOzBK) + kk * 32) >> 4));
+        // the first contribution to every diagonal of a pass comes from slice i = 0 at k-step 0 of chunk 0
+        const uint32_t acc = (kk == 0 && i == 0) ? (first_chunk ? 0u : 1u) : 1u;
+        oz_mma_i8_pair(tmem_base + (uint32_t)((i + j - d_lo) * kOz2TileN), da, db, idesc, acc);
+      }
+    }
+  }
+}
+
+template <int S, int PASS>
+__device__ __forceinline__ void oz2_issue_pass(uint32_t smem0, uint64_t* full_bar, uint64_t* empty_bar, uint64_t* tmem_full,
+                                               uint32_t tmem_base, int KT, uint32_t& slot, uint32_t& phase) {
+  for (int kt = 0; kt < KT; ++kt) {
+    const uint32_t lo = smem0 + slot * kOz2Slot;
+    oz_mbar_wait(&full_bar[slot], phase);
+    if (PASS == 0) oz_mbar_wait(&full_bar[slot + 1], phase);  // slots are taken in pairs (0,1) / (2,3): same phase
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    oz2_issue_chunk<S, PASS>(lo >> 4, (lo + kOz2Slot) >> 4, tmem_base, kt == 0);
+    oz_commit_pair(&empty_bar[slot]);
+    if (PASS == 0) oz_commit_pair(&empty_bar[slot + 1]);
+    slot += PASS == 0 ? 2 : 1;
+    if (slot == kOz2Slots) { slot = 0; phase ^= 1; }
+  }
+  oz_commit_pair(tmem_full);
+}
+
+template <int S>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kOz2Threads, 1)
+    oz2_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const double* __restrict__ scaleA, const double* __restrict__ scaleB, GemmOut out, int M, int N,
+                   int KT, int accumulate) {
+  static_assert(S > 4 && S <= 8, "two passes of at most four diagonals");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kOz2Slots * kOz2Slot);
+  uint64_t* empty_bar = full_bar + kOz2Slots;
+  uint64_t* tmem_full = empty_bar + kOz2Slots;
+  uint64_t* tmem_empty = tmem_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = oz_cluster_rank();
+  int tm, tn;
+  {
+    const int tiles_m = (M + 2 * kOzBM - 1) / (2 * kOzBM), tiles_n = (N + kOz2TileN - 1) / kOz2TileN;
+    constexpr int GROUP = 4;
+    const int tile = blockIdx.x >> 1, per_group = GROUP * tiles_n;
+    const int gid = tile / per_group, first_m = gid * GROUP;
+    const int gsz = min(tiles_m - first_m, GROUP), rem = tile - gid * per_group;
+    tm = first_m + rem % gsz;
+    tn = rem / gsz;
+  }
+  const int m0 = tm * 2 * kOzBM + (int)rank * kOzBM;  // this CTA's rows of C / columns of A
+  const int n0 = tn * kOz2TileN;                      // the pair's columns of C
+  const int nb0 = n0 + (int)rank * kOzBN;             // the half of the B tile this CTA stages
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kOz2Slots; ++s) {
+      oz_mbar_init(&full_bar[s], 1);
+      oz_mbar_init(&empty_bar[s], 1);
+    }
+    oz_mbar_init(tmem_full, 1);
+    oz_mbar_init(tmem_empty, 2 * kOz2EpiWarps);  // every epilogue warp of both CTAs
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(oz_smem_u32(tmem_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  oz_cluster_sync();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // load sequence: t in [0, 2 KT) = pass 0 (chunk t / 2, slice group t % 2), t in [2 KT, 3 KT) = pass 1 (group 0)
+      const int T = 3 * KT;
+      uint32_t slot = 0, phase = 0;
+      for (int t = 0; t < T; ++t) {
+        int kt, sub;
+        if (t < 2 * KT) { kt = t >> 1; sub = t & 1; } else { kt = t - 2 * KT; sub = 0; }
+        oz_mbar_wait(&empty_bar[slot], phase ^ 1);
+        if (rank == 0) oz_mbar_expect_tx(&full_bar[slot], 2 * kOz2Slot);  // both CTAs' boxes land on this barrier
+        const uint32_t leader_full = oz_mapa(oz_smem_u32(&full_bar[slot]), 0);
+        uint8_t* dst = smem + slot * kOz2Slot;
+        oz_tma_3d_pair(dst, &tmA, leader_full, kt * kOzBK, m0, sub * 4);
+        oz_tma_3d_pair(dst + kOz2SlotA, &tmB, leader_full, kt * kOzBK, nb0, sub * 4);
+        if (++slot == kOz2Slots) { slot = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      const uint32_t smem0 = oz_smem_u32(smem);
+      uint32_t slot = 0, phase = 0;
+      oz2_issue_pass<S, 0>(smem0, full_bar, empty_bar, tmem_full, tmem_base, KT, slot, phase);
+      oz_mbar_wait(tmem_empty, 0);  // both CTAs' epilogues have drained the pass-0 accumulators
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      oz2_issue_pass<S, 1>(smem0, full_bar, empty_bar, tmem_full, tmem_base, KT, slot, phase);
+    }
+  } else if (warp >= 4) {
+    // Epilogue: 8 warps; warp w drains TMEM lanes 32 (w % 4) + 16 ((w - 4) / 4) .. + 15 with 16x256b loads, whose
+    // fragment is the mma accumulator layout: thread t holds lanes t/4 and t/4 + 8, columns 8 b + 2 (t % 4) + {0, 1}
+    // of every 8-column block b -- four threads cover 64 contiguous bytes of a C row, so global accesses are
+    // whole sectors without a shared-memory transpose.
+    const int q = warp & 3, half = (warp - 4) >> 2;
+    const int lane_base = q * 32 + half * 16;
+    const int r0 = lane_base + (lane >> 2), r1 = r0 + 8;
+    const int mrow0 = m0 + r0, mrow1 = m0 + r1;
+    const double sa0 = (mrow0 < M) ? scaleA[mrow0] : 0.0, sa1 = (mrow1 < M) ? scaleA[mrow1] : 0.0;
+    double* crow0 = nullptr;
+    double* crow1 = nullptr;
+    if (mrow0 < M) crow0 = out.C + (int64_t)(mrow0 / out.m_inner) * out.c_outer + (int64_t)(mrow0 % out.m_inner) * out.c_inner;
+    if (mrow1 < M) crow1 = out.C + (int64_t)(mrow1 / out.m_inner) * out.c_outer + (int64_t)(mrow1 % out.m_inner) * out.c_inner;
+    const int cpair = 2 * (lane & 3);
+    const uint32_t leader_empty = oz_mapa(oz_smem_u32(tmem_empty), 0);
+    for (int pass = 0; pass < 2; ++pass) {
+      const int d_lo = pass == 0 ? 4 : 0, nd = pass == 0 ? S - 4 : 4;
+      const bool add = pass == 1 || (accumulate & 1);
+      double wgt[4];
+#pragma unroll
+      for (int dd = 0; dd < 4; ++dd) wgt[dd] = ldexp(1.0, -7 * (d_lo + dd + 2));
+      oz_mbar_wait(tmem_full, (uint32_t)pass);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int c0 = 0; c0 < kOz2TileN; c0 += 16) {
+        // current values of the 2 rows x 2 blocks x 2 columns this thread owns (read-modify-write of pass 1)
+        double part[2][2][2];
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int n = n0 + c0 + 8 * b + cpair + e;
+            part[0][b][e] = (add && crow0 != nullptr && n < N) ? crow0[n] : 0.0;
+            part[1][b][e] = (add && crow1 != nullptr && n < N) ? crow1[n] : 0.0;
+          }
+        uint32_t v[4][8];
+#pragma unroll
+        for (int dd = 0; dd < 4; ++dd) {
+          if (dd < nd) {
+            const uint32_t taddr = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(dd * kOz2TileN + c0);
+            asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(v[dd][0]), "=r"(v[dd][1]), "=r"(v[dd][2]), "=r"(v[dd][3]), "=r"(v[dd][4]), "=r"(v[dd][5]),
+                           "=r"(v[dd][6]), "=r"(v[dd][7])
+                         : "r"(taddr));
+          }
+        }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int n = n0 + c0 + 8 * b + cpair + e;
+            const double sb = n < N ? scaleB[n] : 0.0;
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {  // registers 4 b + 2 rr + e: lane t/4 + 8 rr, column 8 b + 2 (t % 4) + e
+              double acc = 0.0;
+#pragma unroll
+              for (int dd = 3; dd >= 0; --dd)  // smallest weights first
+                if (dd < nd) acc = fma((double)(int)v[dd][4 * b + 2 * rr + e], wgt[dd], acc);
+              double* crow = rr == 0 ? crow0 : crow1;
+              if (crow != nullptr && n < N) crow[n] = fma(acc * (rr == 0 ? sa0 : sa1), sb, part[rr][b][e]);
+            }
+          }
+      }
+      if (pass == 0) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) oz_mbar_arrive_remote(leader_empty);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  oz_cluster_sync();  // the peer may still read this CTA's shared memory / signal its barriers until here
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 static PFN_cuTensorMapEncodeTiled_v12000 oz_encoder() {
@@ -279,7 +554,9 @@ static PFN_cuTensorMapEncodeTiled_v12000 oz_encoder() {
 }
 
 // slices[s][row][k]: dims (Kp, rows, S), box (kOzBK, box_rows, S), 64B swizzle
-static int oz_make_map(CUtensorMap* map, const int8_t* base, int64_t Kp, int rows, int S, int box_rows) {
+static int oz_make_map(CUtensorMap* map, const int8_t* base, int64_t Kp, int rows, int S, int box_rows,
+                       int box_slices = 0) {
+  if (box_slices <= 0) box_slices = S;
   auto enc = oz_encoder();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled not available from the driver");
@@ -287,7 +564,7 @@ static int oz_make_map(CUtensorMap* map, const int8_t* base, int64_t Kp, int row
   }
   cuuint64_t dims[3] = {(cuuint64_t)Kp, (cuuint64_t)rows, (cuuint64_t)S};
   cuuint64_t strides[2] = {(cuuint64_t)Kp, (cuuint64_t)Kp * rows};
-  cuuint32_t box[3] = {(cuuint32_t)kOzBK, (cuuint32_t)box_rows, (cuuint32_t)S};
+  cuuint32_t box[3] = {(cuuint32_t)kOzBK, (cuuint32_t)box_rows, (cuuint32_t)box_slices};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<int8_t*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -314,9 +591,40 @@ static int oz_slice(const double* P, int64_t ld, int K, int MN, double* scale, u
   return TNPY_OK;
 }
 
+// 1 = one CTA per 128 x 64 tile (oz_mma_kernel), 2 = CTA pair per 256 x 128 tile in two passes (oz2_mma_kernel)
+static std::atomic<int> g_oz_variant{0};
+static int oz_variant() {
+  int v = g_oz_variant.load();
+  if (v == 0) {
+    const char* e = getenv("TNPY_OZAKI_VARIANT");
+    v = (e && e[0] == '1') ? 1 : 2;
+    g_oz_variant.store(v);
+  }
+  return v;
+}
+
+template <int S>
+static int oz2_gemm(const int8_t* As, const double* scaleA, const int8_t* Bs, const double* scaleB, GemmOut out, int M,
+                    int N, int64_t Kp, int accumulate, cudaStream_t stream) {
+  CUtensorMap tmA, tmB;
+  TNPY_TRY(oz_make_map(&tmA, As, Kp, M, S, kOzBM, 4));
+  TNPY_TRY(oz_make_map(&tmB, Bs, Kp, N, S, kOzBN, 4));
+  constexpr int smem = kOz2Slots * kOz2Slot + 256 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    TNPY_CUDA_OK(cudaFuncSetAttribute(oz2_mma_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const int grid = 2 * ceil_div(N, kOz2TileN) * ceil_div(M, 2 * kOzBM);
+  oz2_mma_kernel<S><<<grid, kOz2Threads, smem, stream>>>(tmA, tmB, scaleA, scaleB, out, M, N, (int)(Kp / kOzBK), accumulate);
+  TNPY_LAUNCH_OK();
+  return TNPY_OK;
+}
+
 template <int S>
 static int oz_gemm(const int8_t* As, const double* scaleA, const int8_t* Bs, const double* scaleB, GemmOut out, int M,
                    int N, int64_t Kp, int accumulate, cudaStream_t stream) {
+  if (oz_variant() == 2) return oz2_gemm<S>(As, scaleA, Bs, scaleB, out, M, N, Kp, accumulate, stream);
   CUtensorMap tmA, tmB;
   TNPY_TRY(oz_make_map(&tmA, As, Kp, M, S, kOzBM));
   TNPY_TRY(oz_make_map(&tmB, Bs, Kp, N, S, kOzBN));
@@ -404,6 +712,15 @@ int ozaki_gemm(const double* A, int64_t lda, const double* B, int64_t ldb, GemmO
 }  // namespace tnpy
 
 using namespace tnpy;
+
+extern "C" int tnpy_set_ozaki_variant(int variant) {
+  if (variant != 1 && variant != 2) {
+    set_error("tnpy_set_ozaki_variant: variant must be 1 (single CTA, 128x64) or 2 (CTA pair, 256x128, two passes)");
+    return TNPY_EINVAL;
+  }
+  g_oz_variant.store(variant);
+  return TNPY_OK;
+}
 
 extern "C" int tnpy_set_ozaki_slices(int slices) {
   if (slices < 6 || slices > kOzMaxSlices) {
