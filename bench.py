@@ -312,6 +312,18 @@ def run_single(args):
         step_oc = lambda: _cuda.heff_apply(Lc, W, Rc, x, y, flags=both)  # noqa: E731
         step_oc()
         dt_oc = cuda_time(step_oc, args.steps, sync)
+        # as the eigensolver runs it: L and R declared constant, their slices made once per solve
+        _cuda.ozaki_const_scope(True)
+        try:
+            y_sc = _cuda.heff_apply(L, W, R, x).clone()
+            scope_diff = float((y_sc - y_oz).abs().max())
+            del y_sc
+            step_o()
+            dt_os = cuda_time(step_o, args.steps, sync)
+            step_oc()
+            dt_ocs = cuda_time(step_oc, args.steps, sync)
+        finally:
+            _cuda.ozaki_const_scope(False)
         del Lc, Rc
     finally:
         _cuda.set_gemm_algo(_cuda.GEMM_AUTO)
@@ -358,6 +370,7 @@ def run_single(args):
         sweep = measure_local_updates(dmrg, site, args.sweep_sites, Direction.RIGHTWARD, args.tol)
 
     value = flops * args.steps / dt / 1e12
+    gemm_flops_oz = 2.0 * (d * r) * (wl * l) * l + 2.0 * (d * l) * r * (r * wr)
     line = {
         "metric": "heff_matvec_fp64_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
@@ -385,9 +398,17 @@ def run_single(args):
             "ms_per_step": dt_o / args.steps * 1e3, "tflops_fp64_equivalent": flops * args.steps / dt_o / 1e12,
             "ms_per_step_canonical_gauge": dt_oc / args.steps * 1e3,
             "tflops_fp64_equivalent_canonical_gauge": flops * args.steps / dt_oc / 1e12,
+            "ms_per_step_const_env": dt_os / args.steps * 1e3,
+            "tflops_fp64_equivalent_const_env": flops * args.steps / dt_os / 1e12,
+            "ms_per_step_canonical_gauge_const_env": dt_ocs / args.steps * 1e3,
+            "tflops_fp64_equivalent_canonical_gauge_const_env": flops * args.steps / dt_ocs / 1e12,
+            "max_abs_diff_const_env_vs_resliced": scope_diff,
             "rel_diff_vs_dmma_path": ozaki_diff, "slices": 8,
-            "note": "same matvec with both GEMMs as 36 exact int8 slice GEMMs on tcgen05 (TMEM int32 accumulators), "
-                    "operands re-sliced every call; opt-in via TNPY_GEMM_ALGO=ozaki / tnpy_set_gemm_algo(3)",
+            "int8_pops_const_env": 36 * gemm_flops_oz * args.steps / dt_os / 1e15,
+            "note": "same matvec with both GEMMs as 36 exact int8 slice GEMMs on tcgen05 (CTA pairs, TMEM int32 "
+                    "accumulators); first figures re-slice every operand on every call, *_const_env keep the slices "
+                    "of L and R for the duration of a scope as tnpy_eig_lowest does; int8_pops = 36 x 2MNK of both "
+                    "GEMMs / whole-step time (ncu peak 4.48 POP/s at 1965 MHz); opt-in via TNPY_GEMM_ALGO=ozaki",
         },
         "canonical_gauge": {
             "ms_per_step": dt_c / args.steps * 1e3, "tflops_algorithmic": flops * args.steps / dt_c / 1e12,

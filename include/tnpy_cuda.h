@@ -92,6 +92,11 @@ int tnpy_set_ozaki_slices(int slices);
  * diagonals accumulated in two passes of four TMEM accumulators; 1 = one CTA per 128 x 64 tile, all eight
  * accumulators at once (operand-pipe bound, kept for comparison).  Env TNPY_OZAKI_VARIANT=1 selects 1. */
 int tnpy_set_ozaki_variant(int variant);
+/* Constant-operand scope for the tcgen05 path: between tnpy_ozaki_const_scope(1) and tnpy_ozaki_const_scope(0)
+ * the caller vouches that the B operands of the chains' GEMMs (the environments L and R) do not change, so
+ * their int8 slices are computed once and reused by every tnpy_heff_apply in the scope.  tnpy_eig_lowest
+ * opens such a scope itself.  Scopes nest; leaving the outermost one drops the cached slices. */
+int tnpy_ozaki_const_scope(int on);
 int tnpy_ozaki_gemm_tn(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
                        int M, int N, int K, int slices, int accumulate, int phase, void* workspace,
                        size_t workspace_bytes, void* stream);

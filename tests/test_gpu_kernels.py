@@ -479,3 +479,60 @@ def test_chain_with_ozaki_gemm(cu, chi, w):
         cu.set_gemm_algo(cu.GEMM_AUTO)
     assert float((got - ref).abs().max() / ref.abs().max()) < 1e-13
     assert float((got_env - ref_env).abs().max() / ref_env.abs().max()) < 1e-13
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("m,n,k", [(256, 128, 64), (700, 300, 1000), (1024, 1024, 1024), (520, 390, 4160), (4096, 2048, 640)])
+def test_ozaki_variants_agree(cu, variant, m, n, k):
+    """Both kernel generations (single CTA 128x64 / CTA pair 256x128 in two passes, with and without the
+    K-split of the last wave) are exact slice GEMMs: they agree with each other to rounding of the recombination
+    and with FP64 at the DMMA level.  (1024^3 and 520x390x4160 exercise the tail split, 4096x2048x640 a full wave.)"""
+    g = torch.Generator(device="cuda").manual_seed(7 * m + n + k)
+    a = torch.randn((k, m), generator=g, dtype=torch.float64, device="cuda")
+    b = torch.randn((k, n), generator=g, dtype=torch.float64, device="cuda")
+    ref = a.t() @ b
+    bound = a.abs().t() @ b.abs()
+    cu.set_ozaki_variant(variant)
+    try:
+        for s, tol in ((8, 4e-15), (7, 2e-13), (6, 3e-11)):
+            got = cu.ozaki_gemm_tn(a, b, slices=s)
+            assert float(((got - ref).abs() / bound).max()) < tol
+        c0 = torch.randn((m, n), generator=g, dtype=torch.float64, device="cuda")
+        acc = cu.ozaki_gemm_tn(a, b, out=c0.clone(), slices=8, accumulate=True)
+        assert float(((acc - (c0 + ref)).abs() / (bound + c0.abs())).max()) < 4e-15
+    finally:
+        cu.set_ozaki_variant(2)
+
+
+def test_ozaki_const_scope_reuses_and_drops_slices(cu):
+    """Inside a constant-operand scope the environments are sliced once; results are bit-identical to the
+    re-sliced path, and a changed environment is picked up again after the scope ends."""
+    chi, w, d = 1024, 5, 2
+    g = torch.Generator(device="cuda").manual_seed(3)
+    rnd = lambda *s: torch.randn(s, generator=g, dtype=torch.float64, device="cuda")  # noqa: E731
+    L, R, W, x = rnd(chi, w, chi), rnd(chi, w, chi), rnd(w, w, d, d), rnd(chi, d, chi)
+    cu.set_gemm_algo(cu.GEMM_OZAKI)
+    try:
+        plain = cu.heff_apply(L, W, R, x).clone()
+        cu.ozaki_const_scope(True)
+        try:
+            first = cu.heff_apply(L, W, R, x).clone()
+            n0 = cu.launch_count()
+            second = cu.heff_apply(L, W, R, 2.0 * x).clone()
+            launches_cached = cu.launch_count() - n0
+        finally:
+            cu.ozaki_const_scope(False)
+        n0 = cu.launch_count()
+        cu.heff_apply(L, W, R, x)
+        launches_plain = cu.launch_count() - n0
+        assert torch.equal(first, plain)
+        assert float((second - 2.0 * plain).abs().max() / plain.abs().max()) < 1e-14
+        assert launches_cached == launches_plain - 4  # colmax + slice kernels of L and of R skipped
+        L2 = L + 1.0
+        ref = cu.heff_apply(L2, W, R, x)
+        cu.set_gemm_algo(cu.GEMM_AUTO)
+        dmma = cu.heff_apply(L2, W, R, x)
+        assert float((ref - dmma).abs().max() / dmma.abs().max()) < 1e-13
+    finally:
+        cu.set_gemm_algo(cu.GEMM_AUTO)
+

@@ -32,6 +32,7 @@ SIGNATURES = {
     "tnpy_ozaki_workspace_bytes": (c_size_t, [c_int] * 4),
     "tnpy_set_ozaki_slices": (c_int, [c_int]),
     "tnpy_set_ozaki_variant": (c_int, [c_int]),
+    "tnpy_ozaki_const_scope": (c_int, [c_int]),
     "tnpy_ozaki_gemm_tn": (
         c_int,
         [_PD, c_int64, _PD, c_int64, _PD, c_int64] + [c_int] * 6 + [c_void_p, c_size_t, c_void_p],
@@ -128,6 +129,12 @@ def set_gemm_algo(algo: int) -> None:
 
 def set_ozaki_slices(slices: int) -> None:
     check(load().tnpy_set_ozaki_slices(int(slices)), "tnpy_set_ozaki_slices")
+
+
+def ozaki_const_scope(on: bool) -> None:
+    """Open / close a scope in which the environments passed to the chains are constant (tcgen05 path: their
+    int8 slices are then computed once).  ``tnpy_eig_lowest`` does this itself."""
+    check(load().tnpy_ozaki_const_scope(int(bool(on))), "tnpy_ozaki_const_scope")
 
 
 def set_ozaki_variant(variant: int) -> None:

@@ -12,6 +12,11 @@
 
 namespace tnpy {
 
+void ozaki_const_scope(bool on);
+struct OzConstScope {  // L, W, R are constant for the whole solve: their int8 slices are made once (tcgen05 path)
+  OzConstScope() { ozaki_const_scope(true); }
+  ~OzConstScope() { ozaki_const_scope(false); }
+};
 int heff_apply(const double* L, const double* W, const double* R, const double* x, double* y, int l, int r, int wl,
                int wr, int d, int flags, Workspace& ws, cudaStream_t stream);
 int multi_dot(const double* V, int64_t ldv, int m, const double* w, int64_t n, double* h, int mode,
@@ -253,6 +258,7 @@ extern "C" int tnpy_eig_lowest(const double* L, const double* W, const double* R
 
   int j = 0, n_matvec = 0, n_restart = 0;
   bool done = false;
+  OzConstScope const_operands;
   while (true) {
     double* vj = V + (int64_t)j * ldv;
     double* w = V + (int64_t)(j + 1) * ldv;

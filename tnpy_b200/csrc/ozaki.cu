@@ -63,15 +63,18 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict_
   const double sc = c < MN ? oz_scale_of(colmax[c]) : 0.0;
   const double inv = sc > 0.0 ? 1.0 / sc : 0.0;  // exact: power of two
   if (blockIdx.y == 0 && ty == 0 && c < MN) scale[c] = sc;
+  // digit = rint(128 t) without conversion instructions: adding 1.5 * 2^52 leaves the rounded integer in the low
+  // mantissa bits (two's complement), subtracting it again gives the rounded value; the remainder is exact.
+  const double magic = 6755399441055744.0;
+#pragma unroll 4
   for (int i = ty; i < 128; i += 8) {
     const int k = k0 + i;
     double t = (k < K && c < MN) ? P[(int64_t)k * ld + c] * inv : 0.0;  // |t| <= 0.5
 #pragma unroll
     for (int sl = 0; sl < S; ++sl) {
-      t *= 128.0;
-      const double dgt = rint(t);  // |dgt| <= 64
-      tile[sl][tx][i] = (int8_t)(int)dgt;
-      t -= dgt;                    // exact remainder, |t| <= 0.5
+      const double u = fma(t, 128.0, magic);
+      tile[sl][tx][i] = (int8_t)__double2loint(u);  // |digit| <= 64
+      t = fma(t, 128.0, magic - u);                 // exact remainder, |t| <= 0.5
     }
   }
   __syncthreads();
@@ -286,6 +289,15 @@ constexpr int kOz2Slot = kOz2SlotA + kOz2SlotB;
 constexpr int kOz2Slots = 4;
 constexpr int kOz2TileN = 2 * kOzBN;  // 128 columns per accumulator
 constexpr int kOz2EpiWarps = 8;       // two per TMEM lane quadrant
+constexpr int kOz2PartDepth = 4;      // 16-column chunks of C requested ahead of use in the epilogue
+
+// Tail splitting: tiles of the last, partly filled wave are cut along K (see oz2_mma_kernel).
+struct Oz2Tail {
+  int n_full;       // work items [0, n_full) are whole tiles
+  int rem;          // number of split tiles (tile indices n_full .. n_full + rem - 1)
+  int splits;       // K ranges per split tile
+  double* scratch;  // (splits - 1) * rem plain 256 x 128 tiles receiving the K ranges ks > 0
+};
 constexpr int kOz2Threads = 128 + 32 * kOz2EpiWarps;
 
 __device__ __forceinline__ uint32_t oz_cluster_rank() {
@@ -386,7 +398,7 @@ template <int S>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kOz2Threads, 1)
     oz2_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const double* __restrict__ scaleA, const double* __restrict__ scaleB, GemmOut out, int M, int N,
-                   int KT, int accumulate) {
+                   int KT, int accumulate, Oz2Tail tail) {
   static_assert(S > 4 && S <= 8, "two passes of at most four diagonals");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -398,11 +410,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kOz2Threads, 1)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = oz_cluster_rank();
-  int tm, tn;
+  int tm, tn, ks = 0, kt0 = 0, kt1 = KT;
+  double* tail_tile = nullptr;
   {
     const int tiles_m = (M + 2 * kOzBM - 1) / (2 * kOzBM), tiles_n = (N + kOz2TileN - 1) / kOz2TileN;
     constexpr int GROUP = 4;
-    const int tile = blockIdx.x >> 1, per_group = GROUP * tiles_n;
+    // work items: the first tail.n_full items are whole tiles; the tiles of the last, partly filled wave are cut
+    // into tail.splits K ranges each so that the wave fills the machine (part ks > 0 goes to a scratch tile)
+    int tile = blockIdx.x >> 1;
+    if (tile >= tail.n_full) {
+      const int j = tile - tail.n_full;
+      tile = tail.n_full + j % tail.rem;
+      ks = j / tail.rem;
+      kt0 = (int)((int64_t)KT * ks / tail.splits);
+      kt1 = (int)((int64_t)KT * (ks + 1) / tail.splits);
+      if (ks > 0) tail_tile = tail.scratch + (int64_t)((ks - 1) * tail.rem + (tile - tail.n_full)) * (2 * kOzBM * kOz2TileN);
+    }
+    const int per_group = GROUP * tiles_n;
     const int gid = tile / per_group, first_m = gid * GROUP;
     const int gsz = min(tiles_m - first_m, GROUP), rem = tile - gid * per_group;
     tm = first_m + rem % gsz;
@@ -435,11 +459,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kOz2Threads, 1)
   if (warp == 0) {
     if (lane == 0) {
       // load sequence: t in [0, 2 KT) = pass 0 (chunk t / 2, slice group t % 2), t in [2 KT, 3 KT) = pass 1 (group 0)
-      const int T = 3 * KT;
+      const int nk = kt1 - kt0, T = 3 * nk;
       uint32_t slot = 0, phase = 0;
       for (int t = 0; t < T; ++t) {
         int kt, sub;
-        if (t < 2 * KT) { kt = t >> 1; sub = t & 1; } else { kt = t - 2 * KT; sub = 0; }
+        if (t < 2 * nk) { kt = kt0 + (t >> 1); sub = t & 1; } else { kt = kt0 + t - 2 * nk; sub = 0; }
         oz_mbar_wait(&empty_bar[slot], phase ^ 1);
         if (rank == 0) oz_mbar_expect_tx(&full_bar[slot], 2 * kOz2Slot);  // both CTAs' boxes land on this barrier
         const uint32_t leader_full = oz_mapa(oz_smem_u32(&full_bar[slot]), 0);
@@ -453,10 +477,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kOz2Threads, 1)
     if (lane == 0 && rank == 0) {
       const uint32_t smem0 = oz_smem_u32(smem);
       uint32_t slot = 0, phase = 0;
-      oz2_issue_pass<S, 0>(smem0, full_bar, empty_bar, tmem_full, tmem_base, KT, slot, phase);
+      oz2_issue_pass<S, 0>(smem0, full_bar, empty_bar, tmem_full, tmem_base, kt1 - kt0, slot, phase);
       oz_mbar_wait(tmem_empty, 0);  // both CTAs' epilogues have drained the pass-0 accumulators
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      oz2_issue_pass<S, 1>(smem0, full_bar, empty_bar, tmem_full, tmem_base, KT, slot, phase);
+      oz2_issue_pass<S, 1>(smem0, full_bar, empty_bar, tmem_full, tmem_base, kt1 - kt0, slot, phase);
     }
   } else if (warp >= 4) {
     // Epilogue: 8 warps; warp w drains TMEM lanes 32 (w % 4) + 16 ((w - 4) / 4) .. + 15 with 16x256b loads, whose
@@ -468,31 +492,60 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kOz2Threads, 1)
     const int r0 = lane_base + (lane >> 2), r1 = r0 + 8;
     const int mrow0 = m0 + r0, mrow1 = m0 + r1;
     const double sa0 = (mrow0 < M) ? scaleA[mrow0] : 0.0, sa1 = (mrow1 < M) ? scaleA[mrow1] : 0.0;
+    // row pointers are biased by the tile's first column: element (row, n0 + c) lives at crow[c]
     double* crow0 = nullptr;
     double* crow1 = nullptr;
-    if (mrow0 < M) crow0 = out.C + (int64_t)(mrow0 / out.m_inner) * out.c_outer + (int64_t)(mrow0 % out.m_inner) * out.c_inner;
-    if (mrow1 < M) crow1 = out.C + (int64_t)(mrow1 / out.m_inner) * out.c_outer + (int64_t)(mrow1 % out.m_inner) * out.c_inner;
+    if (tail_tile != nullptr) {  // K part ks > 0 of a split tile: plain 256 x 128 scratch tile
+      if (mrow0 < M) crow0 = tail_tile + (int64_t)((int)rank * kOzBM + r0) * kOz2TileN;
+      if (mrow1 < M) crow1 = tail_tile + (int64_t)((int)rank * kOzBM + r1) * kOz2TileN;
+    } else {
+      if (mrow0 < M)
+        crow0 = out.C + (int64_t)(mrow0 / out.m_inner) * out.c_outer + (int64_t)(mrow0 % out.m_inner) * out.c_inner + n0;
+      if (mrow1 < M)
+        crow1 = out.C + (int64_t)(mrow1 / out.m_inner) * out.c_outer + (int64_t)(mrow1 % out.m_inner) * out.c_inner + n0;
+    }
     const int cpair = 2 * (lane & 3);
+    const int ncols = min(kOz2TileN, N - n0);  // valid columns of this tile
+    // 16-byte accesses when every pair this thread touches is aligned and in range (uniform per thread)
+    const bool vec = (ncols == kOz2TileN) && ((reinterpret_cast<uintptr_t>(crow0) | reinterpret_cast<uintptr_t>(crow1)) & 15) == 0;
     const uint32_t leader_empty = oz_mapa(oz_smem_u32(tmem_empty), 0);
     for (int pass = 0; pass < 2; ++pass) {
       const int d_lo = pass == 0 ? 4 : 0, nd = pass == 0 ? S - 4 : 4;
-      const bool add = pass == 1 || (accumulate & 1);
+      const bool add = pass == 1 || ((accumulate & 1) && tail_tile == nullptr);
       double wgt[4];
 #pragma unroll
       for (int dd = 0; dd < 4; ++dd) wgt[dd] = ldexp(1.0, -7 * (d_lo + dd + 2));
+      // Current values of the elements this thread owns (read-modify-write of pass 1), kept kOz2PartDepth column
+      // chunks ahead of their use; the first chunks are requested while the MMAs of this pass are still running.
+      double part[kOz2PartDepth][2][2][2];  // [chunk ring][row][block][column of the pair]
+      auto load_part = [&](int slot, int c0) {
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          const int c = c0 + 8 * b + cpair;
+          if (!add) {
+            part[slot][0][b][0] = part[slot][0][b][1] = part[slot][1][b][0] = part[slot][1][b][1] = 0.0;
+          } else if (vec) {
+            const double2 z = make_double2(0.0, 0.0);
+            const double2 p0 = crow0 ? *reinterpret_cast<const double2*>(crow0 + c) : z;
+            const double2 p1 = crow1 ? *reinterpret_cast<const double2*>(crow1 + c) : z;
+            part[slot][0][b][0] = p0.x; part[slot][0][b][1] = p0.y;
+            part[slot][1][b][0] = p1.x; part[slot][1][b][1] = p1.y;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              part[slot][0][b][e] = (crow0 != nullptr && c + e < ncols) ? crow0[c + e] : 0.0;
+              part[slot][1][b][e] = (crow1 != nullptr && c + e < ncols) ? crow1[c + e] : 0.0;
+            }
+          }
+        }
+      };
+#pragma unroll
+      for (int pc = 0; pc < kOz2PartDepth; ++pc) load_part(pc, 16 * pc);
       oz_mbar_wait(tmem_full, (uint32_t)pass);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      for (int c0 = 0; c0 < kOz2TileN; c0 += 16) {
-        // current values of the 2 rows x 2 blocks x 2 columns this thread owns (read-modify-write of pass 1)
-        double part[2][2][2];
 #pragma unroll
-        for (int b = 0; b < 2; ++b)
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int n = n0 + c0 + 8 * b + cpair + e;
-            part[0][b][e] = (add && crow0 != nullptr && n < N) ? crow0[n] : 0.0;
-            part[1][b][e] = (add && crow1 != nullptr && n < N) ? crow1[n] : 0.0;
-          }
+      for (int ci = 0; ci < kOz2TileN / 16; ++ci) {
+        const int c0 = 16 * ci;
         uint32_t v[4][8];
 #pragma unroll
         for (int dd = 0; dd < 4; ++dd) {
@@ -505,22 +558,37 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kOz2Threads, 1)
           }
         }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        double res[2][2][2];
 #pragma unroll
         for (int b = 0; b < 2; ++b)
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
-            const int n = n0 + c0 + 8 * b + cpair + e;
-            const double sb = n < N ? scaleB[n] : 0.0;
+            const int c = c0 + 8 * b + cpair + e;
+            const double sb = c < ncols ? scaleB[n0 + c] : 0.0;
 #pragma unroll
             for (int rr = 0; rr < 2; ++rr) {  // registers 4 b + 2 rr + e: lane t/4 + 8 rr, column 8 b + 2 (t % 4) + e
               double acc = 0.0;
 #pragma unroll
               for (int dd = 3; dd >= 0; --dd)  // smallest weights first
                 if (dd < nd) acc = fma((double)(int)v[dd][4 * b + 2 * rr + e], wgt[dd], acc);
-              double* crow = rr == 0 ? crow0 : crow1;
-              if (crow != nullptr && n < N) crow[n] = fma(acc * (rr == 0 ? sa0 : sa1), sb, part[rr][b][e]);
+              res[rr][b][e] = fma(acc * (rr == 0 ? sa0 : sa1), sb, part[ci % kOz2PartDepth][rr][b][e]);
             }
           }
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          const int c = c0 + 8 * b + cpair;
+          if (vec) {
+            if (crow0) *reinterpret_cast<double2*>(crow0 + c) = make_double2(res[0][b][0], res[0][b][1]);
+            if (crow1) *reinterpret_cast<double2*>(crow1 + c) = make_double2(res[1][b][0], res[1][b][1]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              if (crow0 != nullptr && c + e < ncols) crow0[c + e] = res[0][b][e];
+              if (crow1 != nullptr && c + e < ncols) crow1[c + e] = res[1][b][e];
+            }
+          }
+        }
+        if (ci + kOz2PartDepth < kOz2TileN / 16) load_part(ci % kOz2PartDepth, c0 + 16 * kOz2PartDepth);
       }
       if (pass == 0) {
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -603,6 +671,44 @@ static int oz_variant() {
   return v;
 }
 
+// C tile += scratch tiles of the K ranges ks = 1 .. splits-1, in that fixed order (deterministic).
+__global__ void __launch_bounds__(256) oz2_tail_combine_kernel(GemmOut out, int M, int N, int tiles_m, int tiles_n, Oz2Tail tail) {
+  const int idx = blockIdx.x;  // split tile
+  const int tile = tail.n_full + idx;
+  constexpr int GROUP = 4;
+  const int per_group = GROUP * tiles_n;
+  const int gid = tile / per_group, first_m = gid * GROUP;
+  const int gsz = min(tiles_m - first_m, GROUP), rem = tile - gid * per_group;
+  const int m0 = (first_m + rem % gsz) * 2 * kOzBM, n0 = (rem / gsz) * kOz2TileN;
+  for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < 2 * kOzBM * kOz2TileN; e += gridDim.y * blockDim.x) {
+    const int r = e / kOz2TileN, c = e % kOz2TileN;
+    const int m = m0 + r, n = n0 + c;
+    if (m >= M || n >= N) continue;
+    double* dst = out.C + (int64_t)(m / out.m_inner) * out.c_outer + (int64_t)(m % out.m_inner) * out.c_inner + n;
+    double acc = *dst;
+    for (int ks = 1; ks < tail.splits; ++ks) acc += tail.scratch[(int64_t)((ks - 1) * tail.rem + idx) * (2 * kOzBM * kOz2TileN) + e];
+    *dst = acc;
+  }
+}
+
+// scratch for the tail tiles of oz2_gemm (grow-only, per process)
+static int oz2_tail_scratch(size_t need, double** out) {
+  static void* ptr = nullptr;
+  static size_t bytes = 0;
+  if (bytes < need) {
+    if (ptr) {
+      TNPY_CUDA_OK(cudaDeviceSynchronize());
+      TNPY_CUDA_OK(cudaFree(ptr));
+      ptr = nullptr;
+      bytes = 0;
+    }
+    TNPY_CUDA_OK(cudaMalloc(&ptr, need));
+    bytes = need;
+  }
+  *out = static_cast<double*>(ptr);
+  return TNPY_OK;
+}
+
 template <int S>
 static int oz2_gemm(const int8_t* As, const double* scaleA, const int8_t* Bs, const double* scaleB, GemmOut out, int M,
                     int N, int64_t Kp, int accumulate, cudaStream_t stream) {
@@ -615,9 +721,32 @@ static int oz2_gemm(const int8_t* As, const double* scaleA, const int8_t* Bs, co
     TNPY_CUDA_OK(cudaFuncSetAttribute(oz2_mma_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  const int grid = 2 * ceil_div(N, kOz2TileN) * ceil_div(M, 2 * kOzBM);
-  oz2_mma_kernel<S><<<grid, kOz2Threads, smem, stream>>>(tmA, tmB, scaleA, scaleB, out, M, N, (int)(Kp / kOzBK), accumulate);
+  const int tiles_m = ceil_div(M, 2 * kOzBM), tiles_n = ceil_div(N, kOz2TileN), tiles = tiles_m * tiles_n;
+  const int KT = (int)(Kp / kOzBK);
+  // One CTA pair per SM pair at a time (shared memory): the last wave holds tiles % pairs tiles.  Cut those
+  // along K so that the last wave is as wide as the machine; parts ks > 0 go to scratch tiles and are added
+  // back in a fixed order.
+  const int pairs = sm_count() / 2;
+  Oz2Tail tail{tiles, 0, 1, nullptr};
+  const int rem = tiles % pairs;
+  if (rem > 0 && getenv("TNPY_OZAKI_NO_TAIL_SPLIT") == nullptr) {
+    int splits = pairs / rem;
+    while (splits > 1 && KT / splits < 8) --splits;
+    if (splits > 4) splits = 4;
+    const double full = (double)(tiles / pairs);
+    // worth it only when the last wave is a sizeable part of the run (each part pays its own two epilogues)
+    if (splits > 1 && (full + 1.0 / splits + 0.04) / (full + 1.0) < 0.93) {
+      tail = Oz2Tail{tiles - rem, rem, splits, nullptr};
+      TNPY_TRY(oz2_tail_scratch((size_t)(splits - 1) * rem * 2 * kOzBM * kOz2TileN * sizeof(double), &tail.scratch));
+    }
+  }
+  const int items = tail.n_full + tail.rem * tail.splits;
+  oz2_mma_kernel<S><<<2 * items, kOz2Threads, smem, stream>>>(tmA, tmB, scaleA, scaleB, out, M, N, KT, accumulate, tail);
   TNPY_LAUNCH_OK();
+  if (tail.splits > 1) {
+    oz2_tail_combine_kernel<<<dim3(tail.rem, 16), 256, 0, stream>>>(out, M, N, tiles_m, tiles_n, tail);
+    TNPY_LAUNCH_OK();
+  }
   return TNPY_OK;
 }
 
@@ -673,6 +802,65 @@ bool ozaki_applicable(int M, int N, int K) {
   return K <= 65536 && K >= 64 && M >= 128 && N >= 64 && (double)M * N * K >= 6.0e9;
 }
 
+// Slices of constant B operands (the environments L and R during one local eigensolve) are kept across calls:
+// between ozaki_const_scope(true) and ozaki_const_scope(false) the caller vouches that the B operand behind a
+// given (pointer, ld, K, N) does not change, so it is sliced once per scope instead of once per matvec.
+struct OzConstEntry {
+  const double* ptr = nullptr;
+  int64_t ld = 0;
+  int K = 0, N = 0, S = 0;
+  bool valid = false;
+  void* buf = nullptr;
+  size_t bytes = 0;
+};
+static OzConstEntry g_oz_const[4];
+static std::atomic<int> g_oz_const_depth{0};
+static int g_oz_const_next = 0;
+
+void ozaki_const_scope(bool on) {
+  if (on) {
+    if (g_oz_const_depth.fetch_add(1) == 0)
+      for (auto& e : g_oz_const) e.valid = false;
+  } else {
+    if (g_oz_const_depth.fetch_sub(1) == 1)
+      for (auto& e : g_oz_const) e.valid = false;
+  }
+}
+
+// Returns the cached (or freshly filled) slices of B; *fresh tells the caller to run the slicing kernels.
+static int oz_const_lookup(const double* B, int64_t ldb, int K, int N, int S, int64_t Kp, int8_t** slices, double** scale,
+                           unsigned long long** colmax, bool* fresh) {
+  for (auto& e : g_oz_const)
+    if (e.valid && e.ptr == B && e.ld == ldb && e.K == K && e.N == N && e.S == S) {
+      Workspace ws(e.buf, e.bytes);
+      *slices = ws.take<int8_t>((size_t)S * N * Kp);
+      *scale = ws.take<double>(N);
+      *colmax = ws.take<unsigned long long>(N);
+      *fresh = false;
+      return TNPY_OK;
+    }
+  OzConstEntry& e = g_oz_const[g_oz_const_next];
+  g_oz_const_next = (g_oz_const_next + 1) % 4;
+  const size_t need = Workspace::need((size_t)S * N * Kp, 1) + 2 * Workspace::need(N) + 512;
+  if (e.bytes < need) {
+    if (e.buf) {
+      TNPY_CUDA_OK(cudaDeviceSynchronize());
+      TNPY_CUDA_OK(cudaFree(e.buf));
+      e.buf = nullptr;
+      e.bytes = 0;
+    }
+    TNPY_CUDA_OK(cudaMalloc(&e.buf, need));
+    e.bytes = need;
+  }
+  e.ptr = B; e.ld = ldb; e.K = K; e.N = N; e.S = S; e.valid = true;
+  Workspace ws(e.buf, e.bytes);
+  *slices = ws.take<int8_t>((size_t)S * N * Kp);
+  *scale = ws.take<double>(N);
+  *colmax = ws.take<unsigned long long>(N);
+  *fresh = true;
+  return TNPY_OK;
+}
+
 // C (+)= A^T B through the int8 tensor cores; operands are sliced into the internal scratch.
 int ozaki_gemm(const double* A, int64_t lda, const double* B, int64_t ldb, GemmOut out, int M, int N, int K,
                int accumulate, cudaStream_t stream) {
@@ -693,18 +881,20 @@ int ozaki_gemm(const double* A, int64_t lda, const double* B, int64_t ldb, GemmO
     set_error("ozaki_gemm: internal scratch layout failed");
     return TNPY_EWORKSPACE;
   }
+  bool slice_b = true;
+  if (g_oz_const_depth.load() > 0) TNPY_TRY(oz_const_lookup(B, ldb, K, N, S, Kp, &Bs, &sb, &mb, &slice_b));
   switch (S) {
     case 6:
       TNPY_TRY(oz_slice<6>(A, lda, K, M, sa, ma, As, Kp, stream));
-      TNPY_TRY(oz_slice<6>(B, ldb, K, N, sb, mb, Bs, Kp, stream));
+      if (slice_b) TNPY_TRY(oz_slice<6>(B, ldb, K, N, sb, mb, Bs, Kp, stream));
       return oz_gemm<6>(As, sa, Bs, sb, out, M, N, Kp, accumulate, stream);
     case 7:
       TNPY_TRY(oz_slice<7>(A, lda, K, M, sa, ma, As, Kp, stream));
-      TNPY_TRY(oz_slice<7>(B, ldb, K, N, sb, mb, Bs, Kp, stream));
+      if (slice_b) TNPY_TRY(oz_slice<7>(B, ldb, K, N, sb, mb, Bs, Kp, stream));
       return oz_gemm<7>(As, sa, Bs, sb, out, M, N, Kp, accumulate, stream);
     default:
       TNPY_TRY(oz_slice<8>(A, lda, K, M, sa, ma, As, Kp, stream));
-      TNPY_TRY(oz_slice<8>(B, ldb, K, N, sb, mb, Bs, Kp, stream));
+      if (slice_b) TNPY_TRY(oz_slice<8>(B, ldb, K, N, sb, mb, Bs, Kp, stream));
       return oz_gemm<8>(As, sa, Bs, sb, out, M, N, Kp, accumulate, stream);
   }
 }
@@ -712,6 +902,11 @@ int ozaki_gemm(const double* A, int64_t lda, const double* B, int64_t ldb, GemmO
 }  // namespace tnpy
 
 using namespace tnpy;
+
+extern "C" int tnpy_ozaki_const_scope(int on) {
+  ozaki_const_scope(on != 0);
+  return TNPY_OK;
+}
 
 extern "C" int tnpy_set_ozaki_variant(int variant) {
   if (variant != 1 && variant != 2) {
