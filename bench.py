@@ -322,7 +322,15 @@ def run_single(args):
             dt_os = cuda_time(step_o, args.steps, sync)
             step_oc()
             dt_ocs = cuda_time(step_oc, args.steps, sync)
+            # 7 slices (28 slice GEMMs): what tnpy_eig_lowest selects when its tolerance is >= 1e-10
+            _cuda.set_ozaki_slices(7)
+            y_s7 = _cuda.heff_apply(L, W, R, x).clone()
+            s7_diff = float((y_s7 - y_oz).abs().max() / y_oz.abs().max())
+            del y_s7
+            step_oc()
+            dt_ocs7 = cuda_time(step_oc, args.steps, sync)
         finally:
+            _cuda.set_ozaki_slices(8)
             _cuda.ozaki_const_scope(False)
         del Lc, Rc
     finally:
@@ -365,9 +373,29 @@ def run_single(args):
     parity = float(np.abs(y_np - y.reshape(-1).cpu().numpy()).max())
 
     # local-update breakdown at mid-chain sites (what a sweep is made of)
-    sweep = None
+    sweep = sweep_oz = None
     if args.sweep_sites > 0:
         sweep = measure_local_updates(dmrg, site, args.sweep_sites, Direction.RIGHTWARD, args.tol)
+        # the same local updates with the chains' GEMMs on the tcgen05 path (the next sites of the same sweep)
+        _cuda.set_gemm_algo(_cuda.GEMM_OZAKI)
+        try:
+            sweep_oz = measure_local_updates(dmrg, site + args.sweep_sites, args.sweep_sites, Direction.RIGHTWARD, args.tol)
+        finally:
+            _cuda.set_gemm_algo(_cuda.GEMM_AUTO)
+
+    # the tcgen05 kernel alone on the two GEMM shapes of the step (operands already sliced): int8 roofline
+    t1 = torch.empty((d * r, wl * l), dtype=torch.float64, device="cuda")
+    t2 = torch.randn((r * wr, d * l), dtype=torch.float64, device="cuda")
+    yq = torch.empty((d * l, r), dtype=torch.float64, device="cuda")
+    oz_ms = []
+    for (am, bm, cm) in ((x.reshape(l, d * r), L.reshape(l, wl * l), t1), (t2, R.reshape(r * wr, r), yq)):
+        _cuda.ozaki_gemm_tn(am, bm, out=cm, slices=8, phase=1)
+        mm = lambda: _cuda.ozaki_gemm_tn(am, bm, out=cm, slices=8, phase=2)  # noqa: E731
+        mm()
+        oz_ms.append(cuda_time(mm, args.steps, sync) / args.steps * 1e3)
+    del t1, t2, yq
+    int8_peak = 4.48  # POP/s: ncu sm__ops_path_tensor_op_utcimma_src_int8 peak_sustained at 1965 MHz (profiles/)
+    oz_pops = 36 * gemm_flops / (sum(oz_ms) * 1e-3) / 1e15
 
     value = flops * args.steps / dt / 1e12
     gemm_flops_oz = 2.0 * (d * r) * (wl * l) * l + 2.0 * (d * l) * r * (r * wr)
@@ -382,7 +410,8 @@ def run_single(args):
         },
         "roofline": {
             "bound": "tensor", "achieved": gemm_flops / (tg1 + tg3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
-            "frac": gemm_flops / (tg1 + tg3) / 1e12 / fp64_peak, "traffic": None,
+            "frac": gemm_flops / (tg1 + tg3) / 1e12 / fp64_peak,
+            "traffic": 1.29e9 if chi == 2048 else None,  # dram read + write per launch (mean of the two), ncu --set full (profiles/r01_gemm_tn_dmma_ncu_full_raw.csv)
             "kernel": "gemm_tn_dmma (2 launches per matvec)", "ms_gemm1": tg1 * 1e3, "ms_gemm3": tg3 * 1e3,
             "peak_source": f"cuBLAS dgemm {m8}^3 via torch.matmul, best of 5 in this process (MEASURED_PEAKS.json has no FP64 entry)",
             "whole_step_frac": value / fp64_peak,
@@ -403,8 +432,18 @@ def run_single(args):
             "ms_per_step_canonical_gauge_const_env": dt_ocs / args.steps * 1e3,
             "tflops_fp64_equivalent_canonical_gauge_const_env": flops * args.steps / dt_ocs / 1e12,
             "max_abs_diff_const_env_vs_resliced": scope_diff,
+            "ms_per_step_canonical_gauge_const_env_7_slices": dt_ocs7 / args.steps * 1e3,
+            "tflops_fp64_equivalent_canonical_gauge_const_env_7_slices": flops * args.steps / dt_ocs7 / 1e12,
+            "rel_diff_7_vs_8_slices": s7_diff,
             "rel_diff_vs_dmma_path": ozaki_diff, "slices": 8,
             "int8_pops_const_env": 36 * gemm_flops_oz * args.steps / dt_os / 1e15,
+            "roofline": {
+                "bound": "tensor", "achieved": oz_pops, "peak": int8_peak, "unit": "POP/s (int8)", "frac": oz_pops / int8_peak,
+                "traffic": 1.63e9, "kernel": "oz2_mma_kernel<8> (2 launches per matvec)", "ms_gemm1": oz_ms[0],
+                "ms_gemm3": oz_ms[1], "fp64_equivalent_tflops": gemm_flops / (sum(oz_ms) * 1e-3) / 1e12,
+                "peak_source": "ncu sm__ops_path_tensor_op_utcimma_src_int8 peak_sustained (profiles/r01_oz2_mma_kernel_ncu_full_raw.csv); "
+                               "traffic = dram read + write per launch (mean of the two shapes) from the same capture",
+            },
             "note": "same matvec with both GEMMs as 36 exact int8 slice GEMMs on tcgen05 (CTA pairs, TMEM int32 "
                     "accumulators); first figures re-slice every operand on every call, *_const_env keep the slices "
                     "of L and R for the duration of a scope as tnpy_eig_lowest does; int8_pops = 36 x 2MNK of both "
@@ -419,6 +458,8 @@ def run_single(args):
     }
     if sweep is not None:
         line["sweep"] = sweep
+    if sweep_oz is not None:
+        line["sweep_tcgen05"] = sweep_oz
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(chi)
     print(json.dumps(line), flush=True)

@@ -13,9 +13,20 @@
 namespace tnpy {
 
 void ozaki_const_scope(bool on);
-struct OzConstScope {  // L, W, R are constant for the whole solve: their int8 slices are made once (tcgen05 path)
-  OzConstScope() { ozaki_const_scope(true); }
-  ~OzConstScope() { ozaki_const_scope(false); }
+void ozaki_scope_slices(int slices);
+int ozaki_slices();
+// L, W, R are constant for the whole solve: their int8 slices are made once (tcgen05 path).  A matvec whose
+// error (2e-14 |A|^T|B| with 7 slices) is orders of magnitude below the residual tolerance does not need the
+// eighth slice: 28 instead of 36 slice GEMMs.  The configured count is restored when the solve ends.
+struct OzConstScope {
+  explicit OzConstScope(double tol) {
+    ozaki_const_scope(true);
+    if (tol >= 1e-10 && ozaki_slices() == 8) ozaki_scope_slices(7);
+  }
+  ~OzConstScope() {
+    ozaki_scope_slices(0);
+    ozaki_const_scope(false);
+  }
 };
 int heff_apply(const double* L, const double* W, const double* R, const double* x, double* y, int l, int r, int wl,
                int wr, int d, int flags, Workspace& ws, cudaStream_t stream);
@@ -258,7 +269,7 @@ extern "C" int tnpy_eig_lowest(const double* L, const double* W, const double* R
 
   int j = 0, n_matvec = 0, n_restart = 0;
   bool done = false;
-  OzConstScope const_operands;
+  OzConstScope const_operands(tol);
   while (true) {
     double* vj = V + (int64_t)j * ldv;
     double* w = V + (int64_t)(j + 1) * ldv;

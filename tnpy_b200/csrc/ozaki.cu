@@ -795,7 +795,13 @@ static int oz_scratch(size_t need, void** out) {
 }
 
 static std::atomic<int> g_oz_slices{8};
-int ozaki_slices() { return g_oz_slices.load(); }
+static std::atomic<int> g_oz_scope_slices{0};  // override inside an eigensolve whose tolerance allows fewer slices
+int ozaki_slices() {
+  const int o = g_oz_scope_slices.load();
+  return o ? o : g_oz_slices.load();
+}
+// 0 clears the override.  7 slices: error ~2e-14 |A|^T|B| per GEMM, far below a residual tolerance >= 1e-10 ||A||.
+void ozaki_scope_slices(int slices) { g_oz_scope_slices.store(slices); }
 
 bool ozaki_applicable(int M, int N, int K) {
   // below ~chi = 1024 the slicing passes and extra launches cost more than the faster MMA saves (measured at chi = 512)

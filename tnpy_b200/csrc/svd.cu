@@ -312,6 +312,10 @@ __global__ void __launch_bounds__(512) jb_rotate_kernel(const double* __restrict
   if (nsig == 0) return;  // nothing to rotate here: jb_apply skips this panel
   constexpr int half = kJP / 2;
   {
+    // One inner round = `half` disjoint rotations J = prod_i R_i.  a <- J^T a J is applied in a single pass:
+    // thread (i, j) owns the 2x2 block a[{p_i, q_i}][{p_j, q_j}], rotates its columns with R_j and its rows with
+    // R_i, and nobody else touches those four entries -- so a round costs two barriers (parameters, update)
+    // instead of three, and the parameter chain is div -> sqrt -> div -> rsqrt.
     const int inner_rounds = cross_only ? kJB : kJP - 1;
     for (int round = 0; round < inner_rounds; ++round) {
       if (tid < half) {
@@ -327,7 +331,7 @@ __global__ void __launch_bounds__(512) jb_rotate_kernel(const double* __restrict
         if (fabs(apq) > tol * sqrt(app * aqq) && apq != 0.0) {
           const double tau = (aqq - app) / (2.0 * apq);
           const double tt = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-          c = 1.0 / sqrt(1.0 + tt * tt);
+          c = rsqrt(1.0 + tt * tt);
           s = tt * c;
         }
         cs[tid] = c;
@@ -336,29 +340,30 @@ __global__ void __launch_bounds__(512) jb_rotate_kernel(const double* __restrict
         qq[tid] = q;
       }
       __syncthreads();
+      for (int idx = tid; idx < half * half; idx += nt) {
+        const int i = idx / half, j = idx % half;
+        const double ci = cs[i], si = sn[i], cj = cs[j], sj = sn[j];
+        if (si == 0.0 && sj == 0.0) continue;
+        const int pi = pp[i], qi = qq[i], pj = pp[j], qj = qq[j];
+        const double m00 = a[pi][pj], m01 = a[pi][qj], m10 = a[qi][pj], m11 = a[qi][qj];
+        // columns: (col p_j, col q_j) <- (c_j col p_j - s_j col q_j, s_j col p_j + c_j col q_j)
+        const double t00 = cj * m00 - sj * m01, t01 = sj * m00 + cj * m01;
+        const double t10 = cj * m10 - sj * m11, t11 = sj * m10 + cj * m11;
+        // rows: (row p_i, row q_i) <- (c_i row p_i - s_i row q_i, s_i row p_i + c_i row q_i)
+        a[pi][pj] = ci * t00 - si * t10;
+        a[pi][qj] = ci * t01 - si * t11;
+        a[qi][pj] = si * t00 + ci * t10;
+        a[qi][qj] = si * t01 + ci * t11;
+      }
       for (int idx = tid; idx < half * kJP; idx += nt) {
         const int i = idx / kJP, k = idx % kJP;
         const double s = sn[i];
         if (s == 0.0) continue;
         const double c = cs[i];
         const int p = pp[i], q = qq[i];
-        const double akp = a[k][p], akq = a[k][q];
-        a[k][p] = c * akp - s * akq;
-        a[k][q] = s * akp + c * akq;
         const double zkp = z[k][p], zkq = z[k][q];
         z[k][p] = c * zkp - s * zkq;
         z[k][q] = s * zkp + c * zkq;
-      }
-      __syncthreads();
-      for (int idx = tid; idx < half * kJP; idx += nt) {
-        const int i = idx / kJP, k = idx % kJP;
-        const double s = sn[i];
-        if (s == 0.0) continue;
-        const double c = cs[i];
-        const int p = pp[i], q = qq[i];
-        const double apk = a[p][k], aqk = a[q][k];
-        a[p][k] = c * apk - s * aqk;
-        a[q][k] = s * apk + c * aqk;
       }
       __syncthreads();
     }
