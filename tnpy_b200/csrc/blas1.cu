@@ -43,9 +43,11 @@ template <int MB>
 __global__ void __launch_bounds__(kRedThreads) multi_dot_kernel(const double* __restrict__ V, int64_t ldv, int m,
                                                                 const double* __restrict__ w, int64_t n,
                                                                 double* __restrict__ h, double* __restrict__ partials,
-                                                                unsigned int* __restrict__ counter, int mode) {
+                                                                unsigned int* __restrict__ counter, int mode,
+                                                                const int* __restrict__ skip) {
   __shared__ double sh[32];
   __shared__ bool is_last;
+  if (skip != nullptr && *skip != 0) return;  // uniform over the grid: the caller decided on the device
   const int64_t n2 = n / 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int j0 = 0; j0 < m; j0 += MB) {
@@ -98,9 +100,11 @@ __global__ void __launch_bounds__(kRedThreads) multi_dot_scalar_kernel(const dou
                                                                        const double* __restrict__ w, int64_t n,
                                                                        double* __restrict__ h,
                                                                        double* __restrict__ partials,
-                                                                       unsigned int* __restrict__ counter, int mode) {
+                                                                       unsigned int* __restrict__ counter, int mode,
+                                                                       const int* __restrict__ skip) {
   __shared__ double sh[32];
   __shared__ bool is_last;
+  if (skip != nullptr && *skip != 0) return;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int j = 0; j < m; ++j) {
     double acc = 0.0;
@@ -125,7 +129,7 @@ __global__ void __launch_bounds__(kRedThreads) multi_dot_scalar_kernel(const dou
 }
 
 int multi_dot(const double* V, int64_t ldv, int m, const double* w, int64_t n, double* h, int mode,
-              cudaStream_t stream) {
+              cudaStream_t stream, const int* skip) {
   TNPY_CHECK_ARG(V && w && h && n > 0 && m > 0 && m <= kMaxMulti, "bad argument");
   RedScratch& s = red_scratch();
   if (!s.partials) {
@@ -136,13 +140,13 @@ int multi_dot(const double* V, int64_t ldv, int m, const double* w, int64_t n, d
   const bool vec = (reinterpret_cast<uintptr_t>(V) % 16 == 0) && (reinterpret_cast<uintptr_t>(w) % 16 == 0) &&
                    (ldv % 2 == 0 || m == 1);
   if (!vec)
-    multi_dot_scalar_kernel<<<blocks, kRedThreads, 0, stream>>>(V, ldv, m, w, n, h, s.partials, s.counter, mode);
+    multi_dot_scalar_kernel<<<blocks, kRedThreads, 0, stream>>>(V, ldv, m, w, n, h, s.partials, s.counter, mode, skip);
   else if (m == 1)
-    multi_dot_kernel<1><<<blocks, kRedThreads, 0, stream>>>(V, ldv, m, w, n, h, s.partials, s.counter, mode);
+    multi_dot_kernel<1><<<blocks, kRedThreads, 0, stream>>>(V, ldv, m, w, n, h, s.partials, s.counter, mode, skip);
   else if (m == 2)
-    multi_dot_kernel<2><<<blocks, kRedThreads, 0, stream>>>(V, ldv, m, w, n, h, s.partials, s.counter, mode);
+    multi_dot_kernel<2><<<blocks, kRedThreads, 0, stream>>>(V, ldv, m, w, n, h, s.partials, s.counter, mode, skip);
   else
-    multi_dot_kernel<4><<<blocks, kRedThreads, 0, stream>>>(V, ldv, m, w, n, h, s.partials, s.counter, mode);
+    multi_dot_kernel<4><<<blocks, kRedThreads, 0, stream>>>(V, ldv, m, w, n, h, s.partials, s.counter, mode, skip);
   TNPY_LAUNCH_OK();
   return TNPY_OK;
 }
@@ -153,10 +157,12 @@ __global__ void __launch_bounds__(kRedThreads) multi_axpy_kernel(const double* _
                                                                  const double* __restrict__ h, double* __restrict__ w,
                                                                  int64_t n, int vec, double* __restrict__ nrm,
                                                                  double* __restrict__ partials,
-                                                                 unsigned int* __restrict__ counter) {
+                                                                 unsigned int* __restrict__ counter,
+                                                                 const int* __restrict__ skip) {
   __shared__ double hs[kMaxMulti];
   __shared__ double sh[32];
   __shared__ bool is_last;
+  if (skip != nullptr && *skip != 0) return;
   for (int j = threadIdx.x; j < m; j += blockDim.x) hs[j] = h[j];
   __syncthreads();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -207,7 +213,7 @@ __global__ void __launch_bounds__(kRedThreads) multi_axpy_kernel(const double* _
 }
 
 int multi_axpy(const double* V, int64_t ldv, int m, const double* h, double* w, int64_t n, double* nrm_out,
-               cudaStream_t stream) {
+               cudaStream_t stream, const int* skip) {
   TNPY_CHECK_ARG(V && h && w && n > 0 && m > 0 && m <= kMaxMulti, "bad argument");
   RedScratch& s = red_scratch();
   if (!s.partials) {
@@ -218,9 +224,9 @@ int multi_axpy(const double* V, int64_t ldv, int m, const double* h, double* w, 
   const int vec = (reinterpret_cast<uintptr_t>(V) % 16 == 0) && (reinterpret_cast<uintptr_t>(w) % 16 == 0) &&
                   (ldv % 2 == 0 || m == 1);
   if (nrm_out)
-    multi_axpy_kernel<true><<<blocks, kRedThreads, 0, stream>>>(V, ldv, m, h, w, n, vec, nrm_out, s.partials, s.counter);
+    multi_axpy_kernel<true><<<blocks, kRedThreads, 0, stream>>>(V, ldv, m, h, w, n, vec, nrm_out, s.partials, s.counter, skip);
   else
-    multi_axpy_kernel<false><<<blocks, kRedThreads, 0, stream>>>(V, ldv, m, h, w, n, vec, nullptr, s.partials, s.counter);
+    multi_axpy_kernel<false><<<blocks, kRedThreads, 0, stream>>>(V, ldv, m, h, w, n, vec, nullptr, s.partials, s.counter, skip);
   TNPY_LAUNCH_OK();
   return TNPY_OK;
 }
@@ -327,10 +333,10 @@ int combine(const double* V, int64_t ldv, int m, const double* c, int64_t ldc_, 
 using namespace tnpy;
 
 extern "C" int tnpy_dot(const double* x, const double* y, int64_t n, double* result, void* stream) {
-  return multi_dot(x, n, 1, y, n, result, 0, static_cast<cudaStream_t>(stream));
+  return multi_dot(x, n, 1, y, n, result, 0, static_cast<cudaStream_t>(stream), nullptr);
 }
 extern "C" int tnpy_nrm2(const double* x, int64_t n, double* result, void* stream) {
-  return multi_dot(x, n, 1, x, n, result, 1, static_cast<cudaStream_t>(stream));
+  return multi_dot(x, n, 1, x, n, result, 1, static_cast<cudaStream_t>(stream), nullptr);
 }
 extern "C" int tnpy_axpy(double alpha, const double* x, double* y, int64_t n, void* stream) {
   return axpy(alpha, nullptr, x, y, n, static_cast<cudaStream_t>(stream));
@@ -345,9 +351,9 @@ extern "C" int tnpy_scal(double alpha, double* x, int64_t n, void* stream) {
 }
 extern "C" int tnpy_multi_dot(const double* V, int64_t ldv, int m, const double* w, int64_t n, double* h,
                               void* stream) {
-  return multi_dot(V, ldv, m, w, n, h, 0, static_cast<cudaStream_t>(stream));
+  return multi_dot(V, ldv, m, w, n, h, 0, static_cast<cudaStream_t>(stream), nullptr);
 }
 extern "C" int tnpy_multi_axpy(const double* V, int64_t ldv, int m, const double* h, double* w, int64_t n,
                                void* stream) {
-  return multi_axpy(V, ldv, m, h, w, n, nullptr, static_cast<cudaStream_t>(stream));
+  return multi_axpy(V, ldv, m, h, w, n, nullptr, static_cast<cudaStream_t>(stream), nullptr);
 }

@@ -16,9 +16,9 @@ namespace tnpy {
 int heff_apply(const double* L, const double* W, const double* R, const double* x, double* y, int l, int r, int wl,
                int wr, int d, int flags, Workspace& ws, cudaStream_t stream);
 int multi_dot(const double* V, int64_t ldv, int m, const double* w, int64_t n, double* h, int mode,
-              cudaStream_t stream);
+              cudaStream_t stream, const int* skip = nullptr);
 int multi_axpy(const double* V, int64_t ldv, int m, const double* h, double* w, int64_t n, double* nrm_out,
-               cudaStream_t stream);
+               cudaStream_t stream, const int* skip = nullptr);
 int scale_copy(const double* x, double* out, int64_t n, double alpha, const double* s_dev, int inv,
                cudaStream_t stream);
 int axpy(double alpha, const double* a_dev, const double* x, double* y, int64_t n, cudaStream_t stream);

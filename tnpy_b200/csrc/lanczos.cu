@@ -31,9 +31,9 @@ struct OzConstScope {
 int heff_apply(const double* L, const double* W, const double* R, const double* x, double* y, int l, int r, int wl,
                int wr, int d, int flags, Workspace& ws, cudaStream_t stream);
 int multi_dot(const double* V, int64_t ldv, int m, const double* w, int64_t n, double* h, int mode,
-              cudaStream_t stream);
+              cudaStream_t stream, const int* skip = nullptr);
 int multi_axpy(const double* V, int64_t ldv, int m, const double* h, double* w, int64_t n, double* nrm_out,
-               cudaStream_t stream);
+               cudaStream_t stream, const int* skip = nullptr);
 int scale_copy(const double* x, double* out, int64_t n, double alpha, const double* s_dev, int inv,
                cudaStream_t stream);
 int combine(const double* V, int64_t ldv, int m, const double* c, int64_t ldc_, int nout, double* out, int64_t ldo,
@@ -205,6 +205,24 @@ static size_t eig_ws_layout(int64_t n, int ncv, int keep, size_t chain) {
   return total;
 }
 
+// skip = 1 when the first Gram-Schmidt pass did not cancel heavily (||w'|| >= eta ||h||); h2 is then zero.
+__global__ void reorth_decision_kernel(const double* __restrict__ h, int m, const double* __restrict__ nrm_after,
+                                       double eta, double* __restrict__ h2, int* __restrict__ skip) {
+  __shared__ double sh[32];
+  double a = 0.0;
+  for (int j = threadIdx.x; j < m; j += blockDim.x) a = fma(h[j], h[j], a);
+  a = block_sum(a, sh);
+  __shared__ int decision;
+  if (threadIdx.x == 0) {
+    const double hn = sqrt(a), wn = *nrm_after;
+    decision = (wn >= eta * hn && wn > 0.0) ? 1 : 0;
+    *skip = decision;
+  }
+  __syncthreads();
+  if (decision)
+    for (int j = threadIdx.x; j < m; j += blockDim.x) h2[j] = 0.0;
+}
+
 static void pick_sizes(int64_t n, int ncv_in, int& ncv, int& keep) {
   // default basis of 32: on hard local problems (first sweeps from a random MPS) thick restart with
   // (32, 10) needs ~20 % fewer matvecs than (20, 6) and is within ~10 % of unrestarted Lanczos, while the
@@ -251,6 +269,7 @@ extern "C" int tnpy_eig_lowest(const double* L, const double* W, const double* R
   double* h = ws.take<double>(64);
   double* h2 = ws.take<double>(64);
   double* status = ws.take<double>(64);
+  int* skip2 = reinterpret_cast<int*>(status + 48);  // device flag: skip the second Gram-Schmidt pass of this step
   if (!V || !Y || !T || !S || !thetas || !h || !h2 || !status) {
     set_error("tnpy_eig_lowest: workspace too small (%zu bytes given)", workspace_bytes);
     return TNPY_EWORKSPACE;
@@ -269,6 +288,7 @@ extern "C" int tnpy_eig_lowest(const double* L, const double* W, const double* R
 
   int j = 0, n_matvec = 0, n_restart = 0;
   bool done = false;
+  const double eta = fmax(1e-3, 2.220446049250313e-16 / (1e-3 * tol));
   OzConstScope const_operands(tol);
   while (true) {
     double* vj = V + (int64_t)j * ldv;
@@ -278,10 +298,16 @@ extern "C" int tnpy_eig_lowest(const double* L, const double* W, const double* R
     ++n_matvec;
     // classical Gram-Schmidt against the whole basis, applied twice; the first-pass coefficients are
     // column j of T = V^T H V, the second pass adds the rounding-level correction.
+    // The second pass is what "twice is enough" asks for when the first one cancelled heavily; it is decided on
+    // the device: with ||w'|| >= eta ||h|| the first pass leaves w' orthogonal to the basis to ~eps / eta, which
+    // is kept three orders below the requested residual tolerance (eta >= 1: always two passes, e.g. tol 1e-13),
+    // and the two extra passes over V are skipped.
     TNPY_TRY(multi_dot(V, ldv, j + 1, w, n, h, 0, stream));
-    TNPY_TRY(multi_axpy(V, ldv, j + 1, h, w, n, nullptr, stream));
-    TNPY_TRY(multi_dot(V, ldv, j + 1, w, n, h2, 0, stream));
-    TNPY_TRY(multi_axpy(V, ldv, j + 1, h2, w, n, status + ST_BETA, stream));
+    TNPY_TRY(multi_axpy(V, ldv, j + 1, h, w, n, status + ST_BETA, stream));
+    reorth_decision_kernel<<<1, 64, 0, stream>>>(h, j + 1, status + ST_BETA, eta, h2, skip2);
+    TNPY_LAUNCH_OK();
+    TNPY_TRY(multi_dot(V, ldv, j + 1, w, n, h2, 0, stream, skip2));
+    TNPY_TRY(multi_axpy(V, ldv, j + 1, h2, w, n, status + ST_BETA, stream, skip2));
     ritz_kernel<<<1, 256, 0, stream>>>(T, h, h2, status + ST_BETA, j, tol, S, thetas, status);
     TNPY_LAUNCH_OK();
     TNPY_TRY(scale_copy(w, w, n, 1.0, status + ST_BETA, 1, stream));

@@ -20,7 +20,7 @@
 namespace tnpy {
 
 int multi_dot(const double* V, int64_t ldv, int m, const double* w, int64_t n, double* h, int mode,
-              cudaStream_t stream);
+              cudaStream_t stream, const int* skip = nullptr);
 
 __device__ __forceinline__ void rr_pair(int round, int i, int me, int& p, int& q) {
   // round-robin tournament over `me` (even) players: player me-1 fixed, the rest rotate
@@ -124,7 +124,8 @@ constexpr int kJP = 2 * kJB;        // rows per panel (block pair)
 constexpr int kJCH = 128;           // columns per shared-memory chunk
 constexpr int kJST = kJCH + 4;      // panel row stride in shared memory (conflict-free DMMA fragments)
 constexpr int kJTS = kJP + 4;       // rotation-matrix row stride in shared memory
-constexpr int kJGramCols = 512;     // columns of G per jb_gram CTA
+constexpr int kJGramCols = 256;     // columns of G per jb_gram CTA
+constexpr int kJApplyCols = 256;    // columns of [G | P] per jb_apply CTA (kJCH at a time)
 // Vectors below theta * max norm would be orthogonalised among themselves first (cluster phase).
 // Measured on DMRG wave functions (scripts/svd_trace.py): the cluster phase converges, but the full
 // phase that follows still needs as many sweeps as without it, so the schedule is disabled (theta = 0
@@ -382,9 +383,11 @@ __global__ void __launch_bounds__(256) jb_apply_kernel(double* __restrict__ GP, 
   int I, J;
   block_pair(round, blockIdx.x, ph, I, J);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const int c0 = blockIdx.y * kJCH, c_end = min(width, c0 + kJCH);
+  const int c_first = blockIdx.y * kJApplyCols, c_end = min(width, c_first + kJApplyCols);
   const double* jsrc = Jt + (int64_t)blockIdx.x * kJP * kJP;
   for (int idx = threadIdx.x; idx < kJP * kJP; idx += blockDim.x) jt[(idx / kJP) * kJTS + idx % kJP] = jsrc[idx];
+  // the 32 KB rotation is loaded once and applied to kJApplyCols / kJCH column chunks of the panel
+  for (int c0 = c_first; c0 < c_end; c0 += kJCH) {
   load_panel(GP, ld, I, J, c0, c_end, panel);
   __syncthreads();
   double acc[8][2][2];
@@ -413,6 +416,8 @@ __global__ void __launch_bounds__(256) jb_apply_kernel(double* __restrict__ GP, 
       if (c0 + c + 1 < c_end) *reinterpret_cast<double2*>(dst + c) = make_double2(acc[i][j][0], acc[i][j][1]);
       else if (c0 + c < c_end) dst[c] = acc[i][j][0];
     }
+  }
+  __syncthreads();  // the panel buffer is reloaded for the next chunk
   }
 }
 
@@ -581,7 +586,7 @@ static BlockPlan block_plan(int n, int m) {
   p.pairs = p.nb / 2;
   p.ld = ((int64_t)m + p.n_pad + 3) / 4 * 4;
   p.gchunks = (m + kJGramCols - 1) / kJGramCols;
-  p.achunks = (int)((m + p.n_pad + kJCH - 1) / kJCH);
+  p.achunks = (int)((m + p.n_pad + kJApplyCols - 1) / kJApplyCols);
   p.gp_elems = (size_t)p.n_pad * p.ld;
   p.partial_elems = (size_t)p.pairs * p.gchunks * kJP * kJP;
   p.jt_elems = (size_t)p.pairs * kJP * kJP;
