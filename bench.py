@@ -466,15 +466,22 @@ def run_single(args):
 
 
 def measure_local_updates(dmrg, site, count, direction, tol):
-    """Full local updates (eigensolve + perturb + SVD split + env update) at consecutive mid-chain
+    """Full local updates (eigensolve + perturb + split + env update) at consecutive mid-chain
     sites; per-phase device time and an extrapolated sweep time (sum over sites of the measured
-    per-site time scaled by F_mv(site) / F_mv(mid))."""
+    per-site time scaled by F_mv(site) / F_mv(mid)).  `split` is what the sweep runs (verified
+    Cholesky-QR split -- two passes, then the shifted three-pass variant, then the SVD, whichever the
+    device-side orthogonality check accepted first, all attempts inside the timed phase); the reference-literal Jacobi SVD split
+    of the same tensor is timed beside it on a copy (`svd_split_reference_gauge`, not part of the total)."""
     import torch
+
+    from tnpy_b200.matrix_product_state import Direction, _split_on_device
 
     env = dmrg.environment
     sync = torch.cuda.synchronize
-    phases = {"eigensolve": 0.0, "perturb": 0.0, "svd_split": 0.0, "env_update": 0.0}
+    phases = {"eigensolve": 0.0, "perturb": 0.0, "split": 0.0, "env_update": 0.0}
     matvecs = 0
+    svd_gauge_s = 0.0
+    counts0 = dict(env.split_counts)
     for s in range(site, site + count):
         sync(); t = time.perf_counter()
         dmrg._solve_on_device(s, tol)
@@ -482,8 +489,12 @@ def measure_local_updates(dmrg, site, count, direction, tol):
         matvecs += dmrg.solver_stats[-1].get("n_matvec", 0)
         dmrg.perturb_wave_function(s)
         sync(); phases["perturb"] += time.perf_counter() - t; t = time.perf_counter()
+        nb_site = s + 1 if direction == Direction.RIGHTWARD else s - 1
+        sync(); t = time.perf_counter()
+        _split_on_device(env.device_tensor(s), env.device_tensor(nb_site), direction, "svd")
+        sync(); svd_gauge_s += time.perf_counter() - t; t = time.perf_counter()
         env.split_tensor(s, direction)
-        sync(); phases["svd_split"] += time.perf_counter() - t; t = time.perf_counter()
+        sync(); phases["split"] += time.perf_counter() - t; t = time.perf_counter()
         env.update(s, direction)
         sync(); phases["env_update"] += time.perf_counter() - t
     per_site = {k: v / count for k, v in phases.items()}
@@ -496,6 +507,9 @@ def measure_local_updates(dmrg, site, count, direction, tol):
     return {
         "sites_measured": count, "per_site_s": per_site, "per_site_total_s": total,
         "matvecs_per_site": matvecs / count, "sweep_s_extrapolated": total * weight,
+        "svd_split_reference_gauge_s": svd_gauge_s / count,
+        "sweep_s_extrapolated_svd_gauge": (total - per_site["split"] + svd_gauge_s / count) * weight,
+        "splits": {k: env.split_counts[k] - counts0[k] for k in counts0},
         "note": "extrapolated = per-site total x sum_sites F_mv(site)/F_mv(mid); eigensolver tol %.0e" % tol,
     }
 

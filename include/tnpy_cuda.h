@@ -223,6 +223,24 @@ int tnpy_absorb_left(const double* U, const double* s, int n, int k, const doubl
 /* nb = cols_nb (right) or rows_nb (left) */
 size_t tnpy_absorb_workspace_bytes(int k, int n, int nb);
 
+/* ---- a8/a9 without the SVD: orthogonal split ("QR-then-small-SVD", the small SVD deferred) -----
+ * linalg.svd is only ever called with cutoff = current bond (matrix_product_state.py:206, :218), i.e. as an
+ * orthogonalisation: any A = Q T with orthonormal Q leaves the state, the environments and every later local
+ * problem unchanged (a bond gauge), and the singular values of the bond are those of the small square T.
+ *   rows >= cols:  A = Q T,  Q: rows x cols with orthonormal columns, T: cols x cols   (the U, diag(s) Vt slots)
+ *   rows <  cols:  A = T Q,  T: rows x rows, Q: rows x cols with orthonormal rows      (the U diag(s), Vt slots)
+ * Cholesky-QR applied twice to the norm-scaled vectors, all big products on the FP64 tensor pipe (csrc/qr.cu).
+ * A is not modified.  *defect_dev (device double) receives max|Q^T Q - I| as measured on the device, +inf if a
+ * Cholesky pivot broke down or a vector is exactly zero: the caller must check it (<= ~1e-13) and fall back to
+ * tnpy_svd otherwise.  flags = TNPY_QR_SHIFTED runs the shifted three-pass variant (first factorisation on
+ * G + sigma I, sigma = 100 u n): for vectors too ill-conditioned for two passes (cond of the normalised vectors
+ * between ~1e7 and ~1e12, cold sweeps), at 1.5x the cost.  Never synchronises the stream.
+ * Workspace: tnpy_qr_split_workspace_bytes(). */
+#define TNPY_QR_SHIFTED 1
+size_t tnpy_qr_split_workspace_bytes(int rows, int cols);
+int tnpy_qr_split(const double* A, int rows, int cols, double* Q, double* T, double* defect_dev, int flags,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- layout helper: out[r, p, l] = in[l, p, r]  (mirror of a site tensor, used by the right
  * environment update so that the contracted bond is the slowest index) */
 int tnpy_mirror_lpr(const double* in, double* out, int l, int d, int r, void* stream);

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--tol", type=float, default=1e-8)
     ap.add_argument("--oracle", action="store_true")
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--split", default="qr", choices=["qr", "svd"], help="bond split inside the sweeps")
     args = ap.parse_args()
 
     import logging
@@ -59,10 +60,10 @@ def main():
     out = {"config": args.config, "n": n, "chi": chi, "tol": args.tol}
 
     if init is None:
-        gpu = FiniteDMRG(mdl.mpo, bond_dim=chi, mps=device_init, compute_variance=False)
+        gpu = FiniteDMRG(mdl.mpo, bond_dim=chi, mps=device_init, compute_variance=False, split=args.split)
         del device_init
     else:
-        gpu = FiniteDMRG(mdl.mpo, bond_dim=chi, mps=MatrixProductState([a.copy() for a in init]))
+        gpu = FiniteDMRG(mdl.mpo, bond_dim=chi, mps=MatrixProductState([a.copy() for a in init]), split=args.split)
     gpu.phase_seconds = {}
     torch.cuda.synchronize()
     l0 = _cuda.launch_count()
@@ -88,6 +89,8 @@ def main():
     out["gpu_wall_s"] = time.perf_counter() - t0
     out["gpu_energies"] = e_gpu
     out["gpu_launches"] = _cuda.launch_count() - l0
+    out["split"] = args.split
+    out["split_counts"] = dict(gpu.environment.split_counts)
 
     if args.oracle:
         ref = oracle.FiniteDMRG(mdl.mpo.arrays, chi, mps=[a.copy() for a in init])

@@ -536,3 +536,99 @@ def test_ozaki_const_scope_reuses_and_drops_slices(cu):
     finally:
         cu.set_gemm_algo(cu.GEMM_AUTO)
 
+
+
+# ---- a8/a9 as an orthogonal split: tnpy_qr_split (Cholesky-QR twice, verified on the device) ---------------
+@pytest.mark.parametrize("rows,cols", [(8, 4), (4, 8), (64, 64), (128, 64), (64, 128), (200, 100), (130, 300),
+                                       (520, 260), (1000, 700), (2048, 1024), (1024, 2048), (4096, 2048)])
+def test_qr_split(cu, rows, cols):
+    """A = Q T (tall) / T Q (wide): Q orthonormal to rounding, exact reconstruction, the singular values of the
+    small factor T are those of A (graded columns / rows over 10 decades, as a DMRG site tensor has)."""
+    g = torch.Generator(device="cuda").manual_seed(3 * rows + cols)
+    a = torch.randn((rows, cols), generator=g, dtype=torch.float64, device="cuda")
+    k = min(rows, cols)
+    grade = torch.logspace(0, -10, k, dtype=torch.float64, device="cuda")
+    a = a * grade[None, :] if rows >= cols else a * grade[:, None]
+    keep = a.clone()
+    q, t, defect = cu.qr_split(a)
+    assert torch.equal(a, keep)  # input untouched
+    eye = torch.eye(k, dtype=torch.float64, device="cuda")
+    gram = q.t() @ q if rows >= cols else q @ q.t()
+    measured = float((gram - eye).abs().max())
+    assert measured < 1e-13
+    assert defect < 1e-13 and abs(defect - measured) < 5e-15  # the device-side check measures the same thing
+    back = q @ t if rows >= cols else t @ q
+    assert float((back - a).abs().max()) < 1e-13 * float(a.abs().max())
+    s_ref = torch.linalg.svdvals(a)
+    s_t = torch.linalg.svdvals(t)
+    assert float((s_t - s_ref).abs().max()) < 1e-12 * float(s_ref[0])
+
+
+def test_qr_split_reports_breakdown(cu):
+    """A zero vector cannot be normalised: the defect comes back as inf, which is what sends split_tensor to
+    the SVD (LAPACK-style null-space completion lives there).  Exactly dependent columns either break down or
+    give a valid split (orthonormal Q, exact reconstruction) -- never a silently wrong one."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    b = torch.randn((128, 256), generator=g, dtype=torch.float64, device="cuda")
+    b[17, :] = 0.0
+    assert cu.qr_split(b)[2] == float("inf")
+    assert cu.qr_split(b, shifted=True)[2] == float("inf")
+    a = torch.randn((256, 128), generator=g, dtype=torch.float64, device="cuda")
+    a[:, 70] = a[:, 3]
+    q, t, defect = cu.qr_split(a)
+    if defect <= 1e-13:
+        assert float((q.t() @ q - torch.eye(128, dtype=torch.float64, device="cuda")).abs().max()) < 1e-13
+        assert float((q @ t - a).abs().max()) < 1e-12
+
+
+@pytest.mark.parametrize("rows,cols,cond", [(512, 256, 1e10), (2048, 1024, 1e12), (1024, 2048, 1e11)])
+def test_qr_split_shifted_handles_ill_conditioned(cu, rows, cols, cond):
+    """Vectors whose *normalised* Gram matrix has condition cond^2 (a cold-sweep site tensor: no grading to
+    scale away): two Cholesky-QR passes are not enough -- and say so through the defect -- the shifted
+    three-pass variant is."""
+    k = min(rows, cols)
+    g = torch.Generator(device="cuda").manual_seed(rows + 7)
+    u, _ = torch.linalg.qr(torch.randn((max(rows, cols), k), generator=g, dtype=torch.float64, device="cuda"))
+    v, _ = torch.linalg.qr(torch.randn((k, k), generator=g, dtype=torch.float64, device="cuda"))
+    s = torch.logspace(0, -float(np.log10(cond)), k, dtype=torch.float64, device="cuda")
+    a = (u * s) @ v.t()
+    a = a.contiguous() if rows >= cols else a.t().contiguous()
+    assert cu.qr_split(a)[2] > 1e-13
+    q, t, defect = cu.qr_split(a, shifted=True)
+    assert defect < 1e-13
+    eye = torch.eye(k, dtype=torch.float64, device="cuda")
+    gram = q.t() @ q if rows >= cols else q @ q.t()
+    assert float((gram - eye).abs().max()) < 1e-13
+    back = q @ t if rows >= cols else t @ q
+    assert float((back - a).abs().max()) < 1e-13
+    assert float((torch.linalg.svdvals(t) - s).abs().max()) < 1e-13
+
+
+def test_qr_split_matches_svd_split():
+    """split_tensor in "qr" mode against the reference-literal "svd" mode on the same site tensor: same
+    product A[site].A[site+1], same bond spectrum (deferred small SVD), isometric site tensor, both directions."""
+    from tnpy_b200.matrix_product_state import DeferredSpectrum, Direction, _split_on_device
+
+    g = torch.Generator(device="cuda").manual_seed(9)
+    l, d, r = 96, 2, 128
+    a = torch.randn((l, d, r), generator=g, dtype=torch.float64, device="cuda")
+    a = a * torch.logspace(0, -9, r, dtype=torch.float64, device="cuda")[None, None, :]
+    nb = torch.randn((r, d, 80), generator=g, dtype=torch.float64, device="cuda")
+    theta = torch.einsum("lpr,rqs->lpqs", a, nb)
+    for mode in ("qr", "svd"):
+        q, new_nb, s = _split_on_device(a, nb, Direction.RIGHTWARD, mode, 16)
+        assert isinstance(s, DeferredSpectrum) == (mode == "qr")
+        assert float((torch.einsum("lpr,rqs->lpqs", q, new_nb) - theta).abs().max()) < 1e-12 * float(theta.abs().max())
+        iso = q.reshape(l * d, r)
+        assert float((iso.t() @ iso - torch.eye(r, dtype=torch.float64, device="cuda")).abs().max()) < 1e-12
+        sv = s.cpu().numpy()
+        s_ref = torch.linalg.svdvals(a.reshape(l * d, r)).cpu().numpy()
+        assert np.abs(np.sort(sv)[::-1] - s_ref).max() < 1e-12 * s_ref[0]
+    a2 = a.permute(2, 1, 0).contiguous()  # (128, 2, 96): wide as (l, d r)
+    nb2 = torch.randn((40, d, 128), generator=g, dtype=torch.float64, device="cuda")
+    theta2 = torch.einsum("lpr,rqs->lpqs", nb2, a2)
+    for mode in ("qr", "svd"):
+        q, new_nb, s = _split_on_device(a2, nb2, Direction.LEFTWARD, mode, 16)
+        assert float((torch.einsum("lpr,rqs->lpqs", new_nb, q) - theta2).abs().max()) < 1e-12 * float(theta2.abs().max())
+        iso = q.reshape(128, d * 96)
+        assert float((iso @ iso.t() - torch.eye(128, dtype=torch.float64, device="cuda")).abs().max()) < 1e-12

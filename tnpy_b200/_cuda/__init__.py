@@ -71,6 +71,8 @@ SIGNATURES = {
     "tnpy_last_svd_sweeps": (c_int, []),
     "tnpy_last_svd_trace": (c_int, [ctypes.POINTER(ctypes.c_uint), c_int]),
     "tnpy_svd": (c_int, [_PD, c_int, c_int, _PD, _PD, _PD, c_void_p, c_size_t, c_void_p]),
+    "tnpy_qr_split_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "tnpy_qr_split": (c_int, [_PD, c_int, c_int, _PD, _PD, _PD, c_int, c_void_p, c_size_t, c_void_p]),
     "tnpy_absorb_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "tnpy_absorb_right": (c_int, [_PD, _PD, c_int, c_int, _PD, c_int, _PD, c_void_p, c_size_t, c_void_p]),
     "tnpy_absorb_left": (c_int, [_PD, _PD, c_int, c_int, _PD, c_int, _PD, c_void_p, c_size_t, c_void_p]),
@@ -403,6 +405,28 @@ def svd(A):
     rc = lib.tnpy_svd(_ptr(A), rows, cols, _ptr(U), _ptr(s), _ptr(Vt), _ptr(ws), nbytes, _stream())
     check(rc, "tnpy_svd")
     return U, s, Vt
+
+
+def qr_split(A, shifted: bool = False):
+    """Orthogonal split of a 2-D tensor (not modified): ``A = Q @ T`` (rows >= cols, Q with orthonormal
+    columns) or ``A = T @ Q`` (rows < cols, Q with orthonormal rows).  Returns (Q, T, defect) with
+    defect = max|Q^T Q - I| measured on the device (inf when the Cholesky factorisation broke down); the
+    caller decides whether to accept the split.  ``shifted``: the three-pass variant for ill-conditioned
+    vectors (TNPY_QR_SHIFTED)."""
+    import torch
+
+    _need_cuda(A)
+    rows, cols = A.shape
+    k = min(rows, cols)
+    Q = torch.empty((rows, cols), dtype=torch.float64, device=A.device)
+    T = torch.empty((k, k), dtype=torch.float64, device=A.device)
+    defect = torch.empty(1, dtype=torch.float64, device=A.device)
+    lib = load()
+    nbytes = lib.tnpy_qr_split_workspace_bytes(rows, cols)
+    ws = _scratch.get(nbytes)
+    rc = lib.tnpy_qr_split(_ptr(A), rows, cols, _ptr(Q), _ptr(T), _ptr(defect), 1 if shifted else 0, _ptr(ws), nbytes, _stream())
+    check(rc, "tnpy_qr_split")
+    return Q, T, float(defect.item())
 
 
 def absorb_right(s, Vt, nb):

@@ -48,6 +48,7 @@ class FiniteDMRG:
         compute_variance: bool = True,
         seed: Optional[int] = None,
         canonicalize: bool = False,
+        split: str = "qr",
     ):
         if bond_dim is None:
             bond_dim = chi
@@ -63,7 +64,11 @@ class FiniteDMRG:
             mps = MatrixProductState.random(n=self.n_sites, bond_dim=self.bond_dim, phys_dim=self.phys_dim, seed=seed)
         # canonicalize=True right-canonicalises a user-supplied MPS on the device first; the reference
         # (and the default here) trusts the caller, as MatrixProductState.random is right-canonical
-        self._env = Environment(mpo=mpo, mps=mps, canonicalize=canonicalize)
+        # split="qr" (default): bonds >= 64 are orthogonalised by the verified Cholesky-QR split and the bond's
+        # small SVD is deferred until `bond_singular_values` is read; split="svd": one Jacobi SVD per split,
+        # the reference's literal gauge (matrix_product_state.py:187-225).  Energies, the state and the bond
+        # spectra are the same either way (the two differ by an orthogonal gauge on each bond).
+        self._env = Environment(mpo=mpo, mps=mps, canonicalize=canonicalize, split=split)
         self._energies: List[float] = [np.nan]
         self._variances: List[float] = [np.nan]
         self.solver_stats: List[Dict] = []  # one record per local solve of the last sweep
@@ -85,7 +90,8 @@ class FiniteDMRG:
 
     @property
     def bond_singular_values(self) -> Dict[int, np.ndarray]:
-        """Singular values of the most recent split on every bond (host copies)."""
+        """Singular values of the most recent split on every bond (host copies).  Bonds split by the
+        Cholesky-QR path run their deferred small SVD here, once."""
         return {b: s.cpu().numpy() for b, s in self._env.bond_singular_values.items()}
 
     def variance(self) -> float:
@@ -145,7 +151,7 @@ class FiniteDMRG:
             self.perturb_wave_function(site)
             tick("perturb")
             self._env.split_tensor(site, direction=direction)
-            tick("svd_split")
+            tick("split")
             self._env.update(site, direction=direction)
             tick("env_update")
         return energy
@@ -225,9 +231,10 @@ class ShiftInvertDMRG(FiniteDMRG):
     one on-device generalised Davidson serves both; for N <= 40 its basis spans the whole space)."""
 
     def __init__(self, mpo, bond_dim: Optional[int] = None, offset: float = 0, block_size: int = 1, mps=None,
-                 exact_solver_dim: int = 200, *, chi: Optional[int] = None, seed: Optional[int] = None):
+                 exact_solver_dim: int = 200, *, chi: Optional[int] = None, seed: Optional[int] = None,
+                 split: str = "qr"):
         super().__init__(mpo, bond_dim=bond_dim, block_size=block_size, mps=mps, exact_solver_dim=exact_solver_dim,
-                         chi=chi, seed=seed)
+                         chi=chi, seed=seed, split=split)
         self._env2 = Environment(mpo=mpo.square(), mps=self.mps, share_state_with=self._env)
         self._offset = offset
         self._restored_mps = None

@@ -227,20 +227,79 @@ class MatrixProductState:
         return NotImplemented
 
 
-def _split_on_device(a, nb, direction: Direction):
-    """Device tensors in, device tensors out: (new site tensor, new neighbour, singular values)."""
+#: the verified orthogonality max|Q^T Q - I| a Cholesky-QR split must reach to be accepted (else: Jacobi SVD)
+QR_DEFECT_TOL = 1e-13
+
+
+class DeferredSpectrum:
+    """Bond spectrum of a QR split: the square factor T (device) whose singular values are the bond's;
+    the small SVD runs the first time the values are asked for."""
+
+    def __init__(self, t, shifted: bool = False):
+        self._t, self._s = t, None
+        self.shifted = shifted  # the split needed the shifted three-pass factorisation
+
+    def values(self):
+        if self._s is None:
+            self._s = _cuda.svd(self._t.clone())[1]
+            self._t = None
+        return self._s
+
+    def cpu(self):
+        return self.values().cpu()
+
+
+def _ones(k: int, like):
+    import torch
+
+    return torch.ones(k, dtype=torch.float64, device=like.device)
+
+
+def _verified_qr(mat):
+    """Cholesky-QR split accepted only on the orthogonality the device measured: two passes first, the
+    shifted three-pass variant when those were not enough (ill-conditioned cold-sweep tensors); (None, None,
+    False) sends the caller to the Jacobi SVD."""
+    q, t, defect = _cuda.qr_split(mat)
+    if defect <= QR_DEFECT_TOL:
+        return q, t, False
+    q, t, defect3 = _cuda.qr_split(mat, shifted=True)
+    if defect3 <= QR_DEFECT_TOL:
+        return q, t, True
+    logger.info(f"split_tensor: Cholesky-QR defects {defect:.1e} / {defect3:.1e} (shifted) on a "
+                f"{mat.shape[0]}x{mat.shape[1]} split, using the SVD")
+    return None, None, False
+
+
+def _split_on_device(a, nb, direction: Direction, mode: str = "svd", qr_min_bond: int = 64):
+    """Device tensors in, device tensors out: (new site tensor, new neighbour, bond spectrum).
+
+    ``mode="svd"``: the reference's split (linalg.py:9-23 with cutoff = current bond), spectrum = s.
+    ``mode="qr"``: the same orthogonalisation as A = Q T / T Q by ``tnpy_qr_split`` for bonds >=
+    ``qr_min_bond`` -- the state and every later local problem are unchanged (a bond gauge); the
+    spectrum is a :class:`DeferredSpectrum` over T.  The split is accepted only when the orthogonality
+    measured on the device is at rounding level, otherwise this call falls back to the SVD."""
     l, d, r = a.shape
     if direction == Direction.RIGHTWARD:
         if l * d < r:
             raise ValueError(f"split_tensor: site tensor {tuple(a.shape)} cannot keep a right bond of {r}")
-        u, s, vt = _cuda.svd(a.reshape(l * d, r).clone())
         r2 = nb.shape[2]
+        if mode == "qr" and r >= qr_min_bond:
+            q, t, shifted = _verified_qr(a.reshape(l * d, r))
+            if q is not None:
+                new_nb = _cuda.absorb_right(_ones(r, a), t, nb.reshape(r, d * r2)).reshape(r, d, r2)
+                return q.reshape(l, d, r), new_nb, DeferredSpectrum(t, shifted)
+        u, s, vt = _cuda.svd(a.reshape(l * d, r).clone())
         new_nb = _cuda.absorb_right(s, vt, nb.reshape(r, d * r2)).reshape(r, d, r2)
         return u.reshape(l, d, r), new_nb, s
     if d * r < l:
         raise ValueError(f"split_tensor: site tensor {tuple(a.shape)} cannot keep a left bond of {l}")
-    u, s, vt = _cuda.svd(a.reshape(l, d * r).clone())
     l0 = nb.shape[0]
+    if mode == "qr" and l >= qr_min_bond:
+        q, t, shifted = _verified_qr(a.reshape(l, d * r))
+        if q is not None:
+            new_nb = _cuda.absorb_left(t, _ones(l, a), nb.reshape(l0 * d, l)).reshape(l0, d, l)
+            return q.reshape(l, d, r), new_nb, DeferredSpectrum(t, shifted)
+    u, s, vt = _cuda.svd(a.reshape(l, d * r).clone())
     new_nb = _cuda.absorb_left(u, s, nb.reshape(l0 * d, l)).reshape(l0, d, l)
     return vt.reshape(l, d, r), new_nb, s
 
@@ -342,7 +401,8 @@ class Environment:
     IDENTITY_TOL = 1e-12
 
     def __init__(self, mpo: MatrixProductOperator, mps, build_left: bool = True, use_identity_channels: bool = True,
-                 share_state_with: Optional["Environment"] = None, canonicalize: bool = False):
+                 share_state_with: Optional["Environment"] = None, canonicalize: bool = False,
+                 split: str = "qr", qr_min_bond: int = 64):
         """``mps`` is a :class:`MatrixProductState` (host, as in the reference) or a list of
         three-leg (l, d, r) float64 CUDA tensors (device-born synthetic states for benchmarks).
         ``share_state_with``: a second environment over the *same* MPS (ShiftInvertDMRG's H^2
@@ -352,6 +412,13 @@ class Environment:
         if not torch.cuda.is_available():
             raise RuntimeError("tnpy_b200.Environment needs a CUDA device; there is no CPU fallback.")
         _cuda.load()
+        if split not in ("qr", "svd"):
+            raise ValueError(f"split must be 'qr' or 'svd', got {split!r}")
+        #: how split_tensor orthogonalises: "qr" (Cholesky-QR for bonds >= qr_min_bond, small SVD deferred
+        #: until the bond spectrum is read, SVD fallback when the verified orthogonality is not at rounding
+        #: level) or "svd" (the reference's literal gauge, one Jacobi SVD per split)
+        self.split_mode, self.qr_min_bond = split, qr_min_bond
+        self.split_counts = {"qr": 0, "qr_shifted": 0, "svd": 0}
         self._mpo = mpo
         self._n_sites = mpo.nsites
         if len(mps) != self._n_sites:
@@ -496,7 +563,9 @@ class Environment:
         if direction not in (Direction.RIGHTWARD, Direction.LEFTWARD):
             raise KeyError("MatrixProductState only supplies left or right direction.")
         nb_site = site + 1 if direction == Direction.RIGHTWARD else site - 1
-        a, nb, s = _split_on_device(self._A[site], self._A[nb_site], direction)
+        a, nb, s = _split_on_device(self._A[site], self._A[nb_site], direction, self.split_mode, self.qr_min_bond)
+        kind = "svd" if not isinstance(s, DeferredSpectrum) else ("qr_shifted" if s.shifted else "qr")
+        self.split_counts[kind] += 1
         self._A[site], self._A[nb_site] = a.contiguous(), nb.contiguous()
         self._dirty.update((site, nb_site))
         self.bond_singular_values[min(site, nb_site)] = s
