@@ -601,7 +601,7 @@ def test_qr_split_shifted_handles_ill_conditioned(cu, rows, cols, cond):
     assert float((gram - eye).abs().max()) < 1e-13
     back = q @ t if rows >= cols else t @ q
     assert float((back - a).abs().max()) < 1e-13
-    assert float((torch.linalg.svdvals(t) - s).abs().max()) < 1e-13
+    assert float((torch.linalg.svdvals(t) - s).abs().max()) < 1e-12  # absolute, s_max = 1 (north_star asks 1e-9)
 
 
 def test_qr_split_matches_svd_split():
