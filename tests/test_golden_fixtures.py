@@ -1,0 +1,89 @@
+"""Committed golden fixtures (tests/golden/*.npz, made by tests/golden/make_golden.py from the CPU oracle).
+
+CPU: the oracle still reproduces them (freezes the restatement).  GPU: the CUDA path reproduces them through
+the C ABI without recomputing the oracle -- H_eff matvec / environment updates to 1e-13 of the result's
+scale, fDMRG energies per sweep to 1e-10 relative, bond spectra to 1e-9, energy vs dense ED to 1e-8."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import tnpy_oracle as oracle
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+DMRG_FILES = ["dmrg_xxz_n10_chi16.npz", "dmrg_thirring_n10_chi12.npz", "dmrg_rh_n10_chi16.npz"]
+
+
+def load(name):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+def case_keys(z):
+    return sorted({k.rsplit("_", 1)[0] for k in z.files})
+
+
+def test_oracle_reproduces_heff_and_env_fixtures():
+    heff, env = load("heff_cases.npz"), load("env_cases.npz")
+    keys = case_keys(heff)
+    assert len(keys) == 15
+    for key in keys:
+        L, W, R, x = (heff[f"{key}_{s}"] for s in "LWRx")
+        np.testing.assert_allclose(oracle.heff_apply(L, W, R, x), heff[f"{key}_y"], rtol=0, atol=1e-12 * np.abs(heff[f"{key}_y"]).max())
+        np.testing.assert_allclose(oracle.env_update_left(L, x, W), env[f"{key}_left"], rtol=0, atol=1e-12 * np.abs(env[f"{key}_left"]).max())
+        np.testing.assert_allclose(oracle.env_update_right(R, x, W), env[f"{key}_right"], rtol=0, atol=1e-12 * np.abs(env[f"{key}_right"]).max())
+
+
+@pytest.mark.parametrize("name", DMRG_FILES)
+def test_dmrg_fixture_is_self_consistent(name):
+    """Cheap CPU checks of a DMRG fixture: stored MPO gives the stored ED energy, the energies decrease to it."""
+    z = load(name)
+    n = int(z["n"])
+    mpo = [z[f"mpo_{i}"] for i in range(n)]
+    assert abs(oracle.exact_ground_energy(mpo) - float(z["ed_energy"])) < 1e-10
+    e = z["energies"]
+    assert e[-1] >= float(z["ed_energy"]) - 1e-10 and abs(e[-1] - e[-2]) < 1e-9
+    for bond in range(n - 1):
+        s = z[f"spectrum_{bond}"]
+        assert np.all(s[:-1] >= s[1:] - 1e-15)
+
+
+@pytest.mark.gpu
+def test_gpu_heff_and_env_match_fixtures():
+    torch = pytest.importorskip("torch")
+    from tnpy_b200 import _cuda
+
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()  # noqa: E731
+    heff, env = load("heff_cases.npz"), load("env_cases.npz")
+    for key in case_keys(heff):
+        L, W, R, x = (heff[f"{key}_{s}"] for s in "LWRx")
+        y = _cuda.heff_apply(dev(L), dev(W), dev(R), dev(x)).cpu().numpy()
+        assert np.abs(y - heff[f"{key}_y"]).max() <= 1e-13 * np.abs(heff[f"{key}_y"]).max(), key
+        lo = _cuda.env_update_left(dev(L), dev(x), dev(W)).cpu().numpy()
+        assert np.abs(lo - env[f"{key}_left"]).max() <= 1e-13 * np.abs(env[f"{key}_left"]).max(), key
+        ro = _cuda.env_update_right(dev(R), dev(x), dev(W)).cpu().numpy()
+        assert np.abs(ro - env[f"{key}_right"]).max() <= 1e-13 * np.abs(env[f"{key}_right"]).max(), key
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("split", ["qr", "svd"])
+@pytest.mark.parametrize("name", DMRG_FILES)
+def test_gpu_dmrg_matches_fixture(name, split):
+    pytest.importorskip("torch")
+    from tnpy_b200.finite_dmrg import FiniteDMRG
+    from tnpy_b200.matrix_product_state import MatrixProductState
+    from tnpy_b200.operators import MatrixProductOperator
+
+    z = load(name)
+    n, chi = int(z["n"]), int(z["chi"])
+    mpo = MatrixProductOperator([z[f"mpo_{i}"] for i in range(n)])
+    init = MatrixProductState([z[f"init_{i}"].copy() for i in range(n)])
+    f = FiniteDMRG(mpo, bond_dim=chi, mps=init, split=split)
+    f.environment.qr_min_bond = 4  # exercise the Cholesky-QR split on these small bonds too
+    energies = f.run(tol=1e-13, max_sweep=6)
+    assert len(energies) == len(z["energies"])
+    for a, b in zip(energies, z["energies"]):
+        assert abs(a - b) <= 1e-10 * abs(b), (energies, z["energies"])
+    assert abs(energies[-1] - float(z["ed_energy"])) < 1e-8
+    sv = f.bond_singular_values
+    for bond in range(n - 1):
+        assert np.abs(sv[bond] - z[f"spectrum_{bond}"]).max() < 1e-9, bond
