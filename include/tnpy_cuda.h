@@ -227,8 +227,9 @@ size_t tnpy_absorb_workspace_bytes(int k, int n, int nb);
  * linalg.svd is only ever called with cutoff = current bond (matrix_product_state.py:206, :218), i.e. as an
  * orthogonalisation: any A = Q T with orthonormal Q leaves the state, the environments and every later local
  * problem unchanged (a bond gauge), and the singular values of the bond are those of the small square T.
- *   rows >= cols:  A = Q T,  Q: rows x cols with orthonormal columns, T: cols x cols   (the U, diag(s) Vt slots)
- *   rows <  cols:  A = T Q,  T: rows x rows, Q: rows x cols with orthonormal rows      (the U diag(s), Vt slots)
+ *   rows > cols:  A = Q T,  Q: rows x cols with orthonormal columns, T: cols x cols   (the U, diag(s) Vt slots)
+ *   rows < cols:  A = T Q,  T: rows x rows, Q: rows x cols with orthonormal rows      (the U diag(s), Vt slots)
+ *   rows == cols: A = Q T, or A = T Q when flags has TNPY_QR_T_FIRST (a leftward split of a square site tensor)
  * Cholesky-QR applied twice to the norm-scaled vectors, all big products on the FP64 tensor pipe (csrc/qr.cu).
  * A is not modified.  *defect_dev (device double) receives max|Q^T Q - I| as measured on the device, +inf if a
  * Cholesky pivot broke down or a vector is exactly zero: the caller must check it (<= ~1e-13) and fall back to
@@ -237,6 +238,7 @@ size_t tnpy_absorb_workspace_bytes(int k, int n, int nb);
  * between ~1e7 and ~1e12, cold sweeps), at 1.5x the cost.  Never synchronises the stream.
  * Workspace: tnpy_qr_split_workspace_bytes(). */
 #define TNPY_QR_SHIFTED 1
+#define TNPY_QR_T_FIRST 2 /* square input only: factorise as T Q instead of Q T */
 size_t tnpy_qr_split_workspace_bytes(int rows, int cols);
 int tnpy_qr_split(const double* A, int rows, int cols, double* Q, double* T, double* defect_dev, int flags,
                   void* workspace, size_t workspace_bytes, void* stream);

@@ -196,3 +196,24 @@ def test_qr_split_sweeps_match_svd_split_and_oracle(name, n, chi):
     sv_qr = qr.bond_singular_values
     for bond, s_ref in ref.bond_singular_values.items():
         assert np.abs(sv_qr[bond] - s_ref).max() < 1e-9, bond
+
+
+@pytest.mark.parametrize("split", ["qr", "svd"])
+def test_environment_split_preserves_state_at_every_site(split):
+    """Environment.split_tensor leaves the state untouched at every site and in both directions -- ramp sites
+    included, where the site tensor is a *square* matrix (l == d r or l d == r) and the order of the two
+    factors of the Cholesky-QR split is a choice the caller has to make."""
+    from tnpy_b200.matrix_product_state import Direction, Environment, MatrixProductState
+    from tnpy_b200.model import XXZ
+
+    n, chi = 10, 16  # bonds 2 4 8 16 16 16 8 4 2
+    mps = MatrixProductState.random(n=n, bond_dim=chi, phys_dim=2, seed=4)
+    dense = mps.to_dense()
+    env = Environment(XXZ(n=n, delta=0.5).mpo, mps, split=split, qr_min_bond=2)
+    for direction, sites in ((Direction.RIGHTWARD, range(0, n - 1)), (Direction.LEFTWARD, range(n - 1, 0, -1))):
+        for site in sites:
+            env.split_tensor(site, direction)
+            now = env.mps.to_dense()
+            assert np.abs(now - dense).max() < 1e-12 * np.abs(dense).max(), (split, direction, site)
+    if split == "qr":
+        assert env.split_counts["qr"] + env.split_counts["qr_shifted"] >= 2 * (n - 1) - 4

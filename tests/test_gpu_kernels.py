@@ -564,6 +564,22 @@ def test_qr_split(cu, rows, cols):
     assert float((s_t - s_ref).abs().max()) < 1e-12 * float(s_ref[0])
 
 
+@pytest.mark.parametrize("n", [64, 100, 512])
+@pytest.mark.parametrize("t_first", [False, True])
+def test_qr_split_square_factor_order(cu, n, t_first):
+    """A square matrix is split as Q T or, with TNPY_QR_T_FIRST, as T Q -- the order a leftward split of a
+    square site tensor (l == d r, the ramp of the chain) needs; the two are different factorisations."""
+    g = torch.Generator(device="cuda").manual_seed(n)
+    a = torch.randn((n, n), generator=g, dtype=torch.float64, device="cuda")
+    grade = torch.logspace(0, -8, n, dtype=torch.float64, device="cuda")
+    a = (a * grade[:, None] if t_first else a * grade[None, :]).contiguous()  # graded along the vectors being orthonormalised
+    q, t, defect = cu.qr_split(a, t_first=t_first)
+    assert defect < 1e-13
+    good, bad = (t @ q, q @ t) if t_first else (q @ t, t @ q)
+    assert float((good - a).abs().max()) < 1e-13
+    assert float((bad - a).abs().max()) > 1e-3
+
+
 def test_qr_split_reports_breakdown(cu):
     """A zero vector cannot be normalised: the defect comes back as inf, which is what sends split_tensor to
     the SVD (LAPACK-style null-space completion lives there).  Exactly dependent columns either break down or
@@ -624,6 +640,19 @@ def test_qr_split_matches_svd_split():
         sv = s.cpu().numpy()
         s_ref = torch.linalg.svdvals(a.reshape(l * d, r)).cpu().numpy()
         assert np.abs(np.sort(sv)[::-1] - s_ref).max() < 1e-12 * s_ref[0]
+    # square site tensors (l == d r leftward, l d == r rightward): the ramp sites of a chain
+    sq = torch.randn((128, 2, 64), generator=g, dtype=torch.float64, device="cuda")
+    nb_l = torch.randn((70, d, 128), generator=g, dtype=torch.float64, device="cuda")
+    th = torch.einsum("lpr,rqs->lpqs", nb_l, sq)
+    q, new_nb, s = _split_on_device(sq, nb_l, Direction.LEFTWARD, "qr", 16)
+    assert isinstance(s, DeferredSpectrum)
+    assert float((torch.einsum("lpr,rqs->lpqs", new_nb, q) - th).abs().max()) < 1e-12 * float(th.abs().max())
+    sq = torch.randn((32, 2, 64), generator=g, dtype=torch.float64, device="cuda")
+    nb_r = torch.randn((64, d, 50), generator=g, dtype=torch.float64, device="cuda")
+    th = torch.einsum("lpr,rqs->lpqs", sq, nb_r)
+    q, new_nb, s = _split_on_device(sq, nb_r, Direction.RIGHTWARD, "qr", 16)
+    assert isinstance(s, DeferredSpectrum)
+    assert float((torch.einsum("lpr,rqs->lpqs", q, new_nb) - th).abs().max()) < 1e-12 * float(th.abs().max())
     a2 = a.permute(2, 1, 0).contiguous()  # (128, 2, 96): wide as (l, d r)
     nb2 = torch.randn((40, d, 128), generator=g, dtype=torch.float64, device="cuda")
     theta2 = torch.einsum("lpr,rqs->lpqs", nb2, a2)

@@ -407,12 +407,13 @@ def svd(A):
     return U, s, Vt
 
 
-def qr_split(A, shifted: bool = False):
+def qr_split(A, shifted: bool = False, t_first: bool = False):
     """Orthogonal split of a 2-D tensor (not modified): ``A = Q @ T`` (rows >= cols, Q with orthonormal
     columns) or ``A = T @ Q`` (rows < cols, Q with orthonormal rows).  Returns (Q, T, defect) with
     defect = max|Q^T Q - I| measured on the device (inf when the Cholesky factorisation broke down); the
     caller decides whether to accept the split.  ``shifted``: the three-pass variant for ill-conditioned
-    vectors (TNPY_QR_SHIFTED)."""
+    vectors (TNPY_QR_SHIFTED).  ``t_first``: a *square* A is factorised as ``T @ Q`` instead of ``Q @ T``
+    (TNPY_QR_T_FIRST; the leftward split of a square site tensor) -- ignored otherwise."""
     import torch
 
     _need_cuda(A)
@@ -424,7 +425,7 @@ def qr_split(A, shifted: bool = False):
     lib = load()
     nbytes = lib.tnpy_qr_split_workspace_bytes(rows, cols)
     ws = _scratch.get(nbytes)
-    rc = lib.tnpy_qr_split(_ptr(A), rows, cols, _ptr(Q), _ptr(T), _ptr(defect), 1 if shifted else 0, _ptr(ws), nbytes, _stream())
+    rc = lib.tnpy_qr_split(_ptr(A), rows, cols, _ptr(Q), _ptr(T), _ptr(defect), (1 if shifted else 0) | (2 if t_first else 0), _ptr(ws), nbytes, _stream())
     check(rc, "tnpy_qr_split")
     return Q, T, float(defect.item())
 

@@ -321,7 +321,8 @@ extern "C" int tnpy_qr_split(const double* A, int rows, int cols, double* Q, dou
   TNPY_CHECK_ARG(A && Q && T && defect_dev, "null pointer");
   TNPY_CHECK_ARG(rows > 0 && cols > 0, "non-positive dimension");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const bool tall = rows >= cols;
+  // a square matrix can be split either way: Q first (columns orthonormalised) unless the caller asks for T Q
+  const bool tall = rows > cols || (rows == cols && !(flags & TNPY_QR_T_FIRST));
   const int n = tall ? cols : rows, m = tall ? rows : cols;
   const int np = padded_dim(n);
   Workspace ws(workspace, workspace_bytes);

@@ -255,14 +255,15 @@ def _ones(k: int, like):
     return torch.ones(k, dtype=torch.float64, device=like.device)
 
 
-def _verified_qr(mat):
+def _verified_qr(mat, t_first: bool):
     """Cholesky-QR split accepted only on the orthogonality the device measured: two passes first, the
     shifted three-pass variant when those were not enough (ill-conditioned cold-sweep tensors); (None, None,
-    False) sends the caller to the Jacobi SVD."""
-    q, t, defect = _cuda.qr_split(mat)
+    False) sends the caller to the Jacobi SVD.  ``t_first`` fixes the order of the factors for a square
+    matrix (mat = T Q for a leftward split, Q T for a rightward one)."""
+    q, t, defect = _cuda.qr_split(mat, t_first=t_first)
     if defect <= QR_DEFECT_TOL:
         return q, t, False
-    q, t, defect3 = _cuda.qr_split(mat, shifted=True)
+    q, t, defect3 = _cuda.qr_split(mat, shifted=True, t_first=t_first)
     if defect3 <= QR_DEFECT_TOL:
         return q, t, True
     logger.info(f"split_tensor: Cholesky-QR defects {defect:.1e} / {defect3:.1e} (shifted) on a "
@@ -284,7 +285,7 @@ def _split_on_device(a, nb, direction: Direction, mode: str = "svd", qr_min_bond
             raise ValueError(f"split_tensor: site tensor {tuple(a.shape)} cannot keep a right bond of {r}")
         r2 = nb.shape[2]
         if mode == "qr" and r >= qr_min_bond:
-            q, t, shifted = _verified_qr(a.reshape(l * d, r))
+            q, t, shifted = _verified_qr(a.reshape(l * d, r), t_first=False)
             if q is not None:
                 new_nb = _cuda.absorb_right(_ones(r, a), t, nb.reshape(r, d * r2)).reshape(r, d, r2)
                 return q.reshape(l, d, r), new_nb, DeferredSpectrum(t, shifted)
@@ -295,7 +296,7 @@ def _split_on_device(a, nb, direction: Direction, mode: str = "svd", qr_min_bond
         raise ValueError(f"split_tensor: site tensor {tuple(a.shape)} cannot keep a left bond of {l}")
     l0 = nb.shape[0]
     if mode == "qr" and l >= qr_min_bond:
-        q, t, shifted = _verified_qr(a.reshape(l, d * r))
+        q, t, shifted = _verified_qr(a.reshape(l, d * r), t_first=True)
         if q is not None:
             new_nb = _cuda.absorb_left(t, _ones(l, a), nb.reshape(l0 * d, l)).reshape(l0, d, l)
             return q.reshape(l, d, r), new_nb, DeferredSpectrum(t, shifted)
