@@ -288,7 +288,11 @@ extern "C" int tnpy_eig_lowest(const double* L, const double* W, const double* R
 
   int j = 0, n_matvec = 0, n_restart = 0;
   bool done = false;
-  const double eta = fmax(1e-3, 2.220446049250313e-16 / (1e-3 * tol));
+  // Daniel-Gragg-Kaufman-Stewart: the second pass is skipped only when ||w'|| >= ||w|| / sqrt 2, i.e.
+  // ||w'|| >= ||h|| (||w||^2 = ||h||^2 + ||w'||^2).  A looser, tolerance-tied threshold (1e-3) was measured to
+  // derail cold-sweep solves: spurious Ritz values of order 1e3 and 1000 wasted matvecs at 5 of 34 sites of
+  // XXZ n=40 chi=512 (profiles/r01_sweep_trace_cold_chi512_*.jsonl).
+  const double eta = 1.0;
   OzConstScope const_operands(tol);
   while (true) {
     double* vj = V + (int64_t)j * ldv;
@@ -298,10 +302,8 @@ extern "C" int tnpy_eig_lowest(const double* L, const double* W, const double* R
     ++n_matvec;
     // classical Gram-Schmidt against the whole basis, applied twice; the first-pass coefficients are
     // column j of T = V^T H V, the second pass adds the rounding-level correction.
-    // The second pass is what "twice is enough" asks for when the first one cancelled heavily; it is decided on
-    // the device: with ||w'|| >= eta ||h|| the first pass leaves w' orthogonal to the basis to ~eps / eta, which
-    // is kept three orders below the requested residual tolerance (eta >= 1: always two passes, e.g. tol 1e-13),
-    // and the two extra passes over V are skipped.
+    // The second pass is what "twice is enough" asks for when the first one cancelled; it is decided on the
+    // device (||w'|| >= eta ||h|| => the two extra passes over V are skipped).
     TNPY_TRY(multi_dot(V, ldv, j + 1, w, n, h, 0, stream));
     TNPY_TRY(multi_axpy(V, ldv, j + 1, h, w, n, status + ST_BETA, stream));
     reorth_decision_kernel<<<1, 64, 0, stream>>>(h, j + 1, status + ST_BETA, eta, h2, skip2);
