@@ -219,7 +219,7 @@ def _cpu_baseline(chi, budget_s):
     while True:
         oracle.heff_apply(L, W, R, x)
         n += 1
-        if time.perf_counter() - t0 > budget_s * 0.5 or n >= 20:
+        if time.perf_counter() - t0 > budget_s * 0.6 or n >= 100:
             break
     dt = (time.perf_counter() - t0) / n
     return {

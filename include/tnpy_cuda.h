@@ -171,6 +171,13 @@ size_t tnpy_eig_workspace_bytes(int l, int r, int wl, int wr, int d, int ncv);
 int tnpy_eig_lowest(const double* L, const double* W, const double* R, double* psi,
                     int l, int r, int wl, int wr, int d, int flags, double tol, int max_matvec, int ncv,
                     double* stats_host, void* workspace, size_t workspace_bytes, void* stream);
+/* Same solve, and hpsi (N doubles) = H_eff psi for the returned psi at no extra matvec, from the Lanczos
+ * relation H V_m = V_m T + beta v_{m+1} e_m^T:  H psi = theta psi + (beta s_m) v_{m+1}  (equal to a fresh
+ * tnpy_heff_apply(psi) to rounding).  FiniteDMRG.perturb_wave_function (finite_dmrg.py:116-141), which the
+ * sweep calls right after the solve, needs exactly that vector. */
+int tnpy_eig_lowest_image(const double* L, const double* W, const double* R, double* psi, double* hpsi,
+                          int l, int r, int wl, int wr, int d, int flags, double tol, int max_matvec, int ncv,
+                          double* stats_host, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- f2: ShiftInvertDMRG.one_site_solver -> primme.eigsh(A, M=M, k=1, which="SA")  (finite_dmrg.py:341-355)
  * Lowest eigenpair of the symmetric-definite pencil  A x = lambda M x,  A = H_eff(LA, WA, RA) (MPO of

@@ -217,3 +217,33 @@ def test_environment_split_preserves_state_at_every_site(split):
             assert np.abs(now - dense).max() < 1e-12 * np.abs(dense).max(), (split, direction, site)
     if split == "qr":
         assert env.split_counts["qr"] + env.split_counts["qr_shifted"] >= 2 * (n - 1) - 4
+
+
+def test_perturbation_from_the_solver_image_equals_a_fresh_matvec():
+    """finite_dmrg.py:116-141: psi += alpha H_eff psi.  Inside a sweep the H_eff psi comes from the eigensolve
+    that produced psi (no second matvec); the result must equal the reference-literal route to rounding, and a
+    site tensor rewritten in between must not pick up a stale image."""
+    import torch
+
+    from tnpy_b200.finite_dmrg import FiniteDMRG
+    from tnpy_b200.matrix_product_state import MatrixProductState
+    from tnpy_b200.model import XXZ
+
+    n, chi, site = 12, 32, 6
+    f = FiniteDMRG(XXZ(n=n, delta=0.5).mpo, bond_dim=chi, mps=MatrixProductState.random(n, chi, 2, seed=2))
+    env = f.environment
+    f._solve_on_device(site, 1e-9)
+    psi = env.device_tensor(site).clone()
+    expected = psi + 1e-5 * env.one_site_matvec(site).apply_device(psi)
+    assert env._image is not None and env._image[0] == site
+    f.perturb_wave_function(site)
+    assert env._image is None  # consumed
+    assert float((env.device_tensor(site) - expected).abs().max()) <= 1e-15 * float(expected.abs().max()) + 1e-17
+    # stale image: the tensor is replaced after the solve
+    f._solve_on_device(site, 1e-9)
+    other = torch.randn_like(psi)
+    env.update_mps(site, other)
+    assert env._image is None
+    f.perturb_wave_function(site)
+    expected = other + 1e-5 * env.one_site_matvec(site).apply_device(other)
+    assert float((env.device_tensor(site) - expected).abs().max()) <= 1e-14 * float(expected.abs().max())

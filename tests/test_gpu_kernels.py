@@ -232,6 +232,24 @@ def test_eig_lowest_restarts(cu):
     assert abs(stats["theta"] - e0) <= 1e-9 * abs(e0)
 
 
+@pytest.mark.parametrize("ncv,max_matvec,tol", [(0, 1000, 1e-10), (6, 2000, 1e-10), (0, 7, 1e-10), (0, 1000, 1e-3), (0, 1, 1e-10)])
+def test_eig_lowest_image_is_heff_of_psi(cu, ncv, max_matvec, tol):
+    """tnpy_eig_lowest_image: the H_eff psi it returns from the Lanczos relation equals a fresh matvec of the
+    returned psi -- converged, restarted, cut off after a few steps, loosely converged, one-step solves."""
+    env, mpo, mps = canonical_problem(12, 32, 6, seed=3)
+    site = 6
+    L, W, R = dev(env.left[site]), dev(mpo[site]), dev(env.right[site])
+    psi = dev(np.random.default_rng(1).standard_normal(mps[site].shape))
+    image = torch.empty_like(psi)
+    stats = cu.eig_lowest(L, W, R, psi, tol=tol, ncv=ncv, max_matvec=max_matvec, image=image)
+    fresh = cu.heff_apply(L, W, R, psi)
+    scale = float(fresh.abs().max())
+    assert float((image - fresh).abs().max()) <= 1e-12 * max(scale, stats["anorm"])
+    # and the residual the solver reported is the norm of H psi - theta psi
+    r = fresh - stats["theta"] * psi
+    assert abs(float(r.norm()) - stats["resid"]) <= 1e-10 * stats["anorm"]
+
+
 @pytest.mark.parametrize("n", [4, 16, 64, 100, 199])
 def test_eigh_lowest(cu, n):
     rng = np.random.default_rng(n)

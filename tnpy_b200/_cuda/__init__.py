@@ -58,6 +58,10 @@ SIGNATURES = {
         c_int,
         [_PD, _PD, _PD, _PD] + [c_int] * 6 + [c_double, c_int, c_int, ctypes.POINTER(c_double), c_void_p, c_size_t, c_void_p],
     ),
+    "tnpy_eig_lowest_image": (
+        c_int,
+        [_PD, _PD, _PD, _PD, _PD] + [c_int] * 6 + [c_double, c_int, c_int, ctypes.POINTER(c_double), c_void_p, c_size_t, c_void_p],
+    ),
     "tnpy_geig_workspace_bytes": (c_size_t, [c_int] * 8),
     "tnpy_geig_lowest": (
         c_int,
@@ -321,17 +325,25 @@ def heff_dense(L, W, R, l, r):
     return out
 
 
-def eig_lowest(L, W, R, psi, tol: float = 1e-8, max_matvec: int = 1000, ncv: int = 0, flags: int = 0):
+def eig_lowest(L, W, R, psi, tol: float = 1e-8, max_matvec: int = 1000, ncv: int = 0, flags: int = 0, image=None):
     """In-place: psi (l, d, r) holds v0 on entry and the eigenvector on return.
-    Returns dict(theta, resid, n_matvec, n_restart, converged, anorm)."""
+    Returns dict(theta, resid, n_matvec, n_restart, converged, anorm).  ``image``: an (l, d, r) tensor that
+    receives H_eff psi for the returned psi (tnpy_eig_lowest_image: from the Lanczos relation, no extra matvec)."""
     _need_cuda(L, W, R, psi)
     l, r, wl, wr, d = _dims(psi.shape, W.shape)
     lib = load()
     nbytes = lib.tnpy_eig_workspace_bytes(l, r, wl, wr, d, ncv)
     ws = _scratch.get(nbytes)
     stats = (c_double * 8)()
-    rc = lib.tnpy_eig_lowest(_ptr(L), _ptr(W), _ptr(R), _ptr(psi), l, r, wl, wr, d, int(flags), float(tol), int(max_matvec),
-                             int(ncv), stats, _ptr(ws), nbytes, _stream())
+    if image is None:
+        rc = lib.tnpy_eig_lowest(_ptr(L), _ptr(W), _ptr(R), _ptr(psi), l, r, wl, wr, d, int(flags), float(tol),
+                                 int(max_matvec), int(ncv), stats, _ptr(ws), nbytes, _stream())
+    else:
+        _need_cuda(image)
+        if tuple(image.shape) != tuple(psi.shape) or not image.is_contiguous():
+            raise ValueError("eig_lowest: image must be a contiguous tensor of psi's shape")
+        rc = lib.tnpy_eig_lowest_image(_ptr(L), _ptr(W), _ptr(R), _ptr(psi), _ptr(image), l, r, wl, wr, d, int(flags),
+                                       float(tol), int(max_matvec), int(ncv), stats, _ptr(ws), nbytes, _stream())
     check(rc, "tnpy_eig_lowest", allow_noconv=True)
     return {
         "theta": stats[0], "resid": stats[1], "n_matvec": int(stats[2]), "n_restart": int(stats[3]),

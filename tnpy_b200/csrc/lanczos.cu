@@ -36,13 +36,14 @@ int multi_axpy(const double* V, int64_t ldv, int m, const double* h, double* w, 
                cudaStream_t stream, const int* skip = nullptr);
 int scale_copy(const double* x, double* out, int64_t n, double alpha, const double* s_dev, int inv,
                cudaStream_t stream);
+int axpy(double alpha, const double* a_dev, const double* x, double* y, int64_t n, cudaStream_t stream);
 int combine(const double* V, int64_t ldv, int m, const double* c, int64_t ldc_, int nout, double* out, int64_t ldo,
             int64_t n, cudaStream_t stream);
 
 constexpr int kMaxNcv = 48;
 
 // status record (device and pinned host mirror)
-enum { ST_THETA = 0, ST_RESID = 1, ST_ANORM = 2, ST_DONE = 3, ST_BETA = 4, ST_SIZE = 8 };
+enum { ST_THETA = 0, ST_RESID = 1, ST_ANORM = 2, ST_DONE = 3, ST_BETA = 4, ST_RCOEF = 5, ST_SIZE = 8 };
 
 // Symmetric eigen-decomposition of the m x m matrix held in shared memory `a` (leading dim kMaxNcv)
 // by parallel cyclic Jacobi (round-robin pair ordering).  Eigenvectors accumulate in `z` (columns).
@@ -166,6 +167,8 @@ __global__ void __launch_bounds__(256) ritz_kernel(double* __restrict__ T, const
     status[ST_ANORM] = anorm;
     status[ST_BETA] = beta;
     status[ST_DONE] = (resid <= tol * anorm) ? 1.0 : 0.0;
+    // signed coefficient of v_{m+1} in H x - theta x for the sign convention S is written in below
+    status[ST_RCOEF] = beta * (z[0][lo] < 0.0 ? -z[m - 1][lo] : z[m - 1][lo]);
   }
   __syncthreads();
   for (int idx = tid; idx < m * m; idx += blockDim.x) {
@@ -247,9 +250,9 @@ extern "C" size_t tnpy_eig_workspace_bytes(int l, int r, int wl, int wr, int d, 
   return eig_ws_layout(n, ncv, keep, tnpy_heff_workspace_bytes(l, r, wl, wr, d));
 }
 
-extern "C" int tnpy_eig_lowest(const double* L, const double* W, const double* R, double* psi, int l, int r, int wl,
-                               int wr, int d, int flags, double tol, int max_matvec, int ncv_in, double* stats_host,
-                               void* workspace, size_t workspace_bytes, void* stream_) {
+static int eig_lowest_impl(const double* L, const double* W, const double* R, double* psi, double* hpsi, int l, int r,
+                           int wl, int wr, int d, int flags, double tol, int max_matvec, int ncv_in,
+                           double* stats_host, void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   TNPY_CHECK_ARG(psi && W, "null pointer");
   TNPY_CHECK_ARG(l > 0 && r > 0 && wl > 0 && wr > 0 && d > 0, "non-positive dimension");
@@ -320,6 +323,12 @@ extern "C" int tnpy_eig_lowest(const double* L, const double* W, const double* R
     if (done || n_matvec >= max_matvec) {
       // psi = V[0..m-1] . S[:, 0]
       TNPY_TRY(combine(V, ldv, m, S, kMaxNcv, 1, psi, ldv, n, stream));
+      if (hpsi) {
+        // H psi from the Lanczos relation H V_m = V_m T + beta v_{m+1} e_m^T (exact to rounding here, T being the
+        // explicit projection): H psi = theta psi + (beta s_m) v_{m+1}; v_{m+1} = V[m] was normalised above
+        TNPY_TRY(scale_copy(psi, hpsi, n, hst[ST_THETA], nullptr, 0, stream));
+        if (hst[ST_BETA] > 0.0 && m < n) TNPY_TRY(axpy(hst[ST_RCOEF], nullptr, V + (int64_t)m * ldv, hpsi, n, stream));
+      }
       break;
     }
     if (m == ncv) {
@@ -352,4 +361,20 @@ extern "C" int tnpy_eig_lowest(const double* L, const double* W, const double* R
     return TNPY_ENOCONV;
   }
   return TNPY_OK;
+}
+
+extern "C" int tnpy_eig_lowest(const double* L, const double* W, const double* R, double* psi, int l, int r, int wl,
+                               int wr, int d, int flags, double tol, int max_matvec, int ncv_in, double* stats_host,
+                               void* workspace, size_t workspace_bytes, void* stream_) {
+  return eig_lowest_impl(L, W, R, psi, nullptr, l, r, wl, wr, d, flags, tol, max_matvec, ncv_in, stats_host, workspace,
+                         workspace_bytes, stream_);
+}
+
+extern "C" int tnpy_eig_lowest_image(const double* L, const double* W, const double* R, double* psi, double* hpsi,
+                                     int l, int r, int wl, int wr, int d, int flags, double tol, int max_matvec,
+                                     int ncv_in, double* stats_host, void* workspace, size_t workspace_bytes,
+                                     void* stream_) {
+  TNPY_CHECK_ARG(hpsi != nullptr, "null hpsi");
+  return eig_lowest_impl(L, W, R, psi, hpsi, l, r, wl, wr, d, flags, tol, max_matvec, ncv_in, stats_host, workspace,
+                         workspace_bytes, stream_);
 }

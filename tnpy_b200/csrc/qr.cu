@@ -117,45 +117,54 @@ int mm(const MmArgs& p, int tiles_n, int tiles_m, int batch, cudaStream_t stream
 }
 
 // ---- one 64x64 diagonal block: G_kk = L L^T in place (upper part zeroed) and Dinv = L^-1 ------------------
-// The inverse is built column by column (one thread per column) in the unused upper triangle of the tile.
+// Right-looking column Cholesky in shared memory, two barriers per column (every thread takes the pivot's
+// square root itself; the diagonal of L lives in dd[] so the tile's diagonal is never rewritten mid-step).  The
+// inverse X = L^-1 is built in the unused strict upper triangle of the tile (X[k][c] at S[c][k]), four threads
+// per column splitting each inner product.
 __global__ void __launch_bounds__(256) chol_diag_kernel(double* G, int64_t ld, double* __restrict__ Dinv,
                                                         int* __restrict__ fail) {
   __shared__ double S[NB][NB + 1];
+  __shared__ double dd[NB];
   const int tid = threadIdx.x;
   for (int idx = tid; idx < NB * NB; idx += 256) S[idx >> 6][idx & 63] = G[(int64_t)(idx >> 6) * ld + (idx & 63)];
   __syncthreads();
   for (int j = 0; j < NB; ++j) {
+    double p = S[j][j];
+    const bool bad = !(p > 0.0) || !isfinite(p);  // not positive definite to working precision: flag, stay finite
+    if (bad) p = 1.0;
+    const double d = sqrt(p);
     if (tid == 0) {
-      double p = S[j][j];
-      if (!(p > 0.0) || !isfinite(p)) {  // not positive definite to working precision: flag, keep going finite
-        *fail = 1;
-        p = 1.0;
-      }
-      S[j][j] = sqrt(p);
+      dd[j] = d;
+      if (bad) *fail = 1;
     }
+    if (tid > j && tid < NB) S[tid][j] /= d;
     __syncthreads();
-    if (tid > j && tid < NB) S[tid][j] /= S[j][j];
-    __syncthreads();
-    for (int idx = tid; idx < NB * NB; idx += 256) {
-      const int r = idx >> 6, c = idx & 63;
-      if (c > j && r >= c) S[r][c] -= S[r][j] * S[c][j];
+    const int rows = NB - 1 - j;  // rows j+1 .. 63 of the trailing block
+    for (int idx = tid; idx < rows * NB; idx += 256) {
+      const int r = j + 1 + (idx >> 6), c = idx & 63;
+      if (c > j && c <= r) S[r][c] -= S[r][j] * S[c][j];
     }
     __syncthreads();
   }
-  if (tid < NB) {
-    const int c = tid;  // column c of X = L^-1; X[k][c] (k > c) lives at S[c][k], X[c][c] = 1 / S[c][c]
-    const double xcc = 1.0 / S[c][c];
+  {
+    // column c = tid / 4 of X, lanes q = tid % 4 of a quad split the sum over k
+    const int c = tid >> 2, q = tid & 3;
+    const unsigned quad = 0xFu << (tid & 28);  // the quads of a warp run different trip counts: quad-wide sync only
+    const double xcc = 1.0 / dd[c];
     for (int r = c + 1; r < NB; ++r) {
-      double sum = S[r][c] * xcc;
-      for (int k = c + 1; k < r; ++k) sum = fma(S[r][k], S[c][k], sum);
-      S[c][r] = -sum / S[r][r];
+      double sum = q == 0 ? S[r][c] * xcc : 0.0;
+      for (int k = c + 1 + q; k < r; k += 4) sum = fma(S[r][k], S[c][k], sum);
+      sum += __shfl_xor_sync(quad, sum, 1);
+      sum += __shfl_xor_sync(quad, sum, 2);
+      if (q == 0) S[c][r] = -sum / dd[r];
+      __syncwarp(quad);
     }
   }
   __syncthreads();
   for (int idx = tid; idx < NB * NB; idx += 256) {
     const int r = idx >> 6, c = idx & 63;
-    G[(int64_t)r * ld + c] = r >= c ? S[r][c] : 0.0;
-    Dinv[idx] = r > c ? S[c][r] : (r == c ? 1.0 / S[r][r] : 0.0);
+    G[(int64_t)r * ld + c] = r > c ? S[r][c] : (r == c ? dd[r] : 0.0);
+    Dinv[idx] = r > c ? S[c][r] : (r == c ? 1.0 / dd[r] : 0.0);
   }
 }
 

@@ -109,9 +109,15 @@ class FiniteDMRG:
             self.solver_stats.append({"site": site, "dense": True, "n_matvec": 0})
             return float(energy.item())
         op = env.one_site_matvec(site)
-        energy, vec = eigshmv(op, v0=psi, tol=tol, **kwargs)
+        import torch
+
+        image = torch.empty_like(psi)
+        energy, vec = eigshmv(op, v0=psi, tol=tol, image=image, **kwargs)
         psi.copy_(vec.reshape(psi.shape))
         env._dirty.add(site)
+        # H_eff psi of the vector just written, as the Lanczos relation gives it: perturb_wave_function(site)
+        # uses it instead of a second matvec as long as nothing else touches the site tensor in between
+        env.remember_image(site, image)
         self.solver_stats.append({"site": site, "dense": False, **op.last_stats})
         return float(energy)
 
@@ -134,7 +140,9 @@ class FiniteDMRG:
         """psi <- psi + alpha * H_eff psi, in place, no renormalisation (finite_dmrg.py:116-141)."""
         env = self._env
         psi = env.device_tensor(site)
-        hpsi = env.one_site_matvec(site).apply_device(psi)
+        hpsi = env.take_image(site)
+        if hpsi is None:
+            hpsi = env.one_site_matvec(site).apply_device(psi)
         _cuda.axpy(alpha, hpsi, psi)
         env._dirty.add(site)
 

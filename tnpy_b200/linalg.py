@@ -52,7 +52,8 @@ def eigh(matrix, k: int = 1, backend: str = "numpy", **kwargs):
 
 
 def eigshmv(linear_operator, v0, k: int = 1, which: str = "SA", tol: float = 0, **kwargs) -> Tuple[float, np.ndarray]:
-    """Lowest eigenpair of an ``Environment.one_site_matvec`` operator, solved on the device."""
+    """Lowest eigenpair of an ``Environment.one_site_matvec`` operator, solved on the device.
+    ``image=<device tensor>`` (not a primme option) additionally receives H_eff psi for the returned psi."""
     from tnpy_b200.matrix_product_state import HeffOperator
 
     if not isinstance(linear_operator, HeffOperator):
@@ -60,6 +61,7 @@ def eigshmv(linear_operator, v0, k: int = 1, which: str = "SA", tol: float = 0, 
     if k != 1 or which != "SA":
         raise NotImplementedError("only k=1, which='SA' (the FiniteDMRG call) is implemented")
     opts = {}
+    image = kwargs.pop("image", None)
     for key, value in kwargs.items():
         if key in _PRIMME_KWARGS:
             opts[_PRIMME_KWARGS[key]] = int(value)
@@ -69,7 +71,7 @@ def eigshmv(linear_operator, v0, k: int = 1, which: str = "SA", tol: float = 0, 
     psi = psi.reshape(linear_operator.site_shape).clone()
     L, W, R = linear_operator.env.operands(linear_operator.site)
     flags = linear_operator.env.gauge_flags(linear_operator.site)
-    stats = _cuda.eig_lowest(L, W, R, psi, tol=tol, flags=flags, **opts)
+    stats = _cuda.eig_lowest(L, W, R, psi, tol=tol, flags=flags, image=image, **opts)
     if not stats["converged"]:
         logger.warning(f"eigshmv: not converged after {stats['n_matvec']} matvecs, residual {stats['resid']:.3e}")
     linear_operator.last_stats = stats

@@ -452,6 +452,7 @@ class Environment:
         self._left_identity: Dict[int, bool] = {}
         self._right_identity: Dict[int, bool] = {}
         self.bond_singular_values: Dict[int, object] = {}
+        self._image = None  # (site, H_eff psi) left by the last on-device eigensolve, valid until the site changes
         if canonicalize and share_state_with is None:
             self.right_canonicalize()
         if build_left:  # the reference builds both stacks up front (:247-250)
@@ -548,10 +549,20 @@ class Environment:
         elif direction == Direction.LEFTWARD:
             self.update_right(site - 1)
 
+    def remember_image(self, site: int, image):
+        """H_eff . A[site] for the tensor currently stored at ``site`` (set by the eigensolve that wrote it)."""
+        self._image = (site, image)
+
+    def take_image(self, site: int):
+        """The remembered H_eff . A[site], once; None if the site tensor was rewritten since."""
+        held, self._image = self._image, None
+        return held[1] if held is not None and held[0] == site else None
+
     # -- a10 ------------------------------------------------------------------------------------------
     def update_mps(self, site: int, data):
         import torch
 
+        self._image = None
         if isinstance(data, torch.Tensor):
             src = data.to(device="cuda", dtype=torch.float64)
         else:
@@ -564,6 +575,7 @@ class Environment:
         if direction not in (Direction.RIGHTWARD, Direction.LEFTWARD):
             raise KeyError("MatrixProductState only supplies left or right direction.")
         nb_site = site + 1 if direction == Direction.RIGHTWARD else site - 1
+        self._image = None
         a, nb, s = _split_on_device(self._A[site], self._A[nb_site], direction, self.split_mode, self.qr_min_bond)
         kind = "svd" if not isinstance(s, DeferredSpectrum) else ("qr_shifted" if s.shifted else "qr")
         self.split_counts[kind] += 1
