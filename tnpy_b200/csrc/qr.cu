@@ -117,55 +117,83 @@ int mm(const MmArgs& p, int tiles_n, int tiles_m, int batch, cudaStream_t stream
 }
 
 // ---- one 64x64 diagonal block: G_kk = L L^T in place (upper part zeroed) and Dinv = L^-1 ------------------
-// Right-looking column Cholesky in shared memory, two barriers per column (every thread takes the pivot's
-// square root itself; the diagonal of L lives in dd[] so the tile's diagonal is never rewritten mid-step).  The
-// inverse X = L^-1 is built in the unused strict upper triangle of the tile (X[k][c] at S[c][k]), four threads
-// per column splitting each inner product.
+// The kernel is a chain of 64 dependent column steps on one CTA, i.e. bound by instruction latency (ncu: 120 k
+// warp instructions at 0.19 IPC per scheduler in the shared-memory version), so the tile and the inverse under
+// construction live in REGISTERS: thread (ty, tx) owns the 4x4 blocks S[4ty.., 4tx..] and X[4ty.., 4tx..].
+// Step j: the owners publish column j of S and row j of X (64 + 64 doubles, double-buffered => one barrier per
+// step); every thread then takes the reciprocal square root of the pivot itself and applies two rank-1 updates
+// from registers,  S -= l l^T  (right-looking Cholesky) and  X -= l x_j  (forward substitution of L X = I by
+// columns of L) -- 32 DFMA and 12 LDS per thread and step, no index arithmetic, no serial tail for the inverse.
 __global__ void __launch_bounds__(256) chol_diag_kernel(double* G, int64_t ld, double* __restrict__ Dinv,
                                                         int* __restrict__ fail) {
-  __shared__ double S[NB][NB + 1];
-  __shared__ double dd[NB];
-  const int tid = threadIdx.x;
-  for (int idx = tid; idx < NB * NB; idx += 256) S[idx >> 6][idx & 63] = G[(int64_t)(idx >> 6) * ld + (idx & 63)];
-  __syncthreads();
-  for (int j = 0; j < NB; ++j) {
-    double p = S[j][j];
-    const bool bad = !(p > 0.0) || !isfinite(p);  // not positive definite to working precision: flag, stay finite
-    if (bad) p = 1.0;
-    const double d = sqrt(p);
-    if (tid == 0) {
-      dd[j] = d;
-      if (bad) *fail = 1;
+  __shared__ double colbuf[2][NB];
+  __shared__ double rowbuf[2][NB];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  double sr[4][4], xr[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      sr[i][k] = G[(int64_t)(4 * ty + i) * ld + 4 * tx + k];
+      xr[i][k] = (4 * ty + i == 4 * tx + k) ? 1.0 : 0.0;
     }
-    if (tid > j && tid < NB) S[tid][j] /= d;
-    __syncthreads();
-    const int rows = NB - 1 - j;  // rows j+1 .. 63 of the trailing block
-    for (int idx = tid; idx < rows * NB; idx += 256) {
-      const int r = j + 1 + (idx >> 6), c = idx & 63;
-      if (c > j && c <= r) S[r][c] -= S[r][j] * S[c][j];
+#pragma unroll 1
+  for (int jb = 0; jb < NB / 4; ++jb) {
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const int j = 4 * jb + kk, buf = kk & 1;
+      if (tx == jb) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) colbuf[buf][4 * ty + i] = sr[i][kk];
+      }
+      if (ty == jb) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) rowbuf[buf][4 * tx + k] = xr[kk][k];
+      }
+      __syncthreads();
+      double p = colbuf[buf][j];
+      const bool bad = !(p > 0.0) || !isfinite(p);  // not positive definite to working precision: flag, stay finite
+      if (bad) {
+        p = 1.0;
+        if (tid == 0) *fail = 1;
+      }
+      const double ri = rsqrt(p);
+      double lr[4], lc[4], xj[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) lr[i] = (4 * ty + i > j) ? colbuf[buf][4 * ty + i] * ri : 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        lc[k] = (4 * tx + k > j) ? colbuf[buf][4 * tx + k] * ri : 0.0;
+        xj[k] = rowbuf[buf][4 * tx + k] * ri;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          sr[i][k] = fma(-lr[i], lc[k], sr[i][k]);
+          xr[i][k] = fma(-lr[i], xj[k], xr[i][k]);
+        }
+      if (tx == jb) {  // column j of L is final: below the diagonal the scaled column, on it sqrt(p)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (4 * ty + i > j) sr[i][kk] = lr[i];
+          if (4 * ty + i == j) sr[i][kk] = p * ri;
+        }
+      }
+      if (ty == jb) {  // row j of X is final
+#pragma unroll
+        for (int k = 0; k < 4; ++k) xr[kk][k] = xj[k];
+      }
     }
-    __syncthreads();
   }
-  {
-    // column c = tid / 4 of X, lanes q = tid % 4 of a quad split the sum over k
-    const int c = tid >> 2, q = tid & 3;
-    const unsigned quad = 0xFu << (tid & 28);  // the quads of a warp run different trip counts: quad-wide sync only
-    const double xcc = 1.0 / dd[c];
-    for (int r = c + 1; r < NB; ++r) {
-      double sum = q == 0 ? S[r][c] * xcc : 0.0;
-      for (int k = c + 1 + q; k < r; k += 4) sum = fma(S[r][k], S[c][k], sum);
-      sum += __shfl_xor_sync(quad, sum, 1);
-      sum += __shfl_xor_sync(quad, sum, 2);
-      if (q == 0) S[c][r] = -sum / dd[r];
-      __syncwarp(quad);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = 4 * ty + i, c = 4 * tx + k;
+      G[(int64_t)r * ld + c] = r >= c ? sr[i][k] : 0.0;
+      Dinv[r * NB + c] = r >= c ? xr[i][k] : 0.0;
     }
-  }
-  __syncthreads();
-  for (int idx = tid; idx < NB * NB; idx += 256) {
-    const int r = idx >> 6, c = idx & 63;
-    G[(int64_t)r * ld + c] = r > c ? S[r][c] : (r == c ? dd[r] : 0.0);
-    Dinv[idx] = r > c ? S[c][r] : (r == c ? 1.0 / dd[r] : 0.0);
-  }
 }
 
 // dinv[i] = 1 / sqrt(G[i][i]) for i < n (1 on the padding); a zero / non-finite vector raises the fail flag
