@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--tol", type=float, default=1e-8)
     ap.add_argument("--oracle", action="store_true")
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--ncv", type=int, default=0, help="Lanczos basis size (0 = library default)")
     ap.add_argument("--split", default="qr", choices=["qr", "svd"], help="bond split inside the sweeps")
     args = ap.parse_args()
 
@@ -76,7 +77,7 @@ def main():
         e_gpu, per_sweep = [], []
         for _, direction in zip(range(args.sweeps), cycle([Direction.RIGHTWARD, Direction.LEFTWARD])):
             t = time.perf_counter()
-            e_gpu.append(gpu.sweep(direction, tol=args.tol))
+            e_gpu.append(gpu.sweep(direction, tol=args.tol, **({"ncv": args.ncv} if args.ncv else {})))
             torch.cuda.synchronize()
             per_sweep.append(time.perf_counter() - t)
             out.setdefault("gpu_matvecs_per_sweep", []).append(sum(s.get("n_matvec", 0) for s in gpu.solver_stats))
@@ -90,6 +91,7 @@ def main():
     out["gpu_energies"] = e_gpu
     out["gpu_launches"] = _cuda.launch_count() - l0
     out["split"] = args.split
+    out["ncv"] = args.ncv
     out["split_counts"] = dict(gpu.environment.split_counts)
 
     if args.oracle:
