@@ -13,6 +13,10 @@ Fixtures (float64, NumPy .npz):
   env_cases.npz       update_left / update_right outputs for the same operands
   dmrg_xxz_n10_chi16.npz, dmrg_thirring_n10_chi12.npz, dmrg_rh_n10_chi16.npz
                       initial MPS, per-sweep energies (6 sweeps, exact local solves), final bond spectra, ED energy
+  config1_xxz_n100_chi60.npz
+                      BASELINE.json configs[0] (the reference's README example) run to convergence by the oracle at
+                      tol 1e-8 from random_mps(seed=0): per-sweep energies (the initial state is regenerated from the
+                      seed by the test, it is not stored)
 """
 import os
 import sys
@@ -72,6 +76,10 @@ def main():
                         **dmrg_case(oracle.thirring_mpo(10, 0.5, 1.0, 1.0, 0), 10, 12, 5))
     np.savez_compressed(os.path.join(HERE, "dmrg_rh_n10_chi16.npz"),
                         **dmrg_case(oracle.random_heisenberg_mpo(10, 1.0, seed=2022), 10, 16, 7))
+    f = oracle.FiniteDMRG(oracle.xxz_mpo(100, 0.5), 60, mps=oracle.random_mps(100, 60, 2, seed=0))
+    energies = f.run(tol=1e-8, with_variance=False)
+    np.savez_compressed(os.path.join(HERE, "config1_xxz_n100_chi60.npz"), energies=np.array(energies), n=np.array(100),
+                        chi=np.array(60), delta=np.array(0.5), seed=np.array(0), tol=np.array(1e-8))
     for name in sorted(os.listdir(HERE)):
         if name.endswith(".npz"):
             print(name, os.path.getsize(os.path.join(HERE, name)), "bytes")

@@ -87,3 +87,26 @@ def test_gpu_dmrg_matches_fixture(name, split):
     sv = f.bond_singular_values
     for bond in range(n - 1):
         assert np.abs(sv[bond] - z[f"spectrum_{bond}"]).max() < 1e-9, bond
+
+
+@pytest.mark.gpu
+def test_gpu_baseline_config1_matches_fixture():
+    """BASELINE.json configs[0] -- the reference's README example, XXZ n=100 delta=0.5 chi=60 tol=1e-8, through the
+    README spelling of the API -- against the oracle's committed energies (config1_xxz_n100_chi60.npz; the oracle
+    needs ~100 s of CPU for this run, so it is a fixture rather than a live comparison).  The two sides use
+    different eigensolvers at tol 1e-8, so only the converged energy is comparable: 1e-10 relative (measured
+    5e-13), and every sweep's energy is variational with respect to it."""
+    pytest.importorskip("torch")
+    from tnpy_b200.finite_dmrg import FiniteDMRG
+    from tnpy_b200.matrix_product_state import MatrixProductState
+    from tnpy_b200.model import XXZ
+
+    z = load("config1_xxz_n100_chi60.npz")
+    n, chi = int(z["n"]), int(z["chi"])
+    init = MatrixProductState(oracle.random_mps(n, chi, 2, seed=int(z["seed"])))
+    fdmrg = FiniteDMRG(mpo=XXZ(n=n, delta=float(z["delta"])).mpo, chi=chi, mps=init, compute_variance=False)
+    energies = fdmrg.update(tol=float(z["tol"]))
+    golden = z["energies"]
+    assert abs(energies[-1] - golden[-1]) <= 1e-10 * abs(golden[-1]), (energies, golden)
+    assert 2 <= len(energies) <= len(golden) + 2
+    assert all(e >= golden[-1] - 1e-9 for e in energies)
