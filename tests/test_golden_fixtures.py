@@ -94,8 +94,9 @@ def test_gpu_baseline_config1_matches_fixture():
     """BASELINE.json configs[0] -- the reference's README example, XXZ n=100 delta=0.5 chi=60 tol=1e-8, through the
     README spelling of the API -- against the oracle's committed energies (config1_xxz_n100_chi60.npz; the oracle
     needs ~100 s of CPU for this run, so it is a fixture rather than a live comparison).  The two sides use
-    different eigensolvers at tol 1e-8, so only the converged energy is comparable: 1e-10 relative (measured
-    5e-13), and every sweep's energy is variational with respect to it."""
+    different eigensolvers at tol 1e-8: the first two sweeps differ at the 1e-7 / 1e-10 level, from the third
+    sweep on the energies agree to 1e-10 relative (measured 5e-13).  The run stops on |dE| < 1e-8 where the
+    last step is 1.04e-8, so the number of sweeps is allowed to differ by one; energies are compared sweep by sweep."""
     pytest.importorskip("torch")
     from tnpy_b200.finite_dmrg import FiniteDMRG
     from tnpy_b200.matrix_product_state import MatrixProductState
@@ -107,6 +108,7 @@ def test_gpu_baseline_config1_matches_fixture():
     fdmrg = FiniteDMRG(mpo=XXZ(n=n, delta=float(z["delta"])).mpo, chi=chi, mps=init, compute_variance=False)
     energies = fdmrg.update(tol=float(z["tol"]))
     golden = z["energies"]
-    assert abs(energies[-1] - golden[-1]) <= 1e-10 * abs(golden[-1]), (energies, golden)
-    assert 2 <= len(energies) <= len(golden) + 2
-    assert all(e >= golden[-1] - 1e-9 for e in energies)
+    assert len(golden) - 1 <= len(energies) <= len(golden) + 1, (energies, golden)
+    for k in range(2, min(len(energies), len(golden))):
+        assert abs(energies[k] - golden[k]) <= 1e-10 * abs(golden[k]), (k, energies, golden)
+    assert all(b <= a + 1e-9 for a, b in zip(energies, energies[1:]))  # monotone within the solver tolerance
