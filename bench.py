@@ -1,22 +1,27 @@
 #!/usr/bin/env python
-"""bench.py -- the fDMRG local-update hot path on B200: H_eff matvec FP64 TFLOP/s (+ sweep seconds).
+"""bench.py -- the fDMRG local-update hot path on B200: H_eff matvec FP64 TFLOP/s (+ measured sweep seconds).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
 One JSON line on stdout (rank 0).  A "step" is one H_eff.psi contraction at a full-chi bulk site
 (the call primme makes ~10-30x per site in the reference, matrix_product_state.py:411-440).
 
-  N = 1   workload = BASELINE.json configs[2]: XXZ n=100 delta=0.5 chi=2048 (w=5, d=2), mid-chain site
-          of a synthetic random right-canonical MPS with genuine L / R from the update recursions.
+  N = 1   workload = BASELINE.json configs[2]: XXZ n=100 delta=0.5 chi=2048 (w=5, d=2), mid-chain site of a
+          synthetic random MPS brought into the mixed-canonical form it has inside a sweep (left half
+          left-canonical by the sweep's own QR splits, right half right-canonical), genuine L / R from the
+          update recursions.
   N > 1   workload = configs[4]: XXZ n=200 chi=8192, the matvec sharded over chi-row blocks of L
           (SURVEY 8e.1): every rank holds L[:, :, rows_g], the full R and x; per step the ranks
           all-gather x over NCCL and run the local chain; no reduction is needed.
 
-`value` is whole-job algorithmic TFLOP/s (F_mv = 4 w d chi^3 + 2 w^2 d^2 chi^2 per matvec)
-with operands resident in HBM; `e2e` is the same metric through the reference-facing seam
-(``Environment.one_site_matvec(site).matvec(x_host)``): pinned host vector in, host vector out, both
-copies inside the timed region.  `roofline` is for the dominant kernel (gemm_tn_dmma) against the
-FP64 GEMM rate cuBLAS reaches in the same process (MEASURED_PEAKS.json carries no FP64 figure).
+`value` is whole-job algorithmic TFLOP/s (F_mv = 4 w d chi^3 + 2 w^2 d^2 chi^2 per matvec) of the
+GENERAL chain -- every MPO channel of both environments multiplied out, executed flops = algorithmic flops -- on
+the library's default path (large GEMMs FP64-accurately on the tcgen05 int8 tensor cores), with operands resident
+in HBM, through the prepared operator the eigensolver uses.  `e2e` is the same through the reference-facing seam
+(``Environment.one_site_matvec(site).matvec(x_host)``): pinned host vector in, host vector out, both copies inside
+the timed region.  `canonical_gauge` is the matvec as every sweep step actually runs it (identity channels of the
+mixed-canonical gauge measured and skipped: the direct path, executed flops 0.8 F_mv), `native_fp64` the same two
+on the FP64 tensor pipe (DMMA).  `roofline` is for the dominant kernel of `value`.
 """
 from __future__ import annotations
 
@@ -145,9 +150,59 @@ def all_host_threads():
         return nullcontext()
 
 
+def cpu_workload(chi, n_gpus):
+    """Operands of the CPU arm: the workload's own chi.  chi = 2048: the full matvec (~1.2 s of host BLAS).
+    chi = 8192 (the sharded workload): a 128-row block of it -- y[rows] = H_eff(L[:, :, rows], W, R) x, the unit of
+    work one rank of the GPU arm does -- because one full matvec is 2.2e13 flop, minutes per step on host cores."""
+    from oracle import tnpy_oracle as oracle
+
+    w, d = 5, 2
+    rows = chi if chi <= 2048 else 128
+    rng = np.random.default_rng(0)
+    L = rng.standard_normal((chi, w, rows))
+    R = rng.standard_normal((chi, w, chi))
+    W = np.ascontiguousarray(oracle.xxz_mpo(4, 0.5)[1])
+    x = rng.standard_normal((chi, d, chi))
+    flops = f_mv(chi, chi, w, w, d) * rows / chi
+    what = (f"NumPy tensordot-chain matvecs (oracle/tnpy_oracle.heff_apply) at chi={chi}, w=5, d=2"
+            + ("" if rows == chi else f", rows [0, {rows}) of the output (1/{chi // rows} of one matvec per step)"))
+    return (lambda: oracle.heff_apply(L, W, R, x)), flops, what
+
+
+def reference_install():
+    """The real reference (tnpy + quimb + primme) when it is importable on this box -- an install under
+    baseline/_ref or site-packages.  It is not in the build container (no wheels for quimb / primme /
+    tensornetwork); the probe is here so that a box that has it uses it."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if os.path.isdir(ref) and ref not in sys.path:
+        sys.path.insert(0, ref)
+    try:
+        import primme  # noqa: F401
+        import quimb  # noqa: F401
+        import tnpy as ref_tnpy
+
+        if os.path.realpath(os.path.dirname(ref_tnpy.__file__)).startswith(os.path.realpath(ROOT) + os.sep + "tnpy"):
+            return None  # that is this repo's alias package, not the reference
+        return ref_tnpy
+    except Exception:
+        return None
+
+
+def reference_matvec_step(ref_tnpy, chi):
+    """One H_eff matvec of the real reference at a full-chi site of XXZ n=24 (same bulk shapes as n=100)."""
+    from tnpy.matrix_product_state import Environment, MatrixProductState  # the reference's
+    from tnpy.model import XXZ
+
+    n = max(24, 2 * int(np.ceil(np.log2(chi))) + 2)
+    env = Environment(XXZ(n=n, delta=0.5).mpo, MatrixProductState.random(n=n, bond_dim=chi, phys_dim=2))
+    op = env.one_site_matvec(n // 2)
+    x = np.random.default_rng(0).standard_normal(op.shape[0])
+    return (lambda: op.matvec(x)), f_mv(chi, chi, 5, 5, 2), f"tnpy/quimb Environment.one_site_matvec(site).matvec at chi={chi}"
+
+
 def run_reference(args):
-    """--impl reference: the reference's own CPU algorithm for this step (NumPy restatement in
-    oracle/ -- quimb/primme are not installable here) on the box's host cores."""
+    """--impl reference: the reference's own CPU implementation of the step on the box's host cores -- the real
+    tnpy/quimb/primme when importable, else its NumPy restatement in oracle/ -- at the workload's own chi."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -156,35 +211,24 @@ def run_reference(args):
 
 
 def _run_reference(args):
-    from oracle import tnpy_oracle as oracle
-
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
     chi = args.chi or (2048 if args.gpus == 1 else 8192)
-    sample_chi = min(chi, args.cpu_chi)
-    w, d = 5, 2
-    rng = np.random.default_rng(0)
-    L = rng.standard_normal((sample_chi, w, sample_chi))
-    R = rng.standard_normal((sample_chi, w, sample_chi))
-    W = np.ascontiguousarray(oracle.xxz_mpo(4, 0.5)[1])
-    x = rng.standard_normal((sample_chi, d, sample_chi))
-    for _ in range(max(args.warmup, 1)):
-        oracle.heff_apply(L, W, R, x)
+    ref_tnpy = reference_install() if chi <= 2048 else None
+    kind = "reference" if ref_tnpy is not None else "port"
+    step, flops, what = reference_matvec_step(ref_tnpy, chi) if ref_tnpy is not None else cpu_workload(chi, args.gpus)
+    for _ in range(max(args.warmup, 1) if chi <= 2048 else 1):
+        step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        oracle.heff_apply(L, W, R, x)
+        step()
     dt = time.perf_counter() - t0
-    flops = f_mv(sample_chi, sample_chi, w, w, d)
     value = flops * args.steps / dt / 1e12
     cores = os.cpu_count()
-    sample = f"{args.steps} NumPy tensordot-chain matvecs at chi={sample_chi} (w=5, d=2) of the chi={chi} workload"
     line = {
         "impl": "reference", "metric": "heff_matvec_fp64_tflops", "value": value, "unit": "TFLOP/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.gpus, chi), "chi": chi, "cpu_sample_chi": sample_chi},
-        "cpu_baseline": {"value": value, "unit": "TFLOP/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": workload_name(args.gpus, chi), "chi": chi, "cpu_sample_chi": chi, "same_config": True},
+        "cpu_baseline": {"value": value, "unit": "TFLOP/s", "cores": cores, "kind": kind, "sample": f"{args.steps} {what}"},
         "e2e": {"value": value, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -198,44 +242,60 @@ def workload_name(n_gpus, chi):
 
 
 def cpu_baseline(chi, budget_s=20.0):
-    """Oracle matvec on the host cores, bounded sample (same shapes when they fit the budget)."""
+    """Oracle matvec on the host cores at the workload's chi, bounded sample."""
     with all_host_threads():
-        return _cpu_baseline(chi, budget_s)
-
-
-def _cpu_baseline(chi, budget_s):
-    from oracle import tnpy_oracle as oracle
-
-    w, d = 5, 2
-    sample_chi = min(chi, 1024)
-    rng = np.random.default_rng(0)
-    L = rng.standard_normal((sample_chi, w, sample_chi))
-    R = rng.standard_normal((sample_chi, w, sample_chi))
-    W = np.ascontiguousarray(oracle.xxz_mpo(4, 0.5)[1])
-    x = rng.standard_normal((sample_chi, d, sample_chi))
-    oracle.heff_apply(L, W, R, x)
-    t0 = time.perf_counter()
-    n = 0
-    while True:
-        oracle.heff_apply(L, W, R, x)
-        n += 1
-        if time.perf_counter() - t0 > budget_s * 0.6 or n >= 100:
-            break
-    dt = (time.perf_counter() - t0) / n
-    return {
-        "value": f_mv(sample_chi, sample_chi, w, w, d) / dt / 1e12, "unit": "TFLOP/s", "cores": os.cpu_count(),
-        "kind": "port", "ms_per_matvec": dt * 1e3,
-        "sample": f"{n} NumPy tensordot-chain matvecs (oracle/tnpy_oracle.heff_apply) at chi={sample_chi}, w=5, d=2",
-    }
+        step, flops, what = cpu_workload(chi, 1)
+        step()
+        t0 = time.perf_counter()
+        n = 0
+        while True:
+            step()
+            n += 1
+            if time.perf_counter() - t0 > budget_s * 0.6 or n >= 100:
+                break
+        dt = (time.perf_counter() - t0) / n
+    return {"value": flops / dt / 1e12, "unit": "TFLOP/s", "cores": os.cpu_count(), "kind": "port",
+            "ms_per_matvec": dt * 1e3, "sample": f"{n} {what}"}
 
 
 # ---------------------------------------------------------------------------------------------------
+INT8_PEAK_POPS = 4.48  # ncu sm__ops_path_tensor_op_utcimma_src_int8 peak_sustained at 1965 MHz (profiles/r01_oz2_mma_kernel_ncu_full_raw.csv)
+
+
+def mixed_canonicalize(dmrg, site):
+    """Left-canonicalise sites 0 .. site-1 with the sweep's own split + environment update (no local solves):
+    the state at `site` is then in the mixed-canonical form every sweep step sees, and the identity channels of
+    both environments are *measured* by tnpy_identity_defect, not planted."""
+    from tnpy_b200.matrix_product_state import Direction
+
+    env = dmrg.environment
+    for s in range(site):
+        env.split_tensor(s, Direction.RIGHTWARD)
+        env.update(s, Direction.RIGHTWARD)
+
+
+def timed_plan(plan, x, y, steps, warmup, sync, slices=0):
+    for _ in range(warmup):
+        plan.apply(x, y, slices=slices)
+    return cuda_time(lambda: plan.apply(x, y, slices=slices), steps, sync) / steps
+
+
+def fp64_peak_cublas(m8, sync):
+    """FP64 GEMM yardstick measured in this process: cuBLAS dgemm m8^3, best of 5 (burst)."""
+    import torch
+
+    a = torch.randn(m8, m8, dtype=torch.float64, device="cuda")
+    b = torch.randn(m8, m8, dtype=torch.float64, device="cuda")
+    torch.matmul(a, b)
+    best = min(cuda_time(lambda: torch.matmul(a, b), 1, sync) for _ in range(5))
+    return 2.0 * m8**3 / best / 1e12
+
+
 def run_single(args):
     import torch
 
     from tnpy_b200 import _cuda
     from tnpy_b200.finite_dmrg import FiniteDMRG
-    from tnpy_b200.matrix_product_state import Direction
     from tnpy_b200.model import XXZ
 
     torch.cuda.set_device(0)
@@ -243,104 +303,96 @@ def run_single(args):
     chi = args.chi or 2048
     n = args.n or 100
     d = 2
-    model = XXZ(n=n, delta=0.5)
-    mpo = model.mpo
+    mpo = XXZ(n=n, delta=0.5).mpo
     sync = torch.cuda.synchronize
-
-    # FP64 roofline denominator measured here: cuBLAS dgemm 8192^3 (burst, best of 5) -- yardstick only
     m8 = 8192 if chi >= 1024 else 4096
-    a = torch.randn(m8, m8, dtype=torch.float64, device="cuda")
-    b = torch.randn(m8, m8, dtype=torch.float64, device="cuda")
-    torch.matmul(a, b)
-    best = min(cuda_time(lambda: torch.matmul(a, b), 1, sync) for _ in range(5))
-    fp64_peak = 2.0 * m8**3 / best / 1e12
-    del a, b
+    fp64_peak = fp64_peak_cublas(m8, sync)
 
     t_setup = time.perf_counter()
     tensors = random_right_canonical_device(n, chi, d, seed=0)
     dmrg = FiniteDMRG(mpo, bond_dim=chi, mps=tensors, compute_variance=False)
     env = dmrg.environment
     del tensors
+    site = n // 2
+    mixed_canonicalize(dmrg, site)
     sync()
     t_setup = time.perf_counter() - t_setup
-    site = n // 2
     L, W, R = env.operands(site)
+    W_host = mpo.as_four_leg(site)
     x = env.device_tensor(site).clone()
     y = torch.empty_like(x)
     l, _, r = x.shape
     wl, wr = W.shape[0], W.shape[1]
     flops = f_mv(l, r, wl, wr, d)
+    gauge = env.gauge_flags(site)
+    tf = lambda sec: flops / sec / 1e12  # noqa: E731
 
-    step = lambda: _cuda.heff_apply(L, W, R, x, y)  # noqa: E731
+    # ---- the step: general chain on the default path, through the prepared operator ----------------
+    plan_g = _cuda.HeffPlan(L, W, R, l, r, flags=0, w_host=W_host)
     for _ in range(args.warmup):
-        step()
+        plan_g.apply(x, y)
     sync()
     sampler = ClockSampler(0)
     sampler.start()
     launches0 = _cuda.launch_count()
-    dt = cuda_time(step, args.steps, sync)
+    dt = cuda_time(lambda: plan_g.apply(x, y), args.steps, sync)
     launches = _cuda.launch_count() - launches0
+    y_general = y.clone()
+    bound_g = plan_g.error_bound()
+    mode_g = plan_g.mode
 
-    # the same step in the gauge the sweep actually runs in: mixed-canonical MPS => L[:,0,:] = R[:,w-1,:] = I,
-    # the library replaces those two channel slices of the GEMMs by transposes (executed flops (w-1)/w)
-    Lc = L.clone()
-    Lc[:, 0, :] = torch.eye(l, dtype=torch.float64, device="cuda")
-    Rc = R.clone()
-    Rc[:, wr - 1, :] = torch.eye(r, dtype=torch.float64, device="cuda")
-    both = _cuda.LEFT_IDENTITY | _cuda.RIGHT_IDENTITY
-    step_c = lambda: _cuda.heff_apply(Lc, W, Rc, x, y, flags=both)  # noqa: E731
-    y_ref = _cuda.heff_apply(Lc, W, Rc, x).clone()
-    for _ in range(args.warmup):
-        step_c()
-    dt_c = cuda_time(step_c, args.steps, sync)
-    gauge_diff = float((y - y_ref).abs().max() / y_ref.abs().max())
-    _cuda.heff_apply(L, W, R, x, y)
-    del Lc, Rc, y_ref
+    # ---- the same operands on the native FP64 chain (DMMA) ---------------------------------------
+    plan_f = _cuda.HeffPlan(L, W, R, l, r, flags=0, algo=_cuda.GEMM_FP64)
+    t_f = timed_plan(plan_f, x, y, args.steps, args.warmup, sync)
+    y_fp64 = y.clone()
+    diff_general = float((y_general - y_fp64).abs().max() / y_fp64.abs().max())
+    plan_f.close()
 
-    # the tcgen05 path: same matvec with the GEMMs on the int8 tensor cores (Ozaki scheme, 8 slices)
-    _cuda.set_gemm_algo(_cuda.GEMM_OZAKI)
-    try:
-        y_oz = _cuda.heff_apply(L, W, R, x).clone()
-        step_o = lambda: _cuda.heff_apply(L, W, R, x, y)  # noqa: E731
-        for _ in range(args.warmup):
-            step_o()
-        dt_o = cuda_time(step_o, args.steps, sync)
-        Lc = L.clone()
-        Lc[:, 0, :] = torch.eye(l, dtype=torch.float64, device="cuda")
-        Rc = R.clone()
-        Rc[:, wr - 1, :] = torch.eye(r, dtype=torch.float64, device="cuda")
-        step_oc = lambda: _cuda.heff_apply(Lc, W, Rc, x, y, flags=both)  # noqa: E731
-        step_oc()
-        dt_oc = cuda_time(step_oc, args.steps, sync)
-        # as the eigensolver runs it: L and R declared constant, their slices made once per solve
-        _cuda.ozaki_const_scope(True)
-        try:
-            y_sc = _cuda.heff_apply(L, W, R, x).clone()
-            scope_diff = float((y_sc - y_oz).abs().max())
-            del y_sc
-            step_o()
-            dt_os = cuda_time(step_o, args.steps, sync)
-            step_oc()
-            dt_ocs = cuda_time(step_oc, args.steps, sync)
-            # 7 slices (28 slice GEMMs): what tnpy_eig_lowest selects when its tolerance is >= 1e-10
-            _cuda.set_ozaki_slices(7)
-            y_s7 = _cuda.heff_apply(L, W, R, x).clone()
-            s7_diff = float((y_s7 - y_oz).abs().max() / y_oz.abs().max())
-            del y_s7
-            step_oc()
-            dt_ocs7 = cuda_time(step_oc, args.steps, sync)
-        finally:
-            _cuda.set_ozaki_slices(8)
-            _cuda.ozaki_const_scope(False)
-        del Lc, Rc
-    finally:
-        _cuda.set_gemm_algo(_cuda.GEMM_AUTO)
-    _cuda.heff_apply(L, W, R, x, y)
-    ozaki_diff = float((y_oz - y).abs().max() / y.abs().max())
-    del y_oz
+    # ---- as a sweep runs it: measured identity channels (the direct path when both hold) ---------
+    plan_c = _cuda.HeffPlan(L, W, R, l, r, flags=gauge, w_host=W_host)
+    t_c8 = timed_plan(plan_c, x, y, args.steps, args.warmup, sync, slices=8)
+    y_c8 = y.clone()
+    t_c7 = timed_plan(plan_c, x, y, args.steps, 1, sync, slices=7)
+    y_c7 = y.clone()
+    bound_c = plan_c.error_bound()
+    mode_c = plan_c.mode
+    plan_cf = _cuda.HeffPlan(L, W, R, l, r, flags=gauge, algo=_cuda.GEMM_FP64)
+    t_cf = timed_plan(plan_cf, x, y, args.steps, args.warmup, sync)
+    y_cf = y.clone()
+    plan_cf.close()
+    scale = float(y_fp64.abs().max())
+    canonical = {
+        "ms_per_step": t_c8 * 1e3, "tflops_algorithmic": tf(t_c8), "heff_mode": mode_c, "gauge_flags_measured": gauge,
+        "slices": 8, "executed_flop_fraction": ((wl - 1) / wl if wl == wr else None) if gauge == 3 else 1.0,
+        "rel_diff_vs_general_fp64_chain": float((y_c8 - y_fp64).abs().max()) / scale,
+        "rel_diff_vs_canonical_fp64_chain": float((y_c8 - y_cf).abs().max()) / scale,
+        "ms_per_step_7_slices": t_c7 * 1e3, "tflops_algorithmic_7_slices": tf(t_c7),
+        "rel_diff_7_vs_8_slices": float((y_c7 - y_c8).abs().max()) / scale,
+        "int8_error_bound_frobenius": bound_c, "y_norm": float(y_fp64.norm()),
+        "native_fp64_ms_per_step": t_cf * 1e3, "native_fp64_tflops_algorithmic": tf(t_cf),
+        "note": "the matvec of every sweep step: L[:,0,:] = R[:,w-1,:] = I measured on this state (mixed-canonical "
+                "at the site) and skipped; heff_mode 2 = direct path (two independent tcgen05 GEMMs on operands "
+                "premixed and sliced from x, no FP64 intermediate); 7 slices is what tnpy_eig_lowest uses at tol >= 1e-10",
+    }
+    del y_c8, y_c7, y_cf
 
-    # dominant kernel alone: the two gemm_tn_dmma launches of the chain, timed with events per launch group
-    ws = torch.empty(lib.tnpy_heff_workspace_bytes(l, r, wl, wr, d), dtype=torch.uint8, device="cuda")
+    # ---- dominant kernels alone -------------------------------------------------------------------
+    # (a) oz2_mma_kernel on the shapes it runs: operands already sliced (phase 2), int8 ops = 36 slice pairs x 2MNK
+    def oz_kernel_ms(m_, n_, k_):
+        a_ = torch.randn((k_, m_), dtype=torch.float64, device="cuda")
+        b_ = torch.randn((k_, n_), dtype=torch.float64, device="cuda")
+        c_ = torch.empty((m_, n_), dtype=torch.float64, device="cuda")
+        _cuda.ozaki_gemm_tn(a_, b_, out=c_, slices=8, phase=1)
+        mm = lambda: _cuda.ozaki_gemm_tn(a_, b_, out=c_, slices=8, phase=2)  # noqa: E731
+        mm()
+        return cuda_time(mm, args.steps, sync) / args.steps * 1e3
+
+    shapes_general = [(d * r, wl * l, l), (d * l, r, r * wr)]
+    shapes_direct = [(l * d, r, (wr - 1) * r), (l, d * r, (wl - 1) * l)]
+    oz_g = [oz_kernel_ms(*sh) for sh in shapes_general]
+    oz_d = [oz_kernel_ms(*sh) for sh in shapes_direct]
+    pops = lambda shapes, ms: sum(36 * 2.0 * m_ * n_ * k_ for m_, n_, k_ in shapes) / (sum(ms) * 1e-3) / 1e15  # noqa: E731
+    # (b) gemm_tn_dmma on the two GEMM shapes of the FP64 chain
     t1 = torch.empty((d * r, wl * l), dtype=torch.float64, device="cuda")
     t2 = torch.randn((r * wr, d * l), dtype=torch.float64, device="cuda")
     xm, Lm, Rm = x.reshape(l, d * r), L.reshape(l, wl * l), R.reshape(r * wr, r)
@@ -351,167 +403,152 @@ def run_single(args):
     tg1 = cuda_time(g1, args.steps, sync) / args.steps
     tg3 = cuda_time(g3, args.steps, sync) / args.steps
     gemm_flops = 2.0 * (d * r) * (wl * l) * l + 2.0 * (d * l) * r * (r * wr)
-    del t1, t2, yq, ws
-
-    # e2e through the reference-facing seam: host (pinned) vector in, host vector out
-    op = env.one_site_matvec(site)
-    x_host = torch.empty(x.numel(), dtype=torch.float64).pin_memory()
-    x_host.copy_(x.reshape(-1))
-    x_np = x_host.numpy()
-    for _ in range(max(2, args.warmup // 2)):
-        op.matvec(x_np)
-    sync()
-    t0 = time.perf_counter()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        y_np = op.matvec(x_np)
-    e1.record()
-    sync()
-    dt_e2e = max(e0.elapsed_time(e1) * 1e-3, time.perf_counter() - t0)
-    clocks = sampler.stop()
-    parity = float(np.abs(y_np - y.reshape(-1).cpu().numpy()).max())
-
-    # local-update breakdown at mid-chain sites (what a sweep is made of)
-    sweep = sweep_oz = None
-    if args.sweep_sites > 0:
-        sweep = measure_local_updates(dmrg, site, args.sweep_sites, Direction.RIGHTWARD, args.tol)
-        # the same local updates with the chains' GEMMs on the tcgen05 path (the next sites of the same sweep)
-        _cuda.set_gemm_algo(_cuda.GEMM_OZAKI)
-        try:
-            sweep_oz = measure_local_updates(dmrg, site + args.sweep_sites, args.sweep_sites, Direction.RIGHTWARD, args.tol)
-        finally:
-            _cuda.set_gemm_algo(_cuda.GEMM_AUTO)
-
-    # the tcgen05 kernel alone on the two GEMM shapes of the step (operands already sliced): int8 roofline
-    t1 = torch.empty((d * r, wl * l), dtype=torch.float64, device="cuda")
-    t2 = torch.randn((r * wr, d * l), dtype=torch.float64, device="cuda")
-    yq = torch.empty((d * l, r), dtype=torch.float64, device="cuda")
-    oz_ms = []
-    for (am, bm, cm) in ((x.reshape(l, d * r), L.reshape(l, wl * l), t1), (t2, R.reshape(r * wr, r), yq)):
-        _cuda.ozaki_gemm_tn(am, bm, out=cm, slices=8, phase=1)
-        mm = lambda: _cuda.ozaki_gemm_tn(am, bm, out=cm, slices=8, phase=2)  # noqa: E731
-        mm()
-        oz_ms.append(cuda_time(mm, args.steps, sync) / args.steps * 1e3)
     del t1, t2, yq
-    int8_peak = 4.48  # POP/s: ncu sm__ops_path_tensor_op_utcimma_src_int8 peak_sustained at 1965 MHz (profiles/)
-    oz_pops = 36 * gemm_flops / (sum(oz_ms) * 1e-3) / 1e15
+
+    # ---- e2e through the reference-facing seam: host (pinned) vector in, host vector out ------------
+    def e2e_seconds(use_identity):
+        env.use_identity_channels = use_identity
+        op = env.one_site_matvec(site, zero_copy=True)
+        x_host = torch.empty(x.numel(), dtype=torch.float64).pin_memory()
+        x_host.copy_(x.reshape(-1))
+        x_np = x_host.numpy()
+        for _ in range(max(2, args.warmup // 2)):
+            op.matvec(x_np)
+        sync()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            y_np = op.matvec(x_np)
+        e1.record()
+        sync()
+        sec = max(e0.elapsed_time(e1) * 1e-3, time.perf_counter() - t0) / args.steps
+        return sec, np.array(y_np, copy=True)
+
+    t_e2e, y_np = e2e_seconds(False)
+    parity = float(np.abs(y_np - y_general.reshape(-1).cpu().numpy()).max())
+    t_e2e_c, _ = e2e_seconds(True)
+    clocks = sampler.stop()
+    canonical["e2e_ms_per_step"] = t_e2e_c * 1e3
+    canonical["e2e_tflops_algorithmic"] = tf(t_e2e_c)
+    plan_g.close(); plan_c.close()
 
     value = flops * args.steps / dt / 1e12
-    gemm_flops_oz = 2.0 * (d * r) * (wl * l) * l + 2.0 * (d * l) * r * (r * wr)
+    roofline_oz = {
+        "bound": "tensor", "achieved": pops(shapes_general, oz_g), "peak": INT8_PEAK_POPS, "unit": "POP/s (int8)",
+        "frac": pops(shapes_general, oz_g) / INT8_PEAK_POPS,
+        "traffic": None,
+        "kernel": "oz2_mma_kernel<8> (tcgen05.mma.cta_group::2.kind::i8; 2 launches per matvec, operands already sliced)",
+        "ms_gemm1": oz_g[0], "ms_gemm3": oz_g[1], "shapes_mnk": shapes_general,
+        "fp64_equivalent_tflops": gemm_flops / (sum(oz_g) * 1e-3) / 1e12,
+        "algorithmic_ops": "36 slice pairs x 2 M N K int8 multiply-adds per launch (8 slices; DESIGN 2.2)",
+        "peak_source": "ncu sm__ops_path_tensor_op_utcimma_src_int8 peak_sustained at 1965 MHz (profiles/r01_oz2_mma_kernel_ncu_full_raw.csv)",
+        "direct_path_shapes": {"shapes_mnk": shapes_direct, "ms": oz_d, "achieved": pops(shapes_direct, oz_d),
+                               "frac": pops(shapes_direct, oz_d) / INT8_PEAK_POPS},
+    }
+    roofline_dmma = {
+        "bound": "tensor", "achieved": gemm_flops / (tg1 + tg3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+        "frac": gemm_flops / (tg1 + tg3) / 1e12 / fp64_peak, "traffic": 1.29e9 if chi == 2048 else None,
+        "kernel": "gemm_tn_dmma (2 launches per matvec)", "ms_gemm1": tg1 * 1e3, "ms_gemm3": tg3 * 1e3,
+        "peak_source": f"cuBLAS dgemm {m8}^3 via torch.matmul, best of 5 in this process; hardware DMMA peak and the "
+                       "sustained figure are tracked in profiles/r02_fp64_peak.json (MEASURED_PEAKS.json has no FP64 entry)",
+    }
     line = {
         "metric": "heff_matvec_fp64_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f64 (results); large GEMMs as exact int8 slice products with int32 accumulation, FP64 recombination",
+        "data": "synthetic",
         "config": {
             "workload": workload_name(1, chi), "n": n, "chi": chi, "w": wl, "d": d, "site": site,
-            "flops_per_step": flops, "l2_policy": "operands (L 168 MB + R 168 MB + x + T1/T2 670 MB at chi=2048) exceed the 126 MB L2; no flush needed",
+            "operands": "general chain: all w channels of L and R multiplied out (flags 0), executed = algorithmic flops",
+            "path": {0: "fp64 chain", 1: "chain, GEMMs on tcgen05 int8 (Ozaki, 8 slices)", 2: "direct"}[mode_g],
+            "flops_per_step": flops,
+            "l2_policy": "operands (L 168 MB + R 168 MB + int8 slices 0.3-0.6 GB + T1/T2 670 MB at chi=2048) exceed the 126 MB L2; no flush needed",
             "setup_s": t_setup,
         },
-        "roofline": {
-            "bound": "tensor", "achieved": gemm_flops / (tg1 + tg3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
-            "frac": gemm_flops / (tg1 + tg3) / 1e12 / fp64_peak,
-            "traffic": 1.29e9 if chi == 2048 else None,  # dram read + write per launch (mean of the two), ncu --set full (profiles/r01_gemm_tn_dmma_ncu_full_raw.csv)
-            "kernel": "gemm_tn_dmma (2 launches per matvec)", "ms_gemm1": tg1 * 1e3, "ms_gemm3": tg3 * 1e3,
-            "peak_source": f"cuBLAS dgemm {m8}^3 via torch.matmul, best of 5 in this process (MEASURED_PEAKS.json has no FP64 entry)",
-            "whole_step_frac": value / fp64_peak,
-        },
+        "rel_diff_vs_native_fp64_chain": diff_general,
+        "int8_error_bound_frobenius": bound_g,
+        "roofline": roofline_oz if mode_g != 0 else roofline_dmma,
         "e2e": {
-            "value": flops * args.steps / dt_e2e / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": int(x.numel() * 8),
-            "d2h_bytes_per_step": int(x.numel() * 8), "ms_per_step": dt_e2e / args.steps * 1e3,
-            "api": "Environment.one_site_matvec(site).matvec(x_host)", "max_abs_diff_vs_device_path": parity,
+            "value": tf(t_e2e), "unit": "TFLOP/s", "h2d_bytes_per_step": int(x.numel() * 8),
+            "d2h_bytes_per_step": int(x.numel() * 8), "ms_per_step": t_e2e * 1e3,
+            "api": "Environment.one_site_matvec(site).matvec(x_host), use_identity_channels off (general chain)",
+            "max_abs_diff_vs_device_path": parity,
         },
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "tcgen05_ozaki": {
-            "ms_per_step": dt_o / args.steps * 1e3, "tflops_fp64_equivalent": flops * args.steps / dt_o / 1e12,
-            "ms_per_step_canonical_gauge": dt_oc / args.steps * 1e3,
-            "tflops_fp64_equivalent_canonical_gauge": flops * args.steps / dt_oc / 1e12,
-            "ms_per_step_const_env": dt_os / args.steps * 1e3,
-            "tflops_fp64_equivalent_const_env": flops * args.steps / dt_os / 1e12,
-            "ms_per_step_canonical_gauge_const_env": dt_ocs / args.steps * 1e3,
-            "tflops_fp64_equivalent_canonical_gauge_const_env": flops * args.steps / dt_ocs / 1e12,
-            "max_abs_diff_const_env_vs_resliced": scope_diff,
-            "ms_per_step_canonical_gauge_const_env_7_slices": dt_ocs7 / args.steps * 1e3,
-            "tflops_fp64_equivalent_canonical_gauge_const_env_7_slices": flops * args.steps / dt_ocs7 / 1e12,
-            "rel_diff_7_vs_8_slices": s7_diff,
-            "rel_diff_vs_dmma_path": ozaki_diff, "slices": 8,
-            "int8_pops_const_env": 36 * gemm_flops_oz * args.steps / dt_os / 1e15,
-            "roofline": {
-                "bound": "tensor", "achieved": oz_pops, "peak": int8_peak, "unit": "POP/s (int8)", "frac": oz_pops / int8_peak,
-                "traffic": 1.63e9, "kernel": "oz2_mma_kernel<8> (2 launches per matvec)", "ms_gemm1": oz_ms[0],
-                "ms_gemm3": oz_ms[1], "fp64_equivalent_tflops": gemm_flops / (sum(oz_ms) * 1e-3) / 1e12,
-                "peak_source": "ncu sm__ops_path_tensor_op_utcimma_src_int8 peak_sustained (profiles/r01_oz2_mma_kernel_ncu_full_raw.csv); "
-                               "traffic = dram read + write per launch (mean of the two shapes) from the same capture",
-            },
-            "note": "same matvec with both GEMMs as 36 exact int8 slice GEMMs on tcgen05 (CTA pairs, TMEM int32 "
-                    "accumulators); first figures re-slice every operand on every call, *_const_env keep the slices "
-                    "of L and R for the duration of a scope as tnpy_eig_lowest does; int8_pops = 36 x 2MNK of both "
-                    "GEMMs / whole-step time (ncu peak 4.48 POP/s at 1965 MHz); opt-in via TNPY_GEMM_ALGO=ozaki",
-        },
-        "canonical_gauge": {
-            "ms_per_step": dt_c / args.steps * 1e3, "tflops_algorithmic": flops * args.steps / dt_c / 1e12,
-            "executed_flop_fraction": (wl - 1) / wl if wl == wr else None, "rel_diff_vs_dense_path": gauge_diff,
-            "note": "same matvec with L[:,0,:] = R[:,w-1,:] = I flagged (the state of every site inside a sweep); "
-                    "`value` above is the general dense path",
+        "canonical_gauge": canonical,
+        "native_fp64": {
+            "ms_per_step": t_f * 1e3, "tflops": tf(t_f), "roofline": roofline_dmma,
+            "note": "the same general chain with TNPY_GEMM_ALGO=fp64: gemm_tn_dmma (mma.sync DMMA) -> wmix -> gemm_tn_dmma",
         },
     }
-    if sweep is not None:
-        line["sweep"] = sweep
-    if sweep_oz is not None:
-        line["sweep_tcgen05"] = sweep_oz
+    del plan_g, plan_c, L, R, x, y, y_general, y_fp64, env, dmrg
+    torch.cuda.empty_cache()
+    if args.sweep_n > 0:
+        line["sweep_measured"] = measure_sweeps(args.sweep_n, chi, args.tol, args.sweep_count)
+    if args.scale_chi > 0:
+        line["scaling_reference_n1"] = single_gpu_matvec(args.scale_chi, max(2, args.steps // 4))
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(chi)
     print(json.dumps(line), flush=True)
 
 
-def measure_local_updates(dmrg, site, count, direction, tol):
-    """Full local updates (eigensolve + perturb + split + env update) at consecutive mid-chain
-    sites; per-phase device time and an extrapolated sweep time (sum over sites of the measured
-    per-site time scaled by F_mv(site) / F_mv(mid)).  `split` is what the sweep runs (verified
-    Cholesky-QR split -- two passes, then the shifted three-pass variant, then the SVD, whichever the
-    device-side orthogonality check accepted first, all attempts inside the timed phase); the reference-literal Jacobi SVD split
-    of the same tensor is timed beside it on a copy (`svd_split_reference_gauge`, not part of the total)."""
+def measure_sweeps(n, chi, tol, count):
+    """Whole sweeps, measured (not extrapolated): XXZ delta=0.5 at the stated (reduced) n and the workload's chi from
+    a random right-canonical MPS, default solver / split / GEMM selection, wall seconds with a device synchronise
+    on both sides of every sweep.  Sweep 1 is the cold sweep (local solves dominate), later ones are warm."""
     import torch
 
-    from tnpy_b200.matrix_product_state import Direction, _split_on_device
+    from tnpy_b200 import _cuda
+    from tnpy_b200.finite_dmrg import FiniteDMRG
+    from tnpy_b200.matrix_product_state import Direction
+    from tnpy_b200.model import XXZ
 
-    env = dmrg.environment
-    sync = torch.cuda.synchronize
-    phases = {"eigensolve": 0.0, "perturb": 0.0, "split": 0.0, "env_update": 0.0}
-    matvecs = 0
-    svd_gauge_s = 0.0
-    counts0 = dict(env.split_counts)
-    for s in range(site, site + count):
-        sync(); t = time.perf_counter()
-        dmrg._solve_on_device(s, tol)
-        sync(); phases["eigensolve"] += time.perf_counter() - t; t = time.perf_counter()
-        matvecs += dmrg.solver_stats[-1].get("n_matvec", 0)
-        dmrg.perturb_wave_function(s)
-        sync(); phases["perturb"] += time.perf_counter() - t; t = time.perf_counter()
-        nb_site = s + 1 if direction == Direction.RIGHTWARD else s - 1
-        sync(); t = time.perf_counter()
-        _split_on_device(env.device_tensor(s), env.device_tensor(nb_site), direction, "svd")
-        sync(); svd_gauge_s += time.perf_counter() - t; t = time.perf_counter()
-        env.split_tensor(s, direction)
-        sync(); phases["split"] += time.perf_counter() - t; t = time.perf_counter()
-        env.update(s, direction)
-        sync(); phases["env_update"] += time.perf_counter() - t
-    per_site = {k: v / count for k, v in phases.items()}
-    total = sum(per_site.values())
-    n = env.n_sites
-    shapes = [tuple(env.device_tensor(i).shape) for i in range(n)]
-    w = env.operands(site)[1].shape[0]
-    mid = f_mv(shapes[site][0], shapes[site][2], w, w, 2)
-    weight = sum(f_mv(sh[0], sh[2], w if i else 1, w if i < n - 1 else 1, 2) for i, sh in enumerate(shapes[:-1])) / mid
-    return {
-        "sites_measured": count, "per_site_s": per_site, "per_site_total_s": total,
-        "matvecs_per_site": matvecs / count, "sweep_s_extrapolated": total * weight,
-        "svd_split_reference_gauge_s": svd_gauge_s / count,
-        "sweep_s_extrapolated_svd_gauge": (total - per_site["split"] + svd_gauge_s / count) * weight,
-        "splits": {k: env.split_counts[k] - counts0[k] for k in counts0},
-        "note": "extrapolated = per-site total x sum_sites F_mv(site)/F_mv(mid); eigensolver tol %.0e" % tol,
-    }
+    tensors = random_right_canonical_device(n, chi, 2, seed=1)
+    dmrg = FiniteDMRG(XXZ(n=n, delta=0.5).mpo, bond_dim=chi, mps=tensors, compute_variance=False)
+    del tensors
+    dmrg.phase_seconds = {}
+    out = {"n": n, "chi": chi, "tol": tol, "sweep_s": [], "matvecs": [], "energies": [], "phase_s_cumulative": [],
+           "launches": [], "sites_at_full_chi": sum(1 for i in range(n) if dmrg.environment.device_tensor(i).shape[0] == chi
+                                                    and dmrg.environment.device_tensor(i).shape[2] == chi)}
+    for k in range(count):
+        torch.cuda.synchronize()
+        l0, t0 = _cuda.launch_count(), time.perf_counter()
+        e = dmrg.sweep(Direction.RIGHTWARD if k % 2 == 0 else Direction.LEFTWARD, tol=tol)
+        torch.cuda.synchronize()
+        out["sweep_s"].append(time.perf_counter() - t0)
+        out["launches"].append(_cuda.launch_count() - l0)
+        out["matvecs"].append(sum(st.get("n_matvec", 0) for st in dmrg.solver_stats))
+        out["energies"].append(e)
+        out["phase_s_cumulative"].append(dict(dmrg.phase_seconds))
+    out["split_counts"] = dict(dmrg.environment.split_counts)
+    out["note"] = ("measured whole sweeps at reduced n (the full n=100 chi=2048 run is recorded in profiles/, minutes per "
+                   "cold sweep); the reference's tol=1e-8 stopping rule per local solve")
+    return out
+
+
+def single_gpu_matvec(chi, steps):
+    """The N>1 workload (random L / R at chi, general chain) on ONE GPU, so that the 2/4/8-GPU lines of the same
+    bench have a same-workload N=1 point (the driver's N=1 run is the chi=2048 headline)."""
+    import torch
+
+    from tnpy_b200 import _cuda
+    from tnpy_b200.model import XXZ
+
+    w, d = 5, 2
+    g = torch.Generator(device="cuda").manual_seed(99)
+    rnd = lambda *s: torch.randn(s, generator=g, dtype=torch.float64, device="cuda")  # noqa: E731
+    L, R, x = rnd(chi, w, chi), rnd(chi, w, chi), rnd(chi, d, chi)
+    W = torch.from_numpy(np.ascontiguousarray(XXZ(n=4, delta=0.5).mpo.as_four_leg(1))).cuda()
+    y = torch.empty_like(x)
+    plan = _cuda.HeffPlan(L, W, R, chi, chi)
+    sec = timed_plan(plan, x, y, steps, 1, torch.cuda.synchronize)
+    mode = plan.mode
+    plan.close()
+    flops = f_mv(chi, chi, w, w, d)
+    return {"workload": workload_name(2, chi).replace("on 2 GPUs", "on 1 GPU (unsharded)"), "chi": chi, "steps": steps,
+            "ms_per_step": sec * 1e3, "value": flops / sec / 1e12, "unit": "TFLOP/s", "heff_mode": mode}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -547,16 +584,41 @@ def run_sharded(args):
     if not equal:
         raise SystemExit(f"bench: chi={chi} does not split evenly over {world} ranks")
 
+    plan = _cuda.HeffPlan(L_rows, W, R, chi, chi, l_rows=rows)  # environments sliced once, as in a local solve
+
     def gather():
         dist.all_gather_into_tensor(x_full, x_rows)
 
     def step():
         gather()
-        _cuda.heff_apply_rows(L_rows, W, R, x_full, y_rows)
+        plan.apply(x_full, y_rows)
 
     def barrier():
         dist.barrier()
         torch.cuda.synchronize()
+
+    # correctness of the sharded result, once, outside the timed region: rank 0 rebuilds the full L from every
+    # rank's seed, runs the unsharded matvec on the native FP64 chain and broadcasts y; every rank compares its rows
+    step()
+    y_check = torch.empty((chi, d, chi), dtype=torch.float64, device="cuda")
+    if rank == 0:
+        L_full = torch.empty((chi, w, chi), dtype=torch.float64, device="cuda")
+        for g_ in range(world):
+            lo_g, hi_g = row_block(chi, world, g_)
+            gg = torch.Generator(device="cuda").manual_seed(1234 + g_)
+            L_full[:, :, lo_g:hi_g] = torch.randn((chi, w, hi_g - lo_g), generator=gg, dtype=torch.float64, device="cuda")
+        ref_plan = _cuda.HeffPlan(L_full, W, R, chi, chi, algo=_cuda.GEMM_FP64)
+        ref_plan.apply(x_full, y_check)
+        ref_plan.close()
+        del L_full, ref_plan
+    dist.broadcast(y_check, src=0)
+    diff = ((y_rows - y_check[lo0:lo1]).abs().max() / y_check.abs().max()).reshape(1)
+    dist.all_reduce(diff, op=dist.ReduceOp.MAX)
+    max_rel_diff = float(diff.item())
+    del y_check
+    torch.cuda.empty_cache()
+    if not max_rel_diff < 1e-12:
+        raise SystemExit(f"bench: sharded matvec differs from the unsharded FP64 chain by {max_rel_diff:.3e} (> 1e-12)")
 
     # per-GPU FP64 roofline denominator: cuBLAS dgemm 8192^3 on this rank (yardstick only), max over ranks
     a8 = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
@@ -589,7 +651,7 @@ def run_sharded(args):
     barrier()
     e0.record()
     for _ in range(args.steps):
-        _cuda.heff_apply_rows(L_rows, W, R, x_full, y_rows)
+        plan.apply(x_full, y_rows)
     e1.record()
     barrier()
     dt_compute = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device="cuda")
@@ -618,6 +680,26 @@ def run_sharded(args):
     clocks = sampler.stop() if rank == 0 else None
     if rank == 0:
         t, tc, te = float(dt.item()), float(dt_compute.item()), float(dt_e2e.item())
+        gemm_flops = 4.0 * w * d * float(chi) ** 3  # the two GEMMs of the chain, all ranks
+        if plan.mode != 0:
+            pops = 36 * gemm_flops * args.steps / tc / world / 1e15
+            roofline = {
+                "bound": "tensor", "achieved": pops, "peak": INT8_PEAK_POPS, "unit": "POP/s (int8) per GPU",
+                "frac": pops / INT8_PEAK_POPS, "traffic": None,
+                "kernel": "local chain per GPU (x / T2 slicing + wmix + 2 x oz2_mma_kernel<8>), all-gather excluded; "
+                          "int8 ops = 36 slice pairs x 2MNK of the two GEMMs",
+                "peak_source": "ncu sm__ops_path_tensor_op_utcimma_src_int8 peak_sustained at 1965 MHz (profiles/r01_oz2_mma_kernel_ncu_full_raw.csv)",
+                "fp64_equivalent_tflops_per_gpu": flops * args.steps / tc / 1e12 / world, "cublas_dgemm_tflops": fp64_peak,
+                "ms_compute_per_step": tc / args.steps * 1e3, "ms_allgather_per_step": (t - tc) / args.steps * 1e3,
+            }
+        else:
+            roofline = {
+                "bound": "tensor", "achieved": flops * args.steps / tc / 1e12 / world, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": flops * args.steps / tc / 1e12 / world / fp64_peak, "traffic": None,
+                "kernel": "local chain per GPU (gemm_tn_dmma x2 + wmix), all-gather excluded",
+                "peak_source": "cuBLAS dgemm 8192^3 per GPU, best of 3, max over ranks",
+                "ms_compute_per_step": tc / args.steps * 1e3, "ms_allgather_per_step": (t - tc) / args.steps * 1e3,
+            }
         line = {
             "metric": "heff_matvec_fp64_tflops", "value": flops * args.steps / t / 1e12, "unit": "TFLOP/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3,
@@ -626,14 +708,10 @@ def run_sharded(args):
                 "workload": workload_name(world, chi), "chi": chi, "w": w, "d": d, "rows_per_rank": rows,
                 "parallelism": f"chi-row blocks of L x{world}; all-gather(x) per step over NCCL; no reduction",
                 "flops_per_step": flops, "l2_policy": "operands exceed L2; no flush needed",
+                "path": {0: "fp64 chain", 1: "chain, GEMMs on tcgen05 int8 (Ozaki, 8 slices)", 2: "direct"}[plan.mode],
             },
-            "roofline": {
-                "bound": "tensor", "achieved": flops * args.steps / tc / 1e12 / world, "peak": fp64_peak, "unit": "TFLOP/s",
-                "frac": flops * args.steps / tc / 1e12 / world / fp64_peak, "traffic": None,
-                "kernel": "local chain per GPU (gemm_tn_dmma x2 + wmix), all-gather excluded",
-                "peak_source": "cuBLAS dgemm 8192^3 per GPU, best of 3, max over ranks",
-                "ms_compute_per_step": tc / args.steps * 1e3, "ms_allgather_per_step": (t - tc) / args.steps * 1e3,
-            },
+            "max_rel_diff_vs_unsharded_fp64_chain": max_rel_diff,
+            "roofline": roofline,
             "e2e": {
                 "value": flops * args.steps / te / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": int(x_rows.numel() * 8 * world),
                 "d2h_bytes_per_step": int(x_rows.numel() * 8 * world), "ms_per_step": te / args.steps * 1e3,
@@ -653,8 +731,9 @@ def main():
     ap.add_argument("--chi", type=int, default=0)
     ap.add_argument("--n", type=int, default=0)
     ap.add_argument("--tol", type=float, default=1e-8)
-    ap.add_argument("--sweep-sites", type=int, default=2, help="mid-chain local updates to time for the sweep estimate (0 = skip)")
-    ap.add_argument("--cpu-chi", type=int, default=1024, help="--impl reference: chi of the bounded CPU sample")
+    ap.add_argument("--sweep-n", type=int, default=40, help="chain length of the measured whole sweeps at the workload's chi (0 = skip)")
+    ap.add_argument("--sweep-count", type=int, default=2, help="number of measured sweeps (the first is the cold one)")
+    ap.add_argument("--scale-chi", type=int, default=8192, help="chi of the same-workload single-GPU point of the scaling run (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

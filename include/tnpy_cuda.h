@@ -8,8 +8,13 @@
  *
  * Conventions
  *   - All tensor pointers are DEVICE pointers to C-order (row-major) float64 unless the name ends
- *     in `_host`.  Nothing here owns memory: the caller (PyTorch on the Python side) allocates
- *     inputs, outputs and workspaces; the library only borrows them for the duration of the call.
+ *     in `_host`.  The caller (PyTorch on the Python side) allocates inputs, outputs and workspaces; the library
+ *     only borrows them for the duration of the call (a tnpy_heff_plan borrows its plan memory for the life of the
+ *     handle).  The one piece of device memory the library owns is a 0.6 MB reduction scratch per (device, stream),
+ *     allocated on first use by the vector entry points, which take no workspace argument.
+ *   - One process per GPU, calls from one host thread at a time per stream.  Reduction scratch, the pinned status
+ *     word and kernel attributes are kept per device / per stream, so several streams of one device may be used
+ *     concurrently from different host threads.
  *   - Every call takes the CUDA stream to enqueue on (as a `void*` == cudaStream_t) and is
  *     asynchronous with respect to the host unless documented otherwise.
  *   - Return value: 0 on success, a negative TNPY_E* code otherwise.  Never throws.
@@ -38,12 +43,15 @@ extern "C" {
 #define TNPY_ECUDA (-3)     /* a CUDA runtime / driver call failed */
 #define TNPY_ENOCONV (-4)   /* iterative routine hit its iteration limit (result still written) */
 
-/* GEMM kernel selection for tnpy_gemm_tn / the contraction chain. */
-#define TNPY_GEMM_AUTO 0    /* TMA+DMMA kernel when shapes/alignments allow, else the generic one */
+/* GEMM kernel selection (tnpy_set_gemm_algo, the `algo` arguments, env TNPY_GEMM_ALGO=auto|generic|dmma|ozaki|fp64). */
+#define TNPY_GEMM_AUTO 0    /* the default: large products of the contraction chains run FP64-accurately on the
+                               tcgen05 int8 tensor cores (Ozaki scheme, csrc/ozaki.cu), everything else on the
+                               FP64 tensor pipe (TMA + DMMA) or, for tiny / unaligned operands, the generic kernel */
 #define TNPY_GEMM_GENERIC 1 /* generic shared-memory tiled DFMA kernel (any shape / stride)       */
 #define TNPY_GEMM_DMMA 2    /* force the TMA + mbarrier + FP64 tensor-core (DMMA) kernel           */
-#define TNPY_GEMM_OZAKI 3   /* FP64-accurate GEMM on the tcgen05 int8 tensor cores (Ozaki scheme) for large
-                               problems, DMMA / generic below its size threshold                       */
+#define TNPY_GEMM_OZAKI 3   /* same selection as AUTO, spelled out                                  */
+#define TNPY_GEMM_FP64 4    /* native FP64 arithmetic only: DMMA when TMA-describable, else generic; never the
+                               int8 tensor-core path                                                   */
 
 /* Canonical-gauge shortcuts for the contraction chains (`flags` arguments).  With tnpy's
  * upper-triangular MPOs (model/utils.py:25-28: row 0 / last column are the boundary vectors) and a
@@ -60,7 +68,7 @@ const char* tnpy_last_error(void);
 /* Number of kernels this library has launched from the calling process so far (for bench.py's
  * `gpu_launches`). */
 int64_t tnpy_launch_count(void);
-/* Override the GEMM selection used inside the fused chains (default TNPY_GEMM_AUTO). */
+/* Override the process-wide GEMM selection of the contraction chains (default TNPY_GEMM_AUTO). */
 int tnpy_set_gemm_algo(int algo);
 
 /* Force the DMMA tile configuration (benchmarking): -1 auto, 0 = 128x128, 1 = 128x64, 2 = 64x64. */
@@ -80,26 +88,24 @@ int tnpy_probe_fp64(int kind, int threads_per_block, int blocks_per_sm, int ilp,
 int tnpy_gemm_tn(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
                  int M, int N, int K, int accumulate, int algo, void* stream);
 
-/* ---- EXPERIMENT: the same GEMM in FP64 accuracy on the tcgen05 int8 tensor cores (Ozaki scheme: `slices`
- * error-free 7-bit slices per operand, exact int8 x int8 -> int32 slice products accumulated in TMEM,
- * FP64 recombination in the epilogue).  Not used by the chains unless asked for; reported separately.
- * phase: 0 = slice + multiply, 1 = slice only into the workspace, 2 = multiply from the workspace. */
+/* ---- the same GEMM in FP64 accuracy on the tcgen05 int8 tensor cores (Ozaki scheme: eight error-free 7-bit
+ * slices per operand column, the first `slices` of them multiplied as exact int8 x int8 -> int32 slice GEMMs with
+ * the accumulators in TMEM, FP64 recombination in the epilogue).  This is what the contraction chains run for their
+ * large products; the entry point exposes it for tests and benchmarks.
+ * phase: 0 = slice + multiply, 1 = slice only into the workspace, 2 = multiply from the workspace.
+ * Error (rigorous): |C - A^T B|[m][n] <= K e_S sa[m] sb[n], e_S = (S+2)/4 2^(-7S), sa / sb = the power-of-two column
+ * scales (> 2 max|column|); tnpy_ozaki_error_bound writes K e_S ||sa||_2 ||sb||_2 >= ||C - A^T B||_F for the
+ * operands last sliced into `workspace` to *bound_dev. */
 size_t tnpy_ozaki_workspace_bytes(int M, int N, int K, int slices);
-/* Number of 7-bit slices per operand used when TNPY_GEMM_OZAKI is selected for the chains: 8 (default,
- * componentwise error ~4e-16, same as DMMA), 7 (~2e-14) or 6 (~3e-12). */
+/* Slices used by chain products nobody declared a tolerance for: 8 (default, componentwise error ~4e-16, same as
+ * DMMA), 7 (~2e-14) or 6 (~3e-12).  tnpy_eig_lowest picks 7 by itself when its tolerance is >= 1e-10 and the
+ * rigorous bound of every product stays below 1 % of tol * ||A||. */
 int tnpy_set_ozaki_slices(int slices);
-/* Kernel generation of the tcgen05 GEMM: 2 (default) = CTA pair (cta_group::2), 256 x 128 tile, the slice
- * diagonals accumulated in two passes of four TMEM accumulators; 1 = one CTA per 128 x 64 tile, all eight
- * accumulators at once (operand-pipe bound, kept for comparison).  Env TNPY_OZAKI_VARIANT=1 selects 1. */
-int tnpy_set_ozaki_variant(int variant);
-/* Constant-operand scope for the tcgen05 path: between tnpy_ozaki_const_scope(1) and tnpy_ozaki_const_scope(0)
- * the caller vouches that the B operands of the chains' GEMMs (the environments L and R) do not change, so
- * their int8 slices are computed once and reused by every tnpy_heff_apply in the scope.  tnpy_eig_lowest
- * opens such a scope itself.  Scopes nest; leaving the outermost one drops the cached slices. */
-int tnpy_ozaki_const_scope(int on);
 int tnpy_ozaki_gemm_tn(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
                        int M, int N, int K, int slices, int accumulate, int phase, void* workspace,
                        size_t workspace_bytes, void* stream);
+int tnpy_ozaki_error_bound(int M, int N, int K, int slices, void* workspace, size_t workspace_bytes,
+                           double* bound_dev, void* stream);
 
 /* ---- a1: Environment.one_site_matvec(site).matvec(x)  (matrix_product_state.py:411-440) ----
  * y[m,q,s] = sum_{l,a,p,b,r} L[l,a,m] W[a,b,p,q] R[r,b,s] x[l,p,r]
@@ -108,6 +114,30 @@ size_t tnpy_heff_workspace_bytes(int l, int r, int wl, int wr, int d);
 int tnpy_heff_apply(const double* L, const double* W, const double* R, const double* x, double* y,
                     int l, int r, int wl, int wr, int d, int flags, void* workspace,
                     size_t workspace_bytes, void* stream);
+/* Prepared H_eff (what `Environment.one_site_matvec(site)` returns in the reference is an operator object that is
+ * applied 10-30 times per site, matrix_product_state.py:411-440): everything that depends only on (L, W, R) is
+ * computed once -- on the tcgen05 path the int8 slices of the environments -- into caller-owned `plan_memory`
+ * (tnpy_heff_plan_bytes), which must stay untouched while the handle lives, as must L, W and R.  The handle itself
+ * is a small host object; destroy it with tnpy_heff_plan_destroy.  W_host: host copy of W or NULL (the library then
+ * reads W back, synchronising the stream once, when that decides the mode).  algo: TNPY_GEMM_*.
+ * Modes (tnpy_heff_plan_mode): 0 = FP64 chain, 1 = chain with its large GEMMs on tcgen05, 2 = the direct path of the
+ * mixed-canonical gauge: with both identity flags and an MPO tensor whose non-zero blocks all have a = 0 or
+ * b = wr - 1,  y = sum_{b<wr-1} (W_0b x) R_b + sum_{a>0} L_a^T (W_{a,wr-1} x) + W_{0,wr-1} x  is two independent
+ * tcgen05 GEMMs whose x-side operands are mixed and sliced straight from x -- no FP64 intermediate exists.
+ * tnpy_heff_plan_apply: y = H_eff x; slices = 0 (default), 6, 7 or 8; workspace: tnpy_heff_workspace_bytes().
+ * tnpy_heff_plan_error_bound: the largest rigorous Frobenius-norm bound of any int8 product issued through the
+ * plan so far (0 on the FP64 chain), copied device to device. */
+typedef struct tnpy_heff_plan tnpy_heff_plan;
+size_t tnpy_heff_plan_bytes(int l, int r, int wl, int wr, int d);
+int tnpy_heff_plan_create(tnpy_heff_plan** handle, const double* L, const double* W, const double* R,
+                          const double* W_host, int l, int r, int wl, int wr, int d, int flags, int algo,
+                          void* plan_memory, size_t plan_bytes, void* stream);
+int tnpy_heff_plan_mode(const tnpy_heff_plan* handle);
+int tnpy_heff_plan_apply(const tnpy_heff_plan* handle, const double* x, double* y, int slices, void* workspace,
+                         size_t workspace_bytes, void* stream);
+int tnpy_heff_plan_error_bound(const tnpy_heff_plan* handle, double* bound_dev_out, void* stream);
+int tnpy_heff_plan_destroy(tnpy_heff_plan* handle);
+
 /* max_ij |E[i, channel, j] - delta_ij| of an environment E (dim, w, dim), written to device memory.
  * Workspace: 8 KB. */
 int tnpy_identity_defect(const double* E, int dim, int w, int channel, double* defect_dev,
@@ -120,6 +150,11 @@ int tnpy_identity_defect(const double* E, int dim, int w, int channel, double* d
 int tnpy_heff_apply_rows(const double* L_rows, const double* W, const double* R, const double* x,
                          double* y_rows, int l, int l_rows, int r, int wl, int wr, int d,
                          void* workspace, size_t workspace_bytes, void* stream);
+/* Prepared form of the row block: same handle type and tnpy_heff_plan_apply (x full (l, d, r) in, y_rows (l_rows, d, r)
+ * out); plan memory tnpy_heff_plan_bytes() of the full problem is enough. */
+int tnpy_heff_plan_create_rows(tnpy_heff_plan** handle, const double* L_rows, const double* W, const double* R,
+                               int l, int l_rows, int r, int wl, int wr, int d, int algo, void* plan_memory,
+                               size_t plan_bytes, void* stream);
 
 /* ---- a7: Environment.update_left / update_right  (matrix_product_state.py:296-336) ---------
  * left : Lout[r,b,s] = sum L[l,a,m] A[l,p,r] W[a,b,p,q] A[m,q,s]      Lout: (r, wr, r)
@@ -164,8 +199,10 @@ int tnpy_multi_axpy(const double* V, int64_t ldv, int m, const double* h, double
  * psi: in = start vector v0, out = normalised eigenvector, N = l*d*r doubles.
  * Stops when ||H x - theta x|| <= tol * max|Ritz| (primme's rule); tol <= 0 means 1e4 * eps.
  * stats_host (>= 8 doubles, host memory): [0] = theta, [1] = residual norm, [2] = matvec count,
- * [3] = restart count, [4] = converged (1/0), [5] = max |Ritz value| (the ||A|| estimate).  The call synchronises the stream before returning (one host read-back
- * per convergence check, never per matvec).
+ * [3] = restart count, [4] = converged (1/0), [5] = max |Ritz value| (the ||A|| estimate), [6] = largest rigorous
+ * error bound of an int8 product during the solve (0 on the FP64 chain), [7] = 10 * plan mode + slices in use at the
+ * end.  The call synchronises the stream before returning (one host read-back per convergence check, never per
+ * matvec).
  * Workspace: tnpy_eig_workspace_bytes(). */
 size_t tnpy_eig_workspace_bytes(int l, int r, int wl, int wr, int d, int ncv);
 int tnpy_eig_lowest(const double* L, const double* W, const double* R, double* psi,

@@ -17,6 +17,14 @@ Fixtures (float64, NumPy .npz):
                       BASELINE.json configs[0] (the reference's README example) run to convergence by the oracle at
                       tol 1e-8 from random_mps(seed=0): per-sweep energies (the initial state is regenerated from the
                       seed by the test, it is not stored)
+  config2_thirring_n100_chi256.npz
+                      BASELINE.json configs[1] (scripts/thirring_fdmrg.py's model -- delta 0.5, ma 1.0, penalty 100,
+                      s_target 0 -- at n=100, chi=256): four sweeps from random_mps(seed=0) with every local solve
+                      converged to 1e-12 ||A|| (with the penalty term ||A|| ~ 2e3, so the script's own tol of 1e-8
+                      leaves 1e-5 of slack per local solve and two solvers' trajectories cannot be compared):
+                      per-sweep energies, every bond spectrum of the last two sweeps, the <Sz_i> profile and the
+                      squared norm of the final state.  About an hour of host BLAS; generate it alone with
+                      ``python tests/golden/make_golden.py config2``.
 """
 import os
 import sys
@@ -67,7 +75,45 @@ def dmrg_case(mpo, n, chi, seed):
     return out
 
 
+def sz_profile(mps):
+    """<Sz_i> / <psi|psi> for every site of an 'lpr' MPS (left / right overlap environments)."""
+    n = len(mps)
+    a3 = [oracle._as3(a, i, n) for i, a in enumerate(mps)]
+    left = [np.ones((1, 1))]
+    for a in a3:
+        left.append(np.einsum("lm,lpr,mps->rs", left[-1], a, a, optimize=True))
+    right = [np.ones((1, 1))] * (n + 1)
+    for i in range(n - 1, -1, -1):
+        right[i] = np.einsum("rs,lpr,mps->lm", right[i + 1], a3[i], a3[i], optimize=True)
+    sz = np.diag([0.5, -0.5])
+    norm2 = float(left[-1][0, 0])
+    prof = [float(np.einsum("lm,lpr,pq,mqs,rs->", left[i], a3[i], sz, a3[i], right[i + 1], optimize=True)) / norm2
+            for i in range(n)]
+    return np.array(prof), norm2
+
+
+def config2_case(n=100, chi=256, tol=1e-12, sweeps=4, seed=0):
+    mpo = oracle.thirring_mpo(n, 0.5, 1.0, 100.0, 0)
+    f = oracle.FiniteDMRG(mpo, chi, mps=oracle.random_mps(n, chi, 2, seed=seed))
+    energies, matvecs = [], []
+    for k in range(sweeps):
+        m0 = f.n_matvec
+        energies.append(f.sweep(oracle.RIGHTWARD if k % 2 == 0 else oracle.LEFTWARD, tol=tol))
+        matvecs.append(f.n_matvec - m0)
+        print("config2 sweep", k + 1, energies[-1], matvecs[-1], flush=True)
+    prof, norm2 = sz_profile(f.mps)
+    out = {"energies": np.array(energies), "matvecs": np.array(matvecs), "n": np.array(n), "chi": np.array(chi),
+           "tol": np.array(tol), "seed": np.array(seed), "delta": np.array(0.5), "ma": np.array(1.0),
+           "penalty": np.array(100.0), "s_target": np.array(0), "sz_profile": prof, "norm2": np.array(norm2)}
+    for bond, s in f.bond_singular_values.items():
+        out[f"spectrum_{bond}"] = np.asarray(s)
+    return out
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "config2":
+        np.savez_compressed(os.path.join(HERE, "config2_thirring_n100_chi256.npz"), **config2_case())
+        return
     heff, env = heff_and_env_cases()
     np.savez_compressed(os.path.join(HERE, "heff_cases.npz"), **heff)
     np.savez_compressed(os.path.join(HERE, "env_cases.npz"), **env)

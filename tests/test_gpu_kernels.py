@@ -346,6 +346,45 @@ def test_heff_properties_at_bench_size(cu, chi, w):
     assert float((rows - hx[lo:hi]).abs().max()) < 1e-12 * scale
 
 
+def _bench_size_operands(chi, w, canonical):
+    """Seeded operands at a BASELINE bulk-site size with the model's real MPO tensor (XXZ for w = 5, Thirring
+    with the script's penalty for w = 6); ``canonical`` plants the identity channels of the mixed-canonical gauge."""
+    rng = np.random.default_rng(7 * chi + w)
+    W = np.ascontiguousarray(oracle.xxz_mpo(4, 0.5)[1] if w == 5 else oracle.thirring_mpo(4, 0.5, 1.0, 100.0, 0)[1])
+    assert W.shape[0] == w
+    L, R = rng.standard_normal((chi, w, chi)), rng.standard_normal((chi, w, chi))
+    if canonical:
+        L[:, 0, :] = np.eye(chi)
+        R[:, w - 1, :] = np.eye(chi)
+    x = rng.standard_normal((chi, 2, chi))
+    return L, W, R, x
+
+
+@pytest.mark.parametrize("chi,w", [(2048, 5), (1024, 6)])
+@pytest.mark.parametrize("flags", [0, 3])
+def test_chains_match_oracle_at_bench_size(cu, chi, w, flags):
+    """BASELINE configs[2] (chi=2048, w=5) and configs[3]'s bond (chi=1024, here with the w=6 Thirring tensor):
+    the H_eff matvec and both environment updates against the CPU oracle itself (a few seconds of host BLAS per
+    case), on the native FP64 DMMA path and on the tcgen05 path, general operands (flags 0) and the
+    mixed-canonical gauge with both identity channels flagged (flags 3).  Tolerance 1e-12 max|y|."""
+    L, W, R, x = _bench_size_operands(chi, w, canonical=bool(flags))
+    want_y = oracle.heff_apply(L, W, R, x)
+    want_l = oracle.env_update_left(L, x, W)
+    want_r = oracle.env_update_right(R, x, W)
+    dL, dW, dR, dx = dev(L), dev(W), dev(R), dev(x)
+    for algo in (cu.GEMM_FP64, cu.GEMM_OZAKI):
+        cu.set_gemm_algo(algo)
+        try:
+            got_y = cu.heff_apply(dL, dW, dR, dx, flags=flags).cpu().numpy()
+            got_l = cu.env_update_left(dL, dx, dW, flags=flags & cu.LEFT_IDENTITY).cpu().numpy()
+            got_r = cu.env_update_right(dR, dx, dW, flags=flags & cu.RIGHT_IDENTITY).cpu().numpy()
+        finally:
+            cu.set_gemm_algo(cu.GEMM_AUTO)
+        for got, want, what in ((got_y, want_y, "heff"), (got_l, want_l, "env_left"), (got_r, want_r, "env_right")):
+            err = np.abs(got - want).max() / np.abs(want).max()
+            assert err < 1e-12, (what, algo, err)
+
+
 def test_env_update_identity_channel_at_bench_size(cu):
     """Left-canonical site tensor + identity incoming channel => identity outgoing channel
     (the canonical-gauge invariant of SURVEY 8c) at chi = 1024."""
@@ -482,78 +521,117 @@ def test_ozaki_handles_zero_columns_and_ragged_k(cu):
 
 @pytest.mark.parametrize("chi,w", [(1024, 5), (1280, 6)])
 def test_chain_with_ozaki_gemm(cu, chi, w):
-    """The matvec / environment chains with the tcgen05 path selected agree with the DMMA path."""
+    """The matvec / environment chains on the default selection (large GEMMs on the tcgen05 path) agree with the
+    native FP64 chains."""
     d = 2
     g = torch.Generator(device="cuda").manual_seed(chi)
     rnd = lambda *s: torch.randn(s, generator=g, dtype=torch.float64, device="cuda")  # noqa: E731
     L, R, W, x = rnd(chi, w, chi), rnd(chi, w, chi), rnd(w, w, d, d), rnd(chi, d, chi)
-    ref = cu.heff_apply(L, W, R, x)
-    ref_env = cu.env_update_left(L, x, W)
-    cu.set_gemm_algo(cu.GEMM_OZAKI)
+    n0 = cu.launch_count()
+    got = cu.heff_apply(L, W, R, x)
+    launches_default = cu.launch_count() - n0
+    got_env = cu.env_update_left(L, x, W)
+    got_env_r = cu.env_update_right(R, x, W)
+    cu.set_gemm_algo(cu.GEMM_FP64)
     try:
-        got = cu.heff_apply(L, W, R, x)
-        got_env = cu.env_update_left(L, x, W)
+        n0 = cu.launch_count()
+        ref = cu.heff_apply(L, W, R, x)
+        launches_fp64 = cu.launch_count() - n0
+        ref_env = cu.env_update_left(L, x, W)
+        ref_env_r = cu.env_update_right(R, x, W)
     finally:
         cu.set_gemm_algo(cu.GEMM_AUTO)
+    assert launches_default > launches_fp64  # the default really took the sliced path
     assert float((got - ref).abs().max() / ref.abs().max()) < 1e-13
     assert float((got_env - ref_env).abs().max() / ref_env.abs().max()) < 1e-13
+    assert float((got_env_r - ref_env_r).abs().max() / ref_env_r.abs().max()) < 1e-13
 
 
-@pytest.mark.parametrize("variant", [1, 2])
 @pytest.mark.parametrize("m,n,k", [(256, 128, 64), (700, 300, 1000), (1024, 1024, 1024), (520, 390, 4160), (4096, 2048, 640)])
-def test_ozaki_variants_agree(cu, variant, m, n, k):
-    """Both kernel generations (single CTA 128x64 / CTA pair 256x128 in two passes, with and without the
-    K-split of the last wave) are exact slice GEMMs: they agree with each other to rounding of the recombination
-    and with FP64 at the DMMA level.  (1024^3 and 520x390x4160 exercise the tail split, 4096x2048x640 a full wave.)"""
+def test_ozaki_gemm_shapes_slices_and_bound(cu, m, n, k):
+    """The CTA-pair kernel with and without the K-split of its last wave (1024^3 and 520x390x4160 exercise the
+    split, 4096x2048x640 a full wave): exact slice GEMMs, so the result agrees with FP64 at the DMMA level with 8
+    slices, degrades by 2^7 per dropped slice, and always stays inside the rigorous bound the library reports."""
     g = torch.Generator(device="cuda").manual_seed(7 * m + n + k)
     a = torch.randn((k, m), generator=g, dtype=torch.float64, device="cuda")
     b = torch.randn((k, n), generator=g, dtype=torch.float64, device="cuda")
     ref = a.t() @ b
     bound = a.abs().t() @ b.abs()
-    cu.set_ozaki_variant(variant)
-    try:
-        for s, tol in ((8, 4e-15), (7, 2e-13), (6, 3e-11)):
-            got = cu.ozaki_gemm_tn(a, b, slices=s)
-            assert float(((got - ref).abs() / bound).max()) < tol
-        c0 = torch.randn((m, n), generator=g, dtype=torch.float64, device="cuda")
-        acc = cu.ozaki_gemm_tn(a, b, out=c0.clone(), slices=8, accumulate=True)
-        assert float(((acc - (c0 + ref)).abs() / (bound + c0.abs())).max()) < 4e-15
-    finally:
-        cu.set_ozaki_variant(2)
+    for s, tol in ((8, 4e-15), (7, 2e-13), (6, 3e-11)):
+        got = cu.ozaki_gemm_tn(a, b, slices=s)
+        assert float(((got - ref).abs() / bound).max()) < tol
+        rigorous = cu.ozaki_error_bound(m, n, k, slices=s)
+        err = float((got - ref).norm())
+        assert err <= rigorous + 1e-14 * float(ref.norm()), (s, err, rigorous)  # + the FP64 rounding of ref itself
+        assert rigorous < 1e-12 * 128.0 ** (8 - s) * float(bound.norm())  # and it is not vacuous
+    c0 = torch.randn((m, n), generator=g, dtype=torch.float64, device="cuda")
+    acc = cu.ozaki_gemm_tn(a, b, out=c0.clone(), slices=8, accumulate=True)
+    assert float(((acc - (c0 + ref)).abs() / (bound + c0.abs())).max()) < 4e-15
 
 
-def test_ozaki_const_scope_reuses_and_drops_slices(cu):
-    """Inside a constant-operand scope the environments are sliced once; results are bit-identical to the
-    re-sliced path, and a changed environment is picked up again after the scope ends."""
+def test_heff_plan_slices_environments_once(cu):
+    """A prepared H_eff slices the environments at creation; every application then only slices x-side operands.
+    Results are bit-identical to the one-shot entry point, and the plan notices nothing it should not (a changed
+    environment needs a new plan -- HeffOperator tracks that through Environment.operand_version)."""
     chi, w, d = 1024, 5, 2
     g = torch.Generator(device="cuda").manual_seed(3)
     rnd = lambda *s: torch.randn(s, generator=g, dtype=torch.float64, device="cuda")  # noqa: E731
     L, R, W, x = rnd(chi, w, chi), rnd(chi, w, chi), rnd(w, w, d, d), rnd(chi, d, chi)
-    cu.set_gemm_algo(cu.GEMM_OZAKI)
-    try:
-        plain = cu.heff_apply(L, W, R, x).clone()
-        cu.ozaki_const_scope(True)
-        try:
-            first = cu.heff_apply(L, W, R, x).clone()
-            n0 = cu.launch_count()
-            second = cu.heff_apply(L, W, R, 2.0 * x).clone()
-            launches_cached = cu.launch_count() - n0
-        finally:
-            cu.ozaki_const_scope(False)
-        n0 = cu.launch_count()
-        cu.heff_apply(L, W, R, x)
-        launches_plain = cu.launch_count() - n0
-        assert torch.equal(first, plain)
-        assert float((second - 2.0 * plain).abs().max() / plain.abs().max()) < 1e-14
-        assert launches_cached == launches_plain - 4  # colmax + slice kernels of L and of R skipped
-        L2 = L + 1.0
-        ref = cu.heff_apply(L2, W, R, x)
-        cu.set_gemm_algo(cu.GEMM_AUTO)
-        dmma = cu.heff_apply(L2, W, R, x)
-        assert float((ref - dmma).abs().max() / dmma.abs().max()) < 1e-13
-    finally:
-        cu.set_gemm_algo(cu.GEMM_AUTO)
+    plain = cu.heff_apply(L, W, R, x).clone()
+    n0 = cu.launch_count()
+    cu.heff_apply(L, W, R, x)
+    launches_plain = cu.launch_count() - n0
+    plan = cu.HeffPlan(L, W, R, chi, chi)
+    assert plan.mode == cu.HEFF_OZ_CHAIN  # a dense random W has interior blocks: the chain, on tcgen05
+    first = plan.apply(x).clone()
+    n0 = cu.launch_count()
+    second = plan.apply(2.0 * x).clone()
+    launches_plan = cu.launch_count() - n0
+    assert torch.equal(first, plain)
+    assert float((second - 2.0 * plain).abs().max() / plain.abs().max()) < 1e-14
+    assert launches_plan == launches_plain - 4  # colmax + slice kernels of L and of R are not repeated
+    assert 0.0 < plan.error_bound() < 1e-9 * float(plain.norm())
+    fp64 = cu.HeffPlan(L, W, R, chi, chi, algo=cu.GEMM_FP64)
+    assert fp64.mode == cu.HEFF_FP64_CHAIN and fp64.error_bound() == 0.0
+    ref = fp64.apply(x)
+    assert float((first - ref).abs().max() / ref.abs().max()) < 1e-13
+    plan.close(); fp64.close()
 
+
+@pytest.mark.parametrize("l,r,model", [(1024, 1024, "xxz"), (1200, 1000, "xxz"), (1000, 1204, "rh"), (1024, 1024, "thirring")])
+def test_direct_path_in_canonical_gauge(cu, l, r, model):
+    """Mixed-canonical gauge + an MPO tensor without interior-to-interior blocks => the direct path (two independent
+    tcgen05 GEMMs on operands premixed and sliced from x, no FP64 intermediate).  Checked against the oracle and the
+    FP64 chain, with 8 and 7 slices, on aligned and ragged bonds; Thirring with its penalty channel (W[3,3] = I)
+    must be sent to the chain instead."""
+    mpo = {"xxz": oracle.xxz_mpo(4, 0.5), "rh": oracle.random_heisenberg_mpo(4, 1.0, seed=2022),
+           "thirring": oracle.thirring_mpo(4, 0.5, 1.0, 100.0, 0)}[model]
+    W = np.ascontiguousarray(mpo[1])
+    w, d = W.shape[0], W.shape[2]
+    rng = np.random.default_rng(l + 3 * r)
+    L, R = rng.standard_normal((l, w, l)), rng.standard_normal((r, w, r))
+    L[:, 0, :] = np.eye(l)
+    R[:, w - 1, :] = np.eye(r)
+    x = rng.standard_normal((l, d, r))
+    want = oracle.heff_apply(L, W, R, x)
+    dL, dW, dR, dx = dev(L), dev(W), dev(R), dev(x)
+    plan = cu.HeffPlan(dL, dW, dR, l, r, flags=3, w_host=W)
+    assert plan.mode == (cu.HEFF_OZ_CHAIN if model == "thirring" else cu.HEFF_OZ_DIRECT)
+    got8 = plan.apply(dx).cpu().numpy()
+    scale = np.abs(want).max()
+    assert np.abs(got8 - want).max() < 1e-12 * scale
+    b8 = plan.error_bound()
+    got7 = plan.apply(dx, slices=7).cpu().numpy()
+    assert np.abs(got7 - want).max() < 1e-10 * scale
+    assert np.linalg.norm(got8 - want) <= b8 + 1e-13 * np.linalg.norm(want)
+    assert np.linalg.norm(got7 - want) <= plan.error_bound() + 1e-13 * np.linalg.norm(want)
+    # W_host not given: the library reads W back itself and reaches the same decision
+    plan2 = cu.HeffPlan(dL, dW, dR, l, r, flags=3)
+    assert plan2.mode == plan.mode and torch.equal(plan2.apply(dx), plan.apply(dx))
+    chain = cu.HeffPlan(dL, dW, dR, l, r, flags=3, algo=cu.GEMM_FP64)
+    assert np.abs(chain.apply(dx).cpu().numpy() - got8).max() < 1e-12 * scale
+    for p_ in (plan, plan2, chain):
+        p_.close()
 
 
 # ---- a8/a9 as an orthogonal split: tnpy_qr_split (Cholesky-QR twice, verified on the device) ---------------

@@ -14,7 +14,7 @@ from typing import Optional
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "libtnpy_cuda.so"
 
-GEMM_AUTO, GEMM_GENERIC, GEMM_DMMA, GEMM_OZAKI = 0, 1, 2, 3
+GEMM_AUTO, GEMM_GENERIC, GEMM_DMMA, GEMM_OZAKI, GEMM_FP64 = 0, 1, 2, 3, 4
 LEFT_IDENTITY, RIGHT_IDENTITY = 1, 2
 ENOCONV = -4
 
@@ -31,13 +31,24 @@ SIGNATURES = {
     "tnpy_gemm_tn": (c_int, [_PD, c_int64, _PD, c_int64, _PD, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "tnpy_ozaki_workspace_bytes": (c_size_t, [c_int] * 4),
     "tnpy_set_ozaki_slices": (c_int, [c_int]),
-    "tnpy_set_ozaki_variant": (c_int, [c_int]),
-    "tnpy_ozaki_const_scope": (c_int, [c_int]),
     "tnpy_ozaki_gemm_tn": (
         c_int,
         [_PD, c_int64, _PD, c_int64, _PD, c_int64] + [c_int] * 6 + [c_void_p, c_size_t, c_void_p],
     ),
+    "tnpy_ozaki_error_bound": (c_int, [c_int] * 4 + [c_void_p, c_size_t, _PD, c_void_p]),
     "tnpy_heff_workspace_bytes": (c_size_t, [c_int] * 5),
+    "tnpy_heff_plan_bytes": (c_size_t, [c_int] * 5),
+    "tnpy_heff_plan_create": (
+        c_int,
+        [ctypes.POINTER(c_void_p), _PD, _PD, _PD, ctypes.POINTER(c_double)] + [c_int] * 7 + [c_void_p, c_size_t, c_void_p],
+    ),
+    "tnpy_heff_plan_create_rows": (
+        c_int, [ctypes.POINTER(c_void_p), _PD, _PD, _PD] + [c_int] * 7 + [c_void_p, c_size_t, c_void_p],
+    ),
+    "tnpy_heff_plan_mode": (c_int, [c_void_p]),
+    "tnpy_heff_plan_apply": (c_int, [c_void_p, _PD, _PD, c_int, c_void_p, c_size_t, c_void_p]),
+    "tnpy_heff_plan_error_bound": (c_int, [c_void_p, _PD, c_void_p]),
+    "tnpy_heff_plan_destroy": (c_int, [c_void_p]),
     "tnpy_heff_apply": (c_int, [_PD, _PD, _PD, _PD, _PD] + [c_int] * 6 + [c_void_p, c_size_t, c_void_p]),
     "tnpy_identity_defect": (c_int, [_PD, c_int, c_int, c_int, _PD, c_void_p, c_size_t, c_void_p]),
     "tnpy_heff_apply_rows": (c_int, [_PD, _PD, _PD, _PD, _PD] + [c_int] * 6 + [c_void_p, c_size_t, c_void_p]),
@@ -106,7 +117,7 @@ def load() -> ctypes.CDLL:
 
     choice = os.environ.get("TNPY_GEMM_ALGO", "").lower()
     if choice:
-        table = {"auto": GEMM_AUTO, "generic": GEMM_GENERIC, "dmma": GEMM_DMMA, "ozaki": GEMM_OZAKI}
+        table = {"auto": GEMM_AUTO, "generic": GEMM_GENERIC, "dmma": GEMM_DMMA, "ozaki": GEMM_OZAKI, "fp64": GEMM_FP64}
         if choice not in table:
             raise RuntimeError(f"TNPY_GEMM_ALGO={choice!r}: expected one of {sorted(table)}")
         lib.tnpy_set_gemm_algo(table[choice])
@@ -128,8 +139,9 @@ def launch_count() -> int:
 
 
 def set_gemm_algo(algo: int) -> None:
-    """Select the GEMM used inside the chains: GEMM_AUTO (DMMA / generic), GEMM_OZAKI (tcgen05 int8,
-    FP64-accurate) ...  Also settable through the environment: TNPY_GEMM_ALGO=ozaki|dmma|generic|auto."""
+    """Process-wide GEMM selection of the contraction chains: GEMM_AUTO (default: large products on the tcgen05
+    int8 path, FP64-accurate; the rest DMMA / generic), GEMM_FP64 (native FP64 arithmetic only), GEMM_DMMA /
+    GEMM_GENERIC (force one kernel).  Also settable through the environment: TNPY_GEMM_ALGO=fp64|dmma|generic|auto."""
     check(load().tnpy_set_gemm_algo(algo), "tnpy_set_gemm_algo")
 
 
@@ -137,15 +149,7 @@ def set_ozaki_slices(slices: int) -> None:
     check(load().tnpy_set_ozaki_slices(int(slices)), "tnpy_set_ozaki_slices")
 
 
-def ozaki_const_scope(on: bool) -> None:
-    """Open / close a scope in which the environments passed to the chains are constant (tcgen05 path: their
-    int8 slices are then computed once).  ``tnpy_eig_lowest`` does this itself."""
-    check(load().tnpy_ozaki_const_scope(int(bool(on))), "tnpy_ozaki_const_scope")
-
-
-def set_ozaki_variant(variant: int) -> None:
-    """2 (default): CTA-pair 256x128 two-pass tcgen05 kernel; 1: single-CTA 128x64 kernel."""
-    check(load().tnpy_set_ozaki_variant(int(variant)), "tnpy_set_ozaki_variant")
+HEFF_FP64_CHAIN, HEFF_OZ_CHAIN, HEFF_OZ_DIRECT = 0, 1, 2
 
 
 # ------------------------------------------------------------------------------------------------
@@ -224,6 +228,89 @@ def ozaki_gemm_tn(a, b, out=None, slices: int = 8, accumulate: bool = False, pha
                                 int(accumulate), int(phase), _ptr(ws), nbytes, _stream())
     check(rc, "tnpy_ozaki_gemm_tn")
     return out
+
+
+def ozaki_error_bound(m: int, n: int, k: int, slices: int = 8) -> float:
+    """Rigorous bound on ||C - A^T B||_F for the operands the last ``ozaki_gemm_tn`` call sliced (same m, n, k)."""
+    import torch
+
+    lib = load()
+    nbytes = lib.tnpy_ozaki_workspace_bytes(m, n, k, slices)
+    ws = _scratch.get(nbytes)
+    out = torch.empty((), dtype=torch.float64, device="cuda")
+    check(lib.tnpy_ozaki_error_bound(m, n, k, int(slices), _ptr(ws), nbytes, _ptr(out), _stream()), "tnpy_ozaki_error_bound")
+    return float(out.item())
+
+
+class HeffPlan:
+    """Prepared H_eff of one site (``tnpy_heff_plan_*``): everything that depends only on (L, W, R) -- on the tcgen05
+    path the int8 slices of the environments -- is computed once into a torch-owned buffer; ``apply`` then runs one
+    matvec.  The plan keeps L, W, R alive and must not outlive changes to them."""
+
+    def __init__(self, L, W, R, l: int, r: int, flags: int = 0, algo: int = GEMM_AUTO, w_host=None, l_rows=None):
+        """``l_rows``: L holds only that many bra rows, (l, wl, l_rows) contiguous -- one rank's block of the
+        chi-sharded matvec; ``apply`` then maps the full x (l, d, r) to y_rows (l_rows, d, r)."""
+        import numpy as np
+        import torch
+
+        _need_cuda(L, W, R)
+        self._lib = load()
+        self._keep = (L, W, R)
+        wl, wr, d = W.shape[0], W.shape[1], W.shape[2]
+        self.dims = (l, r, wl, wr, d)
+        self.l_rows = l if l_rows is None else int(l_rows)
+        nbytes = self._lib.tnpy_heff_plan_bytes(l, r, wl, wr, d)
+        self._memory = torch.empty(int(nbytes), dtype=torch.uint8, device=W.device)
+        self._ws_bytes = self._lib.tnpy_heff_workspace_bytes(l, r, wl, wr, d)
+        handle = c_void_p()
+        if l_rows is not None:
+            rc = self._lib.tnpy_heff_plan_create_rows(ctypes.byref(handle), _ptr(L), _ptr(W), _ptr(R), l, self.l_rows, r, wl,
+                                                      wr, d, int(algo), _ptr(self._memory), nbytes, _stream())
+        else:
+            wh = None
+            if w_host is not None:
+                self._w_host = np.ascontiguousarray(w_host, dtype=np.float64)
+                wh = self._w_host.ctypes.data_as(ctypes.POINTER(c_double))
+            rc = self._lib.tnpy_heff_plan_create(ctypes.byref(handle), _ptr(L), _ptr(W), _ptr(R), wh, l, r, wl, wr, d,
+                                                 int(flags), int(algo), _ptr(self._memory), nbytes, _stream())
+        check(rc, "tnpy_heff_plan_create")
+        self._handle = handle
+
+    @property
+    def mode(self) -> int:
+        return int(self._lib.tnpy_heff_plan_mode(self._handle))
+
+    def apply(self, x, out=None, slices: int = 0):
+        import torch
+
+        _need_cuda(x, out)
+        l, r, wl, wr, d = self.dims
+        if x.numel() != l * d * r:
+            raise ValueError(f"HeffPlan.apply: x has {x.numel()} elements, the site has {l * d * r}")
+        if out is None:
+            out = torch.empty((self.l_rows, d, r), dtype=torch.float64, device=x.device)
+        ws = _scratch.get(self._ws_bytes)
+        rc = self._lib.tnpy_heff_plan_apply(self._handle, _ptr(x), _ptr(out), int(slices), _ptr(ws), self._ws_bytes, _stream())
+        check(rc, "tnpy_heff_plan_apply")
+        return out
+
+    def error_bound(self) -> float:
+        import torch
+
+        out = torch.empty((), dtype=torch.float64, device="cuda")
+        check(self._lib.tnpy_heff_plan_error_bound(self._handle, _ptr(out), _stream()), "tnpy_heff_plan_error_bound")
+        return float(out.item())
+
+    def close(self):
+        if getattr(self, "_handle", None) is not None:
+            self._lib.tnpy_heff_plan_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def _dims(x_shape, w_shape):
@@ -347,7 +434,8 @@ def eig_lowest(L, W, R, psi, tol: float = 1e-8, max_matvec: int = 1000, ncv: int
     check(rc, "tnpy_eig_lowest", allow_noconv=True)
     return {
         "theta": stats[0], "resid": stats[1], "n_matvec": int(stats[2]), "n_restart": int(stats[3]),
-        "converged": bool(stats[4]), "anorm": stats[5],
+        "converged": bool(stats[4]), "anorm": stats[5], "int8_error_bound": stats[6],
+        "heff_mode": int(stats[7]) // 10, "slices": int(stats[7]) % 10,
     }
 
 

@@ -3,6 +3,10 @@
 // grid sized as a multiple of the SM count, warp-shuffle + shared-memory block reductions, and a
 // deterministic fixed-order final reduction by the last block to finish (no floating-point atomics,
 // so results are bit-reproducible run to run).
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "common.cuh"
 
 namespace tnpy {
@@ -16,16 +20,24 @@ struct RedScratch {
   unsigned int* counter;  // last-block-done ticket
 };
 
-static RedScratch& red_scratch() {
-  static RedScratch s{nullptr, nullptr};
-  if (!s.partials) {
-    void* p = nullptr;
-    if (cudaMalloc(&p, sizeof(double) * kMaxMulti * kMaxRedBlocks + 256) == cudaSuccess) {
-      s.partials = static_cast<double*>(p);
-      s.counter = reinterpret_cast<unsigned int*>(s.partials + (size_t)kMaxMulti * kMaxRedBlocks);
-      cudaMemset(s.counter, 0, 256);
-    }
+// The BLAS-1 entry points take no workspace, so the partial sums and the ticket counter of their two-stage
+// reductions live in a library-owned scratch (0.6 MB), one per (device, stream): kernels of different streams never
+// share partials or tickets, and a second device gets its own allocation.
+static RedScratch red_scratch(cudaStream_t stream) {
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, RedScratch> table;
+  std::lock_guard<std::mutex> lock(mu);
+  const auto key = std::make_pair(current_device(), stream);
+  auto it = table.find(key);
+  if (it != table.end()) return it->second;
+  RedScratch s{nullptr, nullptr};
+  void* p = nullptr;
+  if (cudaMalloc(&p, sizeof(double) * kMaxMulti * kMaxRedBlocks + 256) == cudaSuccess) {
+    s.partials = static_cast<double*>(p);
+    s.counter = reinterpret_cast<unsigned int*>(s.partials + (size_t)kMaxMulti * kMaxRedBlocks);
+    if (cudaMemset(s.counter, 0, 256) != cudaSuccess) s = RedScratch{nullptr, nullptr};
   }
+  if (s.partials) table.emplace(key, s);
   return s;
 }
 
@@ -131,7 +143,7 @@ __global__ void __launch_bounds__(kRedThreads) multi_dot_scalar_kernel(const dou
 int multi_dot(const double* V, int64_t ldv, int m, const double* w, int64_t n, double* h, int mode,
               cudaStream_t stream, const int* skip) {
   TNPY_CHECK_ARG(V && w && h && n > 0 && m > 0 && m <= kMaxMulti, "bad argument");
-  RedScratch& s = red_scratch();
+  const RedScratch s = red_scratch(stream);
   if (!s.partials) {
     set_error("multi_dot: could not allocate reduction scratch");
     return TNPY_ECUDA;
@@ -215,7 +227,7 @@ __global__ void __launch_bounds__(kRedThreads) multi_axpy_kernel(const double* _
 int multi_axpy(const double* V, int64_t ldv, int m, const double* h, double* w, int64_t n, double* nrm_out,
                cudaStream_t stream, const int* skip) {
   TNPY_CHECK_ARG(V && h && w && n > 0 && m > 0 && m <= kMaxMulti, "bad argument");
-  RedScratch& s = red_scratch();
+  const RedScratch s = red_scratch(stream);
   if (!s.partials) {
     set_error("multi_axpy: could not allocate reduction scratch");
     return TNPY_ECUDA;

@@ -50,7 +50,15 @@ inline void count_launch(int n = 1) { g_launch_count.fetch_add(n, std::memory_or
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
-int sm_count();
+int sm_count();  // of the current device
+int current_device();
+// true exactly once per (key, current device): one-time per-device setup such as cudaFuncSetAttribute
+bool first_time_on_device(const void* key);
+// pinned host scratch of the calling thread (>= 64 bytes, lives as long as the thread): status read-backs
+void* thread_pinned_scratch();
+
+template <typename Kernel>
+inline int set_max_dynamic_smem(Kernel kernel, int bytes);
 
 // Bump allocator over a caller-supplied workspace (256-byte aligned slices).
 struct Workspace {
@@ -86,8 +94,20 @@ int gemm_tn(const double* A, int64_t lda, const double* B, int64_t ldb, GemmOut 
 inline GemmOut plain_out(double* C, int64_t ldc, int M) { return GemmOut{C, ldc, 0, M}; }
 int current_gemm_algo();
 
-// device constant 1.0 used for NULL (unit) environments
+// device constant 1.0 used for NULL (unit) environments (per device)
 const double* device_one();
+
+template <typename Kernel>
+inline int set_max_dynamic_smem(Kernel kernel, int bytes) {
+  if (first_time_on_device(reinterpret_cast<const void*>(kernel))) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(MaxDynamicSharedMemorySize = %d) failed: %s", bytes, cudaGetErrorString(e));
+      return TNPY_ECUDA;
+    }
+  }
+  return TNPY_OK;
+}
 
 #ifdef __CUDACC__
 __device__ __forceinline__ double warp_sum(double v) {

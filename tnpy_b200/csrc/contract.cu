@@ -10,9 +10,13 @@
 //   * the W-mix reads and writes with the long bond index fastest (fully coalesced, any w / d),
 //   * the second GEMM's output rows are scattered straight into the reference layout through the
 //     kernel's split-M row map (no transpose pass).
-#include "common.cuh"
+#include <new>
+
+#include "heff.cuh"
 
 namespace tnpy {
+
+int axpy(double alpha, const double* a_dev, const double* x, double* y, int64_t n, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------------
 // W-mix:  out[X][v'][u'][Y] = sum_{u,v} Wc(u,u',v,v') * in[u][X][v][Y]
@@ -213,6 +217,33 @@ static int check_dims(int l, int r, int wl, int wr, int d) {
   return TNPY_OK;
 }
 
+// May this call use the int8 tensor-core path?  AUTO defers to the process-wide selection (tnpy_set_gemm_algo /
+// TNPY_GEMM_ALGO); the default selection and TNPY_GEMM_OZAKI allow it, GENERIC / DMMA / FP64 mean native FP64.
+static bool tcgen05_allowed(int algo) {
+  if (algo == TNPY_GEMM_AUTO) algo = current_gemm_algo();
+  return algo == TNPY_GEMM_AUTO || algo == TNPY_GEMM_OZAKI;
+}
+
+size_t chain_gemm_bytes(int M, int N, int K) {
+  if (!ozaki_applicable(M, N, K)) return 0;
+  return oz_operand_bytes(M, K) + oz_operand_bytes(N, K) + oz_mma_scratch_bytes(M, N);
+}
+
+int chain_gemm(const double* A, int64_t lda, const double* B, int64_t ldb, GemmOut out, int M, int N, int K,
+               int accumulate, int algo, Workspace& ws, cudaStream_t stream) {
+  if (tcgen05_allowed(algo) && ozaki_applicable(M, N, K)) {
+    Workspace probe = ws;  // all or nothing: fall back to FP64 when the slices do not fit
+    OzOperand a, b;
+    if (oz_operand_take(probe, M, K, &a) && oz_operand_take(probe, N, K, &b)) {
+      TNPY_TRY(oz_slice_operand(A, lda, oz_plain_rows(K), a, stream));
+      TNPY_TRY(oz_slice_operand(B, ldb, oz_plain_rows(K), b, stream));
+      return oz_mma(a, b, out, M, N, ozaki_slices(), accumulate, probe, nullptr, stream);
+    }
+  }
+  return gemm_tn(A, lda, B, ldb, out, M, N, K, accumulate, TNPY_GEMM_FP64, stream);
+}
+
+// ---- prepared H_eff ---------------------------------------------------------------------------
 // lo = number of output (bra) rows of L held by the caller: L is (l, wl, lo), y is (lo, d, r).
 // lo == l is the ordinary matvec; lo < l is one rank's row block of the chi-sharded matvec.
 //
@@ -223,50 +254,209 @@ static int check_dims(int l, int r, int wl, int wr, int d) {
 //                        intermediate is laid out MPO-bond-slowest so the GEMM just drops that K range.
 // The caller vouches for the flags (tnpy_identity_defect measures them); executed flops drop by up to
 // 2/w while the algorithmic flop count F_mv is unchanged.
-int heff_apply_rows(const double* L, const double* W, const double* R, const double* x, double* y, int l, int lo,
-                    int r, int wl, int wr, int d, int flags, Workspace& ws, cudaStream_t stream) {
+struct ChainShape {
+  bool left_id, right_id;
+  int m1, n1, k1;  // GEMM 1: T1 = x^T L      (M = d r, N = channels * lo, K = l)
+  int m3, n3, k3;  // GEMM 3: y  = T2^T R     (M = d lo, N = r, K = r * channels)
+};
+static ChainShape chain_shape(int l, int lo, int r, int wl, int wr, int d, int flags) {
+  ChainShape s;
+  s.left_id = (flags & TNPY_LEFT_IDENTITY) && wl > 1 && lo == l;
+  s.right_id = (flags & TNPY_RIGHT_IDENTITY) && wr > 1;
+  s.m1 = d * r; s.n1 = (s.left_id ? wl - 1 : wl) * lo; s.k1 = l;
+  s.m3 = d * lo; s.n3 = r; s.k3 = r * (s.right_id ? wr - 1 : wr);
+  return s;
+}
+
+static bool direct_shapes_ok(int l, int lo, int r, int wl, int wr, int d) {
+  return lo == l && wl > 1 && wr > 1 && oz_premix_applicable(l, r, wl, wr, d) &&
+         ozaki_applicable(l * d, r, (wr - 1) * r) && ozaki_applicable(l, d * r, (wl - 1) * l);
+}
+
+// no non-zero block W[a, b] with a > 0 and b < wr - 1
+static bool no_interior_blocks(const double* W_host, int wl, int wr, int d) {
+  for (int a = 1; a < wl; ++a)
+    for (int b = 0; b + 1 < wr; ++b)
+      for (int e = 0; e < d * d; ++e)
+        if (W_host[((size_t)a * wr + b) * d * d + e] != 0.0) return false;
+  return true;
+}
+
+size_t heff_plan_bytes(int l, int lo, int r, int wl, int wr, int d) {
+  size_t chain = Workspace::need((size_t)r * wr * r);  // r2 of the FP64 chain
+  if (ozaki_applicable(d * r, wl * lo, l)) chain += oz_operand_bytes(wl * lo, l);
+  if (ozaki_applicable(d * lo, r, r * wr)) chain += oz_operand_bytes(r, r * wr);
+  size_t direct = 0;
+  if (direct_shapes_ok(l, lo, r, wl, wr, d)) direct = oz_operand_bytes(l, (wl - 1) * l) + oz_operand_bytes(r, (wr - 1) * r);
+  return (chain > direct ? chain : direct) + Workspace::need(1) + 1024;
+}
+
+size_t heff_apply_bytes(int l, int lo, int r, int wl, int wr, int d) {
+  size_t chain = Workspace::need((size_t)d * r * wl * lo) + Workspace::need((size_t)r * wr * d * lo);  // T1, T2
+  if (ozaki_applicable(d * r, wl * lo, l)) chain += oz_operand_bytes(d * r, l) + oz_mma_scratch_bytes(d * r, wl * lo);
+  if (ozaki_applicable(d * lo, r, r * wr)) chain += oz_operand_bytes(d * lo, r * wr) + oz_mma_scratch_bytes(d * lo, r);
+  size_t direct = 0;
+  if (direct_shapes_ok(l, lo, r, wl, wr, d))
+    direct = oz_operand_bytes(l * d, (wr - 1) * r) + oz_operand_bytes(d * r, (wl - 1) * l) +
+             oz_mma_scratch_bytes(l * d, r) + oz_mma_scratch_bytes(l, d * r);
+  return (chain > direct ? chain : direct) + 1024;
+}
+
+int heff_plan_init(HeffPlan* plan, const double* L, const double* W, const double* R, const double* W_host, int l,
+                   int lo, int r, int wl, int wr, int d, int flags, int algo, Workspace& mem, cudaStream_t stream) {
   TNPY_TRY(check_dims(l, r, wl, wr, d));
   TNPY_CHECK_ARG(lo > 0, "non-positive row count");
-  TNPY_CHECK_ARG(W && x && y, "null pointer");
+  TNPY_CHECK_ARG(W != nullptr, "null pointer");
   TNPY_CHECK_ARG(L || (l == 1 && wl == 1 && lo == 1), "L may be NULL only for unit left bond");
   TNPY_CHECK_ARG(R || (r == 1 && wr == 1), "R may be NULL only for unit right bond");
   if (!L) L = device_one();
   if (!R) R = device_one();
-  const bool left_id = (flags & TNPY_LEFT_IDENTITY) && wl > 1 && lo == l;
-  const bool right_id = (flags & TNPY_RIGHT_IDENTITY) && wr > 1;
-  double* t1 = ws.take<double>((size_t)d * r * wl * lo);
-  double* t2 = ws.take<double>((size_t)r * wr * d * lo);
-  double* r2 = right_id ? ws.take<double>((size_t)r * (wr - 1) * r) : nullptr;
-  if (!t1 || !t2 || (right_id && !r2)) {
+  *plan = HeffPlan{};
+  plan->L = L; plan->W = W; plan->R = R;
+  plan->l = l; plan->lo = lo; plan->r = r; plan->wl = wl; plan->wr = wr; plan->d = d; plan->flags = flags;
+  plan->mode = HEFF_FP64_CHAIN;
+  const ChainShape s = chain_shape(l, lo, r, wl, wr, d, flags);
+  const bool oz_ok = tcgen05_allowed(algo);
+  if (oz_ok) {
+    plan->bound = mem.take<double>(1);
+    if (!plan->bound) {
+      set_error("heff_plan_init: plan memory too small");
+      return TNPY_EWORKSPACE;
+    }
+    TNPY_CUDA_OK(cudaMemsetAsync(plan->bound, 0, sizeof(double), stream));
+  }
+  if (oz_ok && s.left_id && s.right_id && direct_shapes_ok(l, lo, r, wl, wr, d)) {
+    double w_local[kPmMaxCh * kPmMaxCh * kPmMaxD * kPmMaxD];
+    if (!W_host && (size_t)wl * wr * d * d <= sizeof(w_local) / sizeof(double)) {
+      TNPY_CUDA_OK(cudaMemcpyAsync(w_local, W, sizeof(double) * (size_t)wl * wr * d * d, cudaMemcpyDeviceToHost, stream));
+      TNPY_CUDA_OK(cudaStreamSynchronize(stream));
+      W_host = w_local;
+    }
+    if (W_host && no_interior_blocks(W_host, wl, wr, d)) {
+      Workspace probe = mem;
+      if (oz_operand_take(probe, lo, (wl - 1) * l, &plan->envL) && oz_operand_take(probe, r, (wr - 1) * r, &plan->envR)) {
+        mem = probe;
+        // L'[(a - 1) l + li, m] = L[li, a, m]  (a >= 1);   R'[b r + ri, s] = R[ri, b, s]  (b < wr - 1)
+        TNPY_TRY(oz_slice_operand(L, lo, OzRowMap{l, wl, 1}, plan->envL, stream));
+        TNPY_TRY(oz_slice_operand(R, r, OzRowMap{r, wr, 0}, plan->envR, stream));
+        plan->mode = HEFF_OZ_DIRECT;
+        return TNPY_OK;
+      }
+    }
+  }
+  plan->g1_oz = oz_ok && ozaki_applicable(s.m1, s.n1, s.k1);
+  plan->g3_oz = oz_ok && ozaki_applicable(s.m3, s.n3, s.k3);
+  if (plan->g1_oz) {
+    Workspace probe = mem;
+    if (oz_operand_take(probe, s.n1, s.k1, &plan->envL)) {
+      mem = probe;
+      TNPY_TRY(oz_slice_operand(L + (s.left_id ? lo : 0), (int64_t)wl * lo, oz_plain_rows(l), plan->envL, stream));
+    } else {
+      plan->g1_oz = false;
+    }
+  }
+  if (plan->g3_oz) {
+    Workspace probe = mem;
+    if (oz_operand_take(probe, s.n3, s.k3, &plan->envR)) {
+      mem = probe;
+      // right identity: K runs over (b, ri) with the last channel dropped, matching the channel-major intermediate
+      TNPY_TRY(oz_slice_operand(R, r, s.right_id ? OzRowMap{r, wr, 0} : oz_plain_rows(r * wr), plan->envR, stream));
+    } else {
+      plan->g3_oz = false;
+    }
+  }
+  if (plan->g1_oz || plan->g3_oz) plan->mode = HEFF_OZ_CHAIN;
+  if (s.right_id && !plan->g3_oz) {
+    plan->r2 = mem.take<double>((size_t)r * (wr - 1) * r);
+    if (!plan->r2) {
+      set_error("heff_plan_init: plan memory too small");
+      return TNPY_EWORKSPACE;
+    }
+    channel_major_kernel<<<sm_count() * 8, 256, 0, stream>>>(R, plan->r2, r, wr, wr - 1, r);
+    TNPY_LAUNCH_OK();
+  }
+  return TNPY_OK;
+}
+
+static int apply_direct(const HeffPlan& p, const double* x, double* y, int S, const double* shift_dev, Workspace& ws,
+                        cudaStream_t stream) {
+  const int l = p.l, r = p.r, wl = p.wl, wr = p.wr, d = p.d;
+  OzOperand xa, xb;
+  if (!oz_operand_take(ws, l * d, (wr - 1) * r, &xa) || !oz_operand_take(ws, d * r, (wl - 1) * l, &xb)) {
     set_error("heff_apply: workspace too small");
     return TNPY_EWORKSPACE;
   }
-  const int algo = TNPY_GEMM_AUTO;
+  // y = W[0, wr-1] x - shift x, then both GEMMs accumulate into it
+  TNPY_TRY(oz_premix_a(x, p.W, l, r, wl, wr, d, xa, y, shift_dev, stream));
+  TNPY_TRY(oz_premix_b(x, p.W, l, r, wl, wr, d, xb, stream));
+  // y[(m q), s] += sum_{(b ri)} Xa[(b ri), (m q)] R'[(b ri), s]
+  TNPY_TRY(oz_mma(xa, p.envR, plain_out(y, r, l * d), l * d, r, S, 1, ws, p.bound, stream));
+  // y[m, (q s)] += sum_{(a li)} L'[(a li), m] Xb[(a li), (q s)]
+  TNPY_TRY(oz_mma(p.envL, xb, plain_out(y, (int64_t)d * r, l), l, d * r, S, 1, ws, p.bound, stream));
+  return TNPY_OK;
+}
+
+int heff_plan_apply(const HeffPlan& p, const double* x, double* y, int S, const double* shift_dev, Workspace& ws,
+                    cudaStream_t stream) {
+  TNPY_CHECK_ARG(x && y, "null pointer");
+  if (S <= 0) S = ozaki_slices();
+  if (p.mode == HEFF_OZ_DIRECT) return apply_direct(p, x, y, S, shift_dev, ws, stream);
+  const int l = p.l, lo = p.lo, r = p.r, wl = p.wl, wr = p.wr, d = p.d;
+  const ChainShape s = chain_shape(l, lo, r, wl, wr, d, p.flags);
+  double* t1 = ws.take<double>((size_t)d * r * wl * lo);
+  double* t2 = ws.take<double>((size_t)r * wr * d * lo);
+  if (!t1 || !t2) {
+    set_error("heff_apply: workspace too small");
+    return TNPY_EWORKSPACE;
+  }
   // T1[p, r, a, m] = sum_l x[l, (p r)] L[l, (a m)]
-  if (left_id) {
-    TNPY_TRY(transpose_strided(x, (int64_t)d * r, 0, l, d * r, t1, (int64_t)wl * lo, 0, 1, stream));  // a = 0
-    TNPY_TRY(gemm_tn(x, (int64_t)d * r, L + lo, (int64_t)wl * lo, plain_out(t1 + lo, (int64_t)wl * lo, d * r), d * r,
-                     (wl - 1) * lo, l, 0, algo, stream));
+  double* t1_dst = t1 + (s.left_id ? lo : 0);
+  if (s.left_id) TNPY_TRY(transpose_strided(x, (int64_t)d * r, 0, l, d * r, t1, (int64_t)wl * lo, 0, 1, stream));  // a = 0
+  if (p.g1_oz) {
+    Workspace scratch = ws;
+    OzOperand xs;
+    if (!oz_operand_take(scratch, s.m1, s.k1, &xs)) {
+      set_error("heff_apply: workspace too small");
+      return TNPY_EWORKSPACE;
+    }
+    TNPY_TRY(oz_slice_operand(x, (int64_t)d * r, oz_plain_rows(l), xs, stream));
+    TNPY_TRY(oz_mma(xs, p.envL, plain_out(t1_dst, (int64_t)wl * lo, s.m1), s.m1, s.n1, S, 0, scratch, p.bound, stream));
   } else {
-    TNPY_TRY(gemm_tn(x, (int64_t)d * r, L, (int64_t)wl * lo, plain_out(t1, (int64_t)wl * lo, d * r), d * r, wl * lo, l,
-                     0, algo, stream));
+    TNPY_TRY(gemm_tn(x, (int64_t)d * r, p.L + (s.left_id ? lo : 0), (int64_t)wl * lo,
+                     plain_out(t1_dst, (int64_t)wl * lo, s.m1), s.m1, s.n1, s.k1, 0, TNPY_GEMM_FP64, stream));
   }
   // T2[r, b, q, m] (or [b, r, q, m]) = sum_{a p} W[a, b, p, q] T1[p, r, a, m]      (u=p, u'=q, v=a, v'=b)
-  TNPY_TRY(wmix(t1, t2, W, d, d, wl, wr, r, lo, d, 1, wr * d * d, d * d, stream, right_id ? 1 : 0));
+  TNPY_TRY(wmix(t1, t2, p.W, d, d, wl, wr, r, lo, d, 1, wr * d * d, d * d, stream, s.right_id ? 1 : 0));
   // y[m, q, s] = sum_{r b} T2[(r b), (q m)] R[(r b), s]               rows (q m) -> (m q)
+  // (right identity: the GEMM runs over the channels b < wr-1 and the identity-channel term T2[wr-1, s, q, m]
+  // is added by a transposing pass afterwards so that the GEMM epilogue stays store-only)
   GemmOut out{y, (int64_t)d * r, (int64_t)r, lo};
-  if (right_id) {
-    // y[m, q, s] = (GEMM over the channels b < wr-1) + T2[wr-1, s, q, m]; the identity-channel term is
-    // added by a transposing pass afterwards so that the GEMM epilogue stays store-only
-    channel_major_kernel<<<sm_count() * 8, 256, 0, stream>>>(R, r2, r, wr, wr - 1, r);
-    TNPY_LAUNCH_OK();
-    TNPY_TRY(gemm_tn(t2, (int64_t)d * lo, r2, (int64_t)r, out, d * lo, r, r * (wr - 1), 0, algo, stream));
+  if (p.g3_oz) {
+    Workspace scratch = ws;
+    OzOperand ts;
+    if (!oz_operand_take(scratch, s.m3, s.k3, &ts)) {
+      set_error("heff_apply: workspace too small");
+      return TNPY_EWORKSPACE;
+    }
+    TNPY_TRY(oz_slice_operand(t2, (int64_t)d * lo, oz_plain_rows(s.k3), ts, stream));
+    TNPY_TRY(oz_mma(ts, p.envR, out, s.m3, s.n3, S, 0, scratch, p.bound, stream));
+  } else {
+    TNPY_TRY(gemm_tn(t2, (int64_t)d * lo, s.right_id ? p.r2 : p.R, (int64_t)r, out, s.m3, s.n3, s.k3, 0, TNPY_GEMM_FP64,
+                     stream));
+  }
+  if (s.right_id) {
     const double* t2_last = t2 + (size_t)(wr - 1) * r * d * lo;
     TNPY_TRY(transpose_strided(t2_last, (int64_t)d * lo, lo, r, lo, y, (int64_t)d * r, r, d, stream, true));
-  } else {
-    TNPY_TRY(gemm_tn(t2, (int64_t)d * lo, R, (int64_t)r, out, d * lo, r, r * wr, 0, algo, stream));
   }
+  if (shift_dev) TNPY_TRY(axpy(-1.0, shift_dev, x, y, (int64_t)lo * d * r, stream));
   return TNPY_OK;
+}
+
+int heff_apply_rows(const double* L, const double* W, const double* R, const double* x, double* y, int l, int lo,
+                    int r, int wl, int wr, int d, int flags, Workspace& ws, cudaStream_t stream) {
+  HeffPlan plan;
+  TNPY_TRY(heff_plan_init(&plan, L, W, R, nullptr, l, lo, r, wl, wr, d, flags, TNPY_GEMM_AUTO, ws, stream));
+  return heff_plan_apply(plan, x, y, 0, nullptr, ws, stream);
 }
 
 int heff_apply(const double* L, const double* W, const double* R, const double* x, double* y, int l, int r, int wl,
@@ -290,17 +480,20 @@ int env_update_left(const double* L, const double* A, const double* W, double* L
   // T1[a, m, p, r] = sum_l L[l, (a m)] A[l, (p r)];  identity channel a = 0: T1[0] = A
   if ((flags & TNPY_LEFT_IDENTITY) && wl > 1) {
     TNPY_CUDA_OK(cudaMemcpyAsync(t1, A, sizeof(double) * (size_t)l * d * r, cudaMemcpyDeviceToDevice, stream));
-    TNPY_TRY(gemm_tn(L + l, (int64_t)wl * l, A, (int64_t)d * r, plain_out(t1 + (size_t)l * d * r, (int64_t)d * r, (wl - 1) * l),
-                     (wl - 1) * l, d * r, l, 0, algo, stream));
+    Workspace scratch = ws;
+    TNPY_TRY(chain_gemm(L + l, (int64_t)wl * l, A, (int64_t)d * r, plain_out(t1 + (size_t)l * d * r, (int64_t)d * r, (wl - 1) * l),
+                        (wl - 1) * l, d * r, l, 0, algo, scratch, stream));
   } else {
-    TNPY_TRY(gemm_tn(L, (int64_t)wl * l, A, (int64_t)d * r, plain_out(t1, (int64_t)d * r, wl * l), wl * l, d * r, l, 0,
-                     algo, stream));
+    Workspace scratch = ws;
+    TNPY_TRY(chain_gemm(L, (int64_t)wl * l, A, (int64_t)d * r, plain_out(t1, (int64_t)d * r, wl * l), wl * l, d * r, l, 0,
+                        algo, scratch, stream));
   }
   // T2[m, q, b, r] = sum_{a p} W[a, b, p, q] T1[a, m, p, r]          (u=a, u'=b, v=p, v'=q)
   TNPY_TRY(wmix(t1, t2, W, wl, wr, d, d, l, r, wr * d * d, d * d, d, 1, stream));
   // Lout[r, b, s] = sum_{m q} T2[(m q), (b r)] A[(m q), s]             rows (b r) -> (r b)
   GemmOut out{Lout, (int64_t)wr * r, (int64_t)r, r};
-  TNPY_TRY(gemm_tn(t2, (int64_t)wr * r, A, (int64_t)r, out, wr * r, r, l * d, 0, algo, stream));
+  Workspace scratch = ws;
+  TNPY_TRY(chain_gemm(t2, (int64_t)wr * r, A, (int64_t)r, out, wr * r, r, l * d, 0, algo, scratch, stream));
   return TNPY_OK;
 }
 
@@ -325,17 +518,20 @@ int env_update_right(const double* R, const double* A, const double* W, double* 
   if ((flags & TNPY_RIGHT_IDENTITY) && wr > 1) {
     TNPY_CUDA_OK(cudaMemcpyAsync(t1 + (size_t)(wr - 1) * r * d * l, at, sizeof(double) * (size_t)r * d * l,
                                  cudaMemcpyDeviceToDevice, stream));
-    TNPY_TRY(gemm_tn(R, (int64_t)wr * r, at, (int64_t)d * l, plain_out(t1, (int64_t)d * l, (wr - 1) * r), (wr - 1) * r,
-                     d * l, r, 0, algo, stream));
+    Workspace scratch = ws;
+    TNPY_TRY(chain_gemm(R, (int64_t)wr * r, at, (int64_t)d * l, plain_out(t1, (int64_t)d * l, (wr - 1) * r), (wr - 1) * r,
+                        d * l, r, 0, algo, scratch, stream));
   } else {
-    TNPY_TRY(gemm_tn(R, (int64_t)wr * r, at, (int64_t)d * l, plain_out(t1, (int64_t)d * l, wr * r), wr * r, d * l, r, 0,
-                     algo, stream));
+    Workspace scratch = ws;
+    TNPY_TRY(chain_gemm(R, (int64_t)wr * r, at, (int64_t)d * l, plain_out(t1, (int64_t)d * l, wr * r), wr * r, d * l, r, 0,
+                        algo, scratch, stream));
   }
   // T2[s, q, a, l] = sum_{b p} W[a, b, p, q] T1[b, s, p, l]          (u=b, u'=a, v=p, v'=q)
   TNPY_TRY(wmix(t1, t2, W, wr, wl, d, d, r, l, d * d, wr * d * d, d, 1, stream));
   // Rout[l, a, m] = sum_{s q} T2[(s q), (a l)] At[(s q), m]            rows (a l) -> (l a)
   GemmOut out{Rout, (int64_t)wl * l, (int64_t)l, l};
-  TNPY_TRY(gemm_tn(t2, (int64_t)wl * l, at, (int64_t)l, out, wl * l, l, r * d, 0, algo, stream));
+  Workspace scratch = ws;
+  TNPY_TRY(chain_gemm(t2, (int64_t)wl * l, at, (int64_t)l, out, wl * l, l, r * d, 0, algo, scratch, stream));
   return TNPY_OK;
 }
 
@@ -366,13 +562,17 @@ __global__ void __launch_bounds__(256) heff_dense_kernel(const double* __restric
 
 using namespace tnpy;
 
-static size_t chain_ws(int l, int r, int wl, int wr, int d) {
-  const size_t wmax = (size_t)(wl > wr ? wl : wr);
-  return 3 * Workspace::need((size_t)l * r * d * wmax) + Workspace::need((size_t)r * wr * r) + 1024;
-}
+static size_t max3(size_t a, size_t b, size_t c) { return a > b ? (a > c ? a : c) : (b > c ? b : c); }
 
-extern "C" size_t tnpy_heff_workspace_bytes(int l, int r, int wl, int wr, int d) { return chain_ws(l, r, wl, wr, d); }
-extern "C" size_t tnpy_env_workspace_bytes(int l, int r, int wl, int wr, int d) { return chain_ws(l, r, wl, wr, d); }
+extern "C" size_t tnpy_heff_workspace_bytes(int l, int r, int wl, int wr, int d) {
+  return heff_plan_bytes(l, l, r, wl, wr, d) + heff_apply_bytes(l, l, r, wl, wr, d) + 1024;
+}
+extern "C" size_t tnpy_env_workspace_bytes(int l, int r, int wl, int wr, int d) {
+  const size_t wmax = (size_t)(wl > wr ? wl : wr);
+  const size_t left = max3(chain_gemm_bytes(wl * l, d * r, l), chain_gemm_bytes(wr * r, r, l * d), 0);
+  const size_t right = max3(chain_gemm_bytes(wr * r, d * l, r), chain_gemm_bytes(wl * l, l, r * d), 0);
+  return 3 * Workspace::need((size_t)l * r * d * wmax) + (left > right ? left : right) + 1024;
+}
 extern "C" size_t tnpy_heff_dense_workspace_bytes(int, int, int, int, int) { return 256; }
 
 extern "C" int tnpy_heff_apply(const double* L, const double* W, const double* R, const double* x, double* y, int l,
@@ -380,6 +580,71 @@ extern "C" int tnpy_heff_apply(const double* L, const double* W, const double* R
                                void* stream) {
   Workspace ws(workspace, workspace_bytes);
   return heff_apply(L, W, R, x, y, l, r, wl, wr, d, flags, ws, static_cast<cudaStream_t>(stream));
+}
+
+// ---- prepared H_eff: the host-side handle is a small struct owned by the library, all device memory is the caller's
+struct tnpy_heff_plan {
+  HeffPlan plan;
+};
+
+extern "C" size_t tnpy_heff_plan_bytes(int l, int r, int wl, int wr, int d) { return heff_plan_bytes(l, l, r, wl, wr, d) + 256; }
+
+static int plan_create(tnpy_heff_plan** handle, const double* L, const double* W, const double* R, const double* W_host,
+                       int l, int lo, int r, int wl, int wr, int d, int flags, int algo, void* plan_memory,
+                       size_t plan_bytes, void* stream) {
+  TNPY_CHECK_ARG(handle != nullptr, "null handle");
+  TNPY_CHECK_ARG(algo >= TNPY_GEMM_AUTO && algo <= TNPY_GEMM_FP64, "unknown algo");
+  tnpy_heff_plan* h = new (std::nothrow) tnpy_heff_plan;
+  if (!h) {
+    set_error("tnpy_heff_plan_create: out of host memory");
+    return TNPY_EINVAL;
+  }
+  Workspace mem(plan_memory, plan_bytes);
+  const int rc = heff_plan_init(&h->plan, L, W, R, W_host, l, lo, r, wl, wr, d, flags, algo, mem, static_cast<cudaStream_t>(stream));
+  if (rc != TNPY_OK) {
+    delete h;
+    return rc;
+  }
+  *handle = h;
+  return TNPY_OK;
+}
+
+extern "C" int tnpy_heff_plan_create(tnpy_heff_plan** handle, const double* L, const double* W, const double* R,
+                                     const double* W_host, int l, int r, int wl, int wr, int d, int flags, int algo,
+                                     void* plan_memory, size_t plan_bytes, void* stream) {
+  return plan_create(handle, L, W, R, W_host, l, l, r, wl, wr, d, flags, algo, plan_memory, plan_bytes, stream);
+}
+
+extern "C" int tnpy_heff_plan_create_rows(tnpy_heff_plan** handle, const double* L_rows, const double* W, const double* R,
+                                          int l, int l_rows, int r, int wl, int wr, int d, int algo, void* plan_memory,
+                                          size_t plan_bytes, void* stream) {
+  TNPY_CHECK_ARG(l_rows > 0 && l_rows <= l, "row count outside (0, l]");
+  return plan_create(handle, L_rows, W, R, nullptr, l, l_rows, r, wl, wr, d, 0, algo, plan_memory, plan_bytes, stream);
+}
+
+extern "C" int tnpy_heff_plan_mode(const tnpy_heff_plan* handle) { return handle ? handle->plan.mode : TNPY_EINVAL; }
+
+extern "C" int tnpy_heff_plan_apply(const tnpy_heff_plan* handle, const double* x, double* y, int slices,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+  TNPY_CHECK_ARG(handle != nullptr, "null handle");
+  TNPY_CHECK_ARG(slices == 0 || (slices >= 6 && slices <= kOzMaxSlices), "slices must be 0 (default), 6, 7 or 8");
+  Workspace ws(workspace, workspace_bytes);
+  return heff_plan_apply(handle->plan, x, y, slices, nullptr, ws, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int tnpy_heff_plan_error_bound(const tnpy_heff_plan* handle, double* bound_dev_out, void* stream) {
+  TNPY_CHECK_ARG(handle != nullptr && bound_dev_out != nullptr, "null pointer");
+  if (handle->plan.bound)
+    TNPY_CUDA_OK(cudaMemcpyAsync(bound_dev_out, handle->plan.bound, sizeof(double), cudaMemcpyDeviceToDevice,
+                                 static_cast<cudaStream_t>(stream)));
+  else
+    TNPY_CUDA_OK(cudaMemsetAsync(bound_dev_out, 0, sizeof(double), static_cast<cudaStream_t>(stream)));
+  return TNPY_OK;
+}
+
+extern "C" int tnpy_heff_plan_destroy(tnpy_heff_plan* handle) {
+  delete handle;
+  return TNPY_OK;
 }
 
 extern "C" int tnpy_identity_defect(const double* E, int dim, int w, int channel, double* defect_dev, void* workspace,

@@ -188,11 +188,6 @@ __global__ void geig_reset_kernel(double* __restrict__ GA, double* __restrict__ 
   for (int idx = threadIdx.x; idx < kMaxG * kMaxG; idx += blockDim.x) GA[idx] = GM[idx] = 0.0;
 }
 
-struct PinnedG {
-  double* host = nullptr;
-  PinnedG() { cudaMallocHost(&host, sizeof(double) * GS_SIZE); }
-};
-
 static void geig_sizes(int64_t n, int ncv_in, int& ncv) {
   ncv = ncv_in <= 0 ? 24 : ncv_in;
   if (ncv > kMaxG) ncv = kMaxG;
@@ -243,8 +238,7 @@ extern "C" int tnpy_geig_lowest(const double* LA, const double* WA, const double
     return TNPY_EWORKSPACE;
   }
   const size_t chain_off = ws.used;
-  static PinnedG pinned;
-  double* hst = pinned.host;
+  double* hst = static_cast<double*>(thread_pinned_scratch());
   if (!hst) {
     set_error("tnpy_geig_lowest: pinned status allocation failed");
     return TNPY_ECUDA;

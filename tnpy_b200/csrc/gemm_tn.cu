@@ -23,9 +23,6 @@
 namespace tnpy {
 
 int forced_gemm_tile();
-bool ozaki_applicable(int M, int N, int K);
-int ozaki_gemm(const double* A, int64_t lda, const double* B, int64_t ldb, GemmOut out, int M, int N, int K,
-               int accumulate, cudaStream_t stream);
 
 // =============================================================================================
 // generic kernel
@@ -338,11 +335,7 @@ static int launch_dmma(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmOut o
                        int vec_ok, cudaStream_t stream) {
   using Cfg = DmmaCfg<BM, BN, WM, WN, STAGES>;
   auto kern = gemm_tn_dmma<BM, BN, WM, WN, STAGES>;
-  static bool configured = false;
-  if (!configured) {
-    TNPY_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    configured = true;
-  }
+  TNPY_TRY(set_max_dynamic_smem(kern, Cfg::kSmemBytes));
   const int tiles_m = ceil_div(M, BM), tiles_n = ceil_div(N, BN);
   const int grid = min(tiles_m * tiles_n, sm_count());
   kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, out, M, N, K, accumulate, vec_ok, tiles_m, tiles_n);
@@ -359,12 +352,10 @@ int gemm_tn(const double* A, int64_t lda, const double* B, int64_t ldb, GemmOut 
   TNPY_CHECK_ARG(A && B && out.C, "null operand");
   TNPY_CHECK_ARG(M > 0 && N > 0 && K > 0, "non-positive dimension");
   TNPY_CHECK_ARG(lda >= M && ldb >= N && out.m_inner > 0, "leading dimension too small");
+  // This entry point is native FP64 (the tcgen05 path needs a workspace for its slices: chain_gemm in
+  // contract.cu / tnpy_ozaki_gemm_tn); the process-wide selection only matters when it forces a kernel.
   if (algo == TNPY_GEMM_AUTO) algo = current_gemm_algo();
-  if (algo == TNPY_GEMM_OZAKI) {
-    // FP64-accurate GEMM on the tcgen05 int8 tensor cores; small / very deep problems fall through to DMMA
-    if (ozaki_applicable(M, N, K)) return ozaki_gemm(A, lda, B, ldb, out, M, N, K, accumulate, stream);
-    algo = TNPY_GEMM_AUTO;
-  }
+  if (algo == TNPY_GEMM_OZAKI || algo == TNPY_GEMM_FP64) algo = TNPY_GEMM_AUTO;
   const bool can_tma = tma_ok(A, lda) && tma_ok(B, ldb);
   if (algo == TNPY_GEMM_DMMA && !can_tma) {
     set_error("gemm_tn: TNPY_GEMM_DMMA requested but operands are not TMA-describable (16B base, even ld)");

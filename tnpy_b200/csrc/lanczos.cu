@@ -8,28 +8,10 @@
 // stop or restart.  Basis vectors never leave HBM.
 #include <math.h>
 
-#include "common.cuh"
+#include "heff.cuh"
 
 namespace tnpy {
 
-void ozaki_const_scope(bool on);
-void ozaki_scope_slices(int slices);
-int ozaki_slices();
-// L, W, R are constant for the whole solve: their int8 slices are made once (tcgen05 path).  A matvec whose
-// error (2e-14 |A|^T|B| with 7 slices) is orders of magnitude below the residual tolerance does not need the
-// eighth slice: 28 instead of 36 slice GEMMs.  The configured count is restored when the solve ends.
-struct OzConstScope {
-  explicit OzConstScope(double tol) {
-    ozaki_const_scope(true);
-    if (tol >= 1e-10 && ozaki_slices() == 8) ozaki_scope_slices(7);
-  }
-  ~OzConstScope() {
-    ozaki_scope_slices(0);
-    ozaki_const_scope(false);
-  }
-};
-int heff_apply(const double* L, const double* W, const double* R, const double* x, double* y, int l, int r, int wl,
-               int wr, int d, int flags, Workspace& ws, cudaStream_t stream);
 int multi_dot(const double* V, int64_t ldv, int m, const double* w, int64_t n, double* h, int mode,
               cudaStream_t stream, const int* skip = nullptr);
 int multi_axpy(const double* V, int64_t ldv, int m, const double* h, double* w, int64_t n, double* nrm_out,
@@ -43,7 +25,7 @@ int combine(const double* V, int64_t ldv, int m, const double* c, int64_t ldc_, 
 constexpr int kMaxNcv = 48;
 
 // status record (device and pinned host mirror)
-enum { ST_THETA = 0, ST_RESID = 1, ST_ANORM = 2, ST_DONE = 3, ST_BETA = 4, ST_RCOEF = 5, ST_SIZE = 8 };
+enum { ST_THETA = 0, ST_RESID = 1, ST_ANORM = 2, ST_DONE = 3, ST_BETA = 4, ST_RCOEF = 5, ST_BOUND = 6, ST_SIZE = 8 };
 
 // Symmetric eigen-decomposition of the m x m matrix held in shared memory `a` (leading dim kMaxNcv)
 // by parallel cyclic Jacobi (round-robin pair ordering).  Eigenvectors accumulate in `z` (columns).
@@ -190,14 +172,7 @@ __global__ void restart_T_kernel(double* __restrict__ T, const double* __restric
   }
 }
 
-struct PinnedStatus {
-  double* host = nullptr;
-  PinnedStatus() { cudaMallocHost(&host, sizeof(double) * ST_SIZE); }
-};
-static double* pinned_status() {
-  static PinnedStatus p;
-  return p.host;
-}
+static double* pinned_status() { return static_cast<double*>(thread_pinned_scratch()); }
 
 static size_t eig_ws_layout(int64_t n, int ncv, int keep, size_t chain) {
   const int64_t ldv = n + (n & 1);
@@ -249,7 +224,7 @@ extern "C" size_t tnpy_eig_workspace_bytes(int l, int r, int wl, int wr, int d, 
   int ncv, keep;
   const int64_t n = (int64_t)l * d * r;
   pick_sizes(n, ncv_in, ncv, keep);
-  return eig_ws_layout(n, ncv, keep, tnpy_heff_workspace_bytes(l, r, wl, wr, d));
+  return eig_ws_layout(n, ncv, keep, heff_plan_bytes(l, l, r, wl, wr, d) + heff_apply_bytes(l, l, r, wl, wr, d) + 1024);
 }
 
 static int eig_lowest_impl(const double* L, const double* W, const double* R, double* psi, double* hpsi, int l, int r,
@@ -279,26 +254,42 @@ static int eig_lowest_impl(const double* L, const double* W, const double* R, do
     set_error("tnpy_eig_lowest: workspace too small (%zu bytes given)", workspace_bytes);
     return TNPY_EWORKSPACE;
   }
-  const size_t chain_off = ws.used;
   double* hst = pinned_status();
   if (!hst) {
     set_error("tnpy_eig_lowest: pinned status allocation failed");
     return TNPY_ECUDA;
   }
-
+  // L, W, R are constant for the whole solve: everything that depends only on them (tcgen05 path: the int8 slices
+  // of the environments) is prepared once, in this call's workspace.  A matvec whose rigorous error bound with 7
+  // slices is orders of magnitude below the residual threshold does not need the eighth (28 instead of 36 slice
+  // GEMMs); the bound is read back with every status record and the slice count raised -- or the solve moved to
+  // the native FP64 chain -- if it ever comes within 1 % of tol * ||A||.
+  const size_t plan_bytes = heff_plan_bytes(l, l, r, wl, wr, d);  // enough for any mode: a later re-plan fits too
+  char* plan_mem = ws.take<char>(plan_bytes);
+  if (!plan_mem) {
+    set_error("tnpy_eig_lowest: workspace too small (%zu bytes given)", workspace_bytes);
+    return TNPY_EWORKSPACE;
+  }
+  HeffPlan plan;
+  {
+    Workspace mem(plan_mem, plan_bytes);
+    TNPY_TRY(heff_plan_init(&plan, L, W, R, nullptr, l, l, r, wl, wr, d, flags, TNPY_GEMM_AUTO, mem, stream));
+  }
+  int slices = (tol >= 1e-10 && ozaki_slices() == 8) ? 7 : ozaki_slices();
+  const size_t chain_off = ws.used;
   // V[0] = v0 / ||v0||
   TNPY_TRY(multi_dot(psi, ldv, 1, psi, n, status + ST_BETA, 1, stream));
   TNPY_TRY(scale_copy(psi, V, n, 1.0, status + ST_BETA, 1, stream));
   TNPY_CUDA_OK(cudaMemsetAsync(T, 0, sizeof(double) * kMaxNcv * kMaxNcv, stream));
 
   int j = 0, n_matvec = 0, n_restart = 0;
+  double worst_bound = 0.0;
   bool done = false;
   // Daniel-Gragg-Kaufman-Stewart: the second pass is skipped only when ||w'|| >= ||w|| / sqrt 2, i.e.
   // ||w'|| >= ||h|| (||w||^2 = ||h||^2 + ||w'||^2).  A looser, tolerance-tied threshold (1e-3) was measured to
   // derail cold-sweep solves: spurious Ritz values of order 1e3 and 1000 wasted matvecs at 5 of 34 sites of
   // XXZ n=40 chi=512 (profiles/r01_sweep_trace_cold_chi512_*.jsonl).
   const double eta = 1.0;
-  OzConstScope const_operands(tol);
   // The Ritz problem (a Jacobi eigensolve of T in one CTA, ~0.1 ms) and the host read-back are only needed when
   // somebody looks at the result: on restart steps, at the matvec limit, and every `stride` steps, stride = 1
   // within two decades of the threshold, 2 within four, 3 beyond (a local solve can overshoot by at most two
@@ -308,7 +299,7 @@ static int eig_lowest_impl(const double* L, const double* W, const double* R, do
     double* vj = V + (int64_t)j * ldv;
     double* w = V + (int64_t)(j + 1) * ldv;
     Workspace chain(static_cast<char*>(workspace) + chain_off, workspace_bytes - chain_off);
-    TNPY_TRY(heff_apply(L, W, R, vj, w, l, r, wl, wr, d, flags, chain, stream));
+    TNPY_TRY(heff_plan_apply(plan, vj, w, slices, nullptr, chain, stream));
     ++n_matvec;
     // classical Gram-Schmidt against the whole basis, applied twice; the first-pass coefficients are
     // column j of T = V^T H V, the second pass adds the rounding-level correction.
@@ -331,8 +322,23 @@ static int eig_lowest_impl(const double* L, const double* W, const double* R, do
       continue;
     }
     since_check = 0;
+    if (plan.bound)
+      TNPY_CUDA_OK(cudaMemcpyAsync(status + ST_BOUND, plan.bound, sizeof(double), cudaMemcpyDeviceToDevice, stream));
     TNPY_CUDA_OK(cudaMemcpyAsync(hst, status, sizeof(double) * ST_SIZE, cudaMemcpyDeviceToHost, stream));
     TNPY_CUDA_OK(cudaStreamSynchronize(stream));
+    if (plan.mode != HEFF_FP64_CHAIN && hst[ST_BOUND] > 0.01 * tol * hst[ST_ANORM]) {
+      // the int8 products are no longer safely below the residual threshold: spend the eighth slice, then leave
+      // the tcgen05 path altogether (the basis built so far stays valid: its vectors are exact matvecs to within
+      // the bound, and T is the explicit projection)
+      worst_bound = hst[ST_BOUND];
+      if (slices < kOzMaxSlices) {
+        slices = kOzMaxSlices;
+      } else {
+        Workspace again(plan_mem, plan_bytes);
+        TNPY_TRY(heff_plan_init(&plan, L, W, R, nullptr, l, l, r, wl, wr, d, flags, TNPY_GEMM_FP64, again, stream));
+      }
+      if (plan.bound) TNPY_CUDA_OK(cudaMemsetAsync(plan.bound, 0, sizeof(double), stream));
+    }
     {
       const double thr = tol * hst[ST_ANORM];
       stride = hst[ST_RESID] > 1e4 * thr ? 3 : (hst[ST_RESID] > 1e2 * thr ? 2 : 1);
@@ -372,6 +378,8 @@ static int eig_lowest_impl(const double* L, const double* W, const double* R, do
     stats_host[3] = (double)n_restart;
     stats_host[4] = done ? 1.0 : 0.0;
     stats_host[5] = hst[ST_ANORM];
+    stats_host[6] = worst_bound > hst[ST_BOUND] ? worst_bound : hst[ST_BOUND];  // rigorous bound on the int8 products' error
+    stats_host[7] = (double)(plan.mode * 10 + (plan.mode == HEFF_FP64_CHAIN ? 0 : slices));
   }
   if (!done) {
     set_error("tnpy_eig_lowest: not converged after %d matvecs (resid %.3e, tol*|A| %.3e)", n_matvec, hst[ST_RESID],

@@ -1,81 +1,90 @@
-// EXPERIMENT (reported separately, never substituted silently): FP64-accurate GEMM on the 5th-gen
-// tensor cores.  tcgen05 has no f64 kind, so C = A^T B is evaluated with the Ozaki scheme: every
-// operand column is scaled by a power of two and split error-free into S signed 7-bit slices,
+// FP64-accurate GEMMs on the 5th-gen tensor cores (the default path of the large contractions).
+// tcgen05 has no f64 kind, so C = A^T B is evaluated with the Ozaki scheme: every operand column is scaled by a
+// power of two and split error-free into signed 7-bit slices,
 //     A[k][m] = 2^ea[m] * sum_i a_i[k][m] * 2^(-7(i+1)),    |a_i| <= 64,
-// all slice products a_i^T b_j are exact int8 x int8 -> int32 GEMMs (tcgen05.mma.kind::i8, accumulators
-// in TMEM), slice pairs of equal weight i + j = d share one TMEM accumulator (exact: < 2^31 for
-// K <= 65536), pairs with i + j >= S are below the target precision and skipped, and the epilogue
-// recombines the S accumulators in FP64:  C[m][n] = 2^(ea[m]+eb[n]) * sum_d acc_d[m][n] * 2^(-7(d+2)).
+// all slice products a_i^T b_j are exact int8 x int8 -> int32 GEMMs (tcgen05.mma.kind::i8, accumulators in TMEM),
+// slice pairs of equal weight i + j = d share one TMEM accumulator (exact: < 2^31 for K <= 65536), pairs with
+// i + j >= S are below the target precision and skipped, and the epilogue recombines the S accumulators in FP64:
+//     C[m][n] = 2^(ea[m]+eb[n]) * sum_d acc_d[m][n] * 2^(-7(d+2)).
 //
-// Kernel anatomy (one 128 x 64 output tile per CTA, 256 threads):
-//   warp 0   TMA producer: one 3-D box (k, rows, slices) per operand per stage, 64B-swizzled, K-major
-//   warp 1   MMA issuer (one lane): S(S+1)/2 slice pairs x 2 k-steps of tcgen05.mma per stage,
-//            tcgen05.commit to the stage's empty barrier, final commit to the epilogue barrier
-//   warp 2   TMEM allocator (512 columns = S accumulators of 64 int32 columns)
-//   warps 4-7 epilogue: tcgen05.ld 32x32b, FP64 recombination, scaled store through the GEMM row map
+// Error of one product with S slices (rigorous, worst case): every scaled element is its S slices plus a remainder
+// |rho| <= 2^(-7S-1); the skipped pairs and the remainders add up to at most e_S = (S+2)/4 * 2^(-7S) per element
+// product, so  |C - A^T B|[m][n] <= K e_S sa[m] sb[n]  and  ||C - A^T B||_F <= K e_S ||sa||_2 ||sb||_2
+// (sa, sb the column scales; e_8 = 3.5e-17, e_7 = 4.0e-15, e_6 = 4.5e-13).  oz_mma folds that bound into a device
+// scalar the eigensolver reads with its status record (typical errors are sqrt(K) x random-sign smaller).
+//
+// Nothing here allocates: operands, scales and the tail scratch are carved from the caller's workspace.
 #include <cudaTypedefs.h>
 
 #include <cstdlib>
 #include <mutex>
 
-#include "common.cuh"
+#include "ozaki.cuh"
 
 namespace tnpy {
 
-constexpr int kOzBM = 128;   // tile rows (TMEM lanes)
-constexpr int kOzBN = 64;    // tile columns per accumulator
-constexpr int kOzBK = 64;    // k elements (= bytes) per stage row: one 64B swizzle span
-constexpr int kOzStages = 2;  // measured alternatives: 4 stages of 32-byte rows -10 %, 32-column epilogue loads -4 %
-constexpr int kOzMaxSlices = 8;  // 8 accumulators x 64 columns = all 512 TMEM columns
+constexpr int kOzBM = 128;  // tile rows per CTA (TMEM lanes)
+constexpr int kOzBN = 64;   // B rows staged per CTA (half of the pair's 128 columns)
+constexpr int kOzBK = 64;   // k elements (= bytes) per stage row: one 64B swizzle span
 
 // ---------------------------------------------------------------------------------------------
 // slicing
 // ---------------------------------------------------------------------------------------------
-// colmax[c] = max_k |P[k][c]| as the bit pattern of a non-negative double (integer order == value
+__device__ __forceinline__ int64_t oz_src_row(int k, OzRowMap rows) {
+  return (int64_t)(k % rows.kin) * rows.kmul + k / rows.kin + rows.koff;
+}
+
+// colmax[c] = max_k |P[row(k)][c]| as the bit pattern of a non-negative double (integer order == value
 // order), reduced over k-chunks with atomicMax; colmax must be zeroed first.
-__global__ void __launch_bounds__(256) oz_colmax_kernel(const double* __restrict__ P, int64_t ld, int K, int MN,
-                                                        int k_chunk, unsigned long long* __restrict__ colmax) {
+__global__ void __launch_bounds__(256) oz_colmax_kernel(const double* __restrict__ P, int64_t ld, OzRowMap rows, int K,
+                                                        int MN, int k_chunk, unsigned long long* __restrict__ colmax) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= MN) return;
   const int k0 = blockIdx.y * k_chunk, k1 = min(K, k0 + k_chunk);
   double mx = 0.0;
-  for (int k = k0; k < k1; ++k) mx = fmax(mx, fabs(P[(int64_t)k * ld + c]));
+  for (int k = k0; k < k1; ++k) mx = fmax(mx, fabs(P[oz_src_row(k, rows) * ld + c]));
   if (mx > 0.0) atomicMax(&colmax[c], (unsigned long long)__double_as_longlong(mx));
 }
 
-// scale = 2^e with |P[k][c]| / 2^e <= 0.5 for all k  (0 for an all-zero column)
+// scale = 2^e with |v| / 2^e <= 0.5 for every |v| <= the bound whose bit pattern is `bits` (0 for a zero column)
 __device__ __forceinline__ double oz_scale_of(unsigned long long bits) {
   const double mx = __longlong_as_double((long long)bits);
   return mx > 0.0 ? ldexp(1.0, ilogb(mx) + 2) : 0.0;
 }
 
-// slices[s][c][k] (k contiguous, Kp bytes per row) from P[k][c]: 32 columns x 128 k per block, digits staged
+// digit = rint(128 t) without conversion instructions: adding 1.5 * 2^52 leaves the rounded integer in the low
+// mantissa bits (two's complement), subtracting it again gives the rounded value; the remainder is exact.
+__device__ __forceinline__ int8_t oz_next_digit(double& t) {
+  const double magic = 6755399441055744.0;
+  const double u = fma(t, 128.0, magic);
+  t = fma(t, 128.0, magic - u);  // exact remainder, |t| <= 0.5
+  return (int8_t)__double2loint(u);  // |digit| <= 64
+}
+
+// slices[s][c][k] (k contiguous, Kp bytes per row) from P[row(k)][c]: 32 columns x 128 k per block, digits staged
 // in shared memory so that every (slice, column) row leaves as one 128-byte line.
-template <int S>
-__global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict__ P, int64_t ld, int K, int MN,
-                                                       const unsigned long long* __restrict__ colmax,
-                                                       double* __restrict__ scale, int8_t* __restrict__ slices,
-                                                       int64_t Kp, int64_t slice_stride) {
+__global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict__ P, int64_t ld, OzRowMap rows, int K,
+                                                       int MN, const unsigned long long* __restrict__ colmax,
+                                                       double* __restrict__ scale, double* __restrict__ sumsq,
+                                                       int8_t* __restrict__ slices, int64_t Kp, int64_t slice_stride) {
+  constexpr int S = kOzMaxSlices;
   __shared__ __align__(16) int8_t tile[S][32][132];
   const int c0 = blockIdx.x * 32, k0 = blockIdx.y * 128;
   const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
   const int c = c0 + tx;
   const double sc = c < MN ? oz_scale_of(colmax[c]) : 0.0;
   const double inv = sc > 0.0 ? 1.0 / sc : 0.0;  // exact: power of two
-  if (blockIdx.y == 0 && ty == 0 && c < MN) scale[c] = sc;
-  // digit = rint(128 t) without conversion instructions: adding 1.5 * 2^52 leaves the rounded integer in the low
-  // mantissa bits (two's complement), subtracting it again gives the rounded value; the remainder is exact.
-  const double magic = 6755399441055744.0;
+  if (blockIdx.y == 0 && ty == 0) {
+    if (c < MN) scale[c] = sc;
+    const double part = warp_sum(sc * sc);
+    if (tx == 0 && part > 0.0) atomicAdd(sumsq, part);  // feeds an error *bound*: summation order is immaterial
+  }
 #pragma unroll 4
   for (int i = ty; i < 128; i += 8) {
     const int k = k0 + i;
-    double t = (k < K && c < MN) ? P[(int64_t)k * ld + c] * inv : 0.0;  // |t| <= 0.5
+    double t = (k < K && c < MN) ? P[oz_src_row(k, rows) * ld + c] * inv : 0.0;  // |t| <= 0.5
 #pragma unroll
-    for (int sl = 0; sl < S; ++sl) {
-      const double u = fma(t, 128.0, magic);
-      tile[sl][tx][i] = (int8_t)__double2loint(u);  // |digit| <= 64
-      t = fma(t, 128.0, magic - u);                 // exact remainder, |t| <= 0.5
-    }
+    for (int sl = 0; sl < S; ++sl) tile[sl][tx][i] = oz_next_digit(t);
   }
   __syncthreads();
   for (int idx = threadIdx.x; idx < S * 32 * 32; idx += 256) {
@@ -85,6 +94,240 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict_
       *reinterpret_cast<int32_t*>(slices + sl * slice_stride + (int64_t)(c0 + cc) * Kp + k) =
           *reinterpret_cast<const int32_t*>(&tile[sl][cc][4 * w]);
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// premixed operands of the direct path (mixed-canonical gauge, no interior-to-interior MPO blocks)
+// ---------------------------------------------------------------------------------------------
+
+// A side: one block per left-bond index m.  Xa[(b, ri), (m, q)] = sum_p W[0, b, p, q] x[m, p, ri] for b < wr - 1:
+// for a fixed column (m, q) the K index (b, ri) runs over contiguous ri, so the row x[m, :, :] (d * r doubles) is
+// read once, its column maxima are found, and the digits leave as 8-byte words.  The same pass writes
+// y0[m, q, :] = sum_p W[0, wr - 1, p, q] x[m, p, :] - shift x[m, q, :].
+__global__ void __launch_bounds__(256) oz_premix_a_kernel(const double* __restrict__ x, const double* __restrict__ W,
+                                                          int r, int wr, int d, double* __restrict__ scale,
+                                                          double* __restrict__ sumsq, int8_t* __restrict__ slices,
+                                                          int64_t Kp, int64_t slice_stride, double* __restrict__ y0,
+                                                          const double* __restrict__ shift_dev) {
+  constexpr int S = kOzMaxSlices;
+  extern __shared__ double xs[];  // [d][r + r / 8 + 1]
+  __shared__ double wc[kPmMaxCh][kPmMaxD][kPmMaxD];  // [b][p][q], b = wr - 1 holds the y0 block
+  __shared__ double red[kPmMaxD][8];
+  __shared__ double sc_sh[kPmMaxD];
+  const int m = blockIdx.x, tid = threadIdx.x;
+  const int nb = wr - 1;
+  for (int idx = tid; idx < wr * d * d; idx += blockDim.x) {
+    const int b = idx / (d * d), p = (idx / d) % d, q = idx % d;
+    wc[b][p][q] = W[(b * d + p) * d + q];  // W[0, b, p, q]: the a = 0 row of the (wl, wr, d, d) tensor
+  }
+  const double* xrow = x + (int64_t)m * d * r;
+  // one pad double per 8 entries: the digit loop below reads 8 consecutive ri per thread (stride 9 doubles between
+  // the threads of a warp: conflict-free), the other loops read consecutive ri
+  const int rp = r + r / 8 + 1;
+  auto xi = [rp](int p, int ri) { return p * rp + ri + (ri >> 3); };
+  for (int idx = tid; idx < d * r; idx += blockDim.x) xs[xi(idx / r, idx % r)] = xrow[idx];
+  __syncthreads();
+  // column maxima over (b, ri) for every q
+  double mx[kPmMaxD];
+#pragma unroll
+  for (int q = 0; q < kPmMaxD; ++q) mx[q] = 0.0;
+  for (int ri = tid; ri < r; ri += blockDim.x) {
+    for (int b = 0; b < nb; ++b)
+#pragma unroll
+      for (int q = 0; q < kPmMaxD; ++q)
+        if (q < d) {
+          double v = 0.0;
+          for (int p = 0; p < d; ++p) v = fma(wc[b][p][q], xs[xi(p, ri)], v);
+          mx[q] = fmax(mx[q], fabs(v));
+        }
+  }
+#pragma unroll
+  for (int q = 0; q < kPmMaxD; ++q) {
+    double v = mx[q];
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((tid & 31) == 0) red[q][tid >> 5] = v;
+  }
+  __syncthreads();
+  if (tid < d) {
+    double v = 0.0;
+    for (int w8 = 0; w8 < (int)(blockDim.x >> 5); ++w8) v = fmax(v, red[tid][w8]);
+    const double sc = oz_scale_of((unsigned long long)__double_as_longlong(v));
+    sc_sh[tid] = sc;
+    scale[(int64_t)m * d + tid] = sc;
+    if (sc > 0.0) atomicAdd(sumsq, sc * sc);
+  }
+  __syncthreads();
+  // digits: a thread owns 8 consecutive ri of one (q, b) row piece
+  const int r8 = (r + 7) / 8;
+  for (int item = tid; item < d * nb * r8; item += blockDim.x) {
+    const int i8 = item % r8, b = (item / r8) % nb, q = item / (r8 * nb);
+    const double sc = sc_sh[q];
+    const double inv = sc > 0.0 ? 1.0 / sc : 0.0;
+    uint64_t word[S];
+#pragma unroll
+    for (int sl = 0; sl < S; ++sl) word[sl] = 0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int ri = 8 * i8 + e;
+      double t = 0.0;
+      if (ri < r) {
+        for (int p = 0; p < d; ++p) t = fma(wc[b][p][q], xs[xi(p, ri)], t);
+        t *= inv;
+      }
+#pragma unroll
+      for (int sl = 0; sl < S; ++sl) word[sl] |= (uint64_t)(uint8_t)oz_next_digit(t) << (8 * e);
+    }
+    const int64_t off = ((int64_t)m * d + q) * Kp + (int64_t)b * r + 8 * i8;
+    if (8 * i8 + 8 <= r && (((int64_t)b * r) & 7) == 0) {
+#pragma unroll
+      for (int sl = 0; sl < S; ++sl) *reinterpret_cast<uint64_t*>(slices + sl * slice_stride + off) = word[sl];
+    } else {
+      for (int e = 0; e < 8 && 8 * i8 + e < r; ++e)
+#pragma unroll
+        for (int sl = 0; sl < S; ++sl) slices[sl * slice_stride + off + e] = (int8_t)(word[sl] >> (8 * e));
+    }
+  }
+  // zero the K padding of this block's columns (Kp - nb * r < 64 bytes per row)
+  const int kreal = nb * r, kpad = (int)(Kp - kreal);
+  for (int item = tid; item < d * S * kpad; item += blockDim.x) {
+    const int e = item % kpad, sl = (item / kpad) % S, q = item / (kpad * S);
+    slices[sl * slice_stride + ((int64_t)m * d + q) * Kp + kreal + e] = 0;
+  }
+  if (y0 != nullptr) {
+    const double shift = shift_dev ? *shift_dev : 0.0;
+    for (int idx = tid; idx < d * r; idx += blockDim.x) {
+      const int q = idx / r, ri = idx % r;
+      double v = -shift * xs[xi(q, ri)];
+      for (int p = 0; p < d; ++p) v = fma(wc[nb][p][q], xs[xi(p, ri)], v);
+      y0[(int64_t)m * d * r + idx] = v;
+    }
+  }
+}
+
+// B side, column maxima: colmax[(q, s)] = max over (a, li) of |sum_p W[a + 1, wr - 1, p, q] x[li, p, s]|
+__global__ void __launch_bounds__(256) oz_premix_b_colmax_kernel(const double* __restrict__ x,
+                                                                 const double* __restrict__ W, int l, int r, int wl,
+                                                                 int wr, int d, int l_chunk,
+                                                                 unsigned long long* __restrict__ colmax) {
+  __shared__ double wc[kPmMaxCh][kPmMaxD][kPmMaxD];  // [a][p][q] = W[a + 1, wr - 1, p, q]
+  const int na = wl - 1;
+  for (int idx = threadIdx.x; idx < na * d * d; idx += blockDim.x) {
+    const int a = idx / (d * d), p = (idx / d) % d, q = idx % d;
+    wc[a][p][q] = W[((((int64_t)(a + 1)) * wr + (wr - 1)) * d + p) * d + q];
+  }
+  __syncthreads();
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= r) return;
+  const int l0 = blockIdx.y * l_chunk, l1 = min(l, l0 + l_chunk);
+  double mx[kPmMaxD];
+#pragma unroll
+  for (int q = 0; q < kPmMaxD; ++q) mx[q] = 0.0;
+  for (int li = l0; li < l1; ++li) {
+    double xv[kPmMaxD];
+#pragma unroll
+    for (int p = 0; p < kPmMaxD; ++p) xv[p] = p < d ? x[((int64_t)li * d + p) * r + s] : 0.0;
+    for (int a = 0; a < na; ++a)
+#pragma unroll
+      for (int q = 0; q < kPmMaxD; ++q)
+        if (q < d) {
+          double v = 0.0;
+#pragma unroll
+          for (int p = 0; p < kPmMaxD; ++p)
+            if (p < d) v = fma(wc[a][p][q], xv[p], v);
+          mx[q] = fmax(mx[q], fabs(v));
+        }
+  }
+#pragma unroll
+  for (int q = 0; q < kPmMaxD; ++q)
+    if (q < d && mx[q] > 0.0) atomicMax(&colmax[(int64_t)q * r + s], (unsigned long long)__double_as_longlong(mx[q]));
+}
+
+// B side, digits: Xb[(a, li), (q, s)] for a < wl - 1.  Block = 32 values of s x 128 values of li (the transposing
+// tile of oz_slice_kernel); the x tile is read once per physical index and every (a, q) product is formed from it.
+__global__ void __launch_bounds__(256) oz_premix_b_kernel(const double* __restrict__ x, const double* __restrict__ W,
+                                                          int l, int r, int wl, int wr, int d,
+                                                          const unsigned long long* __restrict__ colmax,
+                                                          double* __restrict__ scale, double* __restrict__ sumsq,
+                                                          int8_t* __restrict__ slices, int64_t Kp,
+                                                          int64_t slice_stride) {
+  constexpr int S = kOzMaxSlices;
+  __shared__ __align__(16) int8_t tile[S][32][132];
+  __shared__ double wc[kPmMaxCh][kPmMaxD][kPmMaxD];
+  const int na = wl - 1;
+  for (int idx = threadIdx.x; idx < na * d * d; idx += blockDim.x) {
+    const int a = idx / (d * d), p = (idx / d) % d, q = idx % d;
+    wc[a][p][q] = W[((((int64_t)(a + 1)) * wr + (wr - 1)) * d + p) * d + q];
+  }
+  const int s0 = blockIdx.x * 32, l0 = blockIdx.y * 128;
+  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
+  const int s = s0 + tx;
+  double sc[kPmMaxD], inv[kPmMaxD];
+#pragma unroll
+  for (int q = 0; q < kPmMaxD; ++q) {
+    sc[q] = (q < d && s < r) ? oz_scale_of(colmax[(int64_t)q * r + s]) : 0.0;
+    inv[q] = sc[q] > 0.0 ? 1.0 / sc[q] : 0.0;
+  }
+  if (blockIdx.y == 0 && ty == 0) {
+    double part = 0.0;
+#pragma unroll
+    for (int q = 0; q < kPmMaxD; ++q)
+      if (q < d) {
+        if (s < r) scale[(int64_t)q * r + s] = sc[q];
+        part += sc[q] * sc[q];
+      }
+    part = warp_sum(part);
+    if (tx == 0 && part > 0.0) atomicAdd(sumsq, part);
+  }
+  __syncthreads();
+  // x values of this thread's 16 (li) x d entries stay in registers across the (a, q) loop
+  double xv[16][kPmMaxD];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int li = l0 + ty + 8 * j;
+#pragma unroll
+    for (int p = 0; p < kPmMaxD; ++p) xv[j][p] = (p < d && li < l && s < r) ? x[((int64_t)li * d + p) * r + s] : 0.0;
+  }
+  for (int a = 0; a < na; ++a)
+    for (int q = 0; q < d; ++q) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        double t = 0.0;
+#pragma unroll
+        for (int p = 0; p < kPmMaxD; ++p)
+          if (p < d) t = fma(wc[a][p][q], xv[j][p], t);
+        t *= inv[q];
+#pragma unroll
+        for (int sl = 0; sl < S; ++sl) tile[sl][tx][ty + 8 * j] = oz_next_digit(t);
+      }
+      __syncthreads();
+      const int64_t kbase = (int64_t)a * l + l0;
+      for (int idx = threadIdx.x; idx < S * 32 * 32; idx += 256) {
+        const int w = idx % 32, cc = (idx / 32) % 32, sl = idx / 1024;
+        if (s0 + cc < r && l0 + 4 * w < l) {
+          int8_t* dst = slices + sl * slice_stride + ((int64_t)q * r + s0 + cc) * Kp + kbase + 4 * w;
+          if (l0 + 4 * w + 4 <= l && ((kbase & 3) == 0))
+            *reinterpret_cast<int32_t*>(dst) = *reinterpret_cast<const int32_t*>(&tile[sl][cc][4 * w]);
+          else
+            for (int e = 0; e < 4 && l0 + 4 * w + e < l; ++e) dst[e] = tile[sl][cc][4 * w + e];
+        }
+      }
+      __syncthreads();
+    }
+  // K padding: rows (q, s) of this block's columns, bytes [na * l, Kp), written by the l0 == 0 blocks
+  if (blockIdx.y == 0) {
+    const int kreal = na * l, kpad = (int)(Kp - kreal);
+    for (int item = threadIdx.x; item < 32 * d * S * kpad; item += 256) {
+      const int e = item % kpad, sl = (item / kpad) % S, q = (item / (kpad * S)) % d, cc = item / (kpad * S * d);
+      if (s0 + cc < r) slices[sl * slice_stride + ((int64_t)q * r + s0 + cc) * Kp + kreal + e] = 0;
+    }
+  }
+}
+
+// *bound = max(*bound, coef * sqrt(sa2 * sb2)): the normwise error bound of one product (header comment)
+__global__ void oz_bound_kernel(const double* __restrict__ sa2, const double* __restrict__ sb2, double coef,
+                                double* __restrict__ bound) {
+  const double b = coef * sqrt(*sa2 * *sb2);
+  if (b > *bound) *bound = b;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -108,168 +351,10 @@ __device__ __forceinline__ void oz_mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   } while (!done);
 }
-__device__ __forceinline__ void oz_tma_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(oz_smem_u32(dst)), "l"(map), "r"(oz_smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-// K-major operand tile, rows of kOzBK bytes, 64B swizzle: SBO = 8 rows * 64 B, LBO unused, version 1
-__device__ __forceinline__ uint64_t oz_smem_desc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);             // start address
-  d |= (uint64_t)0 << 16;                             // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)((8 * kOzBK) >> 4) << 32;            // stride byte offset between 8-row groups
-  d |= (uint64_t)1 << 46;                             // descriptor version (sm_100)
-  d |= (uint64_t)4 << 61;                             // layout type: SWIZZLE_64B
-  return d;
-}
-__device__ __forceinline__ void oz_mma_i8(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-  const uint32_t z = 0;
-  asm volatile(
-      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n}\n"
-      ::"r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(z), "r"(z), "r"(z), "r"(z)
-      : "memory");
-}
-__device__ __forceinline__ void oz_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(oz_smem_u32(bar))
-               : "memory");
-}
 
-template <int S>
-__global__ void __launch_bounds__(256, 1)
-    oz_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const double* __restrict__ scaleA, const double* __restrict__ scaleB, GemmOut out, int M, int N,
-                  int KT, int accumulate) {
-  constexpr int kABytes = S * kOzBM * kOzBK, kBBytes = S * kOzBN * kOzBK;
-  constexpr int kStageBytes = kABytes + kBBytes;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kOzStages * kStageBytes);
-  uint64_t* empty_bar = full_bar + kOzStages;
-  uint64_t* tmem_full = empty_bar + kOzStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // grouped rasterisation (8 m-tiles per sweep over n) so that co-resident CTAs share operand panels in L2
-  int tm, tn;
-  {
-    const int tiles_m = (M + kOzBM - 1) / kOzBM, tiles_n = (N + kOzBN - 1) / kOzBN;
-    constexpr int GROUP = 8;
-    const int tile = blockIdx.x, per_group = GROUP * tiles_n;
-    const int gid = tile / per_group, first_m = gid * GROUP;
-    const int gsz = min(tiles_m - first_m, GROUP), rem = tile - gid * per_group;
-    tm = first_m + rem % gsz;
-    tn = rem / gsz;
-  }
-  const int m0 = tm * kOzBM, n0 = tn * kOzBN;
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < kOzStages; ++s) {
-      oz_mbar_init(&full_bar[s], 1);
-      oz_mbar_init(&empty_bar[s], 1);
-    }
-    oz_mbar_init(tmem_full, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(oz_smem_u32(tmem_slot)), "r"(512u)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (int kt = 0; kt < KT; ++kt) {
-        oz_mbar_wait(&empty_bar[stage], phase ^ 1);
-        oz_mbar_expect_tx(&full_bar[stage], kStageBytes);
-        uint8_t* sa = smem + stage * kStageBytes;
-        oz_tma_3d(sa, &tmA, &full_bar[stage], kt * kOzBK, m0, 0);
-        oz_tma_3d(sa + kABytes, &tmB, &full_bar[stage], kt * kOzBK, n0, 0);
-        if (++stage == kOzStages) { stage = 0; phase ^= 1; }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // instruction descriptor: D = S32, A = B = signed int8, both K-major, N = 64, M = 128
-      constexpr uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kOzBN >> 3) << 17) | ((uint32_t)(kOzBM >> 4) << 24);
-      uint32_t stage = 0, phase = 0;
-      for (int kt = 0; kt < KT; ++kt) {
-        oz_mbar_wait(&full_bar[stage], phase);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sa = oz_smem_u32(smem + stage * kStageBytes);
-        const uint32_t sb = sa + kABytes;
-#pragma unroll
-        for (int kk = 0; kk < kOzBK / 32; ++kk) {
-#pragma unroll
-          for (int i = 0; i < S; ++i) {
-            const uint64_t da = oz_smem_desc(sa + i * (kOzBM * kOzBK) + kk * 32);
-#pragma unroll
-            for (int j = 0; j < S - i; ++j) {
-              const uint64_t db = oz_smem_desc(sb + j * (kOzBN * kOzBK) + kk * 32);
-              // accumulator d = i + j; its first contribution in program order is (kt, kk, i) = (0, 0, 0)
-              oz_mma_i8(tmem_base + (uint32_t)((i + j) * kOzBN), da, db, idesc, (kt | kk | i) != 0 ? 1u : 0u);
-            }
-          }
-        }
-        oz_commit(&empty_bar[stage]);  // frees the stage once these MMAs have read it
-        if (++stage == kOzStages) { stage = 0; phase ^= 1; }
-      }
-      oz_commit(tmem_full);
-    }
-  } else if (warp >= 4) {
-    const int q = warp & 3;  // TMEM lane quadrant this warp may read
-    oz_mbar_wait(tmem_full, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int m = m0 + q * 32 + lane;
-    const double sa = (m < M) ? scaleA[m] : 0.0;
-    double* crow = nullptr;
-    if (m < M) crow = out.C + (int64_t)(m / out.m_inner) * out.c_outer + (int64_t)(m % out.m_inner) * out.c_inner;
-    for (int c0 = 0; c0 < kOzBN; c0 += 8) {
-      double acc[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) acc[c] = 0.0;
-#pragma unroll
-      for (int d = S - 1; d >= 0; --d) {  // smallest weights first
-        uint32_t v[8];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(d * kOzBN + c0);
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-                     : "r"(taddr));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        const double wgt = ldexp(1.0, -7 * (d + 2));
-#pragma unroll
-        for (int c = 0; c < 8; ++c) acc[c] = fma((double)(int)v[c], wgt, acc[c]);
-      }
-      if (m < M) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const int n = n0 + c0 + c;
-          if (n < N) {
-            const double val = acc[c] * sa * scaleB[n];
-            crow[n] = accumulate ? crow[n] + val : val;
-          }
-        }
-      }
-    }
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// tcgen05 kernel, second generation: CTA pair (cta_group::2), 256 x 128 tile, two accumulator passes
-// ---------------------------------------------------------------------------------------------
-// ncu on oz_mma_kernel (profiles/r01_oz_mma_kernel_ncu_full_raw.csv) shows the tensor cores' shared-memory
+// CTA pair (cta_group::2), 256 x 128 tile, two accumulator passes.
+// ncu on the first-generation kernel (one CTA per 128 x 64 tile, all eight accumulators at once; removed, its
+// capture is profiles/r01_oz_mma_kernel_ncu_full_raw.csv) showed the tensor cores' shared-memory
 // operand pipe at 74-89 % of peak with the MMA pipe only 50-60 % busy: an M=128, N=64, K=32 int8 MMA reads
 // 4 KB of A + 2 KB of B = 48 wavefronts of 128 B for 32 cycles of math.  N per instruction is capped by TMEM
 // (S accumulators x N columns <= 512), so this kernel (a) runs the S diagonals in two passes of <= 4
@@ -604,7 +689,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kOz2Threads, 1)
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
-
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -621,18 +705,16 @@ static PFN_cuTensorMapEncodeTiled_v12000 oz_encoder() {
   return fn;
 }
 
-// slices[s][row][k]: dims (Kp, rows, S), box (kOzBK, box_rows, S), 64B swizzle
-static int oz_make_map(CUtensorMap* map, const int8_t* base, int64_t Kp, int rows, int S, int box_rows,
-                       int box_slices = 0) {
-  if (box_slices <= 0) box_slices = S;
+// slices[s][row][k]: dims (Kp, rows, kOzMaxSlices), box (kOzBK, box_rows, 4), 64B swizzle
+static int oz_make_map(CUtensorMap* map, const int8_t* base, int64_t Kp, int rows, int box_rows) {
   auto enc = oz_encoder();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled not available from the driver");
     return TNPY_ECUDA;
   }
-  cuuint64_t dims[3] = {(cuuint64_t)Kp, (cuuint64_t)rows, (cuuint64_t)S};
+  cuuint64_t dims[3] = {(cuuint64_t)Kp, (cuuint64_t)rows, (cuuint64_t)kOzMaxSlices};
   cuuint64_t strides[2] = {(cuuint64_t)Kp, (cuuint64_t)Kp * rows};
-  cuuint32_t box[3] = {(cuuint32_t)kOzBK, (cuuint32_t)box_rows, (cuuint32_t)box_slices};
+  cuuint32_t box[3] = {(cuuint32_t)kOzBK, (cuuint32_t)box_rows, 4};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<int8_t*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -644,31 +726,73 @@ static int oz_make_map(CUtensorMap* map, const int8_t* base, int64_t Kp, int row
   return TNPY_OK;
 }
 
-// `scale` doubles as scratch for the column maxima: the first MN 8-byte words of `colmax_scratch`.
-template <int S>
-static int oz_slice(const double* P, int64_t ld, int K, int MN, double* scale, unsigned long long* colmax_scratch,
-                    int8_t* slices, int64_t Kp, cudaStream_t stream) {
-  TNPY_CUDA_OK(cudaMemsetAsync(colmax_scratch, 0, sizeof(unsigned long long) * (size_t)MN, stream));
+int64_t oz_kp(int K) { return ((int64_t)K + kOzBK - 1) / kOzBK * kOzBK; }
+
+size_t oz_operand_bytes(int cols, int K) {
+  return Workspace::need((size_t)kOzMaxSlices * cols * oz_kp(K), 1) + Workspace::need(cols) + Workspace::need(cols + 1);
+}
+
+bool oz_operand_take(Workspace& ws, int cols, int K, OzOperand* out) {
+  out->cols = cols;
+  out->K = K;
+  out->Kp = oz_kp(K);
+  out->slices = ws.take<int8_t>((size_t)kOzMaxSlices * cols * out->Kp);
+  out->scale = ws.take<double>(cols);
+  out->colmax = ws.take<unsigned long long>(cols + 1);  // [cols] is the sum of squared scales
+  if (!out->slices || !out->scale || !out->colmax) return false;
+  out->sumsq = reinterpret_cast<double*>(out->colmax + cols);
+  return true;
+}
+
+int oz_slice_operand(const double* P, int64_t ld, OzRowMap rows, const OzOperand& op, cudaStream_t stream) {
+  const int K = op.K, MN = op.cols;
+  TNPY_CUDA_OK(cudaMemsetAsync(op.colmax, 0, sizeof(unsigned long long) * (size_t)(MN + 1), stream));
   const int k_chunk = K > 4096 ? 256 : 64;
   dim3 g1(ceil_div(MN, 256), ceil_div(K, k_chunk));
-  oz_colmax_kernel<<<g1, 256, 0, stream>>>(P, ld, K, MN, k_chunk, colmax_scratch);
+  oz_colmax_kernel<<<g1, 256, 0, stream>>>(P, ld, rows, K, MN, k_chunk, op.colmax);
   TNPY_LAUNCH_OK();
-  dim3 grid(ceil_div(MN, 32), (unsigned)((Kp + 127) / 128));
-  oz_slice_kernel<S><<<grid, 256, 0, stream>>>(P, ld, K, MN, colmax_scratch, scale, slices, Kp, (int64_t)MN * Kp);
+  dim3 grid(ceil_div(MN, 32), (unsigned)((op.Kp + 127) / 128));
+  oz_slice_kernel<<<grid, 256, 0, stream>>>(P, ld, rows, K, MN, op.colmax, op.scale, op.sumsq, op.slices, op.Kp,
+                                            (int64_t)MN * op.Kp);
   TNPY_LAUNCH_OK();
   return TNPY_OK;
 }
 
-// 1 = one CTA per 128 x 64 tile (oz_mma_kernel), 2 = CTA pair per 256 x 128 tile in two passes (oz2_mma_kernel)
-static std::atomic<int> g_oz_variant{0};
-static int oz_variant() {
-  int v = g_oz_variant.load();
-  if (v == 0) {
-    const char* e = getenv("TNPY_OZAKI_VARIANT");
-    v = (e && e[0] == '1') ? 1 : 2;
-    g_oz_variant.store(v);
-  }
-  return v;
+static bool premix_dims_ok(int r, int wl, int wr, int d) {
+  return d <= kPmMaxD && wl - 1 <= kPmMaxCh && wr <= kPmMaxCh && wl >= 2 && wr >= 2;
+}
+// padded row length of the x row staged by oz_premix_a_kernel (one extra double per 8: conflict-free 8-strided reads)
+static size_t premix_a_smem(int r, int d) { return sizeof(double) * (size_t)d * (r + r / 8 + 1); }
+
+bool oz_premix_applicable(int l, int r, int wl, int wr, int d) {
+  return premix_dims_ok(r, wl, wr, d) && premix_a_smem(r, d) <= 200 * 1024 && l >= 1;
+}
+
+int oz_premix_a(const double* x, const double* W, int l, int r, int wl, int wr, int d, const OzOperand& op, double* y0,
+                const double* shift_dev, cudaStream_t stream) {
+  TNPY_CHECK_ARG(oz_premix_applicable(l, r, wl, wr, d), "dimensions outside the direct path's limits");
+  TNPY_CHECK_ARG(op.cols == l * d && op.K == (wr - 1) * r, "operand shape mismatch");
+  TNPY_TRY(set_max_dynamic_smem(oz_premix_a_kernel, 200 * 1024));
+  TNPY_CUDA_OK(cudaMemsetAsync(op.sumsq, 0, sizeof(double), stream));
+  oz_premix_a_kernel<<<l, 256, premix_a_smem(r, d), stream>>>(x, W, r, wr, d, op.scale, op.sumsq, op.slices, op.Kp,
+                                                             (int64_t)op.cols * op.Kp, y0, shift_dev);
+  TNPY_LAUNCH_OK();
+  return TNPY_OK;
+}
+
+int oz_premix_b(const double* x, const double* W, int l, int r, int wl, int wr, int d, const OzOperand& op,
+                cudaStream_t stream) {
+  TNPY_CHECK_ARG(oz_premix_applicable(l, r, wl, wr, d), "dimensions outside the direct path's limits");
+  TNPY_CHECK_ARG(op.cols == d * r && op.K == (wl - 1) * l, "operand shape mismatch");
+  TNPY_CUDA_OK(cudaMemsetAsync(op.colmax, 0, sizeof(unsigned long long) * (size_t)(op.cols + 1), stream));
+  const int l_chunk = l > 4096 ? 256 : 64;
+  oz_premix_b_colmax_kernel<<<dim3(ceil_div(r, 256), ceil_div(l, l_chunk)), 256, 0, stream>>>(x, W, l, r, wl, wr, d,
+                                                                                             l_chunk, op.colmax);
+  TNPY_LAUNCH_OK();
+  oz_premix_b_kernel<<<dim3(ceil_div(r, 32), ceil_div(l, 128)), 256, 0, stream>>>(
+      x, W, l, r, wl, wr, d, op.colmax, op.scale, op.sumsq, op.slices, op.Kp, (int64_t)op.cols * op.Kp);
+  TNPY_LAUNCH_OK();
+  return TNPY_OK;
 }
 
 // C tile += scratch tiles of the K ranges ks = 1 .. splits-1, in that fixed order (deterministic).
@@ -691,57 +815,49 @@ __global__ void __launch_bounds__(256) oz2_tail_combine_kernel(GemmOut out, int 
   }
 }
 
-// scratch for the tail tiles of oz2_gemm (grow-only, per process)
-static int oz2_tail_scratch(size_t need, double** out) {
-  static void* ptr = nullptr;
-  static size_t bytes = 0;
-  if (bytes < need) {
-    if (ptr) {
-      TNPY_CUDA_OK(cudaDeviceSynchronize());
-      TNPY_CUDA_OK(cudaFree(ptr));
-      ptr = nullptr;
-      bytes = 0;
-    }
-    TNPY_CUDA_OK(cudaMalloc(&ptr, need));
-    bytes = need;
-  }
-  *out = static_cast<double*>(ptr);
-  return TNPY_OK;
-}
-
-template <int S>
-static int oz2_gemm(const int8_t* As, const double* scaleA, const int8_t* Bs, const double* scaleB, GemmOut out, int M,
-                    int N, int64_t Kp, int accumulate, cudaStream_t stream) {
-  CUtensorMap tmA, tmB;
-  TNPY_TRY(oz_make_map(&tmA, As, Kp, M, S, kOzBM, 4));
-  TNPY_TRY(oz_make_map(&tmB, Bs, Kp, N, S, kOzBN, 4));
-  constexpr int smem = kOz2Slots * kOz2Slot + 256 + 1024;
-  static bool configured = false;
-  if (!configured) {
-    TNPY_CUDA_OK(cudaFuncSetAttribute(oz2_mma_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
-  const int tiles_m = ceil_div(M, 2 * kOzBM), tiles_n = ceil_div(N, kOz2TileN), tiles = tiles_m * tiles_n;
-  const int KT = (int)(Kp / kOzBK);
-  // One CTA pair per SM pair at a time (shared memory): the last wave holds tiles % pairs tiles.  Cut those
-  // along K so that the last wave is as wide as the machine; parts ks > 0 go to scratch tiles and are added
-  // back in a fixed order.
+// One CTA pair per SM pair at a time (shared memory): the last wave holds tiles % pairs tiles.  Cut those along K
+// so that the last wave is as wide as the machine; parts ks > 0 go to scratch tiles and are added back in a fixed
+// order.  Worth it only when the last wave is a sizeable part of the run (each part pays its own two epilogues).
+static Oz2Tail oz2_plan_tail(int M, int N, int KT) {
+  const int tiles = ceil_div(M, 2 * kOzBM) * ceil_div(N, kOz2TileN);
   const int pairs = sm_count() / 2;
   Oz2Tail tail{tiles, 0, 1, nullptr};
   const int rem = tiles % pairs;
-  if (rem > 0 && getenv("TNPY_OZAKI_NO_TAIL_SPLIT") == nullptr) {
+  if (rem > 0) {
     int splits = pairs / rem;
     while (splits > 1 && KT / splits < 8) --splits;
     if (splits > 4) splits = 4;
     const double full = (double)(tiles / pairs);
-    // worth it only when the last wave is a sizeable part of the run (each part pays its own two epilogues)
-    if (splits > 1 && (full + 1.0 / splits + 0.04) / (full + 1.0) < 0.93) {
-      tail = Oz2Tail{tiles - rem, rem, splits, nullptr};
-      TNPY_TRY(oz2_tail_scratch((size_t)(splits - 1) * rem * 2 * kOzBM * kOz2TileN * sizeof(double), &tail.scratch));
-    }
+    if (splits > 1 && (full + 1.0 / splits + 0.04) / (full + 1.0) < 0.93) tail = Oz2Tail{tiles - rem, rem, splits, nullptr};
+  }
+  return tail;
+}
+
+size_t oz_mma_scratch_bytes(int M, int N) {
+  // upper bound over K: at most 3 extra parts of fewer than `pairs` tiles
+  const int pairs = sm_count() / 2;
+  const int tiles = ceil_div(M, 2 * kOzBM) * ceil_div(N, kOz2TileN);
+  const int rem = tiles % pairs;
+  return rem == 0 ? 256 : Workspace::need((size_t)3 * rem * 2 * kOzBM * kOz2TileN) + 256;
+}
+
+template <int S>
+static int oz2_launch(const OzOperand& A, const OzOperand& B, GemmOut out, int M, int N, int accumulate, Workspace& ws,
+                      cudaStream_t stream) {
+  CUtensorMap tmA, tmB;
+  TNPY_TRY(oz_make_map(&tmA, A.slices, A.Kp, M, kOzBM));
+  TNPY_TRY(oz_make_map(&tmB, B.slices, B.Kp, N, kOzBN));
+  constexpr int smem = kOz2Slots * kOz2Slot + 256 + 1024;
+  TNPY_TRY(set_max_dynamic_smem(oz2_mma_kernel<S>, smem));
+  const int tiles_m = ceil_div(M, 2 * kOzBM), tiles_n = ceil_div(N, kOz2TileN);
+  const int KT = (int)(A.Kp / kOzBK);
+  Oz2Tail tail = oz2_plan_tail(M, N, KT);
+  if (tail.splits > 1) {
+    tail.scratch = ws.take<double>((size_t)(tail.splits - 1) * tail.rem * 2 * kOzBM * kOz2TileN);
+    if (!tail.scratch) tail = Oz2Tail{tiles_m * tiles_n, 0, 1, nullptr};  // no room: run the tail unsplit
   }
   const int items = tail.n_full + tail.rem * tail.splits;
-  oz2_mma_kernel<S><<<2 * items, kOz2Threads, smem, stream>>>(tmA, tmB, scaleA, scaleB, out, M, N, KT, accumulate, tail);
+  oz2_mma_kernel<S><<<2 * items, kOz2Threads, smem, stream>>>(tmA, tmB, A.scale, B.scale, out, M, N, KT, accumulate, tail);
   TNPY_LAUNCH_OK();
   if (tail.splits > 1) {
     oz2_tail_combine_kernel<<<dim3(tail.rem, 16), 256, 0, stream>>>(out, M, N, tiles_m, tiles_n, tail);
@@ -750,178 +866,34 @@ static int oz2_gemm(const int8_t* As, const double* scaleA, const int8_t* Bs, co
   return TNPY_OK;
 }
 
-template <int S>
-static int oz_gemm(const int8_t* As, const double* scaleA, const int8_t* Bs, const double* scaleB, GemmOut out, int M,
-                   int N, int64_t Kp, int accumulate, cudaStream_t stream) {
-  if (oz_variant() == 2) return oz2_gemm<S>(As, scaleA, Bs, scaleB, out, M, N, Kp, accumulate, stream);
-  CUtensorMap tmA, tmB;
-  TNPY_TRY(oz_make_map(&tmA, As, Kp, M, S, kOzBM));
-  TNPY_TRY(oz_make_map(&tmB, Bs, Kp, N, S, kOzBN));
-  constexpr int smem = kOzStages * S * (kOzBM + kOzBN) * kOzBK + 1024 + 128;
-  static bool configured = false;
-  if (!configured) {
-    TNPY_CUDA_OK(cudaFuncSetAttribute(oz_mma_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
+int oz_mma(const OzOperand& A, const OzOperand& B, GemmOut out, int M, int N, int S, int accumulate, Workspace& ws,
+           double* bound_dev, cudaStream_t stream) {
+  TNPY_CHECK_ARG(A.cols == M && B.cols == N && A.Kp == B.Kp && A.K == B.K, "operand shapes do not match the product");
+  TNPY_CHECK_ARG(A.K <= 65536, "K too large for exact int32 accumulation");
+  TNPY_CHECK_ARG(S >= 6 && S <= kOzMaxSlices, "slices must be 6, 7 or 8");
+  if (bound_dev) {
+    const double e_s = (S + 2) / 4.0 * ldexp(1.0, -7 * S);
+    oz_bound_kernel<<<1, 1, 0, stream>>>(A.sumsq, B.sumsq, (double)A.K * e_s, bound_dev);
+    TNPY_LAUNCH_OK();
   }
-  const int grid = ceil_div(N, kOzBN) * ceil_div(M, kOzBM);
-  oz_mma_kernel<S><<<grid, 256, smem, stream>>>(tmA, tmB, scaleA, scaleB, out, M, N, (int)(Kp / kOzBK), accumulate);
-  TNPY_LAUNCH_OK();
-  return TNPY_OK;
-}
-
-static int64_t oz_kp_(int K) { return ((int64_t)K + kOzBK - 1) / kOzBK * kOzBK; }
-
-// Library-internal grow-only scratch for the slices (the chains call gemm_tn without a workspace for
-// this purpose).  One buffer per process; calls are expected on one stream at a time.
-struct OzScratch {
-  void* ptr = nullptr;
-  size_t bytes = 0;
-};
-static int oz_scratch(size_t need, void** out) {
-  static OzScratch sc;
-  if (sc.bytes < need) {
-    if (sc.ptr) {
-      TNPY_CUDA_OK(cudaDeviceSynchronize());
-      TNPY_CUDA_OK(cudaFree(sc.ptr));
-      sc.ptr = nullptr;
-      sc.bytes = 0;
-    }
-    const size_t want = need + need / 8;
-    TNPY_CUDA_OK(cudaMalloc(&sc.ptr, want));
-    sc.bytes = want;
+  switch (S) {
+    case 6: return oz2_launch<6>(A, B, out, M, N, accumulate, ws, stream);
+    case 7: return oz2_launch<7>(A, B, out, M, N, accumulate, ws, stream);
+    default: return oz2_launch<8>(A, B, out, M, N, accumulate, ws, stream);
   }
-  *out = sc.ptr;
-  return TNPY_OK;
 }
 
 static std::atomic<int> g_oz_slices{8};
-static std::atomic<int> g_oz_scope_slices{0};  // override inside an eigensolve whose tolerance allows fewer slices
-int ozaki_slices() {
-  const int o = g_oz_scope_slices.load();
-  return o ? o : g_oz_slices.load();
-}
-// 0 clears the override.  7 slices: error ~2e-14 |A|^T|B| per GEMM, far below a residual tolerance >= 1e-10 ||A||.
-void ozaki_scope_slices(int slices) { g_oz_scope_slices.store(slices); }
+int ozaki_slices() { return g_oz_slices.load(); }
 
 bool ozaki_applicable(int M, int N, int K) {
   // below ~chi = 1024 the slicing passes and extra launches cost more than the faster MMA saves (measured at chi = 512)
   return K <= 65536 && K >= 64 && M >= 128 && N >= 64 && (double)M * N * K >= 6.0e9;
 }
 
-// Slices of constant B operands (the environments L and R during one local eigensolve) are kept across calls:
-// between ozaki_const_scope(true) and ozaki_const_scope(false) the caller vouches that the B operand behind a
-// given (pointer, ld, K, N) does not change, so it is sliced once per scope instead of once per matvec.
-struct OzConstEntry {
-  const double* ptr = nullptr;
-  int64_t ld = 0;
-  int K = 0, N = 0, S = 0;
-  bool valid = false;
-  void* buf = nullptr;
-  size_t bytes = 0;
-};
-static OzConstEntry g_oz_const[4];
-static std::atomic<int> g_oz_const_depth{0};
-static int g_oz_const_next = 0;
-
-void ozaki_const_scope(bool on) {
-  if (on) {
-    if (g_oz_const_depth.fetch_add(1) == 0)
-      for (auto& e : g_oz_const) e.valid = false;
-  } else {
-    if (g_oz_const_depth.fetch_sub(1) == 1)
-      for (auto& e : g_oz_const) e.valid = false;
-  }
-}
-
-// Returns the cached (or freshly filled) slices of B; *fresh tells the caller to run the slicing kernels.
-static int oz_const_lookup(const double* B, int64_t ldb, int K, int N, int S, int64_t Kp, int8_t** slices, double** scale,
-                           unsigned long long** colmax, bool* fresh) {
-  for (auto& e : g_oz_const)
-    if (e.valid && e.ptr == B && e.ld == ldb && e.K == K && e.N == N && e.S == S) {
-      Workspace ws(e.buf, e.bytes);
-      *slices = ws.take<int8_t>((size_t)S * N * Kp);
-      *scale = ws.take<double>(N);
-      *colmax = ws.take<unsigned long long>(N);
-      *fresh = false;
-      return TNPY_OK;
-    }
-  OzConstEntry& e = g_oz_const[g_oz_const_next];
-  g_oz_const_next = (g_oz_const_next + 1) % 4;
-  const size_t need = Workspace::need((size_t)S * N * Kp, 1) + 2 * Workspace::need(N) + 512;
-  if (e.bytes < need) {
-    if (e.buf) {
-      TNPY_CUDA_OK(cudaDeviceSynchronize());
-      TNPY_CUDA_OK(cudaFree(e.buf));
-      e.buf = nullptr;
-      e.bytes = 0;
-    }
-    TNPY_CUDA_OK(cudaMalloc(&e.buf, need));
-    e.bytes = need;
-  }
-  e.ptr = B; e.ld = ldb; e.K = K; e.N = N; e.S = S; e.valid = true;
-  Workspace ws(e.buf, e.bytes);
-  *slices = ws.take<int8_t>((size_t)S * N * Kp);
-  *scale = ws.take<double>(N);
-  *colmax = ws.take<unsigned long long>(N);
-  *fresh = true;
-  return TNPY_OK;
-}
-
-// C (+)= A^T B through the int8 tensor cores; operands are sliced into the internal scratch.
-int ozaki_gemm(const double* A, int64_t lda, const double* B, int64_t ldb, GemmOut out, int M, int N, int K,
-               int accumulate, cudaStream_t stream) {
-  const int S = ozaki_slices();
-  const int64_t Kp = oz_kp_(K);
-  const size_t need = Workspace::need((size_t)S * M * Kp, 1) + Workspace::need((size_t)S * N * Kp, 1) +
-                      2 * Workspace::need(M) + 2 * Workspace::need(N) + 1024;
-  void* base = nullptr;
-  TNPY_TRY(oz_scratch(need, &base));
-  Workspace ws(base, need);
-  int8_t* As = ws.take<int8_t>((size_t)S * M * Kp);
-  int8_t* Bs = ws.take<int8_t>((size_t)S * N * Kp);
-  double* sa = ws.take<double>(M);
-  double* sb = ws.take<double>(N);
-  unsigned long long* ma = ws.take<unsigned long long>(M);
-  unsigned long long* mb = ws.take<unsigned long long>(N);
-  if (!As || !Bs || !sa || !sb || !ma || !mb) {
-    set_error("ozaki_gemm: internal scratch layout failed");
-    return TNPY_EWORKSPACE;
-  }
-  bool slice_b = true;
-  if (g_oz_const_depth.load() > 0) TNPY_TRY(oz_const_lookup(B, ldb, K, N, S, Kp, &Bs, &sb, &mb, &slice_b));
-  switch (S) {
-    case 6:
-      TNPY_TRY(oz_slice<6>(A, lda, K, M, sa, ma, As, Kp, stream));
-      if (slice_b) TNPY_TRY(oz_slice<6>(B, ldb, K, N, sb, mb, Bs, Kp, stream));
-      return oz_gemm<6>(As, sa, Bs, sb, out, M, N, Kp, accumulate, stream);
-    case 7:
-      TNPY_TRY(oz_slice<7>(A, lda, K, M, sa, ma, As, Kp, stream));
-      if (slice_b) TNPY_TRY(oz_slice<7>(B, ldb, K, N, sb, mb, Bs, Kp, stream));
-      return oz_gemm<7>(As, sa, Bs, sb, out, M, N, Kp, accumulate, stream);
-    default:
-      TNPY_TRY(oz_slice<8>(A, lda, K, M, sa, ma, As, Kp, stream));
-      if (slice_b) TNPY_TRY(oz_slice<8>(B, ldb, K, N, sb, mb, Bs, Kp, stream));
-      return oz_gemm<8>(As, sa, Bs, sb, out, M, N, Kp, accumulate, stream);
-  }
-}
-
 }  // namespace tnpy
 
 using namespace tnpy;
-
-extern "C" int tnpy_ozaki_const_scope(int on) {
-  ozaki_const_scope(on != 0);
-  return TNPY_OK;
-}
-
-extern "C" int tnpy_set_ozaki_variant(int variant) {
-  if (variant != 1 && variant != 2) {
-    set_error("tnpy_set_ozaki_variant: variant must be 1 (single CTA, 128x64) or 2 (CTA pair, 256x128, two passes)");
-    return TNPY_EINVAL;
-  }
-  g_oz_variant.store(variant);
-  return TNPY_OK;
-}
 
 extern "C" int tnpy_set_ozaki_slices(int slices) {
   if (slices < 6 || slices > kOzMaxSlices) {
@@ -932,12 +904,8 @@ extern "C" int tnpy_set_ozaki_slices(int slices) {
   return TNPY_OK;
 }
 
-static int64_t oz_kp(int K) { return ((int64_t)K + kOzBK - 1) / kOzBK * kOzBK; }
-
-extern "C" size_t tnpy_ozaki_workspace_bytes(int M, int N, int K, int slices) {
-  const int64_t Kp = oz_kp(K);
-  return Workspace::need((size_t)slices * M * Kp, 1) + Workspace::need((size_t)slices * N * Kp, 1) +
-         2 * Workspace::need(M) + 2 * Workspace::need(N) + 1024;
+extern "C" size_t tnpy_ozaki_workspace_bytes(int M, int N, int K, int /*slices*/) {
+  return oz_operand_bytes(M, K) + oz_operand_bytes(N, K) + oz_mma_scratch_bytes(M, N) + Workspace::need(1) + 1024;
 }
 
 // C[m,n] (+)= sum_k A[k,m] B[k,n] in FP64 accuracy on the int8 tensor cores (slices in 6..8).
@@ -950,32 +918,37 @@ extern "C" int tnpy_ozaki_gemm_tn(const double* A, int64_t lda, const double* B,
   TNPY_CHECK_ARG(A && B && C && M > 0 && N > 0 && K > 0, "bad argument");
   TNPY_CHECK_ARG(slices >= 6 && slices <= kOzMaxSlices, "slices must be 6, 7 or 8");
   TNPY_CHECK_ARG(K <= 65536, "K too large for exact int32 accumulation");
-  const int64_t Kp = oz_kp(K);
   Workspace ws(workspace, workspace_bytes);
-  int8_t* As = ws.take<int8_t>((size_t)slices * M * Kp);
-  int8_t* Bs = ws.take<int8_t>((size_t)slices * N * Kp);
-  double* sa = ws.take<double>(M);
-  double* sb = ws.take<double>(N);
-  unsigned long long* ma = ws.take<unsigned long long>(M);
-  unsigned long long* mb = ws.take<unsigned long long>(N);
-  if (!As || !Bs || !sa || !sb || !ma || !mb) {
+  OzOperand a, b;
+  double* bound = ws.take<double>(1);
+  if (!bound || !oz_operand_take(ws, M, K, &a) || !oz_operand_take(ws, N, K, &b)) {
     set_error("tnpy_ozaki_gemm_tn: workspace too small");
     return TNPY_EWORKSPACE;
   }
-  GemmOut out = plain_out(C, ldc, M);
   if (phase != 2) {
-    switch (slices) {
-      case 6: TNPY_TRY(oz_slice<6>(A, lda, K, M, sa, ma, As, Kp, stream)); TNPY_TRY(oz_slice<6>(B, ldb, K, N, sb, mb, Bs, Kp, stream)); break;
-      case 7: TNPY_TRY(oz_slice<7>(A, lda, K, M, sa, ma, As, Kp, stream)); TNPY_TRY(oz_slice<7>(B, ldb, K, N, sb, mb, Bs, Kp, stream)); break;
-      default: TNPY_TRY(oz_slice<8>(A, lda, K, M, sa, ma, As, Kp, stream)); TNPY_TRY(oz_slice<8>(B, ldb, K, N, sb, mb, Bs, Kp, stream)); break;
-    }
+    TNPY_TRY(oz_slice_operand(A, lda, oz_plain_rows(K), a, stream));
+    TNPY_TRY(oz_slice_operand(B, ldb, oz_plain_rows(K), b, stream));
   }
-  if (phase != 1) {
-    switch (slices) {
-      case 6: return oz_gemm<6>(As, sa, Bs, sb, out, M, N, Kp, accumulate, stream);
-      case 7: return oz_gemm<7>(As, sa, Bs, sb, out, M, N, Kp, accumulate, stream);
-      default: return oz_gemm<8>(As, sa, Bs, sb, out, M, N, Kp, accumulate, stream);
-    }
+  if (phase != 1) return oz_mma(a, b, plain_out(C, ldc, M), M, N, slices, accumulate, ws, nullptr, stream);
+  return TNPY_OK;
+}
+
+// The rigorous error bound of the same product (header comment of this file), for tests and callers that want to
+// choose `slices` themselves: K e_S ||sa||_2 ||sb||_2 from the scales left in the workspace by a phase-0/1 call.
+extern "C" int tnpy_ozaki_error_bound(int M, int N, int K, int slices, void* workspace, size_t workspace_bytes,
+                                      double* bound_dev, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TNPY_CHECK_ARG(bound_dev && M > 0 && N > 0 && K > 0 && slices >= 6 && slices <= kOzMaxSlices, "bad argument");
+  Workspace ws(workspace, workspace_bytes);
+  OzOperand a, b;
+  double* scratch = ws.take<double>(1);
+  if (!scratch || !oz_operand_take(ws, M, K, &a) || !oz_operand_take(ws, N, K, &b)) {
+    set_error("tnpy_ozaki_error_bound: workspace too small");
+    return TNPY_EWORKSPACE;
   }
+  TNPY_CUDA_OK(cudaMemsetAsync(bound_dev, 0, sizeof(double), stream));
+  const double e_s = (slices + 2) / 4.0 * ldexp(1.0, -7 * slices);
+  oz_bound_kernel<<<1, 1, 0, stream>>>(a.sumsq, b.sumsq, (double)K * e_s, bound_dev);
+  TNPY_LAUNCH_OK();
   return TNPY_OK;
 }

@@ -550,22 +550,13 @@ __global__ void colscale_kernel(const double* __restrict__ in, const double* __r
 static unsigned int g_trace[64];
 static int g_trace_len = 0;
 
-struct PinnedWord {
-  unsigned int* host = nullptr;
-  PinnedWord() { cudaMallocHost(&host, 64); }
-};
-
 static double jacobi_tol(int m) { return fmax(1e-15, 2.220446049250313e-16 * sqrt((double)m)); }
 
 static bool fits_small(int n, int m) { return sizeof(double) * ((size_t)n * m + (size_t)n * n) <= 200 * 1024; }
 
 // small path: G (n x m, ld m) in place, P (n x n) out
 static int hestenes_small(double* G, int n, int m, double* P, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
-    TNPY_CUDA_OK(cudaFuncSetAttribute(hestenes_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = true;
-  }
+  TNPY_TRY(set_max_dynamic_smem(hestenes_small_kernel, 200 * 1024));
   const size_t bytes = sizeof(double) * ((size_t)n * m + (size_t)n * n);
   const int threads = n >= 32 ? 512 : (n >= 8 ? 256 : 64);
   hestenes_small_kernel<<<1, threads, bytes, stream>>>(G, n, m, m, P, jacobi_tol(m), 60, nullptr);
@@ -597,7 +588,7 @@ static BlockPlan block_plan(int n, int m) {
 // outside the cluster of tiny vectors; see JbPhase.
 static int hestenes_block(double* GP, const BlockPlan& p, int m, int n_big, double* partial, double* Jt, int* skip,
                           unsigned int* counter_dev, cudaStream_t stream, int* sweeps_out) {
-  static PinnedWord pinned;
+  struct { unsigned int* host; } pinned{static_cast<unsigned int*>(thread_pinned_scratch())};
   if (!pinned.host) {
     set_error("hestenes: pinned allocation failed");
     return TNPY_ECUDA;
@@ -605,13 +596,9 @@ static int hestenes_block(double* GP, const BlockPlan& p, int m, int n_big, doub
   const size_t gram_smem = sizeof(double) * kJP * kJST;
   const size_t rot_smem = sizeof(double) * 2 * kJP * (kJP + 1);
   const size_t apply_smem = sizeof(double) * (kJP * kJTS + kJP * kJST);
-  static bool configured = false;
-  if (!configured) {
-    TNPY_CUDA_OK(cudaFuncSetAttribute(jb_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gram_smem));
-    TNPY_CUDA_OK(cudaFuncSetAttribute(jb_rotate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rot_smem));
-    TNPY_CUDA_OK(cudaFuncSetAttribute(jb_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)apply_smem));
-    configured = true;
-  }
+  TNPY_TRY(set_max_dynamic_smem(jb_gram_kernel, (int)gram_smem));
+  TNPY_TRY(set_max_dynamic_smem(jb_rotate_kernel, (int)rot_smem));
+  TNPY_TRY(set_max_dynamic_smem(jb_apply_kernel, (int)apply_smem));
   const double tol = jacobi_tol(m);
   const int width = m + p.n_pad;
   const int max_sweeps = 60;

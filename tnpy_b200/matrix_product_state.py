@@ -309,21 +309,42 @@ class HeffOperator(LinearOperator):
     """``Environment.one_site_matvec(site)``: a SciPy LinearOperator whose matvec runs on the GPU.
 
     Host seam (the reference's contract, :411-440): ``matvec(x)`` takes a host vector of length N
-    (shape (N,) or (N,1)), copies it to the device, applies H_eff through ``tnpy_heff_apply`` and
-    copies the result back as (N,1) / (N,).  ``linalg.eigshmv`` recognises this class and keeps
+    (shape (N,) or (N,1)), copies it to the device, applies H_eff and copies the result back as (N,1) / (N,);
+    ``matmat(X)`` moves the whole block once.  ``linalg.eigshmv`` recognises this class and keeps
     the whole eigensolve on the device instead of calling back per matvec.
+
+    The operator is a *prepared* H_eff (``tnpy_heff_plan``): what depends only on (L, W, R) -- on the tcgen05
+    path the int8 slices of the environments -- is computed at the first application and reused by every later
+    one, as long as the environment at this site is not updated (then it is prepared again).
+
+    ``zero_copy=True`` makes ``matvec`` return a view of one of two alternating pinned buffers (valid until the
+    call after next) instead of a fresh array: for timing loops only, never for block solvers.
     """
 
-    def __init__(self, env: "Environment", site: int):
+    def __init__(self, env: "Environment", site: int, zero_copy: bool = False):
         self.env = env
         self.site = site
+        self.zero_copy = zero_copy
         self.site_shape = tuple(env.device_tensor(site).shape)
+        self._plan = None
+        self._plan_version = None
         n = int(np.prod(self.site_shape))
         super().__init__(dtype=np.dtype("float64"), shape=(n, n))
 
+    def plan(self) -> "_cuda.HeffPlan":
+        flags = self.env.gauge_flags(self.site)
+        version = (self.env.operand_version(self.site), flags)
+        if self._plan is None or self._plan_version != version:
+            if self._plan is not None:
+                self._plan.close()
+            L, W, R = self.env.operands(self.site)
+            l, _, r = self.site_shape
+            self._plan = _cuda.HeffPlan(L, W, R, l, r, flags=flags, w_host=self.env.mpo.as_four_leg(self.site))
+            self._plan_version = version
+        return self._plan
+
     def apply_device(self, x, out=None):
-        L, W, R = self.env.operands(self.site)
-        return _cuda.heff_apply(L, W, R, x.reshape(self.site_shape), out, flags=self.env.gauge_flags(self.site))
+        return self.plan().apply(x.reshape(self.site_shape), out)
 
     def _staging(self):
         import torch
@@ -340,8 +361,7 @@ class HeffOperator(LinearOperator):
         return self._stage
 
     def _matvec(self, x: np.ndarray) -> np.ndarray:
-        """Host vector in, host vector out.  Copies go through pinned staging buffers; the returned
-        array is a view of one of two alternating pinned buffers (valid until the call after next)."""
+        """Host vector in, host vector out; both copies go through pinned staging buffers."""
         import torch
 
         st = self._staging()
@@ -355,7 +375,19 @@ class HeffOperator(LinearOperator):
         out = st["pin_out"][st["flip"]]
         out.copy_(st["yd"].reshape(-1), non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        return out.numpy()
+        return out.numpy() if self.zero_copy else out.numpy().copy()
+
+    def _matmat(self, X: np.ndarray) -> np.ndarray:
+        """Block application (what primme / lobpcg call): one host-to-device copy of the block, one matvec per
+        column on the device, one copy back.  Every column of the result is its own memory."""
+        import torch
+
+        cols = np.ascontiguousarray(np.asarray(X, dtype=np.float64).T)  # (k, N)
+        xd = torch.from_numpy(cols).cuda()
+        yd = torch.empty_like(xd)
+        for i in range(xd.shape[0]):
+            self.apply_device(xd[i].reshape(self.site_shape), yd[i].reshape(self.site_shape))
+        return np.ascontiguousarray(yd.cpu().numpy().T)
 
     def _adjoint(self):
         return self  # H_eff is real symmetric
@@ -449,10 +481,13 @@ class Environment:
         # canonical-gauge shortcuts: is L[site][:, 0, :] / R[site][:, -1, :] the identity?  Measured on the
         # device after every environment update (one scalar read-back), never assumed.
         self._use_identity = use_identity_channels
+        #: runtime switch over the measured shortcuts (benchmarks time the general chain by clearing it)
+        self.use_identity_channels = use_identity_channels
         self._left_identity: Dict[int, bool] = {}
         self._right_identity: Dict[int, bool] = {}
         self.bond_singular_values: Dict[int, object] = {}
         self._image = None  # (site, H_eff psi) left by the last on-device eigensolve, valid until the site changes
+        self._versions: Dict[tuple, int] = {}  # ("L" | "R", site) -> number of times that environment was rewritten
         if canonicalize and share_state_with is None:
             self.right_canonicalize()
         if build_left:  # the reference builds both stacks up front (:247-250)
@@ -516,9 +551,17 @@ class Environment:
             self._right.get(site) if site < self.n_sites - 1 else None
         )
 
+    def operand_version(self, site: int):
+        """Changes whenever L[site] or R[site] is rewritten (environment tensors are updated in place, so a prepared
+        operator must notice)."""
+        return self._versions.get(("L", site), 0), self._versions.get(("R", site), 0)
+
     def gauge_flags(self, site: int) -> int:
-        """TNPY_LEFT_IDENTITY / TNPY_RIGHT_IDENTITY bits valid for H_eff at ``site``."""
+        """TNPY_LEFT_IDENTITY / TNPY_RIGHT_IDENTITY bits valid for H_eff at ``site`` (0 while
+        ``use_identity_channels`` is switched off: the general chain, every channel multiplied out)."""
         flags = 0
+        if not self.use_identity_channels:
+            return 0
         if self._left_identity.get(site, False):
             flags |= _cuda.LEFT_IDENTITY
         if self._right_identity.get(site, False):
@@ -530,6 +573,7 @@ class Environment:
         prev = None if site == 1 else self._left[site - 1]
         flags = _cuda.LEFT_IDENTITY if self._left_identity.get(site - 1, False) else 0
         self._left[site] = _cuda.env_update_left(prev, self._A[site - 1], self._W[site - 1], self._left.get(site), flags)
+        self._versions[("L", site)] = self._versions.get(("L", site), 0) + 1
         self._left_identity[site] = (
             self._use_identity and _cuda.identity_defect(self._left[site], 0) <= self.IDENTITY_TOL
         )
@@ -538,6 +582,7 @@ class Environment:
         prev = None if site == self.n_sites - 2 else self._right[site + 1]
         flags = _cuda.RIGHT_IDENTITY if self._right_identity.get(site + 1, False) else 0
         self._right[site] = _cuda.env_update_right(prev, self._A[site + 1], self._W[site + 1], self._right.get(site), flags)
+        self._versions[("R", site)] = self._versions.get(("R", site), 0) + 1
         w = self._right[site].shape[1]
         self._right_identity[site] = (
             self._use_identity and _cuda.identity_defect(self._right[site], w - 1) <= self.IDENTITY_TOL
@@ -613,8 +658,8 @@ class Environment:
     def one_site_full_matrix(self, site: int) -> np.ndarray:
         return self.one_site_full_matrix_device(site).cpu().numpy()
 
-    def one_site_matvec(self, site: int) -> HeffOperator:
-        return HeffOperator(self, site)
+    def one_site_matvec(self, site: int, zero_copy: bool = False) -> HeffOperator:
+        return HeffOperator(self, site, zero_copy=zero_copy)
 
 
 class MatrixProductStateMeasurements:
