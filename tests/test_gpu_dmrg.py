@@ -247,3 +247,32 @@ def test_perturbation_from_the_solver_image_equals_a_fresh_matvec():
     f.perturb_wave_function(site)
     expected = other + 1e-5 * env.one_site_matvec(site).apply_device(other)
     assert float((env.device_tensor(site) - expected).abs().max()) <= 1e-14 * float(expected.abs().max())
+
+
+def test_heff_operator_matmat_columns_do_not_alias():
+    """SciPy's default LinearOperator.matmat stacks matvec results; with the reference's solver (primme calls matmat)
+    every column must be its own memory.  matvec returns fresh arrays by default (the zero-copy pinned views are an
+    explicit opt-in for timing loops), matmat moves the block once."""
+    from tnpy_b200.matrix_product_state import Environment, MatrixProductState
+    from tnpy_b200.model import XXZ
+
+    n, chi = 10, 16
+    env = Environment(XXZ(n=n, delta=0.5).mpo, MatrixProductState(oracle.random_mps(n, chi, 2, seed=2)))
+    site = 5
+    op = env.one_site_matvec(site)
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((op.shape[0], 4))
+    want = np.column_stack([
+        op.apply_device(torch.from_numpy(np.ascontiguousarray(X[:, i])).cuda()).reshape(-1).cpu().numpy() for i in range(4)
+    ])
+    np.testing.assert_allclose(op.matmat(X), want, rtol=0, atol=1e-13 * np.abs(want).max())
+    np.testing.assert_allclose(op @ X, want, rtol=0, atol=1e-13 * np.abs(want).max())
+    cols = [op.matvec(X[:, i]) for i in range(4)]  # kept results stay valid
+    np.testing.assert_allclose(np.column_stack(cols), want, rtol=0, atol=1e-13 * np.abs(want).max())
+    # against the oracle's H_eff at the same site
+    ref_env = oracle.Environment(XXZ(n=n, delta=0.5).mpo.arrays, oracle.random_mps(n, chi, 2, seed=2))
+    y = ref_env.matvec(site, X[:, 0])
+    np.testing.assert_allclose(cols[0], np.asarray(y).reshape(-1), rtol=0, atol=1e-12 * np.abs(want).max())
+    # the operator notices an environment rewritten in place
+    env.update_right(site)
+    np.testing.assert_allclose(op.matvec(X[:, 1]), want[:, 1], rtol=0, atol=1e-13 * np.abs(want).max())

@@ -86,3 +86,48 @@ def test_shift_invert_parity_with_oracle():
     np.testing.assert_allclose(e_gpu, e_ref, rtol=1e-8)
     a, b = oracle.mps_to_dense(ref.restored_mps), gpu.restored_mps.to_dense()
     assert abs(a @ b) / np.sqrt((a @ a) * (b @ b)) > 1 - 1e-8
+
+
+def test_shift_invert_at_the_reference_test_size():
+    """tests/test_finite_dmrg.py:26-72 as written: n=10, h=10.5, seed=2022, bond_dim 2**6 (bonds compress to 32, so the
+    mid-chain sites have 2048 unknowns: the top of the dense-pencil range)."""
+    from tnpy_b200.finite_dmrg import ShiftInvertDMRG
+    from tnpy_b200.model import RandomHeisenberg
+
+    n, h, seed, offset = 10, 10.5, 2022, 0.1
+    model = RandomHeisenberg(n=n, h=h, seed=seed)
+    evals, evecs = np.linalg.eigh(oracle.full_hamiltonian(model.mpo.arrays))
+    idx = np.where(evals < offset)[0].max()
+    shifted = RandomHeisenberg(n=n, h=h, seed=seed, offset=offset)
+    sidmrg = ShiftInvertDMRG(shifted.mpo, bond_dim=2**6, offset=offset, seed=1)
+    energies = sidmrg.run(tol=1e-8)
+    assert all(st["dense"] for st in sidmrg.solver_stats)
+    np.testing.assert_allclose(energies[-1], evals[idx], atol=1e-6)
+    vec = sidmrg.restored_mps.to_dense()
+    if not np.allclose(vec, evecs[:, idx], atol=1e-6):
+        np.testing.assert_allclose(-vec, evecs[:, idx], atol=1e-6)
+    np.testing.assert_allclose(energies[-1], sidmrg.measurements.expectation_value(model.mpo), atol=1e-6)
+
+
+def test_unconverged_iterative_pencil_raises_and_keeps_the_state():
+    """Above dense_pencil_dim the generalised Davidson is tried; if it does not converge the sweep stops with an
+    error and the site tensor is what it was (never an unconverged vector passed off as the solution)."""
+    from tnpy_b200.finite_dmrg import ShiftInvertDMRG
+    from tnpy_b200.model import RandomHeisenberg
+
+    shifted = RandomHeisenberg(n=10, h=10.5, seed=2022, offset=0.1)
+    sidmrg = ShiftInvertDMRG(shifted.mpo, bond_dim=2**6, offset=0.1, seed=1)
+    sidmrg.dense_pencil_dim = 1024  # the mid-chain sites (2048 unknowns) now iterate
+    site = 5
+    before = sidmrg.environment.device_tensor(site).clone()
+    try:
+        sidmrg._solve_on_device(site, 1e-8, maxiter=60)
+    except RuntimeError as exc:
+        assert "did not converge" in str(exc)
+        assert torch.equal(sidmrg.environment.device_tensor(site), before)
+    else:  # it converged within 60 iterations: then the answer must be the dense one
+        theta_iter = sidmrg.solver_stats[-1]["theta"]
+        sidmrg.environment.device_tensor(site).copy_(before)
+        sidmrg.dense_pencil_dim = 2048
+        theta_dense = sidmrg._solve_on_device(site, 1e-8)
+        assert abs(theta_iter - theta_dense) <= 1e-6 * abs(theta_dense)

@@ -124,3 +124,40 @@ def test_quimb_default_layout_accepted():
 
 def test_direction_enum():
     assert Direction.RIGHTWARD.value == 1 and Direction.LEFTWARD.value == -1
+
+
+def test_bond_dims_of_a_non_uniform_mpo():
+    """Bond i is the right bond of site i (site 0 carries no left bond)."""
+    rng = np.random.default_rng(0)
+    arrays = [rng.standard_normal((2, 2, 2)), rng.standard_normal((2, 3, 2, 2)), rng.standard_normal((3, 4, 2, 2)),
+              rng.standard_normal((4, 2, 2))]
+    assert MatrixProductOperator(arrays).bond_dims() == [2, 3, 4]
+    assert XXZ(n=5, delta=0.5).mpo.bond_dims() == [5, 5, 5, 5]
+    assert XXZ(n=5, delta=0.5).mpo.square().bond_dims() == [25, 25, 25, 25]
+
+
+def test_reference_import_paths_resolve_to_this_implementation():
+    """A user of tanlin2013/tnpy keeps their imports (README.md:97-101, scripts/thirring_fdmrg.py:1-2)."""
+    import tnpy
+    import tnpy_b200.finite_dmrg as impl
+    from tnpy.finite_dmrg import FiniteDMRG, Metric, ShiftInvertDMRG
+    from tnpy.linalg import eigh, eigshmv, svd  # noqa: F401
+    from tnpy.matrix_product_state import Direction as D2, Environment, MatrixProductState as M2  # noqa: F401
+    from tnpy.model import RandomHeisenberg as RH2, Thirring as T2, XXZ as X2
+    from tnpy.model.thirring import Thirring as T3
+    from tnpy.operators import MatrixProductOperator as MPO2
+
+    assert FiniteDMRG is impl.FiniteDMRG and ShiftInvertDMRG is impl.ShiftInvertDMRG and Metric is impl.Metric
+    assert X2 is XXZ and T2 is Thirring and T3 is Thirring and RH2 is RandomHeisenberg
+    assert M2 is MatrixProductState and D2 is Direction and MPO2 is MatrixProductOperator
+    assert tnpy.logger.name == "tnpy"
+
+
+def test_to_quimb_round_trip():
+    """The returned MPS converts to the reference's quimb type when quimb is installed (it is not a dependency)."""
+    pytest.importorskip("quimb")
+    mps = MatrixProductState.random(n=6, bond_dim=4, phys_dim=2, seed=1)
+    q = mps.to_quimb()
+    assert q.L == 6 and abs((q.H @ q) - mps.overlap(mps)) < 1e-12
+    for i in range(6):
+        np.testing.assert_array_equal(np.asarray(q[i].data).reshape(mps[i].shape), mps[i].data)

@@ -35,9 +35,10 @@ enum { GS_THETA = 0, GS_RESID = 1, GS_NA = 2, GS_NM = 3, GS_DONE = 4, GS_FAIL = 
 __global__ void __launch_bounds__(256) geig_small_kernel(double* __restrict__ GA, double* __restrict__ GM,
                                                          const double* __restrict__ ha, const double* __restrict__ hm,
                                                          int j, double* __restrict__ y, double* __restrict__ status) {
-  __shared__ double a[kMaxG][kMaxG];  // GA -> C^-1 GA C^-T -> its eigenvalues on the diagonal
-  __shared__ double b[kMaxG][kMaxG];  // GM -> Cholesky factor C (lower)
-  __shared__ double z[kMaxG][kMaxG];  // eigenvectors
+  // leading dimension kMaxG + 1 (odd): column walks are spread over the shared-memory banks
+  __shared__ double a[kMaxG][kMaxG + 1];  // GA -> C^-1 GA C^-T -> its eigenvalues on the diagonal
+  __shared__ double b[kMaxG][kMaxG + 1];  // GM -> Cholesky factor C (lower)
+  __shared__ double z[kMaxG][kMaxG + 1];  // eigenvectors
   __shared__ double cs[kMaxG], sn[kMaxG], red[72];
   __shared__ int pp[kMaxG], qq[kMaxG];
   __shared__ int fail, lo_idx;

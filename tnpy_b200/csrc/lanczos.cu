@@ -1,8 +1,9 @@
 // On-device lowest-eigenpair solver for H_eff (replaces primme.eigsh behind linalg.eigshmv,
 // reference linalg.py:64-87, called from finite_dmrg.py:111).
 //
-// Thick-restart Lanczos with full (twice-applied classical Gram-Schmidt) reorthogonalisation and an
-// explicitly projected matrix T = V^T H V.  Everything -- the matvec chain, the vector kernels,
+// Thick-restart Lanczos with full reorthogonalisation (a local classical Gram-Schmidt pass against the vectors the
+// three-term recurrence couples to, then a pass against the whole basis, a further one when the DGKS test asks) and
+// an explicitly projected matrix T = V^T H V.  Everything -- the matvec chain, the vector kernels,
 // the Rayleigh-Ritz solve (parallel cyclic Jacobi on T in one CTA) and the convergence test -- runs
 // on the device; the host only reads one 64-byte status record per Lanczos step to decide whether to
 // stop or restart.  Basis vectors never leave HBM.
@@ -23,13 +24,17 @@ int combine(const double* V, int64_t ldv, int m, const double* c, int64_t ldc_, 
             int64_t n, cudaStream_t stream);
 
 constexpr int kMaxNcv = 48;
+// leading dimension of the shared-memory matrices of the Ritz solve: odd, so that a column walk (the A <- A J phase
+// of the Jacobi rounds, consecutive threads on consecutive rows) is spread over the banks.  With the natural 48 every
+// row of a column sits in the same bank and a 30 x 30 Ritz problem took 1.5 ms (profiles/r02_launches_*).
+constexpr int kRitzLd = kMaxNcv + 1;
 
 // status record (device and pinned host mirror)
 enum { ST_THETA = 0, ST_RESID = 1, ST_ANORM = 2, ST_DONE = 3, ST_BETA = 4, ST_RCOEF = 5, ST_BOUND = 6, ST_SIZE = 8 };
 
 // Symmetric eigen-decomposition of the m x m matrix held in shared memory `a` (leading dim kMaxNcv)
 // by parallel cyclic Jacobi (round-robin pair ordering).  Eigenvectors accumulate in `z` (columns).
-__device__ void jacobi_eig_smem(double (*a)[kMaxNcv], double (*z)[kMaxNcv], int m, double* cs, double* sn, int* pp,
+__device__ void jacobi_eig_smem(double (*a)[kRitzLd], double (*z)[kRitzLd], int m, double* cs, double* sn, int* pp,
                                 int* qq, double* red) {
   const int tid = threadIdx.x, nt = blockDim.x;
   for (int idx = tid; idx < m * m; idx += nt) z[idx / m][idx % m] = (idx / m == idx % m) ? 1.0 : 0.0;
@@ -112,18 +117,20 @@ __device__ void jacobi_eig_smem(double (*a)[kMaxNcv], double (*z)[kMaxNcv], int 
 // After Lanczos step j: fold h (+ h2) into column j of T, solve the (j+1) x (j+1) Ritz problem, write
 // status, the sorted Ritz values `thetas` and the sorted Ritz coefficient matrix S (column i = i-th lowest).
 __global__ void __launch_bounds__(256) ritz_kernel(double* __restrict__ T, const double* __restrict__ h,
-                                                   const double* __restrict__ h2, const double* __restrict__ beta_dev,
+                                                   const double* __restrict__ h2, const double* __restrict__ h_local,
+                                                   int local_from, const double* __restrict__ beta_dev,
                                                    int j, double tol, double* __restrict__ S,
                                                    double* __restrict__ thetas, double* __restrict__ status,
                                                    int fold_only) {
-  __shared__ double a[kMaxNcv][kMaxNcv];
-  __shared__ double z[kMaxNcv][kMaxNcv];
+  __shared__ double a[kMaxNcv][kRitzLd];
+  __shared__ double z[kMaxNcv][kRitzLd];
   __shared__ double cs[kMaxNcv], sn[kMaxNcv], red[72];
   __shared__ int pp[kMaxNcv], qq[kMaxNcv], order[kMaxNcv];
   const int m = j + 1;
   const int tid = threadIdx.x;
   if (tid < m) {
-    const double v = h[tid] + (h2 ? h2[tid] : 0.0);
+    // column j of T = V^T H V: the local pass (vectors local_from .. j) plus the full pass(es)
+    const double v = h[tid] + (h2 ? h2[tid] : 0.0) + (tid >= local_from ? h_local[tid - local_from] : 0.0);
     T[tid * kMaxNcv + j] = v;
     T[j * kMaxNcv + tid] = v;
   }
@@ -180,7 +187,7 @@ static size_t eig_ws_layout(int64_t n, int ncv, int keep, size_t chain) {
   total += Workspace::need((size_t)(ncv + 1) * ldv);  // V
   total += Workspace::need((size_t)keep * ldv);       // Y
   total += Workspace::need(kMaxNcv * kMaxNcv) * 2;    // T, S
-  total += Workspace::need(64) * 4;                   // thetas, h, h2, status
+  total += Workspace::need(64) * 5;                   // thetas, h, h2, h_local, status
   total += chain + 512;
   return total;
 }
@@ -248,9 +255,10 @@ static int eig_lowest_impl(const double* L, const double* W, const double* R, do
   double* thetas = ws.take<double>(64);
   double* h = ws.take<double>(64);
   double* h2 = ws.take<double>(64);
+  double* h_local = ws.take<double>(64);
   double* status = ws.take<double>(64);
   int* skip2 = reinterpret_cast<int*>(status + 48);  // device flag: skip the second Gram-Schmidt pass of this step
-  if (!V || !Y || !T || !S || !thetas || !h || !h2 || !status) {
+  if (!V || !Y || !T || !S || !thetas || !h || !h2 || !h_local || !status) {
     set_error("tnpy_eig_lowest: workspace too small (%zu bytes given)", workspace_bytes);
     return TNPY_EWORKSPACE;
   }
@@ -283,6 +291,7 @@ static int eig_lowest_impl(const double* L, const double* W, const double* R, do
   TNPY_CUDA_OK(cudaMemsetAsync(T, 0, sizeof(double) * kMaxNcv * kMaxNcv, stream));
 
   int j = 0, n_matvec = 0, n_restart = 0;
+  int whole_basis_step = 0;  // step whose local Gram-Schmidt set is the whole basis (the first after a restart)
   double worst_bound = 0.0;
   bool done = false;
   // Daniel-Gragg-Kaufman-Stewart: the second pass is skipped only when ||w'|| >= ||w|| / sqrt 2, i.e.
@@ -301,10 +310,20 @@ static int eig_lowest_impl(const double* L, const double* W, const double* R, do
     Workspace chain(static_cast<char*>(workspace) + chain_off, workspace_bytes - chain_off);
     TNPY_TRY(heff_plan_apply(plan, vj, w, slices, nullptr, chain, stream));
     ++n_matvec;
-    // classical Gram-Schmidt against the whole basis, applied twice; the first-pass coefficients are
-    // column j of T = V^T H V, the second pass adds the rounding-level correction.
-    // The second pass is what "twice is enough" asks for when the first one cancelled; it is decided on the
-    // device (||w'|| >= eta ||h|| => the two extra passes over V are skipped).
+    // Gram-Schmidt in two stages.  H v_j has analytically non-zero components only on v_{j-1} and v_j
+    // (three-term recurrence; on every kept Ritz vector in the first step after a thick restart), so a *local*
+    // classical Gram-Schmidt pass against just those removes everything large; the pass against the whole basis
+    // that follows then sees a vector whose components along V are at rounding / loss-of-orthogonality level, i.e.
+    // it is the second pass of "twice is enough" at the cost of one.  The Daniel-Gragg-Kaufman-Stewart test
+    // (||w'|| >= ||w|| / sqrt 2 for the full pass, decided on the device) still guards it: a third, full pass runs
+    // when the full pass cancelled after all.  A plain single full pass is not enough: ||w'|| / ||w|| is ~0.6 in
+    // every Lanczos step, and each unguarded step multiplies the basis' orthogonality defect by ~1.3
+    // (docs/experiments/local_solver_study.py); the coefficients of all passes add up to column j of T = V^T H V.
+    const int local_from = (j == whole_basis_step) ? 0 : (j > 0 ? j - 1 : 0);
+    const int n_local = j + 1 - local_from;
+    double* v_local = V + (int64_t)local_from * ldv;
+    TNPY_TRY(multi_dot(v_local, ldv, n_local, w, n, h_local, 0, stream));
+    TNPY_TRY(multi_axpy(v_local, ldv, n_local, h_local, w, n, nullptr, stream));
     TNPY_TRY(multi_dot(V, ldv, j + 1, w, n, h, 0, stream));
     TNPY_TRY(multi_axpy(V, ldv, j + 1, h, w, n, status + ST_BETA, stream));
     reorth_decision_kernel<<<1, 64, 0, stream>>>(h, j + 1, status + ST_BETA, eta, h2, skip2);
@@ -314,7 +333,7 @@ static int eig_lowest_impl(const double* L, const double* W, const double* R, do
     const int m = j + 1;
     ++since_check;
     const bool look = m == ncv || n_matvec >= max_matvec || m >= n || since_check >= stride;
-    ritz_kernel<<<1, 256, 0, stream>>>(T, h, h2, status + ST_BETA, j, tol, S, thetas, status, look ? 0 : 1);
+    ritz_kernel<<<1, 256, 0, stream>>>(T, h, h2, h_local, local_from, status + ST_BETA, j, tol, S, thetas, status, look ? 0 : 1);
     TNPY_LAUNCH_OK();
     TNPY_TRY(scale_copy(w, w, n, 1.0, status + ST_BETA, 1, stream));
     if (!look) {
@@ -365,6 +384,7 @@ static int eig_lowest_impl(const double* L, const double* W, const double* R, do
       restart_T_kernel<<<1, 256, 0, stream>>>(T, thetas, k);
       TNPY_LAUNCH_OK();
       j = k;
+      whole_basis_step = k;  // H v_k has a component on every kept Ritz vector
       ++n_restart;
     } else {
       ++j;

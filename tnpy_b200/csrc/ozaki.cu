@@ -54,24 +54,58 @@ __device__ __forceinline__ double oz_scale_of(unsigned long long bits) {
 
 // digit = rint(128 t) without conversion instructions: adding 1.5 * 2^52 leaves the rounded integer in the low
 // mantissa bits (two's complement), subtracting it again gives the rounded value; the remainder is exact.
-__device__ __forceinline__ int8_t oz_next_digit(double& t) {
+// Returns the digit (|digit| <= 64) in the low byte of an int.
+__device__ __forceinline__ int oz_next_digit(double& t) {
   const double magic = 6755399441055744.0;
   const double u = fma(t, 128.0, magic);
   t = fma(t, 128.0, magic - u);  // exact remainder, |t| <= 0.5
-  return (int8_t)__double2loint(u);  // |digit| <= 64
+  return __double2loint(u);
 }
 
-// slices[s][c][k] (k contiguous, Kp bytes per row) from P[row(k)][c]: 32 columns x 128 k per block, digits staged
-// in shared memory so that every (slice, column) row leaves as one 128-byte line.
+// The slicing kernels all work on 16 consecutive K entries of one column per thread: 16 scaled values in,
+// kOzMaxSlices x 16 digit bytes out, one 16-byte store per slice (byte e of slice sl = digit sl of value e).
+// Digits of four values are packed with three byte permutes per slice.
+template <typename ValueOf>
+__device__ __forceinline__ void oz_digits16(ValueOf&& value_of, uint4 (&out)[kOzMaxSlices]) {
+  uint32_t w[kOzMaxSlices][4];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    double t0 = value_of(4 * g), t1 = value_of(4 * g + 1), t2 = value_of(4 * g + 2), t3 = value_of(4 * g + 3);
+#pragma unroll
+    for (int sl = 0; sl < kOzMaxSlices; ++sl) {
+      const int d0 = oz_next_digit(t0), d1 = oz_next_digit(t1), d2 = oz_next_digit(t2), d3 = oz_next_digit(t3);
+      w[sl][g] = __byte_perm(__byte_perm(d0, d1, 0x0040), __byte_perm(d2, d3, 0x0040), 0x5410);
+    }
+  }
+#pragma unroll
+  for (int sl = 0; sl < kOzMaxSlices; ++sl) out[sl] = make_uint4(w[sl][0], w[sl][1], w[sl][2], w[sl][3]);
+}
+
+// store the 16 digit bytes of every slice at row + k0 (k0 .. k0 + 15 < Kp); 16-byte stores when aligned
+__device__ __forceinline__ void oz_store16(int8_t* __restrict__ row, int64_t slice_stride, const uint4 (&dig)[kOzMaxSlices],
+                                           bool aligned) {
+  if (aligned) {
+#pragma unroll
+    for (int sl = 0; sl < kOzMaxSlices; ++sl) *reinterpret_cast<uint4*>(row + sl * slice_stride) = dig[sl];
+  } else {
+#pragma unroll
+    for (int sl = 0; sl < kOzMaxSlices; ++sl) {
+      const uint32_t w[4] = {dig[sl].x, dig[sl].y, dig[sl].z, dig[sl].w};
+#pragma unroll
+      for (int e = 0; e < 16; ++e) row[sl * slice_stride + e] = (int8_t)(w[e >> 2] >> (8 * (e & 3)));
+    }
+  }
+}
+
+// slices[s][c][k] (k contiguous, Kp bytes per row) from P[row(k)][c].  Block = 32 columns x 8 chunks of 16 k: the
+// loads are coalesced along the columns, every thread then owns 16 consecutive bytes of one (slice, column) row.
 __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict__ P, int64_t ld, OzRowMap rows, int K,
                                                        int MN, const unsigned long long* __restrict__ colmax,
                                                        double* __restrict__ scale, double* __restrict__ sumsq,
                                                        int8_t* __restrict__ slices, int64_t Kp, int64_t slice_stride) {
-  constexpr int S = kOzMaxSlices;
-  __shared__ __align__(16) int8_t tile[S][32][132];
-  const int c0 = blockIdx.x * 32, k0 = blockIdx.y * 128;
   const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
-  const int c = c0 + tx;
+  const int c = blockIdx.x * 32 + tx;
+  const int k0 = (blockIdx.y * 8 + ty) * 16;
   const double sc = c < MN ? oz_scale_of(colmax[c]) : 0.0;
   const double inv = sc > 0.0 ? 1.0 / sc : 0.0;  // exact: power of two
   if (blockIdx.y == 0 && ty == 0) {
@@ -79,38 +113,28 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict_
     const double part = warp_sum(sc * sc);
     if (tx == 0 && part > 0.0) atomicAdd(sumsq, part);  // feeds an error *bound*: summation order is immaterial
   }
-#pragma unroll 4
-  for (int i = ty; i < 128; i += 8) {
-    const int k = k0 + i;
-    double t = (k < K && c < MN) ? P[oz_src_row(k, rows) * ld + c] * inv : 0.0;  // |t| <= 0.5
+  if (c >= MN || k0 >= Kp) return;
+  double t[16];
 #pragma unroll
-    for (int sl = 0; sl < S; ++sl) tile[sl][tx][i] = oz_next_digit(t);
-  }
-  __syncthreads();
-  for (int idx = threadIdx.x; idx < S * 32 * 32; idx += 256) {
-    const int w = idx % 32, cc = (idx / 32) % 32, sl = idx / 1024;
-    const int64_t k = k0 + 4 * w;
-    if (c0 + cc < MN && k < Kp)
-      *reinterpret_cast<int32_t*>(slices + sl * slice_stride + (int64_t)(c0 + cc) * Kp + k) =
-          *reinterpret_cast<const int32_t*>(&tile[sl][cc][4 * w]);
-  }
+  for (int e = 0; e < 16; ++e) t[e] = (k0 + e < K) ? P[oz_src_row(k0 + e, rows) * ld + c] * inv : 0.0;  // |t| <= 0.5
+  uint4 dig[kOzMaxSlices];
+  oz_digits16([&t](int e) { return t[e]; }, dig);
+  oz_store16(slices + (int64_t)c * Kp + k0, slice_stride, dig, true);  // Kp and k0 are multiples of 16
 }
 
 // ---------------------------------------------------------------------------------------------
 // premixed operands of the direct path (mixed-canonical gauge, no interior-to-interior MPO blocks)
 // ---------------------------------------------------------------------------------------------
-
 // A side: one block per left-bond index m.  Xa[(b, ri), (m, q)] = sum_p W[0, b, p, q] x[m, p, ri] for b < wr - 1:
 // for a fixed column (m, q) the K index (b, ri) runs over contiguous ri, so the row x[m, :, :] (d * r doubles) is
-// read once, its column maxima are found, and the digits leave as 8-byte words.  The same pass writes
-// y0[m, q, :] = sum_p W[0, wr - 1, p, q] x[m, p, :] - shift x[m, q, :].
+// read once into shared memory, its column maxima are found, and every thread then turns 16 consecutive ri of one
+// (q, b) piece into digits.  The same pass writes y0[m, q, :] = sum_p W[0, wr - 1, p, q] x[m, p, :] - shift x[m, q, :].
 __global__ void __launch_bounds__(256) oz_premix_a_kernel(const double* __restrict__ x, const double* __restrict__ W,
                                                           int r, int wr, int d, double* __restrict__ scale,
                                                           double* __restrict__ sumsq, int8_t* __restrict__ slices,
                                                           int64_t Kp, int64_t slice_stride, double* __restrict__ y0,
                                                           const double* __restrict__ shift_dev) {
-  constexpr int S = kOzMaxSlices;
-  extern __shared__ double xs[];  // [d][r + r / 8 + 1]
+  extern __shared__ double xs[];  // [d][r + r / 16 + 1]
   __shared__ double wc[kPmMaxCh][kPmMaxD][kPmMaxD];  // [b][p][q], b = wr - 1 holds the y0 block
   __shared__ double red[kPmMaxD][8];
   __shared__ double sc_sh[kPmMaxD];
@@ -121,10 +145,10 @@ __global__ void __launch_bounds__(256) oz_premix_a_kernel(const double* __restri
     wc[b][p][q] = W[(b * d + p) * d + q];  // W[0, b, p, q]: the a = 0 row of the (wl, wr, d, d) tensor
   }
   const double* xrow = x + (int64_t)m * d * r;
-  // one pad double per 8 entries: the digit loop below reads 8 consecutive ri per thread (stride 9 doubles between
-  // the threads of a warp: conflict-free), the other loops read consecutive ri
-  const int rp = r + r / 8 + 1;
-  auto xi = [rp](int p, int ri) { return p * rp + ri + (ri >> 3); };
+  // one pad double per 16 entries: the digit loop reads 16 consecutive ri per thread (stride 17 doubles between the
+  // threads of a warp: conflict-free), the other loops read consecutive ri
+  const int rp = r + r / 16 + 1;
+  auto xi = [rp](int p, int ri) { return p * rp + ri + (ri >> 4); };
   for (int idx = tid; idx < d * r; idx += blockDim.x) xs[xi(idx / r, idx % r)] = xrow[idx];
   __syncthreads();
   // column maxima over (b, ri) for every q
@@ -132,12 +156,17 @@ __global__ void __launch_bounds__(256) oz_premix_a_kernel(const double* __restri
 #pragma unroll
   for (int q = 0; q < kPmMaxD; ++q) mx[q] = 0.0;
   for (int ri = tid; ri < r; ri += blockDim.x) {
+    double xv[kPmMaxD];
+#pragma unroll
+    for (int p = 0; p < kPmMaxD; ++p) xv[p] = p < d ? xs[xi(p, ri)] : 0.0;
     for (int b = 0; b < nb; ++b)
 #pragma unroll
       for (int q = 0; q < kPmMaxD; ++q)
         if (q < d) {
           double v = 0.0;
-          for (int p = 0; p < d; ++p) v = fma(wc[b][p][q], xs[xi(p, ri)], v);
+#pragma unroll
+          for (int p = 0; p < kPmMaxD; ++p)
+            if (p < d) v = fma(wc[b][p][q], xv[p], v);
           mx[q] = fmax(mx[q], fabs(v));
         }
   }
@@ -157,40 +186,47 @@ __global__ void __launch_bounds__(256) oz_premix_a_kernel(const double* __restri
     if (sc > 0.0) atomicAdd(sumsq, sc * sc);
   }
   __syncthreads();
-  // digits: a thread owns 8 consecutive ri of one (q, b) row piece
-  const int r8 = (r + 7) / 8;
-  for (int item = tid; item < d * nb * r8; item += blockDim.x) {
-    const int i8 = item % r8, b = (item / r8) % nb, q = item / (r8 * nb);
+  // digits: a thread owns 16 consecutive ri of one (q, b) row piece; K = (b, ri), padded with zeros up to Kp
+  const int r16 = (r + 15) / 16;
+  for (int item = tid; item < d * nb * r16; item += blockDim.x) {
+    const int i16 = item % r16, b = (item / r16) % nb, q = item / (r16 * nb);
     const double sc = sc_sh[q];
     const double inv = sc > 0.0 ? 1.0 / sc : 0.0;
-    uint64_t word[S];
+    double cw[kPmMaxD];
 #pragma unroll
-    for (int sl = 0; sl < S; ++sl) word[sl] = 0;
+    for (int p = 0; p < kPmMaxD; ++p) cw[p] = p < d ? wc[b][p][q] * inv : 0.0;  // exact: inv is a power of two
+    uint4 dig[kOzMaxSlices];
+    oz_digits16(
+        [&](int e) {
+          const int ri = 16 * i16 + e;
+          double v = 0.0;
+          if (ri < r) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int ri = 8 * i8 + e;
-      double t = 0.0;
-      if (ri < r) {
-        for (int p = 0; p < d; ++p) t = fma(wc[b][p][q], xs[xi(p, ri)], t);
-        t *= inv;
-      }
-#pragma unroll
-      for (int sl = 0; sl < S; ++sl) word[sl] |= (uint64_t)(uint8_t)oz_next_digit(t) << (8 * e);
-    }
-    const int64_t off = ((int64_t)m * d + q) * Kp + (int64_t)b * r + 8 * i8;
-    if (8 * i8 + 8 <= r && (((int64_t)b * r) & 7) == 0) {
-#pragma unroll
-      for (int sl = 0; sl < S; ++sl) *reinterpret_cast<uint64_t*>(slices + sl * slice_stride + off) = word[sl];
+            for (int p = 0; p < kPmMaxD; ++p)
+              if (p < d) v = fma(cw[p], xs[xi(p, ri)], v);
+          }
+          return v;
+        },
+        dig);
+    const int64_t k0 = (int64_t)b * r + 16 * i16;
+    int8_t* row = slices + ((int64_t)m * d + q) * Kp + k0;
+    const bool last_piece = (b == nb - 1) && (16 * i16 + 16 > r);  // runs into the zero padding: still inside Kp?
+    if (16 * i16 + 16 <= r || (last_piece && k0 + 16 <= Kp)) {
+      oz_store16(row, slice_stride, dig, (k0 & 15) == 0);
     } else {
-      for (int e = 0; e < 8 && 8 * i8 + e < r; ++e)
+      // ragged end of a piece that is followed by the next channel's bytes: store only the valid ones
+      const int valid = r - 16 * i16;
 #pragma unroll
-        for (int sl = 0; sl < S; ++sl) slices[sl * slice_stride + off + e] = (int8_t)(word[sl] >> (8 * e));
+      for (int sl = 0; sl < kOzMaxSlices; ++sl) {
+        const uint32_t w[4] = {dig[sl].x, dig[sl].y, dig[sl].z, dig[sl].w};
+        for (int e = 0; e < valid; ++e) row[sl * slice_stride + e] = (int8_t)(w[e >> 2] >> (8 * (e & 3)));
+      }
     }
   }
-  // zero the K padding of this block's columns (Kp - nb * r < 64 bytes per row)
+  // zero what is left of the K padding of this block's columns (Kp - nb * r < 64 bytes per row)
   const int kreal = nb * r, kpad = (int)(Kp - kreal);
-  for (int item = tid; item < d * S * kpad; item += blockDim.x) {
-    const int e = item % kpad, sl = (item / kpad) % S, q = item / (kpad * S);
+  for (int item = tid; item < d * kOzMaxSlices * kpad; item += blockDim.x) {
+    const int e = item % kpad, sl = (item / kpad) % kOzMaxSlices, q = item / (kpad * kOzMaxSlices);
     slices[sl * slice_stride + ((int64_t)m * d + q) * Kp + kreal + e] = 0;
   }
   if (y0 != nullptr) {
@@ -222,6 +258,7 @@ __global__ void __launch_bounds__(256) oz_premix_b_colmax_kernel(const double* _
   double mx[kPmMaxD];
 #pragma unroll
   for (int q = 0; q < kPmMaxD; ++q) mx[q] = 0.0;
+#pragma unroll 4
   for (int li = l0; li < l1; ++li) {
     double xv[kPmMaxD];
 #pragma unroll
@@ -242,83 +279,85 @@ __global__ void __launch_bounds__(256) oz_premix_b_colmax_kernel(const double* _
     if (q < d && mx[q] > 0.0) atomicMax(&colmax[(int64_t)q * r + s], (unsigned long long)__double_as_longlong(mx[q]));
 }
 
-// B side, digits: Xb[(a, li), (q, s)] for a < wl - 1.  Block = 32 values of s x 128 values of li (the transposing
-// tile of oz_slice_kernel); the x tile is read once per physical index and every (a, q) product is formed from it.
-__global__ void __launch_bounds__(256) oz_premix_b_kernel(const double* __restrict__ x, const double* __restrict__ W,
-                                                          int l, int r, int wl, int wr, int d,
+// B side, digits: Xb[(a, li), (q, s)] for a < wl - 1.  Block = 32 values of s x 8 chunks of 16 li: the x loads are
+// coalesced along s, a thread keeps its 16 x d entries of x in registers and forms every (a, q) product from them,
+// each one leaving as 16 consecutive bytes of the (slice, column (q, s)) rows.
+template <int D>
+__global__ void __launch_bounds__(256, D <= 2 ? 2 : 1) oz_premix_b_kernel(const double* __restrict__ x, const double* __restrict__ W,
+                                                          int l, int r, int wl, int wr,
                                                           const unsigned long long* __restrict__ colmax,
                                                           double* __restrict__ scale, double* __restrict__ sumsq,
                                                           int8_t* __restrict__ slices, int64_t Kp,
                                                           int64_t slice_stride) {
-  constexpr int S = kOzMaxSlices;
-  __shared__ __align__(16) int8_t tile[S][32][132];
-  __shared__ double wc[kPmMaxCh][kPmMaxD][kPmMaxD];
+  constexpr int d = D;
+  __shared__ double wc[kPmMaxCh][D][D];
   const int na = wl - 1;
   for (int idx = threadIdx.x; idx < na * d * d; idx += blockDim.x) {
     const int a = idx / (d * d), p = (idx / d) % d, q = idx % d;
     wc[a][p][q] = W[((((int64_t)(a + 1)) * wr + (wr - 1)) * d + p) * d + q];
   }
-  const int s0 = blockIdx.x * 32, l0 = blockIdx.y * 128;
   const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
-  const int s = s0 + tx;
-  double sc[kPmMaxD], inv[kPmMaxD];
+  const int s = blockIdx.x * 32 + tx;
+  const int l0 = (blockIdx.y * 8 + ty) * 16;
+  double sc[D], inv[D];
 #pragma unroll
-  for (int q = 0; q < kPmMaxD; ++q) {
-    sc[q] = (q < d && s < r) ? oz_scale_of(colmax[(int64_t)q * r + s]) : 0.0;
+  for (int q = 0; q < D; ++q) {
+    sc[q] = s < r ? oz_scale_of(colmax[(int64_t)q * r + s]) : 0.0;
     inv[q] = sc[q] > 0.0 ? 1.0 / sc[q] : 0.0;
   }
   if (blockIdx.y == 0 && ty == 0) {
     double part = 0.0;
 #pragma unroll
-    for (int q = 0; q < kPmMaxD; ++q)
-      if (q < d) {
-        if (s < r) scale[(int64_t)q * r + s] = sc[q];
-        part += sc[q] * sc[q];
-      }
+    for (int q = 0; q < D; ++q) {
+      if (s < r) scale[(int64_t)q * r + s] = sc[q];
+      part += sc[q] * sc[q];
+    }
     part = warp_sum(part);
     if (tx == 0 && part > 0.0) atomicAdd(sumsq, part);
   }
   __syncthreads();
-  // x values of this thread's 16 (li) x d entries stay in registers across the (a, q) loop
-  double xv[16][kPmMaxD];
+  if (s < r && l0 < l) {
+    double xv[16][D];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const int li = l0 + ty + 8 * j;
+    for (int e = 0; e < 16; ++e)
 #pragma unroll
-    for (int p = 0; p < kPmMaxD; ++p) xv[j][p] = (p < d && li < l && s < r) ? x[((int64_t)li * d + p) * r + s] : 0.0;
-  }
-  for (int a = 0; a < na; ++a)
-    for (int q = 0; q < d; ++q) {
+      for (int p = 0; p < D; ++p) xv[e][p] = (l0 + e < l) ? x[((int64_t)(l0 + e) * d + p) * r + s] : 0.0;
+    const int valid = min(16, l - l0);
+    for (int a = 0; a < na; ++a)
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        double t = 0.0;
+      for (int q = 0; q < D; ++q) {
+        double cw[D];
 #pragma unroll
-        for (int p = 0; p < kPmMaxD; ++p)
-          if (p < d) t = fma(wc[a][p][q], xv[j][p], t);
-        t *= inv[q];
+        for (int p = 0; p < D; ++p) cw[p] = wc[a][p][q] * inv[q];  // exact scaling: inv is a power of two
+        uint4 dig[kOzMaxSlices];
+        oz_digits16(
+            [&](int e) {
+              double v = 0.0;
 #pragma unroll
-        for (int sl = 0; sl < S; ++sl) tile[sl][tx][ty + 8 * j] = oz_next_digit(t);
-      }
-      __syncthreads();
-      const int64_t kbase = (int64_t)a * l + l0;
-      for (int idx = threadIdx.x; idx < S * 32 * 32; idx += 256) {
-        const int w = idx % 32, cc = (idx / 32) % 32, sl = idx / 1024;
-        if (s0 + cc < r && l0 + 4 * w < l) {
-          int8_t* dst = slices + sl * slice_stride + ((int64_t)q * r + s0 + cc) * Kp + kbase + 4 * w;
-          if (l0 + 4 * w + 4 <= l && ((kbase & 3) == 0))
-            *reinterpret_cast<int32_t*>(dst) = *reinterpret_cast<const int32_t*>(&tile[sl][cc][4 * w]);
-          else
-            for (int e = 0; e < 4 && l0 + 4 * w + e < l; ++e) dst[e] = tile[sl][cc][4 * w + e];
+              for (int p = 0; p < D; ++p) v = fma(cw[p], xv[e][p], v);
+              return v;
+            },
+            dig);
+        const int64_t k0 = (int64_t)a * l + l0;
+        int8_t* row = slices + ((int64_t)q * r + s) * Kp + k0;
+        if (valid == 16 || (a == na - 1 && k0 + 16 <= Kp)) {
+          oz_store16(row, slice_stride, dig, (k0 & 15) == 0);
+        } else {
+#pragma unroll
+          for (int sl = 0; sl < kOzMaxSlices; ++sl) {
+            const uint32_t w[4] = {dig[sl].x, dig[sl].y, dig[sl].z, dig[sl].w};
+            for (int e = 0; e < valid; ++e) row[sl * slice_stride + e] = (int8_t)(w[e >> 2] >> (8 * (e & 3)));
+          }
         }
       }
-      __syncthreads();
-    }
-  // K padding: rows (q, s) of this block's columns, bytes [na * l, Kp), written by the l0 == 0 blocks
+  }
+  // what is left of the K padding: rows (q, s) of this block's columns, bytes [na * l, Kp), by the first row of blocks
   if (blockIdx.y == 0) {
     const int kreal = na * l, kpad = (int)(Kp - kreal);
-    for (int item = threadIdx.x; item < 32 * d * S * kpad; item += 256) {
-      const int e = item % kpad, sl = (item / kpad) % S, q = (item / (kpad * S)) % d, cc = item / (kpad * S * d);
-      if (s0 + cc < r) slices[sl * slice_stride + ((int64_t)q * r + s0 + cc) * Kp + kreal + e] = 0;
+    for (int item = threadIdx.x; item < 32 * d * kOzMaxSlices * kpad; item += 256) {
+      const int e = item % kpad, sl = (item / kpad) % kOzMaxSlices, q = (item / (kpad * kOzMaxSlices)) % d,
+                cc = item / (kpad * kOzMaxSlices * d);
+      if (blockIdx.x * 32 + cc < r) slices[sl * slice_stride + ((int64_t)q * r + blockIdx.x * 32 + cc) * Kp + kreal + e] = 0;
     }
   }
 }
@@ -751,7 +790,7 @@ int oz_slice_operand(const double* P, int64_t ld, OzRowMap rows, const OzOperand
   dim3 g1(ceil_div(MN, 256), ceil_div(K, k_chunk));
   oz_colmax_kernel<<<g1, 256, 0, stream>>>(P, ld, rows, K, MN, k_chunk, op.colmax);
   TNPY_LAUNCH_OK();
-  dim3 grid(ceil_div(MN, 32), (unsigned)((op.Kp + 127) / 128));
+  dim3 grid(ceil_div(MN, 32), (unsigned)((op.Kp + 127) / 128));  // 8 chunks of 16 k per block
   oz_slice_kernel<<<grid, 256, 0, stream>>>(P, ld, rows, K, MN, op.colmax, op.scale, op.sumsq, op.slices, op.Kp,
                                             (int64_t)MN * op.Kp);
   TNPY_LAUNCH_OK();
@@ -761,8 +800,8 @@ int oz_slice_operand(const double* P, int64_t ld, OzRowMap rows, const OzOperand
 static bool premix_dims_ok(int r, int wl, int wr, int d) {
   return d <= kPmMaxD && wl - 1 <= kPmMaxCh && wr <= kPmMaxCh && wl >= 2 && wr >= 2;
 }
-// padded row length of the x row staged by oz_premix_a_kernel (one extra double per 8: conflict-free 8-strided reads)
-static size_t premix_a_smem(int r, int d) { return sizeof(double) * (size_t)d * (r + r / 8 + 1); }
+// padded row length of the x row staged by oz_premix_a_kernel (one extra double per 16: conflict-free 16-strided reads)
+static size_t premix_a_smem(int r, int d) { return sizeof(double) * (size_t)d * (r + r / 16 + 1); }
 
 bool oz_premix_applicable(int l, int r, int wl, int wr, int d) {
   return premix_dims_ok(r, wl, wr, d) && premix_a_smem(r, d) <= 200 * 1024 && l >= 1;
@@ -785,12 +824,18 @@ int oz_premix_b(const double* x, const double* W, int l, int r, int wl, int wr, 
   TNPY_CHECK_ARG(oz_premix_applicable(l, r, wl, wr, d), "dimensions outside the direct path's limits");
   TNPY_CHECK_ARG(op.cols == d * r && op.K == (wl - 1) * l, "operand shape mismatch");
   TNPY_CUDA_OK(cudaMemsetAsync(op.colmax, 0, sizeof(unsigned long long) * (size_t)(op.cols + 1), stream));
-  const int l_chunk = l > 4096 ? 256 : 64;
+  const int l_chunk = l > 4096 ? 128 : 32;
   oz_premix_b_colmax_kernel<<<dim3(ceil_div(r, 256), ceil_div(l, l_chunk)), 256, 0, stream>>>(x, W, l, r, wl, wr, d,
                                                                                              l_chunk, op.colmax);
   TNPY_LAUNCH_OK();
-  oz_premix_b_kernel<<<dim3(ceil_div(r, 32), ceil_div(l, 128)), 256, 0, stream>>>(
-      x, W, l, r, wl, wr, d, op.colmax, op.scale, op.sumsq, op.slices, op.Kp, (int64_t)op.cols * op.Kp);
+  const dim3 grid(ceil_div(r, 32), ceil_div(l, 128));
+  const int64_t stride = (int64_t)op.cols * op.Kp;
+  switch (d) {
+    case 1: oz_premix_b_kernel<1><<<grid, 256, 0, stream>>>(x, W, l, r, wl, wr, op.colmax, op.scale, op.sumsq, op.slices, op.Kp, stride); break;
+    case 2: oz_premix_b_kernel<2><<<grid, 256, 0, stream>>>(x, W, l, r, wl, wr, op.colmax, op.scale, op.sumsq, op.slices, op.Kp, stride); break;
+    case 3: oz_premix_b_kernel<3><<<grid, 256, 0, stream>>>(x, W, l, r, wl, wr, op.colmax, op.scale, op.sumsq, op.slices, op.Kp, stride); break;
+    default: oz_premix_b_kernel<4><<<grid, 256, 0, stream>>>(x, W, l, r, wl, wr, op.colmax, op.scale, op.sumsq, op.slices, op.Kp, stride); break;
+  }
   TNPY_LAUNCH_OK();
   return TNPY_OK;
 }

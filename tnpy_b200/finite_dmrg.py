@@ -266,7 +266,9 @@ class ShiftInvertDMRG(FiniteDMRG):
         self._restored_mps = MatrixProductState(arrays)
 
     #: up to this many unknowns the local pencil is solved densely on the device (the projected H^2 is too
-    #: ill-conditioned for inverse-free Krylov iterations, see csrc/geig.cu); larger sites iterate
+    #: ill-conditioned for inverse-free Krylov iterations, see csrc/geig.cu); larger sites iterate and raise
+    #: RuntimeError when the iteration does not converge.  The reference's own test size (n=10, chi=64: bonds of 32,
+    #: 2048 unknowns) is inside the dense range; tnpy_heff_dense allows up to 4096.
     dense_pencil_dim = 2048
 
     def _solve_on_device(self, site: int, tol: float, **kwargs) -> float:
@@ -287,9 +289,18 @@ class ShiftInvertDMRG(FiniteDMRG):
             opts["ncv"] = int(kwargs["ncv"])
         if "maxiter" in kwargs:
             opts["max_iter"] = int(kwargs["maxiter"])
+        saved = psi.clone()
         stats = _cuda.geig_lowest(la, wa, ra, lm, wm, rm, psi, tol=tol, flags_a=env.gauge_flags(site), **opts)
         if not stats["converged"]:
-            logger.warning(f"ShiftInvertDMRG: local solve at site {site} not converged, residual {stats['resid']:.3e}")
+            # never hand back an unconverged vector as if it were the local ground state: the projected
+            # (H - eps)^2 is too ill-conditioned for the inverse-free iteration beyond small sites
+            psi.copy_(saved)
+            raise RuntimeError(
+                f"ShiftInvertDMRG: the iterative pencil solve at site {site} ({psi.numel()} unknowns) did not converge "
+                f"(residual {stats['resid']:.3e} after {stats['n_iter']} iterations); the site tensor was left unchanged. "
+                f"Sites up to dense_pencil_dim = {self.dense_pencil_dim} unknowns are solved densely -- raise it (<= 4096) "
+                "or lower the bond dimension."
+            )
         env._dirty.add(site)
         self.solver_stats.append({"site": site, "dense": False, "n_matvec": 2 * stats["n_iter"], **stats})
         return float(stats["theta"])

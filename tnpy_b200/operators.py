@@ -102,7 +102,8 @@ class MatrixProductOperator:
     __rmul__ = __mul__
 
     def bond_dims(self) -> List[int]:
-        return [a.shape[0] if i else a.shape[0] for i, a in enumerate(self._arrays)][:-1]
+        """Bond i joins sites i and i + 1: the right bond of every site but the last (site 0 is (w_r, d, d))."""
+        return [a.shape[0] if i == 0 else a.shape[1] for i, a in enumerate(self._arrays[:-1])]
 
     def as_four_leg(self, site: int) -> np.ndarray:
         """Site tensor with explicit unit bonds at the chain ends: always (w_l, w_r, d, d)."""
