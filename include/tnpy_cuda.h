@@ -144,17 +144,19 @@ int tnpy_identity_defect(const double* E, int dim, int w, int channel, double* d
                          void* workspace, size_t workspace_bytes, void* stream);
 
 /* Row block of the same matvec for the chi-sharded multi-GPU layout: the caller holds
- * L_rows = L[:, :, m0:m0+l_rows] stored contiguously as (l, wl, l_rows), the full x and R, and gets
- * y_rows = y[m0:m0+l_rows] as (l_rows, d, r).  No reduction across ranks is needed; the ranks
- * all-gather the next x.  Workspace: tnpy_heff_workspace_bytes() of the full problem is enough. */
+ * L_rows = L[:, :, row0 : row0 + l_rows] stored contiguously as (l, wl, l_rows), the full x and R, and gets
+ * y_rows = y[row0 : row0 + l_rows] as (l_rows, d, r).  No reduction across ranks is needed; the ranks
+ * all-gather the next x.  flags as for tnpy_heff_apply (TNPY_LEFT_IDENTITY then means
+ * L[li, 0, row0 + m] = delta(li, row0 + m)); in the mixed-canonical gauge the R-side term of the direct path only
+ * reads the caller's own rows of x.  Workspace: tnpy_heff_workspace_bytes() of the full problem is enough. */
 int tnpy_heff_apply_rows(const double* L_rows, const double* W, const double* R, const double* x,
-                         double* y_rows, int l, int l_rows, int r, int wl, int wr, int d,
+                         double* y_rows, int l, int row0, int l_rows, int r, int wl, int wr, int d, int flags,
                          void* workspace, size_t workspace_bytes, void* stream);
 /* Prepared form of the row block: same handle type and tnpy_heff_plan_apply (x full (l, d, r) in, y_rows (l_rows, d, r)
  * out); plan memory tnpy_heff_plan_bytes() of the full problem is enough. */
 int tnpy_heff_plan_create_rows(tnpy_heff_plan** handle, const double* L_rows, const double* W, const double* R,
-                               int l, int l_rows, int r, int wl, int wr, int d, int algo, void* plan_memory,
-                               size_t plan_bytes, void* stream);
+                               const double* W_host, int l, int row0, int l_rows, int r, int wl, int wr, int d,
+                               int flags, int algo, void* plan_memory, size_t plan_bytes, void* stream);
 
 /* ---- a7: Environment.update_left / update_right  (matrix_product_state.py:296-336) ---------
  * left : Lout[r,b,s] = sum L[l,a,m] A[l,p,r] W[a,b,p,q] A[m,q,s]      Lout: (r, wr, r)
@@ -215,6 +217,36 @@ int tnpy_eig_lowest(const double* L, const double* W, const double* R, double* p
 int tnpy_eig_lowest_image(const double* L, const double* W, const double* R, double* psi, double* hpsi,
                           int l, int r, int wl, int wr, int d, int flags, double tol, int max_matvec, int ncv,
                           double* stats_host, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- chi-sharded local solve over the GPUs of one box (BASELINE configs[4]) -------------------
+ * One process per GPU.  A communicator wraps an NCCL communicator that the library creates itself (libnccl.so.2 is
+ * resolved at run time: the copy PyTorch has loaded, else the system's; nothing links against it): rank 0 calls
+ * tnpy_comm_unique_id, the TNPY_COMM_ID_BYTES bytes travel to every rank by any means (tnpy_b200/parallel.py uses a
+ * torch.distributed broadcast), every rank calls tnpy_comm_create -- a collective -- on its own device.
+ * tnpy_comm_allgather / tnpy_comm_allreduce_sum: the two collectives the solve uses, on device doubles. */
+#define TNPY_COMM_ID_BYTES 128
+typedef struct tnpy_comm tnpy_comm;
+int tnpy_comm_unique_id(char* id_out);
+int tnpy_comm_create(tnpy_comm** comm, const char* id, int world, int rank);
+int tnpy_comm_destroy(tnpy_comm* comm);
+int tnpy_comm_world(const tnpy_comm* comm);
+int tnpy_comm_rank(const tnpy_comm* comm);
+int tnpy_comm_allgather(const tnpy_comm* comm, const double* send, double* recv, int64_t count, void* stream);
+int tnpy_comm_allreduce_sum(const tnpy_comm* comm, double* buf, int64_t count, void* stream);
+/* tnpy_eig_lowest with the left bond's bra rows split evenly over the ranks: rank g holds rows [row0, row0 + l_rows),
+ * row0 = g * l_rows, l_rows * world == l -- L_rows = L[:, :, rows] contiguous as (l, wl, l_rows), the same rows of psi
+ * (in: start vector, out: eigenvector), of hpsi (may be NULL; H_eff psi as in tnpy_eig_lowest_image) and of every
+ * Lanczos vector -- plus full copies of W and R.  Per Lanczos step the ranks all-gather the current vector (the
+ * only exchange of data, (G-1)/G of 8 N bytes per rank over NVLink), run their row block of the matvec
+ * (tnpy_heff_apply_rows; in the mixed-canonical gauge its R-side term needs no remote data at all) and all-reduce
+ * the Gram-Schmidt coefficients and norms; the small Ritz problem is solved redundantly from identical inputs, so
+ * every rank takes the same decisions and returns the same stats.  flags as for tnpy_heff_apply_rows.
+ * Collective: every rank of the communicator must call it with the same l, r, wl, wr, d, flags, tol, max_matvec, ncv. */
+size_t tnpy_eig_rows_workspace_bytes(int l, int l_rows, int r, int wl, int wr, int d, int ncv);
+int tnpy_eig_lowest_rows(const tnpy_comm* comm, const double* L_rows, const double* W, const double* R,
+                         double* psi_rows, double* hpsi_rows, int l, int row0, int l_rows, int r, int wl, int wr,
+                         int d, int flags, double tol, int max_matvec, int ncv, double* stats_host, void* workspace,
+                         size_t workspace_bytes, void* stream);
 
 /* ---- f2: ShiftInvertDMRG.one_site_solver -> primme.eigsh(A, M=M, k=1, which="SA")  (finite_dmrg.py:341-355)
  * Lowest eigenpair of the symmetric-definite pencil  A x = lambda M x,  A = H_eff(LA, WA, RA) (MPO of

@@ -342,7 +342,7 @@ def test_heff_properties_at_bench_size(cu, chi, w):
     rhs = float((cu.heff_apply(Lt, Wt, Rt, x) * y).sum())
     assert abs(lhs - rhs) < 1e-11 * abs(lhs) + 1e-9 * scale
     lo, hi = chi // 4, chi // 2
-    rows = cu.heff_apply_rows(L[:, :, lo:hi].contiguous(), W, R, x)
+    rows = cu.heff_apply_rows(L[:, :, lo:hi].contiguous(), W, R, x, row0=lo)
     assert float((rows - hx[lo:hi]).abs().max()) < 1e-12 * scale
 
 
@@ -632,6 +632,29 @@ def test_direct_path_in_canonical_gauge(cu, l, r, model):
     assert np.abs(chain.apply(dx).cpu().numpy() - got8).max() < 1e-12 * scale
     for p_ in (plan, plan2, chain):
         p_.close()
+
+
+def test_row_block_of_the_direct_path(cu):
+    """One rank's row block of the chi-sharded matvec in the mixed-canonical gauge: the identity flags are honoured
+    for a block (L[li, 0, row0 + m] = delta), the R-side term reads only the block's own rows of x, and the result is
+    the corresponding rows of the full matvec -- on the direct path, the tcgen05 chain and the FP64 chain."""
+    chi, w, d = 2048, 5, 2
+    L, W, R, x = _bench_size_operands(chi, w, canonical=True)
+    dL, dW, dR, dx = dev(L), dev(W), dev(R), dev(x)
+    full = cu.HeffPlan(dL, dW, dR, chi, chi, flags=3, w_host=W)
+    want = full.apply(dx)
+    full.close()
+    lo, hi = 512, 1536
+    L_rows = dL[:, :, lo:hi].contiguous()
+    for algo, flags, mode in ((cu.GEMM_AUTO, 3, cu.HEFF_OZ_DIRECT), (cu.GEMM_AUTO, 0, cu.HEFF_OZ_CHAIN), (cu.GEMM_FP64, 3, cu.HEFF_FP64_CHAIN)):
+        plan = cu.HeffPlan(L_rows, dW, dR, chi, chi, flags=flags, algo=algo, w_host=W, l_rows=hi - lo, row0=lo)
+        assert plan.mode == mode
+        got = plan.apply(dx)
+        assert tuple(got.shape) == (hi - lo, d, chi)
+        assert float((got - want[lo:hi]).abs().max() / want.abs().max()) < 1e-13
+        plan.close()
+    one_shot = cu.heff_apply_rows(L_rows, dW, dR, dx, row0=lo, flags=3)
+    assert float((one_shot - want[lo:hi]).abs().max() / want.abs().max()) < 1e-13
 
 
 # ---- a8/a9 as an orthogonal split: tnpy_qr_split (Cholesky-QR twice, verified on the device) ---------------

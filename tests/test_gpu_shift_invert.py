@@ -89,8 +89,8 @@ def test_shift_invert_parity_with_oracle():
 
 
 def test_shift_invert_at_the_reference_test_size():
-    """tests/test_finite_dmrg.py:26-72 as written: n=10, h=10.5, seed=2022, bond_dim 2**6 (bonds compress to 32, so the
-    mid-chain sites have 2048 unknowns: the top of the dense-pencil range)."""
+    """tests/test_finite_dmrg.py:26-72 as written: n=10, h=10.5, seed=2022, bond_dim 2**6 (bonds compress to at most 32,
+    so the two mid-chain sites have 1024 unknowns: inside the dense-pencil range)."""
     from tnpy_b200.finite_dmrg import ShiftInvertDMRG
     from tnpy_b200.model import RandomHeisenberg
 
@@ -117,7 +117,7 @@ def test_unconverged_iterative_pencil_raises_and_keeps_the_state():
 
     shifted = RandomHeisenberg(n=10, h=10.5, seed=2022, offset=0.1)
     sidmrg = ShiftInvertDMRG(shifted.mpo, bond_dim=2**6, offset=0.1, seed=1)
-    sidmrg.dense_pencil_dim = 1024  # the mid-chain sites (2048 unknowns) now iterate
+    sidmrg.dense_pencil_dim = 512  # the two mid-chain sites (1024 unknowns) now iterate
     site = 5
     before = sidmrg.environment.device_tensor(site).clone()
     try:
@@ -130,4 +130,5 @@ def test_unconverged_iterative_pencil_raises_and_keeps_the_state():
         sidmrg.environment.device_tensor(site).copy_(before)
         sidmrg.dense_pencil_dim = 2048
         theta_dense = sidmrg._solve_on_device(site, 1e-8)
+        assert sidmrg.solver_stats[-1]["dense"]
         assert abs(theta_iter - theta_dense) <= 1e-6 * abs(theta_dense)

@@ -43,7 +43,8 @@ SIGNATURES = {
         [ctypes.POINTER(c_void_p), _PD, _PD, _PD, ctypes.POINTER(c_double)] + [c_int] * 7 + [c_void_p, c_size_t, c_void_p],
     ),
     "tnpy_heff_plan_create_rows": (
-        c_int, [ctypes.POINTER(c_void_p), _PD, _PD, _PD] + [c_int] * 7 + [c_void_p, c_size_t, c_void_p],
+        c_int,
+        [ctypes.POINTER(c_void_p), _PD, _PD, _PD, ctypes.POINTER(c_double)] + [c_int] * 9 + [c_void_p, c_size_t, c_void_p],
     ),
     "tnpy_heff_plan_mode": (c_int, [c_void_p]),
     "tnpy_heff_plan_apply": (c_int, [c_void_p, _PD, _PD, c_int, c_void_p, c_size_t, c_void_p]),
@@ -51,7 +52,7 @@ SIGNATURES = {
     "tnpy_heff_plan_destroy": (c_int, [c_void_p]),
     "tnpy_heff_apply": (c_int, [_PD, _PD, _PD, _PD, _PD] + [c_int] * 6 + [c_void_p, c_size_t, c_void_p]),
     "tnpy_identity_defect": (c_int, [_PD, c_int, c_int, c_int, _PD, c_void_p, c_size_t, c_void_p]),
-    "tnpy_heff_apply_rows": (c_int, [_PD, _PD, _PD, _PD, _PD] + [c_int] * 6 + [c_void_p, c_size_t, c_void_p]),
+    "tnpy_heff_apply_rows": (c_int, [_PD, _PD, _PD, _PD, _PD] + [c_int] * 8 + [c_void_p, c_size_t, c_void_p]),
     "tnpy_env_workspace_bytes": (c_size_t, [c_int] * 5),
     "tnpy_env_update_left": (c_int, [_PD, _PD, _PD, _PD] + [c_int] * 6 + [c_void_p, c_size_t, c_void_p]),
     "tnpy_env_update_right": (c_int, [_PD, _PD, _PD, _PD] + [c_int] * 6 + [c_void_p, c_size_t, c_void_p]),
@@ -72,6 +73,18 @@ SIGNATURES = {
     "tnpy_eig_lowest_image": (
         c_int,
         [_PD, _PD, _PD, _PD, _PD] + [c_int] * 6 + [c_double, c_int, c_int, ctypes.POINTER(c_double), c_void_p, c_size_t, c_void_p],
+    ),
+    "tnpy_comm_unique_id": (c_int, [ctypes.c_char_p]),
+    "tnpy_comm_create": (c_int, [ctypes.POINTER(c_void_p), ctypes.c_char_p, c_int, c_int]),
+    "tnpy_comm_destroy": (c_int, [c_void_p]),
+    "tnpy_comm_world": (c_int, [c_void_p]),
+    "tnpy_comm_rank": (c_int, [c_void_p]),
+    "tnpy_comm_allgather": (c_int, [c_void_p, _PD, _PD, c_int64, c_void_p]),
+    "tnpy_comm_allreduce_sum": (c_int, [c_void_p, _PD, c_int64, c_void_p]),
+    "tnpy_eig_rows_workspace_bytes": (c_size_t, [c_int] * 7),
+    "tnpy_eig_lowest_rows": (
+        c_int,
+        [c_void_p, _PD, _PD, _PD, _PD, _PD] + [c_int] * 8 + [c_double, c_int, c_int, ctypes.POINTER(c_double), c_void_p, c_size_t, c_void_p],
     ),
     "tnpy_geig_workspace_bytes": (c_size_t, [c_int] * 8),
     "tnpy_geig_lowest": (
@@ -247,9 +260,10 @@ class HeffPlan:
     path the int8 slices of the environments -- is computed once into a torch-owned buffer; ``apply`` then runs one
     matvec.  The plan keeps L, W, R alive and must not outlive changes to them."""
 
-    def __init__(self, L, W, R, l: int, r: int, flags: int = 0, algo: int = GEMM_AUTO, w_host=None, l_rows=None):
-        """``l_rows``: L holds only that many bra rows, (l, wl, l_rows) contiguous -- one rank's block of the
-        chi-sharded matvec; ``apply`` then maps the full x (l, d, r) to y_rows (l_rows, d, r)."""
+    def __init__(self, L, W, R, l: int, r: int, flags: int = 0, algo: int = GEMM_AUTO, w_host=None, l_rows=None,
+                 row0: int = 0):
+        """``l_rows`` / ``row0``: L holds only the bra rows row0 .. row0 + l_rows - 1, (l, wl, l_rows) contiguous -- one
+        rank's block of the chi-sharded matvec; ``apply`` then maps the full x (l, d, r) to y_rows (l_rows, d, r)."""
         import numpy as np
         import torch
 
@@ -263,14 +277,15 @@ class HeffPlan:
         self._memory = torch.empty(int(nbytes), dtype=torch.uint8, device=W.device)
         self._ws_bytes = self._lib.tnpy_heff_workspace_bytes(l, r, wl, wr, d)
         handle = c_void_p()
+        wh = None
+        if w_host is not None:
+            self._w_host = np.ascontiguousarray(w_host, dtype=np.float64)
+            wh = self._w_host.ctypes.data_as(ctypes.POINTER(c_double))
         if l_rows is not None:
-            rc = self._lib.tnpy_heff_plan_create_rows(ctypes.byref(handle), _ptr(L), _ptr(W), _ptr(R), l, self.l_rows, r, wl,
-                                                      wr, d, int(algo), _ptr(self._memory), nbytes, _stream())
+            rc = self._lib.tnpy_heff_plan_create_rows(ctypes.byref(handle), _ptr(L), _ptr(W), _ptr(R), wh, l, int(row0),
+                                                      self.l_rows, r, wl, wr, d, int(flags), int(algo),
+                                                      _ptr(self._memory), nbytes, _stream())
         else:
-            wh = None
-            if w_host is not None:
-                self._w_host = np.ascontiguousarray(w_host, dtype=np.float64)
-                wh = self._w_host.ctypes.data_as(ctypes.POINTER(c_double))
             rc = self._lib.tnpy_heff_plan_create(ctypes.byref(handle), _ptr(L), _ptr(W), _ptr(R), wh, l, r, wl, wr, d,
                                                  int(flags), int(algo), _ptr(self._memory), nbytes, _stream())
         check(rc, "tnpy_heff_plan_create")
@@ -337,8 +352,9 @@ def heff_apply(L, W, R, x, out=None, flags: int = 0):
     return out
 
 
-def heff_apply_rows(L_rows, W, R, x, out=None):
-    """Row block of H_eff x: L_rows (l, wl, l_rows) contiguous, x (l, d, r) full -> (l_rows, d, r)."""
+def heff_apply_rows(L_rows, W, R, x, out=None, row0: int = 0, flags: int = 0):
+    """Row block of H_eff x: L_rows = L[:, :, row0 : row0 + l_rows] contiguous as (l, wl, l_rows), x (l, d, r) full
+    -> (l_rows, d, r).  ``flags`` as for :func:`heff_apply`."""
     import torch
 
     _need_cuda(L_rows, W, R, x, out)
@@ -349,8 +365,8 @@ def heff_apply_rows(L_rows, W, R, x, out=None):
     lib = load()
     nbytes = lib.tnpy_heff_workspace_bytes(l, r, wl, wr, d)
     ws = _scratch.get(nbytes)
-    rc = lib.tnpy_heff_apply_rows(_ptr(L_rows), _ptr(W), _ptr(R), _ptr(x), _ptr(out), l, lo, r, wl, wr, d, _ptr(ws),
-                                  nbytes, _stream())
+    rc = lib.tnpy_heff_apply_rows(_ptr(L_rows), _ptr(W), _ptr(R), _ptr(x), _ptr(out), l, int(row0), lo, r, wl, wr, d,
+                                  int(flags), _ptr(ws), nbytes, _stream())
     check(rc, "tnpy_heff_apply_rows")
     return out
 
@@ -432,6 +448,86 @@ def eig_lowest(L, W, R, psi, tol: float = 1e-8, max_matvec: int = 1000, ncv: int
         rc = lib.tnpy_eig_lowest_image(_ptr(L), _ptr(W), _ptr(R), _ptr(psi), _ptr(image), l, r, wl, wr, d, int(flags),
                                        float(tol), int(max_matvec), int(ncv), stats, _ptr(ws), nbytes, _stream())
     check(rc, "tnpy_eig_lowest", allow_noconv=True)
+    return {
+        "theta": stats[0], "resid": stats[1], "n_matvec": int(stats[2]), "n_restart": int(stats[3]),
+        "converged": bool(stats[4]), "anorm": stats[5], "int8_error_bound": stats[6],
+        "heff_mode": int(stats[7]) // 10, "slices": int(stats[7]) % 10,
+    }
+
+
+COMM_ID_BYTES = 128
+
+
+class Comm:
+    """NCCL communicator owned by the library (``tnpy_comm_*``), one per process.  ``Comm.from_torch_distributed()``
+    creates it on the current CUDA device from an initialised ``torch.distributed`` group of any backend (the
+    128-byte id travels by broadcast)."""
+
+    def __init__(self, unique_id: bytes, world: int, rank: int):
+        self._lib = load()
+        handle = c_void_p()
+        buf = ctypes.create_string_buffer(bytes(unique_id), COMM_ID_BYTES)
+        check(self._lib.tnpy_comm_create(ctypes.byref(handle), buf, int(world), int(rank)), "tnpy_comm_create")
+        self._handle, self.world, self.rank = handle, int(world), int(rank)
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = ctypes.create_string_buffer(COMM_ID_BYTES)
+        check(load().tnpy_comm_unique_id(buf), "tnpy_comm_unique_id")
+        return buf.raw
+
+    @classmethod
+    def from_torch_distributed(cls, group=None) -> "Comm":
+        import torch
+        import torch.distributed as dist
+
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        box = [cls.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        torch.cuda.synchronize()
+        return cls(box[0], world, rank)
+
+    @property
+    def handle(self):
+        return self._handle
+
+    def allgather(self, send, recv):
+        _need_cuda(send, recv)
+        check(self._lib.tnpy_comm_allgather(self._handle, _ptr(send), _ptr(recv), send.numel(), _stream()), "tnpy_comm_allgather")
+        return recv
+
+    def allreduce_sum(self, buf):
+        _need_cuda(buf)
+        check(self._lib.tnpy_comm_allreduce_sum(self._handle, _ptr(buf), buf.numel(), _stream()), "tnpy_comm_allreduce_sum")
+        return buf
+
+    def close(self):
+        if getattr(self, "_handle", None) is not None:
+            self._lib.tnpy_comm_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def eig_lowest_rows(comm: Comm, L_rows, W, R, psi_rows, l: int, row0: int, tol: float = 1e-8, max_matvec: int = 1000,
+                    ncv: int = 0, flags: int = 0, image_rows=None):
+    """Row-sharded ``eig_lowest`` (collective over ``comm``): in place on this rank's rows of psi, (l_rows, d, r).
+    Returns the same dict as :func:`eig_lowest` (identical on every rank)."""
+    _need_cuda(L_rows, W, R, psi_rows, image_rows)
+    lo, d, r = psi_rows.shape
+    wl, wr = W.shape[0], W.shape[1]
+    lib = load()
+    nbytes = lib.tnpy_eig_rows_workspace_bytes(l, lo, r, wl, wr, d, ncv)
+    ws = _scratch.get(nbytes)
+    stats = (c_double * 8)()
+    rc = lib.tnpy_eig_lowest_rows(comm.handle, _ptr(L_rows), _ptr(W), _ptr(R), _ptr(psi_rows), _ptr(image_rows), l, int(row0),
+                                  lo, r, wl, wr, d, int(flags), float(tol), int(max_matvec), int(ncv), stats, _ptr(ws),
+                                  nbytes, _stream())
+    check(rc, "tnpy_eig_lowest_rows", allow_noconv=True)
     return {
         "theta": stats[0], "resid": stats[1], "n_matvec": int(stats[2]), "n_restart": int(stats[3]),
         "converged": bool(stats[4]), "anorm": stats[5], "int8_error_bound": stats[6],

@@ -19,7 +19,7 @@ CSRC = HERE.parent / "csrc"
 INCLUDE = HERE.parent.parent / "include"
 LIB = HERE / "libtnpy_cuda.so"
 OBJ_DIR = HERE / "build"
-SOURCES = ["lib.cu", "gemm_tn.cu", "contract.cu", "blas1.cu", "lanczos.cu", "svd.cu", "qr.cu", "geig.cu", "ozaki.cu", "probe.cu"]
+SOURCES = ["lib.cu", "gemm_tn.cu", "contract.cu", "blas1.cu", "lanczos.cu", "svd.cu", "qr.cu", "geig.cu", "ozaki.cu", "comm.cu", "probe.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -65,7 +65,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
         objs = list(pool.map(compile_one, SOURCES))
-    link = [nvcc, "-shared", "-o", str(LIB), *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+    link = [nvcc, "-shared", "-o", str(LIB), *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
     res = subprocess.run(link, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")

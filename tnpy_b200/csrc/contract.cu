@@ -244,8 +244,9 @@ int chain_gemm(const double* A, int64_t lda, const double* B, int64_t ldb, GemmO
 }
 
 // ---- prepared H_eff ---------------------------------------------------------------------------
-// lo = number of output (bra) rows of L held by the caller: L is (l, wl, lo), y is (lo, d, r).
-// lo == l is the ordinary matvec; lo < l is one rank's row block of the chi-sharded matvec.
+// lo = number of output (bra) rows of L held by the caller, starting at row0: L is (l, wl, lo) = L_full[:, :, row0 :
+// row0 + lo], y is (lo, d, r).  lo == l is the ordinary matvec; lo < l is one rank's row block of the chi-sharded one
+// (the left identity channel is then L[li, 0, m] = delta(li, row0 + m)).
 //
 // flags (canonical-gauge shortcuts, SURVEY 7 "identity channels"): with the upper-triangular MPOs of
 // tnpy.model and a mixed-canonical MPS, L[:, 0, :] and R[:, wr-1, :] are identity matrices.
@@ -261,7 +262,7 @@ struct ChainShape {
 };
 static ChainShape chain_shape(int l, int lo, int r, int wl, int wr, int d, int flags) {
   ChainShape s;
-  s.left_id = (flags & TNPY_LEFT_IDENTITY) && wl > 1 && lo == l;
+  s.left_id = (flags & TNPY_LEFT_IDENTITY) && wl > 1;
   s.right_id = (flags & TNPY_RIGHT_IDENTITY) && wr > 1;
   s.m1 = d * r; s.n1 = (s.left_id ? wl - 1 : wl) * lo; s.k1 = l;
   s.m3 = d * lo; s.n3 = r; s.k3 = r * (s.right_id ? wr - 1 : wr);
@@ -269,8 +270,8 @@ static ChainShape chain_shape(int l, int lo, int r, int wl, int wr, int d, int f
 }
 
 static bool direct_shapes_ok(int l, int lo, int r, int wl, int wr, int d) {
-  return lo == l && wl > 1 && wr > 1 && oz_premix_applicable(l, r, wl, wr, d) &&
-         ozaki_applicable(l * d, r, (wr - 1) * r) && ozaki_applicable(l, d * r, (wl - 1) * l);
+  return wl > 1 && wr > 1 && oz_premix_applicable(l, r, wl, wr, d) && ozaki_applicable(lo * d, r, (wr - 1) * r) &&
+         ozaki_applicable(lo, d * r, (wl - 1) * l);
 }
 
 // no non-zero block W[a, b] with a > 0 and b < wr - 1
@@ -287,7 +288,7 @@ size_t heff_plan_bytes(int l, int lo, int r, int wl, int wr, int d) {
   if (ozaki_applicable(d * r, wl * lo, l)) chain += oz_operand_bytes(wl * lo, l);
   if (ozaki_applicable(d * lo, r, r * wr)) chain += oz_operand_bytes(r, r * wr);
   size_t direct = 0;
-  if (direct_shapes_ok(l, lo, r, wl, wr, d)) direct = oz_operand_bytes(l, (wl - 1) * l) + oz_operand_bytes(r, (wr - 1) * r);
+  if (direct_shapes_ok(l, lo, r, wl, wr, d)) direct = oz_operand_bytes(lo, (wl - 1) * l) + oz_operand_bytes(r, (wr - 1) * r);
   return (chain > direct ? chain : direct) + Workspace::need(1) + 1024;
 }
 
@@ -297,15 +298,16 @@ size_t heff_apply_bytes(int l, int lo, int r, int wl, int wr, int d) {
   if (ozaki_applicable(d * lo, r, r * wr)) chain += oz_operand_bytes(d * lo, r * wr) + oz_mma_scratch_bytes(d * lo, r);
   size_t direct = 0;
   if (direct_shapes_ok(l, lo, r, wl, wr, d))
-    direct = oz_operand_bytes(l * d, (wr - 1) * r) + oz_operand_bytes(d * r, (wl - 1) * l) +
-             oz_mma_scratch_bytes(l * d, r) + oz_mma_scratch_bytes(l, d * r);
+    direct = oz_operand_bytes(lo * d, (wr - 1) * r) + oz_operand_bytes(d * r, (wl - 1) * l) +
+             oz_mma_scratch_bytes(lo * d, r) + oz_mma_scratch_bytes(lo, d * r);
   return (chain > direct ? chain : direct) + 1024;
 }
 
 int heff_plan_init(HeffPlan* plan, const double* L, const double* W, const double* R, const double* W_host, int l,
-                   int lo, int r, int wl, int wr, int d, int flags, int algo, Workspace& mem, cudaStream_t stream) {
+                   int lo, int row0, int r, int wl, int wr, int d, int flags, int algo, Workspace& mem,
+                   cudaStream_t stream) {
   TNPY_TRY(check_dims(l, r, wl, wr, d));
-  TNPY_CHECK_ARG(lo > 0, "non-positive row count");
+  TNPY_CHECK_ARG(lo > 0 && row0 >= 0 && row0 + lo <= l, "row block outside the left bond");
   TNPY_CHECK_ARG(W != nullptr, "null pointer");
   TNPY_CHECK_ARG(L || (l == 1 && wl == 1 && lo == 1), "L may be NULL only for unit left bond");
   TNPY_CHECK_ARG(R || (r == 1 && wr == 1), "R may be NULL only for unit right bond");
@@ -313,7 +315,7 @@ int heff_plan_init(HeffPlan* plan, const double* L, const double* W, const doubl
   if (!R) R = device_one();
   *plan = HeffPlan{};
   plan->L = L; plan->W = W; plan->R = R;
-  plan->l = l; plan->lo = lo; plan->r = r; plan->wl = wl; plan->wr = wr; plan->d = d; plan->flags = flags;
+  plan->l = l; plan->lo = lo; plan->row0 = row0; plan->r = r; plan->wl = wl; plan->wr = wr; plan->d = d; plan->flags = flags;
   plan->mode = HEFF_FP64_CHAIN;
   const ChainShape s = chain_shape(l, lo, r, wl, wr, d, flags);
   const bool oz_ok = tcgen05_allowed(algo);
@@ -380,19 +382,20 @@ int heff_plan_init(HeffPlan* plan, const double* L, const double* W, const doubl
 
 static int apply_direct(const HeffPlan& p, const double* x, double* y, int S, const double* shift_dev, Workspace& ws,
                         cudaStream_t stream) {
-  const int l = p.l, r = p.r, wl = p.wl, wr = p.wr, d = p.d;
+  const int l = p.l, lo = p.lo, r = p.r, wl = p.wl, wr = p.wr, d = p.d;
+  const double* x_rows = x + (int64_t)p.row0 * d * r;  // the caller's rows of x: all the R-side term needs
   OzOperand xa, xb;
-  if (!oz_operand_take(ws, l * d, (wr - 1) * r, &xa) || !oz_operand_take(ws, d * r, (wl - 1) * l, &xb)) {
+  if (!oz_operand_take(ws, lo * d, (wr - 1) * r, &xa) || !oz_operand_take(ws, d * r, (wl - 1) * l, &xb)) {
     set_error("heff_apply: workspace too small");
     return TNPY_EWORKSPACE;
   }
   // y = W[0, wr-1] x - shift x, then both GEMMs accumulate into it
-  TNPY_TRY(oz_premix_a(x, p.W, l, r, wl, wr, d, xa, y, shift_dev, stream));
+  TNPY_TRY(oz_premix_a(x_rows, p.W, lo, r, wl, wr, d, xa, y, shift_dev, stream));
   TNPY_TRY(oz_premix_b(x, p.W, l, r, wl, wr, d, xb, stream));
   // y[(m q), s] += sum_{(b ri)} Xa[(b ri), (m q)] R'[(b ri), s]
-  TNPY_TRY(oz_mma(xa, p.envR, plain_out(y, r, l * d), l * d, r, S, 1, ws, p.bound, stream));
+  TNPY_TRY(oz_mma(xa, p.envR, plain_out(y, r, lo * d), lo * d, r, S, 1, ws, p.bound, stream));
   // y[m, (q s)] += sum_{(a li)} L'[(a li), m] Xb[(a li), (q s)]
-  TNPY_TRY(oz_mma(p.envL, xb, plain_out(y, (int64_t)d * r, l), l, d * r, S, 1, ws, p.bound, stream));
+  TNPY_TRY(oz_mma(p.envL, xb, plain_out(y, (int64_t)d * r, lo), lo, d * r, S, 1, ws, p.bound, stream));
   return TNPY_OK;
 }
 
@@ -411,7 +414,8 @@ int heff_plan_apply(const HeffPlan& p, const double* x, double* y, int S, const 
   }
   // T1[p, r, a, m] = sum_l x[l, (p r)] L[l, (a m)]
   double* t1_dst = t1 + (s.left_id ? lo : 0);
-  if (s.left_id) TNPY_TRY(transpose_strided(x, (int64_t)d * r, 0, l, d * r, t1, (int64_t)wl * lo, 0, 1, stream));  // a = 0
+  if (s.left_id)  // a = 0: T1[p, r, 0, m] = x[row0 + m, p, r]
+    TNPY_TRY(transpose_strided(x + (int64_t)p.row0 * d * r, (int64_t)d * r, 0, lo, d * r, t1, (int64_t)wl * lo, 0, 1, stream));
   if (p.g1_oz) {
     Workspace scratch = ws;
     OzOperand xs;
@@ -448,20 +452,20 @@ int heff_plan_apply(const HeffPlan& p, const double* x, double* y, int S, const 
     const double* t2_last = t2 + (size_t)(wr - 1) * r * d * lo;
     TNPY_TRY(transpose_strided(t2_last, (int64_t)d * lo, lo, r, lo, y, (int64_t)d * r, r, d, stream, true));
   }
-  if (shift_dev) TNPY_TRY(axpy(-1.0, shift_dev, x, y, (int64_t)lo * d * r, stream));
+  if (shift_dev) TNPY_TRY(axpy(-1.0, shift_dev, x + (int64_t)p.row0 * d * r, y, (int64_t)lo * d * r, stream));
   return TNPY_OK;
 }
 
 int heff_apply_rows(const double* L, const double* W, const double* R, const double* x, double* y, int l, int lo,
-                    int r, int wl, int wr, int d, int flags, Workspace& ws, cudaStream_t stream) {
+                    int row0, int r, int wl, int wr, int d, int flags, Workspace& ws, cudaStream_t stream) {
   HeffPlan plan;
-  TNPY_TRY(heff_plan_init(&plan, L, W, R, nullptr, l, lo, r, wl, wr, d, flags, TNPY_GEMM_AUTO, ws, stream));
+  TNPY_TRY(heff_plan_init(&plan, L, W, R, nullptr, l, lo, row0, r, wl, wr, d, flags, TNPY_GEMM_AUTO, ws, stream));
   return heff_plan_apply(plan, x, y, 0, nullptr, ws, stream);
 }
 
 int heff_apply(const double* L, const double* W, const double* R, const double* x, double* y, int l, int r, int wl,
                int wr, int d, int flags, Workspace& ws, cudaStream_t stream) {
-  return heff_apply_rows(L, W, R, x, y, l, l, r, wl, wr, d, flags, ws, stream);
+  return heff_apply_rows(L, W, R, x, y, l, l, 0, r, wl, wr, d, flags, ws, stream);
 }
 
 int env_update_left(const double* L, const double* A, const double* W, double* Lout, int l, int r, int wl, int wr,
@@ -590,7 +594,7 @@ struct tnpy_heff_plan {
 extern "C" size_t tnpy_heff_plan_bytes(int l, int r, int wl, int wr, int d) { return heff_plan_bytes(l, l, r, wl, wr, d) + 256; }
 
 static int plan_create(tnpy_heff_plan** handle, const double* L, const double* W, const double* R, const double* W_host,
-                       int l, int lo, int r, int wl, int wr, int d, int flags, int algo, void* plan_memory,
+                       int l, int lo, int row0, int r, int wl, int wr, int d, int flags, int algo, void* plan_memory,
                        size_t plan_bytes, void* stream) {
   TNPY_CHECK_ARG(handle != nullptr, "null handle");
   TNPY_CHECK_ARG(algo >= TNPY_GEMM_AUTO && algo <= TNPY_GEMM_FP64, "unknown algo");
@@ -600,7 +604,8 @@ static int plan_create(tnpy_heff_plan** handle, const double* L, const double* W
     return TNPY_EINVAL;
   }
   Workspace mem(plan_memory, plan_bytes);
-  const int rc = heff_plan_init(&h->plan, L, W, R, W_host, l, lo, r, wl, wr, d, flags, algo, mem, static_cast<cudaStream_t>(stream));
+  const int rc = heff_plan_init(&h->plan, L, W, R, W_host, l, lo, row0, r, wl, wr, d, flags, algo, mem,
+                                static_cast<cudaStream_t>(stream));
   if (rc != TNPY_OK) {
     delete h;
     return rc;
@@ -612,14 +617,13 @@ static int plan_create(tnpy_heff_plan** handle, const double* L, const double* W
 extern "C" int tnpy_heff_plan_create(tnpy_heff_plan** handle, const double* L, const double* W, const double* R,
                                      const double* W_host, int l, int r, int wl, int wr, int d, int flags, int algo,
                                      void* plan_memory, size_t plan_bytes, void* stream) {
-  return plan_create(handle, L, W, R, W_host, l, l, r, wl, wr, d, flags, algo, plan_memory, plan_bytes, stream);
+  return plan_create(handle, L, W, R, W_host, l, l, 0, r, wl, wr, d, flags, algo, plan_memory, plan_bytes, stream);
 }
 
 extern "C" int tnpy_heff_plan_create_rows(tnpy_heff_plan** handle, const double* L_rows, const double* W, const double* R,
-                                          int l, int l_rows, int r, int wl, int wr, int d, int algo, void* plan_memory,
-                                          size_t plan_bytes, void* stream) {
-  TNPY_CHECK_ARG(l_rows > 0 && l_rows <= l, "row count outside (0, l]");
-  return plan_create(handle, L_rows, W, R, nullptr, l, l_rows, r, wl, wr, d, 0, algo, plan_memory, plan_bytes, stream);
+                                          const double* W_host, int l, int row0, int l_rows, int r, int wl, int wr, int d,
+                                          int flags, int algo, void* plan_memory, size_t plan_bytes, void* stream) {
+  return plan_create(handle, L_rows, W, R, W_host, l, l_rows, row0, r, wl, wr, d, flags, algo, plan_memory, plan_bytes, stream);
 }
 
 extern "C" int tnpy_heff_plan_mode(const tnpy_heff_plan* handle) { return handle ? handle->plan.mode : TNPY_EINVAL; }
@@ -666,10 +670,10 @@ extern "C" int tnpy_identity_defect(const double* E, int dim, int w, int channel
 }
 
 extern "C" int tnpy_heff_apply_rows(const double* L_rows, const double* W, const double* R, const double* x,
-                                    double* y_rows, int l, int l_rows, int r, int wl, int wr, int d, void* workspace,
-                                    size_t workspace_bytes, void* stream) {
+                                    double* y_rows, int l, int row0, int l_rows, int r, int wl, int wr, int d, int flags,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
   Workspace ws(workspace, workspace_bytes);
-  return heff_apply_rows(L_rows, W, R, x, y_rows, l, l_rows, r, wl, wr, d, 0, ws, static_cast<cudaStream_t>(stream));
+  return heff_apply_rows(L_rows, W, R, x, y_rows, l, l_rows, row0, r, wl, wr, d, flags, ws, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int tnpy_env_update_left(const double* L, const double* A, const double* W, double* Lout, int l, int r,

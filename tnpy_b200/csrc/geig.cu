@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(256) geig_small_kernel(double* __restrict__ GA
   __syncthreads();
   if (m > 1) {
     const int me = (m + 1) & ~1, half = me / 2;
+    double o_prev = 1e300;  // thread 0 only
     for (int sweep = 0; sweep < 40; ++sweep) {
       double off = 0.0, dia = 0.0;
       for (int idx = tid; idx < m * m; idx += nt) {
@@ -115,7 +116,12 @@ __global__ void __launch_bounds__(256) geig_small_kernel(double* __restrict__ GA
       if (tid == 0) {
         double o = 0.0, d2 = 0.0;
         for (int w = 0; w < (nt >> 5); ++w) { o += red[w]; d2 += red[32 + w]; }
-        red[64] = (o <= 1e-31 * d2 || o == 0.0) ? 1.0 : 0.0;
+        // converged: off-diagonal mass below 1e-31 of the diagonal mass, or at its rounding floor -- Jacobi converges
+        // quadratically, so a sweep that no longer shrinks an already tiny off-diagonal mass by 4x has hit the floor
+        // ((m eps)^2-ish; a fixed 1e-31 alone is below it for m > ~16 and made those solves run all 40 sweeps: 1.5 ms)
+        const bool stalled = o <= 1e-24 * d2 && o >= 0.25 * o_prev;
+        red[64] = (o <= 1e-31 * d2 || o == 0.0 || stalled) ? 1.0 : 0.0;
+        o_prev = o;
       }
       __syncthreads();
       const bool converged = red[64] != 0.0;

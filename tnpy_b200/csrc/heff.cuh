@@ -18,7 +18,7 @@ enum HeffMode { HEFF_FP64_CHAIN = 0, HEFF_OZ_CHAIN = 1, HEFF_OZ_DIRECT = 2 };
 
 struct HeffPlan {
   const double *L, *W, *R;
-  int l, lo, r, wl, wr, d, flags;
+  int l, lo, row0, r, wl, wr, d, flags;  // lo rows of the bra bond starting at row0 (lo == l, row0 == 0: all of them)
   int mode;
   bool g1_oz, g3_oz;   // OZ_CHAIN: which of the two GEMMs run on the tcgen05 path
   OzOperand envL, envR;  // sliced constant operands (plan memory)
@@ -32,7 +32,8 @@ size_t heff_apply_bytes(int l, int lo, int r, int wl, int wr, int d);
 // W_host: host copy of W (wl, wr, d, d) or NULL (then the library reads W back when the direct path is otherwise
 // possible, synchronising the stream once).  algo: TNPY_GEMM_* (AUTO = the process-wide selection).
 int heff_plan_init(HeffPlan* plan, const double* L, const double* W, const double* R, const double* W_host, int l,
-                   int lo, int r, int wl, int wr, int d, int flags, int algo, Workspace& mem, cudaStream_t stream);
+                   int lo, int row0, int r, int wl, int wr, int d, int flags, int algo, Workspace& mem,
+                   cudaStream_t stream);
 // y = H_eff x - shift x.  slices: 7-bit slices per operand on the tcgen05 modes (0 = library default);
 // shift_dev: device scalar or NULL.
 int heff_plan_apply(const HeffPlan& plan, const double* x, double* y, int slices, const double* shift_dev,

@@ -9,6 +9,7 @@
 // stop or restart.  Basis vectors never leave HBM.
 #include <math.h>
 
+#include "comm.cuh"
 #include "heff.cuh"
 
 namespace tnpy {
@@ -42,6 +43,7 @@ __device__ void jacobi_eig_smem(double (*a)[kRitzLd], double (*z)[kRitzLd], int 
   if (m == 1) return;
   const int me = (m + 1) & ~1;  // even player count (last one may be a bye)
   const int half = me / 2;
+  double o_prev = 1e300;  // thread 0 only
   for (int sweep = 0; sweep < 40; ++sweep) {
     // convergence: off-diagonal mass vs diagonal mass
     double off = 0.0, dia = 0.0;
@@ -57,7 +59,12 @@ __device__ void jacobi_eig_smem(double (*a)[kRitzLd], double (*z)[kRitzLd], int 
     if (tid == 0) {
       double o = 0.0, d2 = 0.0;
       for (int w = 0; w < (nt >> 5); ++w) { o += red[w]; d2 += red[32 + w]; }
-      red[64] = (o <= 1e-31 * d2 || o == 0.0) ? 1.0 : 0.0;
+      // converged: off-diagonal mass below 1e-31 of the diagonal mass, or at its rounding floor -- Jacobi converges
+      // quadratically, so a sweep that no longer shrinks an already tiny off-diagonal mass by 4x has hit the floor
+      // ((m eps)^2-ish; a fixed 1e-31 alone is below it for m > ~16 and made those solves run all 40 sweeps: 1.5 ms)
+      const bool stalled = o <= 1e-24 * d2 && o >= 0.25 * o_prev;
+      red[64] = (o <= 1e-31 * d2 || o == 0.0 || stalled) ? 1.0 : 0.0;
+      o_prev = o;
     }
     __syncthreads();
     const bool converged = red[64] != 0.0;
@@ -210,6 +217,16 @@ __global__ void reorth_decision_kernel(const double* __restrict__ h, int m, cons
     for (int j = threadIdx.x; j < m; j += blockDim.x) h2[j] = 0.0;
 }
 
+// Row-sharded solve: a norm is the square root of a sum over the ranks.  pre: *sq = the local norm squared -- or, when
+// this step's pass was skipped on the device (*skip != 0) and *norm is therefore already the global norm, *norm^2 /
+// world so that the all-reduce reproduces it; post: *norm = sqrt(*sq).
+__global__ void norm_pre_reduce_kernel(const double* __restrict__ local_norm, const double* __restrict__ norm,
+                                       const int* __restrict__ skip, int world, double* __restrict__ sq) {
+  const bool skipped = skip != nullptr && *skip != 0;
+  *sq = skipped ? (*norm * *norm) / world : (*local_norm * *local_norm);
+}
+__global__ void norm_post_reduce_kernel(const double* __restrict__ sq, double* __restrict__ norm) { *norm = sqrt(*sq); }
+
 static void pick_sizes(int64_t n, int ncv_in, int& ncv, int& keep) {
   // default basis of 32: on hard local problems (first sweeps from a random MPS) thick restart with
   // (32, 10) needs ~20 % fewer matvecs than (20, 6) and is within ~10 % of unrestarted Lanczos, while the
@@ -234,20 +251,36 @@ extern "C" size_t tnpy_eig_workspace_bytes(int l, int r, int wl, int wr, int d, 
   return eig_ws_layout(n, ncv, keep, heff_plan_bytes(l, l, r, wl, wr, d) + heff_apply_bytes(l, l, r, wl, wr, d) + 1024);
 }
 
-static int eig_lowest_impl(const double* L, const double* W, const double* R, double* psi, double* hpsi, int l, int r,
-                           int wl, int wr, int d, int flags, double tol, int max_matvec, int ncv_in,
-                           double* stats_host, void* workspace, size_t workspace_bytes, void* stream_) {
+// comm == nullptr: the whole problem on this GPU (lo == l, row0 == 0).  Otherwise rank g of the communicator holds
+// the bra rows [row0, row0 + lo) of the left bond: L = L_full[:, :, rows] as (l, wl, lo), the same rows of psi / hpsi
+// and of every Lanczos vector, and full copies of W and R.  Per step the ranks all-gather the current vector (the
+// one exchange of data: (G - 1) / G of 8 N bytes per rank over NVLink), run their row block of the matvec, and
+// all-reduce the Gram-Schmidt coefficients and norms (a few dozen doubles); the small Ritz problem is solved
+// redundantly on every rank from identical inputs, so all ranks take identical decisions.
+static int eig_lowest_impl(const tnpy_comm* comm, const double* L, const double* W, const double* R, double* psi,
+                           double* hpsi, int l, int row0, int lo, int r, int wl, int wr, int d, int flags, double tol,
+                           int max_matvec, int ncv_in, double* stats_host, void* workspace, size_t workspace_bytes,
+                           void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   TNPY_CHECK_ARG(psi && W, "null pointer");
   TNPY_CHECK_ARG(l > 0 && r > 0 && wl > 0 && wr > 0 && d > 0, "non-positive dimension");
-  const int64_t n = (int64_t)l * d * r;
+  TNPY_CHECK_ARG(lo > 0 && row0 >= 0 && row0 + lo <= l, "row block outside the left bond");
+  TNPY_CHECK_ARG(comm != nullptr || lo == l, "a row block needs a communicator");
+  TNPY_CHECK_ARG(comm == nullptr || (lo * comm->world == l && row0 == comm->rank * lo), "rows must be split evenly, rank g holding block g");
+  const int64_t n = (int64_t)lo * d * r;        // local vector length
+  const int64_t n_full = (int64_t)l * d * r;    // global vector length
   const int64_t ldv = n + (n & 1);
   int ncv, keep;
-  pick_sizes(n, ncv_in, ncv, keep);
+  pick_sizes(n_full, ncv_in, ncv, keep);
   if (tol <= 0.0) tol = 2.220446049250313e-16 * 1e4;
   if (max_matvec <= 0) max_matvec = 1000;
+  // sum over the ranks of `count` doubles in place / of a squared norm (no-ops on a single GPU)
+  auto reduce = [&](double* buf, int count) -> int {
+    return comm ? comm_allreduce_sum(comm, buf, (size_t)count, stream) : TNPY_OK;
+  };
 
   Workspace ws(workspace, workspace_bytes);
+  double* x_full = comm ? ws.take<double>((size_t)n_full) : nullptr;  // the all-gathered current vector
   double* V = ws.take<double>((size_t)(ncv + 1) * ldv);
   double* Y = ws.take<double>((size_t)keep * ldv);
   double* T = ws.take<double>(kMaxNcv * kMaxNcv);
@@ -258,7 +291,7 @@ static int eig_lowest_impl(const double* L, const double* W, const double* R, do
   double* h_local = ws.take<double>(64);
   double* status = ws.take<double>(64);
   int* skip2 = reinterpret_cast<int*>(status + 48);  // device flag: skip the second Gram-Schmidt pass of this step
-  if (!V || !Y || !T || !S || !thetas || !h || !h2 || !h_local || !status) {
+  if (!V || !Y || !T || !S || !thetas || !h || !h2 || !h_local || !status || (comm && !x_full)) {
     set_error("tnpy_eig_lowest: workspace too small (%zu bytes given)", workspace_bytes);
     return TNPY_EWORKSPACE;
   }
@@ -272,7 +305,7 @@ static int eig_lowest_impl(const double* L, const double* W, const double* R, do
   // slices is orders of magnitude below the residual threshold does not need the eighth (28 instead of 36 slice
   // GEMMs); the bound is read back with every status record and the slice count raised -- or the solve moved to
   // the native FP64 chain -- if it ever comes within 1 % of tol * ||A||.
-  const size_t plan_bytes = heff_plan_bytes(l, l, r, wl, wr, d);  // enough for any mode: a later re-plan fits too
+  const size_t plan_bytes = heff_plan_bytes(l, lo, r, wl, wr, d);  // enough for any mode: a later re-plan fits too
   char* plan_mem = ws.take<char>(plan_bytes);
   if (!plan_mem) {
     set_error("tnpy_eig_lowest: workspace too small (%zu bytes given)", workspace_bytes);
@@ -281,12 +314,24 @@ static int eig_lowest_impl(const double* L, const double* W, const double* R, do
   HeffPlan plan;
   {
     Workspace mem(plan_mem, plan_bytes);
-    TNPY_TRY(heff_plan_init(&plan, L, W, R, nullptr, l, l, r, wl, wr, d, flags, TNPY_GEMM_AUTO, mem, stream));
+    TNPY_TRY(heff_plan_init(&plan, L, W, R, nullptr, l, lo, row0, r, wl, wr, d, flags, TNPY_GEMM_AUTO, mem, stream));
   }
   int slices = (tol >= 1e-10 && ozaki_slices() == 8) ? 7 : ozaki_slices();
   const size_t chain_off = ws.used;
+  // global norm of the vector whose local norm multi_dot / multi_axpy just left in *local (see the kernels above)
+  double* sq = status + 40;
+  auto reduce_norm = [&](const double* local, double* norm, const int* skip) -> int {
+    if (!comm) return TNPY_OK;
+    norm_pre_reduce_kernel<<<1, 1, 0, stream>>>(local, norm, skip, comm->world, sq);
+    TNPY_LAUNCH_OK();
+    TNPY_TRY(comm_allreduce_sum(comm, sq, 1, stream));
+    norm_post_reduce_kernel<<<1, 1, 0, stream>>>(sq, norm);
+    TNPY_LAUNCH_OK();
+    return TNPY_OK;
+  };
   // V[0] = v0 / ||v0||
   TNPY_TRY(multi_dot(psi, ldv, 1, psi, n, status + ST_BETA, 1, stream));
+  TNPY_TRY(reduce_norm(status + ST_BETA, status + ST_BETA, nullptr));
   TNPY_TRY(scale_copy(psi, V, n, 1.0, status + ST_BETA, 1, stream));
   TNPY_CUDA_OK(cudaMemsetAsync(T, 0, sizeof(double) * kMaxNcv * kMaxNcv, stream));
 
@@ -308,7 +353,8 @@ static int eig_lowest_impl(const double* L, const double* W, const double* R, do
     double* vj = V + (int64_t)j * ldv;
     double* w = V + (int64_t)(j + 1) * ldv;
     Workspace chain(static_cast<char*>(workspace) + chain_off, workspace_bytes - chain_off);
-    TNPY_TRY(heff_plan_apply(plan, vj, w, slices, nullptr, chain, stream));
+    if (comm) TNPY_TRY(comm_allgather(comm, vj, x_full, (size_t)n, stream));
+    TNPY_TRY(heff_plan_apply(plan, comm ? x_full : vj, w, slices, nullptr, chain, stream));
     ++n_matvec;
     // Gram-Schmidt in two stages.  H v_j has analytically non-zero components only on v_{j-1} and v_j
     // (three-term recurrence; on every kept Ritz vector in the first step after a thick restart), so a *local*
@@ -322,17 +368,23 @@ static int eig_lowest_impl(const double* L, const double* W, const double* R, do
     const int local_from = (j == whole_basis_step) ? 0 : (j > 0 ? j - 1 : 0);
     const int n_local = j + 1 - local_from;
     double* v_local = V + (int64_t)local_from * ldv;
+    double* local_norm = comm ? status + 41 : status + ST_BETA;  // sharded: multi_axpy leaves the *local* norm here
     TNPY_TRY(multi_dot(v_local, ldv, n_local, w, n, h_local, 0, stream));
+    TNPY_TRY(reduce(h_local, n_local));
     TNPY_TRY(multi_axpy(v_local, ldv, n_local, h_local, w, n, nullptr, stream));
     TNPY_TRY(multi_dot(V, ldv, j + 1, w, n, h, 0, stream));
-    TNPY_TRY(multi_axpy(V, ldv, j + 1, h, w, n, status + ST_BETA, stream));
+    TNPY_TRY(reduce(h, j + 1));
+    TNPY_TRY(multi_axpy(V, ldv, j + 1, h, w, n, local_norm, stream));
+    TNPY_TRY(reduce_norm(local_norm, status + ST_BETA, nullptr));
     reorth_decision_kernel<<<1, 64, 0, stream>>>(h, j + 1, status + ST_BETA, eta, h2, skip2);
     TNPY_LAUNCH_OK();
     TNPY_TRY(multi_dot(V, ldv, j + 1, w, n, h2, 0, stream, skip2));
-    TNPY_TRY(multi_axpy(V, ldv, j + 1, h2, w, n, status + ST_BETA, stream, skip2));
+    TNPY_TRY(reduce(h2, j + 1));  // skipped pass: the decision kernel zeroed h2 on every rank
+    TNPY_TRY(multi_axpy(V, ldv, j + 1, h2, w, n, local_norm, stream, skip2));
+    TNPY_TRY(reduce_norm(local_norm, status + ST_BETA, skip2));
     const int m = j + 1;
     ++since_check;
-    const bool look = m == ncv || n_matvec >= max_matvec || m >= n || since_check >= stride;
+    const bool look = m == ncv || n_matvec >= max_matvec || m >= n_full || since_check >= stride;
     ritz_kernel<<<1, 256, 0, stream>>>(T, h, h2, h_local, local_from, status + ST_BETA, j, tol, S, thetas, status, look ? 0 : 1);
     TNPY_LAUNCH_OK();
     TNPY_TRY(scale_copy(w, w, n, 1.0, status + ST_BETA, 1, stream));
@@ -354,7 +406,7 @@ static int eig_lowest_impl(const double* L, const double* W, const double* R, do
         slices = kOzMaxSlices;
       } else {
         Workspace again(plan_mem, plan_bytes);
-        TNPY_TRY(heff_plan_init(&plan, L, W, R, nullptr, l, l, r, wl, wr, d, flags, TNPY_GEMM_FP64, again, stream));
+        TNPY_TRY(heff_plan_init(&plan, L, W, R, nullptr, l, lo, row0, r, wl, wr, d, flags, TNPY_GEMM_FP64, again, stream));
       }
       if (plan.bound) TNPY_CUDA_OK(cudaMemsetAsync(plan.bound, 0, sizeof(double), stream));
     }
@@ -362,7 +414,7 @@ static int eig_lowest_impl(const double* L, const double* W, const double* R, do
       const double thr = tol * hst[ST_ANORM];
       stride = hst[ST_RESID] > 1e4 * thr ? 3 : (hst[ST_RESID] > 1e2 * thr ? 2 : 1);
     }
-    done = hst[ST_DONE] != 0.0 || !(hst[ST_BETA] > 0.0) || m >= n;
+    done = hst[ST_DONE] != 0.0 || !(hst[ST_BETA] > 0.0) || m >= n_full;
     if (done || n_matvec >= max_matvec) {
       // psi = V[0..m-1] . S[:, 0]
       TNPY_TRY(combine(V, ldv, m, S, kMaxNcv, 1, psi, ldv, n, stream));
@@ -370,7 +422,7 @@ static int eig_lowest_impl(const double* L, const double* W, const double* R, do
         // H psi from the Lanczos relation H V_m = V_m T + beta v_{m+1} e_m^T (exact to rounding here, T being the
         // explicit projection): H psi = theta psi + (beta s_m) v_{m+1}; v_{m+1} = V[m] was normalised above
         TNPY_TRY(scale_copy(psi, hpsi, n, hst[ST_THETA], nullptr, 0, stream));
-        if (hst[ST_BETA] > 0.0 && m < n) TNPY_TRY(axpy(hst[ST_RCOEF], nullptr, V + (int64_t)m * ldv, hpsi, n, stream));
+        if (hst[ST_BETA] > 0.0 && m < n_full) TNPY_TRY(axpy(hst[ST_RCOEF], nullptr, V + (int64_t)m * ldv, hpsi, n, stream));
       }
       break;
     }
@@ -412,8 +464,8 @@ static int eig_lowest_impl(const double* L, const double* W, const double* R, do
 extern "C" int tnpy_eig_lowest(const double* L, const double* W, const double* R, double* psi, int l, int r, int wl,
                                int wr, int d, int flags, double tol, int max_matvec, int ncv_in, double* stats_host,
                                void* workspace, size_t workspace_bytes, void* stream_) {
-  return eig_lowest_impl(L, W, R, psi, nullptr, l, r, wl, wr, d, flags, tol, max_matvec, ncv_in, stats_host, workspace,
-                         workspace_bytes, stream_);
+  return eig_lowest_impl(nullptr, L, W, R, psi, nullptr, l, 0, l, r, wl, wr, d, flags, tol, max_matvec, ncv_in, stats_host,
+                         workspace, workspace_bytes, stream_);
 }
 
 extern "C" int tnpy_eig_lowest_image(const double* L, const double* W, const double* R, double* psi, double* hpsi,
@@ -421,6 +473,23 @@ extern "C" int tnpy_eig_lowest_image(const double* L, const double* W, const dou
                                      int ncv_in, double* stats_host, void* workspace, size_t workspace_bytes,
                                      void* stream_) {
   TNPY_CHECK_ARG(hpsi != nullptr, "null hpsi");
-  return eig_lowest_impl(L, W, R, psi, hpsi, l, r, wl, wr, d, flags, tol, max_matvec, ncv_in, stats_host, workspace,
-                         workspace_bytes, stream_);
+  return eig_lowest_impl(nullptr, L, W, R, psi, hpsi, l, 0, l, r, wl, wr, d, flags, tol, max_matvec, ncv_in, stats_host,
+                         workspace, workspace_bytes, stream_);
+}
+
+extern "C" size_t tnpy_eig_rows_workspace_bytes(int l, int l_rows, int r, int wl, int wr, int d, int ncv_in) {
+  int ncv, keep;
+  pick_sizes((int64_t)l * d * r, ncv_in, ncv, keep);
+  return eig_ws_layout((int64_t)l_rows * d * r, ncv, keep,
+                       heff_plan_bytes(l, l_rows, r, wl, wr, d) + heff_apply_bytes(l, l_rows, r, wl, wr, d) + 1024) +
+         Workspace::need((size_t)l * d * r);
+}
+
+extern "C" int tnpy_eig_lowest_rows(const tnpy_comm* comm, const double* L_rows, const double* W, const double* R,
+                                    double* psi_rows, double* hpsi_rows, int l, int row0, int l_rows, int r, int wl, int wr,
+                                    int d, int flags, double tol, int max_matvec, int ncv_in, double* stats_host,
+                                    void* workspace, size_t workspace_bytes, void* stream_) {
+  TNPY_CHECK_ARG(comm != nullptr, "null communicator");
+  return eig_lowest_impl(comm, L_rows, W, R, psi_rows, hpsi_rows, l, row0, l_rows, r, wl, wr, d, flags, tol, max_matvec,
+                         ncv_in, stats_host, workspace, workspace_bytes, stream_);
 }

@@ -97,6 +97,34 @@ __device__ __forceinline__ void oz_store16(int8_t* __restrict__ row, int64_t sli
   }
 }
 
+// The transposing slicers (source contiguous along the columns, output contiguous along K) stage the digits of a
+// 32-column x 128-k tile in shared memory -- 16 bytes per thread and slice -- and write whole 128-byte lines; 16-byte
+// stores straight from the registers, one row per thread, were measured 2x slower (partial-sector writes).
+constexpr int kSliceTileLd = 144;  // 128 k + 16 pad: the 16-byte chunks of a quarter warp fall into distinct banks
+typedef int8_t OzSliceTile[kOzMaxSlices][32][kSliceTileLd];
+
+__device__ __forceinline__ void oz_tile_put(OzSliceTile& tile, int tx, int ty, const uint4 (&dig)[kOzMaxSlices]) {
+#pragma unroll
+  for (int sl = 0; sl < kOzMaxSlices; ++sl) *reinterpret_cast<uint4*>(&tile[sl][tx][16 * ty]) = dig[sl];
+}
+
+// write the tile's columns c0 .. c0 + 31 (< ncols), bytes [kbase, min(kbase + 128, kend)) of their rows
+__device__ __forceinline__ void oz_tile_flush(const OzSliceTile& tile, int8_t* __restrict__ slices, int64_t slice_stride,
+                                              int64_t Kp, int64_t c0, int64_t ncols, int64_t kbase, int64_t kend) {
+  const bool aligned = (kbase & 15) == 0;
+  for (int idx = threadIdx.x; idx < kOzMaxSlices * 32 * 8; idx += 256) {
+    const int chunk = idx % 8, cc = (idx / 8) % 32, sl = idx / 256;
+    const int64_t k = kbase + 16 * chunk;
+    if (c0 + cc >= ncols || k >= kend) continue;
+    int8_t* dst = slices + sl * slice_stride + (c0 + cc) * Kp + k;
+    if (aligned && k + 16 <= kend) {
+      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(&tile[sl][cc][16 * chunk]);
+    } else {
+      for (int e = 0; e < 16 && k + e < kend; ++e) dst[e] = tile[sl][cc][16 * chunk + e];
+    }
+  }
+}
+
 // slices[s][c][k] (k contiguous, Kp bytes per row) from P[row(k)][c].  Block = 32 columns x 8 chunks of 16 k: the
 // loads are coalesced along the columns, every thread then owns 16 consecutive bytes of one (slice, column) row.
 __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict__ P, int64_t ld, OzRowMap rows, int K,
@@ -113,13 +141,15 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict_
     const double part = warp_sum(sc * sc);
     if (tx == 0 && part > 0.0) atomicAdd(sumsq, part);  // feeds an error *bound*: summation order is immaterial
   }
-  if (c >= MN || k0 >= Kp) return;
+  __shared__ __align__(16) OzSliceTile tile;
   double t[16];
 #pragma unroll
-  for (int e = 0; e < 16; ++e) t[e] = (k0 + e < K) ? P[oz_src_row(k0 + e, rows) * ld + c] * inv : 0.0;  // |t| <= 0.5
+  for (int e = 0; e < 16; ++e) t[e] = (c < MN && k0 + e < K) ? P[oz_src_row(k0 + e, rows) * ld + c] * inv : 0.0;  // |t| <= 0.5
   uint4 dig[kOzMaxSlices];
   oz_digits16([&t](int e) { return t[e]; }, dig);
-  oz_store16(slices + (int64_t)c * Kp + k0, slice_stride, dig, true);  // Kp and k0 are multiples of 16
+  oz_tile_put(tile, tx, ty, dig);
+  __syncthreads();
+  oz_tile_flush(tile, slices, slice_stride, Kp, (int64_t)blockIdx.x * 32, MN, (int64_t)blockIdx.y * 128, Kp);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -315,51 +345,37 @@ __global__ void __launch_bounds__(256, D <= 2 ? 2 : 1) oz_premix_b_kernel(const 
     part = warp_sum(part);
     if (tx == 0 && part > 0.0) atomicAdd(sumsq, part);
   }
+  __shared__ __align__(16) OzSliceTile tile;
   __syncthreads();
-  if (s < r && l0 < l) {
-    double xv[16][D];
+  double xv[16][D];
 #pragma unroll
-    for (int e = 0; e < 16; ++e)
+  for (int e = 0; e < 16; ++e)
 #pragma unroll
-      for (int p = 0; p < D; ++p) xv[e][p] = (l0 + e < l) ? x[((int64_t)(l0 + e) * d + p) * r + s] : 0.0;
-    const int valid = min(16, l - l0);
-    for (int a = 0; a < na; ++a)
+    for (int p = 0; p < D; ++p) xv[e][p] = (s < r && l0 + e < l) ? x[((int64_t)(l0 + e) * d + p) * r + s] : 0.0;
+  const int64_t lb = (int64_t)blockIdx.y * 128;  // first li of this block's tile
+  for (int a = 0; a < na; ++a)
 #pragma unroll
-      for (int q = 0; q < D; ++q) {
-        double cw[D];
+    for (int q = 0; q < D; ++q) {
+      double cw[D];
 #pragma unroll
-        for (int p = 0; p < D; ++p) cw[p] = wc[a][p][q] * inv[q];  // exact scaling: inv is a power of two
-        uint4 dig[kOzMaxSlices];
-        oz_digits16(
-            [&](int e) {
-              double v = 0.0;
+      for (int p = 0; p < D; ++p) cw[p] = wc[a][p][q] * inv[q];  // exact scaling: inv is a power of two
+      uint4 dig[kOzMaxSlices];
+      oz_digits16(
+          [&](int e) {
+            double v = 0.0;
 #pragma unroll
-              for (int p = 0; p < D; ++p) v = fma(cw[p], xv[e][p], v);
-              return v;
-            },
-            dig);
-        const int64_t k0 = (int64_t)a * l + l0;
-        int8_t* row = slices + ((int64_t)q * r + s) * Kp + k0;
-        if (valid == 16 || (a == na - 1 && k0 + 16 <= Kp)) {
-          oz_store16(row, slice_stride, dig, (k0 & 15) == 0);
-        } else {
-#pragma unroll
-          for (int sl = 0; sl < kOzMaxSlices; ++sl) {
-            const uint32_t w[4] = {dig[sl].x, dig[sl].y, dig[sl].z, dig[sl].w};
-            for (int e = 0; e < valid; ++e) row[sl * slice_stride + e] = (int8_t)(w[e >> 2] >> (8 * (e & 3)));
-          }
-        }
-      }
-  }
-  // what is left of the K padding: rows (q, s) of this block's columns, bytes [na * l, Kp), by the first row of blocks
-  if (blockIdx.y == 0) {
-    const int kreal = na * l, kpad = (int)(Kp - kreal);
-    for (int item = threadIdx.x; item < 32 * d * kOzMaxSlices * kpad; item += 256) {
-      const int e = item % kpad, sl = (item / kpad) % kOzMaxSlices, q = (item / (kpad * kOzMaxSlices)) % d,
-                cc = item / (kpad * kOzMaxSlices * d);
-      if (blockIdx.x * 32 + cc < r) slices[sl * slice_stride + ((int64_t)q * r + blockIdx.x * 32 + cc) * Kp + kreal + e] = 0;
+            for (int p = 0; p < D; ++p) v = fma(cw[p], xv[e][p], v);
+            return v;
+          },
+          dig);
+      oz_tile_put(tile, tx, ty, dig);
+      __syncthreads();
+      // K = (a, li): this tile holds li in [lb, lb + 128); the last channel may run on into the zero padding
+      const int64_t kend = (a == na - 1) ? Kp : (int64_t)(a + 1) * l;
+      oz_tile_flush(tile, slices + (int64_t)q * r * Kp, slice_stride, Kp, (int64_t)blockIdx.x * 32, r, (int64_t)a * l + lb,
+                    min(kend, (int64_t)a * l + lb + 128));
+      __syncthreads();
     }
-  }
 }
 
 // *bound = max(*bound, coef * sqrt(sa2 * sb2)): the normwise error bound of one product (header comment)

@@ -267,8 +267,8 @@ class ShiftInvertDMRG(FiniteDMRG):
 
     #: up to this many unknowns the local pencil is solved densely on the device (the projected H^2 is too
     #: ill-conditioned for inverse-free Krylov iterations, see csrc/geig.cu); larger sites iterate and raise
-    #: RuntimeError when the iteration does not converge.  The reference's own test size (n=10, chi=64: bonds of 32,
-    #: 2048 unknowns) is inside the dense range; tnpy_heff_dense allows up to 4096.
+    #: RuntimeError when the iteration does not converge.  The reference's own test size (n=10, chi=64: bonds of at
+    #: most 32, 1024 unknowns) is inside the dense range; tnpy_heff_dense allows up to 4096.
     dense_pencil_dim = 2048
 
     def _solve_on_device(self, site: int, tol: float, **kwargs) -> float:
