@@ -92,29 +92,35 @@ __device__ void jacobi_eig_smem(double (*a)[kRitzLd], double (*z)[kRitzLd], int 
         cs[tid] = c; sn[tid] = s; pp[tid] = p; qq[tid] = q;
       }
       __syncthreads();
-      // column rotations: A <- A J, Z <- Z J
-      for (int idx = tid; idx < half * m; idx += nt) {
-        const int i = idx / m, k = idx % m;
-        const int p = pp[i], q = qq[i];
-        if (q >= m || sn[i] == 0.0) continue;
-        const double c = cs[i], s = sn[i];
-        const double akp = a[k][p], akq = a[k][q];
-        a[k][p] = c * akp - s * akq;
-        a[k][q] = s * akp + c * akq;
-        const double zkp = z[k][p], zkq = z[k][q];
-        z[k][p] = c * zkp - s * zkq;
-        z[k][q] = s * zkp + c * zkq;
-      }
-      __syncthreads();
-      // row rotations: A <- J^T A
-      for (int idx = tid; idx < half * m; idx += nt) {
-        const int i = idx / m, k = idx % m;
-        const int p = pp[i], q = qq[i];
-        if (q >= m || sn[i] == 0.0) continue;
-        const double c = cs[i], s = sn[i];
-        const double apk = a[p][k], aqk = a[q][k];
-        a[p][k] = c * apk - s * aqk;
-        a[q][k] = s * apk + c * aqk;
+      // A <- J^T A J in one pass: work item (i, j) owns the 2 x 2 block A[{p_i, q_i}][{p_j, q_j}], which only the
+      // rotations of pairs i (rows) and j (columns) touch; Z <- Z J: item (k, i) owns Z[k][{p_i, q_i}].
+      for (int idx = tid; idx < half * half + m * half; idx += nt) {
+        if (idx < half * half) {
+          const int i = idx / half, j = idx % half;
+          const int pi = pp[i], qi = qq[i], pj = pp[j], qj = qq[j];
+          if (sn[i] == 0.0 && sn[j] == 0.0) continue;
+          const bool ri = qi < m, rj = qj < m;  // a bye (q == m on an odd m) has no second row / column
+          const double ci = cs[i], si = sn[i], cj = cs[j], sj = sn[j];
+          double b00 = a[pi][pj], b01 = rj ? a[pi][qj] : 0.0, b10 = ri ? a[qi][pj] : 0.0, b11 = (ri && rj) ? a[qi][qj] : 0.0;
+          // rows: J_i^T B
+          const double r00 = ci * b00 - si * b10, r01 = ci * b01 - si * b11;
+          const double r10 = si * b00 + ci * b10, r11 = si * b01 + ci * b11;
+          // columns: (J_i^T B) J_j
+          b00 = cj * r00 - sj * r01; b01 = sj * r00 + cj * r01;
+          b10 = cj * r10 - sj * r11; b11 = sj * r10 + cj * r11;
+          a[pi][pj] = b00;
+          if (rj) a[pi][qj] = b01;
+          if (ri) a[qi][pj] = b10;
+          if (ri && rj) a[qi][qj] = b11;
+        } else {
+          const int e = idx - half * half, k = e / half, i = e % half;
+          const int p = pp[i], q = qq[i];
+          if (q >= m || sn[i] == 0.0) continue;
+          const double c = cs[i], s = sn[i];
+          const double zkp = z[k][p], zkq = z[k][q];
+          z[k][p] = c * zkp - s * zkq;
+          z[k][q] = s * zkp + c * zkq;
+        }
       }
       __syncthreads();
     }

@@ -143,8 +143,14 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict_
   }
   __shared__ __align__(16) OzSliceTile tile;
   double t[16];
+  // source row of k0 by one division, of the following 15 entries by counting (the gather wraps at multiples of kin)
+  int rem = k0 % rows.kin, quo = k0 / rows.kin;
 #pragma unroll
-  for (int e = 0; e < 16; ++e) t[e] = (c < MN && k0 + e < K) ? P[oz_src_row(k0 + e, rows) * ld + c] * inv : 0.0;  // |t| <= 0.5
+  for (int e = 0; e < 16; ++e) {
+    const int64_t row = (int64_t)rem * rows.kmul + quo + rows.koff;
+    t[e] = (c < MN && k0 + e < K) ? P[row * ld + c] * inv : 0.0;  // |t| <= 0.5
+    if (++rem == rows.kin) { rem = 0; ++quo; }
+  }
   uint4 dig[kOzMaxSlices];
   oz_digits16([&t](int e) { return t[e]; }, dig);
   oz_tile_put(tile, tx, ty, dig);

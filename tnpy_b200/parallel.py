@@ -76,3 +76,40 @@ def assign_realisations(n_realisations: int, world: int, rank: int) -> List[int]
     if not 0 <= rank < world:
         raise ValueError(f"rank {rank} outside world of {world}")
     return list(range(rank, n_realisations, world))
+
+
+# ---------------------------------------------------------------------------------------------------
+# chi-sharded local solve (the eigensolve of one DMRG site over the GPUs of a box)
+# ---------------------------------------------------------------------------------------------------
+def make_comm(group=None):
+    """The library's own NCCL communicator for this process (``tnpy_comm_*``), created on the current CUDA device
+    from an initialised ``torch.distributed`` group; the 128-byte NCCL id travels by an object broadcast, so the
+    group's backend can be gloo or nccl."""
+    from tnpy_b200 import _cuda
+
+    return _cuda.Comm.from_torch_distributed(group)
+
+
+def sharded_eig_lowest(comm, L, W, R, psi, tol: float = 1e-8, flags: int = 0, image: bool = False, **opts):
+    """Lowest eigenpair of H_eff(L, W, R) with the bra rows of the left bond split evenly over ``comm``'s ranks.
+
+    Every rank passes the *full* device tensors it holds (L (l, wl, l), psi (l, d, r) as start vector; W and R are
+    needed in full anyway); this helper cuts out the rank's row block, runs ``tnpy_eig_lowest_rows`` -- the whole
+    Lanczos iteration on the devices, one all-gather of the current vector and a few all-reduces of <= 64 doubles per
+    step over NVLink -- and returns ``(stats, psi_rows, image_rows)`` with this rank's rows of the eigenvector (and of
+    H_eff psi when ``image``).  Callers that keep their data sharded call ``_cuda.eig_lowest_rows`` directly."""
+    import torch
+
+    from tnpy_b200 import _cuda
+
+    l = psi.shape[0]
+    if l % comm.world:
+        raise ValueError(f"left bond {l} does not split evenly over {comm.world} ranks")
+    lo, hi = row_block(l, comm.world, comm.rank)
+    if hi - lo != l // comm.world or lo != comm.rank * (l // comm.world):
+        raise ValueError("row blocks must be equal (left bond a multiple of 2 x world)")
+    L_rows = L[:, :, lo:hi].contiguous()
+    psi_rows = psi[lo:hi].contiguous().clone()
+    image_rows = torch.empty_like(psi_rows) if image else None
+    stats = _cuda.eig_lowest_rows(comm, L_rows, W, R, psi_rows, l, lo, tol=tol, flags=flags, image_rows=image_rows, **opts)
+    return stats, psi_rows, image_rows
