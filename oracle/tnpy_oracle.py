@@ -259,6 +259,24 @@ def mps_expectation(mps: Sequence[np.ndarray], mpo: Sequence[np.ndarray]) -> flo
     return float(e[0, 0, 0])
 
 
+def mps_sz_profile(mps: Sequence[np.ndarray]) -> Tuple[np.ndarray, float]:
+    """(<Sz_i> / <psi|psi> for every site, <psi|psi>) of an 'lpr' spin-1/2 MPS: left / right overlap environments
+    (the measurement matrix_product_state.py:447-453 makes through quimb, specialised to one-site operators)."""
+    n = len(mps)
+    a3 = [_as3(a, i, n) for i, a in enumerate(mps)]
+    left = [np.ones((1, 1))]
+    for a in a3:
+        left.append(np.einsum("lm,lpr,mps->rs", left[-1], a, a, optimize=True))
+    right = [np.ones((1, 1))] * (n + 1)
+    for i in range(n - 1, -1, -1):
+        right[i] = np.einsum("rs,lpr,mps->lm", right[i + 1], a3[i], a3[i], optimize=True)
+    sz = np.diag([0.5, -0.5])
+    norm2 = float(left[-1][0, 0])
+    prof = [float(np.einsum("lm,lpr,pq,mqs,rs->", left[i], a3[i], sz, a3[i], right[i + 1], optimize=True)) / norm2
+            for i in range(n)]
+    return np.array(prof), norm2
+
+
 def split_tensor(mps: List[np.ndarray], site: int, direction: int) -> np.ndarray:
     """matrix_product_state.py:187-225 + linalg.py:9-23 -- thin SVD with cutoff = current bond
     (never truncates), A[site] <- U or Vt, neighbour absorbs diag(s) Vt / U diag(s).

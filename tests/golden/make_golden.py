@@ -75,23 +75,6 @@ def dmrg_case(mpo, n, chi, seed):
     return out
 
 
-def sz_profile(mps):
-    """<Sz_i> / <psi|psi> for every site of an 'lpr' MPS (left / right overlap environments)."""
-    n = len(mps)
-    a3 = [oracle._as3(a, i, n) for i, a in enumerate(mps)]
-    left = [np.ones((1, 1))]
-    for a in a3:
-        left.append(np.einsum("lm,lpr,mps->rs", left[-1], a, a, optimize=True))
-    right = [np.ones((1, 1))] * (n + 1)
-    for i in range(n - 1, -1, -1):
-        right[i] = np.einsum("rs,lpr,mps->lm", right[i + 1], a3[i], a3[i], optimize=True)
-    sz = np.diag([0.5, -0.5])
-    norm2 = float(left[-1][0, 0])
-    prof = [float(np.einsum("lm,lpr,pq,mqs,rs->", left[i], a3[i], sz, a3[i], right[i + 1], optimize=True)) / norm2
-            for i in range(n)]
-    return np.array(prof), norm2
-
-
 def config2_case(n=100, chi=256, tol=1e-12, sweeps=4, seed=0):
     mpo = oracle.thirring_mpo(n, 0.5, 1.0, 100.0, 0)
     f = oracle.FiniteDMRG(mpo, chi, mps=oracle.random_mps(n, chi, 2, seed=seed))
@@ -101,7 +84,7 @@ def config2_case(n=100, chi=256, tol=1e-12, sweeps=4, seed=0):
         energies.append(f.sweep(oracle.RIGHTWARD if k % 2 == 0 else oracle.LEFTWARD, tol=tol))
         matvecs.append(f.n_matvec - m0)
         print("config2 sweep", k + 1, energies[-1], matvecs[-1], flush=True)
-    prof, norm2 = sz_profile(f.mps)
+    prof, norm2 = oracle.mps_sz_profile(f.mps)
     out = {"energies": np.array(energies), "matvecs": np.array(matvecs), "n": np.array(n), "chi": np.array(chi),
            "tol": np.array(tol), "seed": np.array(seed), "delta": np.array(0.5), "ma": np.array(1.0),
            "penalty": np.array(100.0), "s_target": np.array(0), "sz_profile": prof, "norm2": np.array(norm2)}

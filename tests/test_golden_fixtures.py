@@ -112,3 +112,50 @@ def test_gpu_baseline_config1_matches_fixture():
     for k in range(2, min(len(energies), len(golden))):
         assert abs(energies[k] - golden[k]) <= 1e-10 * abs(golden[k]), (k, energies, golden)
     assert all(b <= a + 1e-9 for a, b in zip(energies, energies[1:]))  # monotone within the solver tolerance
+
+
+def test_config2_fixture_is_self_consistent():
+    """BASELINE.json configs[1] fixture (Thirring n=100 chi=256, the script's penalty 100): the penalty pins the
+    total S^z at the target 0, the energy is converged to 1e-12 after the second sweep, spectra are sorted and the
+    stored norm is what the un-normalised perturbation step leaves (|1 + 1e-5 E| per local update)."""
+    z = load("config2_thirring_n100_chi256.npz")
+    e = z["energies"]
+    assert len(e) == 4 and abs(e[3] - e[2]) < 1e-11 and abs(e[2] - e[1]) < 1e-11 and e[1] <= e[0]
+    assert abs(z["sz_profile"].sum()) < 1e-10 and np.all(np.abs(z["sz_profile"]) <= 0.5)
+    assert 0.99 < float(z["norm2"]) < 1.0
+    n = int(z["n"])
+    for bond in range(n - 1):
+        s = z[f"spectrum_{bond}"]
+        assert np.all(s[:-1] >= s[1:] - 1e-15) and len(s) == min(2 ** (bond + 1), 256, 2 ** (n - 1 - bond))
+
+
+@pytest.mark.gpu
+def test_gpu_baseline_config2_matches_fixture():
+    """BASELINE.json configs[1]: Thirring n=100 chi=256 with scripts/thirring_fdmrg.py's parameters (delta 0.5, ma 1,
+    penalty 100, s_target 0), same initial MPS as the oracle run that made the fixture, four sweeps with every local
+    solve converged to 1e-12 ||A|| on both sides (the penalty makes ||A|| ~ 2e3: at the script's 1e-8 two different
+    eigensolvers are 1e-5 apart per local solve and their trajectories cannot be compared).  Energy of every sweep to
+    1e-10 relative, every bond spectrum to 1e-9, the <Sz_i> profile to 1e-8, the state's squared norm to 1e-9."""
+    pytest.importorskip("torch")
+    from tnpy_b200.finite_dmrg import FiniteDMRG
+    from tnpy_b200.matrix_product_state import Direction, MatrixProductState
+    from tnpy_b200.model import Thirring
+
+    z = load("config2_thirring_n100_chi256.npz")
+    n, chi, tol = int(z["n"]), int(z["chi"]), float(z["tol"])
+    model = Thirring(n=n, delta=float(z["delta"]), ma=float(z["ma"]), penalty=float(z["penalty"]), s_target=int(z["s_target"]))
+    init = MatrixProductState(oracle.random_mps(n, chi, 2, seed=int(z["seed"])))
+    f = FiniteDMRG(model.mpo, bond_dim=chi, mps=init, compute_variance=False)
+    energies, matvecs = [], []
+    for k in range(len(z["energies"])):
+        energies.append(f.sweep(Direction.RIGHTWARD if k % 2 == 0 else Direction.LEFTWARD, tol=tol, maxiter=20000))
+        matvecs.append(sum(s.get("n_matvec", 0) for s in f.solver_stats))
+        assert all(s.get("converged", True) for s in f.solver_stats), (k, [s for s in f.solver_stats if not s.get("converged", True)][:3])
+    for k, (a, b) in enumerate(zip(energies, z["energies"])):
+        assert abs(a - b) <= 1e-10 * abs(b), (k, energies, list(z["energies"]), matvecs)
+    sv = f.bond_singular_values
+    for bond in range(n - 1):
+        assert np.abs(sv[bond] - z[f"spectrum_{bond}"]).max() < 1e-9, bond
+    prof, norm2 = oracle.mps_sz_profile(f.mps.arrays)
+    assert np.abs(prof - z["sz_profile"]).max() < 1e-8
+    assert abs(norm2 - float(z["norm2"])) < 1e-9
