@@ -41,8 +41,11 @@ static RedScratch red_scratch(cudaStream_t stream) {
   return s;
 }
 
+// Grid of the streaming kernels: one double2 per thread and trip for short vectors (a chi = 60 site has 7200
+// entries: with eight per thread only four CTAs worked and multi_dot took 23 us), up to eight per thread for long
+// ones, capped at eight CTAs per SM.
 static int red_blocks(int64_t n) {
-  int64_t b = (n + (int64_t)kRedThreads * 8 - 1) / ((int64_t)kRedThreads * 8);
+  int64_t b = (n + (int64_t)kRedThreads * 2 - 1) / ((int64_t)kRedThreads * 2);
   const int cap = sm_count() * 8 < kMaxRedBlocks ? sm_count() * 8 : kMaxRedBlocks;
   if (b > cap) b = cap;
   if (b < 1) b = 1;

@@ -350,10 +350,16 @@ static int eig_lowest_impl(const tnpy_comm* comm, const double* L, const double*
   // derail cold-sweep solves: spurious Ritz values of order 1e3 and 1000 wasted matvecs at 5 of 34 sites of
   // XXZ n=40 chi=512 (profiles/r01_sweep_trace_cold_chi512_*.jsonl).
   const double eta = 1.0;
-  // The Ritz problem (a Jacobi eigensolve of T in one CTA, ~0.1 ms) and the host read-back are only needed when
-  // somebody looks at the result: on restart steps, at the matvec limit, and every `stride` steps, stride = 1
-  // within two decades of the threshold, 2 within four, 3 beyond (a local solve can overshoot by at most two
-  // matvecs; the stopping rule itself is unchanged).  At chi <= 1024 that is 15-25 % of a Lanczos step.
+  // The Ritz problem (a Jacobi eigensolve of T in one CTA, 0.05-0.2 ms) and the host read-back are only needed when
+  // somebody looks at the result: on restart steps, at the matvec limit, and every `stride` steps.  The stride comes
+  // from the residual history: Lanczos residuals fall geometrically, so the two last looks give a rate and with it
+  // the number of steps left to the threshold; the next look happens after half of those, at most `stride_cap` steps
+  // on (3 where a matvec costs milliseconds -- an overshoot step is then dearer than a look -- 8 for small sites,
+  // where the Ritz solve is the dearest kernel of a step: 38 % of the device time of XXZ n=100 chi=60 before this).
+  // The stopping rule itself is unchanged; a local solve can overshoot by at most stride_cap - 1 matvecs.
+  const int stride_cap = n_full >= (1 << 20) ? 3 : (n_full >= (1 << 16) ? 4 : 8);
+  double last_resid = 0.0;
+  int last_look_matvec = 0;
   int since_check = 0, stride = 1;
   while (true) {
     double* vj = V + (int64_t)j * ldv;
@@ -417,8 +423,16 @@ static int eig_lowest_impl(const tnpy_comm* comm, const double* L, const double*
       if (plan.bound) TNPY_CUDA_OK(cudaMemsetAsync(plan.bound, 0, sizeof(double), stream));
     }
     {
-      const double thr = tol * hst[ST_ANORM];
-      stride = hst[ST_RESID] > 1e4 * thr ? 3 : (hst[ST_RESID] > 1e2 * thr ? 2 : 1);
+      const double thr = tol * hst[ST_ANORM], res = hst[ST_RESID];
+      int guess = res > 1e4 * thr ? 3 : (res > 1e2 * thr ? 2 : 1);  // no history yet: by the distance alone
+      if (last_resid > 0.0 && res > 0.0 && res < last_resid && thr > 0.0 && res > thr) {
+        const double rate = log(last_resid / res) / (double)(n_matvec - last_look_matvec);  // decades (e-folds) per step
+        const double left = log(res / thr) / rate;
+        guess = left < 2.0 ? 1 : (int)(0.5 * left);
+      }
+      stride = guess < 1 ? 1 : (guess > stride_cap ? stride_cap : guess);
+      last_resid = res;
+      last_look_matvec = n_matvec;
     }
     done = hst[ST_DONE] != 0.0 || !(hst[ST_BETA] > 0.0) || m >= n_full;
     if (done || n_matvec >= max_matvec) {

@@ -64,7 +64,7 @@ class FiniteDMRG:
             mps = MatrixProductState.random(n=self.n_sites, bond_dim=self.bond_dim, phys_dim=self.phys_dim, seed=seed)
         # canonicalize=True right-canonicalises a user-supplied MPS on the device first; the reference
         # (and the default here) trusts the caller, as MatrixProductState.random is right-canonical
-        # split="qr" (default): bonds >= 64 are orthogonalised by the verified Cholesky-QR split and the bond's
+        # split="qr" (default): bonds >= 16 are orthogonalised by the verified Cholesky-QR split and the bond's
         # small SVD is deferred until `bond_singular_values` is read; split="svd": one Jacobi SVD per split,
         # the reference's literal gauge (matrix_product_state.py:187-225).  Energies, the state and the bond
         # spectra are the same either way (the two differ by an orthogonal gauge on each bond).

@@ -271,7 +271,7 @@ def _verified_qr(mat, t_first: bool):
     return None, None, False
 
 
-def _split_on_device(a, nb, direction: Direction, mode: str = "svd", qr_min_bond: int = 64):
+def _split_on_device(a, nb, direction: Direction, mode: str = "svd", qr_min_bond: int = 16):
     """Device tensors in, device tensors out: (new site tensor, new neighbour, bond spectrum).
 
     ``mode="svd"``: the reference's split (linalg.py:9-23 with cutoff = current bond), spectrum = s.
@@ -435,7 +435,7 @@ class Environment:
 
     def __init__(self, mpo: MatrixProductOperator, mps, build_left: bool = True, use_identity_channels: bool = True,
                  share_state_with: Optional["Environment"] = None, canonicalize: bool = False,
-                 split: str = "qr", qr_min_bond: int = 64):
+                 split: str = "qr", qr_min_bond: int = 16):
         """``mps`` is a :class:`MatrixProductState` (host, as in the reference) or a list of
         three-leg (l, d, r) float64 CUDA tensors (device-born synthetic states for benchmarks).
         ``share_state_with``: a second environment over the *same* MPS (ShiftInvertDMRG's H^2
