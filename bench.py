@@ -56,8 +56,9 @@ class ClockSampler:
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index=0):
+    def __init__(self, index=0, period_ms=200):
         self.index = index
+        self.period_ms = period_ms
         self.proc = None
         self.path = None
 
@@ -66,7 +67,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", str(self.period_ms), "-i", str(self.index)],
                 stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -392,6 +393,42 @@ def run_single(args):
     oz_g = [oz_kernel_ms(*sh) for sh in shapes_general]
     oz_d = [oz_kernel_ms(*sh) for sh in shapes_direct]
     pops = lambda shapes, ms: sum(36 * 2.0 * m_ * n_ * k_ for m_, n_, k_ in shapes) / (sum(ms) * 1e-3) / 1e15  # noqa: E731
+
+    # the same kernel back to back for ~1.5 s with the SM clock sampled: under this load the board sits at its power
+    # cap and the clock well below 1965 MHz, so the fraction of the MMA peak *at the clock the kernel is given* is
+    # the number that says how well the kernel uses the pipe
+    def oz_sustained(m_, n_, k_, seconds=1.5):
+        a_ = torch.randn((k_, m_), dtype=torch.float64, device="cuda")
+        b_ = torch.randn((k_, n_), dtype=torch.float64, device="cuda")
+        c_ = torch.empty((m_, n_), dtype=torch.float64, device="cuda")
+        _cuda.ozaki_gemm_tn(a_, b_, out=c_, slices=8, phase=1)
+        mm = lambda: _cuda.ozaki_gemm_tn(a_, b_, out=c_, slices=8, phase=2)  # noqa: E731
+        for _ in range(50):
+            mm()
+        sync()
+        smp = ClockSampler(0, period_ms=100)
+        smp.start()
+        time.sleep(0.15)
+        t0, launches_ = time.perf_counter(), 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        while time.perf_counter() - t0 < seconds:
+            for _ in range(50):
+                mm()
+            launches_ += 50
+            sync()
+        e1.record()
+        sync()
+        clk = smp.stop()
+        ms_ = e0.elapsed_time(e1) / launches_
+        rate = 36 * 2.0 * m_ * n_ * k_ / (ms_ * 1e-3) / 1e15
+        mhz = clk.get("sm_mhz") or 1965.0
+        return {"shape_mnk": [m_, n_, k_], "ms_per_launch": ms_, "launches": launches_, "achieved": rate, "sm_mhz_median": mhz,
+                "power_w_max": clk.get("power_w_max"), "reasons": clk.get("reasons"),
+                "peak_at_that_clock": INT8_PEAK_POPS * mhz / 1965.0, "frac_at_that_clock": rate / (INT8_PEAK_POPS * mhz / 1965.0),
+                "frac_of_1965mhz_peak": rate / INT8_PEAK_POPS}
+
+    oz_sus = oz_sustained(*shapes_direct[0])
     # (b) gemm_tn_dmma on the two GEMM shapes of the FP64 chain
     t1 = torch.empty((d * r, wl * l), dtype=torch.float64, device="cuda")
     t2 = torch.randn((r * wr, d * l), dtype=torch.float64, device="cuda")
@@ -437,14 +474,18 @@ def run_single(args):
     roofline_oz = {
         "bound": "tensor", "achieved": pops(shapes_general, oz_g), "peak": INT8_PEAK_POPS, "unit": "POP/s (int8)",
         "frac": pops(shapes_general, oz_g) / INT8_PEAK_POPS,
-        "traffic": None,
+        "traffic": 1.63e9,  # dram read + write per launch, mean of the two shapes, ncu --set full (profiles/r01_oz2_mma_kernel_ncu_full_raw.csv)
+        "algorithmic_bytes_per_launch": 8.0 * (shapes_general[0][0] + shapes_general[0][1]) * shapes_general[0][2] + 8.0 * shapes_general[0][0] * shapes_general[0][1],
         "kernel": "oz2_mma_kernel<8> (tcgen05.mma.cta_group::2.kind::i8; 2 launches per matvec, operands already sliced)",
         "ms_gemm1": oz_g[0], "ms_gemm3": oz_g[1], "shapes_mnk": shapes_general,
         "fp64_equivalent_tflops": gemm_flops / (sum(oz_g) * 1e-3) / 1e12,
         "algorithmic_ops": "36 slice pairs x 2 M N K int8 multiply-adds per launch (8 slices; DESIGN 2.2)",
         "peak_source": "ncu sm__ops_path_tensor_op_utcimma_src_int8 peak_sustained at 1965 MHz (profiles/r01_oz2_mma_kernel_ncu_full_raw.csv)",
         "direct_path_shapes": {"shapes_mnk": shapes_direct, "ms": oz_d, "achieved": pops(shapes_direct, oz_d),
-                               "frac": pops(shapes_direct, oz_d) / INT8_PEAK_POPS},
+                               "frac": pops(shapes_direct, oz_d) / INT8_PEAK_POPS,
+                               "traffic": 1.64e9,  # ncu --set full: 1.51 GB read + 0.13 GB written per launch (profiles/r02_direct_path_ncu_full_raw.csv)
+                               "algorithmic_bytes_per_launch": 8.0 * (shapes_direct[0][0] + shapes_direct[0][1]) * shapes_direct[0][2] + 16.0 * shapes_direct[0][0] * shapes_direct[0][1]},
+        "sustained_at_measured_clock": oz_sus,
     }
     roofline_dmma = {
         "bound": "tensor", "achieved": gemm_flops / (tg1 + tg3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",

@@ -69,7 +69,28 @@ __global__ void __launch_bounds__(kRedThreads) multi_dot_kernel(const double* __
     double acc[MB];
 #pragma unroll
     for (int j = 0; j < MB; ++j) acc[j] = 0.0;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
+    // two trips per iteration: twice the loads in flight per thread (a single vector pair -- dot, nrm2 -- otherwise
+    // has one 16-byte load per operand outstanding and reached 0.4 of the HBM rate)
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + stride < n2; i += 2 * stride) {
+      const double2 wa = reinterpret_cast<const double2*>(w)[i];
+      const double2 wb = reinterpret_cast<const double2*>(w)[i + stride];
+      double2 va[MB], vb[MB];
+#pragma unroll
+      for (int j = 0; j < MB; ++j) {
+        const bool on = j0 + j < m;
+        va[j] = on ? *reinterpret_cast<const double2*>(V + (int64_t)(j0 + j) * ldv + 2 * i) : make_double2(0.0, 0.0);
+        vb[j] = on ? *reinterpret_cast<const double2*>(V + (int64_t)(j0 + j) * ldv + 2 * (i + stride)) : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int j = 0; j < MB; ++j) {
+        acc[j] = fma(va[j].x, wa.x, acc[j]);
+        acc[j] = fma(va[j].y, wa.y, acc[j]);
+        acc[j] = fma(vb[j].x, wb.x, acc[j]);
+        acc[j] = fma(vb[j].y, wb.y, acc[j]);
+      }
+    }
+    for (; i < n2; i += stride) {
       const double2 wv = reinterpret_cast<const double2*>(w)[i];
 #pragma unroll
       for (int j = 0; j < MB; ++j) {

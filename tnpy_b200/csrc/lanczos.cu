@@ -343,7 +343,7 @@ static int eig_lowest_impl(const tnpy_comm* comm, const double* L, const double*
 
   int j = 0, n_matvec = 0, n_restart = 0;
   int whole_basis_step = 0;  // step whose local Gram-Schmidt set is the whole basis (the first after a restart)
-  double worst_bound = 0.0;
+  double worst_bound = 0.0, anorm_seen = 0.0;
   bool done = false;
   // Daniel-Gragg-Kaufman-Stewart: the second pass is skipped only when ||w'|| >= ||w|| / sqrt 2, i.e.
   // ||w'|| >= ||h|| (||w||^2 = ||h||^2 + ||w'||^2).  A looser, tolerance-tied threshold (1e-3) was measured to
@@ -409,7 +409,10 @@ static int eig_lowest_impl(const tnpy_comm* comm, const double* L, const double*
       TNPY_CUDA_OK(cudaMemcpyAsync(status + ST_BOUND, plan.bound, sizeof(double), cudaMemcpyDeviceToDevice, stream));
     TNPY_CUDA_OK(cudaMemcpyAsync(hst, status, sizeof(double) * ST_SIZE, cudaMemcpyDeviceToHost, stream));
     TNPY_CUDA_OK(cudaStreamSynchronize(stream));
-    if (plan.mode != HEFF_FP64_CHAIN && hst[ST_BOUND] > 0.01 * tol * hst[ST_ANORM]) {
+    // ||A|| for this test: the largest |Ritz value| or Lanczos coefficient seen so far (a lower bound of ||A|| that
+    // is already tight after a few steps; the very first Ritz values of a random start can be near zero)
+    anorm_seen = fmax(anorm_seen, fmax(hst[ST_ANORM], hst[ST_BETA]));
+    if (plan.mode != HEFF_FP64_CHAIN && n_matvec >= 3 && hst[ST_BOUND] > 0.01 * tol * anorm_seen) {
       // the int8 products are no longer safely below the residual threshold: spend the eighth slice, then leave
       // the tcgen05 path altogether (the basis built so far stays valid: its vectors are exact matvecs to within
       // the bound, and T is the explicit projection)
