@@ -169,6 +169,12 @@ int tnpy_env_update_left(const double* L, const double* A, const double* W, doub
 int tnpy_env_update_right(const double* R, const double* A, const double* W, double* Rout,
                           int l, int r, int wl, int wr, int d, int flags, void* workspace,
                           size_t workspace_bytes, void* stream);
+/* Row block of the left update for the chi-sharded sweep: L_rows = L[:, :, row0 : row0 + l_rows] as (l, wl, l_rows), A in
+ * full; Lout_partial (r, wr, r) receives this block's contribution (the sum over the bra index runs over the block
+ * only) -- the ranks' contributions add up to the update (one all-reduce).  Workspace: tnpy_env_workspace_bytes(). */
+int tnpy_env_update_left_rows(const double* L_rows, const double* A, const double* W, double* Lout_partial,
+                              int l, int row0, int l_rows, int r, int wl, int wr, int d, int flags, void* workspace,
+                              size_t workspace_bytes, void* stream);
 
 /* ---- a6: Environment.one_site_full_matrix  (matrix_product_state.py:372-409) ---------------
  * H[(l,p,r),(m,q,s)] = sum_{a,b} L[l,a,m] W[a,b,p,q] R[r,b,s] dense, N = l*d*r <= 4096; H is N x N

@@ -23,6 +23,8 @@ def main():
     ap.add_argument("--realisations", type=int, default=64)
     ap.add_argument("--sweeps", type=int, default=2)
     ap.add_argument("--tol", type=float, default=1e-8)
+    ap.add_argument("--verify", action="store_true",
+                    help="rank 0 also runs 4 realisations at n=16 chi=32 (6 sweeps) on the GPU and on the CPU oracle and reports the largest energy difference")
     args = ap.parse_args()
 
     import torch
@@ -59,6 +61,23 @@ def main():
         dist.destroy_process_group()
     else:
         gathered = [(results, elapsed)]
+    verify = None
+    if rank == 0 and args.verify:
+        from oracle import tnpy_oracle as oracle  # checker only
+        from tnpy_b200.matrix_product_state import MatrixProductState
+
+        worst = 0.0
+        for seed in range(4):
+            model = RandomHeisenberg(n=16, h=args.h, seed=seed)
+            init = oracle.random_mps(16, 32, 2, seed=seed)
+            ref = oracle.FiniteDMRG(model.mpo.arrays, 32, mps=[a.copy() for a in init])
+            gpu = FiniteDMRG(model.mpo, bond_dim=32, mps=MatrixProductState([a.copy() for a in init]), compute_variance=False)
+            e_ref = e_gpu = None
+            for k in range(6):
+                e_ref = ref.sweep(oracle.RIGHTWARD if k % 2 == 0 else oracle.LEFTWARD, tol=1e-12)
+                e_gpu = gpu.sweep(Direction.RIGHTWARD if k % 2 == 0 else Direction.LEFTWARD, tol=1e-12)
+            worst = max(worst, abs(e_gpu - e_ref) / abs(e_ref))
+        verify = {"realisations": 4, "n": 16, "chi": 32, "sweeps": 6, "max_rel_energy_diff_vs_oracle": worst}
     if rank == 0:
         energies = {}
         for res, _ in gathered:
@@ -68,7 +87,7 @@ def main():
             "config": "RandomHeisenberg n=%d chi=%d h=%g, %d realisations on %d GPU(s), %d sweeps each" % (
                 args.n, args.chi, args.h, args.realisations, world, args.sweeps),
             "wall_s": wall, "realisations_per_s": args.realisations / wall,
-            "energies": [energies[s] for s in sorted(energies)],
+            "energies": [energies[s] for s in sorted(energies)], "verify": verify,
         }), flush=True)
 
 

@@ -21,8 +21,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from bench import f_mv, mixed_canonicalize, random_right_canonical_device  # noqa: E402
 from tnpy_b200 import _cuda  # noqa: E402
 from tnpy_b200.finite_dmrg import FiniteDMRG  # noqa: E402
+from tnpy_b200.matrix_product_state import Direction  # noqa: E402
 from tnpy_b200.model import XXZ  # noqa: E402
-from tnpy_b200.parallel import make_comm, sharded_eig_lowest  # noqa: E402
+from tnpy_b200.parallel import make_comm, sharded_eig_lowest, sharded_local_update  # noqa: E402
 
 
 def main():
@@ -33,6 +34,8 @@ def main():
     ap.add_argument("--max-matvec", type=int, default=1000)
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--general", action="store_true", help="do not use the measured identity channels (general chain)")
+    ap.add_argument("--update", action="store_true",
+                    help="time one whole sharded local update (eigensolve + perturbation + split + environment update)")
     args = ap.parse_args()
     import logging
 
@@ -95,6 +98,49 @@ def main():
         out.update(unsharded_theta=ref_stats["theta"], unsharded_n_matvec=ref_stats["n_matvec"],
                    theta_diff=abs(ref_stats["theta"] - stats["theta"]), max_abs_diff_psi_rows=float(diff[0].item()),
                    max_abs_diff_image_rows=float(diff[1].item()))
+    if args.update:
+        lo = l // world
+        L_rows = L[:, :, rank * lo:(rank + 1) * lo].contiguous()
+        psi_rows = psi[rank * lo:(rank + 1) * lo].contiguous().clone()
+        nb = env.device_tensor(site + 1)
+        dist.barrier()
+        upd = sharded_local_update(comm, L_rows, W, R, psi_rows, nb, l, tol=args.tol, flags=flags, max_matvec=args.max_matvec)
+        ph = torch.tensor([upd["phase_s"][k] for k in ("eigensolve", "perturb", "gather_and_split", "env_update")],
+                          dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ph, op=dist.ReduceOp.MAX)
+        out["local_update"] = {"phase_s_max_over_ranks": dict(zip(("eigensolve", "perturb", "gather_and_split", "env_update"),
+                                                                  [float(v) for v in ph])),
+                               "total_s": float(ph.sum()), "n_matvec": upd["stats"]["n_matvec"], "theta": upd["stats"]["theta"]}
+        if args.check:
+            # gauge-independent checks of the three post-solve steps (the split's Q is a sensitive function of psi, so
+            # it is not compared with another run's Q): the new site tensor is left-orthonormal, site x neighbour
+            # still is psi x old neighbour, and the summed row-block environment update equals the unsharded update
+            # of the *same* site tensor
+            q = upd["site_tensor"].reshape(l * d, r)
+            gram = _cuda.gemm_tn(q, q)
+            orth = float((gram - torch.eye(r, dtype=torch.float64, device="cuda")).abs().max())
+            psi_full = torch.empty((l, d, r), dtype=torch.float64, device="cuda")
+            comm.allgather(psi_rows.contiguous(), psi_full)
+            r2 = nb.shape[2]
+            two_new = upd["site_tensor"].reshape(l * d, r) @ upd["neighbour"].reshape(r, d * r2)
+            two_old = psi_full.reshape(l * d, r) @ nb.reshape(r, d * r2)
+            state = float((two_new - two_old).abs().max() / two_old.abs().max())
+            ref_next = _cuda.env_update_left(L, upd["site_tensor"], W, flags=flags & _cuda.LEFT_IDENTITY)
+            ro = r // world
+            d_env = float((upd["next_left_rows"] - ref_next[:, :, rank * ro:(rank + 1) * ro]).abs().max() / ref_next.abs().max())
+            t0 = time.perf_counter()
+            e_ref = dmrg._solve_on_device(site, args.tol, maxiter=args.max_matvec)
+            dmrg.perturb_wave_function(site)
+            env.split_tensor(site, Direction.RIGHTWARD)
+            env.update(site, Direction.RIGHTWARD)
+            torch.cuda.synchronize()
+            out["local_update"]["unsharded_total_s"] = time.perf_counter() - t0
+            diff2 = torch.tensor([d_env, orth, state, abs(e_ref - upd["stats"]["theta"])], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(diff2, op=dist.ReduceOp.MAX)
+            out["local_update"].update(max_rel_diff_next_left_env=float(diff2[0]), site_tensor_orthogonality_defect=float(diff2[1]),
+                                       two_site_state_rel_diff=float(diff2[2]), theta_diff=float(diff2[3]))
     if rank == 0:
         print(json.dumps(out), flush=True)
     comm.close()

@@ -193,6 +193,29 @@ def test_reductions_are_deterministic(cu):
     assert len(vals) == 1
 
 
+def test_two_streams_keep_their_own_reduction_scratch(cu):
+    """The two-stage reductions keep partial sums and a ticket counter per (device, stream): kernels enqueued on two
+    streams at once give bit-identical results to the same calls made one after the other (one global
+    scratch let concurrent streams corrupt each other's dot products)."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    n, m = 1 << 22, 8
+    V1 = torch.randn((m, n), generator=g, dtype=torch.float64, device="cuda")
+    V2 = torch.randn((m, n), generator=g, dtype=torch.float64, device="cuda")
+    w1 = torch.randn(n, generator=g, dtype=torch.float64, device="cuda")
+    w2 = torch.randn(n, generator=g, dtype=torch.float64, device="cuda")
+    want1, want2 = cu.multi_dot(V1, w1).clone(), cu.multi_dot(V2, w2).clone()
+    nrm1, nrm2 = cu.nrm2(w1).clone(), cu.nrm2(w2).clone()
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for _ in range(10):
+        with torch.cuda.stream(s1):
+            a, na = cu.multi_dot(V1, w1), cu.nrm2(w1)
+        with torch.cuda.stream(s2):
+            b, nb = cu.multi_dot(V2, w2), cu.nrm2(w2)
+        torch.cuda.synchronize()
+        assert torch.equal(a, want1) and torch.equal(b, want2) and torch.equal(na, nrm1) and torch.equal(nb, nrm2)
+
+
 # ------------------------------------------------------------------------------------ eigensolver
 def canonical_problem(n_sites, chi, site, seed=0, model="xxz"):
     # penalty 1.0: with the script's 100.0 a *random* environment gives a relative gap of ~5e-7

@@ -23,7 +23,7 @@ def run_sharded(world, chi, extra=()):
 
 
 @pytest.mark.parametrize("world", [1, 2])
-@pytest.mark.parametrize("chi,extra", [(64, ()), (64, ("--general",)), (256, ())])
+@pytest.mark.parametrize("chi,extra", [(64, ()), (64, ("--general",)), (256, ("--update",))])
 def test_sharded_solve_matches_unsharded(world, chi, extra):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
@@ -32,3 +32,10 @@ def test_sharded_solve_matches_unsharded(world, chi, extra):
     assert out["theta_diff"] <= 1e-10 * abs(out["unsharded_theta"])
     assert out["max_abs_diff_psi_rows"] < 1e-7 and out["max_abs_diff_image_rows"] < 1e-6
     assert out["resid"] <= 1e-10 * 30
+    if "--update" in extra:
+        # the whole sharded local update (eigensolve + perturbation + gathered split + row-block environment update
+        # summed over the ranks) against the product's own unsharded sweep step
+        upd = out["local_update"]
+        assert upd["theta_diff"] <= 1e-10 * abs(out["unsharded_theta"])
+        assert upd["max_rel_diff_next_left_env"] < 1e-12
+        assert upd["site_tensor_orthogonality_defect"] < 1e-12 and upd["two_site_state_rel_diff"] < 1e-12

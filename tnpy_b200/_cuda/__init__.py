@@ -56,6 +56,7 @@ SIGNATURES = {
     "tnpy_env_workspace_bytes": (c_size_t, [c_int] * 5),
     "tnpy_env_update_left": (c_int, [_PD, _PD, _PD, _PD] + [c_int] * 6 + [c_void_p, c_size_t, c_void_p]),
     "tnpy_env_update_right": (c_int, [_PD, _PD, _PD, _PD] + [c_int] * 6 + [c_void_p, c_size_t, c_void_p]),
+    "tnpy_env_update_left_rows": (c_int, [_PD, _PD, _PD, _PD] + [c_int] * 8 + [c_void_p, c_size_t, c_void_p]),
     "tnpy_heff_dense_workspace_bytes": (c_size_t, [c_int] * 5),
     "tnpy_heff_dense": (c_int, [_PD, _PD, _PD, _PD] + [c_int] * 5 + [c_void_p, c_size_t, c_void_p]),
     "tnpy_dot": (c_int, [_PD, _PD, c_int64, _PD, c_void_p]),
@@ -397,6 +398,24 @@ def env_update_left(L, A, W, out=None, flags: int = 0):
     rc = lib.tnpy_env_update_left(_ptr(L), _ptr(A), _ptr(W), _ptr(out), l, r, wl, wr, d, int(flags), _ptr(ws), nbytes,
                                   _stream())
     check(rc, "tnpy_env_update_left")
+    return out
+
+
+def env_update_left_rows(L_rows, A, W, row0: int, out=None, flags: int = 0):
+    """One row block's contribution to update_left: L_rows (l, wl, l_rows) = L[:, :, row0 : row0 + l_rows], A full."""
+    import torch
+
+    _need_cuda(L_rows, A, W, out)
+    l, r, wl, wr, d = _dims(A.shape, W.shape)
+    lo = 1 if L_rows is None else L_rows.shape[2]
+    if out is None:
+        out = torch.empty((r, wr, r), dtype=torch.float64, device=A.device)
+    lib = load()
+    nbytes = lib.tnpy_env_workspace_bytes(l, r, wl, wr, d)
+    ws = _scratch.get(nbytes)
+    rc = lib.tnpy_env_update_left_rows(_ptr(L_rows), _ptr(A), _ptr(W), _ptr(out), l, int(row0), lo, r, wl, wr, d, int(flags),
+                                       _ptr(ws), nbytes, _stream())
+    check(rc, "tnpy_env_update_left_rows")
     return out
 
 

@@ -468,37 +468,47 @@ int heff_apply(const double* L, const double* W, const double* R, const double* 
   return heff_apply_rows(L, W, R, x, y, l, l, 0, r, wl, wr, d, flags, ws, stream);
 }
 
-int env_update_left(const double* L, const double* A, const double* W, double* Lout, int l, int r, int wl, int wr,
-                    int d, int flags, Workspace& ws, cudaStream_t stream) {
+// lo bra rows of L starting at row0 (lo == l, row0 == 0: the whole update).  With a row block the result is this
+// block's *contribution* to Lout (the sum over the bra index m runs over the block only): the row-sharded sweep sums
+// the contributions of the ranks (one all-reduce) -- A is needed in full (ket index), L only by rows.
+int env_update_left_rows(const double* L, const double* A, const double* W, double* Lout, int l, int lo, int row0, int r,
+                         int wl, int wr, int d, int flags, Workspace& ws, cudaStream_t stream) {
   TNPY_TRY(check_dims(l, r, wl, wr, d));
   TNPY_CHECK_ARG(A && W && Lout, "null pointer");
+  TNPY_CHECK_ARG(lo > 0 && row0 >= 0 && row0 + lo <= l, "row block outside the left bond");
   TNPY_CHECK_ARG(L || (l == 1 && wl == 1), "L may be NULL only for unit left bond");
   if (!L) L = device_one();
-  double* t1 = ws.take<double>((size_t)wl * l * d * r);
-  double* t2 = ws.take<double>((size_t)l * d * wr * r);
+  double* t1 = ws.take<double>((size_t)wl * lo * d * r);
+  double* t2 = ws.take<double>((size_t)lo * d * wr * r);
   if (!t1 || !t2) {
     set_error("env_update_left: workspace too small");
     return TNPY_EWORKSPACE;
   }
   const int algo = TNPY_GEMM_AUTO;
-  // T1[a, m, p, r] = sum_l L[l, (a m)] A[l, (p r)];  identity channel a = 0: T1[0] = A
+  const double* A_rows = A + (int64_t)row0 * d * r;
+  // T1[a, m, p, r] = sum_l L[l, (a m)] A[l, (p r)];  identity channel a = 0: T1[0, m] = A[row0 + m]
   if ((flags & TNPY_LEFT_IDENTITY) && wl > 1) {
-    TNPY_CUDA_OK(cudaMemcpyAsync(t1, A, sizeof(double) * (size_t)l * d * r, cudaMemcpyDeviceToDevice, stream));
+    TNPY_CUDA_OK(cudaMemcpyAsync(t1, A_rows, sizeof(double) * (size_t)lo * d * r, cudaMemcpyDeviceToDevice, stream));
     Workspace scratch = ws;
-    TNPY_TRY(chain_gemm(L + l, (int64_t)wl * l, A, (int64_t)d * r, plain_out(t1 + (size_t)l * d * r, (int64_t)d * r, (wl - 1) * l),
-                        (wl - 1) * l, d * r, l, 0, algo, scratch, stream));
+    TNPY_TRY(chain_gemm(L + lo, (int64_t)wl * lo, A, (int64_t)d * r, plain_out(t1 + (size_t)lo * d * r, (int64_t)d * r, (wl - 1) * lo),
+                        (wl - 1) * lo, d * r, l, 0, algo, scratch, stream));
   } else {
     Workspace scratch = ws;
-    TNPY_TRY(chain_gemm(L, (int64_t)wl * l, A, (int64_t)d * r, plain_out(t1, (int64_t)d * r, wl * l), wl * l, d * r, l, 0,
+    TNPY_TRY(chain_gemm(L, (int64_t)wl * lo, A, (int64_t)d * r, plain_out(t1, (int64_t)d * r, wl * lo), wl * lo, d * r, l, 0,
                         algo, scratch, stream));
   }
   // T2[m, q, b, r] = sum_{a p} W[a, b, p, q] T1[a, m, p, r]          (u=a, u'=b, v=p, v'=q)
-  TNPY_TRY(wmix(t1, t2, W, wl, wr, d, d, l, r, wr * d * d, d * d, d, 1, stream));
+  TNPY_TRY(wmix(t1, t2, W, wl, wr, d, d, lo, r, wr * d * d, d * d, d, 1, stream));
   // Lout[r, b, s] = sum_{m q} T2[(m q), (b r)] A[(m q), s]             rows (b r) -> (r b)
   GemmOut out{Lout, (int64_t)wr * r, (int64_t)r, r};
   Workspace scratch = ws;
-  TNPY_TRY(chain_gemm(t2, (int64_t)wr * r, A, (int64_t)r, out, wr * r, r, l * d, 0, algo, scratch, stream));
+  TNPY_TRY(chain_gemm(t2, (int64_t)wr * r, A_rows, (int64_t)r, out, wr * r, r, lo * d, 0, algo, scratch, stream));
   return TNPY_OK;
+}
+
+int env_update_left(const double* L, const double* A, const double* W, double* Lout, int l, int r, int wl, int wr,
+                    int d, int flags, Workspace& ws, cudaStream_t stream) {
+  return env_update_left_rows(L, A, W, Lout, l, l, 0, r, wl, wr, d, flags, ws, stream);
 }
 
 int env_update_right(const double* R, const double* A, const double* W, double* Rout, int l, int r, int wl, int wr,
@@ -681,6 +691,14 @@ extern "C" int tnpy_env_update_left(const double* L, const double* A, const doub
                                     void* stream) {
   Workspace ws(workspace, workspace_bytes);
   return env_update_left(L, A, W, Lout, l, r, wl, wr, d, flags, ws, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int tnpy_env_update_left_rows(const double* L_rows, const double* A, const double* W, double* Lout_partial, int l,
+                                         int row0, int l_rows, int r, int wl, int wr, int d, int flags, void* workspace,
+                                         size_t workspace_bytes, void* stream) {
+  Workspace ws(workspace, workspace_bytes);
+  return env_update_left_rows(L_rows, A, W, Lout_partial, l, l_rows, row0, r, wl, wr, d, flags, ws,
+                              static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int tnpy_env_update_right(const double* R, const double* A, const double* W, double* Rout, int l, int r,

@@ -113,3 +113,62 @@ def sharded_eig_lowest(comm, L, W, R, psi, tol: float = 1e-8, flags: int = 0, im
     image_rows = torch.empty_like(psi_rows) if image else None
     stats = _cuda.eig_lowest_rows(comm, L_rows, W, R, psi_rows, l, lo, tol=tol, flags=flags, image_rows=image_rows, **opts)
     return stats, psi_rows, image_rows
+
+
+def sharded_local_update(comm, L_rows, W, R, psi_rows, neighbour, l: int, tol: float = 1e-8, flags: int = 0,
+                         alpha: float = 1e-5, **opts):
+    """One *rightward* local update of a row-sharded site (finite_dmrg.py:164-170 for one site, over ``comm``'s GPUs):
+
+      1. eigensolve            ``tnpy_eig_lowest_rows`` on this rank's rows (collective; H_eff psi comes with it)
+      2. perturbation          psi += alpha * H_eff psi on the rows (no renormalisation, as in the reference)
+      3. split                 all-gather psi (the one vector-sized exchange), then the verified Cholesky-QR split of
+                               the full (l d) x r matrix, replicated on every rank (deterministic: same input, same
+                               kernels), and the absorb into the replicated neighbour
+      4. environment update    every rank contracts *its* bra rows of L with the new site tensor
+                               (``tnpy_env_update_left_rows``), the contributions are summed by one all-reduce and
+                               the rank keeps its row block of the next left environment.
+
+    ``L_rows`` (l, wl, l_rows) and ``psi_rows`` (l_rows, d, r) are this rank's blocks (rank g holds rows
+    [g l / G, (g + 1) l / G)); ``W``, ``R`` (r, wr, r) and ``neighbour`` (r, d, r2) are full.  Returns a dict with the
+    solver stats, the new site tensor (full, left-orthonormal), the new neighbour, this rank's rows of the next left
+    environment, and the seconds of every phase (device-synchronised)."""
+    import time
+
+    import torch
+
+    from tnpy_b200 import _cuda
+    from tnpy_b200.matrix_product_state import Direction, _split_on_device
+
+    lo, d, r = psi_rows.shape
+    if lo * comm.world != l:
+        raise ValueError(f"left bond {l} is not {comm.world} x {lo} rows")
+    if r % comm.world:
+        raise ValueError(f"right bond {r} does not split evenly over {comm.world} ranks")
+    row0 = comm.rank * lo
+    phases = {}
+
+    def tick(name, t0):
+        torch.cuda.synchronize()
+        phases[name] = time.perf_counter() - t0
+        return time.perf_counter()
+
+    torch.cuda.synchronize()
+    t = time.perf_counter()
+    image_rows = torch.empty_like(psi_rows)
+    stats = _cuda.eig_lowest_rows(comm, L_rows, W, R, psi_rows, l, row0, tol=tol, flags=flags, image_rows=image_rows, **opts)
+    t = tick("eigensolve", t)
+    _cuda.axpy(alpha, image_rows, psi_rows)
+    t = tick("perturb", t)
+    psi_full = torch.empty((l, d, r), dtype=torch.float64, device=psi_rows.device)
+    comm.allgather(psi_rows.contiguous(), psi_full)
+    site_tensor, new_neighbour, spectrum = _split_on_device(psi_full, neighbour, Direction.RIGHTWARD, "qr")
+    site_tensor = site_tensor.contiguous()
+    t = tick("gather_and_split", t)
+    left_flag = flags & _cuda.LEFT_IDENTITY
+    partial = _cuda.env_update_left_rows(L_rows, site_tensor, W, row0, flags=left_flag)
+    comm.allreduce_sum(partial)
+    ro = r // comm.world
+    next_rows = partial[:, :, comm.rank * ro:(comm.rank + 1) * ro].contiguous()
+    tick("env_update", t)
+    return {"stats": stats, "site_tensor": site_tensor, "neighbour": new_neighbour.contiguous(), "spectrum": spectrum,
+            "next_left_rows": next_rows, "phase_s": phases}
