@@ -283,6 +283,45 @@ static bool no_interior_blocks(const double* W_host, int wl, int wr, int d) {
   return true;
 }
 
+// K ranges of the direct path's GEMMs that multiply identically zero operand pieces: the piece (channel c, block q) of a
+// premixed operand vanishes when column q of that channel's d x d MPO block does (an S+ or S- block has one non-zero
+// element: half of its pieces).  channel_block(c) = pointer to the (d x d) block of channel c; a channel spans
+// `per_channel` K entries; blocks of tiles of one q are `block_tiles` tiles wide.  Leaves mode 0 (no skipping) when the
+// geometry does not line up with the 64-entry K chunks / the tile grid, or nothing can be skipped.
+template <typename BlockOf>
+static void plan_kskip(OzKSkip* out, int mode, int channels, int d, int per_channel, int block_tiles, BlockOf channel_block) {
+  *out = OzKSkip{};
+  if (per_channel % 64 != 0 || block_tiles <= 0 || d > kOzSkipBlocks) return;
+  OzKSkip s{};
+  s.mode = mode; s.block_tiles = block_tiles; s.nblocks = d;
+  const int chunks = per_channel / 64;
+  bool anything = false;
+  for (int q = 0; q < d; ++q) {
+    int n = 0;
+    bool open = false;
+    for (int c = 0; c < channels; ++c) {
+      const double* blk = channel_block(c);
+      bool nonzero = false;
+      for (int p = 0; p < d; ++p) nonzero = nonzero || blk[p * d + q] != 0.0;
+      if (nonzero) {
+        if (!open) {
+          if (n == kOzSkipRanges) return;
+          s.lo[q][n] = c * chunks;
+          open = true;
+        }
+        s.hi[q][n] = (c + 1) * chunks;
+      } else {
+        anything = true;
+        if (open) { ++n; open = false; }
+      }
+    }
+    if (open) ++n;
+    if (n == 0) return;  // a block with nothing to multiply: leave it to the plain kernel
+    s.nranges[q] = n;
+  }
+  if (anything) *out = s;
+}
+
 size_t heff_plan_bytes(int l, int lo, int r, int wl, int wr, int d) {
   size_t chain = Workspace::need((size_t)r * wr * r);  // r2 of the FP64 chain
   if (ozaki_applicable(d * r, wl * lo, l)) chain += oz_operand_bytes(wl * lo, l);
@@ -341,6 +380,12 @@ int heff_plan_init(HeffPlan* plan, const double* L, const double* W, const doubl
         // L'[(a - 1) l + li, m] = L[li, a, m]  (a >= 1);   R'[b r + ri, s] = R[ri, b, s]  (b < wr - 1)
         TNPY_TRY(oz_slice_operand(L, lo, OzRowMap{l, wl, 1}, plan->envL, stream));
         TNPY_TRY(oz_slice_operand(R, r, OzRowMap{r, wr, 0}, plan->envR, stream));
+        // R-side GEMM: rows (q, m), K = (b, ri), b < wr - 1, piece (b, q) from W[0, b]; blocks of lo / 256 m-tiles
+        plan_kskip(&plan->skipR, 1, wr - 1, d, r, lo % 256 == 0 ? lo / 256 : 0,
+                   [&](int b) { return W_host + (size_t)b * d * d; });
+        // L-side GEMM: columns (q, s), K = (a, li), a >= 1, piece (a, q) from W[a, wr - 1]; blocks of r / 128 n-tiles
+        plan_kskip(&plan->skipL, 2, wl - 1, d, l, r % 128 == 0 ? r / 128 : 0,
+                   [&](int a) { return W_host + ((size_t)(a + 1) * wr + (wr - 1)) * d * d; });
         plan->mode = HEFF_OZ_DIRECT;
         return TNPY_OK;
       }
@@ -390,12 +435,12 @@ static int apply_direct(const HeffPlan& p, const double* x, double* y, int S, co
     return TNPY_EWORKSPACE;
   }
   // y = W[0, wr-1] x - shift x, then both GEMMs accumulate into it
-  TNPY_TRY(oz_premix_a(x_rows, p.W, lo, r, wl, wr, d, xa, y, shift_dev, stream));
-  TNPY_TRY(oz_premix_b(x, p.W, l, r, wl, wr, d, xb, stream));
-  // y[(m q), s] += sum_{(b ri)} Xa[(b ri), (m q)] R'[(b ri), s]
-  TNPY_TRY(oz_mma(xa, p.envR, plain_out(y, r, lo * d), lo * d, r, S, 1, ws, p.bound, stream));
+  TNPY_TRY(oz_premix_a(x_rows, p.W, lo, r, wl, wr, d, xa, y, shift_dev, p.skipR.mode != 0, stream));
+  TNPY_TRY(oz_premix_b(x, p.W, l, r, wl, wr, d, xb, p.skipL.mode != 0, stream));
+  // y[m, q, s] += sum_{(b ri)} Xa[(b ri), (q m)] R'[(b ri), s]: GEMM rows (q, m) -> y rows (m, q) by the split-M row map
+  TNPY_TRY(oz_mma(xa, p.envR, GemmOut{y, (int64_t)d * r, (int64_t)r, lo}, lo * d, r, S, 1, ws, p.bound, stream, &p.skipR));
   // y[m, (q s)] += sum_{(a li)} L'[(a li), m] Xb[(a li), (q s)]
-  TNPY_TRY(oz_mma(p.envL, xb, plain_out(y, (int64_t)d * r, lo), lo, d * r, S, 1, ws, p.bound, stream));
+  TNPY_TRY(oz_mma(p.envL, xb, plain_out(y, (int64_t)d * r, lo), lo, d * r, S, 1, ws, p.bound, stream, &p.skipL));
   return TNPY_OK;
 }
 

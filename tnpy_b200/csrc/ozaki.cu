@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(256) oz_premix_a_kernel(const double* __restri
                                                           int r, int wr, int d, double* __restrict__ scale,
                                                           double* __restrict__ sumsq, int8_t* __restrict__ slices,
                                                           int64_t Kp, int64_t slice_stride, double* __restrict__ y0,
-                                                          const double* __restrict__ shift_dev) {
+                                                          const double* __restrict__ shift_dev, int skip_zero_pieces) {
   extern __shared__ double xs[];  // [d][r + r / 16 + 1]
   __shared__ double wc[kPmMaxCh][kPmMaxD][kPmMaxD];  // [b][p][q], b = wr - 1 holds the y0 block
   __shared__ double red[kPmMaxD][8];
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(256) oz_premix_a_kernel(const double* __restri
     for (int w8 = 0; w8 < (int)(blockDim.x >> 5); ++w8) v = fmax(v, red[tid][w8]);
     const double sc = oz_scale_of((unsigned long long)__double_as_longlong(v));
     sc_sh[tid] = sc;
-    scale[(int64_t)m * d + tid] = sc;
+    scale[(int64_t)tid * gridDim.x + m] = sc;  // columns are ordered (q, m): a tile of the GEMM then has one q
     if (sc > 0.0) atomicAdd(sumsq, sc * sc);
   }
   __syncthreads();
@@ -229,8 +229,13 @@ __global__ void __launch_bounds__(256) oz_premix_a_kernel(const double* __restri
     const double sc = sc_sh[q];
     const double inv = sc > 0.0 ? 1.0 / sc : 0.0;
     double cw[kPmMaxD];
+    bool any = false;
 #pragma unroll
-    for (int p = 0; p < kPmMaxD; ++p) cw[p] = p < d ? wc[b][p][q] * inv : 0.0;  // exact: inv is a power of two
+    for (int p = 0; p < kPmMaxD; ++p) {
+      cw[p] = p < d ? wc[b][p][q] * inv : 0.0;  // exact: inv is a power of two
+      any = any || (p < d && wc[b][p][q] != 0.0);
+    }
+    if (skip_zero_pieces && !any) continue;  // column q of W[0, b] vanishes: the GEMM skips this K range for block q
     uint4 dig[kOzMaxSlices];
     oz_digits16(
         [&](int e) {
@@ -245,7 +250,7 @@ __global__ void __launch_bounds__(256) oz_premix_a_kernel(const double* __restri
         },
         dig);
     const int64_t k0 = (int64_t)b * r + 16 * i16;
-    int8_t* row = slices + ((int64_t)m * d + q) * Kp + k0;
+    int8_t* row = slices + ((int64_t)q * gridDim.x + m) * Kp + k0;
     const bool last_piece = (b == nb - 1) && (16 * i16 + 16 > r);  // runs into the zero padding: still inside Kp?
     if (16 * i16 + 16 <= r || (last_piece && k0 + 16 <= Kp)) {
       oz_store16(row, slice_stride, dig, (k0 & 15) == 0);
@@ -263,7 +268,7 @@ __global__ void __launch_bounds__(256) oz_premix_a_kernel(const double* __restri
   const int kreal = nb * r, kpad = (int)(Kp - kreal);
   for (int item = tid; item < d * kOzMaxSlices * kpad; item += blockDim.x) {
     const int e = item % kpad, sl = (item / kpad) % kOzMaxSlices, q = item / (kpad * kOzMaxSlices);
-    slices[sl * slice_stride + ((int64_t)m * d + q) * Kp + kreal + e] = 0;
+    slices[sl * slice_stride + ((int64_t)q * gridDim.x + m) * Kp + kreal + e] = 0;
   }
   if (y0 != nullptr) {
     const double shift = shift_dev ? *shift_dev : 0.0;
@@ -324,7 +329,7 @@ __global__ void __launch_bounds__(256, D <= 2 ? 2 : 1) oz_premix_b_kernel(const 
                                                           const unsigned long long* __restrict__ colmax,
                                                           double* __restrict__ scale, double* __restrict__ sumsq,
                                                           int8_t* __restrict__ slices, int64_t Kp,
-                                                          int64_t slice_stride) {
+                                                          int64_t slice_stride, int skip_zero_pieces) {
   constexpr int d = D;
   __shared__ double wc[kPmMaxCh][D][D];
   const int na = wl - 1;
@@ -363,8 +368,13 @@ __global__ void __launch_bounds__(256, D <= 2 ? 2 : 1) oz_premix_b_kernel(const 
 #pragma unroll
     for (int q = 0; q < D; ++q) {
       double cw[D];
+      bool any = false;
 #pragma unroll
-      for (int p = 0; p < D; ++p) cw[p] = wc[a][p][q] * inv[q];  // exact scaling: inv is a power of two
+      for (int p = 0; p < D; ++p) {
+        cw[p] = wc[a][p][q] * inv[q];  // exact scaling: inv is a power of two
+        any = any || wc[a][p][q] != 0.0;
+      }
+      if (skip_zero_pieces && !any) continue;  // uniform over the block: the GEMM skips this K range for block q
       uint4 dig[kOzMaxSlices];
       oz_digits16(
           [&](int e) {
@@ -445,6 +455,22 @@ struct Oz2Tail {
   double* scratch;  // (splits - 1) * rem plain 256 x 128 tiles receiving the K ranges ks > 0
 };
 constexpr int kOz2Threads = 128 + 32 * kOz2EpiWarps;
+
+// K chunks a tile may skip because one operand is identically zero there (OzKSkip in ozaki.cuh): the tile's chunk
+// sequence is the concatenation of the ranges of its block.
+__device__ __forceinline__ int oz2_chunk_count(const OzKSkip& s, int blk) {
+  int n = 0;
+  for (int i = 0; i < s.nranges[blk]; ++i) n += s.hi[blk][i] - s.lo[blk][i];
+  return n;
+}
+__device__ __forceinline__ int oz2_chunk_at(const OzKSkip& s, int blk, int seq) {
+  for (int i = 0; i < s.nranges[blk]; ++i) {
+    const int len = s.hi[blk][i] - s.lo[blk][i];
+    if (seq < len) return s.lo[blk][i] + seq;
+    seq -= len;
+  }
+  return 0;
+}
 
 __device__ __forceinline__ uint32_t oz_cluster_rank() {
   uint32_t r;
@@ -544,7 +570,7 @@ template <int S>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kOz2Threads, 1)
     oz2_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const double* __restrict__ scaleA, const double* __restrict__ scaleB, GemmOut out, int M, int N,
-                   int KT, int accumulate, Oz2Tail tail) {
+                   int KT, int accumulate, Oz2Tail tail, const __grid_constant__ OzKSkip skip) {
   static_assert(S > 4 && S <= 8, "two passes of at most four diagonals");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -556,7 +582,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kOz2Threads, 1)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = oz_cluster_rank();
-  int tm, tn, ks = 0, kt0 = 0, kt1 = KT;
+  int tm, tn, ks = 0, kt0 = 0, kt1 = KT, kblk = 0;  // [kt0, kt1): positions in the tile's chunk sequence
   double* tail_tile = nullptr;
   {
     const int tiles_m = (M + 2 * kOzBM - 1) / (2 * kOzBM), tiles_n = (N + kOz2TileN - 1) / kOz2TileN;
@@ -564,12 +590,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kOz2Threads, 1)
     // work items: the first tail.n_full items are whole tiles; the tiles of the last, partly filled wave are cut
     // into tail.splits K ranges each so that the wave fills the machine (part ks > 0 goes to a scratch tile)
     int tile = blockIdx.x >> 1;
+    int split_part = -1;
     if (tile >= tail.n_full) {
       const int j = tile - tail.n_full;
       tile = tail.n_full + j % tail.rem;
       ks = j / tail.rem;
-      kt0 = (int)((int64_t)KT * ks / tail.splits);
-      kt1 = (int)((int64_t)KT * (ks + 1) / tail.splits);
+      split_part = ks;
       if (ks > 0) tail_tile = tail.scratch + (int64_t)((ks - 1) * tail.rem + (tile - tail.n_full)) * (2 * kOzBM * kOz2TileN);
     }
     const int per_group = GROUP * tiles_n;
@@ -577,6 +603,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kOz2Threads, 1)
     const int gsz = min(tiles_m - first_m, GROUP), rem = tile - gid * per_group;
     tm = first_m + rem % gsz;
     tn = rem / gsz;
+    // the K chunks this tile runs: all KT of them, or the ranges of its block when an operand has zero blocks
+    if (skip.mode != 0) {
+      kblk = (skip.mode == 1 ? tm : tn) / skip.block_tiles;
+      kt1 = oz2_chunk_count(skip, kblk);
+    }
+    if (split_part >= 0) {
+      const int nk_tile = kt1;
+      kt0 = (int)((int64_t)nk_tile * split_part / tail.splits);
+      kt1 = (int)((int64_t)nk_tile * (split_part + 1) / tail.splits);
+    }
   }
   const int m0 = tm * 2 * kOzBM + (int)rank * kOzBM;  // this CTA's rows of C / columns of A
   const int n0 = tn * kOz2TileN;                      // the pair's columns of C
@@ -610,6 +646,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kOz2Threads, 1)
       for (int t = 0; t < T; ++t) {
         int kt, sub;
         if (t < 2 * nk) { kt = kt0 + (t >> 1); sub = t & 1; } else { kt = kt0 + t - 2 * nk; sub = 0; }
+        if (skip.mode != 0) kt = oz2_chunk_at(skip, kblk, kt);
         oz_mbar_wait(&empty_bar[slot], phase ^ 1);
         if (rank == 0) oz_mbar_expect_tx(&full_bar[slot], 2 * kOz2Slot);  // both CTAs' boxes land on this barrier
         const uint32_t leader_full = oz_mapa(oz_smem_u32(&full_bar[slot]), 0);
@@ -830,19 +867,19 @@ bool oz_premix_applicable(int l, int r, int wl, int wr, int d) {
 }
 
 int oz_premix_a(const double* x, const double* W, int l, int r, int wl, int wr, int d, const OzOperand& op, double* y0,
-                const double* shift_dev, cudaStream_t stream) {
+                const double* shift_dev, bool skip_zero_pieces, cudaStream_t stream) {
   TNPY_CHECK_ARG(oz_premix_applicable(l, r, wl, wr, d), "dimensions outside the direct path's limits");
   TNPY_CHECK_ARG(op.cols == l * d && op.K == (wr - 1) * r, "operand shape mismatch");
   TNPY_TRY(set_max_dynamic_smem(oz_premix_a_kernel, 200 * 1024));
   TNPY_CUDA_OK(cudaMemsetAsync(op.sumsq, 0, sizeof(double), stream));
   oz_premix_a_kernel<<<l, 256, premix_a_smem(r, d), stream>>>(x, W, r, wr, d, op.scale, op.sumsq, op.slices, op.Kp,
-                                                             (int64_t)op.cols * op.Kp, y0, shift_dev);
+                                                             (int64_t)op.cols * op.Kp, y0, shift_dev, skip_zero_pieces ? 1 : 0);
   TNPY_LAUNCH_OK();
   return TNPY_OK;
 }
 
 int oz_premix_b(const double* x, const double* W, int l, int r, int wl, int wr, int d, const OzOperand& op,
-                cudaStream_t stream) {
+                bool skip_zero_pieces, cudaStream_t stream) {
   TNPY_CHECK_ARG(oz_premix_applicable(l, r, wl, wr, d), "dimensions outside the direct path's limits");
   TNPY_CHECK_ARG(op.cols == d * r && op.K == (wl - 1) * l, "operand shape mismatch");
   TNPY_CUDA_OK(cudaMemsetAsync(op.colmax, 0, sizeof(unsigned long long) * (size_t)(op.cols + 1), stream));
@@ -852,11 +889,12 @@ int oz_premix_b(const double* x, const double* W, int l, int r, int wl, int wr, 
   TNPY_LAUNCH_OK();
   const dim3 grid(ceil_div(r, 32), ceil_div(l, 128));
   const int64_t stride = (int64_t)op.cols * op.Kp;
+  const int skip = skip_zero_pieces ? 1 : 0;
   switch (d) {
-    case 1: oz_premix_b_kernel<1><<<grid, 256, 0, stream>>>(x, W, l, r, wl, wr, op.colmax, op.scale, op.sumsq, op.slices, op.Kp, stride); break;
-    case 2: oz_premix_b_kernel<2><<<grid, 256, 0, stream>>>(x, W, l, r, wl, wr, op.colmax, op.scale, op.sumsq, op.slices, op.Kp, stride); break;
-    case 3: oz_premix_b_kernel<3><<<grid, 256, 0, stream>>>(x, W, l, r, wl, wr, op.colmax, op.scale, op.sumsq, op.slices, op.Kp, stride); break;
-    default: oz_premix_b_kernel<4><<<grid, 256, 0, stream>>>(x, W, l, r, wl, wr, op.colmax, op.scale, op.sumsq, op.slices, op.Kp, stride); break;
+    case 1: oz_premix_b_kernel<1><<<grid, 256, 0, stream>>>(x, W, l, r, wl, wr, op.colmax, op.scale, op.sumsq, op.slices, op.Kp, stride, skip); break;
+    case 2: oz_premix_b_kernel<2><<<grid, 256, 0, stream>>>(x, W, l, r, wl, wr, op.colmax, op.scale, op.sumsq, op.slices, op.Kp, stride, skip); break;
+    case 3: oz_premix_b_kernel<3><<<grid, 256, 0, stream>>>(x, W, l, r, wl, wr, op.colmax, op.scale, op.sumsq, op.slices, op.Kp, stride, skip); break;
+    default: oz_premix_b_kernel<4><<<grid, 256, 0, stream>>>(x, W, l, r, wl, wr, op.colmax, op.scale, op.sumsq, op.slices, op.Kp, stride, skip); break;
   }
   TNPY_LAUNCH_OK();
   return TNPY_OK;
@@ -885,6 +923,17 @@ __global__ void __launch_bounds__(256) oz2_tail_combine_kernel(GemmOut out, int 
 // One CTA pair per SM pair at a time (shared memory): the last wave holds tiles % pairs tiles.  Cut those along K
 // so that the last wave is as wide as the machine; parts ks > 0 go to scratch tiles and are added back in a fixed
 // order.  Worth it only when the last wave is a sizeable part of the run (each part pays its own two epilogues).
+static int oz_min_chunks(const OzKSkip& skip, int KT) {
+  if (skip.mode == 0) return KT;
+  int best = KT;
+  for (int b = 0; b < skip.nblocks; ++b) {
+    int n = 0;
+    for (int i = 0; i < skip.nranges[b]; ++i) n += skip.hi[b][i] - skip.lo[b][i];
+    if (n < best) best = n;
+  }
+  return best;
+}
+
 static Oz2Tail oz2_plan_tail(int M, int N, int KT) {
   const int tiles = ceil_div(M, 2 * kOzBM) * ceil_div(N, kOz2TileN);
   const int pairs = sm_count() / 2;
@@ -910,7 +959,7 @@ size_t oz_mma_scratch_bytes(int M, int N) {
 
 template <int S>
 static int oz2_launch(const OzOperand& A, const OzOperand& B, GemmOut out, int M, int N, int accumulate, Workspace& ws,
-                      cudaStream_t stream) {
+                      const OzKSkip& skip, cudaStream_t stream) {
   CUtensorMap tmA, tmB;
   TNPY_TRY(oz_make_map(&tmA, A.slices, A.Kp, M, kOzBM));
   TNPY_TRY(oz_make_map(&tmB, B.slices, B.Kp, N, kOzBN));
@@ -918,13 +967,13 @@ static int oz2_launch(const OzOperand& A, const OzOperand& B, GemmOut out, int M
   TNPY_TRY(set_max_dynamic_smem(oz2_mma_kernel<S>, smem));
   const int tiles_m = ceil_div(M, 2 * kOzBM), tiles_n = ceil_div(N, kOz2TileN);
   const int KT = (int)(A.Kp / kOzBK);
-  Oz2Tail tail = oz2_plan_tail(M, N, KT);
+  Oz2Tail tail = oz2_plan_tail(M, N, oz_min_chunks(skip, KT));
   if (tail.splits > 1) {
     tail.scratch = ws.take<double>((size_t)(tail.splits - 1) * tail.rem * 2 * kOzBM * kOz2TileN);
     if (!tail.scratch) tail = Oz2Tail{tiles_m * tiles_n, 0, 1, nullptr};  // no room: run the tail unsplit
   }
   const int items = tail.n_full + tail.rem * tail.splits;
-  oz2_mma_kernel<S><<<2 * items, kOz2Threads, smem, stream>>>(tmA, tmB, A.scale, B.scale, out, M, N, KT, accumulate, tail);
+  oz2_mma_kernel<S><<<2 * items, kOz2Threads, smem, stream>>>(tmA, tmB, A.scale, B.scale, out, M, N, KT, accumulate, tail, skip);
   TNPY_LAUNCH_OK();
   if (tail.splits > 1) {
     oz2_tail_combine_kernel<<<dim3(tail.rem, 16), 256, 0, stream>>>(out, M, N, tiles_m, tiles_n, tail);
@@ -934,7 +983,14 @@ static int oz2_launch(const OzOperand& A, const OzOperand& B, GemmOut out, int M
 }
 
 int oz_mma(const OzOperand& A, const OzOperand& B, GemmOut out, int M, int N, int S, int accumulate, Workspace& ws,
-           double* bound_dev, cudaStream_t stream) {
+           double* bound_dev, cudaStream_t stream, const OzKSkip* skip_in) {
+  OzKSkip skip{};  // mode 0: every tile runs all chunks
+  if (skip_in != nullptr && skip_in->mode != 0) {
+    skip = *skip_in;
+    bool ok = skip.block_tiles > 0 && skip.nblocks > 0 && skip.nblocks <= kOzSkipBlocks;
+    for (int b = 0; ok && b < skip.nblocks; ++b) ok = skip.nranges[b] > 0 && skip.nranges[b] <= kOzSkipRanges;
+    TNPY_CHECK_ARG(ok, "malformed K-skip description");
+  }
   TNPY_CHECK_ARG(A.cols == M && B.cols == N && A.Kp == B.Kp && A.K == B.K, "operand shapes do not match the product");
   TNPY_CHECK_ARG(A.K <= 65536, "K too large for exact int32 accumulation");
   TNPY_CHECK_ARG(S >= 6 && S <= kOzMaxSlices, "slices must be 6, 7 or 8");
@@ -944,9 +1000,9 @@ int oz_mma(const OzOperand& A, const OzOperand& B, GemmOut out, int M, int N, in
     TNPY_LAUNCH_OK();
   }
   switch (S) {
-    case 6: return oz2_launch<6>(A, B, out, M, N, accumulate, ws, stream);
-    case 7: return oz2_launch<7>(A, B, out, M, N, accumulate, ws, stream);
-    default: return oz2_launch<8>(A, B, out, M, N, accumulate, ws, stream);
+    case 6: return oz2_launch<6>(A, B, out, M, N, accumulate, ws, skip, stream);
+    case 7: return oz2_launch<7>(A, B, out, M, N, accumulate, ws, skip, stream);
+    default: return oz2_launch<8>(A, B, out, M, N, accumulate, ws, skip, stream);
   }
 }
 
