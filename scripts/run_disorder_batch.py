@@ -2,8 +2,8 @@
 one box -- replicas only (one process per GPU, no collective on the data path).
 
     torchrun --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 scripts/run_disorder_batch.py \
-        --n 64 --chi 1024 --realisations 64 --sweeps 2
-    python scripts/run_disorder_batch.py --n 16 --chi 32 --realisations 4        # single GPU
+        --sites 64 --chi 1024 --realisations 64 --sweeps 2
+    python scripts/run_disorder_batch.py --sites 16 --chi 32 --realisations 4        # single GPU
 """
 import argparse
 import json
@@ -17,7 +17,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=64)
+    ap.add_argument("--sites", "--n", dest="n", type=int, default=64,
+                    help="chain length (spell it --sites under torchrun, whose own parser finds --n ambiguous)")
     ap.add_argument("--chi", type=int, default=1024)
     ap.add_argument("--h", type=float, default=1.0)
     ap.add_argument("--realisations", type=int, default=64)

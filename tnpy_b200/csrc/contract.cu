@@ -286,10 +286,11 @@ static bool no_interior_blocks(const double* W_host, int wl, int wr, int d) {
 // K ranges of the direct path's GEMMs that multiply identically zero operand pieces: the piece (channel c, block q) of a
 // premixed operand vanishes when column q of that channel's d x d MPO block does (an S+ or S- block has one non-zero
 // element: half of its pieces).  channel_block(c) = pointer to the (d x d) block of channel c; a channel spans
-// `per_channel` K entries; blocks of tiles of one q are `block_tiles` tiles wide.  Leaves mode 0 (no skipping) when the
-// geometry does not line up with the 64-entry K chunks / the tile grid, or nothing can be skipped.
-template <typename BlockOf>
-static void plan_kskip(OzKSkip* out, int mode, int channels, int d, int per_channel, int block_tiles, BlockOf channel_block) {
+// `per_channel` K entries; blocks of tiles of one q are `block_tiles` tiles wide; nonzero(c, q) says whether piece (c, q)
+// can be non-zero.  Leaves mode 0 (no skipping) when the geometry does not line up with the 64-entry K chunks / the
+// tile grid, or nothing can be skipped.
+template <typename NonZero>
+static void plan_kskip(OzKSkip* out, int mode, int channels, int d, int per_channel, int block_tiles, NonZero nonzero) {
   *out = OzKSkip{};
   if (per_channel % 64 != 0 || block_tiles <= 0 || d > kOzSkipBlocks) return;
   OzKSkip s{};
@@ -300,10 +301,7 @@ static void plan_kskip(OzKSkip* out, int mode, int channels, int d, int per_chan
     int n = 0;
     bool open = false;
     for (int c = 0; c < channels; ++c) {
-      const double* blk = channel_block(c);
-      bool nonzero = false;
-      for (int p = 0; p < d; ++p) nonzero = nonzero || blk[p * d + q] != 0.0;
-      if (nonzero) {
+      if (nonzero(c, q)) {
         if (!open) {
           if (n == kOzSkipRanges) return;
           s.lo[q][n] = c * chunks;
@@ -381,11 +379,16 @@ int heff_plan_init(HeffPlan* plan, const double* L, const double* W, const doubl
         TNPY_TRY(oz_slice_operand(L, lo, OzRowMap{l, wl, 1}, plan->envL, stream));
         TNPY_TRY(oz_slice_operand(R, r, OzRowMap{r, wr, 0}, plan->envR, stream));
         // R-side GEMM: rows (q, m), K = (b, ri), b < wr - 1, piece (b, q) from W[0, b]; blocks of lo / 256 m-tiles
+        auto column_nonzero = [&](const double* blk, int q) {
+          for (int p = 0; p < d; ++p)
+            if (blk[p * d + q] != 0.0) return true;
+          return false;
+        };
         plan_kskip(&plan->skipR, 1, wr - 1, d, r, lo % 256 == 0 ? lo / 256 : 0,
-                   [&](int b) { return W_host + (size_t)b * d * d; });
+                   [&](int b, int q) { return column_nonzero(W_host + (size_t)b * d * d, q); });
         // L-side GEMM: columns (q, s), K = (a, li), a >= 1, piece (a, q) from W[a, wr - 1]; blocks of r / 128 n-tiles
         plan_kskip(&plan->skipL, 2, wl - 1, d, l, r % 128 == 0 ? r / 128 : 0,
-                   [&](int a) { return W_host + ((size_t)(a + 1) * wr + (wr - 1)) * d * d; });
+                   [&](int a, int q) { return column_nonzero(W_host + ((size_t)(a + 1) * wr + (wr - 1)) * d * d, q); });
         plan->mode = HEFF_OZ_DIRECT;
         return TNPY_OK;
       }
@@ -406,8 +409,24 @@ int heff_plan_init(HeffPlan* plan, const double* L, const double* W, const doubl
     Workspace probe = mem;
     if (oz_operand_take(probe, s.n3, s.k3, &plan->envR)) {
       mem = probe;
-      // right identity: K runs over (b, ri) with the last channel dropped, matching the channel-major intermediate
-      TNPY_TRY(oz_slice_operand(R, r, s.right_id ? OzRowMap{r, wr, 0} : oz_plain_rows(r * wr), plan->envR, stream));
+      // on the tcgen05 path K always runs channel-major, (b, ri) (with the last channel dropped under the right
+      // identity flag), matching the channel-major intermediate: a channel is then a contiguous K range, and the
+      // GEMM can skip the ranges whose piece (b, q) of the mixed intermediate vanishes -- W[a, b, p, q] = 0 for all
+      // a, p (XXZ: 2 of 10 pieces)
+      TNPY_TRY(oz_slice_operand(R, r, OzRowMap{r, wr, 0}, plan->envR, stream));
+      double w_local[kPmMaxCh * kPmMaxCh * kPmMaxD * kPmMaxD];
+      if (!W_host && (size_t)wl * wr * d * d <= sizeof(w_local) / sizeof(double)) {
+        TNPY_CUDA_OK(cudaMemcpyAsync(w_local, W, sizeof(double) * (size_t)wl * wr * d * d, cudaMemcpyDeviceToHost, stream));
+        TNPY_CUDA_OK(cudaStreamSynchronize(stream));
+        W_host = w_local;
+      }
+      if (W_host)
+        plan_kskip(&plan->skip3, 1, s.k3 / r, d, r, lo % 256 == 0 ? lo / 256 : 0, [&](int b, int q) {
+          for (int a = 0; a < wl; ++a)
+            for (int pp = 0; pp < d; ++pp)
+              if (W_host[(((size_t)a * wr + b) * d + pp) * d + q] != 0.0) return true;
+          return false;
+        });
     } else {
       plan->g3_oz = false;
     }
@@ -475,7 +494,7 @@ int heff_plan_apply(const HeffPlan& p, const double* x, double* y, int S, const 
                      plain_out(t1_dst, (int64_t)wl * lo, s.m1), s.m1, s.n1, s.k1, 0, TNPY_GEMM_FP64, stream));
   }
   // T2[r, b, q, m] (or [b, r, q, m]) = sum_{a p} W[a, b, p, q] T1[p, r, a, m]      (u=p, u'=q, v=a, v'=b)
-  TNPY_TRY(wmix(t1, t2, p.W, d, d, wl, wr, r, lo, d, 1, wr * d * d, d * d, stream, s.right_id ? 1 : 0));
+  TNPY_TRY(wmix(t1, t2, p.W, d, d, wl, wr, r, lo, d, 1, wr * d * d, d * d, stream, (s.right_id || p.g3_oz) ? 1 : 0));
   // y[m, q, s] = sum_{r b} T2[(r b), (q m)] R[(r b), s]               rows (q m) -> (m q)
   // (right identity: the GEMM runs over the channels b < wr-1 and the identity-channel term T2[wr-1, s, q, m]
   // is added by a transposing pass afterwards so that the GEMM epilogue stays store-only)
@@ -488,7 +507,7 @@ int heff_plan_apply(const HeffPlan& p, const double* x, double* y, int S, const 
       return TNPY_EWORKSPACE;
     }
     TNPY_TRY(oz_slice_operand(t2, (int64_t)d * lo, oz_plain_rows(s.k3), ts, stream));
-    TNPY_TRY(oz_mma(ts, p.envR, out, s.m3, s.n3, S, 0, scratch, p.bound, stream));
+    TNPY_TRY(oz_mma(ts, p.envR, out, s.m3, s.n3, S, 0, scratch, p.bound, stream, &p.skip3));
   } else {
     TNPY_TRY(gemm_tn(t2, (int64_t)d * lo, s.right_id ? p.r2 : p.R, (int64_t)r, out, s.m3, s.n3, s.k3, 0, TNPY_GEMM_FP64,
                      stream));

@@ -23,6 +23,7 @@ struct HeffPlan {
   bool g1_oz, g3_oz;   // OZ_CHAIN: which of the two GEMMs run on the tcgen05 path
   OzOperand envL, envR;  // sliced constant operands (plan memory)
   OzKSkip skipR, skipL;  // direct path: K ranges the R-side / L-side GEMM skips (zero pieces of the premixed operands)
+  OzKSkip skip3;         // tcgen05 chain: K ranges the second GEMM skips (zero pieces of the mixed intermediate)
   double* r2;            // FP64 chain with the right identity flag: R channel-major without its last channel
   double* bound;         // device scalar: largest rigorous error bound of a tcgen05 product issued through this plan
 };

@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict_
 // for a fixed column (m, q) the K index (b, ri) runs over contiguous ri, so the row x[m, :, :] (d * r doubles) is
 // read once into shared memory, its column maxima are found, and every thread then turns 16 consecutive ri of one
 // (q, b) piece into digits.  The same pass writes y0[m, q, :] = sum_p W[0, wr - 1, p, q] x[m, p, :] - shift x[m, q, :].
-__global__ void __launch_bounds__(256) oz_premix_a_kernel(const double* __restrict__ x, const double* __restrict__ W,
+__global__ void __launch_bounds__(256, 4) oz_premix_a_kernel(const double* __restrict__ x, const double* __restrict__ W,
                                                           int r, int wr, int d, double* __restrict__ scale,
                                                           double* __restrict__ sumsq, int8_t* __restrict__ slices,
                                                           int64_t Kp, int64_t slice_stride, double* __restrict__ y0,
