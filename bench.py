@@ -462,6 +462,23 @@ def run_single(args):
         sec = max(e0.elapsed_time(e1) * 1e-3, time.perf_counter() - t0) / args.steps
         return sec, np.array(y_np, copy=True)
 
+    # one on-device local solve, cut off after 60 matvecs: what a Lanczos step costs on top of its matvec
+    env.use_identity_channels = True
+    psi_try = x.clone()
+    img = torch.empty_like(psi_try)
+    _cuda.eig_lowest(L, W, R, psi_try.clone(), tol=args.tol, max_matvec=3, flags=gauge)
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    st = _cuda.eig_lowest(L, W, R, psi_try, tol=args.tol, max_matvec=60, flags=gauge, image=img)
+    e1.record()
+    sync()
+    lanczos = {"matvecs": st["n_matvec"], "ms_per_step": e0.elapsed_time(e1) / max(st["n_matvec"], 1), "slices": st["slices"],
+               "heff_mode": st["heff_mode"], "restarts": st["n_restart"], "int8_error_bound": st["int8_error_bound"],
+               "note": "tnpy_eig_lowest at the bench site (measured gauge flags), stopped after 60 matvecs: whole-step time = matvec + "
+                       "Gram-Schmidt passes + Ritz solves + status read-backs + environment slicing once"}
+    del psi_try, img
+
     t_e2e, y_np = e2e_seconds(False)
     parity = float(np.abs(y_np - y_general.reshape(-1).cpu().numpy()).max())
     t_e2e_c, _ = e2e_seconds(True)
@@ -519,6 +536,7 @@ def run_single(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "canonical_gauge": canonical,
+        "lanczos_step": lanczos,
         "native_fp64": {
             "ms_per_step": t_f * 1e3, "tflops": tf(t_f), "roofline": roofline_dmma,
             "note": "the same general chain with TNPY_GEMM_ALGO=fp64: gemm_tn_dmma (mma.sync DMMA) -> wmix -> gemm_tn_dmma",
