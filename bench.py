@@ -579,6 +579,8 @@ def measure_sweeps(n, chi, tol, count):
         out["sweep_s"].append(time.perf_counter() - t0)
         out["launches"].append(_cuda.launch_count() - l0)
         out["matvecs"].append(sum(st.get("n_matvec", 0) for st in dmrg.solver_stats))
+        out.setdefault("looks", []).append(sum(st.get("looks", 0) for st in dmrg.solver_stats))
+        out.setdefault("extra_gs_passes", []).append(sum(st.get("extra_gs_passes", 0) for st in dmrg.solver_stats))
         out["energies"].append(e)
         out["phase_s_cumulative"].append(dict(dmrg.phase_seconds))
     out["split_counts"] = dict(dmrg.environment.split_counts)

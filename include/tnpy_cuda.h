@@ -220,6 +220,9 @@ int tnpy_eig_lowest(const double* L, const double* W, const double* R, double* p
  * relation H V_m = V_m T + beta v_{m+1} e_m^T:  H psi = theta psi + (beta s_m) v_{m+1}  (equal to a fresh
  * tnpy_heff_apply(psi) to rounding).  FiniteDMRG.perturb_wave_function (finite_dmrg.py:116-141), which the
  * sweep calls right after the solve, needs exactly that vector. */
+/* Diagnostics of the calling thread's last tnpy_eig_lowest* call: matvecs, looks (status read-backs = stream
+ * synchronisations), extra full Gram-Schmidt passes the DGKS test asked for, thick restarts.  Returns how many were written. */
+int tnpy_last_eig_counters(int64_t* out, int n);
 int tnpy_eig_lowest_image(const double* L, const double* W, const double* R, double* psi, double* hpsi,
                           int l, int r, int wl, int wr, int d, int flags, double tol, int max_matvec, int ncv,
                           double* stats_host, void* workspace, size_t workspace_bytes, void* stream);

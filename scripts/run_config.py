@@ -81,6 +81,8 @@ def main():
             torch.cuda.synchronize()
             per_sweep.append(time.perf_counter() - t)
             out.setdefault("gpu_matvecs_per_sweep", []).append(sum(s.get("n_matvec", 0) for s in gpu.solver_stats))
+            out.setdefault("gpu_looks_per_sweep", []).append(sum(s.get("looks", 0) for s in gpu.solver_stats))
+            out.setdefault("gpu_extra_gs_passes_per_sweep", []).append(sum(s.get("extra_gs_passes", 0) for s in gpu.solver_stats))
             out.setdefault("gpu_phase_s_cumulative", []).append(dict(gpu.phase_seconds))
         out["gpu_sweep_s"] = per_sweep
         out["gpu_matvecs_last_sweep"] = sum(s.get("n_matvec", 0) for s in gpu.solver_stats)

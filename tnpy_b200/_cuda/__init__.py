@@ -71,6 +71,7 @@ SIGNATURES = {
         c_int,
         [_PD, _PD, _PD, _PD] + [c_int] * 6 + [c_double, c_int, c_int, ctypes.POINTER(c_double), c_void_p, c_size_t, c_void_p],
     ),
+    "tnpy_last_eig_counters": (c_int, [ctypes.POINTER(c_int64), c_int]),
     "tnpy_eig_lowest_image": (
         c_int,
         [_PD, _PD, _PD, _PD, _PD] + [c_int] * 6 + [c_double, c_int, c_int, ctypes.POINTER(c_double), c_void_p, c_size_t, c_void_p],
@@ -467,10 +468,12 @@ def eig_lowest(L, W, R, psi, tol: float = 1e-8, max_matvec: int = 1000, ncv: int
         rc = lib.tnpy_eig_lowest_image(_ptr(L), _ptr(W), _ptr(R), _ptr(psi), _ptr(image), l, r, wl, wr, d, int(flags),
                                        float(tol), int(max_matvec), int(ncv), stats, _ptr(ws), nbytes, _stream())
     check(rc, "tnpy_eig_lowest", allow_noconv=True)
+    counters = last_eig_counters()
     return {
         "theta": stats[0], "resid": stats[1], "n_matvec": int(stats[2]), "n_restart": int(stats[3]),
         "converged": bool(stats[4]), "anorm": stats[5], "int8_error_bound": stats[6],
         "heff_mode": int(stats[7]) // 10, "slices": int(stats[7]) % 10,
+        "looks": counters["looks"], "extra_gs_passes": counters["extra_gs_passes"],
     }
 
 
@@ -552,6 +555,13 @@ def eig_lowest_rows(comm: Comm, L_rows, W, R, psi_rows, l: int, row0: int, tol: 
         "converged": bool(stats[4]), "anorm": stats[5], "int8_error_bound": stats[6],
         "heff_mode": int(stats[7]) // 10, "slices": int(stats[7]) % 10,
     }
+
+
+def last_eig_counters() -> dict:
+    """Diagnostics of this thread's last on-device eigensolve: matvecs, looks, extra Gram-Schmidt passes, restarts."""
+    buf = (c_int64 * 4)()
+    load().tnpy_last_eig_counters(buf, 4)
+    return {"n_matvec": buf[0], "looks": buf[1], "extra_gs_passes": buf[2], "restarts": buf[3]}
 
 
 def geig_lowest(LA, WA, RA, LM, WM, RM, psi, tol: float = 1e-8, max_iter: int = 2000, ncv: int = 0, flags_a: int = 0):

@@ -31,7 +31,7 @@ constexpr int kMaxNcv = 48;
 constexpr int kRitzLd = kMaxNcv + 1;
 
 // status record (device and pinned host mirror)
-enum { ST_THETA = 0, ST_RESID = 1, ST_ANORM = 2, ST_DONE = 3, ST_BETA = 4, ST_RCOEF = 5, ST_BOUND = 6, ST_SIZE = 8 };
+enum { ST_THETA = 0, ST_RESID = 1, ST_ANORM = 2, ST_DONE = 3, ST_BETA = 4, ST_RCOEF = 5, ST_BOUND = 6, ST_EXTRA = 7, ST_SIZE = 8 };
 
 // Symmetric eigen-decomposition of the m x m matrix held in shared memory `a` (leading dim kMaxNcv)
 // by parallel cyclic Jacobi (round-robin pair ordering).  Eigenvectors accumulate in `z` (columns).
@@ -207,7 +207,8 @@ static size_t eig_ws_layout(int64_t n, int ncv, int keep, size_t chain) {
 
 // skip = 1 when the first Gram-Schmidt pass did not cancel heavily (||w'|| >= eta ||h||); h2 is then zero.
 __global__ void reorth_decision_kernel(const double* __restrict__ h, int m, const double* __restrict__ nrm_after,
-                                       double eta, double* __restrict__ h2, int* __restrict__ skip) {
+                                       double eta, double* __restrict__ h2, int* __restrict__ skip,
+                                       double* __restrict__ extra_passes) {
   __shared__ double sh[32];
   double a = 0.0;
   for (int j = threadIdx.x; j < m; j += blockDim.x) a = fma(h[j], h[j], a);
@@ -217,6 +218,7 @@ __global__ void reorth_decision_kernel(const double* __restrict__ h, int m, cons
     const double hn = sqrt(a), wn = *nrm_after;
     decision = (wn >= eta * hn && wn > 0.0) ? 1 : 0;
     *skip = decision;
+    if (!decision) *extra_passes += 1.0;  // diagnostics: how often the extra full pass really ran
   }
   __syncthreads();
   if (decision)
@@ -263,6 +265,9 @@ extern "C" size_t tnpy_eig_workspace_bytes(int l, int r, int wl, int wr, int d, 
 // one exchange of data: (G - 1) / G of 8 N bytes per rank over NVLink), run their row block of the matvec, and
 // all-reduce the Gram-Schmidt coefficients and norms (a few dozen doubles); the small Ritz problem is solved
 // redundantly on every rank from identical inputs, so all ranks take identical decisions.
+// diagnostics of the calling thread's last solve: matvecs, looks (status read-backs), extra full Gram-Schmidt passes, restarts
+static thread_local long long g_last_counters[4] = {0, 0, 0, 0};
+
 static int eig_lowest_impl(const tnpy_comm* comm, const double* L, const double* W, const double* R, double* psi,
                            double* hpsi, int l, int row0, int lo, int r, int wl, int wr, int d, int flags, double tol,
                            int max_matvec, int ncv_in, double* stats_host, void* workspace, size_t workspace_bytes,
@@ -335,6 +340,7 @@ static int eig_lowest_impl(const tnpy_comm* comm, const double* L, const double*
     TNPY_LAUNCH_OK();
     return TNPY_OK;
   };
+  TNPY_CUDA_OK(cudaMemsetAsync(status, 0, sizeof(double) * 64, stream));
   // V[0] = v0 / ||v0||
   TNPY_TRY(multi_dot(psi, ldv, 1, psi, n, status + ST_BETA, 1, stream));
   TNPY_TRY(reduce_norm(status + ST_BETA, status + ST_BETA, nullptr));
@@ -342,6 +348,7 @@ static int eig_lowest_impl(const tnpy_comm* comm, const double* L, const double*
   TNPY_CUDA_OK(cudaMemsetAsync(T, 0, sizeof(double) * kMaxNcv * kMaxNcv, stream));
 
   int j = 0, n_matvec = 0, n_restart = 0;
+  int n_looks = 0;
   int whole_basis_step = 0;  // step whose local Gram-Schmidt set is the whole basis (the first after a restart)
   double worst_bound = 0.0, anorm_seen = 0.0;
   bool done = false;
@@ -388,7 +395,7 @@ static int eig_lowest_impl(const tnpy_comm* comm, const double* L, const double*
     TNPY_TRY(reduce(h, j + 1));
     TNPY_TRY(multi_axpy(V, ldv, j + 1, h, w, n, local_norm, stream));
     TNPY_TRY(reduce_norm(local_norm, status + ST_BETA, nullptr));
-    reorth_decision_kernel<<<1, 64, 0, stream>>>(h, j + 1, status + ST_BETA, eta, h2, skip2);
+    reorth_decision_kernel<<<1, 64, 0, stream>>>(h, j + 1, status + ST_BETA, eta, h2, skip2, status + ST_EXTRA);
     TNPY_LAUNCH_OK();
     TNPY_TRY(multi_dot(V, ldv, j + 1, w, n, h2, 0, stream, skip2));
     TNPY_TRY(reduce(h2, j + 1));  // skipped pass: the decision kernel zeroed h2 on every rank
@@ -405,6 +412,7 @@ static int eig_lowest_impl(const tnpy_comm* comm, const double* L, const double*
       continue;
     }
     since_check = 0;
+    ++n_looks;
     if (plan.bound)
       TNPY_CUDA_OK(cudaMemcpyAsync(status + ST_BOUND, plan.bound, sizeof(double), cudaMemcpyDeviceToDevice, stream));
     TNPY_CUDA_OK(cudaMemcpyAsync(hst, status, sizeof(double) * ST_SIZE, cudaMemcpyDeviceToHost, stream));
@@ -476,6 +484,10 @@ static int eig_lowest_impl(const tnpy_comm* comm, const double* L, const double*
     stats_host[6] = worst_bound > hst[ST_BOUND] ? worst_bound : hst[ST_BOUND];  // rigorous bound on the int8 products' error
     stats_host[7] = (double)(plan.mode * 10 + (plan.mode == HEFF_FP64_CHAIN ? 0 : slices));
   }
+  g_last_counters[0] = n_matvec;
+  g_last_counters[1] = n_looks;
+  g_last_counters[2] = (long long)hst[ST_EXTRA];
+  g_last_counters[3] = n_restart;
   if (!done) {
     set_error("tnpy_eig_lowest: not converged after %d matvecs (resid %.3e, tol*|A| %.3e)", n_matvec, hst[ST_RESID],
               tol * hst[ST_ANORM]);
@@ -515,4 +527,10 @@ extern "C" int tnpy_eig_lowest_rows(const tnpy_comm* comm, const double* L_rows,
   TNPY_CHECK_ARG(comm != nullptr, "null communicator");
   return eig_lowest_impl(comm, L_rows, W, R, psi_rows, hpsi_rows, l, row0, l_rows, r, wl, wr, d, flags, tol, max_matvec,
                          ncv_in, stats_host, workspace, workspace_bytes, stream_);
+}
+
+extern "C" int tnpy_last_eig_counters(int64_t* out, int n) {
+  int k = 0;
+  for (; k < n && k < 4; ++k) out[k] = g_last_counters[k];
+  return k;
 }

@@ -1009,9 +1009,19 @@ int oz_mma(const OzOperand& A, const OzOperand& B, GemmOut out, int M, int N, in
 static std::atomic<int> g_oz_slices{8};
 int ozaki_slices() { return g_oz_slices.load(); }
 
+// smallest product (M N K) sent to the int8 path; env TNPY_OZAKI_MIN_WORK overrides it (experiments)
+static double oz_min_work() {
+  static const double v = [] {
+    const char* e = getenv("TNPY_OZAKI_MIN_WORK");
+    const double x = e ? atof(e) : 0.0;
+    return x > 0.0 ? x : 6.0e9;
+  }();
+  return v;
+}
+
 bool ozaki_applicable(int M, int N, int K) {
   // below ~chi = 1024 the slicing passes and extra launches cost more than the faster MMA saves (measured at chi = 512)
-  return K <= 65536 && K >= 64 && M >= 128 && N >= 64 && (double)M * N * K >= 6.0e9;
+  return K <= 65536 && K >= 64 && M >= 128 && N >= 64 && (double)M * N * K >= oz_min_work();
 }
 
 }  // namespace tnpy
