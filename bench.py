@@ -292,6 +292,35 @@ def fp64_peak_cublas(m8, sync):
     return 2.0 * m8**3 / best / 1e12
 
 
+def int8_peak_cublaslt(sync):
+    """int8 tensor-core yardstick measured in this process the way MEASURED_PEAKS.json measures bf16: a library GEMM
+    (cuBLASLt through torch._int_mm, int8 x int8 -> int32, 8192^3), best of 5 (burst) and back to back for 1.5 s
+    (sustained, under the power cap).  None when the library call is not available."""
+    import torch
+
+    try:
+        n = 8192
+        a = torch.randint(-64, 65, (n, n), dtype=torch.int8, device="cuda")
+        b = torch.randint(-64, 65, (n, n), dtype=torch.int8, device="cuda")
+        torch._int_mm(a, b)
+        sync()
+        best = min(cuda_time(lambda: torch._int_mm(a, b), 1, sync) for _ in range(5))
+        t0, cnt = time.perf_counter(), 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        while time.perf_counter() - t0 < 1.5:
+            for _ in range(20):
+                torch._int_mm(a, b)
+            cnt += 20
+            sync()
+        e1.record()
+        sync()
+        return {"burst_pops": 2.0 * n**3 / best / 1e15, "sustained_pops": 2.0 * n**3 * cnt / (e0.elapsed_time(e1) * 1e-3) / 1e15,
+                "how": "torch._int_mm 8192^3 (cuBLASLt int8 -> int32): best of 5, and back to back for 1.5 s"}
+    except Exception as exc:  # pragma: no cover - depends on the installed cuBLASLt
+        return {"burst_pops": None, "sustained_pops": None, "how": f"torch._int_mm unavailable: {exc}"}
+
+
 def run_single(args):
     import torch
 
@@ -308,6 +337,7 @@ def run_single(args):
     sync = torch.cuda.synchronize
     m8 = 8192 if chi >= 1024 else 4096
     fp64_peak = fp64_peak_cublas(m8, sync)
+    int8_lib = int8_peak_cublaslt(sync)
 
     t_setup = time.perf_counter()
     tensors = random_right_canonical_device(n, chi, d, seed=0)
@@ -491,6 +521,8 @@ def run_single(args):
     roofline_oz = {
         "bound": "tensor", "achieved": pops(shapes_general, oz_g), "peak": INT8_PEAK_POPS, "unit": "POP/s (int8)",
         "frac": pops(shapes_general, oz_g) / INT8_PEAK_POPS,
+        "library_int8_gemm": int8_lib,
+        "frac_of_library_int8_gemm_burst": (pops(shapes_general, oz_g) / int8_lib["burst_pops"]) if int8_lib.get("burst_pops") else None,
         "traffic": 1.63e9,  # dram read + write per launch, mean of the two shapes, ncu --set full (profiles/r01_oz2_mma_kernel_ncu_full_raw.csv)
         "algorithmic_bytes_per_launch": 8.0 * (shapes_general[0][0] + shapes_general[0][1]) * shapes_general[0][2] + 8.0 * shapes_general[0][0] * shapes_general[0][1],
         "kernel": "oz2_mma_kernel<8> (tcgen05.mma.cta_group::2.kind::i8; 2 launches per matvec, operands already sliced)",

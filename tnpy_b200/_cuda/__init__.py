@@ -194,18 +194,27 @@ def _need_cuda(*tensors) -> None:
 
 
 class Scratch:
-    """Grow-only device workspace owned by the Python side and lent to the library per call."""
+    """Grow-only device workspace owned by the Python side and lent to the library per call: one buffer per
+    (device, stream), so that calls enqueued on different streams never share scratch."""
 
     def __init__(self):
-        self._buf = None
+        self._bufs = {}
 
     def get(self, nbytes: int):
         import torch
 
-        if self._buf is None or self._buf.numel() < nbytes:
-            self._buf = None
-            self._buf = torch.empty(int(nbytes), dtype=torch.uint8, device="cuda")
-        return self._buf
+        key = (torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream)
+        buf = self._bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            self._bufs.pop(key, None)  # the caching allocator keeps the old block alive for work already enqueued on this stream
+            buf = None
+            buf = torch.empty(int(nbytes), dtype=torch.uint8, device="cuda")
+            self._bufs[key] = buf
+        return buf
+
+    def release(self):
+        """Drop every workspace (they are re-created on demand)."""
+        self._bufs.clear()
 
 
 _scratch = Scratch()
