@@ -447,13 +447,15 @@ int heff_plan_init(HeffPlan* plan, const double* L, const double* W, const doubl
 static int apply_direct(const HeffPlan& p, const double* x, double* y, int S, const double* shift_dev, Workspace& ws,
                         cudaStream_t stream) {
   const int l = p.l, lo = p.lo, r = p.r, wl = p.wl, wr = p.wr, d = p.d;
+  const double* x_rows = x + (int64_t)p.row0 * d * r;  // the caller's rows of x: all the R-side term needs
   OzOperand xa, xb;
   if (!oz_operand_take(ws, lo * d, (wr - 1) * r, &xa) || !oz_operand_take(ws, d * r, (wl - 1) * l, &xb)) {
     set_error("heff_apply: workspace too small");
     return TNPY_EWORKSPACE;
   }
   // y = W[0, wr-1] x - shift x, then both GEMMs accumulate into it
-  TNPY_TRY(oz_premix(x, p.row0, p.W, l, lo, r, wl, wr, d, xa, xb, y, shift_dev, p.skipR.mode != 0, p.skipL.mode != 0, stream));
+  TNPY_TRY(oz_premix_a(x_rows, p.W, lo, r, wl, wr, d, xa, y, shift_dev, p.skipR.mode != 0, stream));
+  TNPY_TRY(oz_premix_b(x, p.W, l, r, wl, wr, d, xb, p.skipL.mode != 0, stream));
   // y[m, q, s] += sum_{(b ri)} Xa[(b ri), (q m)] R'[(b ri), s]: GEMM rows (q, m) -> y rows (m, q) by the split-M row map
   TNPY_TRY(oz_mma(xa, p.envR, GemmOut{y, (int64_t)d * r, (int64_t)r, lo}, lo * d, r, S, 1, ws, p.bound, stream, &p.skipR));
   // y[m, (q s)] += sum_{(a li)} L'[(a li), m] Xb[(a li), (q s)]

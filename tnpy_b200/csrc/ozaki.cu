@@ -161,157 +161,168 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict_
 // ---------------------------------------------------------------------------------------------
 // premixed operands of the direct path (mixed-canonical gauge, no interior-to-interior MPO blocks)
 // ---------------------------------------------------------------------------------------------
-// Column scales without a pass over the premixed values: |sum_p W[p][q] x_p| <= sum_p |W[p][q]| |x_p|, so the maxima of
-// |x| along its rows (A side: over ri for every (m, p)) and along its columns (B side: over li for every (p, s)) bound
-// every column of both operands -- exactly for block columns with one non-zero (S+, S-, S^z, 1: every block of the
-// tnpy models), within a factor d otherwise (one bit).  One pass over x finds both, and writes
-// y0[m, q, :] = sum_p W[0, wr - 1, p, q] x[m, p, :] - shift x[m, q, :] on the way.
-constexpr int kAbsRows = 4;  // rows of x per block
-
-template <int D>
-__global__ void __launch_bounds__(256) oz_absmax_kernel(const double* __restrict__ x, const double* __restrict__ W, int l,
-                                                        int r, int wr, int row0, int lo,
-                                                        double* __restrict__ rowmax,                // [lo][d]
-                                                        unsigned long long* __restrict__ colmax,    // [d][r], zeroed
-                                                        double* __restrict__ y0, const double* __restrict__ shift_dev) {
-  constexpr int d = D;
-  __shared__ double wlast[D][D];  // W[0, wr - 1, p, q]
-  __shared__ double red[kAbsRows][D][8];
-  const int tid = threadIdx.x;
-  if (tid < d * d) wlast[tid / d][tid % d] = W[((size_t)(wr - 1) * d + tid / d) * d + tid % d];
+// A side: one block per left-bond index m.  Xa[(b, ri), (m, q)] = sum_p W[0, b, p, q] x[m, p, ri] for b < wr - 1:
+// for a fixed column (m, q) the K index (b, ri) runs over contiguous ri, so the row x[m, :, :] (d * r doubles) is
+// read once into shared memory, its column maxima are found, and every thread then turns 16 consecutive ri of one
+// (q, b) piece into digits.  The same pass writes y0[m, q, :] = sum_p W[0, wr - 1, p, q] x[m, p, :] - shift x[m, q, :].
+__global__ void __launch_bounds__(256, 4) oz_premix_a_kernel(const double* __restrict__ x, const double* __restrict__ W,
+                                                          int r, int wr, int d, double* __restrict__ scale,
+                                                          double* __restrict__ sumsq, int8_t* __restrict__ slices,
+                                                          int64_t Kp, int64_t slice_stride, double* __restrict__ y0,
+                                                          const double* __restrict__ shift_dev, int skip_zero_pieces) {
+  extern __shared__ double xs[];  // [d][r + r / 16 + 1]
+  __shared__ double wc[kPmMaxCh][kPmMaxD][kPmMaxD];  // [b][p][q], b = wr - 1 holds the y0 block
+  __shared__ double red[kPmMaxD][8];
+  __shared__ double sc_sh[kPmMaxD];
+  const int m = blockIdx.x, tid = threadIdx.x;
+  const int nb = wr - 1;
+  for (int idx = tid; idx < wr * d * d; idx += blockDim.x) {
+    const int b = idx / (d * d), p = (idx / d) % d, q = idx % d;
+    wc[b][p][q] = W[(b * d + p) * d + q];  // W[0, b, p, q]: the a = 0 row of the (wl, wr, d, d) tensor
+  }
+  const double* xrow = x + (int64_t)m * d * r;
+  // one pad double per 16 entries: the digit loop reads 16 consecutive ri per thread (stride 17 doubles between the
+  // threads of a warp: conflict-free), the other loops read consecutive ri
+  const int rp = r + r / 16 + 1;
+  auto xi = [rp](int p, int ri) { return p * rp + ri + (ri >> 4); };
+  for (int idx = tid; idx < d * r; idx += blockDim.x) xs[xi(idx / r, idx % r)] = xrow[idx];
   __syncthreads();
-  const double shift = shift_dev ? *shift_dev : 0.0;
-  const int li0 = blockIdx.x * kAbsRows;
-  double rmx[kAbsRows][D];
+  // column maxima over (b, ri) for every q
+  double mx[kPmMaxD];
 #pragma unroll
-  for (int i = 0; i < kAbsRows; ++i)
+  for (int q = 0; q < kPmMaxD; ++q) mx[q] = 0.0;
+  for (int ri = tid; ri < r; ri += blockDim.x) {
+    double xv[kPmMaxD];
 #pragma unroll
-    for (int p = 0; p < D; ++p) rmx[i][p] = 0.0;
-  for (int s = tid; s < r; s += 256) {  // a thread owns every 256th column
-    double cmx[D];
+    for (int p = 0; p < kPmMaxD; ++p) xv[p] = p < d ? xs[xi(p, ri)] : 0.0;
+    for (int b = 0; b < nb; ++b)
 #pragma unroll
-    for (int p = 0; p < D; ++p) cmx[p] = 0.0;
+      for (int q = 0; q < kPmMaxD; ++q)
+        if (q < d) {
+          double v = 0.0;
 #pragma unroll
-    for (int i = 0; i < kAbsRows; ++i) {
-      const int li = li0 + i;
-      double xv[D];
-#pragma unroll
-      for (int p = 0; p < D; ++p) {
-        xv[p] = li < l ? x[((int64_t)li * d + p) * r + s] : 0.0;
-        cmx[p] = fmax(cmx[p], fabs(xv[p]));
-        rmx[i][p] = fmax(rmx[i][p], fabs(xv[p]));
-      }
-      if (y0 != nullptr && li >= row0 && li < row0 + lo) {
-#pragma unroll
-        for (int q = 0; q < D; ++q) {
-          double v = -shift * xv[q];
-#pragma unroll
-          for (int p = 0; p < D; ++p) v = fma(wlast[p][q], xv[p], v);
-          y0[((int64_t)(li - row0) * d + q) * r + s] = v;
+          for (int p = 0; p < kPmMaxD; ++p)
+            if (p < d) v = fma(wc[b][p][q], xv[p], v);
+          mx[q] = fmax(mx[q], fabs(v));
         }
-      }
-    }
-#pragma unroll
-    for (int p = 0; p < D; ++p)
-      if (cmx[p] > 0.0) atomicMax(&colmax[(int64_t)p * r + s], (unsigned long long)__double_as_longlong(cmx[p]));
   }
 #pragma unroll
-  for (int i = 0; i < kAbsRows; ++i)
-#pragma unroll
-    for (int p = 0; p < D; ++p) {
-      double v = rmx[i][p];
-      for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-      if ((tid & 31) == 0) red[i][p][tid >> 5] = v;
-    }
+  for (int q = 0; q < kPmMaxD; ++q) {
+    double v = mx[q];
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((tid & 31) == 0) red[q][tid >> 5] = v;
+  }
   __syncthreads();
-  if (tid < kAbsRows * d) {
-    const int i = tid / d, p = tid % d, li = li0 + i;
-    if (li >= row0 && li < row0 + lo) {
-      double v = 0.0;
-      for (int w8 = 0; w8 < 8; ++w8) v = fmax(v, red[i][p][w8]);
-      rowmax[(int64_t)(li - row0) * d + p] = v;
+  if (tid < d) {
+    double v = 0.0;
+    for (int w8 = 0; w8 < (int)(blockDim.x >> 5); ++w8) v = fmax(v, red[tid][w8]);
+    const double sc = oz_scale_of((unsigned long long)__double_as_longlong(v));
+    sc_sh[tid] = sc;
+    scale[(int64_t)tid * gridDim.x + m] = sc;  // columns are ordered (q, m): a tile of the GEMM then has one q
+    if (sc > 0.0) atomicAdd(sumsq, sc * sc);
+  }
+  __syncthreads();
+  // digits: a thread owns 16 consecutive ri of one (q, b) row piece; K = (b, ri), padded with zeros up to Kp
+  const int r16 = (r + 15) / 16;
+  for (int item = tid; item < d * nb * r16; item += blockDim.x) {
+    const int i16 = item % r16, b = (item / r16) % nb, q = item / (r16 * nb);
+    const double sc = sc_sh[q];
+    const double inv = sc > 0.0 ? 1.0 / sc : 0.0;
+    double cw[kPmMaxD];
+    bool any = false;
+#pragma unroll
+    for (int p = 0; p < kPmMaxD; ++p) {
+      cw[p] = p < d ? wc[b][p][q] * inv : 0.0;  // exact: inv is a power of two
+      any = any || (p < d && wc[b][p][q] != 0.0);
+    }
+    if (skip_zero_pieces && !any) continue;  // column q of W[0, b] vanishes: the GEMM skips this K range for block q
+    uint4 dig[kOzMaxSlices];
+    oz_digits16(
+        [&](int e) {
+          const int ri = 16 * i16 + e;
+          double v = 0.0;
+          if (ri < r) {
+#pragma unroll
+            for (int p = 0; p < kPmMaxD; ++p)
+              if (p < d) v = fma(cw[p], xs[xi(p, ri)], v);
+          }
+          return v;
+        },
+        dig);
+    const int64_t k0 = (int64_t)b * r + 16 * i16;
+    int8_t* row = slices + ((int64_t)q * gridDim.x + m) * Kp + k0;
+    const bool last_piece = (b == nb - 1) && (16 * i16 + 16 > r);  // runs into the zero padding: still inside Kp?
+    if (16 * i16 + 16 <= r || (last_piece && k0 + 16 <= Kp)) {
+      oz_store16(row, slice_stride, dig, (k0 & 15) == 0);
+    } else {
+      // ragged end of a piece that is followed by the next channel's bytes: store only the valid ones
+      const int valid = r - 16 * i16;
+#pragma unroll
+      for (int sl = 0; sl < kOzMaxSlices; ++sl) {
+        const uint32_t w[4] = {dig[sl].x, dig[sl].y, dig[sl].z, dig[sl].w};
+        for (int e = 0; e < valid; ++e) row[sl * slice_stride + e] = (int8_t)(w[e >> 2] >> (8 * (e & 3)));
+      }
+    }
+  }
+  // zero what is left of the K padding of this block's columns (Kp - nb * r < 64 bytes per row)
+  const int kreal = nb * r, kpad = (int)(Kp - kreal);
+  for (int item = tid; item < d * kOzMaxSlices * kpad; item += blockDim.x) {
+    const int e = item % kpad, sl = (item / kpad) % kOzMaxSlices, q = item / (kpad * kOzMaxSlices);
+    slices[sl * slice_stride + ((int64_t)q * gridDim.x + m) * Kp + kreal + e] = 0;
+  }
+  if (y0 != nullptr) {
+    const double shift = shift_dev ? *shift_dev : 0.0;
+    for (int idx = tid; idx < d * r; idx += blockDim.x) {
+      const int q = idx / r, ri = idx % r;
+      double v = -shift * xs[xi(q, ri)];
+      for (int p = 0; p < d; ++p) v = fma(wc[nb][p][q], xs[xi(p, ri)], v);
+      y0[(int64_t)m * d * r + idx] = v;
     }
   }
 }
 
-// A side: Xa[(b, ri), (q, m)] = sum_p W[0, b, p, q] x[m, p, ri] for b < wr - 1 -- for a fixed column the K index (b, ri)
-// runs over contiguous ri, so a thread reads 16 consecutive entries of the row x[m, p, :] per p and stores 16 digit
-// bytes per slice; a warp covers 512 consecutive ri.  x: the caller's lo rows.
-__global__ void __launch_bounds__(256) oz_premix_a_kernel(const double* __restrict__ x, const double* __restrict__ W,
-                                                          int lo, int r, int wr, int d, const double* __restrict__ rowmax,
-                                                          double* __restrict__ scale, double* __restrict__ sumsq,
-                                                          int8_t* __restrict__ slices, int64_t Kp, int64_t slice_stride,
-                                                          int skip_zero_pieces) {
-  __shared__ double wc[kPmMaxCh][kPmMaxD][kPmMaxD];  // [b][p][q] = W[0, b, p, q]
-  const int nb = wr - 1;
-  for (int idx = threadIdx.x; idx < nb * d * d; idx += blockDim.x) {
-    const int b = idx / (d * d), p = (idx / d) % d, q = idx % d;
-    wc[b][p][q] = W[(b * d + p) * d + q];
+// B side, column maxima: colmax[(q, s)] = max over (a, li) of |sum_p W[a + 1, wr - 1, p, q] x[li, p, s]|
+__global__ void __launch_bounds__(256) oz_premix_b_colmax_kernel(const double* __restrict__ x,
+                                                                 const double* __restrict__ W, int l, int r, int wl,
+                                                                 int wr, int d, int l_chunk,
+                                                                 unsigned long long* __restrict__ colmax) {
+  __shared__ double wc[kPmMaxCh][kPmMaxD][kPmMaxD];  // [a][p][q] = W[a + 1, wr - 1, p, q]
+  const int na = wl - 1;
+  for (int idx = threadIdx.x; idx < na * d * d; idx += blockDim.x) {
+    const int a = idx / (d * d), p = (idx / d) % d, q = idx % d;
+    wc[a][p][q] = W[((((int64_t)(a + 1)) * wr + (wr - 1)) * d + p) * d + q];
   }
   __syncthreads();
-  const int r16 = (r + 15) / 16;
-  const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (item >= (int64_t)lo * d * nb * r16) return;
-  const int i16 = (int)(item % r16), b = (int)((item / r16) % nb), q = (int)((item / ((int64_t)r16 * nb)) % d),
-            m = (int)(item / ((int64_t)r16 * nb * d));
-  // scale of column (q, m): bound over the channels of sum_p |W[0, b', p, q]| max_ri |x[m, p, ri]|
-  double bound = 0.0;
-  for (int bb = 0; bb < nb; ++bb) {
-    double v = 0.0;
-    for (int p = 0; p < d; ++p) v = fma(fabs(wc[bb][p][q]), rowmax[(int64_t)m * d + p], v);
-    bound = fmax(bound, v);
-  }
-  const double sc = oz_scale_of((unsigned long long)__double_as_longlong(bound));
-  const double inv = sc > 0.0 ? 1.0 / sc : 0.0;
-  const int64_t col = (int64_t)q * lo + m;  // columns are ordered (q, m): a tile of the GEMM then has one q
-  if (b == 0 && i16 == 0) {
-    scale[col] = sc;
-    if (sc > 0.0) atomicAdd(sumsq, sc * sc);
-    const int kreal = nb * r;  // zero what is left of the K padding of this column (< 64 bytes per slice)
-    for (int64_t k = kreal; k < Kp; ++k)
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= r) return;
+  const int l0 = blockIdx.y * l_chunk, l1 = min(l, l0 + l_chunk);
+  double mx[kPmMaxD];
 #pragma unroll
-      for (int sl = 0; sl < kOzMaxSlices; ++sl) slices[sl * slice_stride + col * Kp + k] = 0;
-  }
-  double cw[kPmMaxD];
-  bool any = false;
+  for (int q = 0; q < kPmMaxD; ++q) mx[q] = 0.0;
+#pragma unroll 4
+  for (int li = l0; li < l1; ++li) {
+    double xv[kPmMaxD];
 #pragma unroll
-  for (int p = 0; p < kPmMaxD; ++p) {
-    cw[p] = p < d ? wc[b][p][q] * inv : 0.0;  // exact: inv is a power of two
-    any = any || (p < d && wc[b][p][q] != 0.0);
-  }
-  if (skip_zero_pieces && !any) return;  // column q of W[0, b] vanishes: the GEMM skips this K range for block q
-  const double* xrow = x + (int64_t)m * d * r;
-  const int ri0 = 16 * i16;
-  uint4 dig[kOzMaxSlices];
-  oz_digits16(
-      [&](int e) {
-        const int ri = ri0 + e;
-        double v = 0.0;
-        if (ri < r) {
+    for (int p = 0; p < kPmMaxD; ++p) xv[p] = p < d ? x[((int64_t)li * d + p) * r + s] : 0.0;
+    for (int a = 0; a < na; ++a)
+#pragma unroll
+      for (int q = 0; q < kPmMaxD; ++q)
+        if (q < d) {
+          double v = 0.0;
 #pragma unroll
           for (int p = 0; p < kPmMaxD; ++p)
-            if (p < d) v = fma(cw[p], xrow[(int64_t)p * r + ri], v);
+            if (p < d) v = fma(wc[a][p][q], xv[p], v);
+          mx[q] = fmax(mx[q], fabs(v));
         }
-        return v;
-      },
-      dig);
-  const int64_t k0 = (int64_t)b * r + ri0;
-  int8_t* row = slices + col * Kp + k0;
-  if (ri0 + 16 <= r) {
-    oz_store16(row, slice_stride, dig, (k0 & 15) == 0);
-  } else {  // ragged end of a piece: only the valid bytes (the next channel's bytes follow)
-    const int valid = r - ri0;
-#pragma unroll
-    for (int sl = 0; sl < kOzMaxSlices; ++sl) {
-      const uint32_t w[4] = {dig[sl].x, dig[sl].y, dig[sl].z, dig[sl].w};
-      for (int e = 0; e < valid; ++e) row[sl * slice_stride + e] = (int8_t)(w[e >> 2] >> (8 * (e & 3)));
-    }
   }
+#pragma unroll
+  for (int q = 0; q < kPmMaxD; ++q)
+    if (q < d && mx[q] > 0.0) atomicMax(&colmax[(int64_t)q * r + s], (unsigned long long)__double_as_longlong(mx[q]));
 }
 
 // B side, digits: Xb[(a, li), (q, s)] for a < wl - 1.  Block = 32 values of s x 8 chunks of 16 li: the x loads are
-// coalesced along s, a thread keeps its 16 x d entries of x in registers and forms every (a, q) product from them;
-// the digits of a 32 x 128 tile are staged in shared memory and leave as whole 128-byte lines.  colmax: max_li |x|.
+// coalesced along s, a thread keeps its 16 x d entries of x in registers and forms every (a, q) product from them,
+// each one leaving as 16 consecutive bytes of the (slice, column (q, s)) rows.
 template <int D>
 __global__ void __launch_bounds__(256, D <= 2 ? 2 : 1) oz_premix_b_kernel(const double* __restrict__ x, const double* __restrict__ W,
                                                           int l, int r, int wl, int wr,
@@ -326,27 +337,14 @@ __global__ void __launch_bounds__(256, D <= 2 ? 2 : 1) oz_premix_b_kernel(const 
     const int a = idx / (d * d), p = (idx / d) % d, q = idx % d;
     wc[a][p][q] = W[((((int64_t)(a + 1)) * wr + (wr - 1)) * d + p) * d + q];
   }
-  __syncthreads();
   const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
   const int s = blockIdx.x * 32 + tx;
   const int l0 = (blockIdx.y * 8 + ty) * 16;
   double sc[D], inv[D];
-  {
-    double cm[D];
 #pragma unroll
-    for (int p = 0; p < D; ++p) cm[p] = s < r ? __longlong_as_double((long long)colmax[(int64_t)p * r + s]) : 0.0;
-#pragma unroll
-    for (int q = 0; q < D; ++q) {
-      double bound = 0.0;
-      for (int a = 0; a < na; ++a) {
-        double v = 0.0;
-#pragma unroll
-        for (int p = 0; p < D; ++p) v = fma(fabs(wc[a][p][q]), cm[p], v);
-        bound = fmax(bound, v);
-      }
-      sc[q] = oz_scale_of((unsigned long long)__double_as_longlong(bound));
-      inv[q] = sc[q] > 0.0 ? 1.0 / sc[q] : 0.0;
-    }
+  for (int q = 0; q < D; ++q) {
+    sc[q] = s < r ? oz_scale_of(colmax[(int64_t)q * r + s]) : 0.0;
+    inv[q] = sc[q] > 0.0 ? 1.0 / sc[q] : 0.0;
   }
   if (blockIdx.y == 0 && ty == 0) {
     double part = 0.0;
@@ -359,6 +357,7 @@ __global__ void __launch_bounds__(256, D <= 2 ? 2 : 1) oz_premix_b_kernel(const 
     if (tx == 0 && part > 0.0) atomicAdd(sumsq, part);
   }
   __shared__ __align__(16) OzSliceTile tile;
+  __syncthreads();
   double xv[16][D];
 #pragma unroll
   for (int e = 0; e < 16; ++e)
@@ -860,37 +859,42 @@ int oz_slice_operand(const double* P, int64_t ld, OzRowMap rows, const OzOperand
 static bool premix_dims_ok(int r, int wl, int wr, int d) {
   return d <= kPmMaxD && wl - 1 <= kPmMaxCh && wr <= kPmMaxCh && wl >= 2 && wr >= 2;
 }
-bool oz_premix_applicable(int l, int r, int wl, int wr, int d) { return premix_dims_ok(r, wl, wr, d) && l >= 1; }
+// padded row length of the x row staged by oz_premix_a_kernel (one extra double per 16: conflict-free 16-strided reads)
+static size_t premix_a_smem(int r, int d) { return sizeof(double) * (size_t)d * (r + r / 16 + 1); }
 
-int oz_premix(const double* x, int row0, const double* W, int l, int lo, int r, int wl, int wr, int d, const OzOperand& xa,
-              const OzOperand& xb, double* y0, const double* shift_dev, bool skip_a, bool skip_b, cudaStream_t stream) {
+bool oz_premix_applicable(int l, int r, int wl, int wr, int d) {
+  return premix_dims_ok(r, wl, wr, d) && premix_a_smem(r, d) <= 200 * 1024 && l >= 1;
+}
+
+int oz_premix_a(const double* x, const double* W, int l, int r, int wl, int wr, int d, const OzOperand& op, double* y0,
+                const double* shift_dev, bool skip_zero_pieces, cudaStream_t stream) {
   TNPY_CHECK_ARG(oz_premix_applicable(l, r, wl, wr, d), "dimensions outside the direct path's limits");
-  TNPY_CHECK_ARG(xa.cols == lo * d && xa.K == (wr - 1) * r && xb.cols == d * r && xb.K == (wl - 1) * l, "operand shape mismatch");
-  // the operands' colmax scratch holds the |x| maxima: rows of the caller's block (A side, as doubles), columns (B side)
-  double* rowmax = reinterpret_cast<double*>(xa.colmax);
-  TNPY_CUDA_OK(cudaMemsetAsync(xa.sumsq, 0, sizeof(double), stream));
-  TNPY_CUDA_OK(cudaMemsetAsync(xb.colmax, 0, sizeof(unsigned long long) * (size_t)(xb.cols + 1), stream));
-  const int ablocks = ceil_div(l, kAbsRows);
-  switch (d) {
-    case 1: oz_absmax_kernel<1><<<ablocks, 256, 0, stream>>>(x, W, l, r, wr, row0, lo, rowmax, xb.colmax, y0, shift_dev); break;
-    case 2: oz_absmax_kernel<2><<<ablocks, 256, 0, stream>>>(x, W, l, r, wr, row0, lo, rowmax, xb.colmax, y0, shift_dev); break;
-    case 3: oz_absmax_kernel<3><<<ablocks, 256, 0, stream>>>(x, W, l, r, wr, row0, lo, rowmax, xb.colmax, y0, shift_dev); break;
-    default: oz_absmax_kernel<4><<<ablocks, 256, 0, stream>>>(x, W, l, r, wr, row0, lo, rowmax, xb.colmax, y0, shift_dev); break;
-  }
+  TNPY_CHECK_ARG(op.cols == l * d && op.K == (wr - 1) * r, "operand shape mismatch");
+  TNPY_TRY(set_max_dynamic_smem(oz_premix_a_kernel, 200 * 1024));
+  TNPY_CUDA_OK(cudaMemsetAsync(op.sumsq, 0, sizeof(double), stream));
+  oz_premix_a_kernel<<<l, 256, premix_a_smem(r, d), stream>>>(x, W, r, wr, d, op.scale, op.sumsq, op.slices, op.Kp,
+                                                             (int64_t)op.cols * op.Kp, y0, shift_dev, skip_zero_pieces ? 1 : 0);
   TNPY_LAUNCH_OK();
-  const int64_t items = (int64_t)lo * d * (wr - 1) * ((r + 15) / 16);
-  oz_premix_a_kernel<<<(unsigned)((items + 255) / 256), 256, 0, stream>>>(x + (int64_t)row0 * d * r, W, lo, r, wr, d, rowmax,
-                                                                         xa.scale, xa.sumsq, xa.slices, xa.Kp,
-                                                                         (int64_t)xa.cols * xa.Kp, skip_a ? 1 : 0);
+  return TNPY_OK;
+}
+
+int oz_premix_b(const double* x, const double* W, int l, int r, int wl, int wr, int d, const OzOperand& op,
+                bool skip_zero_pieces, cudaStream_t stream) {
+  TNPY_CHECK_ARG(oz_premix_applicable(l, r, wl, wr, d), "dimensions outside the direct path's limits");
+  TNPY_CHECK_ARG(op.cols == d * r && op.K == (wl - 1) * l, "operand shape mismatch");
+  TNPY_CUDA_OK(cudaMemsetAsync(op.colmax, 0, sizeof(unsigned long long) * (size_t)(op.cols + 1), stream));
+  const int l_chunk = l > 4096 ? 128 : 32;
+  oz_premix_b_colmax_kernel<<<dim3(ceil_div(r, 256), ceil_div(l, l_chunk)), 256, 0, stream>>>(x, W, l, r, wl, wr, d,
+                                                                                             l_chunk, op.colmax);
   TNPY_LAUNCH_OK();
   const dim3 grid(ceil_div(r, 32), ceil_div(l, 128));
-  const int64_t stride = (int64_t)xb.cols * xb.Kp;
-  const int skip = skip_b ? 1 : 0;
+  const int64_t stride = (int64_t)op.cols * op.Kp;
+  const int skip = skip_zero_pieces ? 1 : 0;
   switch (d) {
-    case 1: oz_premix_b_kernel<1><<<grid, 256, 0, stream>>>(x, W, l, r, wl, wr, xb.colmax, xb.scale, xb.sumsq, xb.slices, xb.Kp, stride, skip); break;
-    case 2: oz_premix_b_kernel<2><<<grid, 256, 0, stream>>>(x, W, l, r, wl, wr, xb.colmax, xb.scale, xb.sumsq, xb.slices, xb.Kp, stride, skip); break;
-    case 3: oz_premix_b_kernel<3><<<grid, 256, 0, stream>>>(x, W, l, r, wl, wr, xb.colmax, xb.scale, xb.sumsq, xb.slices, xb.Kp, stride, skip); break;
-    default: oz_premix_b_kernel<4><<<grid, 256, 0, stream>>>(x, W, l, r, wl, wr, xb.colmax, xb.scale, xb.sumsq, xb.slices, xb.Kp, stride, skip); break;
+    case 1: oz_premix_b_kernel<1><<<grid, 256, 0, stream>>>(x, W, l, r, wl, wr, op.colmax, op.scale, op.sumsq, op.slices, op.Kp, stride, skip); break;
+    case 2: oz_premix_b_kernel<2><<<grid, 256, 0, stream>>>(x, W, l, r, wl, wr, op.colmax, op.scale, op.sumsq, op.slices, op.Kp, stride, skip); break;
+    case 3: oz_premix_b_kernel<3><<<grid, 256, 0, stream>>>(x, W, l, r, wl, wr, op.colmax, op.scale, op.sumsq, op.slices, op.Kp, stride, skip); break;
+    default: oz_premix_b_kernel<4><<<grid, 256, 0, stream>>>(x, W, l, r, wl, wr, op.colmax, op.scale, op.sumsq, op.slices, op.Kp, stride, skip); break;
   }
   TNPY_LAUNCH_OK();
   return TNPY_OK;

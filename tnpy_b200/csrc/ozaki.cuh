@@ -68,10 +68,11 @@ int ozaki_slices();
 constexpr int kPmMaxD = 4;    // physical dimension limit of the premix kernels
 constexpr int kPmMaxCh = 16;  // MPO bond limit of the premix kernels
 bool oz_premix_applicable(int l, int r, int wl, int wr, int d);
-// x: the full vector (l, d, r); the caller holds rows [row0, row0 + lo) (A side and y0 cover those, the B side all l).
-// skip_a / skip_b: do not write the (channel, q) pieces whose MPO block column vanishes -- only when the GEMM that
+// skip_zero_pieces: do not write the (channel, q) pieces whose MPO block column vanishes -- only when the GEMM that
 // consumes the operand is told to skip those K ranges (OzKSkip), their bytes are then never read.
-int oz_premix(const double* x, int row0, const double* W, int l, int lo, int r, int wl, int wr, int d, const OzOperand& xa,
-              const OzOperand& xb, double* y0, const double* shift_dev, bool skip_a, bool skip_b, cudaStream_t stream);
+int oz_premix_a(const double* x, const double* W, int l, int r, int wl, int wr, int d, const OzOperand& op, double* y0,
+                const double* shift_dev, bool skip_zero_pieces, cudaStream_t stream);
+int oz_premix_b(const double* x, const double* W, int l, int r, int wl, int wr, int d, const OzOperand& op,
+                bool skip_zero_pieces, cudaStream_t stream);
 
 }  // namespace tnpy
