@@ -220,12 +220,17 @@ int tnpy_eig_lowest(const double* L, const double* W, const double* R, double* p
  * relation H V_m = V_m T + beta v_{m+1} e_m^T:  H psi = theta psi + (beta s_m) v_{m+1}  (equal to a fresh
  * tnpy_heff_apply(psi) to rounding).  FiniteDMRG.perturb_wave_function (finite_dmrg.py:116-141), which the
  * sweep calls right after the solve, needs exactly that vector. */
-/* Diagnostics of the calling thread's last tnpy_eig_lowest* call: matvecs, looks (status read-backs = stream
- * synchronisations), extra full Gram-Schmidt passes the DGKS test asked for, thick restarts.  Returns how many were written. */
-int tnpy_last_eig_counters(int64_t* out, int n);
 int tnpy_eig_lowest_image(const double* L, const double* W, const double* R, double* psi, double* hpsi,
                           int l, int r, int wl, int wr, int d, int flags, double tol, int max_matvec, int ncv,
                           double* stats_host, void* workspace, size_t workspace_bytes, void* stream);
+/* Diagnostics of the calling thread's last tnpy_eig_lowest* call: matvecs, looks (status read-backs = stream
+ * synchronisations), extra full Gram-Schmidt passes the DGKS test asked for, thick restarts.  Returns how many were written. */
+int tnpy_last_eig_counters(int64_t* out, int n);
+/* Small sites (vectors of <= 32768 elements on the FP64 chain) run whole Lanczos steps -- matvec, two Gram-Schmidt
+ * passes, normalisation, the new column of T -- in one cooperative launch, `stride` steps per launch, instead of
+ * ~15 launches per step (csrc/lanczos_steps.cu).  on = 0 keeps every site on the general multi-kernel solver (also:
+ * environment TNPY_FUSED_STEPS=0).  Returns the previous setting. */
+int tnpy_set_fused_steps(int on);
 
 /* ---- chi-sharded local solve over the GPUs of one box (BASELINE configs[4]) -------------------
  * One process per GPU.  A communicator wraps an NCCL communicator that the library creates itself (libnccl.so.2 is

@@ -87,7 +87,20 @@ def main():
         out["gpu_sweep_s"] = per_sweep
         out["gpu_matvecs_last_sweep"] = sum(s.get("n_matvec", 0) for s in gpu.solver_stats)
     else:
+        totals = {"n_matvec": 0, "looks": 0, "sweeps": 0}
+        plain_sweep = gpu.sweep
+
+        def counted_sweep(*a, **k):
+            energy = plain_sweep(*a, **k)
+            totals["n_matvec"] += sum(s.get("n_matvec", 0) for s in gpu.solver_stats)
+            totals["looks"] += sum(s.get("looks", 0) for s in gpu.solver_stats)
+            totals["sweeps"] += 1
+            return energy
+
+        gpu.sweep = counted_sweep
         e_gpu = gpu.run(**kw)
+        out["gpu_totals"] = totals
+        out["gpu_phase_s"] = dict(gpu.phase_seconds)  # synchronised per-phase wall seconds, summed over the run
     torch.cuda.synchronize()
     out["gpu_wall_s"] = time.perf_counter() - t0
     out["gpu_energies"] = e_gpu

@@ -273,6 +273,60 @@ def test_eig_lowest_image_is_heff_of_psi(cu, ncv, max_matvec, tol):
     assert abs(float(r.norm()) - stats["resid"]) <= 1e-10 * stats["anorm"]
 
 
+@pytest.mark.parametrize("n_sites,chi,site,model", [(10, 16, 4, "xxz"), (12, 24, 6, "thirring"), (14, 60, 7, "xxz"),
+                                                     (12, 33, 1, "xxz"), (16, 128, 8, "thirring")])
+@pytest.mark.parametrize("ncv", [0, 6])
+def test_fused_small_site_steps_match_the_general_solver(cu, n_sites, chi, site, model, ncv):
+    """Small sites run whole Lanczos steps in one cooperative launch (csrc/lanczos_steps.cu): same eigenvalue and
+    eigenvector as the general multi-kernel solver on the same start vector, the image still equal to a fresh
+    matvec, far fewer launches; edge-of-chain shapes (left bond 2), restarts (ncv = 6), the longest vector the path
+    takes (chi = 128: 32768 elements), and bit-identical results on repetition."""
+    env, mpo, mps = canonical_problem(n_sites, chi, site, model=model, seed=5)
+    L, W, R = dev(env.left[site]), dev(mpo[site]), dev(env.right[site])
+    start = np.random.default_rng(2).standard_normal(mps[site].shape)
+    out = {}
+    for fused in (True, False):
+        previous = cu.set_fused_steps(fused)
+        try:
+            psi = dev(start)
+            image = torch.empty_like(psi)
+            before = cu.launch_count()
+            stats = cu.eig_lowest(L, W, R, psi, tol=1e-10, ncv=ncv, max_matvec=4000, image=image)
+            out[fused] = (stats, psi, image, cu.launch_count() - before)
+        finally:
+            cu.set_fused_steps(previous)
+    (sf, pf, imf, lf), (sg, pg, img, lg) = out[True], out[False]
+    assert sf["converged"] and sg["converged"]
+    assert sf["heff_mode"] == cu.HEFF_FP64_CHAIN
+    anorm = sg["anorm"]
+    assert abs(sf["theta"] - sg["theta"]) <= 1e-11 * anorm
+    # residuals at 1e-10 ||A||: the eigenvectors agree to that divided by the gap; compare through the overlap
+    assert abs(abs(float((pf * pg).sum())) - 1.0) <= 1e-8
+    fresh = cu.heff_apply(L, W, R, pf)
+    assert float((imf - fresh).abs().max()) <= 1e-12 * max(float(fresh.abs().max()), anorm)
+    r = fresh - sf["theta"] * pf
+    assert float(r.norm()) <= 1e-10 * anorm * 1.01
+    assert abs(float(r.norm()) - sf["resid"]) <= 1e-10 * anorm
+    if sg["n_matvec"] >= 20:
+        assert lf * 3 < lg, (lf, lg)
+    # deterministic
+    psi2 = dev(start)
+    cu.eig_lowest(L, W, R, psi2, tol=1e-10, ncv=ncv, max_matvec=4000)
+    assert torch.equal(psi2, pf)
+
+
+def test_fused_steps_handle_a_vector_shorter_than_the_basis(cu):
+    """N = 8 unknowns: the Krylov space is exhausted (exact breakdown or m == N) before the basis is full."""
+    env, mpo, mps = canonical_problem(8, 2, 4, seed=1)
+    site = 4
+    H = env.one_site_full_matrix(site)
+    evals = np.linalg.eigvalsh(0.5 * (H + H.T))
+    psi = dev(np.random.default_rng(3).standard_normal(mps[site].shape))
+    stats = cu.eig_lowest(dev(env.left[site]), dev(mpo[site]), dev(env.right[site]), psi, tol=1e-12)
+    assert stats["converged"]
+    assert abs(stats["theta"] - evals[0]) <= 1e-12 * abs(evals).max()
+
+
 @pytest.mark.parametrize("n", [4, 16, 64, 100, 199])
 def test_eigh_lowest(cu, n):
     rng = np.random.default_rng(n)

@@ -31,6 +31,7 @@ SIGNATURES = {
     "tnpy_gemm_tn": (c_int, [_PD, c_int64, _PD, c_int64, _PD, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "tnpy_ozaki_workspace_bytes": (c_size_t, [c_int] * 4),
     "tnpy_set_ozaki_slices": (c_int, [c_int]),
+    "tnpy_set_fused_steps": (c_int, [c_int]),
     "tnpy_ozaki_gemm_tn": (
         c_int,
         [_PD, c_int64, _PD, c_int64, _PD, c_int64] + [c_int] * 6 + [c_void_p, c_size_t, c_void_p],
@@ -162,6 +163,12 @@ def set_gemm_algo(algo: int) -> None:
 
 def set_ozaki_slices(slices: int) -> None:
     check(load().tnpy_set_ozaki_slices(int(slices)), "tnpy_set_ozaki_slices")
+
+
+def set_fused_steps(on: bool) -> bool:
+    """Small sites run whole Lanczos steps in one cooperative launch (csrc/lanczos_steps.cu); False keeps every
+    site on the general multi-kernel eigensolver.  Returns the previous setting."""
+    return bool(load().tnpy_set_fused_steps(1 if on else 0))
 
 
 HEFF_FP64_CHAIN, HEFF_OZ_CHAIN, HEFF_OZ_DIRECT = 0, 1, 2

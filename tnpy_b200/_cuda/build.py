@@ -19,7 +19,7 @@ CSRC = HERE.parent / "csrc"
 INCLUDE = HERE.parent.parent / "include"
 LIB = HERE / "libtnpy_cuda.so"
 OBJ_DIR = HERE / "build"
-SOURCES = ["lib.cu", "gemm_tn.cu", "contract.cu", "blas1.cu", "lanczos.cu", "svd.cu", "qr.cu", "geig.cu", "ozaki.cu", "comm.cu", "probe.cu"]
+SOURCES = ["lib.cu", "gemm_tn.cu", "contract.cu", "blas1.cu", "lanczos.cu", "lanczos_steps.cu", "svd.cu", "qr.cu", "geig.cu", "ozaki.cu", "comm.cu", "probe.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

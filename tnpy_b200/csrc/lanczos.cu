@@ -11,6 +11,7 @@
 
 #include "comm.cuh"
 #include "heff.cuh"
+#include "lanczos_steps.cuh"
 
 namespace tnpy {
 
@@ -25,13 +26,14 @@ int combine(const double* V, int64_t ldv, int m, const double* c, int64_t ldc_, 
             int64_t n, cudaStream_t stream);
 
 constexpr int kMaxNcv = 48;
+static_assert(kMaxNcv == kStepsMaxNcv, "the fused small-site steps write T with this leading dimension");
 // leading dimension of the shared-memory matrices of the Ritz solve: odd, so that a column walk (the A <- A J phase
 // of the Jacobi rounds, consecutive threads on consecutive rows) is spread over the banks.  With the natural 48 every
 // row of a column sits in the same bank and a 30 x 30 Ritz problem took 1.5 ms (profiles/r02_launches_*).
 constexpr int kRitzLd = kMaxNcv + 1;
 
 // status record (device and pinned host mirror)
-enum { ST_THETA = 0, ST_RESID = 1, ST_ANORM = 2, ST_DONE = 3, ST_BETA = 4, ST_RCOEF = 5, ST_BOUND = 6, ST_EXTRA = 7, ST_SIZE = 8 };
+enum { ST_THETA = 0, ST_RESID = 1, ST_ANORM = 2, ST_DONE = 3, ST_BETA = 4, ST_RCOEF = 5, ST_BOUND = 6, ST_EXTRA = 7, ST_STEPS = 8, ST_SIZE = 9 };
 
 // Symmetric eigen-decomposition of the m x m matrix held in shared memory `a` (leading dim kMaxNcv)
 // by parallel cyclic Jacobi (round-robin pair ordering).  Eigenvectors accumulate in `z` (columns).
@@ -129,19 +131,22 @@ __device__ void jacobi_eig_smem(double (*a)[kRitzLd], double (*z)[kRitzLd], int 
 
 // After Lanczos step j: fold h (+ h2) into column j of T, solve the (j+1) x (j+1) Ritz problem, write
 // status, the sorted Ritz values `thetas` and the sorted Ritz coefficient matrix S (column i = i-th lowest).
+// h == nullptr: T is complete already (the fused small-site steps write their columns themselves) and the last step
+// done is j + *steps_done - 1, j being the first step of that launch.
 __global__ void __launch_bounds__(256) ritz_kernel(double* __restrict__ T, const double* __restrict__ h,
                                                    const double* __restrict__ h2, const double* __restrict__ h_local,
                                                    int local_from, const double* __restrict__ beta_dev,
                                                    int j, double tol, double* __restrict__ S,
                                                    double* __restrict__ thetas, double* __restrict__ status,
-                                                   int fold_only) {
+                                                   int fold_only, const double* __restrict__ steps_done = nullptr) {
   __shared__ double a[kMaxNcv][kRitzLd];
   __shared__ double z[kMaxNcv][kRitzLd];
   __shared__ double cs[kMaxNcv], sn[kMaxNcv], red[72];
   __shared__ int pp[kMaxNcv], qq[kMaxNcv], order[kMaxNcv];
+  if (steps_done) j += (int)*steps_done - 1;
   const int m = j + 1;
   const int tid = threadIdx.x;
-  if (tid < m) {
+  if (h != nullptr && tid < m) {
     // column j of T = V^T H V: the local pass (vectors local_from .. j) plus the full pass(es)
     const double v = h[tid] + (h2 ? h2[tid] : 0.0) + (tid >= local_from ? h_local[tid - local_from] : 0.0);
     T[tid * kMaxNcv + j] = v;
@@ -256,7 +261,12 @@ extern "C" size_t tnpy_eig_workspace_bytes(int l, int r, int wl, int wr, int d, 
   int ncv, keep;
   const int64_t n = (int64_t)l * d * r;
   pick_sizes(n, ncv_in, ncv, keep);
-  return eig_ws_layout(n, ncv, keep, heff_plan_bytes(l, l, r, wl, wr, d) + heff_apply_bytes(l, l, r, wl, wr, d) + 1024);
+  size_t apply = heff_apply_bytes(l, l, r, wl, wr, d);
+  if (lanczos_steps_supported(l, r, wl, wr, d)) {
+    const size_t fused = lanczos_steps_plan(l, r, wl, wr, d).bytes;
+    if (fused > apply) apply = fused;  // the fused small-site steps use the chain's part of the workspace instead
+  }
+  return eig_ws_layout(n, ncv, keep, heff_plan_bytes(l, l, r, wl, wr, d) + apply + 1024);
 }
 
 // comm == nullptr: the whole problem on this GPU (lo == l, row0 == 0).  Otherwise rank g of the communicator holds
@@ -329,6 +339,15 @@ static int eig_lowest_impl(const tnpy_comm* comm, const double* L, const double*
   }
   int slices = (tol >= 1e-10 && ozaki_slices() == 8) ? 7 : ozaki_slices();
   const size_t chain_off = ws.used;
+  // Small sites: whole steps in one cooperative launch (csrc/lanczos_steps.cu); the host then only launches the
+  // Ritz solve and reads the status record every `stride` steps.
+  bool fused = !comm && plan.mode == HEFF_FP64_CHAIN && lanczos_steps_supported(l, r, wl, wr, d);
+  LanczosStepsPlan steps_plan{};
+  if (fused) {
+    steps_plan = lanczos_steps_plan(l, r, wl, wr, d);
+    // a workspace sized while the fused path was switched off only holds the general solver's scratch
+    if (workspace_bytes < chain_off + steps_plan.bytes) fused = false;
+  }
   // global norm of the vector whose local norm multi_dot / multi_axpy just left in *local (see the kernels above)
   double* sq = status + 40;
   auto reduce_norm = [&](const double* local, double* norm, const int* skip) -> int {
@@ -369,6 +388,28 @@ static int eig_lowest_impl(const tnpy_comm* comm, const double* L, const double*
   int last_look_matvec = 0;
   int since_check = 0, stride = 1;
   while (true) {
+    int m;  // size of the Ritz problem looked at below
+    if (fused) {
+      int nsteps = stride < 1 ? 1 : stride;
+      if (nsteps > ncv - j) nsteps = ncv - j;
+      if (nsteps > max_matvec - n_matvec) nsteps = max_matvec - n_matvec;
+      if ((int64_t)nsteps > n_full - j) nsteps = (int)(n_full - j);
+      if (nsteps < 1) nsteps = 1;
+      TNPY_TRY(lanczos_steps_launch(steps_plan, plan.L, plan.W, plan.R, V, ldv, T, status, ST_BETA, ST_STEPS, l, r, wl, wr, d, j, nsteps,
+                                    static_cast<char*>(workspace) + chain_off, stream));
+      ritz_kernel<<<1, 256, 0, stream>>>(T, nullptr, nullptr, nullptr, 0, status + ST_BETA, j, tol, S, thetas, status, 0,
+                                         status + ST_STEPS);
+      TNPY_LAUNCH_OK();
+      ++n_looks;
+      TNPY_CUDA_OK(cudaMemcpyAsync(hst, status, sizeof(double) * ST_SIZE, cudaMemcpyDeviceToHost, stream));
+      TNPY_CUDA_OK(cudaStreamSynchronize(stream));
+      const int steps_done = (int)hst[ST_STEPS];  // fewer than asked only after an exact breakdown
+      n_matvec += steps_done;
+      j += steps_done - 1;
+      m = j + 1;
+      goto looked;
+    }
+    {
     double* vj = V + (int64_t)j * ldv;
     double* w = V + (int64_t)(j + 1) * ldv;
     Workspace chain(static_cast<char*>(workspace) + chain_off, workspace_bytes - chain_off);
@@ -401,7 +442,7 @@ static int eig_lowest_impl(const tnpy_comm* comm, const double* L, const double*
     TNPY_TRY(reduce(h2, j + 1));  // skipped pass: the decision kernel zeroed h2 on every rank
     TNPY_TRY(multi_axpy(V, ldv, j + 1, h2, w, n, local_norm, stream, skip2));
     TNPY_TRY(reduce_norm(local_norm, status + ST_BETA, skip2));
-    const int m = j + 1;
+    m = j + 1;
     ++since_check;
     const bool look = m == ncv || n_matvec >= max_matvec || m >= n_full || since_check >= stride;
     ritz_kernel<<<1, 256, 0, stream>>>(T, h, h2, h_local, local_from, status + ST_BETA, j, tol, S, thetas, status, look ? 0 : 1);
@@ -417,6 +458,8 @@ static int eig_lowest_impl(const tnpy_comm* comm, const double* L, const double*
       TNPY_CUDA_OK(cudaMemcpyAsync(status + ST_BOUND, plan.bound, sizeof(double), cudaMemcpyDeviceToDevice, stream));
     TNPY_CUDA_OK(cudaMemcpyAsync(hst, status, sizeof(double) * ST_SIZE, cudaMemcpyDeviceToHost, stream));
     TNPY_CUDA_OK(cudaStreamSynchronize(stream));
+    }
+  looked:
     // ||A|| for this test: the largest |Ritz value| or Lanczos coefficient seen so far (a lower bound of ||A|| that
     // is already tight after a few steps; the very first Ritz values of a random start can be near zero)
     anorm_seen = fmax(anorm_seen, fmax(hst[ST_ANORM], hst[ST_BETA]));

@@ -1,0 +1,31 @@
+// Small sites: several whole Lanczos steps (matvec chain + two Gram-Schmidt passes + normalisation + the new column
+// of T) in ONE cooperative launch (csrc/lanczos_steps.cu).  Used by the eigensolver (csrc/lanczos.cu) when the vector
+// is short enough that a step is bound by kernel latencies, not by arithmetic or bandwidth.
+#pragma once
+#include "common.cuh"
+
+namespace tnpy {
+
+constexpr int kStepsMaxNcv = 48;  // == kMaxNcv of lanczos.cu: leading dimension of T, longest basis
+
+struct LanczosStepsPlan {
+  int grid;     // CTAs of the cooperative launch (<= SM count)
+  int chunk;    // vector elements owned by one CTA (<= 256)
+  int ksplit;   // the second GEMM's K range is cut into `ksplit` pieces of `kchunk` rows
+  int kchunk;
+  size_t bytes; // scratch the launch needs from the caller's workspace
+};
+
+// true when this site runs on the fused path: full (unsharded) problem, FP64, short vectors, small MPO tensor
+bool lanczos_steps_supported(int l, int r, int wl, int wr, int d);
+LanczosStepsPlan lanczos_steps_plan(int l, int r, int wl, int wr, int d);
+
+// Runs Lanczos steps j0 .. j0 + nsteps - 1 on the basis V (column j at V + j * ldv; V[j0] normalised): for each step
+// w = H_eff v_j, two classical Gram-Schmidt passes against V[0..j], T[:, j] = T[j, :] = the summed coefficients,
+// V[j + 1] = w / ||w||.  status[beta_slot] = the last ||w||, status[steps_slot] = steps done (fewer than nsteps only
+// after an exact breakdown ||w|| == 0).  `scratch` holds plan.bytes.
+int lanczos_steps_launch(const LanczosStepsPlan& plan, const double* L, const double* W, const double* R, double* V,
+                         int64_t ldv, double* T, double* status, int beta_slot, int steps_slot, int l, int r, int wl,
+                         int wr, int d, int j0, int nsteps, void* scratch, cudaStream_t stream);
+
+}  // namespace tnpy
