@@ -231,6 +231,11 @@ int tnpy_last_eig_counters(int64_t* out, int n);
  * ~15 launches per step (csrc/lanczos_steps.cu).  on = 0 keeps every site on the general multi-kernel solver (also:
  * environment TNPY_FUSED_STEPS=0).  Returns the previous setting. */
 int tnpy_set_fused_steps(int on);
+/* Diagnostics: with a device buffer of 64 * 16 uint64 set, every fused launch records %globaltimer (ns) at the phase
+ * boundaries of its first 64 steps -- slots 0-7 of a step by CTA 0 (step start, P1 done, after barrier 1, P2 done,
+ * P3 done, P4 done, P5 done, after barrier 5), slots 8-15 the same by the convergence-watching CTA.  NULL switches it
+ * off (the default). */
+int tnpy_steps_trace(void* device_buffer);
 
 /* ---- chi-sharded local solve over the GPUs of one box (BASELINE configs[4]) -------------------
  * One process per GPU.  A communicator wraps an NCCL communicator that the library creates itself (libnccl.so.2 is

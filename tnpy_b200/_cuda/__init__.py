@@ -32,6 +32,7 @@ SIGNATURES = {
     "tnpy_ozaki_workspace_bytes": (c_size_t, [c_int] * 4),
     "tnpy_set_ozaki_slices": (c_int, [c_int]),
     "tnpy_set_fused_steps": (c_int, [c_int]),
+    "tnpy_steps_trace": (c_int, [c_void_p]),
     "tnpy_ozaki_gemm_tn": (
         c_int,
         [_PD, c_int64, _PD, c_int64, _PD, c_int64] + [c_int] * 6 + [c_void_p, c_size_t, c_void_p],

@@ -384,26 +384,30 @@ static int eig_lowest_impl(const tnpy_comm* comm, const double* L, const double*
   // where the Ritz solve is the dearest kernel of a step: 38 % of the device time of XXZ n=100 chi=60 before this).
   // The stopping rule itself is unchanged; a local solve can overshoot by at most stride_cap - 1 matvecs.
   const int stride_cap = n_full >= (1 << 20) ? 3 : (n_full >= (1 << 16) ? 4 : 8);
-  double last_resid = 0.0;
+  double last_resid = 0.0, last_anorm = 0.0;
   int last_look_matvec = 0;
   int since_check = 0, stride = 1;
   while (true) {
     int m;  // size of the Ritz problem looked at below
     if (fused) {
-      int nsteps = stride < 1 ? 1 : stride;
-      if (nsteps > ncv - j) nsteps = ncv - j;
+      // The launch runs to the next restart and returns by itself two steps after the device-side estimate of the
+      // residual has reached 0.7 tol ||A|| (||A|| >= the last look's max |Ritz value| and |theta| of the estimate
+      // itself; the margin covers estimates of ||A|| that shrink across a restart); the stopping rule proper is still
+      // ritz_kernel's, on the full T.
+      int nsteps = ncv - j;
       if (nsteps > max_matvec - n_matvec) nsteps = max_matvec - n_matvec;
       if ((int64_t)nsteps > n_full - j) nsteps = (int)(n_full - j);
       if (nsteps < 1) nsteps = 1;
       TNPY_TRY(lanczos_steps_launch(steps_plan, plan.L, plan.W, plan.R, V, ldv, T, status, ST_BETA, ST_STEPS, l, r, wl, wr, d, j, nsteps,
-                                    static_cast<char*>(workspace) + chain_off, stream));
+                                    ncv, whole_basis_step, tol, last_anorm, static_cast<char*>(workspace) + chain_off, stream));
       ritz_kernel<<<1, 256, 0, stream>>>(T, nullptr, nullptr, nullptr, 0, status + ST_BETA, j, tol, S, thetas, status, 0,
                                          status + ST_STEPS);
       TNPY_LAUNCH_OK();
       ++n_looks;
       TNPY_CUDA_OK(cudaMemcpyAsync(hst, status, sizeof(double) * ST_SIZE, cudaMemcpyDeviceToHost, stream));
       TNPY_CUDA_OK(cudaStreamSynchronize(stream));
-      const int steps_done = (int)hst[ST_STEPS];  // fewer than asked only after an exact breakdown
+      const int steps_done = (int)hst[ST_STEPS];  // fewer than asked: stopped by itself, or an exact breakdown
+      last_anorm = hst[ST_ANORM];
       n_matvec += steps_done;
       j += steps_done - 1;
       m = j + 1;

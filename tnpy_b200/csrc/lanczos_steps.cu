@@ -34,6 +34,7 @@ constexpr int kMaxTerms = 1024;  // wl * wr * d * d of the MPO tensor (its non-z
 constexpr int kMaxGroups = 128;  // wr * d
 constexpr int64_t kMaxVector = 32768;
 constexpr int kMaxKSplit = 8;
+constexpr int kMaxGatherLoads = 19;  // ceil(148 work CTAs / 8 threads per coefficient)
 
 struct StepsArgs {
   const double* L;
@@ -48,46 +49,324 @@ struct StepsArgs {
   double* wbuf;
   double* part;  // [2][grid][kStepsMaxNcv]
   double* nrm;   // [grid]
+  int* stop;     // [2], by step parity: set by the watcher CTA when the lowest Ritz pair has converged
   int beta_slot, steps_slot;
   int l, r, wl, wr, d;
   int j0, nsteps;
   int ksplit, kchunk, chunk;
+  int ldc;            // leading dimension of a CTA's shared-memory copy of its basis columns (>= chunk, = 8 mod 32)
+  unsigned long long* trace;  // diagnostics: CTA 0's and the watcher's %globaltimer at each phase boundary (or null)
+  int arrow;          // T = diag(arrow kept Ritz values) + their coupling to row `arrow` + a tridiagonal tail
+  double tol, anorm;  // the launch stops on its own once |beta z_last| <= 0.7 tol max(anorm, |theta|) (tol <= 0: never)
 };
 
 __device__ __forceinline__ void tile_mma(const double (*As)[kTile + 1], const double (*Bs)[kTile + 1], int tx, int ty,
                                          double (&acc)[2][2]) {
-#pragma unroll 8
-  for (int kk = 0; kk < kSlab; ++kk) {
+  // two independent chains per accumulator (even / odd rows of the slab): the loop is bound by the latency of
+  // dependent FP64 FMAs, not by their throughput
+  double odd[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll 4
+  for (int kk = 0; kk < kSlab; kk += 2) {
     const double a0 = As[kk][ty], a1 = As[kk][ty + 16];
     const double b0 = Bs[kk][tx], b1 = Bs[kk][tx + 16];
+    const double c0 = As[kk + 1][ty], c1 = As[kk + 1][ty + 16];
+    const double d0 = Bs[kk + 1][tx], d1 = Bs[kk + 1][tx + 16];
     acc[0][0] = fma(a0, b0, acc[0][0]);
     acc[0][1] = fma(a0, b1, acc[0][1]);
     acc[1][0] = fma(a1, b0, acc[1][0]);
     acc[1][1] = fma(a1, b1, acc[1][1]);
+    odd[0][0] = fma(c0, d0, odd[0][0]);
+    odd[0][1] = fma(c0, d1, odd[0][1]);
+    odd[1][0] = fma(c1, d0, odd[1][0]);
+    odd[1][1] = fma(c1, d1, odd[1][1]);
   }
+  acc[0][0] += odd[0][0];
+  acc[0][1] += odd[0][1];
+  acc[1][0] += odd[1][0];
+  acc[1][1] += odd[1][1];
 }
 
-// partial[k] = sum over this CTA's elements of V[k][.] * w[.] for k < m; warp `wv` takes k = wv, wv + 8, ...
-__device__ __forceinline__ void partial_dots(const double* V, int64_t ldv, int m, int64_t first, int count,
-                                             const double* wsm, double* out) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int k = warp; k < m; k += kThreads / 32) {
-    const double* vk = V + (int64_t)k * ldv + first;
+// partial[k] = sum over this CTA's elements of V[k][.] * w[.] for k < m, from the CTA's shared-memory copy of its
+// basis columns (vs[k * ldc + e]): eight threads per k, each over every eighth element, then three shuffles.
+// ldc % 32 == 8, so the four k of a warp sit in disjoint banks.
+__device__ __forceinline__ void partial_dots(const double* vs, int ldc, int m, int count, const double* wsm, double* out) {
+  const int sub = threadIdx.x & 7;
+  for (int k = threadIdx.x >> 3; k < ((m + 31) & ~31); k += kThreads / 8) {  // whole warps stay in the loop
     double s = 0.0;
-    for (int e = lane; e < count; e += 32) s = fma(vk[e], wsm[e], s);
-    s = warp_sum(s);
-    if (lane == 0) out[k] = s;
+    if (k < m) {
+      const double* vk = vs + k * ldc;
+      for (int e = sub; e < count; e += 8) s = fma(vk[e], wsm[e], s);
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    if (sub == 0 && k < m) out[k] = s;
   }
 }
 
-// h[k] = sum over the CTAs of their partials (fixed order), k < m
+// h[k] = sum over the CTAs of their partials (fixed order), k < m: eight threads per k, every load of a thread in
+// flight at once (the partials come from L2: one round trip per pass, not one per k)
 __device__ __forceinline__ void gather_partials(const double* part, int ctas, int m, double* h) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int k = warp; k < m; k += kThreads / 32) {
+  const int sub = threadIdx.x & 7;
+  for (int k = threadIdx.x >> 3; k < ((m + 31) & ~31); k += kThreads / 8) {
     double s = 0.0;
-    for (int c = lane; c < ctas; c += 32) s += part[(int64_t)c * kStepsMaxNcv + k];
-    s = warp_sum(s);
-    if (lane == 0) h[k] = s;
+    if (k < m) {
+      double v[kMaxGatherLoads];
+#pragma unroll
+      for (int i = 0; i < kMaxGatherLoads; ++i) {
+        const int c = sub + 8 * i;
+        v[i] = c < ctas ? part[(int64_t)c * kStepsMaxNcv + k] : 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < kMaxGatherLoads; ++i) s += v[i];
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    if (sub == 0 && k < m) h[k] = s;
+  }
+}
+
+// ---- convergence estimate on the device --------------------------------------------------------------------------
+// Between restarts the projected matrix is, up to rounding-level fill, T~ = diag(theta_0 .. theta_{k-1}) coupled to row k
+// (the thick-restart arrow) followed by a tridiagonal tail: a tree (star + path), so every factorisation below is O(m)
+// without fill.  One extra CTA finds the lowest eigenvalue of T~ by 257-section on Sturm counts (all threads, 7 rounds)
+// and the last component of its eigenvector from a twisted factorisation rooted where the eigenvector is largest
+// (Parlett-Dhillon: the root with the smallest |gamma|), which stays accurate when the pair has converged and the top-down
+// pivots are noise.  This only decides when the launch returns; the stopping rule itself is evaluated by ritz_kernel
+// on the full T afterwards.
+__device__ __forceinline__ int sturm_count(const double* dg, const double* cp2, int k, int m, double s, double tiny) {
+  // cp2 = squared couplings.  Negative pivots of T~ - s in the elimination order kept vectors, row k, tail: the kept
+  // vectors' pivots directly, then sign changes of the tail's polynomial recurrence (no division on that chain)
+  int cnt = 0;
+  double hub = dg[k] - s;
+  for (int i = 0; i < k; ++i) {
+    double dd = dg[i] - s;
+    if (dd == 0.0) dd = -tiny;
+    cnt += dd < 0.0;
+    hub -= cp2[i] / dd;
+  }
+  if (hub == 0.0) hub = -tiny;
+  cnt += hub < 0.0;
+  double qp = 1.0, q = hub;
+  int i = k + 1;
+  while (i < m) {
+    const int end = min(m, i + 8);
+    for (; i < end; ++i) {
+      double qn = fma(dg[i] - s, q, -cp2[i - 1] * qp);
+      if (qn == 0.0) qn = q < 0.0 ? tiny : -tiny;  // a zero takes the sign opposite to its predecessor
+      cnt += (qn < 0.0) != (q < 0.0);
+      qp = q;
+      q = qn;
+    }
+    const double aq = fabs(q);  // rescaled every eight rows: off the dependency chain of the recurrence
+    if (aq > 1e100) {
+      q *= 1e-100;
+      qp *= 1e-100;
+    } else if (aq < 1e-100) {
+      q *= 1e100;
+      qp *= 1e100;
+    }
+  }
+  return cnt;
+}
+
+// The estimate is spread over the barrier intervals of one step so that it rarely holds the other CTAs up:
+// watch_begin + 1 round, then one round per interval, the rest and the eigenvector in watch_finish.  State lives in
+// the watcher's shared memory (e: >= 640 doubles, ei: >= 16 ints); every thread of the CTA calls each stage.
+struct WatchMem {
+  double *dg, *cp, *cp2, *dsp, *rdsp, *dm, *rdm, *dp, *rdp, *gam, *dki, *z, *box;
+  __device__ explicit WatchMem(double* e)
+      : dg(e), cp(e + 48), cp2(e + 96), dsp(e + 144), rdsp(e + 192), dm(e + 240), rdm(e + 290), dp(e + 340),
+        rdp(e + 388), gam(e + 436), dki(e + 484), z(e + 532), box(e + 580) {}
+  // dg: diagonal of T~;  cp[i]: i < k coupling of kept vector i to row k, i >= k sub-diagonal T[i + 1][i];
+  // dsp: pivots of the kept vectors as leaves;  dm: bottom-up pivots of the tail (49 entries);  dp: top-down pivots
+  // from row k;  r*: their reciprocals;  gam: twist values;  dki: pivot of row k when kept vector i is the root;
+  // box: 0 lo, 1 hi, 2 pivot floor, 3 spoke sum, 4 beta, 5 bracket tolerance, 6 / 7 Gershgorin lo / hi,
+  //      8 / 9 / 10 the previous estimate's lo / hi / residual, 11 whether there is one, 12 size of T at which the
+  //      next estimate is due, 13 size at the previous one
+};
+constexpr int kWatchBox = 580;
+
+__device__ void watch_begin(const double* T, int m, int k, double beta, double* e) {
+  WatchMem w(e);
+  const int tid = threadIdx.x;
+  if (tid < m) {
+    w.dg[tid] = T[tid * kStepsMaxNcv + tid];
+    const double c = tid < m - 1 ? (tid < k ? T[k * kStepsMaxNcv + tid] : T[(tid + 1) * kStepsMaxNcv + tid]) : 0.0;
+    w.cp[tid] = c;
+    w.cp2[tid] = c * c;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double lo = 1e300, hi = -1e300, big = 0.0, hubrad = 0.0;
+    for (int i = 0; i < k; ++i) hubrad += fabs(w.cp[i]);
+    for (int i = 0; i < m; ++i) {
+      double rad;
+      if (i < k) rad = fabs(w.cp[i]);
+      else if (i == k) rad = hubrad + (k < m - 1 ? fabs(w.cp[k]) : 0.0);
+      else rad = fabs(w.cp[i - 1]) + (i < m - 1 ? fabs(w.cp[i]) : 0.0);
+      lo = fmin(lo, w.dg[i] - rad);
+      hi = fmax(hi, w.dg[i] + rad);
+      big = fmax(big, fabs(w.dg[i]));
+    }
+    lo -= 1e-3 * (hi - lo) + 1e-300;
+    hi += 1e-3 * (hi - lo);
+    const double scale = fmax(fmax(fabs(lo), fabs(hi)), fmax(big, 1e-280));
+    w.box[6] = lo;
+    w.box[7] = hi;
+    if (w.box[11] != 0.0) {
+      // the lowest Ritz value only falls as the basis grows, and by no more than the residual: start from the last
+      // estimate (the rounds check the ends of the bracket and fall back to the Gershgorin interval)
+      lo = fmax(lo, w.box[8] - fmax(4.0 * w.box[10], 1e-9 * scale));
+      hi = fmin(hi, w.box[9] + 1e-12 * scale);
+    }
+    w.box[0] = lo;
+    w.box[1] = hi;
+    w.box[2] = 1e-18 * scale;
+    w.box[4] = beta;
+    w.box[5] = 1e-13 * scale;
+  }
+  __syncthreads();
+}
+
+__device__ void watch_rounds(int rounds, int m, int k, double* e, int* ei) {
+  WatchMem w(e);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const double tiny = w.box[2] * 1e-12;
+  for (int round = 0; round < rounds; ++round) {
+    const double lo = w.box[0], hi = w.box[1];
+    if (hi - lo <= w.box[5]) break;
+    // 256 shifts from lo to hi inclusive; the lowest eigenvalue lies between the last shift with no eigenvalue
+    // below it and the first with one
+    const double sigma = lo + (hi - lo) * (double)tid / (double)(kThreads - 1);
+    const int cnt = sturm_count(w.dg, w.cp2, k, m, sigma, tiny);
+    const unsigned ball = __ballot_sync(0xffffffffu, cnt >= 1);
+    if (lane == 0) ei[warp] = (int)ball;
+    __syncthreads();
+    if (tid == 0) {
+      int f = kThreads;
+      for (int wv = 0; wv < kThreads / 32; ++wv)
+        if (ei[wv] != 0) {
+          f = wv * 32 + __ffs(ei[wv]) - 1;
+          break;
+        }
+      if (f == 0) {  // already an eigenvalue below lo: the warm start was too high
+        w.box[1] = lo;
+        w.box[0] = w.box[6];
+      } else if (f == kThreads) {  // none below hi
+        w.box[0] = hi;
+        w.box[1] = w.box[7];
+      } else {
+        w.box[0] = lo + (hi - lo) * (double)(f - 1) / (double)(kThreads - 1);
+        w.box[1] = lo + (hi - lo) * (double)f / (double)(kThreads - 1);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// |beta z_last| <= 0.7 tol max(anorm, |theta|) for the lowest pair (theta, z) of T~ ?
+__device__ bool watch_finish(int m, int k, double tol, double anorm, double* e, int* ei) {
+  WatchMem w(e);
+  const int tid = threadIdx.x;
+  watch_rounds(8, m, k, e, ei);  // whatever the intervals of the step left over
+  const double s = w.box[0];  // just below the lowest eigenvalue: T~ - s is positive definite, every pivot positive
+  const double floor_ = w.box[2];
+  auto guard = [&](double v) { return v > floor_ ? v : floor_; };
+  if (tid < k) {
+    const double dd = guard(w.dg[tid] - s);
+    w.dsp[tid] = dd;
+    w.rdsp[tid] = 1.0 / dd;
+  }
+  __syncthreads();
+  if (tid == 0) {  // bottom-up along the tail
+    double rnext = 0.0;
+    for (int j = m - 1; j > k; --j) {
+      const double dd = guard(w.dg[j] - s - w.cp2[j] * rnext);  // cp2[m - 1] == 0
+      rnext = 1.0 / dd;
+      w.dm[j] = dd;
+      w.rdm[j] = rnext;
+    }
+  } else if (tid == 32) {  // top-down from row k
+    double sum = 0.0;
+    for (int i = 0; i < k; ++i) sum += w.cp2[i] * w.rdsp[i];
+    w.box[3] = sum;
+    double dd = guard(w.dg[k] - s - sum), rr = 1.0 / dd;
+    w.dp[k] = dd;
+    w.rdp[k] = rr;
+    for (int j = k + 1; j < m; ++j) {
+      dd = guard(w.dg[j] - s - w.cp2[j - 1] * rr);
+      rr = 1.0 / dd;
+      w.dp[j] = dd;
+      w.rdp[j] = rr;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) w.gam[k] = w.dg[k] - s - w.box[3] - (k < m - 1 ? w.cp2[k] * w.rdm[k + 1] : 0.0);
+  __syncthreads();
+  if (tid < m && tid != k) {
+    if (tid < k) {
+      w.dki[tid] = guard(w.gam[k] + w.cp2[tid] * w.rdsp[tid]);
+      w.gam[tid] = w.dg[tid] - s - w.cp2[tid] / w.dki[tid];
+    } else {
+      w.gam[tid] = w.dg[tid] - s - w.cp2[tid - 1] * w.rdp[tid - 1] - (tid < m - 1 ? w.cp2[tid] * w.rdm[tid + 1] : 0.0);
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double* z = w.z;
+    int root = 0;
+    for (int i = 1; i < m; ++i)
+      if (fabs(w.gam[i]) < fabs(w.gam[root])) root = i;
+    for (int i = 0; i < m; ++i) z[i] = 0.0;
+    z[root] = 1.0;
+    int from = k;  // the tail is walked downwards from here
+    if (root == k) {
+      for (int i = 0; i < k; ++i) z[i] = -w.cp[i] * w.rdsp[i];
+    } else if (root < k) {
+      z[k] = -w.cp[root] / w.dki[root];
+      for (int i = 0; i < k; ++i)
+        if (i != root) z[i] = -w.cp[i] * z[k] * w.rdsp[i];
+    } else {
+      for (int j = root; j > k; --j) z[j - 1] = -w.cp[j - 1] * z[j] * w.rdp[j - 1];
+      for (int i = 0; i < k; ++i) z[i] = -w.cp[i] * z[k] * w.rdsp[i];
+      from = root;
+    }
+    for (int j = from; j < m - 1; ++j) z[j + 1] = -w.cp[j] * z[j] * w.rdm[j + 1];
+    double nn = 0.0;
+    for (int i = 0; i < m; ++i) nn = fma(z[i], z[i], nn);
+    const double resid = fabs(w.box[4] * z[m - 1]) / sqrt(nn);
+    const double theta = 0.5 * (w.box[0] + w.box[1]);
+    ei[15] = (resid <= 0.7 * tol * fmax(anorm, fabs(theta))) ? 1 : 0;
+    // Residuals fall geometrically: the last two estimates give the rate and with it the number of steps left;
+    // the next estimate is made after half of them (at most eight), so most steps run without one
+    const double thr = 0.7 * tol * fmax(anorm, fabs(theta));
+    int skip = 1;
+    if (w.box[11] != 0.0 && w.box[10] > resid && resid > thr && thr > 0.0 && (double)m > w.box[13]) {
+      const double rate = log(w.box[10] / resid) / ((double)m - w.box[13]);
+      const double left = log(resid / thr) / rate;
+      skip = left < 4.0 ? 1 : (left > 16.0 ? 8 : (int)(0.5 * left));
+    }
+    w.box[12] = (double)(m + skip);
+    w.box[13] = (double)m;
+    w.box[8] = w.box[0];
+    w.box[9] = w.box[1];
+    w.box[10] = resid;
+    w.box[11] = 1.0;
+  }
+  __syncthreads();
+  const bool done = ei[15] != 0;
+  __syncthreads();
+  return done;
+}
+
+__device__ __forceinline__ void trace_mark(const StepsArgs& a, int step, int slot, bool watcher) {
+  // 16 slots per step: 0-7 CTA 0, 8-15 the watcher
+  if (a.trace != nullptr && threadIdx.x == 0 && (blockIdx.x == 0 || watcher) && step < 64) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    a.trace[step * 16 + (watcher ? 8 : 0) + slot] = t;
   }
 }
 
@@ -108,7 +387,17 @@ __global__ void __launch_bounds__(kThreads, 1) lanczos_steps_kernel(const StepsA
   const int n = l * d * r;
   const int M1 = d * r, N1 = wl * l, K1 = l;  // t1 is M1 x N1, leading dimension N1
   const int M2 = d * l, N2 = r, K2 = r * wr;  // rows c = (q, m), m fastest
-  const int ctas = gridDim.x, cta = blockIdx.x;
+  // the last CTA takes no tiles and owns no vector elements: it watches the convergence of the Ritz pair
+  const int ctas = gridDim.x - 1;
+  const bool watcher = (int)blockIdx.x == ctas;
+  const int cta = watcher ? (1 << 29) : (int)blockIdx.x;
+  __shared__ int est_i[16];
+  if (watcher && threadIdx.x == 0) {
+    a.stop[0] = a.stop[1] = 0;
+    (&As[0][0])[kWatchBox + 11] = 0.0;  // no previous estimate yet (the watcher keeps its state in As)
+    (&As[0][0])[kWatchBox + 12] = 0.0;
+    (&As[0][0])[kWatchBox + 13] = 0.0;
+  }
 
   // the non-zeros of W, grouped by the output pair (b, q), in (a, p) order
   const int ngroups = wr * d;
@@ -142,9 +431,15 @@ __global__ void __launch_bounds__(kThreads, 1) lanczos_steps_kernel(const StepsA
   }
   __syncthreads();
 
-  const int64_t first = (int64_t)cta * a.chunk;
+  const int64_t first = watcher ? (int64_t)n : (int64_t)cta * a.chunk;
   const int count = first >= n ? 0 : (int)min((int64_t)a.chunk, n - first);
   const bool own = tid < count;
+  // this CTA's elements of every basis vector stay in shared memory for the whole launch: the Gram-Schmidt phases
+  // then never wait for L2 (the barriers invalidate L1)
+  extern __shared__ double vs[];
+  const int ldc = a.ldc;
+  if (own)
+    for (int k = 0; k <= a.j0; ++k) vs[k * ldc + tid] = a.V[(int64_t)k * a.ldv + first + tid];
   double w = 0.0;
   const double* xsrc = a.V + (int64_t)a.j0 * a.ldv;
   double xscale = 1.0;
@@ -153,21 +448,34 @@ __global__ void __launch_bounds__(kThreads, 1) lanczos_steps_kernel(const StepsA
 
   for (int step = 0; step < a.nsteps; ++step) {
     const int j = a.j0 + step, m = j + 1;
+    trace_mark(a, step, 0, watcher);
 
     // ---- P1 ----
     {
       const int tiles_n = (N1 + kTile - 1) / kTile, tiles = ((M1 + kTile - 1) / kTile) * tiles_n;
+      constexpr int kPer = kSlab * kTile / kThreads;  // slab elements per thread and operand
       for (int tile = cta; tile < tiles; tile += ctas) {
         const int m0 = (tile / tiles_n) * kTile, n0 = (tile % tiles_n) * kTile;
         double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+        double pa[kPer], pb[kPer];
+        auto fetch = [&](int k0) {  // the slab's loads, all in flight together
+#pragma unroll
+          for (int it = 0; it < kPer; ++it) {
+            const int idx = tid + it * kThreads, kk = idx >> 5, c = idx & 31, k = k0 + kk;
+            pa[it] = (k < K1 && m0 + c < M1) ? xsrc[(int64_t)k * M1 + m0 + c] : 0.0;
+            pb[it] = (k < K1 && n0 + c < N1) ? a.L[(int64_t)k * N1 + n0 + c] : 0.0;
+          }
+        };
+        fetch(0);
         for (int k0 = 0; k0 < K1; k0 += kSlab) {
 #pragma unroll
-          for (int it = 0; it < kSlab * kTile / kThreads; ++it) {
-            const int idx = tid + it * kThreads, kk = idx >> 5, c = idx & 31, k = k0 + kk;
-            As[kk][c] = (k < K1 && m0 + c < M1) ? xsrc[(int64_t)k * M1 + m0 + c] * xscale : 0.0;
-            Bs[kk][c] = (k < K1 && n0 + c < N1) ? a.L[(int64_t)k * N1 + n0 + c] : 0.0;
+          for (int it = 0; it < kPer; ++it) {
+            const int idx = tid + it * kThreads, kk = idx >> 5, c = idx & 31;
+            As[kk][c] = pa[it] * xscale;
+            Bs[kk][c] = pb[it];
           }
           __syncthreads();
+          if (k0 + kSlab < K1) fetch(k0 + kSlab);  // the next slab travels while this one is multiplied
           tile_mma(As, Bs, tx, ty, acc);
           __syncthreads();
         }
@@ -180,32 +488,78 @@ __global__ void __launch_bounds__(kThreads, 1) lanczos_steps_kernel(const StepsA
           }
       }
     }
+    trace_mark(a, step, 1, watcher);
     grid.sync();
+    trace_mark(a, step, 2, watcher);
+    // The watcher examines T as the steps before this one left it (j columns; status holds the norm the last one
+    // found) while the others run this step, and publishes its verdict before the next step's first barrier.
+    double* const wmem = &As[0][0];
+    const bool watching = watcher && step >= 1 && a.tol > 0.0 && a.arrow <= j - 1 && (double)j >= wmem[kWatchBox + 12];
+    if (watching) {
+      watch_begin(a.T, j, a.arrow, a.status[a.beta_slot], wmem);
+      watch_rounds(1, j, a.arrow, wmem, est_i);
+    }
 
     // ---- P2 ----
     {
       const int tiles_n = (N2 + kTile - 1) / kTile, tiles = ((M2 + kTile - 1) / kTile) * tiles_n;
       const int items = tiles * a.ksplit;
+      constexpr int kPer = kSlab * kTile / kThreads;
       for (int item = cta; item < items; item += ctas) {
         const int ks = item % a.ksplit, tile = item / a.ksplit;
         const int m0 = (tile / tiles_n) * kTile, n0 = (tile % tiles_n) * kTile;
         const int kbeg = ks * a.kchunk, kend = min(K2, kbeg + a.kchunk);
+        // the row (q, m) of this thread's slab elements does not change from slab to slab
+        const int cc = m0 + (tid & 31);
+        const int q_of = cc / l, mm_of = cc - q_of * l;
         double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+        double pa[kPer], pb[kPer];
+        auto fetch = [&](int k0) {
+          // A[(r' b), (q m)] = sum over the non-zeros W[a, b, p, q] of W * t1[(p r'), (a m)]: the loads of up to four
+          // terms of all the thread's elements are issued before anything is summed (one L2 round trip per slab)
+          double x[kPer][4], cf[kPer][4];
+          int more[kPer];
+#pragma unroll
+          for (int it = 0; it < kPer; ++it) {
+            const int kk = (tid >> 5) + it * (kThreads / 32), k = k0 + kk;
+            const bool live = k < kend && cc < M2;
+            const int rp = k / wr, b = k - rp * wr;
+            const int g = live ? b * d + q_of : 0;
+            const int t0 = goff[g], t1e = live ? goff[g + 1] : t0;
+            const double* src = a.t1 + (int64_t)rp * N1 + mm_of;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const bool on = t0 + u < t1e;
+              cf[it][u] = on ? coef[t0 + u] : 0.0;
+              x[it][u] = on ? src[toff[t0 + u]] : 0.0;
+            }
+            more[it] = t1e - t0 > 4 ? t1e : 0;
+            pb[it] = (k < kend && n0 + (tid & 31) < N2) ? a.R[(int64_t)k * r + n0 + (tid & 31)] : 0.0;
+          }
+#pragma unroll
+          for (int it = 0; it < kPer; ++it) {
+            double v = 0.0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v = fma(cf[it][u], x[it][u], v);
+            if (more[it]) {  // a denser MPO tensor: the remaining terms one by one
+              const int kk = (tid >> 5) + it * (kThreads / 32), k = k0 + kk;
+              const int rp = k / wr, b = k - rp * wr, g = b * d + q_of;
+              const double* src = a.t1 + (int64_t)rp * N1 + mm_of;
+              for (int t = goff[g] + 4; t < more[it]; ++t) v = fma(coef[t], src[toff[t]], v);
+            }
+            pa[it] = v;
+          }
+        };
+        fetch(kbeg);
         for (int k0 = kbeg; k0 < kend; k0 += kSlab) {
 #pragma unroll
-          for (int it = 0; it < kSlab * kTile / kThreads; ++it) {
-            const int idx = tid + it * kThreads, kk = idx >> 5, c = idx & 31, k = k0 + kk, cc = m0 + c;
-            double v = 0.0;
-            if (k < kend && cc < M2) {
-              const int rp = k / wr, b = k - rp * wr, q = cc / l, mm = cc - q * l;
-              const int g = b * d + q;
-              const double* src = a.t1 + (int64_t)rp * N1 + mm;
-              for (int t = goff[g]; t < goff[g + 1]; ++t) v = fma(coef[t], src[toff[t]], v);
-            }
-            As[kk][c] = v;
-            Bs[kk][c] = (k < kend && n0 + c < N2) ? a.R[(int64_t)k * r + n0 + c] : 0.0;
+          for (int it = 0; it < kPer; ++it) {
+            const int kk = (tid >> 5) + it * (kThreads / 32);
+            As[kk][tid & 31] = pa[it];
+            Bs[kk][tid & 31] = pb[it];
           }
           __syncthreads();
+          if (k0 + kSlab < kend) fetch(k0 + kSlab);
           tile_mma(As, Bs, tx, ty, acc);
           __syncthreads();
         }
@@ -214,15 +568,17 @@ __global__ void __launch_bounds__(kThreads, 1) lanczos_steps_kernel(const StepsA
         for (int i = 0; i < 2; ++i)
 #pragma unroll
           for (int jj = 0; jj < 2; ++jj) {
-            const int cc = m0 + ty + 16 * i, col = n0 + tx + 16 * jj;
-            if (cc < M2 && col < N2) {
-              const int q = cc / l, mm = cc - q * l;
+            const int cr = m0 + ty + 16 * i, col = n0 + tx + 16 * jj;
+            if (cr < M2 && col < N2) {
+              const int q = cr / l, mm = cr - q * l;
               yp[((int64_t)mm * d + q) * r + col] = acc[i][jj];
             }
           }
       }
     }
+    trace_mark(a, step, 3, watcher);
     grid.sync();
+    if (watching) watch_rounds(1, j, a.arrow, wmem, est_i);
 
     // ---- P3: w and the first pass' partial coefficients ----
     w = 0.0;
@@ -230,34 +586,46 @@ __global__ void __launch_bounds__(kThreads, 1) lanczos_steps_kernel(const StepsA
       for (int ks = 0; ks < a.ksplit; ++ks) w += a.ypart[(int64_t)ks * n + first + tid];
     wsm[tid] = w;
     __syncthreads();
-    partial_dots(a.V, a.ldv, m, first, count, wsm, part0 + (int64_t)cta * kStepsMaxNcv);
+    if (!watcher) partial_dots(vs, ldc, m, count, wsm, part0 + (int64_t)cta * kStepsMaxNcv);
+    trace_mark(a, step, 4, watcher);
     grid.sync();
+    if (watching) watch_rounds(1, j, a.arrow, wmem, est_i);
 
     // ---- P4: first pass applied, second pass' partial coefficients ----
     gather_partials(part0, ctas, m, hs);
     __syncthreads();
-    if (own) {
-      const double* v = a.V + first + tid;
-      for (int k = 0; k < m; ++k) w = fma(-hs[k], v[(int64_t)k * a.ldv], w);
-    }
+    if (own)
+      for (int k = 0; k < m; ++k) w = fma(-hs[k], vs[k * ldc + tid], w);
     wsm[tid] = w;
     __syncthreads();
-    partial_dots(a.V, a.ldv, m, first, count, wsm, part1 + (int64_t)cta * kStepsMaxNcv);
+    if (!watcher) partial_dots(vs, ldc, m, count, wsm, part1 + (int64_t)cta * kStepsMaxNcv);
+    trace_mark(a, step, 5, watcher);
     grid.sync();
+    if (watching) watch_rounds(1, j, a.arrow, wmem, est_i);
 
     // ---- P5: second pass applied, partial norm, w published ----
     gather_partials(part1, ctas, m, h2s);
     __syncthreads();
     if (own) {
-      const double* v = a.V + first + tid;
-      for (int k = 0; k < m; ++k) w = fma(-h2s[k], v[(int64_t)k * a.ldv], w);
+      for (int k = 0; k < m; ++k) w = fma(-h2s[k], vs[k * ldc + tid], w);
       a.wbuf[first + tid] = w;
     }
     {
       const double sq = block_sum(own ? w * w : 0.0, red);
-      if (tid == 0) a.nrm[cta] = sq;
+      if (tid == 0 && !watcher) a.nrm[cta] = sq;
     }
+    trace_mark(a, step, 6, watcher);
     grid.sync();
+    trace_mark(a, step, 7, watcher);
+    // the verdict on the previous step's T, written before this step's first barrier (slots alternate: the watcher
+    // may be writing this step's verdict right now)
+    const int stop = step >= 2 ? *(volatile int*)(a.stop + ((step - 1) & 1)) : 0;
+    if (watching) {
+      const bool converged = watch_finish(j, a.arrow, a.tol, a.anorm, wmem, est_i);
+      if (tid == 0) a.stop[step & 1] = converged ? 1 : 0;
+    } else if (watcher && tid == 0) {
+      a.stop[step & 1] = 0;
+    }
 
     // ---- P6: normalise, new column of T ----
     if (tid < 32) {
@@ -269,7 +637,10 @@ __global__ void __launch_bounds__(kThreads, 1) lanczos_steps_kernel(const StepsA
     __syncthreads();
     const double beta = beta_sh;
     const double inv = beta > 0.0 ? 1.0 / beta : 0.0;
-    if (own) a.V[(int64_t)(j + 1) * a.ldv + first + tid] = w * inv;
+    if (own) {
+      a.V[(int64_t)(j + 1) * a.ldv + first + tid] = w * inv;
+      vs[(j + 1) * ldc + tid] = w * inv;
+    }
     if (cta == 0) {
       if (tid < m) {
         const double t = hs[tid] + h2s[tid];
@@ -283,9 +654,14 @@ __global__ void __launch_bounds__(kThreads, 1) lanczos_steps_kernel(const StepsA
     }
     xsrc = a.wbuf;
     xscale = inv;
-    if (!(beta > 0.0)) break;  // exact breakdown: every CTA sees the same beta
+    if (!(beta > 0.0) || stop) break;  // exact breakdown / converged: every CTA sees the same values
     __syncthreads();           // beta_sh, hs, h2s are rewritten in the next step
   }
+}
+
+std::atomic<unsigned long long*>& trace_buffer() {
+  static std::atomic<unsigned long long*> p(nullptr);
+  return p;
 }
 
 std::atomic<int>& fused_steps_switch() {
@@ -300,7 +676,7 @@ std::atomic<int>& fused_steps_switch() {
 bool lanczos_steps_supported(int l, int r, int wl, int wr, int d) {
   if (!fused_steps_switch().load(std::memory_order_relaxed)) return false;
   const int64_t n = (int64_t)l * d * r;
-  return n <= kMaxVector && (n + kThreads - 1) / kThreads <= sm_count() && (int64_t)wl * wr * d * d <= kMaxTerms &&
+  return n <= kMaxVector && (n + kThreads - 1) / kThreads <= sm_count() - 1 && (int64_t)wl * wr * d * d <= kMaxTerms &&
          wr * d <= kMaxGroups && l >= 1 && r >= 1;
 }
 
@@ -314,7 +690,7 @@ LanczosStepsPlan lanczos_steps_plan(int l, int r, int wl, int wr, int d) {
   if (tiles1 > want) want = tiles1;
   if (tiles2 > want) want = tiles2;
   if (want < 8) want = 8;
-  p.grid = want < sms ? want : sms;
+  p.grid = want < sms - 1 ? want : sms - 1;  // work CTAs; the launch adds the one that watches convergence
   p.chunk = (int)((n + p.grid - 1) / p.grid);  // <= 256: grid >= n / 256 (n <= 32768 needs 128 CTAs, a B200 has 148)
   const int K2 = r * wr;
   int ksplit = p.grid / tiles2;
@@ -324,14 +700,16 @@ LanczosStepsPlan lanczos_steps_plan(int l, int r, int wl, int wr, int d) {
   p.kchunk = ceil_div(ceil_div(K2, ksplit), kSlab) * kSlab;
   p.ksplit = ceil_div(K2, p.kchunk);
   p.bytes = Workspace::need((size_t)d * r * wl * l) + Workspace::need((size_t)p.ksplit * n) + Workspace::need((size_t)n) +
-            Workspace::need((size_t)2 * p.grid * kStepsMaxNcv) + Workspace::need((size_t)p.grid) + 256;
+            Workspace::need((size_t)2 * p.grid * kStepsMaxNcv) + Workspace::need((size_t)p.grid) + Workspace::need(64, 1) + 256;
   return p;
 }
 
 int lanczos_steps_launch(const LanczosStepsPlan& plan, const double* L, const double* W, const double* R, double* V,
                          int64_t ldv, double* T, double* status, int beta_slot, int steps_slot, int l, int r, int wl,
-                         int wr, int d, int j0, int nsteps, void* scratch, cudaStream_t stream) {
+                         int wr, int d, int j0, int nsteps, int ncv, int arrow, double tol, double anorm, void* scratch,
+                         cudaStream_t stream) {
   TNPY_CHECK_ARG(plan.chunk <= kThreads && plan.grid >= 1, "vector too long for the fused path");
+  TNPY_CHECK_ARG(ncv <= kStepsMaxNcv && j0 + nsteps <= ncv, "steps beyond the basis");
   const int64_t n = (int64_t)l * d * r;
   Workspace ws(scratch, plan.bytes);
   StepsArgs a;
@@ -347,7 +725,8 @@ int lanczos_steps_launch(const LanczosStepsPlan& plan, const double* L, const do
   a.wbuf = ws.take<double>((size_t)n);
   a.part = ws.take<double>((size_t)2 * plan.grid * kStepsMaxNcv);
   a.nrm = ws.take<double>((size_t)plan.grid);
-  if (!a.t1 || !a.ypart || !a.wbuf || !a.part || !a.nrm) {
+  a.stop = ws.take<int>(16);
+  if (!a.t1 || !a.ypart || !a.wbuf || !a.part || !a.nrm || !a.stop) {
     set_error("lanczos_steps: workspace too small");
     return TNPY_EWORKSPACE;
   }
@@ -363,9 +742,16 @@ int lanczos_steps_launch(const LanczosStepsPlan& plan, const double* L, const do
   a.ksplit = plan.ksplit;
   a.kchunk = plan.kchunk;
   a.chunk = plan.chunk;
+  a.ldc = ((plan.chunk + 23) / 32) * 32 + 8;  // smallest value >= chunk that is 8 mod 32
+  const int smem = (ncv + 1) * a.ldc * (int)sizeof(double);
+  TNPY_TRY(set_max_dynamic_smem(lanczos_steps_kernel, (kStepsMaxNcv + 1) * (((kThreads + 23) / 32) * 32 + 8) * (int)sizeof(double)));
+  a.trace = trace_buffer().load(std::memory_order_relaxed);
+  a.arrow = arrow;
+  a.tol = tol;
+  a.anorm = anorm;
   void* args[] = {&a};
-  TNPY_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lanczos_steps_kernel), dim3(plan.grid), dim3(kThreads),
-                                           args, 0, stream));
+  TNPY_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lanczos_steps_kernel), dim3(plan.grid + 1), dim3(kThreads),
+                                           args, smem, stream));
   count_launch();
   return TNPY_OK;
 }
@@ -373,3 +759,7 @@ int lanczos_steps_launch(const LanczosStepsPlan& plan, const double* L, const do
 }  // namespace tnpy
 
 extern "C" int tnpy_set_fused_steps(int on) { return tnpy::fused_steps_switch().exchange(on ? 1 : 0); }
+extern "C" int tnpy_steps_trace(void* device_buffer) {
+  tnpy::trace_buffer().store(static_cast<unsigned long long*>(device_buffer));
+  return TNPY_OK;
+}
