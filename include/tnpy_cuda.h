@@ -284,6 +284,15 @@ int tnpy_geig_lowest(const double* LA, const double* WA, const double* RA, const
 size_t tnpy_geig_dense_workspace_bytes(int n);
 int tnpy_geig_dense_lowest(double* a, double* b, int n, double* theta_dev, double* x, void* workspace,
                            size_t workspace_bytes, void* stream);
+/* The same pencil for large n (10^3 .. 3 x 10^4 unknowns): b = D C C^T D by a blocked Cholesky factorisation (D =
+ * sqrt(diag b)), S = X^T a X with X = D^-1 C^-T on the FP64 tensor pipe, lowest eigenpair of S by the on-device
+ * Lanczos solver of tnpy_eig_lowest (tol, max_matvec and stats_host as there; stats_host may be NULL), x = X z with
+ * x^T b x = 1.  a and b are left intact.  TNPY_ENOCONV with "not positive definite" in tnpy_last_error() when the
+ * factorisation breaks down, or when the Lanczos iteration did not reach tol (x, theta then hold the best pair).
+ * Workspace: tnpy_geig_chol_workspace_bytes(n) (about 4 padded n x n matrices). */
+size_t tnpy_geig_chol_workspace_bytes(int n);
+int tnpy_geig_chol_lowest(const double* a, const double* b, int n, double tol, int max_matvec, double* theta_dev,
+                          double* x, double* stats_host, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- a5: linalg.eigh(matrix)  (linalg.py:42-61), k = 1 --------------------------------------
  * Lowest eigenpair of a dense symmetric N x N matrix (row-major, destroyed) by cyclic Jacobi

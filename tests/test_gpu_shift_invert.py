@@ -118,6 +118,7 @@ def test_unconverged_iterative_pencil_raises_and_keeps_the_state():
     shifted = RandomHeisenberg(n=10, h=10.5, seed=2022, offset=0.1)
     sidmrg = ShiftInvertDMRG(shifted.mpo, bond_dim=2**6, offset=0.1, seed=1)
     sidmrg.dense_pencil_dim = 512  # the two mid-chain sites (1024 unknowns) now iterate
+    sidmrg.cholesky_pencil_dim = 0
     site = 5
     before = sidmrg.environment.device_tensor(site).clone()
     try:
@@ -132,3 +133,71 @@ def test_unconverged_iterative_pencil_raises_and_keeps_the_state():
         theta_dense = sidmrg._solve_on_device(site, 1e-8)
         assert sidmrg.solver_stats[-1]["dense"]
         assert abs(theta_iter - theta_dense) <= 1e-6 * abs(theta_dense)
+
+
+def test_cholesky_pencil_matches_lapack():
+    """tnpy_geig_chol_lowest (Cholesky factor of the right-hand matrix + the on-device Lanczos solver on the reduced
+    matrix) against scipy.linalg.eigh(a, b) -- LAPACK's sygvd, the same reduction -- on a projected pencil of 2048
+    unknowns: eigenvalue, M-normalisation and the pencil residual; a and b are left intact."""
+    from tnpy_b200 import _cuda
+
+    n, chi, offset, site = 12, 32, 0.1, 6
+    mpo = oracle.random_heisenberg_mpo(n, 10.5, seed=2022, offset=offset)
+    mps = oracle.random_mps(n, chi, 2, seed=5)
+    env, env2 = oracle.Environment(mpo, mps), oracle.Environment(oracle.mpo_square(mpo), mps)
+    l, d, r = mps[site].shape
+    assert l * d * r == 2048
+    L, W, R = dev(env.left[site]), dev(oracle._w4(mpo[site], site, n)), dev(env.right[site])
+    L2, W2, R2 = dev(env2.left[site]), dev(oracle._w4(env2.mpo[site], site, n)), dev(env2.right[site])
+    ad = _cuda.heff_dense(L, W, R, l, r)
+    bd = _cuda.heff_dense(L2, W2, R2, l, r)
+    a, b = ad.cpu().numpy(), bd.cpu().numpy()
+    a, b = 0.5 * (a + a.T), 0.5 * (b + b.T)
+    want = spla.eigh(a, b, eigvals_only=True, subset_by_index=[0, 0])[0]
+    a_before, b_before = ad.clone(), bd.clone()
+    theta, xd, stats = _cuda.geig_chol_lowest(ad, bd, tol=1e-12)
+    assert stats["converged"] and stats["n_matvec"] < 400
+    assert torch.equal(ad, a_before) and torch.equal(bd, b_before)
+    cond = np.linalg.cond(b)
+    assert abs(theta.item() - want) <= max(1e-8, 10 * cond * 2.2e-16) * abs(want)
+    x = xd.cpu().numpy()
+    assert abs(x @ b @ x - 1.0) < 1e-6
+    assert np.linalg.norm(a @ x - theta.item() * (b @ x)) <= 1e-6 * np.linalg.norm(a @ x)
+    # and it agrees with the SVD / Jacobi route of the smaller sites
+    theta_svd, _ = _cuda.geig_dense_lowest(ad.clone(), bd.clone())
+    assert abs(theta.item() - theta_svd.item()) <= max(1e-8, 10 * cond * 2.2e-16) * abs(want)
+
+
+def test_cholesky_pencil_reports_an_indefinite_right_hand_side():
+    from tnpy_b200 import _cuda
+
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((300, 300))
+    b = np.eye(300)
+    b[17, 17] = -1.0
+    with pytest.raises(RuntimeError, match="positive definite"):
+        _cuda.geig_chol_lowest(dev(a + a.T), dev(b))
+
+
+def test_shift_invert_through_the_cholesky_pencil_beyond_the_dense_limit():
+    """n = 12, bond_dim 64 (exact: the state space is 4096-dimensional): the mid-chain sites have 4096 and 8192 unknowns,
+    beyond dense_pencil_dim, and go through tnpy_geig_chol_lowest.  Same anchors as the reference's test
+    (tests/test_finite_dmrg.py:56-72): nearest eigenvalue below the offset, the restored state is the ED
+    eigenvector, the energy is <H> on it -- all atol 1e-6."""
+    from tnpy_b200.finite_dmrg import ShiftInvertDMRG
+    from tnpy_b200.model import RandomHeisenberg
+
+    n, h, seed, offset = 12, 10.5, 2022, 0.1
+    model = RandomHeisenberg(n=n, h=h, seed=seed)
+    evals, evecs = np.linalg.eigh(oracle.full_hamiltonian(model.mpo.arrays))
+    idx = np.where(evals < offset)[0].max()
+    shifted = RandomHeisenberg(n=n, h=h, seed=seed, offset=offset)
+    sidmrg = ShiftInvertDMRG(shifted.mpo, bond_dim=2**6, offset=offset, seed=1)
+    energies = sidmrg.run(tol=1e-8)
+    sizes = [st.get("n_matvec", 0) for st in sidmrg.solver_stats]
+    assert all(st["dense"] for st in sidmrg.solver_stats) and max(sizes) > 0  # some sites went through Lanczos
+    np.testing.assert_allclose(energies[-1], evals[idx], atol=1e-6)
+    vec = sidmrg.restored_mps.to_dense()
+    if not np.allclose(vec, evecs[:, idx], atol=1e-6):
+        np.testing.assert_allclose(-vec, evecs[:, idx], atol=1e-6)
+    np.testing.assert_allclose(energies[-1], sidmrg.measurements.expectation_value(model.mpo), atol=1e-6)

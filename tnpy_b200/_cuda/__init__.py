@@ -97,6 +97,9 @@ SIGNATURES = {
     ),
     "tnpy_geig_dense_workspace_bytes": (c_size_t, [c_int]),
     "tnpy_geig_dense_lowest": (c_int, [_PD, _PD, c_int, _PD, _PD, c_void_p, c_size_t, c_void_p]),
+    "tnpy_geig_chol_workspace_bytes": (c_size_t, [c_int]),
+    "tnpy_geig_chol_lowest": (c_int, [_PD, _PD, c_int, c_double, c_int, _PD, _PD, ctypes.POINTER(c_double), c_void_p,
+                              c_size_t, c_void_p]),
     "tnpy_eigh_workspace_bytes": (c_size_t, [c_int]),
     "tnpy_eigh_lowest": (c_int, [_PD, c_int, _PD, _PD, c_void_p, c_size_t, c_void_p]),
     "tnpy_svd_workspace_bytes": (c_size_t, [c_int, c_int]),
@@ -613,6 +616,29 @@ def geig_dense_lowest(a, b):
     check(lib.tnpy_geig_dense_lowest(_ptr(a), _ptr(b), n, _ptr(theta), _ptr(x), _ptr(ws), nbytes, _stream()),
           "tnpy_geig_dense_lowest")
     return theta, x
+
+
+def geig_chol_lowest(a, b, tol: float = 1e-12, max_matvec: int = 2000):
+    """Lowest eigenpair of the dense pencil a x = lambda b x through a Cholesky factor of b and the on-device
+    Lanczos solver (a, b left intact; thousands to tens of thousands of unknowns).  Returns (theta 0-d, x, stats)
+    with x^T b x = 1; raises RuntimeError when b is not positive definite to working precision."""
+    import torch
+
+    _need_cuda(a, b)
+    n = a.shape[0]
+    lib = load()
+    nbytes = lib.tnpy_geig_chol_workspace_bytes(n)
+    ws = _scratch.get(nbytes)
+    theta = torch.empty((), dtype=torch.float64, device=a.device)
+    x = torch.empty(n, dtype=torch.float64, device=a.device)
+    stats = (c_double * 8)()
+    rc = lib.tnpy_geig_chol_lowest(_ptr(a), _ptr(b), n, float(tol), int(max_matvec), _ptr(theta), _ptr(x), stats,
+                                   _ptr(ws), nbytes, _stream())
+    if rc == ENOCONV and "positive definite" in last_error():
+        raise RuntimeError(f"tnpy_geig_chol_lowest failed (code {rc}): {last_error()}")
+    check(rc, "tnpy_geig_chol_lowest", allow_noconv=True)
+    return theta, x, {"theta": stats[0], "resid": stats[1], "n_matvec": int(stats[2]), "n_restart": int(stats[3]),
+                      "converged": bool(stats[4]), "anorm": stats[5]}
 
 
 def eigh_lowest(H):

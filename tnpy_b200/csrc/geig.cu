@@ -9,7 +9,7 @@
 // One 64-byte status read-back per iteration, vectors never leave the device.
 #include <math.h>
 
-#include "common.cuh"
+#include "chol.cuh"
 
 namespace tnpy {
 
@@ -395,4 +395,102 @@ extern "C" int tnpy_geig_dense_lowest(double* a, double* b, int n, double* theta
   // x = X z = sum_k z[k] * Xt[k][:]
   TNPY_TRY(combine(Xt, n, n, z, 1, 1, x, n, n, stream));
   return TNPY_OK;
+}
+
+// ---- the same pencil through a Cholesky factor of b and the on-device Lanczos solver ----------------------------
+// b = D C C^T D (D = sqrt(diag b): the factorisation then only sees the conditioning of the scaled matrix),
+// X = D^-1 C^-T, S = X^T a X, lowest eigenpair (theta, z) of S by the thick-restart Lanczos of csrc/lanczos.cu --
+// S enters it as a "left environment" with one channel (H_eff y = S^T y), so the vectors stay on the device and the
+// small-site fused steps apply -- and x = X z, x^T b x = 1.  Unlike tnpy_geig_dense_lowest (Jacobi SVD of b, Jacobi
+// eigensolve of S: O(n^3) per sweep of each) this is three O(n^3) passes on the FP64 tensor pipe plus O(n^2) per
+// Lanczos step, which is what makes pencils of 10^4 unknowns practical.  The lowest eigenvalue of S is 1 / (E - eps)
+// for the level just below the shift: an outlier of a spectrum clustered around zero, so Lanczos needs few steps.
+namespace tnpy {
+__global__ void pad_copy_kernel(const double* __restrict__ in, int n, double* __restrict__ out, int np) {
+  const int64_t total = (int64_t)np * np;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e / np), j = (int)(e % np);
+    out[e] = (i < n && j < n) ? in[(int64_t)i * n + j] : 0.0;
+  }
+}
+// deterministic start vector with every component non-zero
+__global__ void start_vector_kernel(double* __restrict__ z, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    unsigned h = (unsigned)i * 2654435761u + 12345u;
+    h ^= h >> 15;
+    h *= 2246822519u;
+    h ^= h >> 13;
+    z[i] = 0.5 + (double)(h & 0xffffu) / 65536.0;
+  }
+}
+__global__ void scale_by_kernel(double* __restrict__ x, const double* __restrict__ dinv, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] *= dinv[i];
+}
+}  // namespace tnpy
+
+extern "C" size_t tnpy_geig_chol_workspace_bytes(int n) {
+  if (n <= 0) return 0;
+  const size_t np = (size_t)chol_padded_dim(n);
+  return 4 * Workspace::need(np * np) + Workspace::need(np * kCholBlock) + 2 * Workspace::need(np) + Workspace::need(64, 1) +
+         tnpy_eig_workspace_bytes(n, 1, 1, 1, 1, 0) + 4096;
+}
+
+extern "C" int tnpy_geig_chol_lowest(const double* a, const double* b, int n, double tol, int max_matvec,
+                                     double* theta_dev, double* x, double* stats_host, void* workspace,
+                                     size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TNPY_CHECK_ARG(a && b && theta_dev && x && n > 0, "bad argument");
+  const int np = chol_padded_dim(n);
+  Workspace ws(workspace, workspace_bytes);
+  const size_t nn = (size_t)np * np;
+  double* G = ws.take<double>(nn);     // scaled b -> its Cholesky factor -> S
+  double* Cinv = ws.take<double>(nn);
+  double* X = ws.take<double>(nn);     // scratch of the inverse, then X = D^-1 C^-T
+  double* Y = ws.take<double>(nn);
+  double* Dk = ws.take<double>((size_t)np * kCholBlock);
+  double* dinv = ws.take<double>(np);
+  double* z = ws.take<double>(np);
+  int* fail = ws.take<int>(16);
+  if (!G || !Cinv || !X || !Y || !Dk || !dinv || !z || !fail) {
+    set_error("tnpy_geig_chol_lowest: workspace too small (%zu bytes given, %zu needed)", workspace_bytes,
+              tnpy_geig_chol_workspace_bytes(n));
+    return TNPY_EWORKSPACE;
+  }
+  const int grid = sm_count() * 8;
+  TNPY_CUDA_OK(cudaMemsetAsync(fail, 0, 16 * sizeof(int), stream));
+  pad_copy_kernel<<<grid, 256, 0, stream>>>(b, n, G, np);
+  TNPY_LAUNCH_OK();
+  TNPY_TRY(spd_scale_pad(G, n, np, dinv, fail, stream));
+  TNPY_TRY(cholesky_inverse(G, np, Cinv, X, Dk, fail, stream));
+  int failed = 0;
+  TNPY_CUDA_OK(cudaMemcpyAsync(&failed, fail, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  TNPY_CUDA_OK(cudaStreamSynchronize(stream));
+  if (failed) {
+    set_error("tnpy_geig_chol_lowest: the right-hand matrix is not positive definite to working precision (n = %d)", n);
+    return TNPY_ENOCONV;
+  }
+  // X[k][i] = dinv[k] * Cinv[i][k]
+  TNPY_TRY(transpose(Cinv, np, np, np, X, np, dinv, stream));
+  // Y = a X (a symmetric: sum_k a[k][i] X[k][j]);  S = X^T Y, stored densely (n x n) over G
+  TNPY_TRY(gemm_tn(a, n, X, np, plain_out(Y, np, n), n, n, n, 0, TNPY_GEMM_FP64, stream));
+  double* S = G;
+  TNPY_TRY(gemm_tn(X, np, Y, np, plain_out(S, n, n), n, n, n, 0, TNPY_GEMM_FP64, stream));
+  start_vector_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(z, n);
+  TNPY_LAUNCH_OK();
+  double stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  char* rest = static_cast<char*>(workspace) + ws.used;
+  const int rc = tnpy_eig_lowest(S, device_one(), device_one(), z, n, 1, 1, 1, 1, 0, tol, max_matvec, 0, stats, rest,
+                                 workspace_bytes - ws.used, stream_);
+  if (stats_host)
+    for (int i = 0; i < 8; ++i) stats_host[i] = stats[i];
+  if (rc != TNPY_OK && rc != TNPY_ENOCONV) return rc;
+  // x = X z: x[k] = dinv[k] * sum_i Cinv[i][k] z[i]
+  TNPY_TRY(gemm_tn(Cinv, np, z, 1, plain_out(x, 1, n), n, 1, n, 0, TNPY_GEMM_GENERIC, stream));
+  scale_by_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(x, dinv, n);
+  TNPY_LAUNCH_OK();
+  TNPY_CUDA_OK(cudaMemcpyAsync(theta_dev, &stats[0], sizeof(double), cudaMemcpyHostToDevice, stream));
+  TNPY_CUDA_OK(cudaStreamSynchronize(stream));
+  return rc;
 }

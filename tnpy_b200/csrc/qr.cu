@@ -14,7 +14,7 @@
 // from a random state can be that ill-conditioned) or when a pivot broke down (reported as +inf).
 #include <math.h>
 
-#include "common.cuh"
+#include "chol.cuh"
 
 namespace tnpy {
 namespace {
@@ -258,6 +258,8 @@ __global__ void __launch_bounds__(256) transpose_kernel(const double* __restrict
   }
 }
 
+}  // namespace
+
 int transpose(const double* in, int rows, int cols, int64_t ld_in, double* out, int64_t ld_out, const double* scale,
               cudaStream_t stream) {
   dim3 grid(ceil_div(cols, 32), ceil_div(rows, 32));
@@ -265,6 +267,8 @@ int transpose(const double* in, int rows, int cols, int64_t ld_in, double* out, 
   TNPY_LAUNCH_OK();
   return TNPY_OK;
 }
+
+namespace {
 
 // out = max |G - I| over n x n as the bit pattern of a non-negative double (ordered like uint64); NaN or a
 // raised fail flag gives +inf
@@ -295,16 +299,28 @@ int gemm_fp64(const double* A, int64_t lda, const double* B, int64_t ldb, double
   return gemm_tn(A, lda, B, ldb, plain_out(C, ldc, M), M, N, K, 0, algo, stream);
 }
 
-int padded_dim(int n) {
+int stream_grid(int64_t total) {
+  int64_t want = (total + 255) / 256;
+  int64_t cap = (int64_t)sm_count() * 8;
+  return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+}  // namespace
+
+int chol_padded_dim(int n) {
   int blocks = ceil_div(n, NB), p = 1;
   while (p < blocks) p <<= 1;
   return p * NB;
 }
 
-int stream_grid(int64_t total) {
-  int64_t want = (total + 255) / 256;
-  int64_t cap = (int64_t)sm_count() * 8;
-  return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+// G (np x np, leading n x n = a symmetric positive definite matrix) -> D^-1 G D^-1 with D = sqrt(diag G), identity
+// on the padding; dinv (np) receives 1 / D (1 on the padding).  A non-positive diagonal entry raises *fail.
+int spd_scale_pad(double* G, int n, int np, double* dinv, int* fail, cudaStream_t stream) {
+  gram_dinv_kernel<<<ceil_div(np, 256), 256, 0, stream>>>(G, np, n, np, dinv, fail);
+  TNPY_LAUNCH_OK();
+  gram_scale_pad_kernel<<<stream_grid((int64_t)np * np), 256, 0, stream>>>(G, np, n, np, dinv, 0.0);
+  TNPY_LAUNCH_OK();
+  return TNPY_OK;
 }
 
 // G (np x np, lower part = SPD matrix, destroyed: holds L afterwards)  ->  Cinv = L^-1 (np x np, lower)
@@ -340,6 +356,8 @@ int cholesky_inverse(double* G, int np, double* Cinv, double* Tmp, double* Dk, i
   return TNPY_OK;
 }
 
+namespace {
+int padded_dim(int n) { return chol_padded_dim(n); }
 }  // namespace
 }  // namespace tnpy
 

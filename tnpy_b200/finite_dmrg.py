@@ -265,22 +265,36 @@ class ShiftInvertDMRG(FiniteDMRG):
         arrays[-1] = arrays[-1][:, :, 0]
         self._restored_mps = MatrixProductState(arrays)
 
-    #: up to this many unknowns the local pencil is solved densely on the device (the projected H^2 is too
-    #: ill-conditioned for inverse-free Krylov iterations, see csrc/geig.cu); larger sites iterate and raise
-    #: RuntimeError when the iteration does not converge.  The reference's own test size (n=10, chi=64: bonds of at
-    #: most 32, 1024 unknowns) is inside the dense range; tnpy_heff_dense allows up to 4096.
+    #: The projected H^2 is too ill-conditioned (1e9 and up) for inverse-free Krylov iterations on the pencil itself
+    #: (csrc/geig.cu), so the local pencil is formed densely on the device and reduced to a standard problem:
+    #: up to ``dense_pencil_dim`` unknowns through a Jacobi SVD of the right-hand matrix (tolerates a numerically
+    #: singular one; the reference's own test size -- n=10, chi=64: 1024 unknowns -- is in this range), up to
+    #: ``cholesky_pencil_dim`` through a Cholesky factor and the on-device Lanczos solver (tnpy_geig_chol_lowest:
+    #: O(N^3) tensor-pipe work, seconds at N = 16384; needs 6 N^2 doubles).  Larger sites fall to the iterative
+    #: solver, which raises RuntimeError when it does not converge.
     dense_pencil_dim = 2048
+    cholesky_pencil_dim = 32768
 
     def _solve_on_device(self, site: int, tol: float, **kwargs) -> float:
         env, env2 = self._env, self._env2
         psi = env.device_tensor(site)
-        if psi.numel() <= self.dense_pencil_dim:
+        if psi.numel() <= max(self.dense_pencil_dim, self.cholesky_pencil_dim):
             a = env.one_site_full_matrix_device(site)
             b = env2.one_site_full_matrix_device(site)
-            theta, x = _cuda.geig_dense_lowest(a, b)
+            if psi.numel() <= self.dense_pencil_dim:
+                theta, x = _cuda.geig_dense_lowest(a, b)
+                stats = {"n_matvec": 0}
+            else:
+                theta, x, stats = _cuda.geig_chol_lowest(a, b, tol=min(tol, 1e-10))
+                if not stats["converged"]:
+                    raise RuntimeError(
+                        f"ShiftInvertDMRG: the Lanczos solve of the reduced pencil at site {site} ({psi.numel()} unknowns) "
+                        f"stopped at residual {stats['resid']:.3e} after {stats['n_matvec']} matvecs; the site tensor was "
+                        "left unchanged."
+                    )
             psi.copy_(x.reshape(psi.shape))
             env._dirty.add(site)
-            self.solver_stats.append({"site": site, "dense": True, "n_matvec": 0})
+            self.solver_stats.append({"site": site, "dense": True, **stats})
             return float(theta.item())
         la, wa, ra = env.operands(site)
         lm, wm, rm = env2.operands(site)
@@ -298,8 +312,8 @@ class ShiftInvertDMRG(FiniteDMRG):
             raise RuntimeError(
                 f"ShiftInvertDMRG: the iterative pencil solve at site {site} ({psi.numel()} unknowns) did not converge "
                 f"(residual {stats['resid']:.3e} after {stats['n_iter']} iterations); the site tensor was left unchanged. "
-                f"Sites up to dense_pencil_dim = {self.dense_pencil_dim} unknowns are solved densely -- raise it (<= 4096) "
-                "or lower the bond dimension."
+                f"Sites up to cholesky_pencil_dim = {self.cholesky_pencil_dim} unknowns are solved through dense "
+                "factorisations -- raise it (memory: 6 N^2 doubles) or lower the bond dimension."
             )
         env._dirty.add(site)
         self.solver_stats.append({"site": site, "dense": False, "n_matvec": 2 * stats["n_iter"], **stats})
