@@ -177,8 +177,9 @@ int tnpy_env_update_left_rows(const double* L_rows, const double* A, const doubl
                               size_t workspace_bytes, void* stream);
 
 /* ---- a6: Environment.one_site_full_matrix  (matrix_product_state.py:372-409) ---------------
- * H[(l,p,r),(m,q,s)] = sum_{a,b} L[l,a,m] W[a,b,p,q] R[r,b,s] dense, N = l*d*r <= 4096; H is N x N
- * row-major (one thread per matrix element).  Workspace: none needed (query returns a token size). */
+ * H[(l,p,r),(m,q,s)] = sum_{a,b} L[l,a,m] W[a,b,p,q] R[r,b,s] dense, N = l*d*r <= 32768; H is N x N
+ * row-major.  With the workspace of the query (d^2 l^2 wr doubles) the matrix is built in two passes -- L W first,
+ * then wr multiply-adds per entry --, without one (NULL, 0) or for tiny sites in one pass of wl * wr per entry. */
 size_t tnpy_heff_dense_workspace_bytes(int l, int r, int wl, int wr, int d);
 int tnpy_heff_dense(const double* L, const double* W, const double* R, double* H,
                     int l, int r, int wl, int wr, int d, void* workspace, size_t workspace_bytes,

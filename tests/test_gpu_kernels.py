@@ -145,7 +145,8 @@ def test_env_updates_edges(cu):
     assert rel_err(got, oracle.env_update_right(None, An, W0)) < 1e-12
 
 
-@pytest.mark.parametrize("l,r,wl,wr,d", [(2, 4, 5, 5, 2), (4, 8, 5, 6, 2), (1, 2, 1, 5, 2), (3, 3, 4, 4, 3)])
+@pytest.mark.parametrize("l,r,wl,wr,d", [(2, 4, 5, 5, 2), (4, 8, 5, 6, 2), (1, 2, 1, 5, 2), (3, 3, 4, 4, 3),
+                                          (16, 12, 6, 5, 2), (8, 9, 25, 25, 2), (1, 40, 1, 5, 2), (33, 1, 5, 1, 2)])
 def test_heff_dense(cu, l, r, wl, wr, d):
     rng = np.random.default_rng(l + 10 * r)
     L, W, R, _ = random_operands(rng, l, r, wl, wr, d)

@@ -180,7 +180,7 @@ def test_cholesky_pencil_reports_an_indefinite_right_hand_side():
 
 
 def test_shift_invert_through_the_cholesky_pencil_beyond_the_dense_limit():
-    """n = 12, bond_dim 64 (exact: the state space is 4096-dimensional): the mid-chain sites have 4096 and 8192 unknowns,
+    """n = 12, bond_dim 64 (exact: the state space is 4096-dimensional): the mid-chain sites have 4096 unknowns,
     beyond dense_pencil_dim, and go through tnpy_geig_chol_lowest.  Same anchors as the reference's test
     (tests/test_finite_dmrg.py:56-72): nearest eigenvalue below the offset, the restored state is the ED
     eigenvector, the energy is <H> on it -- all atol 1e-6."""

@@ -463,7 +463,9 @@ def heff_dense(L, W, R, l, r):
     wl, wr, d = W.shape[0], W.shape[1], W.shape[2]
     n = l * d * r
     out = torch.empty((n, n), dtype=torch.float64, device=W.device)
-    rc = load().tnpy_heff_dense(_ptr(L), _ptr(W), _ptr(R), _ptr(out), l, r, wl, wr, d, None, 0, _stream())
+    nbytes = load().tnpy_heff_dense_workspace_bytes(l, r, wl, wr, d)
+    ws = _scratch.get(nbytes)
+    rc = load().tnpy_heff_dense(_ptr(L), _ptr(W), _ptr(R), _ptr(out), l, r, wl, wr, d, _ptr(ws), nbytes, _stream())
     check(rc, "tnpy_heff_dense")
     return out
 

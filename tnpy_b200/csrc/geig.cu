@@ -398,20 +398,70 @@ extern "C" int tnpy_geig_dense_lowest(double* a, double* b, int n, double* theta
 }
 
 // ---- the same pencil through a Cholesky factor of b and the on-device Lanczos solver ----------------------------
-// b = D C C^T D (D = sqrt(diag b): the factorisation then only sees the conditioning of the scaled matrix),
-// X = D^-1 C^-T, S = X^T a X, lowest eigenpair (theta, z) of S by the thick-restart Lanczos of csrc/lanczos.cu --
-// S enters it as a "left environment" with one channel (H_eff y = S^T y), so the vectors stay on the device and the
-// small-site fused steps apply -- and x = X z, x^T b x = 1.  Unlike tnpy_geig_dense_lowest (Jacobi SVD of b, Jacobi
-// eigensolve of S: O(n^3) per sweep of each) this is three O(n^3) passes on the FP64 tensor pipe plus O(n^2) per
-// Lanczos step, which is what makes pencils of 10^4 unknowns practical.  The lowest eigenvalue of S is 1 / (E - eps)
-// for the level just below the shift: an outlier of a spectrum clustered around zero, so Lanczos needs few steps.
+// b = D U^T U D (D = sqrt(diag b): the factorisation then only sees the conditioning of the scaled matrix, U upper
+// triangular), S = U^-T (D^-1 a D^-1) U^-1, lowest eigenpair (theta, z) of S by the thick-restart Lanczos of
+// csrc/lanczos.cu -- S enters it as a "left environment" with one channel (H_eff y = S^T y), so the vectors stay on the
+// device and the fused small-site steps apply -- and x = D^-1 U^-1 z, x^T b x = 1.
+//
+// Everything O(n^3) is a TN GEMM on the FP64 tensor pipe, which is why the factor is the *upper* one, built by row
+// panels of 512: with U_kk = L^T from the small blocked Cholesky of the diagonal block (csrc/qr.cu, also its explicit
+// inverse),
+//     row panel   U_k,rest = L^-1 G_k,rest                       = (L^-T)^T G_k,rest          K = 512
+//     trailing    G_rest,rest -= U_k,rest^T U_k,rest              = (-U_k,rest)^T U_k,rest     K = 512
+//     U^T Y = R   Y_k = L^-1 (R_k - U_(rows < k, cols k)^T Y_(rows < k))                       K = 512 k
+// all have the contracted index slowest in both operands, as gemm_tn wants; S = U^-T (U^-T a')^T is two such forward
+// substitutions with a transpose in between.  Unlike tnpy_geig_dense_lowest (Jacobi SVD of b, Jacobi eigensolve of S:
+// O(n^3) per sweep of each) this is ~2.7 n^3 tensor-pipe flops plus O(n^2) per Lanczos step, which is what makes
+// pencils of 10^4 unknowns practical.  The lowest eigenvalue of S is 1 / (E - eps) for the level just below the shift:
+// an outlier of a spectrum clustered around zero, so Lanczos needs few steps.
 namespace tnpy {
-__global__ void pad_copy_kernel(const double* __restrict__ in, int n, double* __restrict__ out, int np) {
+namespace {
+constexpr int kPanel = 512;
+
+// out (rows x cols, ld_out) = scale_row ? in * scale_row[i] * scale_col[j] : in, zero outside the n x n corner of `in`
+__global__ void pad_scale_kernel(const double* __restrict__ in, int n, int64_t ld_in, double* __restrict__ out, int np,
+                                 const double* __restrict__ dinv) {
   const int64_t total = (int64_t)np * np;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int i = (int)(e / np), j = (int)(e % np);
-    out[e] = (i < n && j < n) ? in[(int64_t)i * n + j] : 0.0;
+    double v = 0.0;
+    if (i < n && j < n) {
+      v = in[(int64_t)i * ld_in + j];
+      if (dinv) v *= dinv[i] * dinv[j];
+    }
+    out[e] = v;
   }
+}
+// dst (rows x cols, ld_dst) = src (rows x cols, ld_src); neg (same shape as dst, optional) = -src
+__global__ void block_copy_kernel(const double* __restrict__ src, int64_t ld_src, double* __restrict__ dst, int64_t ld_dst,
+                                  double* __restrict__ neg, int64_t ld_neg, int rows, int cols) {
+  const int64_t total = (int64_t)rows * cols;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e / cols), j = (int)(e % cols);
+    const double v = src[(int64_t)i * ld_src + j];
+    dst[(int64_t)i * ld_dst + j] = v;
+    if (neg) neg[(int64_t)i * ld_neg + j] = -v;
+  }
+}
+// dst (rows x cols, ld_dst) -= sub (rows x cols, ld_sub)
+__global__ void block_sub_kernel(double* __restrict__ dst, int64_t ld_dst, const double* __restrict__ sub, int64_t ld_sub,
+                                 int rows, int cols) {
+  const int64_t total = (int64_t)rows * cols;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e / cols), j = (int)(e % cols);
+    dst[(int64_t)i * ld_dst + j] -= sub[(int64_t)i * ld_sub + j];
+  }
+}
+// v[i] = z[i] - sum_j U[i][j] y[j] over `cols` columns (one warp per row); U, y already offset to the panel
+__global__ void __launch_bounds__(256) panel_gemv_sub_kernel(const double* __restrict__ U, int64_t ld, const double* __restrict__ y,
+                                                             const double* __restrict__ z, double* __restrict__ v, int rows,
+                                                             int cols) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  double s = 0.0;
+  for (int j = lane; j < cols; j += 32) s = fma(U[(int64_t)row * ld + j], y[j], s);
+  s = warp_sum(s);
+  if (lane == 0) v[row] = z[row] - s;
 }
 // deterministic start vector with every component non-zero
 __global__ void start_vector_kernel(double* __restrict__ z, int n) {
@@ -428,13 +478,94 @@ __global__ void scale_by_kernel(double* __restrict__ x, const double* __restrict
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) x[i] *= dinv[i];
 }
+
+int grid_for(int64_t total) {
+  const int64_t want = (total + 255) / 256, cap = (int64_t)sm_count() * 8;
+  return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+struct PanelScratch {
+  double *diag, *tmp, *dk;           // B x B each (dk: B x 64): the small Cholesky of a diagonal block
+  double *panel, *panel_neg;         // B x np
+  double *cinv_all, *cinvt_all;      // (np / B) blocks of B x B: L_kk^-1 and its transpose
+};
+
+// G (np x np, symmetric, full storage) -> U in its upper triangle (row panels; the diagonal blocks are left as they
+// were -- only their inverses, kept in ps.cinv_all / cinvt_all, are used afterwards)
+int cholesky_upper_blocked(double* G, int np, int B, const PanelScratch& ps, int* fail, cudaStream_t stream) {
+  const int nb = np / B;
+  for (int k = 0; k < nb; ++k) {
+    const int k0 = k * B, rem = np - k0 - B;
+    double* gkk = G + (int64_t)k0 * np + k0;
+    block_copy_kernel<<<grid_for((int64_t)B * B), 256, 0, stream>>>(gkk, np, ps.diag, B, nullptr, 0, B, B);
+    TNPY_LAUNCH_OK();
+    double* cinv = ps.cinv_all + (int64_t)k * B * B;
+    double* cinvt = ps.cinvt_all + (int64_t)k * B * B;
+    TNPY_TRY(cholesky_inverse(ps.diag, B, cinv, ps.tmp, ps.dk, fail, stream));
+    TNPY_TRY(transpose(cinv, B, B, B, cinvt, B, nullptr, stream));
+    if (rem == 0) break;
+    double* gpanel = gkk + B;  // rows of block k, columns to the right
+    // U_k,rest = L^-1 G_k,rest: C[i][j] = sum_l cinvt[l][i] G[k0 + l][k0 + B + j]
+    TNPY_TRY(gemm_tn(cinvt, B, gpanel, np, plain_out(ps.panel, rem, B), B, rem, B, 0, TNPY_GEMM_FP64, stream));
+    block_copy_kernel<<<grid_for((int64_t)B * rem), 256, 0, stream>>>(ps.panel, rem, gpanel, np, ps.panel_neg, rem, B, rem);
+    TNPY_LAUNCH_OK();
+    // G_rest,rest += (-U_k,rest)^T U_k,rest
+    TNPY_TRY(gemm_tn(ps.panel_neg, rem, ps.panel, rem, plain_out(gkk + (int64_t)B * np + B, np, rem), rem, rem, B, 1,
+                     TNPY_GEMM_FP64, stream));
+  }
+  return TNPY_OK;
+}
+
+// R (np x cols, ld) <- U^-T R, block row by block row (U in the upper triangle of G, diagonal blocks through cinvt_all)
+int forward_substitute(const double* G, int np, int B, const PanelScratch& ps, double* R, int64_t ld, int cols,
+                       cudaStream_t stream) {
+  const int nb = np / B;
+  for (int k = 0; k < nb; ++k) {
+    const int k0 = k * B;
+    double* rk = R + (int64_t)k0 * ld;
+    if (k > 0) {
+      // T = U[0:k0, block k]^T Y[0:k0, :]   (K = k0)
+      TNPY_TRY(gemm_tn(G + k0, np, R, ld, plain_out(ps.panel, cols, B), B, cols, k0, 0, TNPY_GEMM_FP64, stream));
+      block_sub_kernel<<<grid_for((int64_t)B * cols), 256, 0, stream>>>(rk, ld, ps.panel, cols, B, cols);
+      TNPY_LAUNCH_OK();
+    }
+    // Y_k = L^-1 (.)
+    TNPY_TRY(gemm_tn(ps.cinvt_all + (int64_t)k * B * B, B, rk, ld, plain_out(ps.panel, cols, B), B, cols, B, 0, TNPY_GEMM_FP64,
+                     stream));
+    block_copy_kernel<<<grid_for((int64_t)B * cols), 256, 0, stream>>>(ps.panel, cols, rk, ld, nullptr, 0, B, cols);
+    TNPY_LAUNCH_OK();
+  }
+  return TNPY_OK;
+}
+
+// y (np) = U^-1 z, from the last block row upwards; v: B doubles of scratch
+int backward_substitute(const double* G, int np, int B, const PanelScratch& ps, const double* z, double* y, double* v,
+                        cudaStream_t stream) {
+  const int nb = np / B;
+  for (int k = nb - 1; k >= 0; --k) {
+    const int k0 = k * B, rem = np - k0 - B;
+    const double* rhs = z + k0;
+    if (rem > 0) {
+      panel_gemv_sub_kernel<<<ceil_div(B, 8), 256, 0, stream>>>(G + (int64_t)k0 * np + k0 + B, np, y + k0 + B, z + k0, v, B, rem);
+      TNPY_LAUNCH_OK();
+      rhs = v;
+    }
+    // y_k = U_kk^-1 rhs = L^-T rhs: y_k[i] = sum_l cinv[l][i] rhs[l]
+    TNPY_TRY(gemm_tn(ps.cinv_all + (int64_t)k * B * B, B, rhs, 1, plain_out(y + k0, 1, B), B, 1, B, 0, TNPY_GEMM_GENERIC, stream));
+  }
+  return TNPY_OK;
+}
+}  // namespace
 }  // namespace tnpy
+
+static size_t chol_panel(int np) { return (size_t)(np < tnpy::kPanel ? np : tnpy::kPanel); }
 
 extern "C" size_t tnpy_geig_chol_workspace_bytes(int n) {
   if (n <= 0) return 0;
-  const size_t np = (size_t)chol_padded_dim(n);
-  return 4 * Workspace::need(np * np) + Workspace::need(np * kCholBlock) + 2 * Workspace::need(np) + Workspace::need(64, 1) +
-         tnpy_eig_workspace_bytes(n, 1, 1, 1, 1, 0) + 4096;
+  const size_t np = (size_t)chol_padded_dim(n), B = chol_panel((int)np);
+  return 3 * Workspace::need(np * np) + Workspace::need((size_t)n * n) + 2 * Workspace::need(B * B) +
+         Workspace::need(B * kCholBlock) + 2 * Workspace::need(B * np) + 2 * Workspace::need(np * B) + 3 * Workspace::need(np) +
+         Workspace::need(B) + Workspace::need(64, 1) + tnpy_eig_workspace_bytes(n, 1, 1, 1, 1, 0) + 8192;
 }
 
 extern "C" int tnpy_geig_chol_lowest(const double* a, const double* b, int n, double tol, int max_matvec,
@@ -442,28 +573,37 @@ extern "C" int tnpy_geig_chol_lowest(const double* a, const double* b, int n, do
                                      size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   TNPY_CHECK_ARG(a && b && theta_dev && x && n > 0, "bad argument");
-  const int np = chol_padded_dim(n);
+  const int np = chol_padded_dim(n), B = (int)chol_panel(np);
   Workspace ws(workspace, workspace_bytes);
   const size_t nn = (size_t)np * np;
-  double* G = ws.take<double>(nn);     // scaled b -> its Cholesky factor -> S
-  double* Cinv = ws.take<double>(nn);
-  double* X = ws.take<double>(nn);     // scratch of the inverse, then X = D^-1 C^-T
-  double* Y = ws.take<double>(nn);
-  double* Dk = ws.take<double>((size_t)np * kCholBlock);
+  double* G = ws.take<double>(nn);   // scaled b -> U (upper triangle)
+  double* Y = ws.take<double>(nn);   // scaled a -> U^-T a'
+  double* Yt = ws.take<double>(nn);  // its transpose -> S (padded)
+  double* S = ws.take<double>((size_t)n * n);
+  PanelScratch ps;
+  ps.diag = ws.take<double>((size_t)B * B);
+  ps.tmp = ws.take<double>((size_t)B * B);
+  ps.dk = ws.take<double>((size_t)B * kCholBlock);
+  ps.panel = ws.take<double>((size_t)B * np);
+  ps.panel_neg = ws.take<double>((size_t)B * np);
+  ps.cinv_all = ws.take<double>((size_t)np * B);
+  ps.cinvt_all = ws.take<double>((size_t)np * B);
   double* dinv = ws.take<double>(np);
   double* z = ws.take<double>(np);
+  double* y = ws.take<double>(np);
+  double* v = ws.take<double>(B);
   int* fail = ws.take<int>(16);
-  if (!G || !Cinv || !X || !Y || !Dk || !dinv || !z || !fail) {
+  if (!G || !Y || !Yt || !S || !ps.diag || !ps.tmp || !ps.dk || !ps.panel || !ps.panel_neg || !ps.cinv_all ||
+      !ps.cinvt_all || !dinv || !z || !y || !v || !fail) {
     set_error("tnpy_geig_chol_lowest: workspace too small (%zu bytes given, %zu needed)", workspace_bytes,
               tnpy_geig_chol_workspace_bytes(n));
     return TNPY_EWORKSPACE;
   }
-  const int grid = sm_count() * 8;
   TNPY_CUDA_OK(cudaMemsetAsync(fail, 0, 16 * sizeof(int), stream));
-  pad_copy_kernel<<<grid, 256, 0, stream>>>(b, n, G, np);
+  pad_scale_kernel<<<grid_for((int64_t)nn), 256, 0, stream>>>(b, n, n, G, np, nullptr);
   TNPY_LAUNCH_OK();
-  TNPY_TRY(spd_scale_pad(G, n, np, dinv, fail, stream));
-  TNPY_TRY(cholesky_inverse(G, np, Cinv, X, Dk, fail, stream));
+  TNPY_TRY(spd_scale_pad(G, n, np, dinv, fail, stream));  // G <- D^-1 b D^-1, identity on the padding
+  TNPY_TRY(cholesky_upper_blocked(G, np, B, ps, fail, stream));
   int failed = 0;
   TNPY_CUDA_OK(cudaMemcpyAsync(&failed, fail, sizeof(int), cudaMemcpyDeviceToHost, stream));
   TNPY_CUDA_OK(cudaStreamSynchronize(stream));
@@ -471,12 +611,14 @@ extern "C" int tnpy_geig_chol_lowest(const double* a, const double* b, int n, do
     set_error("tnpy_geig_chol_lowest: the right-hand matrix is not positive definite to working precision (n = %d)", n);
     return TNPY_ENOCONV;
   }
-  // X[k][i] = dinv[k] * Cinv[i][k]
-  TNPY_TRY(transpose(Cinv, np, np, np, X, np, dinv, stream));
-  // Y = a X (a symmetric: sum_k a[k][i] X[k][j]);  S = X^T Y, stored densely (n x n) over G
-  TNPY_TRY(gemm_tn(a, n, X, np, plain_out(Y, np, n), n, n, n, 0, TNPY_GEMM_FP64, stream));
-  double* S = G;
-  TNPY_TRY(gemm_tn(X, np, Y, np, plain_out(S, n, n), n, n, n, 0, TNPY_GEMM_FP64, stream));
+  // S = U^-T a' U^-1 = U^-T (U^-T a')^T, a' = D^-1 a D^-1 (zero on the padding)
+  pad_scale_kernel<<<grid_for((int64_t)nn), 256, 0, stream>>>(a, n, n, Y, np, dinv);
+  TNPY_LAUNCH_OK();
+  TNPY_TRY(forward_substitute(G, np, B, ps, Y, np, np, stream));
+  TNPY_TRY(transpose(Y, np, np, np, Yt, np, nullptr, stream));
+  TNPY_TRY(forward_substitute(G, np, B, ps, Yt, np, np, stream));
+  block_copy_kernel<<<grid_for((int64_t)n * n), 256, 0, stream>>>(Yt, np, S, n, nullptr, 0, n, n);
+  TNPY_LAUNCH_OK();
   start_vector_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(z, n);
   TNPY_LAUNCH_OK();
   double stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -486,8 +628,10 @@ extern "C" int tnpy_geig_chol_lowest(const double* a, const double* b, int n, do
   if (stats_host)
     for (int i = 0; i < 8; ++i) stats_host[i] = stats[i];
   if (rc != TNPY_OK && rc != TNPY_ENOCONV) return rc;
-  // x = X z: x[k] = dinv[k] * sum_i Cinv[i][k] z[i]
-  TNPY_TRY(gemm_tn(Cinv, np, z, 1, plain_out(x, 1, n), n, 1, n, 0, TNPY_GEMM_GENERIC, stream));
+  // x = D^-1 U^-1 z (z zero on the padding)
+  if (np > n) TNPY_CUDA_OK(cudaMemsetAsync(z + n, 0, sizeof(double) * (np - n), stream));
+  TNPY_TRY(backward_substitute(G, np, B, ps, z, y, v, stream));
+  TNPY_CUDA_OK(cudaMemcpyAsync(x, y, sizeof(double) * n, cudaMemcpyDeviceToDevice, stream));
   scale_by_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(x, dinv, n);
   TNPY_LAUNCH_OK();
   TNPY_CUDA_OK(cudaMemcpyAsync(theta_dev, &stats[0], sizeof(double), cudaMemcpyHostToDevice, stream));
