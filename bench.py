@@ -578,6 +578,8 @@ def run_single(args):
     torch.cuda.empty_cache()
     if args.sweep_n > 0:
         line["sweep_measured"] = measure_sweeps(args.sweep_n, chi, args.tol, args.sweep_count)
+    if not args.no_readme_run:
+        line["readme_config"] = measure_readme_config(args.tol)
     if args.scale_chi > 0:
         line["scaling_reference_n1"] = single_gpu_matvec(args.scale_chi, max(2, args.steps // 4))
     if not args.no_cpu_baseline:
@@ -618,6 +620,30 @@ def measure_sweeps(n, chi, tol, count):
     out["split_counts"] = dict(dmrg.environment.split_counts)
     out["note"] = ("measured whole sweeps at reduced n (the full n=100 chi=2048 run is recorded in profiles/, minutes per "
                    "cold sweep); the reference's tol=1e-8 stopping rule per local solve")
+    return out
+
+
+def measure_readme_config(tol):
+    """BASELINE configs[0], the reference README's own example, through the public API to convergence: XXZ n=100
+    delta=0.5, FiniteDMRG(chi=60).update(tol=1e-8) from the seeded random MPS -- the small-site regime, where whole
+    Lanczos steps run in one cooperative launch (csrc/lanczos_steps.cu).  Wall seconds with a device synchronise on
+    both sides; the second run is the warm-process number (the first pays one-time module / allocator set-up)."""
+    import torch
+
+    from tnpy_b200 import _cuda
+    from tnpy_b200.finite_dmrg import FiniteDMRG
+    from tnpy_b200.model import XXZ
+
+    out = {"config": "XXZ n=100 delta=0.5 chi=60 tol=%g to convergence (FiniteDMRG(mpo, chi=60).update(tol))" % tol, "runs": []}
+    for _ in range(2):
+        dmrg = FiniteDMRG(XXZ(n=100, delta=0.5).mpo, chi=60, seed=0)
+        torch.cuda.synchronize()
+        l0, t0 = _cuda.launch_count(), time.perf_counter()
+        energies = dmrg.update(tol=tol)
+        torch.cuda.synchronize()
+        out["runs"].append({"seconds": time.perf_counter() - t0, "launches": int(_cuda.launch_count() - l0),
+                            "sweeps": len(energies), "energy": energies[-1]})
+    out["seconds"] = min(r["seconds"] for r in out["runs"])
     return out
 
 
@@ -828,6 +854,7 @@ def main():
     ap.add_argument("--sweep-count", type=int, default=2, help="number of measured sweeps (the first is the cold one)")
     ap.add_argument("--scale-chi", type=int, default=8192, help="chi of the same-workload single-GPU point of the scaling run (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-readme-run", action="store_true", help="skip the XXZ n=100 chi=60 run to convergence (about 3 s)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

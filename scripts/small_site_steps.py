@@ -59,6 +59,9 @@ def main():
         key = "fused" if fused else "general"
         out[key] = {"solve_10_steps_us": 1e6 * t10, "solve_30_steps_us": 1e6 * t30, "us_per_step": 1e6 * (t30 - t10) / 20,
                     "looks_10": s10["looks"], "looks_30": s30["looks"], "n_matvec_30": s30["n_matvec"]}
+    if not cu.load().tnpy_set_fused_steps(1) or chi * d * chi > 32768:
+        print(json.dumps(out))  # beyond the fused path's range: the general solver's numbers only
+        return
     # phase durations inside one 30-step launch (ns, CTA 0): P1, barrier 1, P2, P3, P4, P5 (each up to the point where
     # the CTA arrives at the following barrier, i.e. including the wait at the preceding one), barrier 5, P6
     trace = torch.zeros(64 * 16, dtype=torch.int64, device="cuda")

@@ -380,10 +380,10 @@ static int eig_lowest_impl(const tnpy_comm* comm, const double* L, const double*
   // somebody looks at the result: on restart steps, at the matvec limit, and every `stride` steps.  The stride comes
   // from the residual history: Lanczos residuals fall geometrically, so the two last looks give a rate and with it
   // the number of steps left to the threshold; the next look happens after half of those, at most `stride_cap` steps
-  // on (3 where a matvec costs milliseconds -- an overshoot step is then dearer than a look -- 8 for small sites,
-  // where the Ritz solve is the dearest kernel of a step: 38 % of the device time of XXZ n=100 chi=60 before this).
+  // on (3 where a matvec costs milliseconds -- an overshoot step is then dearer than a look -- 8 below 2^20 unknowns,
+  // where a look costs as much as one to three steps: at (256, 2, 256) a step is 0.2 ms, a Ritz solve at m = 30 0.25 ms).
   // The stopping rule itself is unchanged; a local solve can overshoot by at most stride_cap - 1 matvecs.
-  const int stride_cap = n_full >= (1 << 20) ? 3 : (n_full >= (1 << 16) ? 4 : 8);
+  const int stride_cap = n_full >= (1 << 20) ? 3 : 8;
   double last_resid = 0.0, last_anorm = 0.0;
   int last_look_matvec = 0;
   int since_check = 0, stride = 1;
