@@ -91,6 +91,11 @@ struct GemmOut {
 };
 int gemm_tn(const double* A, int64_t lda, const double* B, int64_t ldb, GemmOut out, int M, int N, int K,
             int accumulate, int algo, cudaStream_t stream);
+// the same with scratch for split-K partials (gemm_splitk_doubles(M, N, K) doubles, 0 when the shape is not split:
+// few output tiles and a long K); without enough scratch the product runs unsplit
+int gemm_tn_ws(const double* A, int64_t lda, const double* B, int64_t ldb, GemmOut out, int M, int N, int K,
+               int accumulate, int algo, double* scratch, size_t scratch_doubles, cudaStream_t stream);
+size_t gemm_splitk_doubles(int M, int N, int K);
 inline GemmOut plain_out(double* C, int64_t ldc, int M) { return GemmOut{C, ldc, 0, M}; }
 int current_gemm_algo();
 

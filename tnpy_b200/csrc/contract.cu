@@ -225,8 +225,16 @@ static bool tcgen05_allowed(int algo) {
 }
 
 size_t chain_gemm_bytes(int M, int N, int K) {
-  if (!ozaki_applicable(M, N, K)) return 0;
+  if (!ozaki_applicable(M, N, K)) return Workspace::need(gemm_splitk_doubles(M, N, K));  // FP64: split-K partials
   return oz_operand_bytes(M, K) + oz_operand_bytes(N, K) + oz_mma_scratch_bytes(M, N);
+}
+
+// FP64 GEMM with split-K partials taken from a copy of the workspace (released again on return)
+static int fp64_gemm(const double* A, int64_t lda, const double* B, int64_t ldb, GemmOut out, int M, int N, int K,
+                     int accumulate, Workspace ws, cudaStream_t stream) {
+  const size_t want = gemm_splitk_doubles(M, N, K);
+  double* scratch = want ? ws.take<double>(want) : nullptr;
+  return gemm_tn_ws(A, lda, B, ldb, out, M, N, K, accumulate, TNPY_GEMM_FP64, scratch, scratch ? want : 0, stream);
 }
 
 int chain_gemm(const double* A, int64_t lda, const double* B, int64_t ldb, GemmOut out, int M, int N, int K,
@@ -240,7 +248,7 @@ int chain_gemm(const double* A, int64_t lda, const double* B, int64_t ldb, GemmO
       return oz_mma(a, b, out, M, N, ozaki_slices(), accumulate, probe, nullptr, stream);
     }
   }
-  return gemm_tn(A, lda, B, ldb, out, M, N, K, accumulate, TNPY_GEMM_FP64, stream);
+  return fp64_gemm(A, lda, B, ldb, out, M, N, K, accumulate, ws, stream);
 }
 
 // ---- prepared H_eff ---------------------------------------------------------------------------
@@ -333,6 +341,10 @@ size_t heff_apply_bytes(int l, int lo, int r, int wl, int wr, int d) {
   size_t chain = Workspace::need((size_t)d * r * wl * lo) + Workspace::need((size_t)r * wr * d * lo);  // T1, T2
   if (ozaki_applicable(d * r, wl * lo, l)) chain += oz_operand_bytes(d * r, l) + oz_mma_scratch_bytes(d * r, wl * lo);
   if (ozaki_applicable(d * lo, r, r * wr)) chain += oz_operand_bytes(d * lo, r * wr) + oz_mma_scratch_bytes(d * lo, r);
+  {  // split-K partials of the FP64 GEMMs (one at a time)
+    const size_t a = gemm_splitk_doubles(d * r, wl * lo, l), b = gemm_splitk_doubles(d * lo, r, r * wr);
+    chain += Workspace::need(a > b ? a : b);
+  }
   size_t direct = 0;
   if (direct_shapes_ok(l, lo, r, wl, wr, d))
     direct = oz_operand_bytes(lo * d, (wr - 1) * r) + oz_operand_bytes(d * r, (wl - 1) * l) +
@@ -490,8 +502,8 @@ int heff_plan_apply(const HeffPlan& p, const double* x, double* y, int S, const 
     TNPY_TRY(oz_slice_operand(x, (int64_t)d * r, oz_plain_rows(l), xs, stream));
     TNPY_TRY(oz_mma(xs, p.envL, plain_out(t1_dst, (int64_t)wl * lo, s.m1), s.m1, s.n1, S, 0, scratch, p.bound, stream));
   } else {
-    TNPY_TRY(gemm_tn(x, (int64_t)d * r, p.L + (s.left_id ? lo : 0), (int64_t)wl * lo,
-                     plain_out(t1_dst, (int64_t)wl * lo, s.m1), s.m1, s.n1, s.k1, 0, TNPY_GEMM_FP64, stream));
+    TNPY_TRY(fp64_gemm(x, (int64_t)d * r, p.L + (s.left_id ? lo : 0), (int64_t)wl * lo,
+                       plain_out(t1_dst, (int64_t)wl * lo, s.m1), s.m1, s.n1, s.k1, 0, ws, stream));
   }
   // T2[r, b, q, m] (or [b, r, q, m]) = sum_{a p} W[a, b, p, q] T1[p, r, a, m]      (u=p, u'=q, v=a, v'=b)
   TNPY_TRY(wmix(t1, t2, p.W, d, d, wl, wr, r, lo, d, 1, wr * d * d, d * d, stream, (s.right_id || p.g3_oz) ? 1 : 0));
@@ -509,8 +521,7 @@ int heff_plan_apply(const HeffPlan& p, const double* x, double* y, int S, const 
     TNPY_TRY(oz_slice_operand(t2, (int64_t)d * lo, oz_plain_rows(s.k3), ts, stream));
     TNPY_TRY(oz_mma(ts, p.envR, out, s.m3, s.n3, S, 0, scratch, p.bound, stream, &p.skip3));
   } else {
-    TNPY_TRY(gemm_tn(t2, (int64_t)d * lo, s.right_id ? p.r2 : p.R, (int64_t)r, out, s.m3, s.n3, s.k3, 0, TNPY_GEMM_FP64,
-                     stream));
+    TNPY_TRY(fp64_gemm(t2, (int64_t)d * lo, s.right_id ? p.r2 : p.R, (int64_t)r, out, s.m3, s.n3, s.k3, 0, ws, stream));
   }
   if (s.right_id) {
     const double* t2_last = t2 + (size_t)(wr - 1) * r * d * lo;

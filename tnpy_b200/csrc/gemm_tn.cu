@@ -156,7 +156,8 @@ struct DmmaCfg {
 template <int BM, int BN, int WM, int WN, int STAGES>
 __global__ void __launch_bounds__(DmmaCfg<BM, BN, WM, WN, STAGES>::kThreads, 1)
     gemm_tn_dmma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmOut out,
-                 int M, int N, int K, int accumulate, int vec_ok, int tiles_m, int tiles_n) {
+                 int M, int N, int K, int accumulate, int vec_ok, int tiles_m, int tiles_n, int ksplit,
+                 double* __restrict__ partial) {
   using Cfg = DmmaCfg<BM, BN, WM, WN, STAGES>;
   constexpr int NWN = BN / WN;
   constexpr int MI = WM / 8, NI = WN / 8;
@@ -181,20 +182,27 @@ __global__ void __launch_bounds__(DmmaCfg<BM, BN, WM, WN, STAGES>::kThreads, 1)
 
   const int KT = (K + kBK - 1) / kBK;
   const int total_tiles = tiles_m * tiles_n;
+  // split-K (few output tiles, long K: e.g. the second GEMM of H_eff at chi = 256, 32 tiles x 96 k-steps on 148 SMs):
+  // work item = (tile, K piece); piece ks writes its plain M x N partial to `partial + ks M N`, summed in a fixed order
+  // by splitk_reduce_kernel afterwards.  ksplit == 1: the plain kernel.
+  const int kt_per = (KT + ksplit - 1) / ksplit;
+  const int total_work = total_tiles * ksplit;
 
   if (warp >= Cfg::kConsumerWarps) {
     // ------------------------------- TMA producer (one elected lane) --------------------------
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::kRegsProducer));
     if (warp == Cfg::kConsumerWarps && lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+        const int tile = work % total_tiles, ks = work / total_tiles;
         int tm, tn;
         tile_coords(tile, tiles_m, tiles_n, tm, tn);
         const int m0 = tm * BM, n0 = tn * BN;
         const int a_slabs = min(Cfg::kASlabs, (M - m0 + 15) / 16);
         const int b_slabs = min(Cfg::kBSlabs, (N - n0 + 15) / 16);
         const uint32_t bytes = (a_slabs + b_slabs) * kSlabBytes;
-        for (int kt = 0; kt < KT; ++kt) {
+        const int kt_end = min(KT, (ks + 1) * kt_per);
+        for (int kt = ks * kt_per; kt < kt_end; ++kt) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], bytes);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
@@ -225,7 +233,8 @@ __global__ void __launch_bounds__(DmmaCfg<BM, BN, WM, WN, STAGES>::kThreads, 1)
 
   const uint32_t smem_base = smem_u32(smem);
   uint32_t stage = 0, phase = 0;
-  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+  for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+    const int tile = work % total_tiles, ks = work / total_tiles;
     int tm, tn;
     tile_coords(tile, tiles_m, tiles_n, tm, tn);
     double acc[MI][NI][2];
@@ -234,7 +243,8 @@ __global__ void __launch_bounds__(DmmaCfg<BM, BN, WM, WN, STAGES>::kThreads, 1)
 #pragma unroll
       for (int n = 0; n < NI; ++n) acc[i][n][0] = acc[i][n][1] = 0.0;
 
-    for (int kt = 0; kt < KT; ++kt) {
+    const int kt_end = min(KT, (ks + 1) * kt_per);
+    for (int kt = ks * kt_per; kt < kt_end; ++kt) {
       mbar_wait(&full_bar[stage], phase);
       const uint32_t sa = smem_base + stage * Cfg::kStageBytes + (wm_idx * (WM / 16)) * kSlabBytes;
       const uint32_t sb = smem_base + stage * Cfg::kStageBytes + (Cfg::kASlabs + wn_idx * (WN / 16)) * kSlabBytes;
@@ -270,7 +280,8 @@ __global__ void __launch_bounds__(DmmaCfg<BM, BN, WM, WN, STAGES>::kThreads, 1)
     for (int i = 0; i < MI; ++i) {
       const int m = row_base + 8 * i;
       if (m >= M) continue;
-      double* crow = out.C + (int64_t)(m / out.m_inner) * out.c_outer + (int64_t)(m % out.m_inner) * out.c_inner;
+      double* crow = ksplit > 1 ? partial + ((int64_t)ks * M + m) * N
+                                : out.C + (int64_t)(m / out.m_inner) * out.c_outer + (int64_t)(m % out.m_inner) * out.c_inner;
 #pragma unroll
       for (int n = 0; n < NI; ++n) {
         const int col = col_base + 8 * n;
@@ -289,6 +300,19 @@ __global__ void __launch_bounds__(DmmaCfg<BM, BN, WM, WN, STAGES>::kThreads, 1)
         }
       }
     }
+  }
+}
+
+// out(m, n) (+)= sum over the K pieces of partial[ks][m][n], pieces in ascending order (bit-reproducible)
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const double* __restrict__ partial, int ksplit, GemmOut out, int M,
+                                                            int N, int accumulate) {
+  const int64_t total = (int64_t)M * N;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int m = (int)(e / N), n = (int)(e % N);
+    double* c = out.C + (int64_t)(m / out.m_inner) * out.c_outer + (int64_t)(m % out.m_inner) * out.c_inner + n;
+    double v = accumulate ? *c : 0.0;
+    for (int ks = 0; ks < ksplit; ++ks) v += partial[(int64_t)ks * total + e];
+    *c = v;
   }
 }
 
@@ -332,15 +356,63 @@ static int make_operand_map(CUtensorMap* map, const double* P, int64_t ld, int M
 
 template <int BM, int BN, int WM, int WN, int STAGES>
 static int launch_dmma(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmOut out, int M, int N, int K, int accumulate,
-                       int vec_ok, cudaStream_t stream) {
+                       int vec_ok, int ksplit, double* partial, cudaStream_t stream) {
   using Cfg = DmmaCfg<BM, BN, WM, WN, STAGES>;
   auto kern = gemm_tn_dmma<BM, BN, WM, WN, STAGES>;
   TNPY_TRY(set_max_dynamic_smem(kern, Cfg::kSmemBytes));
   const int tiles_m = ceil_div(M, BM), tiles_n = ceil_div(N, BN);
-  const int grid = min(tiles_m * tiles_n, sm_count());
-  kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, out, M, N, K, accumulate, vec_ok, tiles_m, tiles_n);
+  const int grid = min(tiles_m * tiles_n * ksplit, sm_count());
+  if (ksplit > 1) {
+    const int pvec = (reinterpret_cast<uintptr_t>(partial) % 16 == 0) && (N % 2 == 0);
+    kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, out, M, N, K, 0, pvec, tiles_m, tiles_n, ksplit, partial);
+    TNPY_LAUNCH_OK();
+    const int64_t total = (int64_t)M * N;
+    const int64_t want = (total + 255) / 256, cap = (int64_t)sm_count() * 8;
+    const int rgrid = (int)(want < cap ? want : cap);
+    splitk_reduce_kernel<<<rgrid, 256, 0, stream>>>(partial, ksplit, out, M, N, accumulate);
+    TNPY_LAUNCH_OK();
+    return TNPY_OK;
+  }
+  kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, out, M, N, K, accumulate, vec_ok, tiles_m, tiles_n, 1, nullptr);
   TNPY_LAUNCH_OK();
   return TNPY_OK;
+}
+
+// Tile choice: minimise (waves x tile area / relative efficiency) over the compiled configurations.
+static int pick_tile(int M, int N) {
+  const int sms = sm_count();
+  auto cost = [&](int bm, int bn, double eff) {
+    const int64_t tiles = (int64_t)ceil_div(M, bm) * ceil_div(N, bn);
+    const int64_t waves = (tiles + sms - 1) / sms;
+    return (double)waves * bm * bn / eff;
+  };
+  double c0 = cost(128, 128, 1.00), c1 = cost(128, 64, 0.93), c2 = cost(64, 64, 0.80);
+  const int forced = forced_gemm_tile();
+  if (forced == 0) c0 = -1.0;
+  if (forced == 1) { c1 = -1.0; c0 = 1e300; }
+  if (forced == 2) { c2 = -1.0; c0 = c1 = 1e300; }
+  if (c0 <= c1 && c0 <= c2) return 0;
+  return c1 <= c2 ? 1 : 2;
+}
+
+// K pieces for the DMMA kernel: when the output has fewer tiles than half the SMs and K is long, cut K so that the
+// work items fill the machine (at most 8 pieces, each at least 128 rows of K)
+static int pick_ksplit(int M, int N, int K, int tile) {
+  const int bm = tile == 2 ? 64 : 128, bn = tile == 0 ? 128 : 64;
+  const int64_t tiles = (int64_t)ceil_div(M, bm) * ceil_div(N, bn);
+  const int sms = sm_count();
+  if (K < 512 || tiles * 2 > sms) return 1;
+  int ks = (int)(sms / tiles);
+  if (ks > 8) ks = 8;
+  if (ks > K / 128) ks = K / 128;
+  return ks < 2 ? 1 : ks;
+}
+
+size_t gemm_splitk_doubles(int M, int N, int K) {
+  const bool tiny = (int64_t)M * N < 64 * 64 || K < 16 || M < 32 || N < 32;
+  if (tiny) return 0;
+  const int ks = pick_ksplit(M, N, K, pick_tile(M, N));
+  return ks > 1 ? (size_t)ks * M * N : 0;
 }
 
 static bool tma_ok(const double* P, int64_t ld) {
@@ -349,6 +421,12 @@ static bool tma_ok(const double* P, int64_t ld) {
 
 int gemm_tn(const double* A, int64_t lda, const double* B, int64_t ldb, GemmOut out, int M, int N, int K,
             int accumulate, int algo, cudaStream_t stream) {
+  return gemm_tn_ws(A, lda, B, ldb, out, M, N, K, accumulate, algo, nullptr, 0, stream);
+}
+
+// The same with scratch for the split-K partials (gemm_splitk_doubles(M, N, K) doubles; fewer: no split)
+int gemm_tn_ws(const double* A, int64_t lda, const double* B, int64_t ldb, GemmOut out, int M, int N, int K,
+               int accumulate, int algo, double* scratch, size_t scratch_doubles, cudaStream_t stream) {
   TNPY_CHECK_ARG(A && B && out.C, "null operand");
   TNPY_CHECK_ARG(M > 0 && N > 0 && K > 0, "non-positive dimension");
   TNPY_CHECK_ARG(lda >= M && ldb >= N && out.m_inner > 0, "leading dimension too small");
@@ -373,21 +451,12 @@ int gemm_tn(const double* A, int64_t lda, const double* B, int64_t ldb, GemmOut 
   TNPY_TRY(make_operand_map(&tmA, A, lda, M, K));
   TNPY_TRY(make_operand_map(&tmB, B, ldb, N, K));
   const int vec_ok = (reinterpret_cast<uintptr_t>(out.C) % 16 == 0) && (out.c_inner % 2 == 0) && (out.c_outer % 2 == 0);
-  // Tile choice: minimise (waves x tile area / relative efficiency) over the compiled configurations.
-  const int sms = sm_count();
-  auto cost = [&](int bm, int bn, double eff) {
-    const int64_t tiles = (int64_t)ceil_div(M, bm) * ceil_div(N, bn);
-    const int64_t waves = (tiles + sms - 1) / sms;
-    return (double)waves * bm * bn / eff;
-  };
-  double c0 = cost(128, 128, 1.00), c1 = cost(128, 64, 0.93), c2 = cost(64, 64, 0.80);
-  const int forced = forced_gemm_tile();
-  if (forced == 0) c0 = -1.0;
-  if (forced == 1) { c1 = -1.0; c0 = 1e300; }
-  if (forced == 2) { c2 = -1.0; c0 = c1 = 1e300; }
-  if (c0 <= c1 && c0 <= c2) return launch_dmma<128, 128, 64, 32, 4>(tmA, tmB, out, M, N, K, accumulate, vec_ok, stream);
-  if (c1 <= c2) return launch_dmma<128, 64, 32, 32, 6>(tmA, tmB, out, M, N, K, accumulate, vec_ok, stream);
-  return launch_dmma<64, 64, 32, 16, 8>(tmA, tmB, out, M, N, K, accumulate, vec_ok, stream);
+  const int tile = pick_tile(M, N);
+  int ksplit = pick_ksplit(M, N, K, tile);
+  if (ksplit > 1 && (scratch == nullptr || scratch_doubles < (size_t)ksplit * M * N)) ksplit = 1;
+  if (tile == 0) return launch_dmma<128, 128, 64, 32, 4>(tmA, tmB, out, M, N, K, accumulate, vec_ok, ksplit, scratch, stream);
+  if (tile == 1) return launch_dmma<128, 64, 32, 32, 6>(tmA, tmB, out, M, N, K, accumulate, vec_ok, ksplit, scratch, stream);
+  return launch_dmma<64, 64, 32, 16, 8>(tmA, tmB, out, M, N, K, accumulate, vec_ok, ksplit, scratch, stream);
 }
 
 }  // namespace tnpy

@@ -8,10 +8,12 @@
 // on the device; the host only reads one 64-byte status record per Lanczos step to decide whether to
 // stop or restart.  Basis vectors never leave HBM.
 #include <math.h>
+#include <stdlib.h>
 
 #include "comm.cuh"
 #include "heff.cuh"
 #include "lanczos_steps.cuh"
+#include "ritz_watch.cuh"
 
 namespace tnpy {
 
@@ -26,7 +28,7 @@ int combine(const double* V, int64_t ldv, int m, const double* c, int64_t ldc_, 
             int64_t n, cudaStream_t stream);
 
 constexpr int kMaxNcv = 48;
-static_assert(kMaxNcv == kStepsMaxNcv, "the fused small-site steps write T with this leading dimension");
+static_assert(kMaxNcv == kStepsMaxNcv && kMaxNcv == kWatchLd, "the fused small-site steps and the O(m) Ritz code read T with this leading dimension");
 // leading dimension of the shared-memory matrices of the Ritz solve: odd, so that a column walk (the A <- A J phase
 // of the Jacobi rounds, consecutive threads on consecutive rows) is spread over the banks.  With the natural 48 every
 // row of a column sits in the same bank and a 30 x 30 Ritz problem took 1.5 ms (profiles/r02_launches_*).
@@ -138,7 +140,8 @@ __global__ void __launch_bounds__(256) ritz_kernel(double* __restrict__ T, const
                                                    int local_from, const double* __restrict__ beta_dev,
                                                    int j, double tol, double* __restrict__ S,
                                                    double* __restrict__ thetas, double* __restrict__ status,
-                                                   int fold_only, const double* __restrict__ steps_done = nullptr) {
+                                                   int fold_only, const double* __restrict__ steps_done = nullptr,
+                                                   int arrow = 0, int ncv = 0) {
   __shared__ double a[kMaxNcv][kRitzLd];
   __shared__ double z[kMaxNcv][kRitzLd];
   __shared__ double cs[kMaxNcv], sn[kMaxNcv], red[72];
@@ -156,6 +159,65 @@ __global__ void __launch_bounds__(256) ritz_kernel(double* __restrict__ T, const
   __syncthreads();
   for (int idx = tid; idx < m * m; idx += blockDim.x) a[idx / m][idx % m] = T[(idx / m) * kMaxNcv + idx % m];
   __syncthreads();
+  // A look that is not a restart needs nothing but the lowest Ritz pair (the status record, column 0 of S).  T is, up to
+  // rounding-level fill, diag(`arrow` kept Ritz values) + their coupling to row `arrow` + a tridiagonal tail, whose lowest
+  // pair costs O(m) per evaluation (csrc/ritz_watch.cuh) instead of the ~8 Jacobi sweeps of 2 m barriers each below
+  // (0.25 ms at m = 30).  The vector is then checked against the *full* T -- Rayleigh quotient and residual -- and only
+  // trusted when it is an eigenvector of it to 1e-13 ||T|| (and 1 % of the solver's tolerance); otherwise, and on
+  // restart looks (ncv > 0 && m == ncv: every kept Ritz vector is needed), the Jacobi solve runs.
+  if (ncv > 0 && m < ncv && m >= 12 && arrow <= m - 1) {
+    double* e = &z[0][0];
+    int* ei = pp;
+    WatchMem w(e);
+    if (tid == 0) w.box[11] = 0.0;  // no previous estimate to start from
+    __syncthreads();
+    const double beta = *beta_dev;
+    watch_begin(T, m, arrow, beta, e);
+    if (tid == 0) w.box[5] = 4e-16 * (w.box[2] * 1e18);  // bracket to working precision (box[2] = 1e-18 scale)
+    __syncthreads();
+    watch_rounds(10, m, arrow, e, ei, 1);
+    watch_vector(m, arrow, e);
+    double ti = 0.0;
+    if (tid < m)
+      for (int k = 0; k < m; ++k) ti = fma(a[tid][k], w.z[k], ti);
+    double s1 = block_sum(tid < m ? w.z[tid] * ti : 0.0, red);
+    if (tid == 0) red[64] = s1;
+    __syncthreads();
+    const double theta = red[64];
+    const double ri = tid < m ? ti - theta * w.z[tid] : 0.0;
+    double s2 = block_sum(ri * ri, red);
+    // the largest eigenvalue, coarsely (it only scales the stopping rule): three rounds from [max diagonal, Gershgorin]
+    if (tid == 0) {
+      red[65] = sqrt(s2);
+      double top = w.dg[0];
+      for (int i = 1; i < m; ++i) top = fmax(top, w.dg[i]);
+      w.box[0] = top;
+      w.box[1] = w.box[7];
+      w.box[5] = 0.0;
+    }
+    __syncthreads();
+    watch_rounds(3, m, arrow, e, ei, m);
+    const double anorm = fmax(fabs(theta), fabs(w.box[0]));
+    const double rn = red[65];
+    const bool trusted = rn <= fmin(1e-13, 1e-2 * tol) * anorm;
+    if (trusted) {
+      const double zl = w.z[m - 1];
+      const double sgn = w.z[0] < 0.0 ? -1.0 : 1.0;
+      if (tid < m) S[tid * kMaxNcv + 0] = sgn * w.z[tid];
+      if (tid == 0) {
+        const double resid = fabs(beta * zl);
+        thetas[0] = theta;
+        status[ST_THETA] = theta;
+        status[ST_RESID] = resid;
+        status[ST_ANORM] = anorm;
+        status[ST_BETA] = beta;
+        status[ST_DONE] = (resid <= tol * anorm) ? 1.0 : 0.0;
+        status[ST_RCOEF] = beta * sgn * zl;
+      }
+      return;
+    }
+    __syncthreads();
+  }
   jacobi_eig_smem(a, z, m, cs, sn, pp, qq, red);
   if (tid == 0) {
     // sort eigenvalues ascending (stable selection; m <= 48)
@@ -384,6 +446,10 @@ static int eig_lowest_impl(const tnpy_comm* comm, const double* L, const double*
   // where a look costs as much as one to three steps: at (256, 2, 256) a step is 0.2 ms, a Ritz solve at m = 30 0.25 ms).
   // The stopping rule itself is unchanged; a local solve can overshoot by at most stride_cap - 1 matvecs.
   const int stride_cap = n_full >= (1 << 20) ? 3 : 8;
+  static const bool fast_ritz = [] {  // TNPY_FAST_RITZ=0: every look runs the Jacobi solve
+    const char* env = getenv("TNPY_FAST_RITZ");
+    return !(env && env[0] == '0');
+  }();
   double last_resid = 0.0, last_anorm = 0.0;
   int last_look_matvec = 0;
   int since_check = 0, stride = 1;
@@ -401,7 +467,7 @@ static int eig_lowest_impl(const tnpy_comm* comm, const double* L, const double*
       TNPY_TRY(lanczos_steps_launch(steps_plan, plan.L, plan.W, plan.R, V, ldv, T, status, ST_BETA, ST_STEPS, l, r, wl, wr, d, j, nsteps,
                                     ncv, whole_basis_step, tol, last_anorm, static_cast<char*>(workspace) + chain_off, stream));
       ritz_kernel<<<1, 256, 0, stream>>>(T, nullptr, nullptr, nullptr, 0, status + ST_BETA, j, tol, S, thetas, status, 0,
-                                         status + ST_STEPS);
+                                         status + ST_STEPS, whole_basis_step, fast_ritz ? ncv : 0);
       TNPY_LAUNCH_OK();
       ++n_looks;
       TNPY_CUDA_OK(cudaMemcpyAsync(hst, status, sizeof(double) * ST_SIZE, cudaMemcpyDeviceToHost, stream));
@@ -449,7 +515,8 @@ static int eig_lowest_impl(const tnpy_comm* comm, const double* L, const double*
     m = j + 1;
     ++since_check;
     const bool look = m == ncv || n_matvec >= max_matvec || m >= n_full || since_check >= stride;
-    ritz_kernel<<<1, 256, 0, stream>>>(T, h, h2, h_local, local_from, status + ST_BETA, j, tol, S, thetas, status, look ? 0 : 1);
+    ritz_kernel<<<1, 256, 0, stream>>>(T, h, h2, h_local, local_from, status + ST_BETA, j, tol, S, thetas, status, look ? 0 : 1,
+                                       nullptr, whole_basis_step, fast_ritz ? ncv : 0);
     TNPY_LAUNCH_OK();
     TNPY_TRY(scale_copy(w, w, n, 1.0, status + ST_BETA, 1, stream));
     if (!look) {
