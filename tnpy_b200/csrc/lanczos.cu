@@ -464,8 +464,15 @@ static int eig_lowest_impl(const tnpy_comm* comm, const double* L, const double*
       if (nsteps > max_matvec - n_matvec) nsteps = max_matvec - n_matvec;
       if ((int64_t)nsteps > n_full - j) nsteps = (int)(n_full - j);
       if (nsteps < 1) nsteps = 1;
-      TNPY_TRY(lanczos_steps_launch(steps_plan, plan.L, plan.W, plan.R, V, ldv, T, status, ST_BETA, ST_STEPS, l, r, wl, wr, d, j, nsteps,
-                                    ncv, whole_basis_step, tol, last_anorm, static_cast<char*>(workspace) + chain_off, stream));
+      if (lanczos_steps_launch(steps_plan, plan.L, plan.W, plan.R, V, ldv, T, status, ST_BETA, ST_STEPS, l, r, wl, wr, d, j, nsteps,
+                               ncv, whole_basis_step, tol, last_anorm, static_cast<char*>(workspace) + chain_off,
+                               stream) != TNPY_OK) {
+        // a cooperative launch the device cannot place right now (other contexts holding SMs): nothing has run,
+        // the general multi-kernel solver continues from the same state
+        cudaGetLastError();
+        fused = false;
+        continue;
+      }
       ritz_kernel<<<1, 256, 0, stream>>>(T, nullptr, nullptr, nullptr, 0, status + ST_BETA, j, tol, S, thetas, status, 0,
                                          status + ST_STEPS, whole_basis_step, fast_ritz ? ncv : 0);
       TNPY_LAUNCH_OK();
