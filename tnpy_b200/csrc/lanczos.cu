@@ -268,6 +268,7 @@ static size_t eig_ws_layout(int64_t n, int ncv, int keep, size_t chain) {
   total += Workspace::need((size_t)keep * ldv);       // Y
   total += Workspace::need(kMaxNcv * kMaxNcv) * 2;    // T, S
   total += Workspace::need(64) * 5;                   // thetas, h, h2, h_local, status
+  total += lanczos_gs_bytes() + 256;                  // partials of the fused Gram-Schmidt launch
   total += chain + 512;
   return total;
 }
@@ -374,7 +375,8 @@ static int eig_lowest_impl(const tnpy_comm* comm, const double* L, const double*
   double* h_local = ws.take<double>(64);
   double* status = ws.take<double>(64);
   int* skip2 = reinterpret_cast<int*>(status + 48);  // device flag: skip the second Gram-Schmidt pass of this step
-  if (!V || !Y || !T || !S || !thetas || !h || !h2 || !h_local || !status || (comm && !x_full)) {
+  char* gs_mem = ws.take<char>(lanczos_gs_bytes());
+  if (!V || !Y || !T || !S || !thetas || !h || !h2 || !h_local || !status || !gs_mem || (comm && !x_full)) {
     set_error("tnpy_eig_lowest: workspace too small (%zu bytes given)", workspace_bytes);
     return TNPY_EWORKSPACE;
   }
@@ -404,11 +406,15 @@ static int eig_lowest_impl(const tnpy_comm* comm, const double* L, const double*
   // Small sites: whole steps in one cooperative launch (csrc/lanczos_steps.cu); the host then only launches the
   // Ritz solve and reads the status record every `stride` steps.
   bool fused = !comm && plan.mode == HEFF_FP64_CHAIN && lanczos_steps_supported(l, r, wl, wr, d);
+  // Mid-size sites keep the GEMM kernels for the matvec and run the rest of a step -- both Gram-Schmidt passes, the
+  // norm, the normalised copy, the new column of T -- in one cooperative launch instead of nine small ones.
+  bool gs_fused = !comm && !fused && lanczos_gs_supported(n_full);
   LanczosStepsPlan steps_plan{};
   if (fused) {
     steps_plan = lanczos_steps_plan(l, r, wl, wr, d);
     // a workspace sized while the fused path was switched off only holds the general solver's scratch
     if (workspace_bytes < chain_off + steps_plan.bytes) fused = false;
+    if (!fused) gs_fused = lanczos_gs_supported(n_full);
   }
   // global norm of the vector whose local norm multi_dot / multi_axpy just left in *local (see the kernels above)
   double* sq = status + 40;
@@ -502,10 +508,20 @@ static int eig_lowest_impl(const tnpy_comm* comm, const double* L, const double*
     // when the full pass cancelled after all.  A plain single full pass is not enough: ||w'|| / ||w|| is ~0.6 in
     // every Lanczos step, and each unguarded step multiplies the basis' orthogonality defect by ~1.3
     // (docs/experiments/local_solver_study.py); the coefficients of all passes add up to column j of T = V^T H V.
+    bool gs_done = false;
+    if (gs_fused) {
+      if (lanczos_gs_launch(V, ldv, n, j, T, status, ST_BETA, gs_mem, stream) == TNPY_OK) {
+        gs_done = true;
+      } else {  // the device cannot place the cooperative launch: the separate kernels below do the same work
+        cudaGetLastError();
+        gs_fused = false;
+      }
+    }
     const int local_from = (j == whole_basis_step) ? 0 : (j > 0 ? j - 1 : 0);
     const int n_local = j + 1 - local_from;
     double* v_local = V + (int64_t)local_from * ldv;
     double* local_norm = comm ? status + 41 : status + ST_BETA;  // sharded: multi_axpy leaves the *local* norm here
+    if (!gs_done) {
     TNPY_TRY(multi_dot(v_local, ldv, n_local, w, n, h_local, 0, stream));
     TNPY_TRY(reduce(h_local, n_local));
     TNPY_TRY(multi_axpy(v_local, ldv, n_local, h_local, w, n, nullptr, stream));
@@ -519,13 +535,22 @@ static int eig_lowest_impl(const tnpy_comm* comm, const double* L, const double*
     TNPY_TRY(reduce(h2, j + 1));  // skipped pass: the decision kernel zeroed h2 on every rank
     TNPY_TRY(multi_axpy(V, ldv, j + 1, h2, w, n, local_norm, stream, skip2));
     TNPY_TRY(reduce_norm(local_norm, status + ST_BETA, skip2));
+    }
     m = j + 1;
     ++since_check;
     const bool look = m == ncv || n_matvec >= max_matvec || m >= n_full || since_check >= stride;
-    ritz_kernel<<<1, 256, 0, stream>>>(T, h, h2, h_local, local_from, status + ST_BETA, j, tol, S, thetas, status, look ? 0 : 1,
-                                       nullptr, whole_basis_step, fast_ritz ? ncv : 0);
-    TNPY_LAUNCH_OK();
-    TNPY_TRY(scale_copy(w, w, n, 1.0, status + ST_BETA, 1, stream));
+    if (gs_done) {  // T has its column and w is normalised already: the Ritz kernel only runs when somebody looks
+      if (look) {
+        ritz_kernel<<<1, 256, 0, stream>>>(T, nullptr, nullptr, nullptr, 0, status + ST_BETA, j, tol, S, thetas, status, 0, nullptr,
+                                           whole_basis_step, fast_ritz ? ncv : 0);
+        TNPY_LAUNCH_OK();
+      }
+    } else {
+      ritz_kernel<<<1, 256, 0, stream>>>(T, h, h2, h_local, local_from, status + ST_BETA, j, tol, S, thetas, status, look ? 0 : 1,
+                                         nullptr, whole_basis_step, fast_ritz ? ncv : 0);
+      TNPY_LAUNCH_OK();
+      TNPY_TRY(scale_copy(w, w, n, 1.0, status + ST_BETA, 1, stream));
+    }
     if (!look) {
       ++j;
       continue;

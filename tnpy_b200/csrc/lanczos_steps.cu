@@ -36,6 +36,7 @@ constexpr int kMaxTerms = 1024;  // wl * wr * d * d of the MPO tensor (its non-z
 constexpr int kMaxGroups = 128;  // wr * d
 constexpr int64_t kMaxVector = 32768;
 constexpr int kMaxKSplit = 8;
+constexpr int64_t kGsMaxVector = 1 << 20;  // fused Gram-Schmidt: longest vector (8192 elements of w per CTA in shared memory)
 constexpr int kMaxGatherLoads = 19;  // ceil(148 work CTAs / 8 threads per coefficient)
 
 struct StepsArgs {
@@ -461,6 +462,109 @@ __global__ void __launch_bounds__(kThreads, 1) lanczos_steps_kernel(const StepsA
   }
 }
 
+// ---- mid-size sites: the Gram-Schmidt half of a step in one cooperative launch -------------------------------------
+// Between 2^15 and 2^20 unknowns the matvec belongs on the tensor-pipe GEMM kernels, but the rest of a step -- two
+// classical Gram-Schmidt passes against the basis, the norm, the normalised copy, the new column of T -- is nine
+// launches of 4-13 us on vectors that live in L2.  Here it is one: every CTA owns a contiguous range of elements, keeps
+// its part of w in shared memory through three grid barriers, reads its part of the basis from L2 / HBM four times
+// (dot, apply, dot, apply -- the same traffic as the separate kernels), and all sums run in a fixed order.
+struct GsArgs {
+  double* V;
+  int64_t ldv;
+  int64_t n;
+  int j;
+  double* T;
+  double* status;
+  int beta_slot;
+  double* part;  // [2][grid][kStepsMaxNcv]
+  double* nrm;   // [grid]
+  int chunk;
+};
+
+// partial[k] = sum over this CTA's elements of V[k][first + .] * w[.]: one warp per k, eight k in flight
+__device__ __forceinline__ void partial_dots_global(const double* V, int64_t ldv, int m, int count, const double* wsm, double* out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int k = warp; k < m; k += kThreads / 32) {
+    const double* vk = V + (int64_t)k * ldv;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int e = lane;
+    for (; e + 96 < count; e += 128) {
+      const double a0 = vk[e], a1 = vk[e + 32], a2 = vk[e + 64], a3 = vk[e + 96];
+      s0 = fma(a0, wsm[e], s0);
+      s1 = fma(a1, wsm[e + 32], s1);
+      s2 = fma(a2, wsm[e + 64], s2);
+      s3 = fma(a3, wsm[e + 96], s3);
+    }
+    for (; e < count; e += 32) s0 = fma(vk[e], wsm[e], s0);
+    const double s = warp_sum((s0 + s1) + (s2 + s3));
+    if (lane == 0) out[k] = s;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) lanczos_gs_kernel(const GsArgs a) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ double wsm[];  // this CTA's elements of w
+  __shared__ double hs[kStepsMaxNcv], h2s[kStepsMaxNcv];
+  __shared__ double red[32];
+  __shared__ double beta_sh;
+  const int tid = threadIdx.x, ctas = gridDim.x, cta = blockIdx.x;
+  const int j = a.j, m = j + 1;
+  const int64_t first = (int64_t)cta * a.chunk;
+  const int count = first >= a.n ? 0 : (int)min((int64_t)a.chunk, a.n - first);
+  const double* Vc = a.V + first;                         // column k of the basis, this CTA's part: Vc + k * ldv
+  double* wg = a.V + (int64_t)(j + 1) * a.ldv + first;    // H v_j as the matvec left it
+  double* part0 = a.part;
+  double* part1 = a.part + (int64_t)ctas * kStepsMaxNcv;
+
+  for (int e = tid; e < count; e += kThreads) wsm[e] = wg[e];
+  __syncthreads();
+  partial_dots_global(Vc, a.ldv, m, count, wsm, part0 + (int64_t)cta * kStepsMaxNcv);
+  grid.sync();
+
+  gather_partials(part0, ctas, m, hs);
+  __syncthreads();
+  for (int e = tid; e < count; e += kThreads) {
+    double w = wsm[e];
+    for (int k = 0; k < m; ++k) w = fma(-hs[k], Vc[(int64_t)k * a.ldv + e], w);
+    wsm[e] = w;
+  }
+  __syncthreads();
+  partial_dots_global(Vc, a.ldv, m, count, wsm, part1 + (int64_t)cta * kStepsMaxNcv);
+  grid.sync();
+
+  gather_partials(part1, ctas, m, h2s);
+  __syncthreads();
+  double sq = 0.0;
+  for (int e = tid; e < count; e += kThreads) {
+    double w = wsm[e];
+    for (int k = 0; k < m; ++k) w = fma(-h2s[k], Vc[(int64_t)k * a.ldv + e], w);
+    wsm[e] = w;
+    sq = fma(w, w, sq);
+  }
+  sq = block_sum(sq, red);
+  if (tid == 0) a.nrm[cta] = sq;
+  grid.sync();
+
+  if (tid < 32) {
+    double s = 0.0;
+    for (int c = tid; c < ctas; c += 32) s += a.nrm[c];
+    s = warp_sum(s);
+    if (tid == 0) beta_sh = sqrt(s);
+  }
+  __syncthreads();
+  const double beta = beta_sh;
+  const double inv = beta > 0.0 ? 1.0 / beta : 0.0;
+  for (int e = tid; e < count; e += kThreads) wg[e] = wsm[e] * inv;
+  if (cta == 0) {
+    if (tid < m) {
+      const double t = hs[tid] + h2s[tid];
+      a.T[tid * kStepsMaxNcv + j] = t;
+      a.T[j * kStepsMaxNcv + tid] = t;
+    }
+    if (tid == 0) a.status[a.beta_slot] = beta;
+  }
+}
+
 std::atomic<unsigned long long*>& trace_buffer() {
   static std::atomic<unsigned long long*> p(nullptr);
   return p;
@@ -504,6 +608,40 @@ LanczosStepsPlan lanczos_steps_plan(int l, int r, int wl, int wr, int d) {
   p.bytes = Workspace::need((size_t)d * r * wl * l) + Workspace::need((size_t)p.ksplit * n) + Workspace::need((size_t)n) +
             Workspace::need((size_t)2 * p.grid * kStepsMaxNcv) + Workspace::need((size_t)p.grid) + Workspace::need(64, 1) + 256;
   return p;
+}
+
+bool lanczos_gs_supported(int64_t n) {
+  return fused_steps_switch().load(std::memory_order_relaxed) != 0 && n > 0 && n <= kGsMaxVector;
+}
+
+size_t lanczos_gs_bytes() { return Workspace::need((size_t)2 * sm_count() * kStepsMaxNcv) + Workspace::need((size_t)sm_count()) + 256; }
+
+int lanczos_gs_launch(double* V, int64_t ldv, int64_t n, int j, double* T, double* status, int beta_slot, void* scratch,
+                      cudaStream_t stream) {
+  TNPY_CHECK_ARG(V && T && status && scratch && n > 0 && j >= 0 && j < kStepsMaxNcv, "bad argument");
+  const int sms = sm_count();
+  int64_t want = (n + kThreads - 1) / kThreads;
+  int ctas = (int)(want < sms ? want : sms);
+  if (ctas > 8 * kMaxGatherLoads) ctas = 8 * kMaxGatherLoads;  // gather_partials reads that many partials per coefficient
+  GsArgs a;
+  a.V = V;
+  a.ldv = ldv;
+  a.n = n;
+  a.j = j;
+  a.T = T;
+  a.status = status;
+  a.beta_slot = beta_slot;
+  Workspace ws(scratch, lanczos_gs_bytes());
+  a.part = ws.take<double>((size_t)2 * sms * kStepsMaxNcv);
+  a.nrm = ws.take<double>((size_t)sms);
+  a.chunk = (int)((n + ctas - 1) / ctas);
+  const int smem = a.chunk * (int)sizeof(double);
+  TNPY_TRY(set_max_dynamic_smem(lanczos_gs_kernel, (int)((kGsMaxVector / 128 + 64) * sizeof(double))));
+  void* args[] = {&a};
+  TNPY_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lanczos_gs_kernel), dim3(ctas), dim3(kThreads), args, smem,
+                                           stream));
+  count_launch();
+  return TNPY_OK;
 }
 
 int lanczos_steps_launch(const LanczosStepsPlan& plan, const double* L, const double* W, const double* R, double* V,

@@ -32,4 +32,12 @@ int lanczos_steps_launch(const LanczosStepsPlan& plan, const double* L, const do
                          int wr, int d, int j0, int nsteps, int ncv, int arrow, double tol, double anorm, void* scratch,
                          cudaStream_t stream);
 
+// Mid-size sites (up to 2^20 unknowns): the Gram-Schmidt half of step j in one cooperative launch.  On entry V[j + 1]
+// holds H v_j as the matvec left it; on return V[j + 1] is orthogonalised twice against V[0..j] and normalised,
+// T[:, j] = T[j, :] holds the summed coefficients and status[beta_slot] the norm.  scratch: lanczos_gs_bytes().
+bool lanczos_gs_supported(int64_t n);
+size_t lanczos_gs_bytes();
+int lanczos_gs_launch(double* V, int64_t ldv, int64_t n, int j, double* T, double* status, int beta_slot, void* scratch,
+                      cudaStream_t stream);
+
 }  // namespace tnpy
