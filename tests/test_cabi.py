@@ -44,6 +44,19 @@ def test_host_only_entry_points(lib):
     assert b"unknown algo" in lib.tnpy_last_error()
 
 
+def test_solver_switches_and_workspace_queries_without_gpu(lib):
+    # process-wide switch of the fused small-site / mid-size steps: returns the previous setting
+    assert lib.tnpy_set_fused_steps(0) == 1
+    assert lib.tnpy_set_fused_steps(1) == 0
+    assert lib.tnpy_steps_trace(None) == 0
+    # workspace queries are pure host arithmetic (they must not need a device)
+    small = lib.tnpy_eig_workspace_bytes(60, 60, 5, 5, 2, 0)
+    assert small >= 33 * 7200 * 8
+    assert lib.tnpy_geig_chol_workspace_bytes(8192) >= 4 * 8192 * 8192 * 8
+    assert lib.tnpy_heff_dense_workspace_bytes(64, 64, 25, 25, 2) >= 4 * 64 * 64 * 25 * 8
+    assert lib.tnpy_geig_chol_workspace_bytes(0) == 0
+
+
 def test_argument_validation_without_gpu(lib):
     rc = lib.tnpy_gemm_tn(None, 1, None, 1, None, 1, 1, 1, 1, 0, 0, None)
     assert rc == -1 and b"invalid argument" in lib.tnpy_last_error()
