@@ -615,6 +615,8 @@ def measure_sweeps(n, chi, tol, count):
         out["matvecs"].append(sum(st.get("n_matvec", 0) for st in dmrg.solver_stats))
         out.setdefault("looks", []).append(sum(st.get("looks", 0) for st in dmrg.solver_stats))
         out.setdefault("extra_gs_passes", []).append(sum(st.get("extra_gs_passes", 0) for st in dmrg.solver_stats))
+        out.setdefault("reduced_slice_matvecs", []).append(sum(st.get("reduced_slice_matvecs", 0) for st in dmrg.solver_stats))
+        out.setdefault("failed_residual_checks", []).append(sum(st.get("failed_residual_checks", 0) for st in dmrg.solver_stats))
         out["energies"].append(e)
         out["phase_s_cumulative"].append(dict(dmrg.phase_seconds))
     out["split_counts"] = dict(dmrg.environment.split_counts)

@@ -124,7 +124,7 @@ int tnpy_heff_apply(const double* L, const double* W, const double* R, const dou
  * mixed-canonical gauge: with both identity flags and an MPO tensor whose non-zero blocks all have a = 0 or
  * b = wr - 1,  y = sum_{b<wr-1} (W_0b x) R_b + sum_{a>0} L_a^T (W_{a,wr-1} x) + W_{0,wr-1} x  is two independent
  * tcgen05 GEMMs whose x-side operands are mixed and sliced straight from x -- no FP64 intermediate exists.
- * tnpy_heff_plan_apply: y = H_eff x; slices = 0 (default), 6, 7 or 8; workspace: tnpy_heff_workspace_bytes().
+ * tnpy_heff_plan_apply: y = H_eff x; slices = 0 (default) or 5 .. 8; workspace: tnpy_heff_workspace_bytes().
  * tnpy_heff_plan_error_bound: the largest rigorous Frobenius-norm bound of any int8 product issued through the
  * plan so far (0 on the FP64 chain), copied device to device. */
 typedef struct tnpy_heff_plan tnpy_heff_plan;
@@ -225,8 +225,17 @@ int tnpy_eig_lowest_image(const double* L, const double* W, const double* R, dou
                           int l, int r, int wl, int wr, int d, int flags, double tol, int max_matvec, int ncv,
                           double* stats_host, void* workspace, size_t workspace_bytes, void* stream);
 /* Diagnostics of the calling thread's last tnpy_eig_lowest* call: matvecs, looks (status read-backs = stream
- * synchronisations), extra full Gram-Schmidt passes the DGKS test asked for, thick restarts.  Returns how many were written. */
+ * synchronisations), extra full Gram-Schmidt passes the DGKS test asked for, thick restarts, matvecs that ran with
+ * fewer int8 slices than the solve's base count (inexact-Krylov schedule), true-residual checks that failed and sent the
+ * solve on at full accuracy.  Returns how many were written (at most 6). */
 int tnpy_last_eig_counters(int64_t* out, int n);
+/* On the tcgen05 path tnpy_eig_lowest runs the later steps of a solve with fewer int8 slices (inexact Krylov: the
+ * matvec error a Lanczos step tolerates grows like 1 / ||r|| of the current Ritz pair), chosen at every look from the
+ * rigorous bound of the products, bound(S) <= (0.01 / 8) tol ||A||^2 / ||r||, S >= 5; a solve that did so is accepted only
+ * on its *true* residual ||H psi - theta psi|| <= tol ||A||, formed with one matvec at full accuracy (which is also the
+ * image tnpy_eig_lowest_image returns), and otherwise continues from psi with the schedule off.  on = 0 switches the
+ * schedule off for the process (also: environment TNPY_INEXACT_SLICES=0).  Returns the previous setting. */
+int tnpy_set_inexact_slices(int on);
 /* Small sites (vectors of <= 32768 elements on the FP64 chain) run whole Lanczos steps -- matvec, two Gram-Schmidt
  * passes, normalisation, the new column of T -- in one cooperative launch, `stride` steps per launch, instead of
  * ~15 launches per step (csrc/lanczos_steps.cu).  on = 0 keeps every site on the general multi-kernel solver (also:

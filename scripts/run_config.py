@@ -83,6 +83,8 @@ def main():
             out.setdefault("gpu_matvecs_per_sweep", []).append(sum(s.get("n_matvec", 0) for s in gpu.solver_stats))
             out.setdefault("gpu_looks_per_sweep", []).append(sum(s.get("looks", 0) for s in gpu.solver_stats))
             out.setdefault("gpu_extra_gs_passes_per_sweep", []).append(sum(s.get("extra_gs_passes", 0) for s in gpu.solver_stats))
+            out.setdefault("gpu_reduced_slice_matvecs_per_sweep", []).append(sum(s.get("reduced_slice_matvecs", 0) for s in gpu.solver_stats))
+            out.setdefault("gpu_failed_residual_checks_per_sweep", []).append(sum(s.get("failed_residual_checks", 0) for s in gpu.solver_stats))
             out.setdefault("gpu_phase_s_cumulative", []).append(dict(gpu.phase_seconds))
         out["gpu_sweep_s"] = per_sweep
         out["gpu_matvecs_last_sweep"] = sum(s.get("n_matvec", 0) for s in gpu.solver_stats)

@@ -715,6 +715,55 @@ def test_direct_path_in_canonical_gauge(cu, l, r, model):
         p_.close()
 
 
+def test_inexact_slice_schedule_is_accepted_on_the_true_residual(cu):
+    """On the tcgen05 path the eigensolver runs the later steps of a solve with fewer int8 slices and accepts the result
+    only on the true residual (one matvec at full accuracy).  XXZ n=22 chi=1024 in the mixed-canonical gauge: the
+    schedule is used, no check fails, the eigenvalue equals the full-accuracy solve's to 1e-12 |theta|, the true
+    residual holds the tolerance, and the returned image is H_eff psi."""
+    import sys
+    from pathlib import Path
+
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+    import bench
+    from tnpy_b200.finite_dmrg import FiniteDMRG
+    from tnpy_b200.model import XXZ
+
+    n, chi, tol = 22, 1024, 1e-8
+    dmrg = FiniteDMRG(XXZ(n=n, delta=0.5).mpo, bond_dim=chi, mps=bench.random_right_canonical_device(n, chi, 2, seed=3),
+                      compute_variance=False)
+    site = n // 2
+    bench.mixed_canonicalize(dmrg, site)
+    env = dmrg.environment
+    L, W, R = env.operands(site)
+    flags = env.gauge_flags(site)
+    assert flags == 3
+    start = env.device_tensor(site).clone()
+    out = {}
+    for on in (True, False):
+        previous = cu.set_inexact_slices(on)
+        try:
+            psi = start.clone()
+            image = torch.empty_like(psi)
+            stats = cu.eig_lowest(L, W, R, psi, tol=tol, max_matvec=3000, flags=flags, image=image)
+            out[on] = (stats, psi, image)
+        finally:
+            cu.set_inexact_slices(previous)
+    (s_on, p_on, im_on), (s_off, p_off, _) = out[True], out[False]
+    assert s_on["converged"] and s_off["converged"]
+    assert s_on["heff_mode"] == cu.HEFF_OZ_DIRECT
+    assert s_on["reduced_slice_matvecs"] > 0 and s_off["reduced_slice_matvecs"] == 0
+    assert s_on["failed_residual_checks"] == 0
+    assert abs(s_on["theta"] - s_off["theta"]) <= 1e-12 * abs(s_off["theta"])
+    assert abs(abs(float((p_on * p_off).sum())) - 1.0) <= 1e-8
+    # the true residual, from a fresh FP64 matvec
+    fresh = cu.heff_apply(L, W, R, p_on, flags=flags)
+    r = fresh - s_on["theta"] * p_on
+    assert float(r.norm()) <= 1.05 * tol * s_on["anorm"]
+    assert abs(float(r.norm()) - s_on["resid"]) <= 1e-3 * tol * s_on["anorm"]
+    assert float((im_on - fresh).abs().max()) <= 1e-11 * max(float(fresh.abs().max()), 1.0)
+    assert s_on["n_matvec"] <= s_off["n_matvec"] + 8
+
+
 def test_row_block_of_the_direct_path(cu):
     """One rank's row block of the chi-sharded matvec in the mixed-canonical gauge: the identity flags are honoured
     for a block (L[li, 0, row0 + m] = delta), the R-side term reads only the block's own rows of x, and the result is

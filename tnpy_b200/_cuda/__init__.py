@@ -32,6 +32,7 @@ SIGNATURES = {
     "tnpy_ozaki_workspace_bytes": (c_size_t, [c_int] * 4),
     "tnpy_set_ozaki_slices": (c_int, [c_int]),
     "tnpy_set_fused_steps": (c_int, [c_int]),
+    "tnpy_set_inexact_slices": (c_int, [c_int]),
     "tnpy_steps_trace": (c_int, [c_void_p]),
     "tnpy_ozaki_gemm_tn": (
         c_int,
@@ -173,6 +174,13 @@ def set_fused_steps(on: bool) -> bool:
     """Small sites run whole Lanczos steps in one cooperative launch (csrc/lanczos_steps.cu); False keeps every
     site on the general multi-kernel eigensolver.  Returns the previous setting."""
     return bool(load().tnpy_set_fused_steps(1 if on else 0))
+
+
+def set_inexact_slices(on: bool) -> bool:
+    """The eigensolver's inexact-Krylov slice schedule on the tcgen05 path (fewer int8 slices for the later steps of a
+    solve, accepted only on the true residual); False keeps every product at the solve's base slice count.  Returns the
+    previous setting."""
+    return bool(load().tnpy_set_inexact_slices(1 if on else 0))
 
 
 HEFF_FP64_CHAIN, HEFF_OZ_CHAIN, HEFF_OZ_DIRECT = 0, 1, 2
@@ -496,6 +504,8 @@ def eig_lowest(L, W, R, psi, tol: float = 1e-8, max_matvec: int = 1000, ncv: int
         "converged": bool(stats[4]), "anorm": stats[5], "int8_error_bound": stats[6],
         "heff_mode": int(stats[7]) // 10, "slices": int(stats[7]) % 10,
         "looks": counters["looks"], "extra_gs_passes": counters["extra_gs_passes"],
+        "reduced_slice_matvecs": counters["reduced_slice_matvecs"],
+        "failed_residual_checks": counters["failed_residual_checks"],
     }
 
 
@@ -581,9 +591,10 @@ def eig_lowest_rows(comm: Comm, L_rows, W, R, psi_rows, l: int, row0: int, tol: 
 
 def last_eig_counters() -> dict:
     """Diagnostics of this thread's last on-device eigensolve: matvecs, looks, extra Gram-Schmidt passes, restarts."""
-    buf = (c_int64 * 4)()
-    load().tnpy_last_eig_counters(buf, 4)
-    return {"n_matvec": buf[0], "looks": buf[1], "extra_gs_passes": buf[2], "restarts": buf[3]}
+    buf = (c_int64 * 6)()
+    load().tnpy_last_eig_counters(buf, 6)
+    return {"n_matvec": buf[0], "looks": buf[1], "extra_gs_passes": buf[2], "restarts": buf[3],
+            "reduced_slice_matvecs": buf[4], "failed_residual_checks": buf[5]}
 
 
 def geig_lowest(LA, WA, RA, LM, WM, RM, psi, tol: float = 1e-8, max_iter: int = 2000, ncv: int = 0, flags_a: int = 0):

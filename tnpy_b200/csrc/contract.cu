@@ -756,7 +756,7 @@ extern "C" int tnpy_heff_plan_mode(const tnpy_heff_plan* handle) { return handle
 extern "C" int tnpy_heff_plan_apply(const tnpy_heff_plan* handle, const double* x, double* y, int slices,
                                     void* workspace, size_t workspace_bytes, void* stream) {
   TNPY_CHECK_ARG(handle != nullptr, "null handle");
-  TNPY_CHECK_ARG(slices == 0 || (slices >= 6 && slices <= kOzMaxSlices), "slices must be 0 (default), 6, 7 or 8");
+  TNPY_CHECK_ARG(slices == 0 || (slices >= 5 && slices <= kOzMaxSlices), "slices must be 0 (default) or 5 .. 8");
   Workspace ws(workspace, workspace_bytes);
   return heff_plan_apply(handle->plan, x, y, slices, nullptr, ws, static_cast<cudaStream_t>(stream));
 }

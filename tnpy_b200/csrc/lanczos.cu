@@ -35,7 +35,7 @@ static_assert(kMaxNcv == kStepsMaxNcv && kMaxNcv == kWatchLd, "the fused small-s
 constexpr int kRitzLd = kMaxNcv + 1;
 
 // status record (device and pinned host mirror)
-enum { ST_THETA = 0, ST_RESID = 1, ST_ANORM = 2, ST_DONE = 3, ST_BETA = 4, ST_RCOEF = 5, ST_BOUND = 6, ST_EXTRA = 7, ST_STEPS = 8, ST_SIZE = 9 };
+enum { ST_THETA = 0, ST_RESID = 1, ST_ANORM = 2, ST_DONE = 3, ST_BETA = 4, ST_RCOEF = 5, ST_BOUND = 6, ST_EXTRA = 7, ST_STEPS = 8, ST_TRUE = 9, ST_SIZE = 10 };
 
 // Symmetric eigen-decomposition of the m x m matrix held in shared memory `a` (leading dim kMaxNcv)
 // by parallel cyclic Jacobi (round-robin pair ordering).  Eigenvectors accumulate in `z` (columns).
@@ -259,6 +259,15 @@ __global__ void restart_T_kernel(double* __restrict__ T, const double* __restric
   }
 }
 
+// process-wide switch of the inexact-Krylov slice schedule (tnpy_set_inexact_slices / TNPY_INEXACT_SLICES=0)
+static std::atomic<int>& inexact_switch() {
+  static std::atomic<int> on([] {
+    const char* env = getenv("TNPY_INEXACT_SLICES");
+    return (env && env[0] == '0') ? 0 : 1;
+  }());
+  return on;
+}
+
 static double* pinned_status() { return static_cast<double*>(thread_pinned_scratch()); }
 
 static size_t eig_ws_layout(int64_t n, int ncv, int keep, size_t chain) {
@@ -338,8 +347,9 @@ extern "C" size_t tnpy_eig_workspace_bytes(int l, int r, int wl, int wr, int d, 
 // one exchange of data: (G - 1) / G of 8 N bytes per rank over NVLink), run their row block of the matvec, and
 // all-reduce the Gram-Schmidt coefficients and norms (a few dozen doubles); the small Ritz problem is solved
 // redundantly on every rank from identical inputs, so all ranks take identical decisions.
-// diagnostics of the calling thread's last solve: matvecs, looks (status read-backs), extra full Gram-Schmidt passes, restarts
-static thread_local long long g_last_counters[4] = {0, 0, 0, 0};
+// diagnostics of the calling thread's last solve: matvecs, looks (status read-backs), extra full Gram-Schmidt passes,
+// restarts, matvecs that ran with fewer int8 slices than the solve's base count, failed true-residual checks
+static thread_local long long g_last_counters[6] = {0, 0, 0, 0, 0, 0};
 
 static int eig_lowest_impl(const tnpy_comm* comm, const double* L, const double* W, const double* R, double* psi,
                            double* hpsi, int l, int row0, int lo, int r, int wl, int wr, int d, int flags, double tol,
@@ -402,6 +412,20 @@ static int eig_lowest_impl(const tnpy_comm* comm, const double* L, const double*
     TNPY_TRY(heff_plan_init(&plan, L, W, R, nullptr, l, lo, row0, r, wl, wr, d, flags, TNPY_GEMM_AUTO, mem, stream));
   }
   int slices = (tol >= 1e-10 && ozaki_slices() == 8) ? 7 : ozaki_slices();
+  // Inexact Krylov (Simoncini & Szyld; Bouras & Fraysse): the matvec error a Lanczos step tolerates grows like
+  // 1 / ||r|| of the current Ritz pair, because later basis vectors enter the converged Ritz vector with ever smaller
+  // weights.  On the tcgen05 path that is fewer int8 slices for the later steps of a solve -- 21 or 15 slice-pair
+  // GEMMs instead of 28 -- chosen at every look from the *rigorous* bound of the products (it scales with e_S):
+  //     bound(S) <= (0.01 / 8) tol ||A|| / (||r|| / ||A||).
+  // A solve that used fewer slices than `slices` is not trusted on its Lanczos residual: the true residual
+  // H psi - theta psi is formed with one matvec at full accuracy (it is also the image the sweep wants next), and a
+  // solve that fails it continues from psi with the schedule switched off.  TNPY_INEXACT_SLICES=0 switches it off.
+  bool inexact = inexact_switch().load(std::memory_order_relaxed) != 0 && !comm && tol >= 1e-10;
+  bool used_inexact = false;
+  long long n_reduced = 0, n_failed_checks = 0;
+  int cur_slices = slices, last_used_slices = slices;
+  double unit_bound = 0.0;  // measured bound / e_S: the scale-free part
+  auto e_of = [](int S) { return (S + 2) / 4.0 * ldexp(1.0, -7 * S); };
   const size_t chain_off = ws.used;
   // Small sites: whole steps in one cooperative launch (csrc/lanczos_steps.cu); the host then only launches the
   // Ritz solve and reads the status record every `stride` steps.
@@ -497,7 +521,15 @@ static int eig_lowest_impl(const tnpy_comm* comm, const double* L, const double*
     double* w = V + (int64_t)(j + 1) * ldv;
     Workspace chain(static_cast<char*>(workspace) + chain_off, workspace_bytes - chain_off);
     if (comm) TNPY_TRY(comm_allgather(comm, vj, x_full, (size_t)n, stream));
-    TNPY_TRY(heff_plan_apply(plan, comm ? x_full : vj, w, slices, nullptr, chain, stream));
+    const int step_slices = cur_slices < slices ? cur_slices : slices;
+    TNPY_TRY(heff_plan_apply(plan, comm ? x_full : vj, w, step_slices, nullptr, chain, stream));
+    if (plan.mode != HEFF_FP64_CHAIN) {
+      if (step_slices < slices) {
+        used_inexact = true;
+        ++n_reduced;
+      }
+      last_used_slices = step_slices;
+    }
     ++n_matvec;
     // Gram-Schmidt in two stages.  H v_j has analytically non-zero components only on v_{j-1} and v_j
     // (three-term recurrence; on every kept Ritz vector in the first step after a thick restart), so a *local*
@@ -566,7 +598,10 @@ static int eig_lowest_impl(const tnpy_comm* comm, const double* L, const double*
     // ||A|| for this test: the largest |Ritz value| or Lanczos coefficient seen so far (a lower bound of ||A|| that
     // is already tight after a few steps; the very first Ritz values of a random start can be near zero)
     anorm_seen = fmax(anorm_seen, fmax(hst[ST_ANORM], hst[ST_BETA]));
-    if (plan.mode != HEFF_FP64_CHAIN && n_matvec >= 3 && hst[ST_BOUND] > 0.01 * tol * anorm_seen) {
+    // the measured bound belongs to the slice count of the products since the last look; its scale-free part
+    // predicts the bound of any other count
+    if (plan.mode != HEFF_FP64_CHAIN && hst[ST_BOUND] > 0.0) unit_bound = hst[ST_BOUND] / e_of(last_used_slices);
+    if (plan.mode != HEFF_FP64_CHAIN && n_matvec >= 3 && unit_bound * e_of(slices) > 0.01 * tol * anorm_seen) {
       // the int8 products are no longer safely below the residual threshold: spend the eighth slice, then leave
       // the tcgen05 path altogether (the basis built so far stays valid: its vectors are exact matvecs to within
       // the bound, and T is the explicit projection)
@@ -578,6 +613,18 @@ static int eig_lowest_impl(const tnpy_comm* comm, const double* L, const double*
         TNPY_TRY(heff_plan_init(&plan, L, W, R, nullptr, l, lo, row0, r, wl, wr, d, flags, TNPY_GEMM_FP64, again, stream));
       }
       if (plan.bound) TNPY_CUDA_OK(cudaMemsetAsync(plan.bound, 0, sizeof(double), stream));
+      unit_bound = 0.0;
+      cur_slices = slices;
+    }
+    if (inexact && plan.mode != HEFF_FP64_CHAIN && n_matvec >= 3 && unit_bound > 0.0 && anorm_seen > 0.0) {
+      const double rel = fmin(1.0, fmax(hst[ST_RESID] / anorm_seen, tol));
+      const double allowed = 0.00125 * tol * anorm_seen / rel;
+      int pick = slices;
+      while (pick > 5 && unit_bound * e_of(pick - 1) <= allowed) --pick;
+      if (pick != cur_slices) {
+        cur_slices = pick;
+        if (plan.bound) TNPY_CUDA_OK(cudaMemsetAsync(plan.bound, 0, sizeof(double), stream));  // next reading: this count only
+      }
     }
     {
       const double thr = tol * hst[ST_ANORM], res = hst[ST_RESID];
@@ -595,6 +642,44 @@ static int eig_lowest_impl(const tnpy_comm* comm, const double* L, const double*
     if (done || n_matvec >= max_matvec) {
       // psi = V[0..m-1] . S[:, 0]
       TNPY_TRY(combine(V, ldv, m, S, kMaxNcv, 1, psi, ldv, n, stream));
+      if (used_inexact && done && hst[ST_BETA] > 0.0 && m < n_full) {
+        // some steps ran with fewer slices: the Lanczos residual is an estimate, the true one decides.  Y = H psi at
+        // full accuracy, V[0] (the basis is spent either way) = Y - theta psi.
+        Workspace chain(static_cast<char*>(workspace) + chain_off, workspace_bytes - chain_off);
+        TNPY_TRY(heff_plan_apply(plan, psi, Y, slices, nullptr, chain, stream));
+        ++n_matvec;
+        TNPY_TRY(scale_copy(Y, V, n, 1.0, nullptr, 0, stream));
+        TNPY_TRY(axpy(-hst[ST_THETA], nullptr, psi, V, n, stream));
+        TNPY_TRY(multi_dot(V, ldv, 1, V, n, status + ST_TRUE, 1, stream));
+        TNPY_CUDA_OK(cudaMemcpyAsync(hst + ST_TRUE, status + ST_TRUE, sizeof(double), cudaMemcpyDeviceToHost, stream));
+        TNPY_CUDA_OK(cudaStreamSynchronize(stream));
+        ++n_looks;
+        if (hst[ST_TRUE] <= tol * hst[ST_ANORM]) {
+          hst[ST_RESID] = hst[ST_TRUE];
+          if (hpsi) TNPY_TRY(scale_copy(Y, hpsi, n, 1.0, nullptr, 0, stream));
+          break;
+        }
+        // not there yet: carry on from psi with every product at full accuracy
+        ++n_failed_checks;
+        inexact = false;
+        used_inexact = false;
+        cur_slices = slices;
+        done = false;
+        if (n_matvec >= max_matvec) {
+          if (hpsi) TNPY_TRY(scale_copy(Y, hpsi, n, 1.0, nullptr, 0, stream));
+          hst[ST_RESID] = hst[ST_TRUE];
+          break;
+        }
+        TNPY_TRY(scale_copy(psi, V, n, 1.0, nullptr, 0, stream));
+        TNPY_CUDA_OK(cudaMemsetAsync(T, 0, sizeof(double) * kMaxNcv * kMaxNcv, stream));
+        j = 0;
+        whole_basis_step = 0;
+        since_check = 0;
+        stride = 1;
+        last_resid = 0.0;
+        ++n_restart;
+        continue;
+      }
       if (hpsi) {
         // H psi from the Lanczos relation H V_m = V_m T + beta v_{m+1} e_m^T (exact to rounding here, T being the
         // explicit projection): H psi = theta psi + (beta s_m) v_{m+1}; v_{m+1} = V[m] was normalised above
@@ -634,6 +719,8 @@ static int eig_lowest_impl(const tnpy_comm* comm, const double* L, const double*
   g_last_counters[1] = n_looks;
   g_last_counters[2] = (long long)hst[ST_EXTRA];
   g_last_counters[3] = n_restart;
+  g_last_counters[4] = n_reduced;
+  g_last_counters[5] = n_failed_checks;
   if (!done) {
     set_error("tnpy_eig_lowest: not converged after %d matvecs (resid %.3e, tol*|A| %.3e)", n_matvec, hst[ST_RESID],
               tol * hst[ST_ANORM]);
@@ -677,6 +764,8 @@ extern "C" int tnpy_eig_lowest_rows(const tnpy_comm* comm, const double* L_rows,
 
 extern "C" int tnpy_last_eig_counters(int64_t* out, int n) {
   int k = 0;
-  for (; k < n && k < 4; ++k) out[k] = g_last_counters[k];
+  for (; k < n && k < 6; ++k) out[k] = g_last_counters[k];
   return k;
 }
+
+extern "C" int tnpy_set_inexact_slices(int on) { return inexact_switch().exchange(on ? 1 : 0); }

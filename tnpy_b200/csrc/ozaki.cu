@@ -993,13 +993,14 @@ int oz_mma(const OzOperand& A, const OzOperand& B, GemmOut out, int M, int N, in
   }
   TNPY_CHECK_ARG(A.cols == M && B.cols == N && A.Kp == B.Kp && A.K == B.K, "operand shapes do not match the product");
   TNPY_CHECK_ARG(A.K <= 65536, "K too large for exact int32 accumulation");
-  TNPY_CHECK_ARG(S >= 6 && S <= kOzMaxSlices, "slices must be 6, 7 or 8");
+  TNPY_CHECK_ARG(S >= 5 && S <= kOzMaxSlices, "slices must be 5 .. 8");
   if (bound_dev) {
     const double e_s = (S + 2) / 4.0 * ldexp(1.0, -7 * S);
     oz_bound_kernel<<<1, 1, 0, stream>>>(A.sumsq, B.sumsq, (double)A.K * e_s, bound_dev);
     TNPY_LAUNCH_OK();
   }
   switch (S) {
+    case 5: return oz2_launch<5>(A, B, out, M, N, accumulate, ws, skip, stream);
     case 6: return oz2_launch<6>(A, B, out, M, N, accumulate, ws, skip, stream);
     case 7: return oz2_launch<7>(A, B, out, M, N, accumulate, ws, skip, stream);
     default: return oz2_launch<8>(A, B, out, M, N, accumulate, ws, skip, stream);
@@ -1041,7 +1042,8 @@ extern "C" size_t tnpy_ozaki_workspace_bytes(int M, int N, int K, int /*slices*/
   return oz_operand_bytes(M, K) + oz_operand_bytes(N, K) + oz_mma_scratch_bytes(M, N) + Workspace::need(1) + 1024;
 }
 
-// C[m,n] (+)= sum_k A[k,m] B[k,n] in FP64 accuracy on the int8 tensor cores (slices in 6..8).
+// C[m,n] (+)= sum_k A[k,m] B[k,n] in FP64 accuracy on the int8 tensor cores (slices in 5..8; 5 = 35 bits, what the
+// eigensolver's inexact-Krylov schedule uses for the late steps of a solve).
 // phase: 0 = slice both operands and multiply, 1 = slice only (fills the workspace), 2 = multiply only
 // (workspace already holds the slices of these operands) -- lets a caller time / reuse the parts.
 extern "C" int tnpy_ozaki_gemm_tn(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
@@ -1049,7 +1051,7 @@ extern "C" int tnpy_ozaki_gemm_tn(const double* A, int64_t lda, const double* B,
                                   size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   TNPY_CHECK_ARG(A && B && C && M > 0 && N > 0 && K > 0, "bad argument");
-  TNPY_CHECK_ARG(slices >= 6 && slices <= kOzMaxSlices, "slices must be 6, 7 or 8");
+  TNPY_CHECK_ARG(slices >= 5 && slices <= kOzMaxSlices, "slices must be 5 .. 8");
   TNPY_CHECK_ARG(K <= 65536, "K too large for exact int32 accumulation");
   Workspace ws(workspace, workspace_bytes);
   OzOperand a, b;
@@ -1071,7 +1073,7 @@ extern "C" int tnpy_ozaki_gemm_tn(const double* A, int64_t lda, const double* B,
 extern "C" int tnpy_ozaki_error_bound(int M, int N, int K, int slices, void* workspace, size_t workspace_bytes,
                                       double* bound_dev, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  TNPY_CHECK_ARG(bound_dev && M > 0 && N > 0 && K > 0 && slices >= 6 && slices <= kOzMaxSlices, "bad argument");
+  TNPY_CHECK_ARG(bound_dev && M > 0 && N > 0 && K > 0 && slices >= 5 && slices <= kOzMaxSlices, "bad argument");
   Workspace ws(workspace, workspace_bytes);
   OzOperand a, b;
   double* scratch = ws.take<double>(1);
