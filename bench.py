@@ -617,6 +617,7 @@ def measure_sweeps(n, chi, tol, count):
         out.setdefault("extra_gs_passes", []).append(sum(st.get("extra_gs_passes", 0) for st in dmrg.solver_stats))
         out.setdefault("reduced_slice_matvecs", []).append(sum(st.get("reduced_slice_matvecs", 0) for st in dmrg.solver_stats))
         out.setdefault("failed_residual_checks", []).append(sum(st.get("failed_residual_checks", 0) for st in dmrg.solver_stats))
+        out.setdefault("five_slice_matvecs", []).append(sum(st.get("five_slice_matvecs", 0) for st in dmrg.solver_stats))
         out["energies"].append(e)
         out["phase_s_cumulative"].append(dict(dmrg.phase_seconds))
     out["split_counts"] = dict(dmrg.environment.split_counts)

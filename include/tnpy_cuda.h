@@ -227,7 +227,7 @@ int tnpy_eig_lowest_image(const double* L, const double* W, const double* R, dou
 /* Diagnostics of the calling thread's last tnpy_eig_lowest* call: matvecs, looks (status read-backs = stream
  * synchronisations), extra full Gram-Schmidt passes the DGKS test asked for, thick restarts, matvecs that ran with
  * fewer int8 slices than the solve's base count (inexact-Krylov schedule), true-residual checks that failed and sent the
- * solve on at full accuracy.  Returns how many were written (at most 6). */
+ * solve on at full accuracy, matvecs with five slices.  Returns how many were written (at most 7). */
 int tnpy_last_eig_counters(int64_t* out, int n);
 /* On the tcgen05 path tnpy_eig_lowest runs the later steps of a solve with fewer int8 slices (inexact Krylov: the
  * matvec error a Lanczos step tolerates grows like 1 / ||r|| of the current Ritz pair), chosen at every look from the

@@ -506,6 +506,7 @@ def eig_lowest(L, W, R, psi, tol: float = 1e-8, max_matvec: int = 1000, ncv: int
         "looks": counters["looks"], "extra_gs_passes": counters["extra_gs_passes"],
         "reduced_slice_matvecs": counters["reduced_slice_matvecs"],
         "failed_residual_checks": counters["failed_residual_checks"],
+        "five_slice_matvecs": counters["five_slice_matvecs"],
     }
 
 
@@ -591,10 +592,10 @@ def eig_lowest_rows(comm: Comm, L_rows, W, R, psi_rows, l: int, row0: int, tol: 
 
 def last_eig_counters() -> dict:
     """Diagnostics of this thread's last on-device eigensolve: matvecs, looks, extra Gram-Schmidt passes, restarts."""
-    buf = (c_int64 * 6)()
-    load().tnpy_last_eig_counters(buf, 6)
+    buf = (c_int64 * 7)()
+    load().tnpy_last_eig_counters(buf, 7)
     return {"n_matvec": buf[0], "looks": buf[1], "extra_gs_passes": buf[2], "restarts": buf[3],
-            "reduced_slice_matvecs": buf[4], "failed_residual_checks": buf[5]}
+            "reduced_slice_matvecs": buf[4], "failed_residual_checks": buf[5], "five_slice_matvecs": buf[6]}
 
 
 def geig_lowest(LA, WA, RA, LM, WM, RM, psi, tol: float = 1e-8, max_iter: int = 2000, ncv: int = 0, flags_a: int = 0):

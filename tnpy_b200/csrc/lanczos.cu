@@ -268,6 +268,16 @@ static std::atomic<int>& inexact_switch() {
   return on;
 }
 
+// safety factor of the schedule: bound(S) <= factor tol ||A|| / (||r|| / ||A||); TNPY_INEXACT_FACTOR overrides it (experiments)
+static double inexact_factor() {
+  static const double f = [] {
+    const char* env = getenv("TNPY_INEXACT_FACTOR");
+    const double v = env ? atof(env) : 0.0;
+    return v > 0.0 ? v : 0.00125;
+  }();
+  return f;
+}
+
 static double* pinned_status() { return static_cast<double*>(thread_pinned_scratch()); }
 
 static size_t eig_ws_layout(int64_t n, int ncv, int keep, size_t chain) {
@@ -348,8 +358,9 @@ extern "C" size_t tnpy_eig_workspace_bytes(int l, int r, int wl, int wr, int d, 
 // all-reduce the Gram-Schmidt coefficients and norms (a few dozen doubles); the small Ritz problem is solved
 // redundantly on every rank from identical inputs, so all ranks take identical decisions.
 // diagnostics of the calling thread's last solve: matvecs, looks (status read-backs), extra full Gram-Schmidt passes,
-// restarts, matvecs that ran with fewer int8 slices than the solve's base count, failed true-residual checks
-static thread_local long long g_last_counters[6] = {0, 0, 0, 0, 0, 0};
+// restarts, matvecs that ran with fewer int8 slices than the solve's base count, failed true-residual checks, matvecs
+// with five slices
+static thread_local long long g_last_counters[7] = {0, 0, 0, 0, 0, 0, 0};
 
 static int eig_lowest_impl(const tnpy_comm* comm, const double* L, const double* W, const double* R, double* psi,
                            double* hpsi, int l, int row0, int lo, int r, int wl, int wr, int d, int flags, double tol,
@@ -422,7 +433,7 @@ static int eig_lowest_impl(const tnpy_comm* comm, const double* L, const double*
   // solve that fails it continues from psi with the schedule switched off.  TNPY_INEXACT_SLICES=0 switches it off.
   bool inexact = inexact_switch().load(std::memory_order_relaxed) != 0 && !comm && tol >= 1e-10;
   bool used_inexact = false;
-  long long n_reduced = 0, n_failed_checks = 0;
+  long long n_reduced = 0, n_five = 0, n_failed_checks = 0;
   int cur_slices = slices, last_used_slices = slices;
   double unit_bound = 0.0;  // measured bound / e_S: the scale-free part
   auto e_of = [](int S) { return (S + 2) / 4.0 * ldexp(1.0, -7 * S); };
@@ -527,6 +538,7 @@ static int eig_lowest_impl(const tnpy_comm* comm, const double* L, const double*
       if (step_slices < slices) {
         used_inexact = true;
         ++n_reduced;
+        if (step_slices == 5) ++n_five;
       }
       last_used_slices = step_slices;
     }
@@ -618,7 +630,7 @@ static int eig_lowest_impl(const tnpy_comm* comm, const double* L, const double*
     }
     if (inexact && plan.mode != HEFF_FP64_CHAIN && n_matvec >= 3 && unit_bound > 0.0 && anorm_seen > 0.0) {
       const double rel = fmin(1.0, fmax(hst[ST_RESID] / anorm_seen, tol));
-      const double allowed = 0.00125 * tol * anorm_seen / rel;
+      const double allowed = inexact_factor() * tol * anorm_seen / rel;
       int pick = slices;
       while (pick > 5 && unit_bound * e_of(pick - 1) <= allowed) --pick;
       if (pick != cur_slices) {
@@ -720,6 +732,7 @@ static int eig_lowest_impl(const tnpy_comm* comm, const double* L, const double*
   g_last_counters[2] = (long long)hst[ST_EXTRA];
   g_last_counters[3] = n_restart;
   g_last_counters[4] = n_reduced;
+  g_last_counters[6] = n_five;
   g_last_counters[5] = n_failed_checks;
   if (!done) {
     set_error("tnpy_eig_lowest: not converged after %d matvecs (resid %.3e, tol*|A| %.3e)", n_matvec, hst[ST_RESID],
@@ -764,7 +777,7 @@ extern "C" int tnpy_eig_lowest_rows(const tnpy_comm* comm, const double* L_rows,
 
 extern "C" int tnpy_last_eig_counters(int64_t* out, int n) {
   int k = 0;
-  for (; k < n && k < 6; ++k) out[k] = g_last_counters[k];
+  for (; k < n && k < 7; ++k) out[k] = g_last_counters[k];
   return k;
 }
 
