@@ -638,7 +638,7 @@ def test_ozaki_gemm_shapes_slices_and_bound(cu, m, n, k):
     b = torch.randn((k, n), generator=g, dtype=torch.float64, device="cuda")
     ref = a.t() @ b
     bound = a.abs().t() @ b.abs()
-    for s, tol in ((8, 4e-15), (7, 2e-13), (6, 3e-11)):
+    for s, tol in ((8, 4e-15), (7, 2e-13), (6, 3e-11), (5, 4e-9)):
         got = cu.ozaki_gemm_tn(a, b, slices=s)
         assert float(((got - ref).abs() / bound).max()) < tol
         rigorous = cu.ozaki_error_bound(m, n, k, slices=s)

@@ -803,14 +803,16 @@ static PFN_cuTensorMapEncodeTiled_v12000 oz_encoder() {
   return fn;
 }
 
-// slices[s][row][k]: dims (Kp, rows, kOzMaxSlices), box (kOzBK, box_rows, 4), 64B swizzle
-static int oz_make_map(CUtensorMap* map, const int8_t* base, int64_t Kp, int rows, int box_rows) {
+// slices[s][row][k]: dims (Kp, rows, nslices), box (kOzBK, box_rows, 4), 64B swizzle.  nslices = the slices the product
+// uses: the box of the second slice group then reaches past the tensor for S < 8, and TMA fills the part outside with
+// zeros without reading it -- the unused slices cost no L2 / HBM traffic (the MMAs never touch them).
+static int oz_make_map(CUtensorMap* map, const int8_t* base, int64_t Kp, int rows, int box_rows, int nslices) {
   auto enc = oz_encoder();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled not available from the driver");
     return TNPY_ECUDA;
   }
-  cuuint64_t dims[3] = {(cuuint64_t)Kp, (cuuint64_t)rows, (cuuint64_t)kOzMaxSlices};
+  cuuint64_t dims[3] = {(cuuint64_t)Kp, (cuuint64_t)rows, (cuuint64_t)nslices};
   cuuint64_t strides[2] = {(cuuint64_t)Kp, (cuuint64_t)Kp * rows};
   cuuint32_t box[3] = {(cuuint32_t)kOzBK, (cuuint32_t)box_rows, 4};
   cuuint32_t estr[3] = {1, 1, 1};
@@ -961,8 +963,8 @@ template <int S>
 static int oz2_launch(const OzOperand& A, const OzOperand& B, GemmOut out, int M, int N, int accumulate, Workspace& ws,
                       const OzKSkip& skip, cudaStream_t stream) {
   CUtensorMap tmA, tmB;
-  TNPY_TRY(oz_make_map(&tmA, A.slices, A.Kp, M, kOzBM));
-  TNPY_TRY(oz_make_map(&tmB, B.slices, B.Kp, N, kOzBN));
+  TNPY_TRY(oz_make_map(&tmA, A.slices, A.Kp, M, kOzBM, S));
+  TNPY_TRY(oz_make_map(&tmB, B.slices, B.Kp, N, kOzBN, S));
   constexpr int smem = kOz2Slots * kOz2Slot + 256 + 1024;
   TNPY_TRY(set_max_dynamic_smem(oz2_mma_kernel<S>, smem));
   const int tiles_m = ceil_div(M, 2 * kOzBM), tiles_n = ceil_div(N, kOz2TileN);
