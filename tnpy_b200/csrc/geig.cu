@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(256) geig_small_kernel(double* __restrict__ GA
   __shared__ double z[kMaxG][kMaxG + 1];  // eigenvectors
   __shared__ double cs[kMaxG], sn[kMaxG], red[72];
   __shared__ int pp[kMaxG], qq[kMaxG];
-  __shared__ int fail, lo_idx;
+  __shared__ int fail;
   const int m = j + 1, tid = threadIdx.x, nt = blockDim.x;
   if (tid < m) {
     GA[tid * kMaxG + j] = GA[j * kMaxG + tid] = ha[tid];
@@ -170,7 +170,6 @@ __global__ void __launch_bounds__(256) geig_small_kernel(double* __restrict__ GA
     int lo = 0;
     for (int i = 1; i < m; ++i)
       if (a[i][i] < a[lo][lo]) lo = i;
-    lo_idx = lo;
     status[GS_THETA] = a[lo][lo];
     status[GS_FAIL] = fail ? 1.0 : 0.0;
     // y = C^-T z_lo  (back substitution), sign: first component non-negative
